@@ -1,0 +1,152 @@
+"""Generate golden fixtures by running the UNMODIFIED reference
+(/root/reference/finetune/{losses,optimizers,config}.py) on seeded inputs.
+
+Run in the build container (the reference is not on the GPU box):
+    python tests/golden/make_golden.py
+Writes tests/golden/*.pt (inputs + reference outputs, fp32 stored; fp64 outputs
+kept as well for ill-conditioned cases).  The reference is imported, never copied.
+"""
+import os
+import sys
+import types
+
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF = "/root/reference/finetune"
+
+
+def import_reference():
+    sys.path.insert(0, REF)
+    import losses as ref_losses          # noqa: E402
+    import optimizers as ref_opt         # noqa: E402
+    sys.path.pop(0)
+    return ref_losses, ref_opt
+
+
+def cfg(thr, gw, lw, s):
+    return types.SimpleNamespace(similarity_threshold=thr, global_loss_weight=gw, local_loss_weight=lw,
+                                 inverse_temperature=s)
+
+
+def sparc_case(ref_losses, name, B, P, T, D, thr, gw, lw, s, seed, backprop="total_loss", dtype=torch.float32):
+    g = torch.Generator().manual_seed(seed)
+    v = torch.randn(B, P, D, generator=g, dtype=torch.float32)
+    l = torch.randn(B, T, D, generator=g, dtype=torch.float32)
+    mask = torch.ones(B, T, dtype=torch.bool)
+    outs = {}
+    for tag, dt in (("f32", torch.float32), ("f64", torch.float64)):
+        vv = v.detach().clone().to(dt).requires_grad_(True)
+        ll = l.detach().clone().to(dt).requires_grad_(True)
+        mod = ref_losses.SPARCLoss(cfg(thr, gw, lw, s))
+        out = mod(vv, ll, mask)
+        out[backprop].backward()
+        outs[tag] = {"losses": {k: o.detach().clone() for k, o in out.items()},
+                     "dv": vv.grad.clone(), "dl": ll.grad.clone()}
+    fix = dict(name=name, v=v, l=l, mask=mask, thr=thr, gw=gw, lw=lw, s=s, backprop=backprop, **outs)
+    torch.save(fix, os.path.join(HERE, f"sparc_{name}.pt"))
+    print("sparc", name, {k: float(x) for k, x in outs["f32"]["losses"].items()})
+
+
+def sparc_masked_case(ref_losses, name, B, P, T, D, thr, s, seed):
+    """Pins the 'truncate' mask semantics: reference run per sample on valid tokens only."""
+    sys.path.insert(0, os.path.join(HERE, "..", ".."))
+    from oracle.losses_oracle import sparc_reference_truncated
+    g = torch.Generator().manual_seed(seed)
+    v = torch.randn(B, P, D, generator=g, dtype=torch.float64)
+    l = torch.randn(B, T, D, generator=g, dtype=torch.float64)
+    lens = torch.randint(3, T + 1, (B,), generator=g)
+    lens[0] = T
+    mask = torch.arange(T)[None, :] < lens[:, None]
+    mod = ref_losses.SPARCLoss(cfg(thr, 1.0, 1.0, s))
+    vv = v.clone().requires_grad_(True)
+    ll = l.clone().requires_grad_(True)
+    vl, lv = sparc_reference_truncated(mod, vv, ll, mask)
+    # global part: the reference is finite for padded masks (losses.py:207-217)
+    full = mod(vv, ll, mask)
+    total = full["global_loss"] + 0.5 * (vl + lv)
+    total.backward()
+    dl = ll.grad.clone()
+    fix = dict(name=name, v=v.float(), l=l.float(), mask=mask, thr=thr, s=s,
+               loss_vl_local=vl.detach(), loss_lv_local=lv.detach(), global_loss=full["global_loss"].detach(),
+               loss_vl=full["loss_vl"].detach(), loss_lv=full["loss_lv"].detach(),
+               total=total.detach(), dv=vv.grad.clone(), dl=dl,
+               ref_local_is_nan=bool(torch.isnan(full["local_loss"])))
+    torch.save(fix, os.path.join(HERE, f"sparc_masked_{name}.pt"))
+    print("sparc masked", name, float(vl), float(lv), "ref local NaN:", fix["ref_local_is_nan"])
+
+
+def clip_case(ref_losses, name, B, D, temperature, seed):
+    g = torch.Generator().manual_seed(seed)
+    a = torch.randn(B, D, generator=g)
+    b = torch.randn(B, D, generator=g)
+    outs = {}
+    for tag, dt in (("f32", torch.float32), ("f64", torch.float64)):
+        aa = a.detach().clone().to(dt).requires_grad_(True)
+        bb = b.detach().clone().to(dt).requires_grad_(True)
+        out = ref_losses.CustomCLIPLoss(temperature)(aa, bb)
+        out["total_loss"].backward()
+        outs[tag] = {"clip_loss": out["clip_loss"].detach().clone(), "da": aa.grad.clone(), "db": bb.grad.clone()}
+    torch.save(dict(name=name, a=a, b=b, temperature=temperature, **outs), os.path.join(HERE, f"clip_{name}.pt"))
+    print("clip", name, float(outs["f32"]["clip_loss"]))
+
+
+def pairwise_case(ref_losses, name, B, D, s, seed):
+    """SPARCLoss.pairwise_contrastive_loss alone (losses.py:145-163)."""
+    g = torch.Generator().manual_seed(seed)
+    a = torch.randn(B, D, generator=g, dtype=torch.float64).requires_grad_(True)
+    b = torch.randn(B, D, generator=g, dtype=torch.float64).requires_grad_(True)
+    mod = ref_losses.SPARCLoss(cfg(0.5, 1.0, 1.0, s))
+    loss = mod.pairwise_contrastive_loss(a, b)
+    loss.backward()
+    torch.save(dict(name=name, a=a.detach().float(), b=b.detach().float(), s=s, loss=loss.detach(),
+                    da=a.grad.clone(), db=b.grad.clone()), os.path.join(HERE, f"pairwise_{name}.pt"))
+    print("pairwise", name, float(loss))
+
+
+def adamspd_case(ref_opt, name, sizes, steps, lr, betas, eps, wd, amsgrad, seed, with_pre=True, none_grad_idx=()):
+    g = torch.Generator().manual_seed(seed)
+    p0 = [torch.randn(*s, generator=g) * 0.02 for s in sizes]
+    pre = [p + 1e-3 * torch.randn(*p.shape, generator=g) for p in p0] if with_pre else None
+    grads = [[torch.randn(*s, generator=g) * 1e-3 for s in sizes] for _ in range(steps)]
+    params = [torch.nn.Parameter(p.clone()) for p in p0]
+    opt = ref_opt.AdamSPD([{"params": params, "pre": pre}], lr=lr, betas=betas, eps=eps, weight_decay=wd,
+                          amsgrad=amsgrad)
+    snaps = {}
+    for t in range(steps):
+        for j, p in enumerate(params):
+            p.grad = None if j in none_grad_idx and t % 2 == 1 else grads[t][j].clone()
+        opt.step()
+        if t + 1 in (1, 2, steps // 2, steps):
+            snaps[t + 1] = [p.detach().clone() for p in params]
+    state = [{k: (x.clone() if torch.is_tensor(x) else x) for k, x in opt.state[p].items() if k != "hyper"}
+             for p in params]
+    torch.save(dict(name=name, sizes=sizes, steps=steps, lr=lr, betas=betas, eps=eps, wd=wd, amsgrad=amsgrad,
+                    p0=p0, pre=pre, grads=grads, snaps=snaps, state=state, none_grad_idx=tuple(none_grad_idx)),
+               os.path.join(HERE, f"adamspd_{name}.pt"))
+    print("adamspd", name, "steps", steps, "p[0][:3]", params[0].detach().flatten()[:3].tolist())
+
+
+def main():
+    torch.manual_seed(0)
+    torch.set_num_threads(4)
+    ref_losses, ref_opt = import_reference()
+    # SPARC: thr = 1/P is well conditioned (SURVEY finding 2); one trainer-default case (thr=.5, s=.07)
+    sparc_case(ref_losses, "b4_p50_d64_thrP", 4, 50, 77, 64, 1.0 / 50, 1.0, 1.0, 1.0, seed=1)
+    sparc_case(ref_losses, "b3_p197_d32_thrP_w", 3, 197, 77, 32, 1.0 / 197, 0.7, 1.3, 2.5, seed=2)
+    sparc_case(ref_losses, "b2_p50_d64_thr05_s007", 2, 50, 77, 64, 0.5, 1.0, 1.0, 0.07, seed=3)
+    sparc_case(ref_losses, "b2_p33_t20_d48_local", 2, 33, 20, 48, 1.0 / 33, 1.0, 1.0, 3.0, seed=4,
+               backprop="loss_vl_local")
+    sparc_masked_case(ref_losses, "b4_p50_d64", 4, 50, 77, 64, 1.0 / 50, 1.5, seed=5)
+    clip_case(ref_losses, "b16_d64", 16, 64, 0.07, seed=6)
+    clip_case(ref_losses, "b5_d40_t1", 5, 40, 1.0, seed=7)
+    pairwise_case(ref_losses, "b12_d32", 12, 32, 4.0, seed=8)
+    sizes = [(1,), (7,), (33, 31), (4099,), (64, 64)]
+    adamspd_case(ref_opt, "s20", sizes, 20, 2e-5, (0.9, 0.999), 1e-8, 0.1, False, seed=9)
+    adamspd_case(ref_opt, "s12_ams_lr1e3", sizes, 12, 1e-3, (0.9, 0.98), 5e-6, 0.2, True, seed=10)
+    adamspd_case(ref_opt, "s8_nopre_nonegrad", sizes, 8, 1e-3, (0.9, 0.999), 1e-8, 0.1, False, seed=11,
+                 with_pre=False, none_grad_idx=(1, 3))
+
+
+if __name__ == "__main__":
+    main()
