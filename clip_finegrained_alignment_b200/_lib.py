@@ -1,0 +1,85 @@
+"""ctypes binding of libcfa_b200.so (C ABI declared in include/cfa_b200.h).
+
+There is no CPU or PyTorch fallback: if the shared library is missing the import fails, and
+every compute entry point raises unless it runs on a CUDA (sm_100a) device.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import torch
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "libcfa_b200.so")
+
+DTYPE_CODE = {torch.float32: 0, torch.bfloat16: 1, torch.float16: 2}
+
+
+class CfaError(RuntimeError):
+    pass
+
+
+def _load() -> C.CDLL:
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `python -m clip_finegrained_alignment_b200.build` "
+            "(nvcc, sm_100a).  This package has no CPU/PyTorch fallback.")
+    return C.CDLL(LIB_PATH)
+
+
+lib = _load()
+
+_vp, _i, _f, _sz = C.c_void_p, C.c_int, C.c_float, C.c_size_t
+
+SIGNATURES = {
+    "cfa_abi_version": (C.c_int, []),
+    "cfa_error_string": (C.c_char_p, [_i]),
+    "cfa_adamspd_chunk_elems": (C.c_int, []),
+    "cfa_adamspd_step": (C.c_int, [_vp, _i, _vp, _i, _vp, _vp, _i, _i, _vp]),
+    "cfa_rows_normalize": (C.c_int, [_vp, _i, _i, _f, _vp, _vp, _vp]),
+    "cfa_rows_normalize_bwd": (C.c_int, [_vp, _vp, _vp, _i, _sz, _i, _i, _vp, _vp]),
+    "cfa_infonce_fwd_workspace_bytes": (_sz, [_i, _i, _i]),
+    "cfa_infonce_fwd": (C.c_int, [_vp, _i, _vp, _i, _i, _i, _f, _vp, _vp, _vp, _sz, _vp]),
+    "cfa_infonce_bwd_workspace_bytes": (_sz, [_i, _i, _i, C.POINTER(C.c_int)]),
+    "cfa_infonce_bwd": (C.c_int, [_vp, _i, _vp, _i, _i, _i, _f, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "cfa_sparc_fwd": (C.c_int, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "cfa_sparc_bwd": (C.c_int, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "cfa_sparc_max_patches": (C.c_int, [_i, _i]),
+    "cfa_sum2": (C.c_int, [_vp, _vp, _i, _vp, _vp]),
+    "cfa_sparc_finalize": (C.c_int, [_vp, _i, _vp, _vp, _i, _i, _f, _f, _vp, _vp]),
+    "cfa_sparc_coef": (C.c_int, [_vp, _f, _f, _i, _vp, _vp, _vp]),
+}
+
+for _name, (_res, _args) in SIGNATURES.items():
+    _fn = getattr(lib, _name)
+    _fn.restype = _res
+    _fn.argtypes = _args
+
+
+def check(code: int, what: str) -> None:
+    if code != 0:
+        msg = lib.cfa_error_string(code)
+        raise CfaError(f"{what} failed ({code}): {msg.decode() if msg else '?'}")
+
+
+def ptr(t) -> int:
+    return 0 if t is None else t.data_ptr()
+
+
+def stream_ptr() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def require_cuda(*tensors) -> torch.device:
+    dev = None
+    for t in tensors:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise CfaError("clip_finegrained_alignment_b200 runs on CUDA (sm_100a) tensors only; there is no CPU fallback")
+        if dev is None:
+            dev = t.device
+        elif t.device != dev:
+            raise CfaError("all tensors of one call must live on the same device")
+    return dev

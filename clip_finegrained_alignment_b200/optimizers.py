@@ -1,0 +1,191 @@
+"""AdamSPD as a torch.optim.Optimizer backed by one multi-tensor sm_100a kernel pair.
+
+Drop-in for the reference's `finetune/optimizers.py:8-157`: same constructor, same validation and
+error behaviour, same param-group convention (`{'params': [...], 'pre': [...] or None}`), same
+`state_dict()` layout (`step` as a Python int, `exp_avg`, `exp_avg_sq`, unused `hyper`,
+`max_exp_avg_sq` when amsgrad).  The per-tensor Python loop with ~20 launches and one host sync per
+tensor (optimizers.py:113-152) is replaced by `cfa_adamspd_step` (include/cfa_b200.h): no host sync.
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+import torch
+from torch.optim.optimizer import Optimizer
+
+from . import _lib
+
+_TENSOR_DT = np.dtype([
+    ("p", "<u8"), ("g", "<u8"), ("m", "<u8"), ("v", "<u8"), ("pre", "<u8"), ("vmax", "<u8"), ("numel", "<i8"),
+    ("beta1", "<f4"), ("omb1", "<f4"), ("beta2", "<f4"), ("omb2", "<f4"), ("eps", "<f4"),
+    ("step_size", "<f4"), ("sqrt_bc2", "<f4"), ("wd", "<f4")])
+assert _TENSOR_DT.itemsize == 88
+
+
+class _Plan:
+    """Cached launch plan for one set of (param, state, pre) tensors: the static half of the
+    descriptor table and the chunk table live here; per step only `g` and the step scalars change."""
+
+    def __init__(self, entries, amsgrad, device):
+        n = len(entries)
+        self.n = n
+        self.key = tuple((id(p), p.data_ptr(), p.numel()) for p, _, _ in entries)
+        self.amsgrad = amsgrad
+        chunk = _lib.lib.cfa_adamspd_chunk_elems()
+        tab = np.zeros(n, dtype=_TENSOR_DT)
+        chunks = []
+        for k, (p, st, pre) in enumerate(entries):
+            tab["p"][k] = p.data_ptr()
+            tab["m"][k] = st["exp_avg"].data_ptr()
+            tab["v"][k] = st["exp_avg_sq"].data_ptr()
+            tab["pre"][k] = 0 if pre is None else pre.data_ptr()
+            tab["vmax"][k] = st["max_exp_avg_sq"].data_ptr() if amsgrad else 0
+            tab["numel"][k] = p.numel()
+            nc = (p.numel() + chunk - 1) // chunk
+            chunks.append(np.stack([np.full(nc, k, dtype=np.int32), np.arange(nc, dtype=np.int32)], axis=1))
+        self.static = tab
+        ch = np.concatenate(chunks, axis=0) if chunks else np.zeros((0, 2), np.int32)
+        self.n_chunks = int(ch.shape[0])
+        self.d_chunks = torch.from_numpy(np.ascontiguousarray(ch)).to(device)
+        # two pinned staging buffers so that refilling never races the previous step's async copy
+        self.h_tab = [torch.empty(n * _TENSOR_DT.itemsize, dtype=torch.uint8).pin_memory() for _ in range(2)]
+        self.h_np = [t.numpy().view(_TENSOR_DT) for t in self.h_tab]
+        self.h_evt = [torch.cuda.Event() for _ in range(2)]
+        self.h_used = [False, False]
+        self.flip = 0
+        self.d_tab = torch.empty(n * _TENSOR_DT.itemsize, dtype=torch.uint8, device=device)
+        self.d_reduce = torch.empty(3 * n, dtype=torch.float64, device=device)
+        self.d_stats = torch.zeros(n, 2, dtype=torch.float32, device=device)
+
+
+class AdamSPD(Optimizer):
+    """Adam with Selective Projection Decay (https://arxiv.org/abs/2411.01713), reference API."""
+
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0, amsgrad=False):
+        # validation mirrors optimizers.py:11-20
+        if not 0.0 <= lr:
+            raise ValueError("Invalid learning rate: {}".format(lr))
+        if not 0.0 <= eps:
+            raise ValueError("Invalid epsilon value: {}".format(eps))
+        if not 0.0 <= betas[0] < 1.0:
+            raise ValueError("Invalid beta parameter at index 0: {}".format(betas[0]))
+        if not 0.0 <= betas[1] < 1.0:
+            raise ValueError("Invalid beta parameter at index 1: {}".format(betas[1]))
+        if not 0.0 <= weight_decay:
+            raise ValueError("Invalid weight_decay value: {}".format(weight_decay))
+        defaults = dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, amsgrad=amsgrad)
+        super().__init__(params, defaults)
+        self._plan = None
+
+    def __setstate__(self, state):
+        super().__setstate__(state)
+        for group in self.param_groups:
+            group.setdefault("amsgrad", False)
+        self._plan = None
+
+    # ------------------------------------------------------------------
+    @property
+    def last_step_stats(self):
+        """[n_tensors, 2] device tensor of (projected?, ratio) from the most recent step, in the order
+        params-with-grad were visited.  Reading it on the host synchronises; step() itself never does."""
+        return None if self._plan is None else self._plan.d_stats
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        loss = None
+        if closure is not None:
+            with torch.enable_grad():
+                loss = closure()
+
+        entries = []      # (param, state, pre) for every param with a grad, reference visiting order
+        grads = []
+        hyper = []        # (beta1, beta2, eps, lr, wd, step) per entry
+        amsgrad_all = None
+        for group in self.param_groups:
+            beta1, beta2 = group["betas"]
+            ams = bool(group["amsgrad"])
+            have_grad = False
+            for j, p in enumerate(group["params"]):
+                g = p.grad
+                if g is None:
+                    continue
+                if g.is_sparse:
+                    raise RuntimeError("Adam does not support sparse gradients, please consider SparseAdam instead")
+                have_grad = True
+                state = self.state[p]
+                if len(state) == 0:       # lazy init, optimizers.py:61-70
+                    state["step"] = 0
+                    state["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+                    state["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+                    state["hyper"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+                    if ams:
+                        state["max_exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+                state["step"] += 1        # optimizers.py:81
+                pre_list = group["pre"]   # KeyError('pre') like the reference (optimizers.py:146)
+                pre = pre_list[j] if pre_list is not None else None
+                entries.append((p, state, pre))
+                grads.append(g)
+                hyper.append((beta1, beta2, group["eps"], group["lr"], group["weight_decay"], state["step"]))
+            if have_grad:
+                if amsgrad_all is None:
+                    amsgrad_all = ams
+                elif amsgrad_all != ams:
+                    raise _lib.CfaError("AdamSPD: mixing amsgrad and non-amsgrad groups in one optimizer is unsupported")
+        if not entries:
+            return loss
+        self._launch(entries, grads, hyper, bool(amsgrad_all))
+        return loss
+
+    # ------------------------------------------------------------------
+    def _launch(self, entries, grads, hyper, amsgrad):
+        p0 = entries[0][0]
+        dev = _lib.require_cuda(*[e[0] for e in entries], *grads, *[e[2] for e in entries])
+        for (p, st, pre), g in zip(entries, grads):
+            if p.dtype != torch.float32 or g.dtype != torch.float32:
+                raise _lib.CfaError("AdamSPD kernels are fp32 (the reference keeps fp32 master params); got "
+                                    f"{p.dtype}/{g.dtype}")
+            if not p.is_contiguous() or not st["exp_avg"].is_contiguous() or not st["exp_avg_sq"].is_contiguous():
+                raise _lib.CfaError("AdamSPD: parameters and optimizer state must be contiguous")
+            if pre is not None and (pre.shape != p.shape or not pre.is_contiguous() or pre.dtype != p.dtype
+                                    or pre.device != p.device):
+                raise _lib.CfaError("AdamSPD: group['pre'][j] must match its parameter (shape, dtype, device, contiguous)")
+        grads = [g if g.is_contiguous() else g.contiguous() for g in grads]
+
+        plan = self._plan
+        key = tuple((id(p), p.data_ptr(), p.numel()) for p, _, _ in entries)
+        if plan is None or plan.key != key or plan.amsgrad != amsgrad:
+            plan = self._plan = _Plan(entries, amsgrad, dev)
+
+        k = plan.flip
+        plan.flip ^= 1
+        if plan.h_used[k]:
+            plan.h_evt[k].synchronize()      # normally long finished: two steps ago
+        tab = plan.h_np[k]
+        tab[:] = plan.static
+        tab["g"] = np.fromiter((g.data_ptr() for g in grads), dtype=np.uint64, count=plan.n)
+        # per-step scalars: Python doubles like the reference (optimizers.py:123-124,139), rounded once to fp32
+        cache = {}
+        cols = np.empty((plan.n, 8), dtype=np.float32)
+        for i, h in enumerate(hyper):
+            row = cache.get(h)
+            if row is None:
+                beta1, beta2, eps, lr, wd, step = h
+                bc1 = 1 - beta1 ** step
+                bc2 = 1 - beta2 ** step
+                row = (beta1, 1 - beta1, beta2, 1 - beta2, eps, lr / bc1, math.sqrt(bc2), wd)
+                cache[h] = row
+            cols[i] = row
+        for c, name in enumerate(("beta1", "omb1", "beta2", "omb2", "eps", "step_size", "sqrt_bc2", "wd")):
+            tab[name] = cols[:, c]
+
+        with torch.cuda.device(dev):
+            plan.d_tab.copy_(plan.h_tab[k], non_blocking=True)
+            plan.h_evt[k].record()
+            plan.h_used[k] = True
+            rc = _lib.lib.cfa_adamspd_step(plan.d_tab.data_ptr(), plan.n, plan.d_chunks.data_ptr(), plan.n_chunks,
+                                           plan.d_reduce.data_ptr(), plan.d_stats.data_ptr(), 0, int(amsgrad),
+                                           _lib.stream_ptr())
+        _lib.check(rc, "cfa_adamspd_step")
+        self._keepalive = grads      # contiguous copies (if any) must outlive the async launch
+        del p0

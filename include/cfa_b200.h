@@ -1,0 +1,166 @@
+/*
+ * cfa_b200.h — C ABI of libcfa_b200.so: the sm_100a implementation of the contrastive-loss
+ * and optimizer hot path of tpeat/clip-finegrained-alignment.
+ *
+ * The reference has no FFI/plugin layer: its boundary for this path is three Python classes
+ * (finetune/losses.py: SPARCLoss :136-264, CustomCLIPLoss :7-36; finetune/optimizers.py: AdamSPD :8-157)
+ * whose arithmetic is torch tensor ops.  The entry points below are what a ctypes binding inside those
+ * classes calls instead of the torch ops; each one names the reference lines it replaces.
+ * INTEGRATION.md shows the reference-side stub.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name starts with h_ (host);
+ *   - tensors are dense row-major; sizes are element counts; `dtype` is one of CFA_DTYPE_*;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
+ *   - no allocation, no host synchronisation and no host read-back inside any call; scratch is
+ *     passed in and sized by the matching *_workspace_bytes query;
+ *   - return value: 0 = success, >0 = a cudaError_t, <0 = CFA_ERR_*; cfa_error_string() decodes both.
+ *   - sm_100a only.  There is no CPU fallback: without a B200 every compute call fails.
+ */
+#ifndef CFA_B200_H
+#define CFA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CFA_ABI_VERSION 1
+
+#define CFA_DTYPE_F32 0
+#define CFA_DTYPE_BF16 1
+#define CFA_DTYPE_F16 2
+
+#define CFA_OK 0
+#define CFA_ERR_BAD_ARG (-1)
+#define CFA_ERR_UNSUPPORTED (-2)
+#define CFA_ERR_WORKSPACE (-3)
+
+int cfa_abi_version(void);
+const char* cfa_error_string(int code);
+
+/* ------------------------------------------------------------------------------------------------
+ * AdamSPD multi-tensor step — replaces the per-tensor Python loop AdamSPD.adam + _ratio
+ * (finetune/optimizers.py:100-157; state handling of :31-98 stays in Python).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct cfa_adamspd_tensor {
+  void* p;            /* parameter, updated in place                     (optimizers.py:151) */
+  const void* g;      /* gradient                                        (optimizers.py:116) */
+  void* m;            /* exp_avg, updated in place                       (optimizers.py:128) */
+  void* v;            /* exp_avg_sq, updated in place                    (optimizers.py:129) */
+  const void* pre;    /* anchor group['pre'][j]; NULL = zeros            (optimizers.py:146) */
+  void* vmax;         /* max_exp_avg_sq when amsgrad, else NULL          (optimizers.py:131-135) */
+  int64_t numel;
+  float beta1, one_minus_beta1;
+  float beta2, one_minus_beta2;
+  float eps;
+  float step_size;    /* lr / (1 - beta1^t), evaluated in double on the host (optimizers.py:123,139) */
+  float sqrt_bc2;     /* sqrt(1 - beta2^t), evaluated in double on the host  (optimizers.py:124,137) */
+  float weight_decay;
+} cfa_adamspd_tensor;   /* 88 bytes, 8-byte aligned */
+
+typedef struct cfa_adamspd_chunk {
+  int32_t tensor;     /* index into the tensor table */
+  int32_t chunk;      /* chunk number inside that tensor; elements [chunk*chunk_elems, ...) */
+} cfa_adamspd_chunk;
+
+/* elements per chunk the kernels expect in the chunk table */
+int cfa_adamspd_chunk_elems(void);
+
+/*
+ * One optimizer step over every tensor in the table (two launches + one memset, no host sync):
+ *   pass 1: moments, bias-corrected update, p <- new_p, and per-tensor sums
+ *           sum g*(p-pre), sum (new_p-pre)^2, sum (p-pre)^2            (optimizers.py:128-147,155)
+ *   pass 2: for tensors with condition < 0 and ratio > 0: p <- p - wd*ratio*(p - pre)  (:148-150,154-157)
+ * d_reduce: [3*n_tensors] doubles of scratch (zeroed by the call).
+ * d_stats : optional [2*n_tensors] floats: (projected ? 1 : 0, ratio) per tensor, or NULL.
+ * amsgrad : non-zero = every tensor carries vmax (optimizers.py:131-135).
+ */
+int cfa_adamspd_step(const cfa_adamspd_tensor* d_tensors, int n_tensors,
+                     const cfa_adamspd_chunk* d_chunks, int n_chunks,
+                     double* d_reduce, float* d_stats, int dtype, int amsgrad, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Row normalisation: F.normalize(x, dim=-1, eps) and its backward
+ * (losses.py:17-18 with eps=0; :152-153, :207, :212 with eps=1e-12).
+ * ---------------------------------------------------------------------------------------------- */
+int cfa_rows_normalize(const float* x, int rows, int D, float eps, float* x_hat, float* norm, void* stream);
+/* dx = (sum over n_partials of dxh[k] - x_hat * (x_hat . sum dxh)) / norm ; partial k at dxh + k*partial_stride */
+int cfa_rows_normalize_bwd(const float* x_hat, const float* norm, const float* dxh, int n_partials,
+                           size_t partial_stride, int rows, int D, float* dx, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * InfoNCE, one direction: local rows a_hat [B,D] against global columns b_hat [Bg,D]
+ * (losses.py:155-163 and :21-28).  Row i's target is column col_offset+i.
+ * Outputs: lse[B] (log-sum-exp of row i of scale*a_hat.b_hat^T) and ce[B] = lse - logit[i, target].
+ * The B x Bg logits are never written to memory.
+ * ---------------------------------------------------------------------------------------------- */
+size_t cfa_infonce_fwd_workspace_bytes(int B, int Bg, int D);
+int cfa_infonce_fwd(const float* a_hat, int B, const float* b_hat, int Bg, int D, int col_offset, float scale,
+                    float* lse, float* ce, void* workspace, size_t workspace_bytes, void* stream);
+
+/*
+ * Gradient w.r.t. a_hat of  sum_i coef[0]*CE_a(i) + sum_j coef[1]*CE_b(j)  (both directions share the logits):
+ *   da_hat[i,:] = scale * sum_j ( coef[0]*exp(S_ij - lse_a[i]) + coef[1]*exp(S_ij - lse_b[j])
+ *                                 - (coef[0]+coef[1])*[j == col_offset+i] ) * b_hat[j,:]
+ * coef is a DEVICE pointer to 2 floats (already divided by the global batch).  lse_b has Bg entries.
+ * Result is written as n_partials partial sums [n_partials][B][D] into the workspace; the query returns
+ * n_partials via *n_partials and cfa_rows_normalize_bwd folds them.
+ */
+size_t cfa_infonce_bwd_workspace_bytes(int B, int Bg, int D, int* n_partials);
+int cfa_infonce_bwd(const float* a_hat, int B, const float* b_hat, int Bg, int D, int col_offset, float scale,
+                    const float* lse_a, const float* lse_b, const float* coef,
+                    void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * SPARC fine-grained path, one CTA per sample (losses.py:207-212 pooling and :221-252 local loss).
+ * v [B,P,D], l [B,T,D] in `dtype`; mask [B,T] bytes (torch.bool).  Masked tokens are skipped
+ * ("truncate" semantics; identical to the reference for all-True masks).
+ *   pooled_v [B,D] = mean_p v ; pooled_l [B,D] = sum_t m l / max(sum_t m, 1e-8)          (:207-212)
+ *   lse_row/lse_col [B,T]: row / column log-sum-exp of the masked T x T logits           (:180-193)
+ *   local_partial [B,2]: per-sample sum_t m_t CE for the two directions                  (:196)
+ * The T x P similarity, its min-max normalisation, threshold, renormalised weights and the grouped
+ * patch embeddings (:225-245) live only in shared memory / registers.
+ * ---------------------------------------------------------------------------------------------- */
+int cfa_sparc_fwd(const void* v, const void* l, const uint8_t* mask, int B, int P, int T, int D, int dtype,
+                  float thr, float scale, float* pooled_v, float* pooled_l, float* lse_row, float* lse_col,
+                  float* local_partial, void* stream);
+
+/*
+ * Backward of the above.  coef: DEVICE pointer to 2 floats = upstream coefficient of loss_vl_local and
+ * loss_lv_local, already divided by n_valid.  dpooled_v / dpooled_l [B,D]: gradient w.r.t. the pooled
+ * means (from the global InfoNCE), may be NULL.  dv [B,P,D], dl [B,T,D] are written in `dtype`.
+ */
+int cfa_sparc_bwd(const void* v, const void* l, const uint8_t* mask, int B, int P, int T, int D, int dtype,
+                  float thr, float scale, const float* lse_row, const float* lse_col, const float* coef,
+                  const float* dpooled_v, const float* dpooled_l, void* dv, void* dl, void* stream);
+
+/* largest P the SPARC kernels accept for a given T (shared-memory residency of the T x P tiles) */
+int cfa_sparc_max_patches(int T, int backward);
+
+/*
+ * Scalar epilogue (losses.py:163,196,217,252-264): sums the per-row / per-sample partials and writes
+ * out[0..6] = global_loss, local_loss, total_loss, loss_vl, loss_lv, loss_vl_local, loss_lv_local and
+ * out[7] = n_valid (sum of mask).  global_sums: DEVICE [2] = sum_i CE_vl(i), sum_j CE_lv(j) over the GLOBAL
+ * batch (after the cross-rank all-reduce when distributed); cfa_sum2 produces the local part.
+ */
+int cfa_sum2(const float* x0, const float* x1, int n, float* out2, void* stream);
+int cfa_sparc_finalize(const float* global_sums, int global_batch, const float* local_partial,
+                       const uint8_t* mask, int B, int T, float gw, float lw, float* out8, void* stream);
+
+/*
+ * Upstream gradient of the 7 outputs -> kernel coefficients (device side, no sync).
+ * grad7: DEVICE [7] floats, d(loss)/d(out[k]) in the out[] order above (the autograd gradient of the out vector).
+ * coef8 = { c_vl/Bg, c_lv/Bg, c_vl_local/n_valid, c_lv_local/n_valid, c_lv/Bg, c_vl/Bg, 0, 0 } where
+ *   c_vl = g[loss_vl] + (g[global] + gw*g[total])/2, c_vl_local = g[loss_vl_local] + (g[local] + lw*g[total])/2, ...
+ * (coef8+0 feeds the image-direction InfoNCE backward, coef8+4 the text-direction one, coef8+2 cfa_sparc_bwd).
+ */
+int cfa_sparc_coef(const float* grad7, float gw, float lw, int global_batch, const float* out8, float* coef8,
+                   void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CFA_B200_H */
