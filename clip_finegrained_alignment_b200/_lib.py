@@ -57,6 +57,30 @@ for _name, (_res, _args) in SIGNATURES.items():
     _fn.argtypes = _args
 
 
+# kernels launched per C-ABI call (cudaMemsetAsync not counted); bench.py reports the running total
+LAUNCHES = {"cfa_adamspd_step": 2, "cfa_rows_normalize": 1, "cfa_rows_normalize_bwd": 1, "cfa_infonce_fwd": 2,
+            "cfa_infonce_bwd": 1, "cfa_sparc_fwd": 1, "cfa_sparc_bwd": 1, "cfa_sum2": 1, "cfa_sparc_finalize": 1,
+            "cfa_sparc_coef": 1}
+launch_count = 0
+kernel_events = None       # {abi name: [(start_event, end_event), ...]} while bench.py profiles; else None
+
+
+def call(name: str, *args) -> None:
+    """Invoke a C-ABI entry point on the current stream, raising CfaError on a non-zero status."""
+    global launch_count
+    ev = kernel_events.get(name) if kernel_events is not None else None
+    if ev is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = getattr(lib, name)(*args)
+        e1.record()
+        ev.append((e0, e1))
+    else:
+        rc = getattr(lib, name)(*args)
+    launch_count += LAUNCHES.get(name, 0)
+    check(rc, name)
+
+
 def check(code: int, what: str) -> None:
     if code != 0:
         msg = lib.cfa_error_string(code)

@@ -38,8 +38,8 @@ _NORM_EPS = 1e-12
 def _rows_normalize(x: torch.Tensor, eps: float):
     xh = torch.empty_like(x)
     n = torch.empty(x.shape[0], dtype=torch.float32, device=x.device)
-    _lib.check(_L.cfa_rows_normalize(x.data_ptr(), x.shape[0], x.shape[1], eps, xh.data_ptr(), n.data_ptr(),
-                                     _lib.stream_ptr()), "cfa_rows_normalize")
+    _lib.call("cfa_rows_normalize", x.data_ptr(), x.shape[0], x.shape[1], eps, xh.data_ptr(), n.data_ptr(),
+                                     _lib.stream_ptr())
     return xh, n
 
 
@@ -50,8 +50,8 @@ def _infonce_fwd(a_hat: torch.Tensor, b_hat_all: torch.Tensor, col_offset: int, 
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=a_hat.device)
     lse = torch.empty(B, dtype=torch.float32, device=a_hat.device)
     ce = torch.empty(B, dtype=torch.float32, device=a_hat.device)
-    _lib.check(_L.cfa_infonce_fwd(a_hat.data_ptr(), B, b_hat_all.data_ptr(), Bg, D, col_offset, scale, lse.data_ptr(),
-                                  ce.data_ptr(), ws.data_ptr(), ws_bytes, _lib.stream_ptr()), "cfa_infonce_fwd")
+    _lib.call("cfa_infonce_fwd", a_hat.data_ptr(), B, b_hat_all.data_ptr(), Bg, D, col_offset, scale, lse.data_ptr(),
+                                  ce.data_ptr(), ws.data_ptr(), ws_bytes, _lib.stream_ptr())
     return lse, ce
 
 
@@ -63,18 +63,17 @@ def _infonce_bwd(a_hat, a_norm, b_hat_all, col_offset, scale, lse_a, lse_b_all, 
     npart = ctypes.c_int(0)
     ws_bytes = _L.cfa_infonce_bwd_workspace_bytes(B, Bg, D, ctypes.byref(npart))
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=a_hat.device)
-    _lib.check(_L.cfa_infonce_bwd(a_hat.data_ptr(), B, b_hat_all.data_ptr(), Bg, D, col_offset, scale, lse_a.data_ptr(),
-                                  lse_b_all.data_ptr(), coef.data_ptr(), ws.data_ptr(), ws_bytes, _lib.stream_ptr()),
-               "cfa_infonce_bwd")
+    _lib.call("cfa_infonce_bwd", a_hat.data_ptr(), B, b_hat_all.data_ptr(), Bg, D, col_offset, scale, lse_a.data_ptr(),
+                                  lse_b_all.data_ptr(), coef.data_ptr(), ws.data_ptr(), ws_bytes, _lib.stream_ptr())
     da = torch.empty_like(a_hat)
-    _lib.check(_L.cfa_rows_normalize_bwd(a_hat.data_ptr(), a_norm.data_ptr(), ws.data_ptr(), npart.value, B * D, B, D,
-                                         da.data_ptr(), _lib.stream_ptr()), "cfa_rows_normalize_bwd")
+    _lib.call("cfa_rows_normalize_bwd", a_hat.data_ptr(), a_norm.data_ptr(), ws.data_ptr(), npart.value, B * D, B, D,
+                                         da.data_ptr(), _lib.stream_ptr())
     return da
 
 
 def _sum2(x0, x1):
     out = torch.empty(2, dtype=torch.float32, device=x0.device)
-    _lib.check(_L.cfa_sum2(x0.data_ptr(), x1.data_ptr(), x0.numel(), out.data_ptr(), _lib.stream_ptr()), "cfa_sum2")
+    _lib.call("cfa_sum2", x0.data_ptr(), x1.data_ptr(), x0.numel(), out.data_ptr(), _lib.stream_ptr())
     return out
 
 
@@ -164,14 +163,14 @@ class _SparcFunction(torch.autograd.Function):
         lse_c = torch.empty(B, T, **f32)
         part = torch.empty(B, 2, **f32)
         with torch.cuda.device(dev):
-            _lib.check(_L.cfa_sparc_fwd(v.data_ptr(), l.data_ptr(), mask_u8.data_ptr(), B, P, T, D, code, thr, scale,
+            _lib.call("cfa_sparc_fwd", v.data_ptr(), l.data_ptr(), mask_u8.data_ptr(), B, P, T, D, code, thr, scale,
                                         pooled_v.data_ptr(), pooled_l.data_ptr(), lse_r.data_ptr(), lse_c.data_ptr(),
-                                        part.data_ptr(), _lib.stream_ptr()), "cfa_sparc_fwd")
+                                        part.data_ptr(), _lib.stream_ptr())
             world, rank, group = _dist_ctx(group, gather)
             gst, sums = _global_forward(pooled_v, pooled_l, scale, _NORM_EPS, world, rank, group)
             out8 = torch.empty(8, **f32)
-            _lib.check(_L.cfa_sparc_finalize(sums.data_ptr(), gst.Bg, part.data_ptr(), mask_u8.data_ptr(), B, T, gw, lw,
-                                             out8.data_ptr(), _lib.stream_ptr()), "cfa_sparc_finalize")
+            _lib.call("cfa_sparc_finalize", sums.data_ptr(), gst.Bg, part.data_ptr(), mask_u8.data_ptr(), B, T, gw, lw,
+                                             out8.data_ptr(), _lib.stream_ptr())
         ctx.save_for_backward(v, l, mask_u8, lse_r, lse_c, out8)
         ctx.gst = gst
         ctx.hp = (thr, gw, lw, scale, code)
@@ -188,15 +187,14 @@ class _SparcFunction(torch.autograd.Function):
         grad7 = grad7.to(torch.float32).contiguous()
         with torch.cuda.device(dev):
             coef = torch.empty(8, dtype=torch.float32, device=dev)
-            _lib.check(_L.cfa_sparc_coef(grad7.data_ptr(), gw, lw, gst.Bg, out8.data_ptr(), coef.data_ptr(),
-                                         _lib.stream_ptr()), "cfa_sparc_coef")
+            _lib.call("cfa_sparc_coef", grad7.data_ptr(), gw, lw, gst.Bg, out8.data_ptr(), coef.data_ptr(),
+                                         _lib.stream_ptr())
             dpv, dpl = _global_backward(gst, coef[0:2], coef[4:6])
             dv = torch.empty_like(v)
             dl = torch.empty_like(l)
-            _lib.check(_L.cfa_sparc_bwd(v.data_ptr(), l.data_ptr(), mask_u8.data_ptr(), B, P, T, D, code, thr, scale,
+            _lib.call("cfa_sparc_bwd", v.data_ptr(), l.data_ptr(), mask_u8.data_ptr(), B, P, T, D, code, thr, scale,
                                         lse_r.data_ptr(), lse_c.data_ptr(), coef[2:4].data_ptr(), dpv.data_ptr(),
-                                        dpl.data_ptr(), dv.data_ptr(), dl.data_ptr(), _lib.stream_ptr()),
-                       "cfa_sparc_bwd")
+                                        dpl.data_ptr(), dv.data_ptr(), dl.data_ptr(), _lib.stream_ptr())
         return dv, dl, None, None, None, None, None, None, None
 
 

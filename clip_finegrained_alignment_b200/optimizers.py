@@ -183,9 +183,7 @@ class AdamSPD(Optimizer):
             plan.d_tab.copy_(plan.h_tab[k], non_blocking=True)
             plan.h_evt[k].record()
             plan.h_used[k] = True
-            rc = _lib.lib.cfa_adamspd_step(plan.d_tab.data_ptr(), plan.n, plan.d_chunks.data_ptr(), plan.n_chunks,
-                                           plan.d_reduce.data_ptr(), plan.d_stats.data_ptr(), 0, int(amsgrad),
-                                           _lib.stream_ptr())
-        _lib.check(rc, "cfa_adamspd_step")
+            _lib.call("cfa_adamspd_step", plan.d_tab.data_ptr(), plan.n, plan.d_chunks.data_ptr(), plan.n_chunks,
+                      plan.d_reduce.data_ptr(), plan.d_stats.data_ptr(), 0, int(amsgrad), _lib.stream_ptr())
         self._keepalive = grads      # contiguous copies (if any) must outlive the async launch
         del p0
