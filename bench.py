@@ -1,0 +1,407 @@
+"""bench.py — SPARC + global InfoNCE fwd+bwd pairs/s (BASELINE.json metric) and AdamSPD step GB/s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--batch B]
+
+A "step" is one pass of the hot path over one batch of synthetic CLIP-shaped embeddings:
+SPARCLoss forward (fine-grained + global InfoNCE) and backward to dv, dl — through the package's
+public API, which calls the sm_100a kernels over the C ABI.  Workload = BASELINE config 2
+(ViT-B/16: B=256/GPU, P=196, T=77, D=512, bf16, thr=1/P, s=1, all-True mask, seed 42+rank); with
+N > 1 the global InfoNCE all-gathers the pooled embeddings over NCCL (weak scaling, fixed B/GPU).
+Prints ONE JSON line (rank 0).  `--impl reference` times the CPU implementation of the same path
+(the unmodified reference when /root/reference is mounted, else the oracle port) on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+import types
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+P, T, D = 196, 77, 512
+L2_BYTES = 126 * 2 ** 20
+METRIC = "sparc_infonce_fwd_bwd_pairs_per_s"
+UNIT = "pairs/s"
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sus=d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                    src="measured (MEASURED_PEAKS.json)")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sus=1400.0, src="fallback (B200_PROFILING.md)")
+
+
+def cfg(thr, s=1.0):
+    return types.SimpleNamespace(similarity_threshold=thr, global_loss_weight=1.0, local_loss_weight=1.0,
+                                 inverse_temperature=s)
+
+
+def flops_per_pair(Bg):
+    """Algorithmic FLOPs per pair fwd+bwd: 12 T P D + 6 T^2 D + 6 Bg D."""
+    return 12 * T * P * D + 6 * T * T * D + 6 * Bg * D
+
+
+# --------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(index)], stdout=subprocess.PIPE, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, val in zip(names, f[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# --------------------------------------------------------------------------------------------
+def vit_l14_clip_shapes():
+    """Parameter tensor shapes of HF CLIP ViT-L/14 (590 tensors, 427 616 513 elements)."""
+    def tower(hidden, mlp, layers):
+        s = []
+        for _ in range(layers):
+            s += [(hidden, hidden), (hidden,)] * 4            # k, v, q, out projections + biases
+            s += [(hidden,), (hidden,)] * 2                   # layer_norm1/2 weight + bias
+            s += [(mlp, hidden), (mlp,), (hidden, mlp), (hidden,)]
+        return s
+    text = [(49408, 768), (77, 768)] + tower(768, 3072, 12) + [(768,), (768,)]
+    vision = [(1024,), (1024, 3, 14, 14), (257, 1024), (1024,), (1024,)] + tower(1024, 4096, 24) + [(1024,), (1024,)]
+    shapes = [(1,)] + text + vision + [(768, 1024), (768, 768)]
+    n = sum(int(torch.Size(s).numel()) for s in shapes)
+    assert len(shapes) == 590 and n == 427616513, (len(shapes), n)
+    return shapes
+
+
+def bench_adamspd(dev, steps, warmup, pk):
+    """AdamSPD full-model step on the ViT-L/14 CLIP tensor list (BASELINE config 5), fp32, random grads."""
+    from clip_finegrained_alignment_b200 import AdamSPD, _lib
+    shapes = vit_l14_clip_shapes()
+    g = torch.Generator(device=dev).manual_seed(7)
+    params = [torch.nn.Parameter(torch.randn(*s, device=dev, generator=g) * 0.02) for s in shapes]
+    pre = [p.detach() + 1e-3 * torch.randn(*p.shape, device=dev, generator=g) for p in params]
+    for p in params:
+        p.grad = torch.randn(*p.shape, device=dev, generator=g) * 1e-3
+    opt = AdamSPD([{"params": params, "pre": pre}], lr=2e-5, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.1)
+    n_elts = sum(p.numel() for p in params)
+    numel = torch.tensor([p.numel() for p in params], dtype=torch.float64)
+
+    def regrad():
+        for p in params:                      # fresh random grads each step so both SPD branches occur
+            p.grad.normal_(0.0, 1e-3, generator=g)
+
+    for _ in range(warmup):
+        regrad(); opt.step()
+    torch.cuda.synchronize(dev)
+    times, bytes_total = [], 0.0
+    l0 = _lib.launch_count
+    for _ in range(steps):
+        regrad()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); opt.step(); e1.record()
+        torch.cuda.synchronize(dev)
+        times.append(e0.elapsed_time(e1))
+        st = opt.last_step_stats.cpu().double()
+        proj = (st[:, 0] > 0) & (st[:, 1] > 0)
+        bytes_total += 32.0 * n_elts + 12.0 * float(numel[proj].sum())
+    launches = _lib.launch_count - l0
+    ms = sum(times) / len(times)
+    gbs = bytes_total / len(times) / (ms * 1e-3) / 1e9
+    # comparator: torch fused AdamW on the same tensors (28 B/elt)
+    cmp_ms = None
+    try:
+        ref_params = [torch.nn.Parameter(p.detach().clone()) for p in params]
+        for q, p in zip(ref_params, params):
+            q.grad = p.grad
+        ref = torch.optim.AdamW(ref_params, lr=2e-5, weight_decay=0.1, fused=True)
+        for _ in range(2):
+            ref.step()
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(3):
+            ref.step()
+        e1.record(); torch.cuda.synchronize(dev)
+        cmp_ms = e0.elapsed_time(e1) / 3
+        del ref, ref_params
+    except Exception:
+        pass
+    out = {"metric": "adamspd_step_hbm_gbs", "value": round(gbs, 1), "unit": "GB/s", "ms_per_step": round(ms, 4),
+           "workload": "ViT-L/14 CLIP, 590 fp32 tensors, 427616513 params, random grads, lr 2e-5, wd 0.1",
+           "algorithmic_bytes_per_step": bytes_total / len(times), "gpu_launches_per_step": launches // max(1, steps),
+           "roofline": {"bound": "hbm", "achieved": round(gbs, 1), "peak": pk["hbm"], "unit": "GB/s",
+                        "frac": round(gbs / pk["hbm"], 4), "traffic": None, "peak_source": pk["src"]},
+           "torch_fused_adamw_ms": None if cmp_ms is None else round(cmp_ms, 4)}
+    del opt, params, pre
+    torch.cuda.empty_cache()
+    return out
+
+
+# --------------------------------------------------------------------------------------------
+def make_cpu_runner(B):
+    """The reference's CPU implementation of the path on a bounded sample: B pairs of the workload's shapes,
+    fp32, all host threads.  Uses the unmodified reference when /root/reference is mounted (build container),
+    else the oracle port (GPU box)."""
+    torch.set_num_threads(os.cpu_count() or 1)
+    g = torch.Generator().manual_seed(42)
+    v = torch.randn(B, P, D, generator=g)
+    l = torch.randn(B, T, D, generator=g)
+    m = torch.ones(B, T, dtype=torch.bool)
+    thr = 1.0 / P
+    ref_dir = "/root/reference/finetune"
+    kind = "port"
+    if os.path.isdir(ref_dir):
+        sys.path.insert(0, ref_dir)
+        try:
+            import losses as ref_losses
+            kind = "reference"
+        except Exception:
+            kind = "port"
+        finally:
+            sys.path.pop(0)
+    if kind == "reference":
+        mod = ref_losses.SPARCLoss(cfg(thr))
+
+        def run():
+            vv = v.clone().requires_grad_(True)
+            ll = l.clone().requires_grad_(True)
+            mod(vv, ll, m)["total_loss"].backward()
+    else:
+        from oracle import losses_oracle as lo          # cpu_baseline leg: the checker, timed as the baseline
+
+        def run():
+            with torch.no_grad():
+                lo.sparc_backward(lo.sparc_forward(v, l, m, thr, 1.0, 1.0, 1.0))
+    what = "unmodified reference losses.py (autograd)" if kind == "reference" else "oracle/losses_oracle.py port"
+    sample = f"{B} pairs per step of the same shapes (P={P}, T={T}, D={D}), fp32, {what}"
+    return run, kind, torch.get_num_threads(), sample
+
+
+def cpu_baseline(B=32, budget_s=12.0):
+    run, kind, cores, sample = make_cpu_runner(B)
+    run()
+    ts, t_start = [], time.perf_counter()
+    while len(ts) < 3 or (time.perf_counter() - t_start < budget_s and len(ts) < 10):
+        t0 = time.perf_counter(); run(); ts.append(time.perf_counter() - t0)
+    return {"value": round(B / min(ts), 1), "unit": UNIT, "cores": cores, "kind": kind,
+            "sample": sample + f", best of {len(ts)}"}
+
+
+def run_reference_arm(args, rank):
+    """--impl reference: the reference's own CPU implementation of the path, all host threads, rank 0 only."""
+    if rank != 0:
+        return
+    B = 64
+    run, kind, cores, sample = make_cpu_runner(B)
+    for _ in range(args.warmup):
+        run()
+    ts = []
+    t_start = time.perf_counter()
+    for _ in range(args.steps):
+        t0 = time.perf_counter(); run(); ts.append(time.perf_counter() - t0)
+        if time.perf_counter() - t_start > 240:
+            break
+    sec = sum(ts) / len(ts)
+    val = B / sec
+    line = {"impl": "reference", "metric": METRIC, "value": round(val, 1), "unit": UNIT, "n_gpus": args.gpus,
+            "steps": len(ts), "warmup": args.warmup, "ms_per_step": round(sec * 1e3, 3), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"BASELINE config 2 shapes (ViT-B/16 SPARC + global InfoNCE fwd+bwd, P={P}, T={T}, "
+                                   f"D={D}, thr=1/P, s=1), CPU, bounded sample of {B} pairs per step"},
+            "cpu_baseline": {"value": round(val, 1), "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+            "e2e": {"value": round(val, 1), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=256, help="pairs per GPU (BASELINE config 2: 256)")
+    ap.add_argument("--dtype", default="bf16", choices=["bf16", "f32", "f16"])
+    ap.add_argument("--no-adamspd", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference_arm(args, rank)
+        return
+
+    assert torch.cuda.is_available(), "bench.py needs a B200 (there is no CPU fallback)"
+    args.warmup = max(args.warmup, 3)
+    import torch.distributed as dist
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    from clip_finegrained_alignment_b200 import SPARCLoss, _lib
+    pk = peaks()
+    dt = {"bf16": torch.bfloat16, "f32": torch.float32, "f16": torch.float16}[args.dtype]
+    B = args.batch
+    Bg = B * world
+    torch.manual_seed(42 + rank)
+    in_bytes = B * (P + T) * D * torch.empty(0, dtype=dt).element_size()
+    nbuf = max(2, -(-2 * L2_BYTES // in_bytes))            # rotate input sets: working set > 2 x L2
+    vs = [torch.randn(B, P, D, device=dev).to(dt).requires_grad_(True) for _ in range(nbuf)]
+    ls = [torch.randn(B, T, D, device=dev).to(dt).requires_grad_(True) for _ in range(nbuf)]
+    mask = torch.ones(B, T, dtype=torch.bool, device=dev)
+    crit = SPARCLoss(cfg(1.0 / P), gather=world > 1)
+
+    def step(i):
+        v, l = vs[i % nbuf], ls[i % nbuf]
+        v.grad = None; l.grad = None
+        out = crit(v, l, mask)
+        out["total_loss"].backward()
+        return out["total_loss"]
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for i in range(args.warmup):
+        step(i)
+    sync_all()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    _lib.kernel_events = {"cfa_sparc_bwd": [], "cfa_sparc_fwd": []}
+    l0 = _lib.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        step(args.warmup + i)
+    e1.record()
+    sync_all()
+    launches = _lib.launch_count - l0
+    ms_total = e0.elapsed_time(e1)
+    kev = _lib.kernel_events
+    _lib.kernel_events = None
+    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    ms_step = ms_total / args.steps
+    value = Bg * args.steps / (ms_total * 1e-3)
+    bwd_ms = statistics.mean(a.elapsed_time(b) for a, b in kev["cfa_sparc_bwd"])
+    fwd_ms = statistics.mean(a.elapsed_time(b) for a, b in kev["cfa_sparc_fwd"])
+
+    # ---- end to end through the public API with HOST buffers (pinned), H2D + loss read-back inside the timing
+    hv = torch.randn(B, P, D).to(dt).pin_memory()
+    hl = torch.randn(B, T, D).to(dt).pin_memory()
+    hm = torch.ones(B, T, dtype=torch.bool).pin_memory()
+    dv_ = torch.empty(B, P, D, dtype=dt, device=dev)
+    dl_ = torch.empty(B, T, D, dtype=dt, device=dev)
+    dm_ = torch.empty(B, T, dtype=torch.bool, device=dev)
+
+    def e2e_step():
+        dv_.copy_(hv, non_blocking=True); dl_.copy_(hl, non_blocking=True); dm_.copy_(hm, non_blocking=True)
+        v = dv_.detach().requires_grad_(True); l = dl_.detach().requires_grad_(True)
+        out = crit(v, l, dm_)
+        out["total_loss"].backward()
+        return float(out["total_loss"].item())            # D2H read of the step's result
+
+    for _ in range(3):
+        e2e_step()
+    sync_all()
+    e2e_steps = max(5, min(args.steps, 20))
+    t0 = time.perf_counter()
+    e0.record()
+    for _ in range(e2e_steps):
+        e2e_step()
+    e1.record()
+    sync_all()
+    e2e_ms = e0.elapsed_time(e1)
+    t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_val = Bg * e2e_steps / (float(t.item()) * 1e-3)
+    clocks = sampler.stop() if sampler else None
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # roofline of the dominant kernel (cfa_sparc_bwd): algorithmic backward FLOPs of the fine-grained part per launch
+    bwd_flops = B * (8 * T * P * D + 4 * T * T * D)
+    ach = bwd_flops / (bwd_ms * 1e-3) / 1e12
+    line = {
+        "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": round(ms_step, 4), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+        "config": {"workload": f"BASELINE config 2: ViT-B/16 SPARC + global InfoNCE fwd+bwd, B={B}/GPU, P={P}, T={T}, "
+                               f"D={D}, thr=1/P, s=1, all-True mask" + (", all-gathered global InfoNCE" if world > 1 else ""),
+                   "global_batch": Bg, "l2": f"inputs rotated over {nbuf} sets ({nbuf * in_bytes >> 20} MiB > 2x L2)",
+                   "algorithmic_flops_per_pair": flops_per_pair(Bg),
+                   "algorithmic_tflops": round(value * flops_per_pair(Bg) / 1e12, 2),
+                   "kernel_ms": {"cfa_sparc_fwd": round(fwd_ms, 4), "cfa_sparc_bwd": round(bwd_ms, 4)}},
+        "roofline": {"bound": "tensor", "kernel": "cfa_sparc_bwd", "achieved": round(ach, 2), "peak": pk["tf_sus"],
+                     "unit": "TFLOP/s", "frac": round(ach / pk["tf_sus"], 5), "traffic": None,
+                     "peak_source": pk["src"] + ", sustained bf16 GEMM", "algorithmic_flops_per_launch": bwd_flops},
+        "e2e": {"value": round(e2e_val, 1), "unit": UNIT,
+                "h2d_bytes_per_step": int(hv.numel() * hv.element_size() + hl.numel() * hl.element_size() + hm.numel()),
+                "d2h_bytes_per_step": 4, "steps": e2e_steps},
+        "gpu_launches": launches, "clocks": clocks,
+    }
+    del vs, ls
+    torch.cuda.empty_cache()
+    if not args.no_adamspd:
+        line["adamspd"] = bench_adamspd(dev, max(3, min(args.steps, 10)), 3, pk)
+    if world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline(32)
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
