@@ -49,6 +49,7 @@ SIGNATURES = {
     "cfa_sum2": (C.c_int, [_vp, _vp, _i, _vp, _vp]),
     "cfa_sparc_finalize": (C.c_int, [_vp, _i, _vp, _vp, _i, _i, _f, _f, _vp, _vp]),
     "cfa_sparc_coef": (C.c_int, [_vp, _f, _f, _i, _vp, _vp, _vp]),
+    "cfa_tc_selftest": (C.c_int, [_i, _i, _i, _i, _vp, _vp, _vp, _vp]),
 }
 
 for _name, (_res, _args) in SIGNATURES.items():

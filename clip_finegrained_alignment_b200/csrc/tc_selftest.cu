@@ -1,0 +1,111 @@
+// tcgen05 / TMA self-test: one CTA computes D[128 x N] = A . B with every operand flavour the SPARC
+// tensor-core kernels use (TMA-written SWIZZLE_128B tiles read K-major or MN-major, thread-written
+// interleaved tiles read K-major or MN-major).  tests/test_gpu_tc.py checks each mode against torch.
+#include "tc_common.cuh"
+
+namespace cfa {
+using namespace tc;
+typedef __nv_bfloat16 bf16;
+
+__global__ void __launch_bounds__(128, 1)
+tc_selftest_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                   const bf16* __restrict__ A, const bf16* __restrict__ B, float* __restrict__ D, int a_mode,
+                   int b_mode, int N, int K) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* base = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* As = base;                 // 64 KB
+  uint8_t* Bs = base + 65536;         // 64 KB
+  __shared__ uint64_t bar_tma, bar_mma;
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5;
+
+  if (tid == 0) {
+    mbar_init(&bar_tma, 1);
+    mbar_init(&bar_mma, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc(&tmem_base_s, 256);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+
+  // ---- stage operands
+  uint32_t tx_bytes = 0;
+  if (a_mode == 0) tx_bytes += (K / 64) * 16384;
+  if (b_mode == 0) tx_bytes += (K / 64) * N * 128;
+  if (b_mode == 1) tx_bytes += K * 128;
+  if (tid == 0 && tx_bytes) {
+    mbar_expect_tx(&bar_tma, tx_bytes);
+    if (a_mode == 0) for (int kb = 0; kb < K / 64; ++kb) tma_load_3d(As + kb * 16384, &tmA, &bar_tma, kb * 64, 0, 0);
+    if (b_mode == 0) for (int kb = 0; kb < K / 64; ++kb) tma_load_3d(Bs + kb * N * 128, &tmB, &bar_tma, kb * 64, 0, 0);
+    if (b_mode == 1) tma_load_3d(Bs, &tmB, &bar_tma, 0, 0, 0);
+  }
+  if (a_mode == 1) {          // A [128 x K] -> interleaved, rows = 128
+    for (int i = tid; i < 128 * K; i += 128) { const int r = i / K, k = i % K; *(bf16*)(As + il_offset(128, r, k)) = A[i]; }
+  } else if (a_mode == 2) {   // At [K x 128] -> interleaved with "rows" = K (k plays the row role)
+    for (int i = tid; i < K * 128; i += 128) { const int k = i / 128, m = i % 128; *(bf16*)(As + il_offset(K, k, m)) = A[i]; }
+  }
+  if (b_mode == 2) {          // B [N x K] -> interleaved, rows = N
+    for (int i = tid; i < N * K; i += 128) { const int r = i / K, k = i % K; *(bf16*)(Bs + il_offset(N, r, k)) = B[i]; }
+  } else if (b_mode == 3) {   // Bt [K x N] -> interleaved with "rows" = K
+    for (int i = tid; i < K * N; i += 128) { const int k = i / N, n = i % N; *(bf16*)(Bs + il_offset(K, k, n)) = B[i]; }
+  }
+  fence_proxy_async();        // generic-proxy smem writes -> visible to the tensor core (async proxy)
+  __syncthreads();
+  if (tx_bytes) mbar_wait(&bar_tma, 0);
+  tc_fence_after();
+
+  // ---- issue
+  if (tid == 0) {
+    const uint32_t idesc = make_idesc_bf16(128, N, a_mode == 2, b_mode == 1 || b_mode == 3);
+    for (int ks = 0; ks < K / 16; ++ks) {
+      uint64_t da, db;
+      if (a_mode == 0) da = make_smem_desc(smem_u32(As) + (ks >> 2) * 16384 + (ks & 3) * 32, 16, 1024, kLayoutSw128);
+      else if (a_mode == 1) da = make_smem_desc(smem_u32(As) + ks * 2 * (128 * 16), 128 * 16, 128, kLayoutNone);
+      else da = make_smem_desc(smem_u32(As) + ks * 256, 128, K * 16, kLayoutNone);
+      if (b_mode == 0) db = make_smem_desc(smem_u32(Bs) + (ks >> 2) * N * 128 + (ks & 3) * 32, 16, 1024, kLayoutSw128);
+      else if (b_mode == 1) db = make_smem_desc(smem_u32(Bs) + ks * 2048, 16, 1024, kLayoutSw128);
+      else if (b_mode == 2) db = make_smem_desc(smem_u32(Bs) + ks * 2 * (N * 16), N * 16, 128, kLayoutNone);
+      else db = make_smem_desc(smem_u32(Bs) + ks * 256, 128, K * 16, kLayoutNone);
+      umma_ss(tmem, da, db, idesc, ks > 0);
+    }
+    umma_commit(&bar_mma);
+  }
+  mbar_wait(&bar_mma, 0);
+  tc_fence_after();
+
+  // ---- read back: warp w owns TMEM lanes 32w .. 32w+31
+  const int row = tid;
+  for (int c0 = 0; c0 < N; c0 += 16) {
+    float r[16];
+    tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + c0, r);
+    tmem_ld_wait();
+    for (int j = 0; j < 16; ++j) D[row * N + c0 + j] = r[j];
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 256);
+}
+
+}  // namespace cfa
+
+using namespace cfa;
+
+// Debug / validation entry point (not part of the product surface; declared in include/cfa_b200.h).
+extern "C" int cfa_tc_selftest(int a_mode, int b_mode, int N, int K, const void* A, const void* B, float* D, void* stream) {
+  if (N % 16 || N < 16 || N > 256 || K % 16 || K < 16 || K > 256) return CFA_ERR_BAD_ARG;
+  if ((a_mode == 0 || b_mode == 0) && K % 64) return CFA_ERR_BAD_ARG;
+  if (b_mode == 1 && N != 64) return CFA_ERR_BAD_ARG;
+  CUtensorMap tmA, tmB;
+  memset(&tmA, 0, sizeof(tmA));
+  memset(&tmB, 0, sizeof(tmB));
+  int rc;
+  if (a_mode == 0 && (rc = make_tmap_bf16_3d(&tmA, A, K, 128, 1, 64, 128)) != CFA_OK) return rc;
+  if (b_mode == 0 && (rc = make_tmap_bf16_3d(&tmB, B, K, N, 1, 64, N)) != CFA_OK) return rc;
+  if (b_mode == 1 && (rc = make_tmap_bf16_3d(&tmB, B, 64, K, 1, 64, K)) != CFA_OK) return rc;
+  const size_t smem = 2 * 65536 + 1024;
+  CFA_CUDA_TRY(cudaFuncSetAttribute(tc_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  tc_selftest_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(tmA, tmB, (const bf16*)A, (const bf16*)B, D, a_mode, b_mode, N, K);
+  return launch_status();
+}

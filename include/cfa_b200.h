@@ -160,6 +160,15 @@ int cfa_sparc_finalize(const float* global_sums, int global_batch, const float* 
 int cfa_sparc_coef(const float* grad7, float gw, float lw, int global_batch, const float* out8, float* coef8,
                    void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Validation hook (not a reference replacement): one CTA computes D[128 x N] = A . B on the tcgen05 tensor
+ * cores with the operand flavours the tensor-core kernels use.  a_mode: 0 = A[128,K] via TMA (SWIZZLE_128B,
+ * K-major), 1 = A[128,K] thread-written interleaved K-major, 2 = A^T[K,128] interleaved read MN-major.
+ * b_mode: 0 = B[N,K] via TMA K-major, 1 = B^T[K,64] via TMA read MN-major (N = 64), 2 = B[N,K] interleaved
+ * K-major, 3 = B^T[K,N] interleaved MN-major.  D[n] = sum_k A[m,k] * B[n,k].  bf16 in, fp32 out.
+ * ---------------------------------------------------------------------------------------------- */
+int cfa_tc_selftest(int a_mode, int b_mode, int N, int K, const void* A, const void* B, float* D, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
