@@ -43,8 +43,10 @@ SIGNATURES = {
     "cfa_infonce_fwd": (C.c_int, [_vp, _i, _vp, _i, _i, _i, _f, _vp, _vp, _vp, _sz, _vp]),
     "cfa_infonce_bwd_workspace_bytes": (_sz, [_i, _i, _i, C.POINTER(C.c_int)]),
     "cfa_infonce_bwd": (C.c_int, [_vp, _i, _vp, _i, _i, _i, _f, _vp, _vp, _vp, _vp, _sz, _vp]),
-    "cfa_sparc_fwd": (C.c_int, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp]),
-    "cfa_sparc_bwd": (C.c_int, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "cfa_sparc_fwd": (C.c_int, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp]),
+    "cfa_sparc_bwd": (C.c_int, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+                                _i, _vp]),
+    "cfa_sparc_path": (C.c_int, [_i, _i, _i, _i, _i]),
     "cfa_sparc_max_patches": (C.c_int, [_i, _i]),
     "cfa_sum2": (C.c_int, [_vp, _vp, _i, _vp, _vp]),
     "cfa_sparc_finalize": (C.c_int, [_vp, _i, _vp, _vp, _i, _i, _f, _f, _vp, _vp]),
@@ -60,7 +62,7 @@ for _name, (_res, _args) in SIGNATURES.items():
 
 # kernels launched per C-ABI call (cudaMemsetAsync not counted); bench.py reports the running total
 LAUNCHES = {"cfa_adamspd_step": 2, "cfa_rows_normalize": 1, "cfa_rows_normalize_bwd": 1, "cfa_infonce_fwd": 2,
-            "cfa_infonce_bwd": 1, "cfa_sparc_fwd": 1, "cfa_sparc_bwd": 1, "cfa_sum2": 1, "cfa_sparc_finalize": 1,
+            "cfa_infonce_bwd": 1, "cfa_sparc_fwd": 2, "cfa_sparc_bwd": 1, "cfa_sum2": 1, "cfa_sparc_finalize": 1,
             "cfa_sparc_coef": 1}
 launch_count = 0
 kernel_events = None       # {abi name: [(start_event, end_event), ...]} while bench.py profiles; else None

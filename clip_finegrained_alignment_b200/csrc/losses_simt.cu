@@ -7,6 +7,7 @@
 // (SURVEY.md §8 a-bwd) and works on the RAW embeddings: every gradient w.r.t. a normalised dot product is
 // folded into a gradient w.r.t. the raw dot product, so all contractions read the raw input tiles.
 #include "common.cuh"
+#include "sparc_paths.h"
 #include <math_constants.h>
 
 namespace cfa {
@@ -905,7 +906,7 @@ static int sparc_fwd_launch(const void* v, const void* l, const uint8_t* mask, i
   return launch_status();
 }
 
-extern "C" int cfa_sparc_fwd(const void* v, const void* l, const uint8_t* mask, int B, int P, int T, int D, int dtype,
+int cfa::sparc_fwd_simt(const void* v, const void* l, const uint8_t* mask, int B, int P, int T, int D, int dtype,
                              float thr, float scale, float* pooled_v, float* pooled_l, float* lse_row, float* lse_col,
                              float* local_partial, void* stream) {
   if (B <= 0 || P <= 0 || T <= 0 || D <= 0 || !v || !l || !mask) return CFA_ERR_BAD_ARG;
@@ -931,7 +932,7 @@ static int sparc_bwd_launch(const void* v, const void* l, const uint8_t* mask, i
   return launch_status();
 }
 
-extern "C" int cfa_sparc_bwd(const void* v, const void* l, const uint8_t* mask, int B, int P, int T, int D, int dtype,
+int cfa::sparc_bwd_simt(const void* v, const void* l, const uint8_t* mask, int B, int P, int T, int D, int dtype,
                              float thr, float scale, const float* lse_row, const float* lse_col, const float* coef,
                              const float* dpooled_v, const float* dpooled_l, void* dv, void* dl, void* stream) {
   if (B <= 0 || P <= 0 || T <= 0 || D <= 0 || !v || !l || !mask || !coef || !dv || !dl) return CFA_ERR_BAD_ARG;

@@ -1,0 +1,501 @@
+// Tensor-core (tcgen05 / TMEM / TMA) SPARC fine-grained kernels for bf16 embeddings on sm_100a.
+//
+// One CTA per sample, warp-specialised: warp 0 = TMA producer, warp 1 = MMA issuer (+ TMEM owner),
+// warps 2..5 = epilogue (one thread per token row = one TMEM lane).  The raw bf16 l[T,D] and v[P,D] tiles
+// stream through a TMA/mbarrier ring in 64-wide D blocks (SWIZZLE_128B) and are consumed directly by
+// tcgen05.mma — normalisation is folded into the epilogue (S = (l.v)/(|l||v|)), so the bf16 products are
+// exact and only fp32 accumulation order differs from the fp32 reference.  Operands produced on chip
+// (alignment weights W, grouped embeddings G, gradient tiles) are split into bf16 hi + lo parts and fed as
+// two MMAs, which keeps ~16 mantissa bits.  The T x P similarity never leaves TMEM / shared memory.
+//
+//   forward  pass 0:  S[T,P]  = sum_kb l_kb . v_kb^T                      (TMEM, 13x16 columns)
+//            epilogue: min-max, threshold, renormalise -> W (hi/lo) in smem (losses.py:228-243)
+//            pass 1:  G_kb    = W . v_kb       (v_kb tile read MN-major)  (losses.py:245)
+//                     L[T,T] += G_kb . l_kb^T                             (losses.py:180)
+//            epilogue: masked row/column log-sum-exp and CE               (losses.py:186-196)
+#include "tc_common.cuh"
+#include "sparc_paths.h"
+#include <math_constants.h>
+
+namespace cfa {
+using namespace tc;
+typedef __nv_bfloat16 bf16;
+
+constexpr int kTcThreads = 192;
+constexpr float kTcNormEps = 1e-12f, kTcMinMaxEps = 1e-8f, kTcClampEps = 1e-8f;
+constexpr uint32_t kTmemCols = 512, kTmemG = 256, kTmemL = 384;
+
+struct TcLayout {
+  int NP, NT, KB, NS;
+  uint32_t l_bytes, v_bytes, stage_bytes, w_bytes, g_bytes;
+  uint32_t off_w, off_g, off_f, off_bar, total;     // byte offsets from the 1024-aligned base
+};
+
+__host__ __device__ inline TcLayout tc_fwd_layout(int P, int T, int D, int NS) {
+  TcLayout L;
+  L.NP = (P + 15) & ~15; L.NT = (T + 15) & ~15; L.KB = D / 64; L.NS = NS;
+  L.l_bytes = L.NT * 128; L.v_bytes = L.NP * 128; L.stage_bytes = L.l_bytes + L.v_bytes;
+  L.w_bytes = (uint32_t)L.NP * L.NT * 2;            // one of hi / lo, interleaved [NP/8][NT][8]
+  L.g_bytes = 64u * L.NT * 2;                       // one of hi / lo of one G_kb buffer
+  L.off_w = L.NS * L.stage_bytes;
+  const uint32_t lb_bytes = (uint32_t)L.NT * (L.NT + 1) * 4;      // fp32 logits scratch aliases the W region
+  L.off_g = L.off_w + ((2 * L.w_bytes > lb_bytes ? 2 * L.w_bytes : lb_bytes) + 1023 & ~1023u);
+  L.off_f = L.off_g + 4 * L.g_bytes + 1024;         // +1 KB: phantom rows of the last interleaved chunk stay in bounds
+  L.off_bar = L.off_f + 4 * (L.NP + 3 * L.NT + 32);
+  L.off_bar = (L.off_bar + 7) & ~7u;
+  L.total = L.off_bar + 8 * (2 * L.NS + 12) + 16;
+  return L;
+}
+
+// ------------------------------------------------------------------------------------------------
+// prep: inverse row norms and pooled means in one pass over the inputs (losses.py:207-212, 221-222)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+sparc_prep_kernel(const bf16* __restrict__ v, const bf16* __restrict__ l, const uint8_t* __restrict__ mask, int P, int T,
+                  int D, float* __restrict__ inv_vn, float* __restrict__ inv_ln, float* __restrict__ pooled_v,
+                  float* __restrict__ pooled_l) {
+  extern __shared__ float red[];            // [8][D]
+  const int b = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ng = D >> 3;                    // 8-column groups per row (<= 128)
+  for (int which = 0; which < 2; ++which) {
+    const int rows = which ? T : P;
+    const bf16* src = which ? l + (size_t)b * T * D : v + (size_t)b * P * D;
+    float acc[4][8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+    float cnt = 0.f;
+    for (int r = warp; r < rows; r += 8) {
+      const float m = which ? (mask[(size_t)b * T + r] ? 1.f : 0.f) : 1.f;
+      float ss = 0.f;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int g = lane + 32 * i;
+        if (g < ng) {
+          const uint4 u = __ldg(reinterpret_cast<const uint4*>(src + (size_t)r * D + 8 * g));
+          const bf16* h = reinterpret_cast<const bf16*>(&u);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float f = __bfloat162float(h[j]);
+            ss = fmaf(f, f, ss);
+            acc[i][j] = fmaf(m, f, acc[i][j]);
+          }
+        }
+      }
+      ss = warp_sum(ss);
+      if (lane == 0) (which ? inv_ln + (size_t)b * T : inv_vn + (size_t)b * P)[r] = 1.f / fmaxf(sqrtf(ss), kTcNormEps);
+    }
+    if (which) for (int t = 0; t < T; ++t) cnt += mask[(size_t)b * T + t] ? 1.f : 0.f;
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int g = lane + 32 * i;
+      if (g < ng)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) red[warp * D + 8 * g + j] = acc[i][j];
+    }
+    __syncthreads();
+    const float denom = which ? fmaxf(cnt, kTcClampEps) : (float)P;
+    for (int d = threadIdx.x; d < D; d += 256) {
+      float s = 0.f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) s += red[k * D + d];
+      (which ? pooled_l : pooled_v)[(size_t)b * D + d] = s / denom;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// small helpers for the epilogue
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void split_bf16x8(const float* x, uint4& hi, uint4& lo) {
+  uint32_t h[4], l[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const bf16 h0 = __float2bfloat16_rn(x[2 * i]), h1 = __float2bfloat16_rn(x[2 * i + 1]);
+    const bf16 l0 = __float2bfloat16_rn(x[2 * i] - __bfloat162float(h0));
+    const bf16 l1 = __float2bfloat16_rn(x[2 * i + 1] - __bfloat162float(h1));
+    h[i] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+    l[i] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+  }
+  hi = make_uint4(h[0], h[1], h[2], h[3]);
+  lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+// load `n` (16 or 32) consecutive columns of this thread's TMEM lane
+__device__ __forceinline__ void tmem_ld_chunk(uint32_t taddr, int n, float* x) {
+  if (n == 32) tmem_ld32(taddr, x); else tmem_ld16(taddr, x);
+  tmem_ld_wait();
+}
+
+struct TcFwdParams {
+  int P, T, D, NS;
+  float thr, scale;
+  const uint8_t* mask;
+  const float* inv_vn;
+  const float* inv_ln;
+  float* lse_row;
+  float* lse_col;
+  float* local_partial;
+};
+
+__global__ void __launch_bounds__(kTcThreads, 1)
+sparc_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmL, const TcFwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* base = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const TcLayout L = tc_fwd_layout(p.P, p.T, p.D, p.NS);
+  const int NP = L.NP, NT = L.NT, KB = L.KB, NS = L.NS, P = p.P, T = p.T;
+  const int b = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  uint8_t* Whi = base + L.off_w;
+  uint8_t* Wlo = Whi + L.w_bytes;
+  uint8_t* Gs = base + L.off_g;                       // [buf][hi|lo][g_bytes]
+  float* ivn = (float*)(base + L.off_f);              // [NP]
+  float* iln = ivn + NP;                              // [NT]
+  float* msk = iln + NT;                              // [NT]
+  float* gnorm = msk + NT;                            // [NT]
+  float* red = gnorm + NT;                            // [32]
+  uint64_t* bars = (uint64_t*)(base + L.off_bar);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + NS;
+  uint64_t* s_full = bars + 2 * NS;
+  uint64_t* w_ready = s_full + 1;
+  uint64_t* g_full = s_full + 2;                      // [2]
+  uint64_t* g_free = s_full + 4;                      // [2]
+  uint64_t* gs_ready = s_full + 6;                    // [2]
+  uint64_t* gs_free = s_full + 8;                     // [2]
+  uint64_t* l_full = s_full + 10;
+  uint32_t* tmem_slot = (uint32_t*)(s_full + 11);
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < NS; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, 1); }
+    mbar_init(s_full, 1); mbar_init(w_ready, 4); mbar_init(l_full, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(g_full + i, 1); mbar_init(g_free + i, 4); mbar_init(gs_ready + i, 4); mbar_init(gs_free + i, 1); }
+    fence_barrier_init();
+    tma_prefetch_desc(&tmV);
+    tma_prefetch_desc(&tmL);
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, kTmemCols);
+  for (int i = threadIdx.x; i < NP + 2 * NT; i += kTcThreads) {
+    if (i < NP) ivn[i] = (i < P) ? p.inv_vn[(size_t)b * P + i] : 0.f;
+    else if (i < NP + NT) { const int t = i - NP; iln[t] = (t < T) ? p.inv_ln[(size_t)b * T + t] : 0.f; }
+    else { const int t = i - NP - NT; msk[t] = (t < T && p.mask[(size_t)b * T + t]) ? 1.f : 0.f; }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0) {
+    // =============================== TMA producer ===============================
+    if (lane == 0) {
+      for (int u = 0; u < 2 * KB; ++u) {
+        const int slot = u % NS, kb = u % KB;
+        mbar_wait(empty + slot, ((u / NS) & 1) ^ 1);
+        uint8_t* st = base + (size_t)slot * L.stage_bytes;
+        mbar_expect_tx(full + slot, L.stage_bytes);
+        tma_load_3d(st, &tmL, full + slot, kb * 64, 0, b);
+        tma_load_3d(st + L.l_bytes, &tmV, full + slot, kb * 64, 0, b);
+      }
+    }
+  } else if (warp == 1) {
+    // =============================== MMA issuer ===============================
+    if (lane == 0) {
+      const uint32_t idesc_s = make_idesc_bf16(128, NP, false, false);
+      const uint32_t idesc_g = make_idesc_bf16(128, 64, false, true);
+      const uint32_t idesc_l = make_idesc_bf16(128, NT, false, false);
+      const uint32_t il_lbo = (uint32_t)NT * 16;      // interleaved operand: next 8-wide k chunk
+      // ---- pass 0: S = l . v^T
+      for (int u = 0; u < KB; ++u) {
+        const int slot = u % NS;
+        mbar_wait(full + slot, (u / NS) & 1);
+        tc_fence_after();
+        const uint32_t sl = smem_u32(base + (size_t)slot * L.stage_bytes), sv = sl + L.l_bytes;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_ss(tmem, make_smem_desc(sl + k * 32, 16, 1024, kLayoutSw128), make_smem_desc(sv + k * 32, 16, 1024, kLayoutSw128),
+                  idesc_s, (u | k) != 0);
+        umma_commit(empty + slot);
+      }
+      umma_commit(s_full);
+      // ---- pass 1: G_kb = W . v_kb ; L += G_kb . l_kb^T   (G issued one block ahead of L)
+      mbar_wait(w_ready, 0);
+      tc_fence_after();
+      auto issue_g = [&](int kb) {
+        const int u = KB + kb, slot = u % NS, buf = kb & 1;
+        mbar_wait(full + slot, (u / NS) & 1);
+        mbar_wait(g_free + buf, ((kb >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t sv = smem_u32(base + (size_t)slot * L.stage_bytes) + L.l_bytes;
+        const uint32_t d = tmem + kTmemG + 64 * buf;
+        const int nks = NP / 16;
+        for (int half = 0; half < 2; ++half) {
+          const uint32_t wa = smem_u32(half ? Wlo : Whi);
+          for (int ks = 0; ks < nks; ++ks)
+            umma_ss(d, make_smem_desc(wa + ks * 2 * il_lbo, il_lbo, 128, kLayoutNone),
+                    make_smem_desc(sv + ks * 2048, 16, 1024, kLayoutSw128), idesc_g, (half | ks) != 0);
+        }
+        umma_commit(g_full + buf);
+      };
+      auto issue_l = [&](int kb) {
+        const int u = KB + kb, slot = u % NS, buf = kb & 1;
+        mbar_wait(gs_ready + buf, (kb >> 1) & 1);
+        tc_fence_after();
+        const uint32_t sl = smem_u32(base + (size_t)slot * L.stage_bytes);
+        for (int half = 0; half < 2; ++half) {
+          const uint32_t ga = smem_u32(Gs + (size_t)(2 * buf + half) * L.g_bytes);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_ss(tmem + kTmemL, make_smem_desc(ga + k * 2 * il_lbo, il_lbo, 128, kLayoutNone),
+                    make_smem_desc(sl + k * 32, 16, 1024, kLayoutSw128), idesc_l, (kb | half | k) != 0);
+        }
+        umma_commit(gs_free + buf);
+        umma_commit(empty + slot);
+      };
+      issue_g(0);
+      for (int kb = 0; kb < KB; ++kb) {
+        if (kb + 1 < KB) issue_g(kb + 1);
+        issue_l(kb);
+      }
+      umma_commit(l_full);
+    }
+  } else {
+    // =============================== epilogue (4 warps, thread = token row) ===============================
+    const int q = warp & 3;                           // TMEM lane quarter this warp may access
+    const int row = 32 * q + lane;
+    const uint32_t trow = tmem + ((uint32_t)(32 * q) << 16);
+    const bool valid = row < T && msk[row < NT ? row : 0] != 0.f;
+    const float il = (row < NT) ? iln[row] : 0.f;
+
+    // ---- epilogue 1: S -> W
+    mbar_wait(s_full, 0);
+    tc_fence_after();
+    float mn = CUDART_INF_F, mx = -CUDART_INF_F;
+    for (int c0 = 0; c0 < NP; c0 += 32) {
+      float x[32];
+      const int n = min(32, NP - c0);
+      tmem_ld_chunk(trow + c0, n, x);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        if (j < n && c0 + j < P) {
+          const float s = x[j] * il * ivn[c0 + j];
+          mn = fminf(mn, s); mx = fmaxf(mx, s);
+        }
+      }
+    }
+    const float rng = mx - mn + kTcMinMaxEps;
+    float sum = 0.f;
+    for (int c0 = 0; c0 < NP; c0 += 32) {
+      float x[32];
+      const int n = min(32, NP - c0);
+      tmem_ld_chunk(trow + c0, n, x);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        if (j < n && c0 + j < P) {
+          const float nn = (x[j] * il * ivn[c0 + j] - mn) / rng;
+          sum += (nn < p.thr) ? 0.f : nn;
+        }
+      }
+    }
+    const float sigma = fmaxf(sum, kTcClampEps);
+    for (int c0 = 0; c0 < NP; c0 += 32) {
+      float x[32];
+      const int n = min(32, NP - c0);
+      tmem_ld_chunk(trow + c0, n, x);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        float w = 0.f;
+        if (j < n && c0 + j < P && valid) {
+          const float nn = (x[j] * il * ivn[c0 + j] - mn) / rng;
+          w = ((nn < p.thr) ? 0.f : nn) / sigma;
+        }
+        x[j] = w;
+      }
+      if (row < NT) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          if (g * 8 < n) {
+            uint4 hi, lo;
+            split_bf16x8(x + 8 * g, hi, lo);
+            const uint32_t off = il_offset(NT, row, c0 + 8 * g);
+            *reinterpret_cast<uint4*>(Whi + off) = hi;
+            *reinterpret_cast<uint4*>(Wlo + off) = lo;
+          }
+        }
+      }
+    }
+    tc_fence_before();
+    fence_proxy_async();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(w_ready);
+
+    // ---- epilogue 2: G_kb -> ||G||^2, bf16 hi/lo A operand for the logits MMA
+    float gn2 = 0.f;
+    for (int kb = 0; kb < KB; ++kb) {
+      const int buf = kb & 1;
+      mbar_wait(g_full + buf, (kb >> 1) & 1);
+      tc_fence_after();
+      float x[64];
+      tmem_ld32(trow + kTmemG + 64 * buf, x);
+      tmem_ld32(trow + kTmemG + 64 * buf + 32, x + 32);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(g_free + buf);
+      mbar_wait(gs_free + buf, ((kb >> 1) & 1) ^ 1);
+      if (row < NT) {
+        uint8_t* gh = Gs + (size_t)(2 * buf) * L.g_bytes;
+        uint8_t* gl = gh + L.g_bytes;
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+          float y[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { y[j] = valid ? x[8 * g + j] : 0.f; gn2 = fmaf(y[j], y[j], gn2); }
+          uint4 hi, lo;
+          split_bf16x8(y, hi, lo);
+          const uint32_t off = il_offset(NT, row, 8 * g);
+          *reinterpret_cast<uint4*>(gh + off) = hi;
+          *reinterpret_cast<uint4*>(gl + off) = lo;
+        }
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(gs_ready + buf);
+    }
+    const float ign = 1.f / fmaxf(sqrtf(gn2), kTcNormEps);
+
+    // ---- epilogue 3: masked logits, row LSE in registers, column LSE through smem (W region is free now)
+    mbar_wait(l_full, 0);
+    tc_fence_after();
+    float* Lb = reinterpret_cast<float*>(Whi);          // [T][NT+1]
+    const int ldl = NT + 1;
+    float rmax = -CUDART_INF_F;
+    for (int c0 = 0; c0 < NT; c0 += 16) {
+      float x[16];
+      tmem_ld_chunk(trow + kTmemL + c0, 16, x);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const int col = c0 + j;
+        const float y = (valid && col < T && msk[col] != 0.f) ? p.scale * (x[j] * ign * iln[col]) : -CUDART_INF_F;
+        if (row < T) Lb[row * ldl + col] = y;
+        rmax = fmaxf(rmax, y);
+      }
+    }
+    float ce_r = 0.f, ce_c = 0.f;
+    if (valid) {
+      float s = 0.f;
+      for (int col = 0; col < T; ++col) { const float y = Lb[row * ldl + col]; if (y != -CUDART_INF_F) s += expf(y - rmax); }
+      const float lse = rmax + logf(s);
+      p.lse_row[(size_t)b * T + row] = lse;
+      ce_r = lse - Lb[row * ldl + row];
+    } else if (row < T) {
+      p.lse_row[(size_t)b * T + row] = 0.f;
+    }
+    epi_bar_sync();
+    if (valid) {                                         // thread `row` now owns column `row`
+      float cmax = -CUDART_INF_F;
+      for (int i = 0; i < T; ++i) cmax = fmaxf(cmax, Lb[i * ldl + row]);
+      float s = 0.f;
+      for (int i = 0; i < T; ++i) { const float y = Lb[i * ldl + row]; if (y != -CUDART_INF_F) s += expf(y - cmax); }
+      const float lse = cmax + logf(s);
+      p.lse_col[(size_t)b * T + row] = lse;
+      ce_c = lse - Lb[row * ldl + row];
+    } else if (row < T) {
+      p.lse_col[(size_t)b * T + row] = 0.f;
+    }
+    ce_r = warp_sum(ce_r); ce_c = warp_sum(ce_c);
+    if (lane == 0) { red[q] = ce_r; red[4 + q] = ce_c; }
+    epi_bar_sync();
+    if (row == 0) {
+      p.local_partial[2 * b] = red[0] + red[1] + red[2] + red[3];
+      p.local_partial[2 * b + 1] = red[4] + red[5] + red[6] + red[7];
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem, kTmemCols); }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+static int tc_pick_stages(int P, int T, int D) {
+  for (int ns = 4; ns >= 2; --ns)
+    if (tc_fwd_layout(P, T, D, ns).total + 1024 <= 227 * 1024) return ns;
+  return 0;
+}
+
+bool sparc_tc_supported(int P, int T, int D, int dtype) {
+  if (dtype != CFA_DTYPE_BF16) return false;
+  if (D % 256 != 0 || D > 1024 || T < 1 || T > 128 || P < 1 || P > 256) return false;
+  return tc_pick_stages(P, T, D) != 0;
+}
+
+int sparc_prep_launch(const void* v, const void* l, const uint8_t* mask, int B, int P, int T, int D, float* inv_vn,
+                      float* inv_ln, float* pooled_v, float* pooled_l, cudaStream_t st) {
+  const size_t smem = (size_t)8 * D * sizeof(float);
+  static bool attr = false;
+  if (!attr) { CFA_CUDA_TRY(cudaFuncSetAttribute(sparc_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 1024 * 4)); attr = true; }
+  sparc_prep_kernel<<<B, 256, smem, st>>>((const bf16*)v, (const bf16*)l, mask, P, T, D, inv_vn, inv_ln, pooled_v, pooled_l);
+  return launch_status();
+}
+
+int sparc_fwd_tc_launch(const void* v, const void* l, const uint8_t* mask, int B, int P, int T, int D, float thr,
+                        float scale, float* row_inv_norm, float* pooled_v, float* pooled_l, float* lse_row,
+                        float* lse_col, float* local_partial, cudaStream_t st) {
+  float* inv_vn = row_inv_norm;
+  float* inv_ln = row_inv_norm + (size_t)B * P;
+  int rc = sparc_prep_launch(v, l, mask, B, P, T, D, inv_vn, inv_ln, pooled_v, pooled_l, st);
+  if (rc != CFA_OK) return rc;
+  const int NS = tc_pick_stages(P, T, D);
+  const TcLayout L = tc_fwd_layout(P, T, D, NS);
+  CUtensorMap tmV, tmL;
+  if ((rc = make_tmap_bf16_3d(&tmV, v, D, P, B, 64, L.NP)) != CFA_OK) return rc;
+  if ((rc = make_tmap_bf16_3d(&tmL, l, D, T, B, 64, L.NT)) != CFA_OK) return rc;
+  TcFwdParams prm{P, T, D, NS, thr, scale, mask, inv_vn, inv_ln, lse_row, lse_col, local_partial};
+  const size_t smem = L.total + 1024;
+  CFA_CUDA_TRY(cudaFuncSetAttribute(sparc_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  sparc_fwd_tc_kernel<<<B, kTcThreads, smem, st>>>(tmV, tmL, prm);
+  return launch_status();
+}
+
+}  // namespace cfa
+
+using namespace cfa;
+
+// path: 0 = auto (tensor cores when the shape/dtype allows, else CUDA cores), 1 = CUDA cores, 2 = tensor cores
+extern "C" int cfa_sparc_path(int P, int T, int D, int dtype, int path) {
+  if (path == 1) return 1;
+  const bool ok = sparc_tc_supported(P, T, D, dtype);
+  if (path == 2) return ok ? 2 : CFA_ERR_UNSUPPORTED;
+  return ok ? 2 : 1;
+}
+
+extern "C" int cfa_sparc_fwd(const void* v, const void* l, const uint8_t* mask, int B, int P, int T, int D, int dtype,
+                             float thr, float scale, float* row_inv_norm, float* pooled_v, float* pooled_l,
+                             float* lse_row, float* lse_col, float* local_partial, int path, void* stream) {
+  if (B <= 0 || P <= 0 || T <= 0 || D <= 0 || !v || !l || !mask) return CFA_ERR_BAD_ARG;
+  const int which = cfa_sparc_path(P, T, D, dtype, path);
+  if (which < 0) return which;
+  if (which == 2) {
+    if (!row_inv_norm) return CFA_ERR_WORKSPACE;
+    return sparc_fwd_tc_launch(v, l, mask, B, P, T, D, thr, scale, row_inv_norm, pooled_v, pooled_l, lse_row, lse_col,
+                               local_partial, (cudaStream_t)stream);
+  }
+  return sparc_fwd_simt(v, l, mask, B, P, T, D, dtype, thr, scale, pooled_v, pooled_l, lse_row, lse_col, local_partial,
+                        stream);
+}
+
+extern "C" int cfa_sparc_bwd(const void* v, const void* l, const uint8_t* mask, int B, int P, int T, int D, int dtype,
+                             float thr, float scale, const float* row_inv_norm, const float* lse_row,
+                             const float* lse_col, const float* coef, const float* dpooled_v, const float* dpooled_l,
+                             void* dv, void* dl, int path, void* stream) {
+  if (B <= 0 || P <= 0 || T <= 0 || D <= 0 || !v || !l || !mask || !coef || !dv || !dl) return CFA_ERR_BAD_ARG;
+  (void)row_inv_norm; (void)path;
+  return sparc_bwd_simt(v, l, mask, B, P, T, D, dtype, thr, scale, lse_row, lse_col, coef, dpooled_v, dpooled_l, dv, dl,
+                        stream);
+}

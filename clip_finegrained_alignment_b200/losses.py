@@ -143,7 +143,7 @@ class _SparcFunction(torch.autograd.Function):
     a single [7] gradient vector to backward — no host synchronisation anywhere."""
 
     @staticmethod
-    def forward(ctx, v, l, mask, thr, gw, lw, scale, gather, group):
+    def forward(ctx, v, l, mask, thr, gw, lw, scale, gather, group, path):
         dev = _lib.require_cuda(v, l, mask)
         if v.dtype != l.dtype or v.dtype not in _lib.DTYPE_CODE:
             raise _lib.CfaError(f"SPARCLoss: embeddings must share a dtype in fp32/bf16/fp16, got {v.dtype}, {l.dtype}")
@@ -162,24 +162,25 @@ class _SparcFunction(torch.autograd.Function):
         lse_r = torch.empty(B, T, **f32)
         lse_c = torch.empty(B, T, **f32)
         part = torch.empty(B, 2, **f32)
+        inv_norm = torch.empty(B * (P + T), **f32)
         with torch.cuda.device(dev):
             _lib.call("cfa_sparc_fwd", v.data_ptr(), l.data_ptr(), mask_u8.data_ptr(), B, P, T, D, code, thr, scale,
-                                        pooled_v.data_ptr(), pooled_l.data_ptr(), lse_r.data_ptr(), lse_c.data_ptr(),
-                                        part.data_ptr(), _lib.stream_ptr())
+                      inv_norm.data_ptr(), pooled_v.data_ptr(), pooled_l.data_ptr(), lse_r.data_ptr(), lse_c.data_ptr(),
+                      part.data_ptr(), path, _lib.stream_ptr())
             world, rank, group = _dist_ctx(group, gather)
             gst, sums = _global_forward(pooled_v, pooled_l, scale, _NORM_EPS, world, rank, group)
             out8 = torch.empty(8, **f32)
             _lib.call("cfa_sparc_finalize", sums.data_ptr(), gst.Bg, part.data_ptr(), mask_u8.data_ptr(), B, T, gw, lw,
                                              out8.data_ptr(), _lib.stream_ptr())
-        ctx.save_for_backward(v, l, mask_u8, lse_r, lse_c, out8)
+        ctx.save_for_backward(v, l, mask_u8, lse_r, lse_c, out8, inv_norm)
         ctx.gst = gst
-        ctx.hp = (thr, gw, lw, scale, code)
+        ctx.hp = (thr, gw, lw, scale, code, path)
         return out8[:7].clone()
 
     @staticmethod
     def backward(ctx, grad7):
-        v, l, mask_u8, lse_r, lse_c, out8 = ctx.saved_tensors
-        thr, gw, lw, scale, code = ctx.hp
+        v, l, mask_u8, lse_r, lse_c, out8, inv_norm = ctx.saved_tensors
+        thr, gw, lw, scale, code, path = ctx.hp
         gst = ctx.gst
         B, P, D = v.shape
         T = l.shape[1]
@@ -193,9 +194,9 @@ class _SparcFunction(torch.autograd.Function):
             dv = torch.empty_like(v)
             dl = torch.empty_like(l)
             _lib.call("cfa_sparc_bwd", v.data_ptr(), l.data_ptr(), mask_u8.data_ptr(), B, P, T, D, code, thr, scale,
-                                        lse_r.data_ptr(), lse_c.data_ptr(), coef[2:4].data_ptr(), dpv.data_ptr(),
-                                        dpl.data_ptr(), dv.data_ptr(), dl.data_ptr(), _lib.stream_ptr())
-        return dv, dl, None, None, None, None, None, None, None
+                      inv_norm.data_ptr(), lse_r.data_ptr(), lse_c.data_ptr(), coef[2:4].data_ptr(), dpv.data_ptr(),
+                      dpl.data_ptr(), dv.data_ptr(), dl.data_ptr(), path, _lib.stream_ptr())
+        return dv, dl, None, None, None, None, None, None, None, None
 
 
 class _PairwiseFunction(torch.autograd.Function):
@@ -234,8 +235,11 @@ class _PairwiseFunction(torch.autograd.Function):
 class SPARCLoss(nn.Module):
     """SPARC loss (https://arxiv.org/abs/2401.09865), reference API: finetune/losses.py:136-264."""
 
-    def __init__(self, config, gather: bool = False, process_group=None):
+    def __init__(self, config, gather: bool = False, process_group=None, kernel_path: str = "auto"):
         super().__init__()
+        # "auto": tcgen05 tensor-core kernels for bf16 inputs of supported shapes, fp32-exact CUDA-core kernels
+        # otherwise; "simt" / "tc" force one of them (tests, benchmarks)
+        self.kernel_path = {"auto": 0, "simt": 1, "tc": 2}[kernel_path]
         self.similarity_threshold = config.similarity_threshold      # losses.py:140-143
         self.global_loss_weight = config.global_loss_weight
         self.local_loss_weight = config.local_loss_weight
@@ -259,7 +263,7 @@ class SPARCLoss(nn.Module):
             raise TypeError(f"language_mask must be bool or integer, got {language_mask.dtype}")
         out = _SparcFunction.apply(v_patch_embed, l_token_embed, language_mask, float(self.similarity_threshold),
                                    float(self.global_loss_weight), float(self.local_loss_weight),
-                                   float(self.inverse_temperature), self.gather, self.process_group)
+                                   float(self.inverse_temperature), self.gather, self.process_group, self.kernel_path)
         return {k: out[i] for i, k in enumerate(SPARC_KEYS)}
 
 

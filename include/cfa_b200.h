@@ -125,17 +125,24 @@ int cfa_infonce_bwd(const float* a_hat, int B, const float* b_hat, int Bg, int D
  * patch embeddings (:225-245) live only in shared memory / registers.
  * ---------------------------------------------------------------------------------------------- */
 int cfa_sparc_fwd(const void* v, const void* l, const uint8_t* mask, int B, int P, int T, int D, int dtype,
-                  float thr, float scale, float* pooled_v, float* pooled_l, float* lse_row, float* lse_col,
-                  float* local_partial, void* stream);
+                  float thr, float scale, float* row_inv_norm, float* pooled_v, float* pooled_l, float* lse_row,
+                  float* lse_col, float* local_partial, int path, void* stream);
 
 /*
  * Backward of the above.  coef: DEVICE pointer to 2 floats = upstream coefficient of loss_vl_local and
  * loss_lv_local, already divided by n_valid.  dpooled_v / dpooled_l [B,D]: gradient w.r.t. the pooled
  * means (from the global InfoNCE), may be NULL.  dv [B,P,D], dl [B,T,D] are written in `dtype`.
+ *
+ * row_inv_norm: [B*(P+T)] floats of scratch saved between forward and backward (1/max(|v_p|,eps) then
+ * 1/max(|l_t|,eps)); written by cfa_sparc_fwd, read by cfa_sparc_bwd.
+ * path: 0 = auto, 1 = fp32-exact CUDA-core kernels, 2 = tcgen05 tensor-core kernels (bf16, D % 256 == 0,
+ * P <= 256, T <= 128; CFA_ERR_UNSUPPORTED otherwise).  cfa_sparc_path reports what `auto` resolves to.
  */
 int cfa_sparc_bwd(const void* v, const void* l, const uint8_t* mask, int B, int P, int T, int D, int dtype,
-                  float thr, float scale, const float* lse_row, const float* lse_col, const float* coef,
-                  const float* dpooled_v, const float* dpooled_l, void* dv, void* dl, void* stream);
+                  float thr, float scale, const float* row_inv_norm, const float* lse_row, const float* lse_col,
+                  const float* coef, const float* dpooled_v, const float* dpooled_l, void* dv, void* dl, int path,
+                  void* stream);
+int cfa_sparc_path(int P, int T, int D, int dtype, int path);
 
 /* largest P the SPARC kernels accept for a given T (shared-memory residency of the T x P tiles) */
 int cfa_sparc_max_patches(int T, int backward);

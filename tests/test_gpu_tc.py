@@ -37,3 +37,76 @@ def test_tcgen05_operand_modes(a_mode, b_mode, N, K):
     err = (D - ref).abs().max().item()
     assert torch.isfinite(D).all(), (a_mode, b_mode)
     assert err <= 1e-3 * max(1.0, ref.abs().max().item()), (a_mode, b_mode, N, K, err)
+
+
+# ----------------------------------------------------------------------------------------------
+# tensor-core SPARC kernels vs the oracle (oracle-A: fp64 reference math on the bf16-representable inputs)
+# ----------------------------------------------------------------------------------------------
+import types
+
+from conftest import rel_err
+from oracle import losses_oracle as lo
+
+
+def _cfg(thr, gw=1.0, lw=1.0, s=1.0):
+    return types.SimpleNamespace(similarity_threshold=thr, global_loss_weight=gw, local_loss_weight=lw,
+                                 inverse_temperature=s)
+
+
+def _sparc_tc(v, l, m, c, key="total_loss", path="tc"):
+    from clip_finegrained_alignment_b200 import SPARCLoss
+    vv = v.cuda().requires_grad_(True)
+    ll = l.cuda().requires_grad_(True)
+    out = SPARCLoss(c, kernel_path=path)(vv, ll, m.cuda())
+    out[key].backward()
+    torch.cuda.synchronize()
+    return {k: x.detach().float().cpu() for k, x in out.items()}, vv.grad, ll.grad
+
+
+@pytest.mark.parametrize("B,P,T,D,s", [(3, 196, 77, 512, 1.0), (2, 197, 77, 512, 2.0), (4, 50, 77, 256, 1.0),
+                                       (2, 33, 20, 256, 3.0), (2, 256, 77, 768, 1.0), (5, 64, 128, 256, 1.0)])
+def test_sparc_tc_vs_oracle(B, P, T, D, s):
+    g = torch.Generator().manual_seed(B * 7 + P)
+    v = torch.randn(B, P, D, generator=g).to(torch.bfloat16)
+    l = torch.randn(B, T, D, generator=g).to(torch.bfloat16)
+    m = torch.ones(B, T, dtype=torch.bool)
+    thr = float(torch.tensor(1.0 / P, dtype=torch.float32))
+    out, dv, dl = _sparc_tc(v, l, m, _cfg(thr, 0.9, 1.1, s))
+    o = lo.sparc_forward(v.double(), l.double(), m, thr, 0.9, 1.1, s)
+    rv, rl = lo.sparc_backward(o)
+    for k in lo.SPARC_KEYS:
+        assert abs(float(out[k]) - float(o[k])) <= 1e-4 * max(1.0, abs(float(o[k]))), (k, float(out[k]), float(o[k]))
+    # gradients come back in bf16: allow one output rounding (2^-9 relative, rms) on top of rtol 1e-3
+    assert rel_err(dv.float(), rv) <= 1e-3 + 2.0 ** -8
+    assert rel_err(dl.float(), rl) <= 1e-3 + 2.0 ** -8
+
+
+def test_sparc_tc_padded_mask():
+    g = torch.Generator().manual_seed(3)
+    B, P, T, D = 4, 196, 77, 256
+    v = torch.randn(B, P, D, generator=g).to(torch.bfloat16)
+    l = torch.randn(B, T, D, generator=g).to(torch.bfloat16)
+    lens = torch.tensor([77, 5, 40, 76])
+    m = torch.arange(T)[None, :] < lens[:, None]
+    thr = float(torch.tensor(1.0 / P, dtype=torch.float32))
+    out, dv, dl = _sparc_tc(v, l, m, _cfg(thr))
+    o = lo.sparc_forward(v.double(), l.double(), m, thr, 1.0, 1.0, 1.0, mask_semantics="truncate")
+    rv, rl = lo.sparc_backward(o)
+    for k in lo.SPARC_KEYS:
+        assert abs(float(out[k]) - float(o[k])) <= 1e-4 * max(1.0, abs(float(o[k]))), k
+    assert rel_err(dv.float(), rv) <= 1e-3 + 2.0 ** -8
+    assert rel_err(dl.float(), rl) <= 1e-3 + 2.0 ** -8
+
+
+def test_sparc_tc_matches_simt_path():
+    g = torch.Generator().manual_seed(11)
+    B, P, T, D = 6, 196, 77, 512
+    v = torch.randn(B, P, D, generator=g).to(torch.bfloat16)
+    l = torch.randn(B, T, D, generator=g).to(torch.bfloat16)
+    m = torch.ones(B, T, dtype=torch.bool)
+    a, dva, dla = _sparc_tc(v, l, m, _cfg(1.0 / P), path="tc")
+    b, dvb, dlb = _sparc_tc(v, l, m, _cfg(1.0 / P), path="simt")
+    for k in a:
+        assert abs(float(a[k]) - float(b[k])) <= 2e-5 * max(1.0, abs(float(b[k]))), k
+    assert rel_err(dva.float(), dvb.float()) <= 5e-3
+    assert rel_err(dla.float(), dlb.float()) <= 5e-3
