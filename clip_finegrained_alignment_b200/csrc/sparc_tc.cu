@@ -463,6 +463,695 @@ int sparc_fwd_tc_launch(const void* v, const void* l, const uint8_t* mask, int B
   return launch_status();
 }
 
+
+// ================================================================================================
+// backward (tensor cores).  32-wide D blocks (SWIZZLE_64B TMA tiles) so that W, dShat (hi/lo), dLhat (hi/lo)
+// and the per-block G / dG operands all stay resident in shared memory.  Four streaming passes over (l, v):
+//   pass 1  S = l . v^T                                  -> epilogue: W (hi/lo), row stats
+//   pass 2  G_kb = W . v_kb ; L += G_kb . l_kb^T         -> epilogue: dLhat (hi/lo), gfac, ldotL
+//   pass 3  G_kb, X_kb = dLhat . l_kb -> dG_kb ; dW += dG_kb . v_kb^T   -> epilogue: dShat (hi/lo), lfac, vfac
+//   pass 4  G_kb, dG_kb ; dv_kb = dShat^T . l_kb + W^T . dG_kb ; dl_kb = dShat . v_kb + dLhat^T . G_kb -> global
+// All gradients are w.r.t. RAW dot products (SURVEY §8 a-bwd with the normalisations folded in), so every
+// contraction reads the raw TMA tiles.
+// ================================================================================================
+struct TcBwdLayout {
+  int NP, NT, KB, NS;
+  uint32_t l_bytes, v_bytes, stage_bytes, w_bytes, dl_bytes, g_bytes;
+  uint32_t off_w, off_dl, off_g, off_f, off_bar, total;
+};
+
+__host__ __device__ inline TcBwdLayout tc_bwd_layout(int P, int T, int D, int NS) {
+  TcBwdLayout L;
+  L.NP = (P + 15) & ~15; L.NT = (T + 15) & ~15; L.KB = D / 32; L.NS = NS;
+  L.l_bytes = L.NT * 64; L.v_bytes = L.NP * 64; L.stage_bytes = L.l_bytes + L.v_bytes;
+  L.w_bytes = (uint32_t)L.NP * L.NT * 2;
+  L.dl_bytes = (uint32_t)L.NT * L.NT * 2;
+  L.g_bytes = 32u * L.NT * 2;
+  L.off_w = (L.NS * L.stage_bytes + 1023) & ~1023u;   // Whi, Wlo, DShi, DSlo
+  const uint32_t sc_bytes = (uint32_t)L.NT * (L.NT + 1) * 4;       // phase-3 fp32 scratch aliases the dShat region
+  L.off_dl = L.off_w + 2 * L.w_bytes + (2 * L.w_bytes > sc_bytes ? 2 * L.w_bytes : ((sc_bytes + 15) & ~15u));   // dLhi, dLlo
+  L.off_g = L.off_dl + 2 * L.dl_bytes;                // 4 operand buffers of g_bytes
+  L.off_f = L.off_g + 4 * L.g_bytes + 1024;           // phantom rows of the last buffer stay in bounds
+  L.off_bar = (L.off_f + 4 * (2 * L.NP + 5 * L.NT + 32) + 7) & ~7u;
+  L.total = L.off_bar + 8 * (2 * L.NS + 34) + 16;
+  return L;
+}
+
+struct TcBwdParams {
+  int P, T, D, NS;
+  float thr, scale;
+  const uint8_t* mask;
+  const float* inv_vn;
+  const float* inv_ln;
+  const float* lse_row;
+  const float* lse_col;
+  const float* coef;
+  const float* dpool_v;
+  const float* dpool_l;
+  const bf16* v;
+  const bf16* l;
+  bf16* dv;
+  bf16* dl;
+};
+
+__device__ __forceinline__ void unpack_bf16x8(const uint4& u, float* f) {
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    f[2 * i] = __uint_as_float(w[i] << 16);
+    f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+  }
+}
+__device__ __forceinline__ uint4 pack_bf16x8(const float* f) {
+  uint32_t w[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    w[i] = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(f[2 * i])) |
+           ((uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(f[2 * i + 1])) << 16);
+  return make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+__global__ void __launch_bounds__(kTcThreads, 1)
+sparc_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmL, const TcBwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* base = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const TcBwdLayout L = tc_bwd_layout(p.P, p.T, p.D, p.NS);
+  const int NP = L.NP, NT = L.NT, KB = L.KB, NS = L.NS, P = p.P, T = p.T, D = p.D;
+  const int b = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  uint8_t* Whi = base + L.off_w;
+  uint8_t* Wlo = Whi + L.w_bytes;
+  uint8_t* DShi = Wlo + L.w_bytes;
+  uint8_t* DSlo = DShi + L.w_bytes;
+  uint8_t* dLhi = base + L.off_dl;
+  uint8_t* dLlo = dLhi + L.dl_bytes;
+  uint8_t* Gb = base + L.off_g;                        // 4 x g_bytes
+  float* ivn = (float*)(base + L.off_f);               // [NP]
+  float* vdot = ivn + NP;                              // [NP]  -> vfac
+  float* iln = vdot + NP;                              // [NT]
+  float* msk = iln + NT;                               // [NT]
+  float* lser = msk + NT;                              // [NT]
+  float* lsec = lser + NT;                             // [NT]
+  float* ldot = lsec + NT;                             // [NT]
+  uint64_t* bars = (uint64_t*)(base + L.off_bar);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + NS;
+  uint64_t* bb = bars + 2 * NS;
+  uint64_t* s_full = bb + 0;  uint64_t* w_ready = bb + 1;
+  uint64_t* g_full2 = bb + 2; uint64_t* g_free2 = bb + 4; uint64_t* gs_ready2 = bb + 6; uint64_t* gs_free2 = bb + 8;
+  uint64_t* l_full = bb + 10; uint64_t* dl_ready = bb + 11;
+  uint64_t* g_full3 = bb + 12; uint64_t* g_free3 = bb + 14; uint64_t* dg_ready3 = bb + 16; uint64_t* dg_free3 = bb + 18;
+  uint64_t* dw_full = bb + 20; uint64_t* ds_ready = bb + 21;
+  uint64_t* g_full4 = bb + 22; uint64_t* g_free4 = bb + 24; uint64_t* gs_ready4 = bb + 26; uint64_t* gs_free4 = bb + 27;
+  uint64_t* out_full = bb + 28; uint64_t* out_free = bb + 30;
+  uint32_t* tmem_slot = (uint32_t*)(bb + 32);
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < NS; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, 1); }
+    mbar_init(s_full, 1); mbar_init(w_ready, 4); mbar_init(l_full, 1); mbar_init(dl_ready, 4);
+    mbar_init(dw_full, 1); mbar_init(ds_ready, 4); mbar_init(gs_ready4, 4); mbar_init(gs_free4, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(g_full2 + i, 1); mbar_init(g_free2 + i, 4); mbar_init(gs_ready2 + i, 4); mbar_init(gs_free2 + i, 1);
+      mbar_init(g_full3 + i, 1); mbar_init(g_free3 + i, 4); mbar_init(dg_ready3 + i, 4); mbar_init(dg_free3 + i, 1);
+      mbar_init(g_full4 + i, 1); mbar_init(g_free4 + i, 4); mbar_init(out_full + i, 1); mbar_init(out_free + i, 4);
+    }
+    fence_barrier_init();
+    tma_prefetch_desc(&tmV);
+    tma_prefetch_desc(&tmL);
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, kTmemCols);
+  for (int i = threadIdx.x; i < 2 * NP + 5 * NT; i += kTcThreads) {
+    if (i < NP) ivn[i] = (i < P) ? p.inv_vn[(size_t)b * P + i] : 0.f;
+    else if (i < 2 * NP) vdot[i - NP] = 0.f;
+    else {
+      const int k = (i - 2 * NP) / NT, t = (i - 2 * NP) % NT;
+      const bool in = t < T;
+      float x = 0.f;
+      if (k == 0) x = in ? p.inv_ln[(size_t)b * T + t] : 0.f;
+      else if (k == 1) x = (in && p.mask[(size_t)b * T + t]) ? 1.f : 0.f;
+      else if (k == 2) x = in ? p.lse_row[(size_t)b * T + t] : 0.f;
+      else if (k == 3) x = in ? p.lse_col[(size_t)b * T + t] : 0.f;
+      (k == 0 ? iln : k == 1 ? msk : k == 2 ? lser : k == 3 ? lsec : ldot)[t] = x;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  constexpr uint32_t cS = 0, cG = 256, cX = 320, cL = 384, cDV = 0, cDL = 128;
+  const uint32_t il_lbo = (uint32_t)NT * 16;           // interleaved operand: K-major chunk stride == MN-major group stride
+
+  if (warp == 0) {
+    // =============================== TMA producer ===============================
+    if (lane == 0) {
+      for (int u = 0; u < 4 * KB; ++u) {
+        const int slot = u % NS, kb = u % KB;
+        mbar_wait(empty + slot, ((u / NS) & 1) ^ 1);
+        uint8_t* st = base + (size_t)slot * L.stage_bytes;
+        mbar_expect_tx(full + slot, L.stage_bytes);
+        tma_load_3d(st, &tmL, full + slot, kb * 32, 0, b);
+        tma_load_3d(st + L.l_bytes, &tmV, full + slot, kb * 32, 0, b);
+      }
+    }
+  } else if (warp == 1) {
+    // =============================== MMA issuer ===============================
+    if (lane == 0) {
+      const uint32_t id_s = make_idesc_bf16(128, NP, false, false);     // [T x NP]  K-major x K-major
+      const uint32_t id_kn32 = make_idesc_bf16(128, 32, false, true);   // A K-major, B MN-major, N = 32
+      const uint32_t id_nn32 = make_idesc_bf16(128, 32, true, true);    // A MN-major, B MN-major, N = 32
+      const uint32_t id_l = make_idesc_bf16(128, NT, false, false);
+      const int nksP = NP / 16, nksT = NT / 16;
+      auto il_k = [&](const uint8_t* a, int ks) { return make_smem_desc(smem_u32(a) + ks * 2 * il_lbo, il_lbo, 128, kLayoutNone); };
+      auto il_mn = [&](const uint8_t* a, int ks, int mtile) {
+        return make_smem_desc(smem_u32(a) + mtile * 16 * il_lbo + ks * 256, 128, il_lbo, kLayoutNone);
+      };
+      auto sw_k = [&](uint32_t s, int k) { return make_smem_desc(s + k * 32, 16, 512, kLayoutSw64); };
+      auto sw_mn = [&](uint32_t s, int ks) { return make_smem_desc(s + ks * 1024, 16, 512, kLayoutSw64); };
+
+      // ---- pass 1: S
+      for (int u = 0; u < KB; ++u) {
+        const int slot = u % NS;
+        mbar_wait(full + slot, (u / NS) & 1);
+        tc_fence_after();
+        const uint32_t sl = smem_u32(base + (size_t)slot * L.stage_bytes), sv = sl + L.l_bytes;
+#pragma unroll
+        for (int k = 0; k < 2; ++k) umma_ss(tmem + cS, sw_k(sl, k), sw_k(sv, k), id_s, (u | k) != 0);
+        umma_commit(empty + slot);
+      }
+      umma_commit(s_full);
+
+      // G_kb = W . v_kb (hi, lo) into TMEM cG[buf]; optionally X_kb = dLhat . l_kb into cX[buf]
+      auto issue_gx = [&](int pass, int kb, uint64_t* gfull, uint64_t* gfree, bool with_x) {
+        const int u = pass * KB + kb, slot = u % NS, buf = kb & 1;
+        mbar_wait(full + slot, (u / NS) & 1);
+        mbar_wait(gfree + buf, ((kb >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t sl = smem_u32(base + (size_t)slot * L.stage_bytes), sv = sl + L.l_bytes;
+        for (int half = 0; half < 2; ++half)
+          for (int ks = 0; ks < nksP; ++ks)
+            umma_ss(tmem + cG + 32 * buf, il_k(half ? Wlo : Whi, ks), sw_mn(sv, ks), id_kn32, (half | ks) != 0);
+        if (with_x)
+          for (int half = 0; half < 2; ++half)
+            for (int ks = 0; ks < nksT; ++ks)
+              umma_ss(tmem + cX + 32 * buf, il_k(half ? dLlo : dLhi, ks), sw_mn(sl, ks), id_kn32, (half | ks) != 0);
+        umma_commit(gfull + buf);
+      };
+
+      // ---- pass 2: L += G_kb . l_kb^T
+      mbar_wait(w_ready, 0);
+      tc_fence_after();
+      issue_gx(1, 0, g_full2, g_free2, false);
+      for (int kb = 0; kb < KB; ++kb) {
+        if (kb + 1 < KB) issue_gx(1, kb + 1, g_full2, g_free2, false);
+        const int u = KB + kb, slot = u % NS, buf = kb & 1;
+        mbar_wait(gs_ready2 + buf, (kb >> 1) & 1);
+        tc_fence_after();
+        const uint32_t sl = smem_u32(base + (size_t)slot * L.stage_bytes);
+        for (int half = 0; half < 2; ++half)
+#pragma unroll
+          for (int k = 0; k < 2; ++k)
+            umma_ss(tmem + cL, il_k(Gb + (size_t)(2 * buf + half) * L.g_bytes, k), sw_k(sl, k), id_l, (kb | half | k) != 0);
+        umma_commit(gs_free2 + buf);
+        umma_commit(empty + slot);
+      }
+      umma_commit(l_full);
+
+      // ---- pass 3: dW += dG_kb . v_kb^T
+      mbar_wait(dl_ready, 0);
+      tc_fence_after();
+      issue_gx(2, 0, g_full3, g_free3, true);
+      for (int kb = 0; kb < KB; ++kb) {
+        if (kb + 1 < KB) issue_gx(2, kb + 1, g_full3, g_free3, true);
+        const int u = 2 * KB + kb, slot = u % NS, buf = kb & 1;
+        mbar_wait(dg_ready3 + buf, (kb >> 1) & 1);
+        tc_fence_after();
+        const uint32_t sv = smem_u32(base + (size_t)slot * L.stage_bytes) + L.l_bytes;
+        for (int half = 0; half < 2; ++half)
+#pragma unroll
+          for (int k = 0; k < 2; ++k)
+            umma_ss(tmem + cS, il_k(Gb + (size_t)(2 * buf + half) * L.g_bytes, k), sw_k(sv, k), id_s, (kb | half | k) != 0);
+        umma_commit(dg_free3 + buf);
+        umma_commit(empty + slot);
+      }
+      umma_commit(dw_full);
+
+      // ---- pass 4: dv_kb, dl_kb
+      mbar_wait(ds_ready, 0);
+      tc_fence_after();
+      const uint8_t* Ghi = Gb; const uint8_t* Glo = Gb + L.g_bytes;
+      const uint8_t* dGhi = Gb + 2 * L.g_bytes; const uint8_t* dGlo = Gb + 3 * L.g_bytes;
+      issue_gx(3, 0, g_full4, g_free4, true);
+      for (int kb = 0; kb < KB; ++kb) {
+        if (kb + 1 < KB) issue_gx(3, kb + 1, g_full4, g_free4, true);
+        const int u = 3 * KB + kb, slot = u % NS, buf = kb & 1;
+        mbar_wait(gs_ready4, kb & 1);
+        mbar_wait(out_free + buf, ((kb >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t sl = smem_u32(base + (size_t)slot * L.stage_bytes), sv = sl + L.l_bytes;
+        for (int m = 0; m < 2; ++m) {                 // dv rows p = 128 m ...
+          const uint32_t d = tmem + cDV + 64 * buf + 32 * m;
+          bool acc = false;
+          for (int half = 0; half < 2; ++half)
+            for (int ks = 0; ks < nksT; ++ks) { umma_ss(d, il_mn(half ? DSlo : DShi, ks, m), sw_mn(sl, ks), id_nn32, acc); acc = true; }
+          for (int c = 0; c < 3; ++c) {               // W^T . dG : hi.hi + hi.lo + lo.hi
+            const uint8_t* wa = (c == 2) ? Wlo : Whi;
+            const uint8_t* ga = (c == 1) ? dGlo : dGhi;
+            for (int ks = 0; ks < nksT; ++ks) umma_ss(d, il_mn(wa, ks, m), il_mn(ga, ks, 0), id_nn32, true);
+          }
+        }
+        {                                             // dl rows t
+          const uint32_t d = tmem + cDL + 32 * buf;
+          bool acc = false;
+          for (int half = 0; half < 2; ++half)
+            for (int ks = 0; ks < nksP; ++ks) { umma_ss(d, il_k(half ? DSlo : DShi, ks), sw_mn(sv, ks), id_kn32, acc); acc = true; }
+          for (int c = 0; c < 3; ++c) {               // dLhat^T . G
+            const uint8_t* la = (c == 2) ? dLlo : dLhi;
+            const uint8_t* ga = (c == 1) ? Glo : Ghi;
+            for (int ks = 0; ks < nksT; ++ks) umma_ss(d, il_mn(la, ks, 0), il_mn(ga, ks, 0), id_nn32, true);
+          }
+        }
+        umma_commit(out_full + buf);
+        umma_commit(gs_free4);
+        umma_commit(empty + slot);
+      }
+    }
+  } else {
+    // =============================== epilogue (4 warps, thread = TMEM lane) ===============================
+    const int q = warp & 3;
+    const int row = 32 * q + lane;
+    const uint32_t trow = tmem + ((uint32_t)(32 * q) << 16);
+    const bool valid = row < T && msk[row < NT ? row : 0] != 0.f;
+    const float il = (row < NT) ? iln[row] : 0.f;
+    const float c_r = p.coef[0], c_c = p.coef[1];
+
+    // ---- phase 1: S -> W, row stats
+    mbar_wait(s_full, 0);
+    tc_fence_after();
+    float mn = CUDART_INF_F, mx = -CUDART_INF_F;
+    int imn = 0, imx = 0;
+    for (int c0 = 0; c0 < NP; c0 += 32) {
+      float x[32];
+      const int n = min(32, NP - c0);
+      tmem_ld_chunk(trow + cS + c0, n, x);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        if (j < n && c0 + j < P) {
+          const float s = x[j] * il * ivn[c0 + j];
+          if (s < mn) { mn = s; imn = c0 + j; }
+          if (s > mx) { mx = s; imx = c0 + j; }
+        }
+      }
+    }
+    const float rng = mx - mn + kTcMinMaxEps;
+    float sum = 0.f;
+    for (int c0 = 0; c0 < NP; c0 += 32) {
+      float x[32];
+      const int n = min(32, NP - c0);
+      tmem_ld_chunk(trow + cS + c0, n, x);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        if (j < n && c0 + j < P) {
+          const float nn = (x[j] * il * ivn[c0 + j] - mn) / rng;
+          sum += (nn < p.thr) ? 0.f : nn;
+        }
+      }
+    }
+    const float sigma = fmaxf(sum, kTcClampEps);
+    for (int c0 = 0; c0 < NP; c0 += 32) {
+      float x[32];
+      const int n = min(32, NP - c0);
+      tmem_ld_chunk(trow + cS + c0, n, x);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        float w = 0.f;
+        if (j < n && c0 + j < P && valid) {
+          const float nn = (x[j] * il * ivn[c0 + j] - mn) / rng;
+          w = ((nn < p.thr) ? 0.f : nn) / sigma;
+        }
+        x[j] = w;
+      }
+      if (row < NT) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g)
+          if (g * 8 < n) {
+            uint4 hi, lo;
+            split_bf16x8(x + 8 * g, hi, lo);
+            const uint32_t off = il_offset(NT, row, c0 + 8 * g);
+            *reinterpret_cast<uint4*>(Whi + off) = hi;
+            *reinterpret_cast<uint4*>(Wlo + off) = lo;
+          }
+      }
+    }
+    tc_fence_before();
+    fence_proxy_async();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(w_ready);
+
+    // ---- pass 2 epilogue: G_kb -> ||G||^2 and the A operand of the logits MMA
+    float gn2 = 0.f;
+    for (int kb = 0; kb < KB; ++kb) {
+      const int buf = kb & 1;
+      mbar_wait(g_full2 + buf, (kb >> 1) & 1);
+      tc_fence_after();
+      float x[32];
+      tmem_ld32(trow + cG + 32 * buf, x);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(g_free2 + buf);
+      mbar_wait(gs_free2 + buf, ((kb >> 1) & 1) ^ 1);
+      if (row < NT) {
+        uint8_t* gh = Gb + (size_t)(2 * buf) * L.g_bytes;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          float y[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { y[j] = valid ? x[8 * g + j] : 0.f; gn2 = fmaf(y[j], y[j], gn2); }
+          uint4 hi, lo;
+          split_bf16x8(y, hi, lo);
+          const uint32_t off = il_offset(NT, row, 8 * g);
+          *reinterpret_cast<uint4*>(gh + off) = hi;
+          *reinterpret_cast<uint4*>(gh + L.g_bytes + off) = lo;
+        }
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(gs_ready2 + buf);
+    }
+    const float gnc = fmaxf(sqrtf(gn2), kTcNormEps);
+    const float ign = 1.f / gnc;
+
+    // ---- phase 3: L -> dLhat (hi/lo), gdot_i, ldotL_j        (scratch aliases the dShat region)
+    mbar_wait(l_full, 0);
+    tc_fence_after();
+    float* Sc = reinterpret_cast<float*>(DShi);         // [T][NT+1] products dL_ij * L_ij
+    const int ldl = NT + 1;
+    float gdot = 0.f;
+    const float lr = (row < NT) ? lser[row] : 0.f;
+    for (int c0 = 0; c0 < NT; c0 += 16) {
+      float x[16];
+      tmem_ld_chunk(trow + cL + c0, 16, x);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const int col = c0 + j;
+        float o = 0.f, pr = 0.f;
+        if (valid && col < T && msk[col] != 0.f) {
+          const float den = ign * iln[col];
+          const float y = p.scale * (x[j] * den);
+          float g = c_r * expf(y - lr) + c_c * expf(y - lsec[col]);
+          if (col == row) g -= (c_r + c_c);
+          pr = g * y;
+          o = p.scale * g * den;
+        }
+        gdot += pr;
+        if (row < T) Sc[row * ldl + col] = pr;
+        x[j] = o;
+      }
+      if (row < NT) {
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+          uint4 hi, lo;
+          split_bf16x8(x + 8 * g, hi, lo);
+          const uint32_t off = il_offset(NT, row, c0 + 8 * g);
+          *reinterpret_cast<uint4*>(dLhi + off) = hi;
+          *reinterpret_cast<uint4*>(dLlo + off) = lo;
+        }
+      }
+    }
+    const float gfac = gdot * ign * ign;                // (g^_i . dg^_i) / ||G_i||^2
+    epi_bar_sync();
+    float ldl_j = 0.f;
+    if (row < T) for (int i = 0; i < T; ++i) ldl_j += Sc[i * ldl + row];
+    epi_bar_sync();                                     // scratch reads done before dShat is written later
+    tc_fence_before();
+    fence_proxy_async();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(dl_ready);
+
+    // ---- pass 3 epilogue: dG_kb = (X_kb - G_kb gfac) -> A operand of the dW MMA
+    for (int kb = 0; kb < KB; ++kb) {
+      const int buf = kb & 1;
+      mbar_wait(g_full3 + buf, (kb >> 1) & 1);
+      tc_fence_after();
+      float x[32], gx[32];
+      tmem_ld32(trow + cG + 32 * buf, gx);
+      tmem_ld32(trow + cX + 32 * buf, x);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(g_free3 + buf);
+      mbar_wait(dg_free3 + buf, ((kb >> 1) & 1) ^ 1);
+      if (row < NT) {
+        uint8_t* gh = Gb + (size_t)(2 * buf) * L.g_bytes;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          float y[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) y[j] = valid ? fmaf(-gx[8 * g + j], gfac, x[8 * g + j]) : 0.f;
+          uint4 hi, lo;
+          split_bf16x8(y, hi, lo);
+          const uint32_t off = il_offset(NT, row, 8 * g);
+          *reinterpret_cast<uint4*>(gh + off) = hi;
+          *reinterpret_cast<uint4*>(gh + L.g_bytes + off) = lo;
+        }
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(dg_ready3 + buf);
+    }
+
+    // ---- phase 5: dW -> dShat (hi/lo), sdot_t, vdot_p          (renorm / threshold / min-max backward)
+    mbar_wait(dw_full, 0);
+    tc_fence_after();
+    auto load_w8 = [&](int c, float* w) {               // this row's W[c .. c+8) = hi + lo
+      float h[8], l8[8];
+      const uint32_t off = il_offset(NT, row < NT ? row : 0, c);
+      unpack_bf16x8(*reinterpret_cast<const uint4*>(Whi + off), h);
+      unpack_bf16x8(*reinterpret_cast<const uint4*>(Wlo + off), l8);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) w[j] = h[j] + l8[j];
+    };
+    float wdot = 0.f;
+    for (int c0 = 0; c0 < NP; c0 += 32) {
+      float x[32];
+      const int n = min(32, NP - c0);
+      tmem_ld_chunk(trow + cS + c0, n, x);
+#pragma unroll
+      for (int g = 0; g < 4; ++g)
+        if (g * 8 < n) {
+          float w[8];
+          load_w8(c0 + 8 * g, w);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) wdot = fmaf(w[j], x[8 * g + j], wdot);
+        }
+    }
+    float a1 = 0.f, a2 = 0.f;
+    for (int c0 = 0; c0 < NP; c0 += 32) {
+      float x[32];
+      const int n = min(32, NP - c0);
+      tmem_ld_chunk(trow + cS + c0, n, x);
+#pragma unroll
+      for (int g = 0; g < 4; ++g)
+        if (g * 8 < n) {
+          float w[8];
+          load_w8(c0 + 8 * g, w);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const bool kept = (p.thr <= 0.f) || (w[j] > 0.f);
+            const float dn = (kept && c0 + 8 * g + j < P) ? (x[8 * g + j] - wdot) / sigma : 0.f;
+            const float nn = w[j] * sigma;
+            a1 = fmaf(dn, nn - 1.f, a1);
+            a2 = fmaf(dn, nn, a2);
+          }
+        }
+    }
+    const float dmn = a1 / rng, dmx = -a2 / rng;
+    float sdot = 0.f;
+    for (int c0 = 0; c0 < NP; c0 += 32) {
+      float x[32], pr[32];
+      const int n = min(32, NP - c0);
+      tmem_ld_chunk(trow + cS + c0, n, x);
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        if (g * 8 < n) {
+          float w[8];
+          load_w8(c0 + 8 * g, w);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int pc = c0 + 8 * g + j;
+            float o = 0.f, prod = 0.f;
+            if (valid && pc < P) {
+              const bool kept = (p.thr <= 0.f) || (w[j] > 0.f);
+              float ds = kept ? ((x[8 * g + j] - wdot) / sigma) / rng : 0.f;
+              if (pc == imn) ds += dmn;
+              if (pc == imx) ds += dmx;
+              const float s = kept ? fmaf(w[j] * sigma, rng, mn) : mn;
+              prod = ds * s;
+              o = ds * il * ivn[pc];
+            }
+            sdot += prod;
+            pr[8 * g + j] = prod;
+            x[8 * g + j] = o;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) pr[8 * g + j] = 0.f;
+        }
+      }
+      if (row < NT) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g)
+          if (g * 8 < n) {
+            uint4 hi, lo;
+            split_bf16x8(x + 8 * g, hi, lo);
+            const uint32_t off = il_offset(NT, row, c0 + 8 * g);
+            *reinterpret_cast<uint4*>(DShi + off) = hi;
+            *reinterpret_cast<uint4*>(DSlo + off) = lo;
+          }
+      }
+      // column sums over this warp's 32 rows, one shared-memory atomic per column per warp
+      float mine = 0.f;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const float s = warp_sum(pr[j]);
+        if (lane == j) mine = s;
+      }
+      if (c0 + lane < NP) atomicAdd(vdot + c0 + lane, mine);
+    }
+    const float lfac = (sdot + ldl_j) * il * il;        // (l^_t . dl^_t) / ||l_t||^2
+    epi_bar_sync();
+    for (int i = threadIdx.x - 64; i < NP; i += 128) vdot[i] = vdot[i] * ivn[i] * ivn[i];   // -> vfac_p
+    epi_bar_sync();
+    tc_fence_before();
+    fence_proxy_async();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(ds_ready);
+
+    // ---- pass 4 epilogue: operands G_kb, dG_kb (hi/lo) -> smem; outputs dv_kb, dl_kb -> global
+    float cnt = 0.f;
+    for (int t = 0; t < T; ++t) cnt += msk[t];
+    const float invc = 1.f / fmaxf(cnt, kTcClampEps), invP = 1.f / (float)P;
+    const float mrow = (row < NT) ? msk[row] : 0.f;
+    auto output = [&](int kb) {
+      const int buf = kb & 1, d0 = kb * 32;
+      mbar_wait(out_full + buf, (kb >> 1) & 1);
+      tc_fence_after();
+      float x[32];
+#pragma unroll
+      for (int m = 0; m < 2; ++m) {
+        const int pr = 128 * m + row;
+        tmem_ld32(trow + cDV + 64 * buf + 32 * m, x);
+        tmem_ld_wait();
+        if (pr < P) {
+          const bf16* vsrc = p.v + ((size_t)b * P + pr) * D + d0;
+          bf16* dst = p.dv + ((size_t)b * P + pr) * D + d0;
+          const float vf = vdot[pr];
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            float vv[8], o[8];
+            unpack_bf16x8(__ldg(reinterpret_cast<const uint4*>(vsrc) + g), vv);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              o[j] = fmaf(-vv[j], vf, x[8 * g + j]);
+              if (p.dpool_v) o[j] = fmaf(__ldg(p.dpool_v + (size_t)b * D + d0 + 8 * g + j), invP, o[j]);
+            }
+            reinterpret_cast<uint4*>(dst)[g] = pack_bf16x8(o);
+          }
+        }
+      }
+      tmem_ld32(trow + cDL + 32 * buf, x);
+      tmem_ld_wait();
+      if (row < T) {
+        const bf16* lsrc = p.l + ((size_t)b * T + row) * D + d0;
+        bf16* dst = p.dl + ((size_t)b * T + row) * D + d0;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          float lv[8], o[8];
+          unpack_bf16x8(__ldg(reinterpret_cast<const uint4*>(lsrc) + g), lv);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            o[j] = fmaf(-lv[j], lfac, x[8 * g + j]);
+            if (p.dpool_l) o[j] = fmaf(__ldg(p.dpool_l + (size_t)b * D + d0 + 8 * g + j) * mrow, invc, o[j]);
+          }
+          reinterpret_cast<uint4*>(dst)[g] = pack_bf16x8(o);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(out_free + buf);
+    };
+    for (int kb = 0; kb < KB; ++kb) {
+      const int buf = kb & 1;
+      mbar_wait(g_full4 + buf, (kb >> 1) & 1);
+      tc_fence_after();
+      float x[32], gx[32];
+      tmem_ld32(trow + cG + 32 * buf, gx);
+      tmem_ld32(trow + cX + 32 * buf, x);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(g_free4 + buf);
+      mbar_wait(gs_free4, (kb & 1) ^ 1);
+      if (row < NT) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          float y[8], z[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            y[j] = valid ? gx[8 * g + j] : 0.f;
+            z[j] = valid ? fmaf(-gx[8 * g + j], gfac, x[8 * g + j]) : 0.f;
+          }
+          uint4 hi, lo;
+          const uint32_t off = il_offset(NT, row, 8 * g);
+          split_bf16x8(y, hi, lo);
+          *reinterpret_cast<uint4*>(Gb + off) = hi;
+          *reinterpret_cast<uint4*>(Gb + L.g_bytes + off) = lo;
+          split_bf16x8(z, hi, lo);
+          *reinterpret_cast<uint4*>(Gb + 2 * L.g_bytes + off) = hi;
+          *reinterpret_cast<uint4*>(Gb + 3 * L.g_bytes + off) = lo;
+        }
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(gs_ready4);
+      if (kb > 0) output(kb - 1);
+    }
+    output(KB - 1);
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem, kTmemCols); }
+}
+
+static int tc_bwd_pick_stages(int P, int T, int D) {
+  for (int ns = 4; ns >= 2; --ns)
+    if (tc_bwd_layout(P, T, D, ns).total + 1024 <= 227 * 1024) return ns;
+  return 0;
+}
+
+bool sparc_tc_bwd_supported(int P, int T, int D, int dtype) {
+  if (!sparc_tc_supported(P, T, D, dtype)) return false;
+  return tc_bwd_pick_stages(P, T, D) != 0;
+}
+
+int sparc_bwd_tc_launch(const void* v, const void* l, const uint8_t* mask, int B, int P, int T, int D, float thr,
+                        float scale, const float* row_inv_norm, const float* lse_row, const float* lse_col,
+                        const float* coef, const float* dpv, const float* dpl, void* dv, void* dl, cudaStream_t st) {
+  const int NS = tc_bwd_pick_stages(P, T, D);
+  const TcBwdLayout L = tc_bwd_layout(P, T, D, NS);
+  CUtensorMap tmV, tmL;
+  int rc;
+  if ((rc = make_tmap_bf16_3d(&tmV, v, D, P, B, 32, L.NP)) != CFA_OK) return rc;
+  if ((rc = make_tmap_bf16_3d(&tmL, l, D, T, B, 32, L.NT)) != CFA_OK) return rc;
+  TcBwdParams prm{P, T, D, NS, thr, scale, mask, row_inv_norm, row_inv_norm + (size_t)B * P, lse_row, lse_col, coef,
+                  dpv, dpl, (const bf16*)v, (const bf16*)l, (bf16*)dv, (bf16*)dl};
+  const size_t smem = L.total + 1024;
+  CFA_CUDA_TRY(cudaFuncSetAttribute(sparc_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  sparc_bwd_tc_kernel<<<B, kTcThreads, smem, st>>>(tmV, tmL, prm);
+  return launch_status();
+}
+
 }  // namespace cfa
 
 using namespace cfa;
@@ -473,6 +1162,13 @@ extern "C" int cfa_sparc_path(int P, int T, int D, int dtype, int path) {
   const bool ok = sparc_tc_supported(P, T, D, dtype);
   if (path == 2) return ok ? 2 : CFA_ERR_UNSUPPORTED;
   return ok ? 2 : 1;
+}
+
+// same for the backward (the tensor-core backward needs more shared memory than the forward)
+extern "C" int cfa_sparc_bwd_path(int P, int T, int D, int dtype, int path) {
+  const int which = cfa_sparc_path(P, T, D, dtype, path);
+  if (which != 2) return which;
+  return sparc_tc_bwd_supported(P, T, D, dtype) ? 2 : 1;
 }
 
 extern "C" int cfa_sparc_fwd(const void* v, const void* l, const uint8_t* mask, int B, int P, int T, int D, int dtype,
@@ -495,7 +1191,13 @@ extern "C" int cfa_sparc_bwd(const void* v, const void* l, const uint8_t* mask, 
                              const float* lse_col, const float* coef, const float* dpooled_v, const float* dpooled_l,
                              void* dv, void* dl, int path, void* stream) {
   if (B <= 0 || P <= 0 || T <= 0 || D <= 0 || !v || !l || !mask || !coef || !dv || !dl) return CFA_ERR_BAD_ARG;
-  (void)row_inv_norm; (void)path;
+  const int which = cfa_sparc_bwd_path(P, T, D, dtype, path);
+  if (which < 0) return which;
+  if (which == 2) {
+    if (!row_inv_norm) return CFA_ERR_WORKSPACE;
+    return sparc_bwd_tc_launch(v, l, mask, B, P, T, D, thr, scale, row_inv_norm, lse_row, lse_col, coef, dpooled_v,
+                               dpooled_l, dv, dl, (cudaStream_t)stream);
+  }
   return sparc_bwd_simt(v, l, mask, B, P, T, D, dtype, thr, scale, lse_row, lse_col, coef, dpooled_v, dpooled_l, dv, dl,
                         stream);
 }

@@ -92,7 +92,7 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* r) {
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // ---------------------------------------------------------------- UMMA descriptors
-constexpr uint32_t kLayoutNone = 0, kLayoutSw128 = 2;
+constexpr uint32_t kLayoutNone = 0, kLayoutSw128 = 2, kLayoutSw64 = 4;
 
 // 64-bit shared-memory matrix descriptor (PTX ISA "tcgen05 shared memory descriptor"):
 // [0,14) start>>4, [16,30) LBO>>4, [32,46) SBO>>4, [46,48) version=1, [61,64) swizzle mode.
@@ -157,7 +157,8 @@ static inline PFN_tmapEncodeTiled get_tmap_encoder() {
   return fn;
 }
 
-// bf16 tensor [d2][d1][d0] (d0 contiguous), box [1][box1][box0], 128-byte swizzle, zero fill out of bounds.
+// bf16 tensor [d2][d1][d0] (d0 contiguous), box [1][box1][box0], zero fill out of bounds.
+// box0 = 64 elements -> 128-byte swizzle, box0 = 32 elements -> 64-byte swizzle.
 static inline int make_tmap_bf16_3d(CUtensorMap* m, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint32_t box0,
                                     uint32_t box1) {
   PFN_tmapEncodeTiled enc = get_tmap_encoder();
@@ -167,7 +168,8 @@ static inline int make_tmap_bf16_3d(CUtensorMap* m, const void* base, uint64_t d
   cuuint32_t box[3] = {box0, box1, 1};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, box0 == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? CFA_OK : CFA_ERR_BAD_ARG;
 }

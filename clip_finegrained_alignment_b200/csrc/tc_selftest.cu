@@ -33,13 +33,19 @@ tc_selftest_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   // ---- stage operands
   uint32_t tx_bytes = 0;
   if (a_mode == 0) tx_bytes += (K / 64) * 16384;
+  if (a_mode == 4) tx_bytes += (K / 32) * 8192;
   if (b_mode == 0) tx_bytes += (K / 64) * N * 128;
   if (b_mode == 1) tx_bytes += K * 128;
+  if (b_mode == 4) tx_bytes += (K / 32) * N * 64;
+  if (b_mode == 5) tx_bytes += K * 64;
   if (tid == 0 && tx_bytes) {
     mbar_expect_tx(&bar_tma, tx_bytes);
     if (a_mode == 0) for (int kb = 0; kb < K / 64; ++kb) tma_load_3d(As + kb * 16384, &tmA, &bar_tma, kb * 64, 0, 0);
     if (b_mode == 0) for (int kb = 0; kb < K / 64; ++kb) tma_load_3d(Bs + kb * N * 128, &tmB, &bar_tma, kb * 64, 0, 0);
     if (b_mode == 1) tma_load_3d(Bs, &tmB, &bar_tma, 0, 0, 0);
+    if (a_mode == 4) for (int kb = 0; kb < K / 32; ++kb) tma_load_3d(As + kb * 8192, &tmA, &bar_tma, kb * 32, 0, 0);
+    if (b_mode == 4) for (int kb = 0; kb < K / 32; ++kb) tma_load_3d(Bs + kb * N * 64, &tmB, &bar_tma, kb * 32, 0, 0);
+    if (b_mode == 5) tma_load_3d(Bs, &tmB, &bar_tma, 0, 0, 0);
   }
   if (a_mode == 1) {          // A [128 x K] -> interleaved, rows = 128
     for (int i = tid; i < 128 * K; i += 128) { const int r = i / K, k = i % K; *(bf16*)(As + il_offset(128, r, k)) = A[i]; }
@@ -58,14 +64,17 @@ tc_selftest_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 
   // ---- issue
   if (tid == 0) {
-    const uint32_t idesc = make_idesc_bf16(128, N, a_mode == 2, b_mode == 1 || b_mode == 3);
+    const uint32_t idesc = make_idesc_bf16(128, N, a_mode == 2, b_mode == 1 || b_mode == 3 || b_mode == 5);
     for (int ks = 0; ks < K / 16; ++ks) {
       uint64_t da, db;
       if (a_mode == 0) da = make_smem_desc(smem_u32(As) + (ks >> 2) * 16384 + (ks & 3) * 32, 16, 1024, kLayoutSw128);
+      else if (a_mode == 4) da = make_smem_desc(smem_u32(As) + (ks >> 1) * 8192 + (ks & 1) * 32, 16, 512, kLayoutSw64);
       else if (a_mode == 1) da = make_smem_desc(smem_u32(As) + ks * 2 * (128 * 16), 128 * 16, 128, kLayoutNone);
       else da = make_smem_desc(smem_u32(As) + ks * 256, 128, K * 16, kLayoutNone);
       if (b_mode == 0) db = make_smem_desc(smem_u32(Bs) + (ks >> 2) * N * 128 + (ks & 3) * 32, 16, 1024, kLayoutSw128);
       else if (b_mode == 1) db = make_smem_desc(smem_u32(Bs) + ks * 2048, 16, 1024, kLayoutSw128);
+      else if (b_mode == 4) db = make_smem_desc(smem_u32(Bs) + (ks >> 1) * N * 64 + (ks & 1) * 32, 16, 512, kLayoutSw64);
+      else if (b_mode == 5) db = make_smem_desc(smem_u32(Bs) + ks * 1024, 16, 512, kLayoutSw64);
       else if (b_mode == 2) db = make_smem_desc(smem_u32(Bs) + ks * 2 * (N * 16), N * 16, 128, kLayoutNone);
       else db = make_smem_desc(smem_u32(Bs) + ks * 256, 128, K * 16, kLayoutNone);
       umma_ss(tmem, da, db, idesc, ks > 0);
@@ -96,7 +105,9 @@ using namespace cfa;
 extern "C" int cfa_tc_selftest(int a_mode, int b_mode, int N, int K, const void* A, const void* B, float* D, void* stream) {
   if (N % 16 || N < 16 || N > 256 || K % 16 || K < 16 || K > 256) return CFA_ERR_BAD_ARG;
   if ((a_mode == 0 || b_mode == 0) && K % 64) return CFA_ERR_BAD_ARG;
+  if ((a_mode == 4 || b_mode == 4) && K % 32) return CFA_ERR_BAD_ARG;
   if (b_mode == 1 && N != 64) return CFA_ERR_BAD_ARG;
+  if (b_mode == 5 && N != 32) return CFA_ERR_BAD_ARG;
   CUtensorMap tmA, tmB;
   memset(&tmA, 0, sizeof(tmA));
   memset(&tmB, 0, sizeof(tmB));
@@ -104,6 +115,9 @@ extern "C" int cfa_tc_selftest(int a_mode, int b_mode, int N, int K, const void*
   if (a_mode == 0 && (rc = make_tmap_bf16_3d(&tmA, A, K, 128, 1, 64, 128)) != CFA_OK) return rc;
   if (b_mode == 0 && (rc = make_tmap_bf16_3d(&tmB, B, K, N, 1, 64, N)) != CFA_OK) return rc;
   if (b_mode == 1 && (rc = make_tmap_bf16_3d(&tmB, B, 64, K, 1, 64, K)) != CFA_OK) return rc;
+  if (a_mode == 4 && (rc = make_tmap_bf16_3d(&tmA, A, K, 128, 1, 32, 128)) != CFA_OK) return rc;
+  if (b_mode == 4 && (rc = make_tmap_bf16_3d(&tmB, B, K, N, 1, 32, N)) != CFA_OK) return rc;
+  if (b_mode == 5 && (rc = make_tmap_bf16_3d(&tmB, B, 32, K, 1, 32, K)) != CFA_OK) return rc;
   const size_t smem = 2 * 65536 + 1024;
   CFA_CUDA_TRY(cudaFuncSetAttribute(tc_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   tc_selftest_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(tmA, tmB, (const bf16*)A, (const bf16*)B, D, a_mode, b_mode, N, K);

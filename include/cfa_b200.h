@@ -143,6 +143,7 @@ int cfa_sparc_bwd(const void* v, const void* l, const uint8_t* mask, int B, int 
                   const float* coef, const float* dpooled_v, const float* dpooled_l, void* dv, void* dl, int path,
                   void* stream);
 int cfa_sparc_path(int P, int T, int D, int dtype, int path);
+int cfa_sparc_bwd_path(int P, int T, int D, int dtype, int path);   /* backward: tensor cores need P <= ~224 at T = 77 */
 
 /* largest P the SPARC kernels accept for a given T (shared-memory residency of the T x P tiles) */
 int cfa_sparc_max_patches(int T, int backward);

@@ -13,7 +13,7 @@ def _run(a_mode, b_mode, N, K):
     B = torch.randn(N, K, generator=g).to(torch.bfloat16)            # logical B[n, k]
     ref = A.float() @ B.float().t()
     a_src = (A.t().contiguous() if a_mode == 2 else A).cuda()
-    b_src = (B.t().contiguous() if b_mode in (1, 3) else B).cuda()
+    b_src = (B.t().contiguous() if b_mode in (1, 3, 5) else B).cuda()
     D = torch.full((128, N), float("nan"), device="cuda")
     _lib.call("cfa_tc_selftest", a_mode, b_mode, N, K, a_src.data_ptr(), b_src.data_ptr(), D.data_ptr(),
               _lib.stream_ptr())
@@ -31,6 +31,13 @@ def _run(a_mode, b_mode, N, K):
     (2, 3, 64, 80),      # both interleaved, both MN-major                (dv_kb += W^T . dG_kb)
     (1, 2, 96, 64),
     (1, 3, 64, 208),     # interleaved K-major A x interleaved MN-major B (dl_kb += dL^T . G_kb uses a_mode 2)
+    (4, 4, 208, 64),     # 32-wide blocks, SWIZZLE_64B tiles (backward kernel): S
+    (4, 4, 80, 96),
+    (1, 4, 208, 32),     # dW += dG_kb . v_kb^T
+    (1, 5, 32, 208),     # G_kb = W . v_kb ; dl_kb = dS . v_kb
+    (1, 5, 32, 80),      # X_kb = dL . l_kb
+    (2, 5, 32, 80),      # dv_kb = dS^T . l_kb
+    (2, 3, 32, 80),      # dv_kb += W^T . dG_kb ; dl_kb += dL^T . G_kb
 ])
 def test_tcgen05_operand_modes(a_mode, b_mode, N, K):
     D, ref = _run(a_mode, b_mode, N, K)
