@@ -41,7 +41,7 @@ __host__ __device__ inline TcLayout tc_fwd_layout(int P, int T, int D, int NS) {
   const uint32_t lb_bytes = (uint32_t)L.NT * (L.NT + 1) * 4;      // fp32 logits scratch aliases the W region
   L.off_g = L.off_w + ((2 * L.w_bytes > lb_bytes ? 2 * L.w_bytes : lb_bytes) + 1023 & ~1023u);
   L.off_f = L.off_g + 4 * L.g_bytes + 1024;         // +1 KB: phantom rows of the last interleaved chunk stay in bounds
-  L.off_bar = L.off_f + 4 * (L.NP + 3 * L.NT + 32);
+  L.off_bar = L.off_f + 4 * ((L.NP + 32) + 3 * L.NT + 32);
   L.off_bar = (L.off_bar + 7) & ~7u;
   L.total = L.off_bar + 8 * (2 * L.NS + 12) + 16;
   return L;
@@ -154,8 +154,8 @@ sparc_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_consta
   uint8_t* Whi = base + L.off_w;
   uint8_t* Wlo = Whi + L.w_bytes;
   uint8_t* Gs = base + L.off_g;                       // [buf][hi|lo][g_bytes]
-  float* ivn = (float*)(base + L.off_f);              // [NP]
-  float* iln = ivn + NP;                              // [NT]
+  float* ivn = (float*)(base + L.off_f);              // [NP + 32], zero beyond P
+  float* iln = ivn + NP + 32;                         // [NT]
   float* msk = iln + NT;                              // [NT]
   float* gnorm = msk + NT;                            // [NT]
   float* red = gnorm + NT;                            // [32]
@@ -180,10 +180,10 @@ sparc_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_consta
     tma_prefetch_desc(&tmL);
   }
   if (warp == 1) tmem_alloc(tmem_slot, kTmemCols);
-  for (int i = threadIdx.x; i < NP + 2 * NT; i += kTcThreads) {
-    if (i < NP) ivn[i] = (i < P) ? p.inv_vn[(size_t)b * P + i] : 0.f;
-    else if (i < NP + NT) { const int t = i - NP; iln[t] = (t < T) ? p.inv_ln[(size_t)b * T + t] : 0.f; }
-    else { const int t = i - NP - NT; msk[t] = (t < T && p.mask[(size_t)b * T + t]) ? 1.f : 0.f; }
+  for (int i = threadIdx.x; i < NP + 32 + 2 * NT; i += kTcThreads) {
+    if (i < NP + 32) ivn[i] = (i < P) ? p.inv_vn[(size_t)b * P + i] : 0.f;
+    else if (i < NP + 32 + NT) { const int t = i - NP - 32; iln[t] = (t < T) ? p.inv_ln[(size_t)b * T + t] : 0.f; }
+    else { const int t = i - NP - 32 - NT; msk[t] = (t < T && p.mask[(size_t)b * T + t]) ? 1.f : 0.f; }
   }
   tc_fence_before();
   __syncthreads();
@@ -271,54 +271,48 @@ sparc_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_consta
     const bool valid = row < T && msk[row < NT ? row : 0] != 0.f;
     const float il = (row < NT) ? iln[row] : 0.f;
 
-    // ---- epilogue 1: S -> W
+    // ---- epilogue 1: S -> W   (branch-free; columns >= P are masked with selects, never with control flow)
     mbar_wait(s_full, 0);
     tc_fence_after();
     float mn = CUDART_INF_F, mx = -CUDART_INF_F;
     for (int c0 = 0; c0 < NP; c0 += 32) {
       float x[32];
-      const int n = min(32, NP - c0);
-      tmem_ld_chunk(trow + c0, n, x);
+      tmem_ld32(trow + c0, x);
+      tmem_ld_wait();
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
-        if (j < n && c0 + j < P) {
-          const float s = x[j] * il * ivn[c0 + j];
-          mn = fminf(mn, s); mx = fmaxf(mx, s);
-        }
+        const float s = x[j] * il * ivn[c0 + j];
+        const bool in = c0 + j < P;
+        mn = fminf(mn, in ? s : CUDART_INF_F);
+        mx = fmaxf(mx, in ? s : -CUDART_INF_F);
       }
     }
-    const float rng = mx - mn + kTcMinMaxEps;
+    const float inv_rng = 1.f / (mx - mn + kTcMinMaxEps);
     float sum = 0.f;
     for (int c0 = 0; c0 < NP; c0 += 32) {
       float x[32];
-      const int n = min(32, NP - c0);
-      tmem_ld_chunk(trow + c0, n, x);
+      tmem_ld32(trow + c0, x);
+      tmem_ld_wait();
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
-        if (j < n && c0 + j < P) {
-          const float nn = (x[j] * il * ivn[c0 + j] - mn) / rng;
-          sum += (nn < p.thr) ? 0.f : nn;
-        }
+        const float nn = (x[j] * il * ivn[c0 + j] - mn) * inv_rng;
+        sum += (c0 + j < P && !(nn < p.thr)) ? nn : 0.f;
       }
     }
-    const float sigma = fmaxf(sum, kTcClampEps);
+    const float inv_sigma = valid ? 1.f / fmaxf(sum, kTcClampEps) : 0.f;
     for (int c0 = 0; c0 < NP; c0 += 32) {
       float x[32];
-      const int n = min(32, NP - c0);
-      tmem_ld_chunk(trow + c0, n, x);
+      tmem_ld32(trow + c0, x);
+      tmem_ld_wait();
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
-        float w = 0.f;
-        if (j < n && c0 + j < P && valid) {
-          const float nn = (x[j] * il * ivn[c0 + j] - mn) / rng;
-          w = ((nn < p.thr) ? 0.f : nn) / sigma;
-        }
-        x[j] = w;
+        const float nn = (x[j] * il * ivn[c0 + j] - mn) * inv_rng;
+        x[j] = (valid && c0 + j < P && !(nn < p.thr)) ? nn * inv_sigma : 0.f;
       }
       if (row < NT) {
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
-          if (g * 8 < n) {
+          if (c0 + 8 * g < NP) {
             uint4 hi, lo;
             split_bf16x8(x + 8 * g, hi, lo);
             const uint32_t off = il_offset(NT, row, c0 + 8 * g);
@@ -374,13 +368,14 @@ sparc_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_consta
     float* Lb = reinterpret_cast<float*>(Whi);          // [T][NT+1]
     const int ldl = NT + 1;
     float rmax = -CUDART_INF_F;
+    const float sc_row = valid ? p.scale * ign : 0.f;
     for (int c0 = 0; c0 < NT; c0 += 16) {
       float x[16];
       tmem_ld_chunk(trow + kTmemL + c0, 16, x);
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
         const int col = c0 + j;
-        const float y = (valid && col < T && msk[col] != 0.f) ? p.scale * (x[j] * ign * iln[col]) : -CUDART_INF_F;
+        const float y = (valid && msk[col] != 0.f) ? x[j] * sc_row * iln[col] : -CUDART_INF_F;   // msk/iln are 0 beyond T
         if (row < T) Lb[row * ldl + col] = y;
         rmax = fmaxf(rmax, y);
       }
@@ -492,7 +487,7 @@ __host__ __device__ inline TcBwdLayout tc_bwd_layout(int P, int T, int D, int NS
   L.off_dl = L.off_w + 2 * L.w_bytes + (2 * L.w_bytes > sc_bytes ? 2 * L.w_bytes : ((sc_bytes + 15) & ~15u));   // dLhi, dLlo
   L.off_g = L.off_dl + 2 * L.dl_bytes;                // 4 operand buffers of g_bytes
   L.off_f = L.off_g + 4 * L.g_bytes + 1024;           // phantom rows of the last buffer stay in bounds
-  L.off_bar = (L.off_f + 4 * (2 * L.NP + 5 * L.NT + 32) + 7) & ~7u;
+  L.off_bar = (L.off_f + 4 * (2 * (L.NP + 32) + 5 * L.NT + 32) + 7) & ~7u;
   L.total = L.off_bar + 8 * (2 * L.NS + 34) + 16;
   return L;
 }
@@ -547,9 +542,9 @@ sparc_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_consta
   uint8_t* dLhi = base + L.off_dl;
   uint8_t* dLlo = dLhi + L.dl_bytes;
   uint8_t* Gb = base + L.off_g;                        // 4 x g_bytes
-  float* ivn = (float*)(base + L.off_f);               // [NP]
-  float* vdot = ivn + NP;                              // [NP]  -> vfac
-  float* iln = vdot + NP;                              // [NT]
+  float* ivn = (float*)(base + L.off_f);               // [NP + 32], zero beyond P
+  float* vdot = ivn + NP + 32;                         // [NP + 32]  -> vfac
+  float* iln = vdot + NP + 32;                         // [NT]
   float* msk = iln + NT;                               // [NT]
   float* lser = msk + NT;                              // [NT]
   float* lsec = lser + NT;                             // [NT]
@@ -581,11 +576,11 @@ sparc_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_consta
     tma_prefetch_desc(&tmL);
   }
   if (warp == 1) tmem_alloc(tmem_slot, kTmemCols);
-  for (int i = threadIdx.x; i < 2 * NP + 5 * NT; i += kTcThreads) {
-    if (i < NP) ivn[i] = (i < P) ? p.inv_vn[(size_t)b * P + i] : 0.f;
-    else if (i < 2 * NP) vdot[i - NP] = 0.f;
+  for (int i = threadIdx.x; i < 2 * (NP + 32) + 5 * NT; i += kTcThreads) {
+    if (i < NP + 32) ivn[i] = (i < P) ? p.inv_vn[(size_t)b * P + i] : 0.f;
+    else if (i < 2 * (NP + 32)) vdot[i - NP - 32] = 0.f;
     else {
-      const int k = (i - 2 * NP) / NT, t = (i - 2 * NP) % NT;
+      const int k = (i - 2 * (NP + 32)) / NT, t = (i - 2 * (NP + 32)) % NT;
       const bool in = t < T;
       float x = 0.f;
       if (k == 0) x = in ? p.inv_ln[(size_t)b * T + t] : 0.f;
@@ -745,56 +740,52 @@ sparc_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_consta
     const float il = (row < NT) ? iln[row] : 0.f;
     const float c_r = p.coef[0], c_c = p.coef[1];
 
-    // ---- phase 1: S -> W, row stats
+    // ---- phase 1: S -> W, row stats   (branch-free)
     mbar_wait(s_full, 0);
     tc_fence_after();
     float mn = CUDART_INF_F, mx = -CUDART_INF_F;
     int imn = 0, imx = 0;
     for (int c0 = 0; c0 < NP; c0 += 32) {
       float x[32];
-      const int n = min(32, NP - c0);
-      tmem_ld_chunk(trow + cS + c0, n, x);
+      tmem_ld32(trow + cS + c0, x);
+      tmem_ld_wait();
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
-        if (j < n && c0 + j < P) {
-          const float s = x[j] * il * ivn[c0 + j];
-          if (s < mn) { mn = s; imn = c0 + j; }
-          if (s > mx) { mx = s; imx = c0 + j; }
-        }
+        const float s = x[j] * il * ivn[c0 + j];
+        const bool in = c0 + j < P;
+        const bool lt = in && s < mn, gt = in && s > mx;     // strict: first occurrence wins, like torch.min/max
+        mn = lt ? s : mn; imn = lt ? c0 + j : imn;
+        mx = gt ? s : mx; imx = gt ? c0 + j : imx;
       }
     }
     const float rng = mx - mn + kTcMinMaxEps;
+    const float inv_rng = 1.f / rng;
     float sum = 0.f;
     for (int c0 = 0; c0 < NP; c0 += 32) {
       float x[32];
-      const int n = min(32, NP - c0);
-      tmem_ld_chunk(trow + cS + c0, n, x);
+      tmem_ld32(trow + cS + c0, x);
+      tmem_ld_wait();
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
-        if (j < n && c0 + j < P) {
-          const float nn = (x[j] * il * ivn[c0 + j] - mn) / rng;
-          sum += (nn < p.thr) ? 0.f : nn;
-        }
+        const float nn = (x[j] * il * ivn[c0 + j] - mn) * inv_rng;
+        sum += (c0 + j < P && !(nn < p.thr)) ? nn : 0.f;
       }
     }
     const float sigma = fmaxf(sum, kTcClampEps);
+    const float inv_sigma = valid ? 1.f / sigma : 0.f;
     for (int c0 = 0; c0 < NP; c0 += 32) {
       float x[32];
-      const int n = min(32, NP - c0);
-      tmem_ld_chunk(trow + cS + c0, n, x);
+      tmem_ld32(trow + cS + c0, x);
+      tmem_ld_wait();
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
-        float w = 0.f;
-        if (j < n && c0 + j < P && valid) {
-          const float nn = (x[j] * il * ivn[c0 + j] - mn) / rng;
-          w = ((nn < p.thr) ? 0.f : nn) / sigma;
-        }
-        x[j] = w;
+        const float nn = (x[j] * il * ivn[c0 + j] - mn) * inv_rng;
+        x[j] = (valid && c0 + j < P && !(nn < p.thr)) ? nn * inv_sigma : 0.f;
       }
       if (row < NT) {
 #pragma unroll
         for (int g = 0; g < 4; ++g)
-          if (g * 8 < n) {
+          if (c0 + 8 * g < NP) {
             uint4 hi, lo;
             split_bf16x8(x + 8 * g, hi, lo);
             const uint32_t off = il_offset(NT, row, c0 + 8 * g);
@@ -855,18 +846,16 @@ sparc_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_consta
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
         const int col = c0 + j;
-        float o = 0.f, pr = 0.f;
-        if (valid && col < T && msk[col] != 0.f) {
-          const float den = ign * iln[col];
-          const float y = p.scale * (x[j] * den);
-          float g = c_r * expf(y - lr) + c_c * expf(y - lsec[col]);
-          if (col == row) g -= (c_r + c_c);
-          pr = g * y;
-          o = p.scale * g * den;
-        }
+        const bool on = valid && msk[col] != 0.f;            // msk / iln are 0 beyond T
+        const float den = ign * iln[col];
+        const float y = p.scale * (x[j] * den);
+        float g = c_r * __expf(fminf(y - lr, 0.f)) + c_c * __expf(fminf(y - lsec[col], 0.f));
+        g -= (col == row) ? (c_r + c_c) : 0.f;
+        g = on ? g : 0.f;
+        const float pr = on ? g * y : 0.f;
         gdot += pr;
         if (row < T) Sc[row * ldl + col] = pr;
-        x[j] = o;
+        x[j] = p.scale * g * den;
       }
       if (row < NT) {
 #pragma unroll
@@ -935,64 +924,63 @@ sparc_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_consta
     float wdot = 0.f;
     for (int c0 = 0; c0 < NP; c0 += 32) {
       float x[32];
-      const int n = min(32, NP - c0);
-      tmem_ld_chunk(trow + cS + c0, n, x);
+      tmem_ld32(trow + cS + c0, x);
+      tmem_ld_wait();
 #pragma unroll
       for (int g = 0; g < 4; ++g)
-        if (g * 8 < n) {
+        if (c0 + 8 * g < NP) {
           float w[8];
           load_w8(c0 + 8 * g, w);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) wdot = fmaf(w[j], x[8 * g + j], wdot);
+          for (int j = 0; j < 8; ++j) wdot = fmaf(w[j], x[8 * g + j], wdot);     // W is 0 beyond P and on masked rows
         }
     }
+    const float isg = 1.f / sigma;
+    const bool keep_all = p.thr <= 0.f;
     float a1 = 0.f, a2 = 0.f;
     for (int c0 = 0; c0 < NP; c0 += 32) {
       float x[32];
-      const int n = min(32, NP - c0);
-      tmem_ld_chunk(trow + cS + c0, n, x);
+      tmem_ld32(trow + cS + c0, x);
+      tmem_ld_wait();
 #pragma unroll
       for (int g = 0; g < 4; ++g)
-        if (g * 8 < n) {
+        if (c0 + 8 * g < NP) {
           float w[8];
           load_w8(c0 + 8 * g, w);
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            const bool kept = (p.thr <= 0.f) || (w[j] > 0.f);
-            const float dn = (kept && c0 + 8 * g + j < P) ? (x[8 * g + j] - wdot) / sigma : 0.f;
+            const bool kept = (keep_all || w[j] > 0.f) && (c0 + 8 * g + j < P);
+            const float dn = kept ? (x[8 * g + j] - wdot) * isg : 0.f;
             const float nn = w[j] * sigma;
             a1 = fmaf(dn, nn - 1.f, a1);
             a2 = fmaf(dn, nn, a2);
           }
         }
     }
-    const float dmn = a1 / rng, dmx = -a2 / rng;
+    const float dmn = a1 * inv_rng, dmx = -a2 * inv_rng;
     float sdot = 0.f;
     for (int c0 = 0; c0 < NP; c0 += 32) {
       float x[32], pr[32];
-      const int n = min(32, NP - c0);
-      tmem_ld_chunk(trow + cS + c0, n, x);
+      tmem_ld32(trow + cS + c0, x);
+      tmem_ld_wait();
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
-        if (g * 8 < n) {
+        if (c0 + 8 * g < NP) {
           float w[8];
           load_w8(c0 + 8 * g, w);
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const int pc = c0 + 8 * g + j;
-            float o = 0.f, prod = 0.f;
-            if (valid && pc < P) {
-              const bool kept = (p.thr <= 0.f) || (w[j] > 0.f);
-              float ds = kept ? ((x[8 * g + j] - wdot) / sigma) / rng : 0.f;
-              if (pc == imn) ds += dmn;
-              if (pc == imx) ds += dmx;
-              const float s = kept ? fmaf(w[j] * sigma, rng, mn) : mn;
-              prod = ds * s;
-              o = ds * il * ivn[pc];
-            }
+            const bool kept = (keep_all || w[j] > 0.f) && pc < P;
+            float ds = kept ? ((x[8 * g + j] - wdot) * isg) * inv_rng : 0.f;
+            ds += (pc == imn) ? dmn : 0.f;
+            ds += (pc == imx) ? dmx : 0.f;
+            ds = (valid && pc < P) ? ds : 0.f;
+            const float sv = kept ? fmaf(w[j] * sigma, rng, mn) : mn;            // only read where ds != 0
+            const float prod = (valid && pc < P) ? ds * sv : 0.f;   // phantom rows may hold NaN/Inf: select, never 0*x
             sdot += prod;
             pr[8 * g + j] = prod;
-            x[8 * g + j] = o;
+            x[8 * g + j] = (valid && pc < P) ? ds * il * ivn[pc] : 0.f;
           }
         } else {
 #pragma unroll
@@ -1002,7 +990,7 @@ sparc_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_consta
       if (row < NT) {
 #pragma unroll
         for (int g = 0; g < 4; ++g)
-          if (g * 8 < n) {
+          if (c0 + 8 * g < NP) {
             uint4 hi, lo;
             split_bf16x8(x + 8 * g, hi, lo);
             const uint32_t off = il_offset(NT, row, c0 + 8 * g);
@@ -1014,8 +1002,8 @@ sparc_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_consta
       float mine = 0.f;
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
-        const float s = warp_sum(pr[j]);
-        if (lane == j) mine = s;
+        const float cs = warp_sum(pr[j]);
+        mine = (lane == j) ? cs : mine;
       }
       if (c0 + lane < NP) atomicAdd(vdot + c0 + lane, mine);
     }
