@@ -1,0 +1,321 @@
+// Global (batch-level) InfoNCE, both directions per launch, fp32 CUDA-core tiles (losses.py:14-36, 145-163, 207-217).
+//
+// Inputs are the RAW pooled embeddings: local rows a_loc/b_loc [B,D] and the (all-gathered) columns a_all/b_all
+// [Bg,D].  L2 normalisation (F.normalize, eps) is folded into the kernels: row / column norms are accumulated
+// while the K chunks stream through shared memory and the logits tile is scaled afterwards, so there is no
+// separate normalise pass and the B x Bg logits never reach memory.
+//   direction 0: rows = a_loc, columns = b_all  (image -> text);   direction 1: rows = b_loc, columns = a_all.
+#include "common.cuh"
+#include "simt_tile.cuh"
+#include <math_constants.h>
+
+namespace cfa {
+
+constexpr int kGR = 32, kGC = 64, kGK = 32, kGLd = kGK + 1;     // forward tile: 32 rows x 64 cols, K chunks of 32
+
+__global__ void __launch_bounds__(kNT)
+global_fwd_kernel(const float* __restrict__ a_loc, const float* __restrict__ b_loc, const float* __restrict__ a_all,
+                  const float* __restrict__ b_all, int B, int Bg, int D, int col_offset, float scale, float eps,
+                  float* __restrict__ part_m, float* __restrict__ part_l, float* __restrict__ diag,
+                  float* __restrict__ norms /* [2][B] clamped row norms */) {
+  __shared__ float stA[kGR * kGLd];
+  __shared__ float stB[kGC * kGLd];
+  __shared__ float nrm[kGR + kGC];
+  const int dir = blockIdx.z, split = blockIdx.y, nsplit = gridDim.y, r0 = blockIdx.x * kGR;
+  const float* rows = dir ? b_loc : a_loc;
+  const float* cols = dir ? a_all : b_all;
+  const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
+  const int rows_valid = min(kGR, B - r0);
+  float run_m[2], run_l[2];
+#pragma unroll
+  for (int i = 0; i < 2; ++i) { run_m[i] = -CUDART_INF_F; run_l[i] = 0.f; }
+  const int ntiles = (Bg + kGC - 1) / kGC;
+  for (int ct = split; ct < ntiles; ct += nsplit) {
+    const int c0 = ct * kGC;
+    const int cols_valid = min(kGC, Bg - c0);
+    float acc[2][4];
+    tile_zero(acc);
+    float ss = 0.f;                                   // thread t < 96 owns the squared norm of one row / column
+    for (int d0 = 0; d0 < D; d0 += kGK) {
+      __syncthreads();
+      load_tile<float>(stA, kGLd, rows + (size_t)r0 * D, kGR, rows_valid, D, d0, kGK);
+      load_tile<float>(stB, kGLd, cols + (size_t)c0 * D, kGC, cols_valid, D, d0, kGK);
+      __syncthreads();
+      if (threadIdx.x < kGR + kGC) {
+        const float* src = threadIdx.x < kGR ? stA + threadIdx.x * kGLd : stB + (threadIdx.x - kGR) * kGLd;
+#pragma unroll 8
+        for (int k = 0; k < kGK; ++k) ss = fmaf(src[k], src[k], ss);
+      }
+      tile_mac<2, 4>(acc, 0, 0, kGR, kGC, kGK, [&](int m, int k) { return stA[m * kGLd + k]; },
+                     [&](int k, int n) { return stB[n * kGLd + k]; });
+    }
+    __syncthreads();
+    if (threadIdx.x < kGR + kGC) nrm[threadIdx.x] = fmaxf(sqrtf(ss), eps);
+    __syncthreads();
+    if (ct == split && split == 0 && threadIdx.x < rows_valid) norms[(size_t)dir * B + r0 + threadIdx.x] = nrm[threadIdx.x];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int m = ty + 16 * i, grow = r0 + m;
+      float v[4], tmax = -CUDART_INF_F;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int n = tx + 16 * j, gcol = c0 + n;
+        v[j] = (gcol < Bg) ? scale * (acc[i][j] / (nrm[m] * nrm[kGR + n])) : -CUDART_INF_F;
+        tmax = fmaxf(tmax, v[j]);
+        if (grow < B && gcol == col_offset + grow) diag[(size_t)dir * B + grow] = v[j];
+      }
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) tmax = fmaxf(tmax, __shfl_xor_sync(0xffffffffu, tmax, o));
+      const float new_m = fmaxf(run_m[i], tmax);
+      float s = 0.f;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) s += (v[j] == -CUDART_INF_F) ? 0.f : expf(v[j] - new_m);
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      run_l[i] = run_l[i] * ((run_m[i] == -CUDART_INF_F) ? 0.f : expf(run_m[i] - new_m)) + s;
+      run_m[i] = new_m;
+    }
+  }
+  if (tx == 0) {
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int grow = r0 + ty + 16 * i;
+      if (grow < B) {
+        part_m[((size_t)dir * nsplit + split) * B + grow] = run_m[i];
+        part_l[((size_t)dir * nsplit + split) * B + grow] = run_l[i];
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ float block_sum(float x, float* red) {
+  x = warp_sum(x);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = x;
+  __syncthreads();
+  float s = 0.f;
+  for (int k = 0; k < kNT / 32; ++k) s += red[k];
+  return s;
+}
+
+// One CTA: merge the per-split online-softmax partials -> lse[2][B], sums2 = (sum CE_a, sum CE_b) over the LOCAL rows.
+// If out8 != NULL (single process) it also performs the SPARC scalar epilogue (losses.py:163,196,217,252-264).
+__global__ void __launch_bounds__(kNT)
+global_combine_kernel(const float* __restrict__ part_m, const float* __restrict__ part_l, const float* __restrict__ diag,
+                      int B, int nsplit, float* __restrict__ lse, float* __restrict__ sums2, int global_batch,
+                      const float* __restrict__ local_partial, const uint8_t* __restrict__ mask, int T, float gw, float lw,
+                      float* __restrict__ out8) {
+  __shared__ float red[8];
+  float ce[2] = {0.f, 0.f};
+  for (int idx = threadIdx.x; idx < 2 * B; idx += kNT) {
+    const int dir = idx / B, i = idx - dir * B;
+    float M = -CUDART_INF_F;
+    for (int s = 0; s < nsplit; ++s) M = fmaxf(M, part_m[((size_t)dir * nsplit + s) * B + i]);
+    float Lsum = 0.f;
+    for (int s = 0; s < nsplit; ++s) {
+      const float m = part_m[((size_t)dir * nsplit + s) * B + i];
+      if (m != -CUDART_INF_F) Lsum += part_l[((size_t)dir * nsplit + s) * B + i] * expf(m - M);
+    }
+    const float x = M + logf(Lsum);
+    lse[idx] = x;
+    ce[dir] += x - diag[idx];
+  }
+  const float sa = block_sum(ce[0], red), sb = block_sum(ce[1], red);
+  if (threadIdx.x == 0) { sums2[0] = sa; sums2[1] = sb; }
+  if (out8) {
+    float nv = 0.f, a = 0.f, c = 0.f;
+    const int nb = (int)((size_t)global_batch);     // single process: global_batch == B
+    for (int i = threadIdx.x; i < nb * T; i += kNT) nv += mask[i] ? 1.f : 0.f;
+    for (int i = threadIdx.x; i < nb; i += kNT) { a += local_partial[2 * i]; c += local_partial[2 * i + 1]; }
+    nv = block_sum(nv, red); a = block_sum(a, red); c = block_sum(c, red);
+    if (threadIdx.x == 0) {
+      const float n_valid = nv + 1e-8f;               // evaluated in fp32 like the reference (losses.py:196)
+      const float vl = sa / (float)global_batch, lv = sb / (float)global_batch;
+      const float vll = a / n_valid, lvl = c / n_valid;
+      const float g = 0.5f * (vl + lv), lo = 0.5f * (vll + lvl);
+      out8[0] = g; out8[1] = lo; out8[2] = gw * g + lw * lo;
+      out8[3] = vl; out8[4] = lv; out8[5] = vll; out8[6] = lvl; out8[7] = n_valid;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// backward: per 32 x 32 logits tile recompute S (with on-the-fly norms), form
+//   dS_ij = c_self exp(S_ij - lse_self[i]) + c_other exp(S_ij - lse_other[j]) - (c_self + c_other) [j == off + i]
+// and accumulate  sum_j (dS_ij / |col_j|) col_j  for a 256-wide slice of D.  Partials per column split.
+// ------------------------------------------------------------------------------------------------
+constexpr int kBR = 32, kBC = 32, kBK = 32, kBLd = 33, kBDz = 256, kBLdB = kBDz + 1;
+
+__global__ void __launch_bounds__(kNT)
+global_bwd_kernel(const float* __restrict__ a_loc, const float* __restrict__ b_loc, const float* __restrict__ a_all,
+                  const float* __restrict__ b_all, int B, int Bg, int D, int col_offset, float scale, float eps,
+                  const float* __restrict__ lse_loc /* [2][B] */, const float* __restrict__ lse_all /* [2][Bg] */,
+                  const float* __restrict__ norms /* [2][B] */, const float* __restrict__ coef /* c_a, c_b */,
+                  float* __restrict__ out /* [2][nsplit][B][D] */) {
+  extern __shared__ float smem[];
+  float* stA = smem;                       // [32 x 33]
+  float* stB = stA + kBR * kBLd;           // [32 x 33]
+  float* dS = stB + kBC * kBLd;            // [32 x 33]
+  float* bt = dS + kBR * kBLd;             // [32 x 257]
+  float* cn = bt + kBC * kBLdB;            // [32] column norms
+  const int rb = (B + kBR - 1) / kBR;
+  const int dir = blockIdx.x / rb, r0 = (blockIdx.x - dir * rb) * kBR;
+  const int split = blockIdx.y, nsplit = gridDim.y, dz0 = blockIdx.z * kBDz;
+  const float* rows = dir ? b_loc : a_loc;
+  const float* cols = dir ? a_all : b_all;
+  const float* lse_self = lse_loc + (size_t)dir * B;            // rows' own direction
+  const float* lse_other = lse_all + (size_t)(1 - dir) * Bg;    // the columns' direction, global
+  const float* rn = norms + (size_t)dir * B;
+  const float c_self = coef[dir], c_other = coef[1 - dir];
+  const int dzn = min(kBDz, D - dz0);
+  const int rows_valid = min(kBR, B - r0);
+  float oacc[2][16];
+  tile_zero(oacc);
+  const int ntiles = (Bg + kBC - 1) / kBC;
+  for (int ct = split; ct < ntiles; ct += nsplit) {
+    const int c0 = ct * kBC;
+    const int cols_valid = min(kBC, Bg - c0);
+    float acc[2][2];
+    tile_zero(acc);
+    float ss = 0.f;
+    for (int d0 = 0; d0 < D; d0 += kBK) {
+      __syncthreads();
+      load_tile<float>(stA, kBLd, rows + (size_t)r0 * D, kBR, rows_valid, D, d0, kBK);
+      load_tile<float>(stB, kBLd, cols + (size_t)c0 * D, kBC, cols_valid, D, d0, kBK);
+      __syncthreads();
+      if (threadIdx.x < kBC) {
+        const float* src = stB + threadIdx.x * kBLd;
+#pragma unroll 8
+        for (int k = 0; k < kBK; ++k) ss = fmaf(src[k], src[k], ss);
+      }
+      tile_mac<2, 2>(acc, 0, 0, kBR, kBC, kBK, [&](int m, int k) { return stA[m * kBLd + k]; },
+                     [&](int k, int n) { return stB[n * kBLd + k]; });
+    }
+    if (threadIdx.x < kBC) cn[threadIdx.x] = fmaxf(sqrtf(ss), eps);
+    for (int idx = threadIdx.x; idx < kBC * dzn; idx += kNT) {   // raw column rows for the output contraction
+      const int r = idx / dzn, c = idx - r * dzn;
+      bt[r * kBLdB + c] = (r < cols_valid) ? cols[(size_t)(c0 + r) * D + dz0 + c] : 0.f;
+    }
+    __syncthreads();
+    {
+      const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const int m = ty + 16 * i, n = tx + 16 * j;
+          const int grow = r0 + m, gcol = c0 + n;
+          float g = 0.f;
+          if (grow < B && gcol < Bg) {
+            const float s = scale * (acc[i][j] / (rn[grow] * cn[n]));
+            g = c_self * expf(s - lse_self[grow]) + c_other * expf(s - lse_other[gcol]);
+            if (gcol == col_offset + grow) g -= (c_self + c_other);
+            g /= cn[n];                                           // d/d(col_hat) -> raw column, first factor
+          }
+          dS[m * kBLd + n] = g;
+        }
+    }
+    __syncthreads();
+    tile_mac<2, 16>(oacc, 0, 0, kBR, dzn, kBC, [&](int m, int k) { return dS[m * kBLd + k]; },
+                    [&](int k, int n) { return bt[k * kBLdB + n]; });
+  }
+  tile_foreach<2, 16>(oacc, 0, 0, rows_valid, dzn, [&](int m, int n, float x) {
+    out[(((size_t)dir * nsplit + split) * B + r0 + m) * D + dz0 + n] = x * scale;
+  });
+}
+
+// d(raw row) = J_n^T (sum of partials):  (g - x_hat (x_hat . g)) / max(|x|, eps)      one CTA per (row, direction)
+__global__ void __launch_bounds__(128)
+global_norm_bwd_kernel(const float* __restrict__ a_loc, const float* __restrict__ b_loc, const float* __restrict__ norms,
+                       const float* __restrict__ part, int nsplit, int B, int D, float* __restrict__ da,
+                       float* __restrict__ db) {
+  __shared__ float red[4];
+  const int r = blockIdx.x, dir = blockIdx.y;
+  const float* x = (dir ? b_loc : a_loc) + (size_t)r * D;
+  float* dx = (dir ? db : da) + (size_t)r * D;
+  const float inv = 1.f / norms[(size_t)dir * B + r];
+  float g[8];                                   // D <= 1024 per 128 threads
+  float dot = 0.f;
+  int cnt = 0;
+  for (int d = threadIdx.x; d < D; d += 128, ++cnt) {
+    float s = 0.f;
+    for (int k = 0; k < nsplit; ++k) s += part[(((size_t)dir * nsplit + k) * B + r) * D + d];
+    g[cnt] = s;
+    dot = fmaf(s, x[d] * inv, dot);
+  }
+  dot = warp_sum(dot);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = dot;
+  __syncthreads();
+  dot = red[0] + red[1] + red[2] + red[3];
+  cnt = 0;
+  for (int d = threadIdx.x; d < D; d += 128, ++cnt) dx[d] = (g[cnt] - x[d] * inv * dot) * inv;
+}
+
+static int gf_splits(int B, int Bg) {
+  const int rb = (B + kGR - 1) / kGR, nt = (Bg + kGC - 1) / kGC;
+  int s = (296 + 2 * rb - 1) / (2 * rb);
+  if (s > nt) s = nt;
+  if (s < 1) s = 1;
+  return s;
+}
+static int gb_splits(int B, int Bg, int D) {
+  const int rb = (B + kBR - 1) / kBR, nt = (Bg + kBC - 1) / kBC, dz = (D + kBDz - 1) / kBDz;
+  int s = (296 + 2 * rb * dz - 1) / (2 * rb * dz);
+  if (s > nt) s = nt;
+  if (s > 16) s = 16;
+  if (s < 1) s = 1;
+  return s;
+}
+
+}  // namespace cfa
+
+using namespace cfa;
+
+extern "C" size_t cfa_global_infonce_workspace_bytes(int B, int Bg, int D) {
+  const size_t fwd = ((size_t)4 * gf_splits(B, Bg) * B + 2 * (size_t)B) * sizeof(float);
+  const size_t bwd = (size_t)2 * gb_splits(B, Bg, D) * B * D * sizeof(float);
+  return fwd > bwd ? fwd : bwd;
+}
+
+extern "C" int cfa_global_infonce_fwd(const float* a_loc, const float* b_loc, const float* a_all, const float* b_all, int B,
+                                      int Bg, int D, int col_offset, float scale, float eps, float* lse2, float* norms2,
+                                      float* sums2, const float* local_partial, const uint8_t* mask, int T, float gw,
+                                      float lw, float* out8, void* workspace, size_t workspace_bytes, void* stream) {
+  if (B <= 0 || Bg <= 0 || D <= 0 || col_offset < 0 || col_offset + B > Bg) return CFA_ERR_BAD_ARG;
+  if (!workspace || workspace_bytes < cfa_global_infonce_workspace_bytes(B, Bg, D)) return CFA_ERR_WORKSPACE;
+  if (out8 && (Bg != B || !local_partial || !mask)) return CFA_ERR_BAD_ARG;   // fused scalar epilogue: single process only
+  const int ns = gf_splits(B, Bg);
+  float* part_m = (float*)workspace;
+  float* part_l = part_m + (size_t)2 * ns * B;
+  float* diag = part_l + (size_t)2 * ns * B;
+  cudaStream_t st = (cudaStream_t)stream;
+  dim3 grid((B + kGR - 1) / kGR, ns, 2);
+  global_fwd_kernel<<<grid, kNT, 0, st>>>(a_loc, b_loc, a_all, b_all, B, Bg, D, col_offset, scale, eps, part_m, part_l,
+                                          diag, norms2);
+  CFA_CUDA_TRY(cudaGetLastError());
+  global_combine_kernel<<<1, kNT, 0, st>>>(part_m, part_l, diag, B, ns, lse2, sums2, Bg, local_partial, mask, T, gw, lw, out8);
+  return launch_status();
+}
+
+extern "C" int cfa_global_infonce_bwd(const float* a_loc, const float* b_loc, const float* a_all, const float* b_all, int B,
+                                      int Bg, int D, int col_offset, float scale, float eps, const float* lse_loc2,
+                                      const float* lse_all2, const float* norms2, const float* coef2, float* da, float* db,
+                                      void* workspace, size_t workspace_bytes, void* stream) {
+  if (B <= 0 || Bg <= 0 || D <= 0 || D > 1024 || col_offset < 0 || col_offset + B > Bg) return CFA_ERR_BAD_ARG;
+  if (!workspace || workspace_bytes < cfa_global_infonce_workspace_bytes(B, Bg, D)) return CFA_ERR_WORKSPACE;
+  const int ns = gb_splits(B, Bg, D);
+  const size_t smem = sizeof(float) * (3 * kBR * kBLd + kBC * kBLdB + kBC);
+  static bool attr_set = false;
+  if (!attr_set) {
+    CFA_CUDA_TRY(cudaFuncSetAttribute(global_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  const int rb = (B + kBR - 1) / kBR;
+  dim3 grid(2 * rb, ns, (D + kBDz - 1) / kBDz);
+  global_bwd_kernel<<<grid, kNT, smem, st>>>(a_loc, b_loc, a_all, b_all, B, Bg, D, col_offset, scale, eps, lse_loc2, lse_all2,
+                                             norms2, coef2, (float*)workspace);
+  CFA_CUDA_TRY(cudaGetLastError());
+  global_norm_bwd_kernel<<<dim3(B, 2), 128, 0, st>>>(a_loc, b_loc, norms2, (const float*)workspace, ns, B, D, da, db);
+  return launch_status();
+}

@@ -7,280 +7,15 @@
 // (SURVEY.md §8 a-bwd) and works on the RAW embeddings: every gradient w.r.t. a normalised dot product is
 // folded into a gradient w.r.t. the raw dot product, so all contractions read the raw input tiles.
 #include "common.cuh"
+#include "simt_tile.cuh"
 #include "sparc_paths.h"
 #include <math_constants.h>
 
 namespace cfa {
 
-constexpr int kNT = 256;             // threads per CTA (16 x 16 thread grid for the register-tiled GEMMs)
 constexpr float kNormEps = 1e-12f;   // F.normalize eps          (losses.py:152,173,207,212,221)
 constexpr float kMinMaxEps = 1e-8f;  // losses.py:231
 constexpr float kClampEps = 1e-8f;   // losses.py:211,242
-
-// ------------------------------------------------------------------------------------------------
-// register-tiled GEMM over operands in shared memory.
-// thread (ty,tx) = (tid/16, tid%16) owns rows m0+ty+16i (i<TM) and columns n0+tx+16j (j<TN).
-// A(m,k) and Bm(k,n) are callables returning float; out-of-range rows/cols are clamped on read and
-// dropped in tile_foreach.
-// ------------------------------------------------------------------------------------------------
-template <int TM, int TN, typename AF, typename BF>
-__device__ __forceinline__ void tile_mac(float (&acc)[TM][TN], int m0, int n0, int M, int N, int K, AF A, BF Bm) {
-  const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
-  int rm[TM], cn[TN];
-#pragma unroll
-  for (int i = 0; i < TM; ++i) rm[i] = min(m0 + ty + 16 * i, M - 1);
-#pragma unroll
-  for (int j = 0; j < TN; ++j) cn[j] = min(n0 + tx + 16 * j, N - 1);
-#pragma unroll 4
-  for (int k = 0; k < K; ++k) {
-    float a[TM], b[TN];
-#pragma unroll
-    for (int i = 0; i < TM; ++i) a[i] = A(rm[i], k);
-#pragma unroll
-    for (int j = 0; j < TN; ++j) b[j] = Bm(k, cn[j]);
-#pragma unroll
-    for (int i = 0; i < TM; ++i)
-#pragma unroll
-      for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
-  }
-}
-
-template <int TM, int TN, typename F>
-__device__ __forceinline__ void tile_foreach(const float (&acc)[TM][TN], int m0, int n0, int M, int N, F f) {
-  const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
-#pragma unroll
-  for (int i = 0; i < TM; ++i)
-#pragma unroll
-    for (int j = 0; j < TN; ++j) {
-      const int m = m0 + ty + 16 * i, n = n0 + tx + 16 * j;
-      if (m < M && n < N) f(m, n, acc[i][j]);
-    }
-}
-
-template <int TM, int TN>
-__device__ __forceinline__ void tile_zero(float (&acc)[TM][TN]) {
-#pragma unroll
-  for (int i = 0; i < TM; ++i)
-#pragma unroll
-    for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
-}
-
-// global [rows x D] (row stride D, element type T) columns [d0, d0+kc) -> smem fp32 [rows x ld], zero filled
-// beyond D or beyond `rows_valid`.  128-bit (fp32) / 64-bit (16-bit types) loads when the layout allows.
-template <typename T>
-__device__ __forceinline__ void load_tile(float* __restrict__ dst, int ld, const T* __restrict__ src, int rows,
-                                          int rows_valid, int D, int d0, int kc) {
-  const bool vec = ((D & 3) == 0) && ((kc & 3) == 0) && ((((uintptr_t)src) & 15) == 0);
-  if (vec) {
-    const int q = kc >> 2;
-    for (int idx = threadIdx.x; idx < rows * q; idx += kNT) {
-      const int r = idx / q, c = (idx - r * q) << 2;
-      float x0 = 0.f, x1 = 0.f, x2 = 0.f, x3 = 0.f;
-      if (r < rows_valid && d0 + c < D) {
-        const T* p = src + (size_t)r * D + d0 + c;
-        if constexpr (sizeof(T) == 4) {
-          const float4 t = __ldg(reinterpret_cast<const float4*>(p));
-          x0 = t.x; x1 = t.y; x2 = t.z; x3 = t.w;
-        } else {
-          const uint2 t = __ldg(reinterpret_cast<const uint2*>(p));
-          const T* h = reinterpret_cast<const T*>(&t);
-          x0 = to_f32<T>(h[0]); x1 = to_f32<T>(h[1]); x2 = to_f32<T>(h[2]); x3 = to_f32<T>(h[3]);
-        }
-      }
-      float* o = dst + r * ld + c;
-      o[0] = x0; o[1] = x1; o[2] = x2; o[3] = x3;
-    }
-  } else {
-    for (int idx = threadIdx.x; idx < rows * kc; idx += kNT) {
-      const int r = idx / kc, c = idx - r * kc;
-      float x = 0.f;
-      if (r < rows_valid && d0 + c < D) x = to_f32<T>(src[(size_t)r * D + d0 + c]);
-      dst[r * ld + c] = x;
-    }
-  }
-}
-
-// ------------------------------------------------------------------------------------------------
-// row normalisation
-// ------------------------------------------------------------------------------------------------
-__global__ void rows_normalize_kernel(const float* __restrict__ x, int rows, int D, float eps,
-                                      float* __restrict__ xh, float* __restrict__ norm) {
-  const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-  if (r >= rows) return;
-  const float* xr = x + (size_t)r * D;
-  float s = 0.f;
-  for (int d = lane; d < D; d += 32) { const float t = xr[d]; s = fmaf(t, t, s); }
-  s = warp_sum(s);
-  const float n = fmaxf(sqrtf(s), eps);
-  for (int d = lane; d < D; d += 32) xh[(size_t)r * D + d] = xr[d] / n;
-  if (lane == 0) norm[r] = n;
-}
-
-__global__ void rows_normalize_bwd_kernel(const float* __restrict__ xh, const float* __restrict__ norm,
-                                          const float* __restrict__ dxh, int n_partials, size_t pstride, int rows,
-                                          int D, float* __restrict__ dx) {
-  const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-  if (r >= rows) return;
-  const size_t o = (size_t)r * D;
-  float dot = 0.f;
-  for (int d = lane; d < D; d += 32) {
-    float g = 0.f;
-    for (int k = 0; k < n_partials; ++k) g += dxh[k * pstride + o + d];
-    dot = fmaf(g, xh[o + d], dot);
-  }
-  dot = warp_sum(dot);
-  const float inv = 1.f / norm[r];
-  for (int d = lane; d < D; d += 32) {
-    float g = 0.f;
-    for (int k = 0; k < n_partials; ++k) g += dxh[k * pstride + o + d];
-    dx[o + d] = (g - xh[o + d] * dot) * inv;
-  }
-}
-
-// ------------------------------------------------------------------------------------------------
-// InfoNCE forward: 64 x 64 logits tiles, online log-sum-exp per row, column range split over blockIdx.y
-// ------------------------------------------------------------------------------------------------
-constexpr int kIfTile = 64, kIfK = 32, kIfLd = kIfK + 1;
-
-__global__ void __launch_bounds__(kNT)
-infonce_fwd_kernel(const float* __restrict__ a, int B, const float* __restrict__ b, int Bg, int D, int col_offset,
-                   float scale, float* __restrict__ part_m, float* __restrict__ part_l, float* __restrict__ diag) {
-  __shared__ float stA[kIfTile * kIfLd];
-  __shared__ float stB[kIfTile * kIfLd];
-  const int r0 = blockIdx.x * kIfTile, split = blockIdx.y, nsplit = gridDim.y;
-  const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
-  const int rows_valid = min(kIfTile, B - r0);
-  float run_m[4], run_l[4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) { run_m[i] = -CUDART_INF_F; run_l[i] = 0.f; }
-  const int ntiles = (Bg + kIfTile - 1) / kIfTile;
-  for (int ct = split; ct < ntiles; ct += nsplit) {
-    const int c0 = ct * kIfTile;
-    const int cols_valid = min(kIfTile, Bg - c0);
-    float acc[4][4];
-    tile_zero(acc);
-    for (int d0 = 0; d0 < D; d0 += kIfK) {
-      __syncthreads();
-      load_tile<float>(stA, kIfLd, a + (size_t)r0 * D, kIfTile, rows_valid, D, d0, kIfK);
-      load_tile<float>(stB, kIfLd, b + (size_t)c0 * D, kIfTile, cols_valid, D, d0, kIfK);
-      __syncthreads();
-      tile_mac<4, 4>(acc, 0, 0, kIfTile, kIfTile, kIfK, [&](int m, int k) { return stA[m * kIfLd + k]; },
-                     [&](int k, int n) { return stB[n * kIfLd + k]; });
-    }
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int grow = r0 + ty + 16 * i;
-      float v[4], tmax = -CUDART_INF_F;
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int gcol = c0 + tx + 16 * j;
-        v[j] = (gcol < Bg) ? acc[i][j] * scale : -CUDART_INF_F;
-        tmax = fmaxf(tmax, v[j]);
-        if (grow < B && gcol == col_offset + grow) diag[grow] = v[j];
-      }
-#pragma unroll
-      for (int o = 8; o > 0; o >>= 1) tmax = fmaxf(tmax, __shfl_xor_sync(0xffffffffu, tmax, o));
-      const float new_m = fmaxf(run_m[i], tmax);
-      float s = 0.f;
-#pragma unroll
-      for (int j = 0; j < 4; ++j) s += (v[j] == -CUDART_INF_F) ? 0.f : expf(v[j] - new_m);
-#pragma unroll
-      for (int o = 8; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-      run_l[i] = run_l[i] * ((run_m[i] == -CUDART_INF_F) ? 0.f : expf(run_m[i] - new_m)) + s;
-      run_m[i] = new_m;
-    }
-  }
-  if (tx == 0) {
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int grow = r0 + ty + 16 * i;
-      if (grow < B) { part_m[(size_t)split * B + grow] = run_m[i]; part_l[(size_t)split * B + grow] = run_l[i]; }
-    }
-  }
-}
-
-__global__ void infonce_combine_kernel(const float* __restrict__ part_m, const float* __restrict__ part_l,
-                                       const float* __restrict__ diag, int B, int nsplit, float* __restrict__ lse,
-                                       float* __restrict__ ce) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= B) return;
-  float M = -CUDART_INF_F;
-  for (int s = 0; s < nsplit; ++s) M = fmaxf(M, part_m[(size_t)s * B + i]);
-  float L = 0.f;
-  for (int s = 0; s < nsplit; ++s) {
-    const float m = part_m[(size_t)s * B + i];
-    if (m != -CUDART_INF_F) L += part_l[(size_t)s * B + i] * expf(m - M);
-  }
-  const float x = M + logf(L);
-  lse[i] = x;
-  ce[i] = x - diag[i];
-}
-
-// ------------------------------------------------------------------------------------------------
-// InfoNCE backward: 32-row blocks; per 32-column tile recompute the logits, form dS in smem and
-// accumulate dS . b_hat for a 256-wide slice of D (blockIdx.z) in registers.
-// ------------------------------------------------------------------------------------------------
-constexpr int kIbR = 32, kIbC = 32, kIbK = 32, kIbLd = 33, kIbDz = 256, kIbLdB = kIbDz + 1;
-
-__global__ void __launch_bounds__(kNT)
-infonce_bwd_kernel(const float* __restrict__ a, int B, const float* __restrict__ b, int Bg, int D, int col_offset,
-                   float scale, const float* __restrict__ lse_a, const float* __restrict__ lse_b,
-                   const float* __restrict__ coef, float* __restrict__ out /* [nsplit][B][D] */) {
-  extern __shared__ float smem[];
-  float* stA = smem;                       // [32 x 33]
-  float* stB = stA + kIbR * kIbLd;         // [32 x 33]
-  float* dS = stB + kIbC * kIbLd;          // [32 x 33]
-  float* bt = dS + kIbR * kIbLd;           // [32 x 257]
-  const int r0 = blockIdx.x * kIbR, split = blockIdx.y, nsplit = gridDim.y, dz0 = blockIdx.z * kIbDz;
-  const int dzn = min(kIbDz, D - dz0);
-  const int rows_valid = min(kIbR, B - r0);
-  const float c0f = coef[0], c1f = coef[1];
-  float oacc[2][16];
-  tile_zero(oacc);
-  const int ntiles = (Bg + kIbC - 1) / kIbC;
-  for (int ct = split; ct < ntiles; ct += nsplit) {
-    const int c0 = ct * kIbC;
-    const int cols_valid = min(kIbC, Bg - c0);
-    float acc[2][2];
-    tile_zero(acc);
-    for (int d0 = 0; d0 < D; d0 += kIbK) {
-      __syncthreads();
-      load_tile<float>(stA, kIbLd, a + (size_t)r0 * D, kIbR, rows_valid, D, d0, kIbK);
-      load_tile<float>(stB, kIbLd, b + (size_t)c0 * D, kIbC, cols_valid, D, d0, kIbK);
-      __syncthreads();
-      tile_mac<2, 2>(acc, 0, 0, kIbR, kIbC, kIbK, [&](int m, int k) { return stA[m * kIbLd + k]; },
-                     [&](int k, int n) { return stB[n * kIbLd + k]; });
-    }
-    // b_hat tile slice for the output contraction (rows c0.., columns dz0..dz0+dzn)
-    for (int idx = threadIdx.x; idx < kIbC * dzn; idx += kNT) {
-      const int r = idx / dzn, c = idx - r * dzn;
-      bt[r * kIbLdB + c] = (r < cols_valid) ? b[(size_t)(c0 + r) * D + dz0 + c] : 0.f;
-    }
-    {
-      const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
-#pragma unroll
-      for (int i = 0; i < 2; ++i)
-#pragma unroll
-        for (int j = 0; j < 2; ++j) {
-          const int m = ty + 16 * i, n = tx + 16 * j;
-          const int grow = r0 + m, gcol = c0 + n;
-          float g = 0.f;
-          if (grow < B && gcol < Bg) {
-            const float s = acc[i][j] * scale;
-            g = c0f * expf(s - lse_a[grow]) + c1f * expf(s - lse_b[gcol]);
-            if (gcol == col_offset + grow) g -= (c0f + c1f);
-          }
-          dS[m * kIbLd + n] = g;
-        }
-    }
-    __syncthreads();
-    tile_mac<2, 16>(oacc, 0, 0, kIbR, dzn, kIbC, [&](int m, int k) { return dS[m * kIbLd + k]; },
-                    [&](int k, int n) { return bt[k * kIbLdB + n]; });
-  }
-  tile_foreach<2, 16>(oacc, 0, 0, rows_valid, dzn, [&](int m, int n, float x) {
-    out[((size_t)split * B + r0 + m) * D + dz0 + n] = x * scale;
-  });
-}
 
 // ------------------------------------------------------------------------------------------------
 // SPARC fine-grained kernels
@@ -761,15 +496,6 @@ __device__ __forceinline__ float block_sum_256(float x, float* red) {
   return s;
 }
 
-__global__ void __launch_bounds__(kNT) sum2_kernel(const float* x0, const float* x1, int n, float* out2) {
-  __shared__ float red[8];
-  float a = 0.f, c = 0.f;
-  for (int i = threadIdx.x; i < n; i += kNT) { a += x0[i]; c += x1[i]; }
-  a = block_sum_256(a, red);
-  c = block_sum_256(c, red);
-  if (threadIdx.x == 0) { out2[0] = a; out2[1] = c; }
-}
-
 __global__ void __launch_bounds__(kNT)
 sparc_finalize_kernel(const float* global_sums, int global_batch, const float* local_partial, const uint8_t* mask,
                       int B, int Tn, float gw, float lw, float* out8) {
@@ -805,84 +531,9 @@ __global__ void sparc_coef_kernel(const float* grad7, float gw, float lw, int gl
   coef8[4] = clv; coef8[5] = cvl; coef8[6] = 0.f; coef8[7] = 0.f;
 }
 
-static int if_fwd_splits(int B, int Bg) {
-  const int rb = (B + kIfTile - 1) / kIfTile, nt = (Bg + kIfTile - 1) / kIfTile;
-  int s = (296 + rb - 1) / rb;
-  if (s > nt) s = nt;
-  if (s < 1) s = 1;
-  return s;
-}
-static int if_bwd_splits(int B, int Bg, int D) {
-  const int rb = (B + kIbR - 1) / kIbR, nt = (Bg + kIbC - 1) / kIbC, dz = (D + kIbDz - 1) / kIbDz;
-  int s = (296 + rb * dz - 1) / (rb * dz);
-  if (s > nt) s = nt;
-  if (s > 16) s = 16;
-  if (s < 1) s = 1;
-  return s;
-}
-
 }  // namespace cfa
 
 using namespace cfa;
-
-extern "C" int cfa_rows_normalize(const float* x, int rows, int D, float eps, float* x_hat, float* norm, void* stream) {
-  if (rows <= 0 || D <= 0) return rows == 0 ? CFA_OK : CFA_ERR_BAD_ARG;
-  rows_normalize_kernel<<<(rows + 7) / 8, 256, 0, (cudaStream_t)stream>>>(x, rows, D, eps, x_hat, norm);
-  return launch_status();
-}
-
-extern "C" int cfa_rows_normalize_bwd(const float* x_hat, const float* norm, const float* dxh, int n_partials,
-                                      size_t partial_stride, int rows, int D, float* dx, void* stream) {
-  if (rows <= 0 || D <= 0 || n_partials < 1) return rows == 0 ? CFA_OK : CFA_ERR_BAD_ARG;
-  rows_normalize_bwd_kernel<<<(rows + 7) / 8, 256, 0, (cudaStream_t)stream>>>(x_hat, norm, dxh, n_partials,
-                                                                              partial_stride, rows, D, dx);
-  return launch_status();
-}
-
-extern "C" size_t cfa_infonce_fwd_workspace_bytes(int B, int Bg, int D) {
-  (void)D;
-  return sizeof(float) * ((size_t)2 * if_fwd_splits(B, Bg) * B + B);
-}
-
-extern "C" int cfa_infonce_fwd(const float* a_hat, int B, const float* b_hat, int Bg, int D, int col_offset, float scale,
-                               float* lse, float* ce, void* workspace, size_t workspace_bytes, void* stream) {
-  if (B <= 0 || Bg <= 0 || D <= 0 || col_offset < 0 || col_offset + B > Bg) return CFA_ERR_BAD_ARG;
-  if (workspace_bytes < cfa_infonce_fwd_workspace_bytes(B, Bg, D) || !workspace) return CFA_ERR_WORKSPACE;
-  const int ns = if_fwd_splits(B, Bg);
-  float* part_m = (float*)workspace;
-  float* part_l = part_m + (size_t)ns * B;
-  float* diag = part_l + (size_t)ns * B;
-  cudaStream_t st = (cudaStream_t)stream;
-  dim3 grid((B + kIfTile - 1) / kIfTile, ns);
-  infonce_fwd_kernel<<<grid, kNT, 0, st>>>(a_hat, B, b_hat, Bg, D, col_offset, scale, part_m, part_l, diag);
-  CFA_CUDA_TRY(cudaGetLastError());
-  infonce_combine_kernel<<<(B + 255) / 256, 256, 0, st>>>(part_m, part_l, diag, B, ns, lse, ce);
-  return launch_status();
-}
-
-extern "C" size_t cfa_infonce_bwd_workspace_bytes(int B, int Bg, int D, int* n_partials) {
-  const int ns = if_bwd_splits(B, Bg, D);
-  if (n_partials) *n_partials = ns;
-  return sizeof(float) * (size_t)ns * B * D;
-}
-
-extern "C" int cfa_infonce_bwd(const float* a_hat, int B, const float* b_hat, int Bg, int D, int col_offset, float scale,
-                               const float* lse_a, const float* lse_b, const float* coef, void* workspace,
-                               size_t workspace_bytes, void* stream) {
-  if (B <= 0 || Bg <= 0 || D <= 0 || col_offset < 0 || col_offset + B > Bg) return CFA_ERR_BAD_ARG;
-  if (workspace_bytes < cfa_infonce_bwd_workspace_bytes(B, Bg, D, nullptr) || !workspace) return CFA_ERR_WORKSPACE;
-  const int ns = if_bwd_splits(B, Bg, D);
-  const size_t smem = sizeof(float) * (3 * kIbR * kIbLd + kIbC * kIbLdB);
-  static bool attr_set = false;
-  if (!attr_set) {
-    CFA_CUDA_TRY(cudaFuncSetAttribute(infonce_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
-  }
-  dim3 grid((B + kIbR - 1) / kIbR, ns, (D + kIbDz - 1) / kIbDz);
-  infonce_bwd_kernel<<<grid, kNT, smem, (cudaStream_t)stream>>>(a_hat, B, b_hat, Bg, D, col_offset, scale, lse_a,
-                                                                lse_b, coef, (float*)workspace);
-  return launch_status();
-}
 
 extern "C" int cfa_sparc_max_patches(int T, int backward) {
   int best = 0;
@@ -943,12 +594,6 @@ int cfa::sparc_bwd_simt(const void* v, const void* l, const uint8_t* mask, int B
     case CFA_DTYPE_F16: return sparc_bwd_launch<__half>(v, l, mask, B, P, T, D, thr, scale, lse_row, lse_col, coef, dpooled_v, dpooled_l, dv, dl, st);
     default: return CFA_ERR_UNSUPPORTED;
   }
-}
-
-extern "C" int cfa_sum2(const float* x0, const float* x1, int n, float* out2, void* stream) {
-  if (n < 0) return CFA_ERR_BAD_ARG;
-  sum2_kernel<<<1, kNT, 0, (cudaStream_t)stream>>>(x0, x1, n, out2);
-  return launch_status();
 }
 
 extern "C" int cfa_sparc_finalize(const float* global_sums, int global_batch, const float* local_partial,

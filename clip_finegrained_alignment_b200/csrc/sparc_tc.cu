@@ -492,7 +492,11 @@ __host__ __device__ inline TcBwdLayout tc_bwd_layout(int P, int T, int D, int NS
   return L;
 }
 
+// optional phase timestamps (clock64) for tuning: [B][2][16] long long, set through cfa_debug_set_profile_buffer
+static long long* g_prof_buffer = nullptr;
+
 struct TcBwdParams {
+  long long* prof;
   int P, T, D, NS;
   float thr, scale;
   const uint8_t* mask;
@@ -624,6 +628,10 @@ sparc_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_consta
       auto sw_k = [&](uint32_t s, int k) { return make_smem_desc(s + k * 32, 16, 512, kLayoutSw64); };
       auto sw_mn = [&](uint32_t s, int ks) { return make_smem_desc(s + ks * 1024, 16, 512, kLayoutSw64); };
 
+      long long* pf = p.prof ? p.prof + (size_t)b * 32 : nullptr;
+      int pi = 0;
+      auto stamp = [&]() { if (pf) pf[pi++] = clock64(); };
+      stamp();
       // ---- pass 1: S
       for (int u = 0; u < KB; ++u) {
         const int slot = u % NS;
@@ -635,6 +643,7 @@ sparc_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_consta
         umma_commit(empty + slot);
       }
       umma_commit(s_full);
+      stamp();
 
       // G_kb = W . v_kb (hi, lo) into TMEM cG[buf]; optionally X_kb = dLhat . l_kb into cX[buf]
       auto issue_gx = [&](int pass, int kb, uint64_t* gfull, uint64_t* gfree, bool with_x) {
@@ -656,6 +665,7 @@ sparc_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_consta
       // ---- pass 2: L += G_kb . l_kb^T
       mbar_wait(w_ready, 0);
       tc_fence_after();
+      stamp();
       issue_gx(1, 0, g_full2, g_free2, false);
       for (int kb = 0; kb < KB; ++kb) {
         if (kb + 1 < KB) issue_gx(1, kb + 1, g_full2, g_free2, false);
@@ -671,10 +681,12 @@ sparc_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_consta
         umma_commit(empty + slot);
       }
       umma_commit(l_full);
+      stamp();
 
       // ---- pass 3: dW += dG_kb . v_kb^T
       mbar_wait(dl_ready, 0);
       tc_fence_after();
+      stamp();
       issue_gx(2, 0, g_full3, g_free3, true);
       for (int kb = 0; kb < KB; ++kb) {
         if (kb + 1 < KB) issue_gx(2, kb + 1, g_full3, g_free3, true);
@@ -690,10 +702,12 @@ sparc_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_consta
         umma_commit(empty + slot);
       }
       umma_commit(dw_full);
+      stamp();
 
       // ---- pass 4: dv_kb, dl_kb
       mbar_wait(ds_ready, 0);
       tc_fence_after();
+      stamp();
       const uint8_t* Ghi = Gb; const uint8_t* Glo = Gb + L.g_bytes;
       const uint8_t* dGhi = Gb + 2 * L.g_bytes; const uint8_t* dGlo = Gb + 3 * L.g_bytes;
       issue_gx(3, 0, g_full4, g_free4, true);
@@ -730,6 +744,7 @@ sparc_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_consta
         umma_commit(gs_free4);
         umma_commit(empty + slot);
       }
+      stamp();
     }
   } else {
     // =============================== epilogue (4 warps, thread = TMEM lane) ===============================
@@ -739,10 +754,15 @@ sparc_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_consta
     const bool valid = row < T && msk[row < NT ? row : 0] != 0.f;
     const float il = (row < NT) ? iln[row] : 0.f;
     const float c_r = p.coef[0], c_c = p.coef[1];
+    long long* pf = (p.prof && row == 0) ? p.prof + (size_t)b * 32 + 16 : nullptr;
+    int pi = 0;
+    auto stamp = [&]() { if (pf) pf[pi++] = clock64(); };
+    stamp();
 
     // ---- phase 1: S -> W, row stats   (branch-free)
     mbar_wait(s_full, 0);
     tc_fence_after();
+    stamp();
     float mn = CUDART_INF_F, mx = -CUDART_INF_F;
     int imn = 0, imx = 0;
     for (int c0 = 0; c0 < NP; c0 += 32) {
@@ -798,6 +818,7 @@ sparc_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_consta
     fence_proxy_async();
     __syncwarp();
     if (lane == 0) mbar_arrive(w_ready);
+    stamp();
 
     // ---- pass 2 epilogue: G_kb -> ||G||^2 and the A operand of the logits MMA
     float gn2 = 0.f;
@@ -834,8 +855,10 @@ sparc_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_consta
     const float ign = 1.f / gnc;
 
     // ---- phase 3: L -> dLhat (hi/lo), gdot_i, ldotL_j        (scratch aliases the dShat region)
+    stamp();
     mbar_wait(l_full, 0);
     tc_fence_after();
+    stamp();
     float* Sc = reinterpret_cast<float*>(DShi);         // [T][NT+1] products dL_ij * L_ij
     const int ldl = NT + 1;
     float gdot = 0.f;
@@ -877,6 +900,7 @@ sparc_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_consta
     fence_proxy_async();
     __syncwarp();
     if (lane == 0) mbar_arrive(dl_ready);
+    stamp();
 
     // ---- pass 3 epilogue: dG_kb = (X_kb - G_kb gfac) -> A operand of the dW MMA
     for (int kb = 0; kb < KB; ++kb) {
@@ -911,8 +935,10 @@ sparc_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_consta
     }
 
     // ---- phase 5: dW -> dShat (hi/lo), sdot_t, vdot_p          (renorm / threshold / min-max backward)
+    stamp();
     mbar_wait(dw_full, 0);
     tc_fence_after();
+    stamp();
     auto load_w8 = [&](int c, float* w) {               // this row's W[c .. c+8) = hi + lo
       float h[8], l8[8];
       const uint32_t off = il_offset(NT, row < NT ? row : 0, c);
@@ -1015,6 +1041,7 @@ sparc_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_consta
     fence_proxy_async();
     __syncwarp();
     if (lane == 0) mbar_arrive(ds_ready);
+    stamp();
 
     // ---- pass 4 epilogue: operands G_kb, dG_kb (hi/lo) -> smem; outputs dv_kb, dl_kb -> global
     float cnt = 0.f;
@@ -1106,6 +1133,7 @@ sparc_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_consta
       if (kb > 0) output(kb - 1);
     }
     output(KB - 1);
+    stamp();
     tc_fence_before();
   }
   __syncthreads();
@@ -1132,7 +1160,7 @@ int sparc_bwd_tc_launch(const void* v, const void* l, const uint8_t* mask, int B
   int rc;
   if ((rc = make_tmap_bf16_3d(&tmV, v, D, P, B, 32, L.NP)) != CFA_OK) return rc;
   if ((rc = make_tmap_bf16_3d(&tmL, l, D, T, B, 32, L.NT)) != CFA_OK) return rc;
-  TcBwdParams prm{P, T, D, NS, thr, scale, mask, row_inv_norm, row_inv_norm + (size_t)B * P, lse_row, lse_col, coef,
+  TcBwdParams prm{g_prof_buffer, P, T, D, NS, thr, scale, mask, row_inv_norm, row_inv_norm + (size_t)B * P, lse_row, lse_col, coef,
                   dpv, dpl, (const bf16*)v, (const bf16*)l, (bf16*)dv, (bf16*)dl};
   const size_t smem = L.total + 1024;
   CFA_CUDA_TRY(cudaFuncSetAttribute(sparc_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1150,6 +1178,12 @@ extern "C" int cfa_sparc_path(int P, int T, int D, int dtype, int path) {
   const bool ok = sparc_tc_supported(P, T, D, dtype);
   if (path == 2) return ok ? 2 : CFA_ERR_UNSUPPORTED;
   return ok ? 2 : 1;
+}
+
+// tuning aid: device buffer of [B][32] long long receiving clock64 phase stamps of the tensor-core backward
+extern "C" int cfa_debug_set_profile_buffer(void* device_buffer) {
+  g_prof_buffer = (long long*)device_buffer;
+  return CFA_OK;
 }
 
 // same for the backward (the tensor-core backward needs more shared memory than the forward)

@@ -33,50 +33,8 @@ _NORM_EPS = 1e-12
 
 
 # ----------------------------------------------------------------------------------------------
-# thin wrappers over the C ABI (allocation happens here; the library never allocates)
+# global InfoNCE on [B, D] embeddings (both directions per launch), shared by both losses
 # ----------------------------------------------------------------------------------------------
-def _rows_normalize(x: torch.Tensor, eps: float):
-    xh = torch.empty_like(x)
-    n = torch.empty(x.shape[0], dtype=torch.float32, device=x.device)
-    _lib.call("cfa_rows_normalize", x.data_ptr(), x.shape[0], x.shape[1], eps, xh.data_ptr(), n.data_ptr(),
-                                     _lib.stream_ptr())
-    return xh, n
-
-
-def _infonce_fwd(a_hat: torch.Tensor, b_hat_all: torch.Tensor, col_offset: int, scale: float):
-    B, D = a_hat.shape
-    Bg = b_hat_all.shape[0]
-    ws_bytes = _L.cfa_infonce_fwd_workspace_bytes(B, Bg, D)
-    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=a_hat.device)
-    lse = torch.empty(B, dtype=torch.float32, device=a_hat.device)
-    ce = torch.empty(B, dtype=torch.float32, device=a_hat.device)
-    _lib.call("cfa_infonce_fwd", a_hat.data_ptr(), B, b_hat_all.data_ptr(), Bg, D, col_offset, scale, lse.data_ptr(),
-                                  ce.data_ptr(), ws.data_ptr(), ws_bytes, _lib.stream_ptr())
-    return lse, ce
-
-
-def _infonce_bwd(a_hat, a_norm, b_hat_all, col_offset, scale, lse_a, lse_b_all, coef):
-    """Gradient w.r.t. the UN-normalised local rows `a` (J_n applied)."""
-    import ctypes
-    B, D = a_hat.shape
-    Bg = b_hat_all.shape[0]
-    npart = ctypes.c_int(0)
-    ws_bytes = _L.cfa_infonce_bwd_workspace_bytes(B, Bg, D, ctypes.byref(npart))
-    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=a_hat.device)
-    _lib.call("cfa_infonce_bwd", a_hat.data_ptr(), B, b_hat_all.data_ptr(), Bg, D, col_offset, scale, lse_a.data_ptr(),
-                                  lse_b_all.data_ptr(), coef.data_ptr(), ws.data_ptr(), ws_bytes, _lib.stream_ptr())
-    da = torch.empty_like(a_hat)
-    _lib.call("cfa_rows_normalize_bwd", a_hat.data_ptr(), a_norm.data_ptr(), ws.data_ptr(), npart.value, B * D, B, D,
-                                         da.data_ptr(), _lib.stream_ptr())
-    return da
-
-
-def _sum2(x0, x1):
-    out = torch.empty(2, dtype=torch.float32, device=x0.device)
-    _lib.call("cfa_sum2", x0.data_ptr(), x1.data_ptr(), x0.numel(), out.data_ptr(), _lib.stream_ptr())
-    return out
-
-
 def _dist_ctx(group, gather: bool):
     """(world, rank, group) of the gathered global loss; world == 1 means rank-local."""
     if not gather:
@@ -97,41 +55,61 @@ def _all_gather_rows(x: torch.Tensor, world: int, group) -> torch.Tensor:
     return out
 
 
-# ----------------------------------------------------------------------------------------------
-# global InfoNCE on [B, D] embeddings: forward state + backward, shared by both losses
-# ----------------------------------------------------------------------------------------------
+def _gather_lse(lse2: torch.Tensor, world: int, group) -> torch.Tensor:
+    """[2, B] per rank -> [2, world * B] with global row order (rank-major)."""
+    if world == 1:
+        return lse2
+    g = _all_gather_rows(lse2, world, group)                 # [world * 2, B]
+    B = lse2.shape[1]
+    return g.view(world, 2, B).permute(1, 0, 2).reshape(2, world * B).contiguous()
+
+
 class _GlobalState:
-    __slots__ = ("ah", "an", "bh", "bn", "ah_all", "bh_all", "lse_a", "lse_b", "off", "world", "group", "scale", "Bg")
+    __slots__ = ("a", "b", "a_all", "b_all", "lse2", "norms2", "off", "world", "group", "scale", "eps", "Bg", "ws")
 
 
-def _global_forward(a: torch.Tensor, b: torch.Tensor, scale: float, eps: float, world: int, rank: int, group):
-    """a, b: local fp32 [B, D].  Returns (state, sums[2]) with sums = (sum_i CE_a(i), sum_j CE_b(j)) over
-    the GLOBAL batch (all-reduced when world > 1)."""
+def _global_forward(a, b, scale, eps, world, rank, group, fused=None):
+    """a, b: local RAW fp32 [B, D].  Returns (state, sums2) with sums2 = (sum_i CE_a, sum_j CE_b) over the GLOBAL
+    batch (all-reduced when world > 1).  `fused` = (local_partial, mask_u8, T, gw, lw, out8) fuses the SPARC scalar
+    epilogue into the same call when the loss is rank-local."""
     st = _GlobalState()
-    st.world, st.group, st.scale = world, group, scale
-    B = a.shape[0]
-    st.off = rank * B
-    st.Bg = world * B
-    st.ah, st.an = _rows_normalize(a, eps)
-    st.bh, st.bn = _rows_normalize(b, eps)
-    st.ah_all = _all_gather_rows(st.ah, world, group)
-    st.bh_all = _all_gather_rows(st.bh, world, group)
-    st.lse_a, ce_a = _infonce_fwd(st.ah, st.bh_all, st.off, scale)     # image rows vs all text columns
-    st.lse_b, ce_b = _infonce_fwd(st.bh, st.ah_all, st.off, scale)     # text rows vs all image columns
-    sums = _sum2(ce_a, ce_b)
-    if world > 1:
-        import torch.distributed as dist
-        dist.all_reduce(sums, group=group)
-    return st, sums
+    B, D = a.shape
+    st.world, st.group, st.scale, st.eps = world, group, scale, eps
+    st.off, st.Bg = rank * B, world * B
+    st.a, st.b = a, b
+    st.a_all = _all_gather_rows(a, world, group)
+    st.b_all = _all_gather_rows(b, world, group)
+    f32 = dict(dtype=torch.float32, device=a.device)
+    st.lse2 = torch.empty(2, B, **f32)
+    st.norms2 = torch.empty(2, B, **f32)
+    sums2 = torch.empty(2, **f32)
+    ws_bytes = _L.cfa_global_infonce_workspace_bytes(B, st.Bg, D)
+    st.ws = torch.empty(ws_bytes, dtype=torch.uint8, device=a.device)
+    if fused is not None and world == 1:
+        part, mask_u8, T, gw, lw, out8 = fused
+        _lib.call("cfa_global_infonce_fwd", a.data_ptr(), b.data_ptr(), st.a_all.data_ptr(), st.b_all.data_ptr(), B, st.Bg,
+                  D, st.off, scale, eps, st.lse2.data_ptr(), st.norms2.data_ptr(), sums2.data_ptr(), part.data_ptr(),
+                  mask_u8.data_ptr(), T, gw, lw, out8.data_ptr(), st.ws.data_ptr(), ws_bytes, _lib.stream_ptr())
+    else:
+        _lib.call("cfa_global_infonce_fwd", a.data_ptr(), b.data_ptr(), st.a_all.data_ptr(), st.b_all.data_ptr(), B, st.Bg,
+                  D, st.off, scale, eps, st.lse2.data_ptr(), st.norms2.data_ptr(), sums2.data_ptr(), 0, 0, 0, 0.0, 0.0, 0,
+                  st.ws.data_ptr(), ws_bytes, _lib.stream_ptr())
+        if world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(sums2, group=group)
+    return st, sums2
 
 
-def _global_backward(st: _GlobalState, coef_a: torch.Tensor, coef_b: torch.Tensor):
-    """coef_a = device [2] (c_a, c_b)/Bg, coef_b = (c_b, c_a)/Bg.  Returns (da, db) w.r.t. the local
-    un-normalised rows; cross-rank terms come from the other direction's gathered LSE vector."""
-    lse_a_all = _all_gather_rows(st.lse_a, st.world, st.group)
-    lse_b_all = _all_gather_rows(st.lse_b, st.world, st.group)
-    da = _infonce_bwd(st.ah, st.an, st.bh_all, st.off, st.scale, st.lse_a, lse_b_all, coef_a)
-    db = _infonce_bwd(st.bh, st.bn, st.ah_all, st.off, st.scale, st.lse_b, lse_a_all, coef_b)
+def _global_backward(st: _GlobalState, coef2: torch.Tensor):
+    """coef2 = device [2] (c_a, c_b)/Bg.  Returns (da, db) w.r.t. the local raw rows; cross-rank terms come
+    from the other direction's gathered LSE vector."""
+    B, D = st.a.shape
+    lse_all = _gather_lse(st.lse2, st.world, st.group)
+    da = torch.empty_like(st.a)
+    db = torch.empty_like(st.b)
+    _lib.call("cfa_global_infonce_bwd", st.a.data_ptr(), st.b.data_ptr(), st.a_all.data_ptr(), st.b_all.data_ptr(), B,
+              st.Bg, D, st.off, st.scale, st.eps, st.lse2.data_ptr(), lse_all.data_ptr(), st.norms2.data_ptr(),
+              coef2.data_ptr(), da.data_ptr(), db.data_ptr(), st.ws.data_ptr(), st.ws.numel(), _lib.stream_ptr())
     return da, db
 
 
@@ -168,10 +146,12 @@ class _SparcFunction(torch.autograd.Function):
                       inv_norm.data_ptr(), pooled_v.data_ptr(), pooled_l.data_ptr(), lse_r.data_ptr(), lse_c.data_ptr(),
                       part.data_ptr(), path, _lib.stream_ptr())
             world, rank, group = _dist_ctx(group, gather)
-            gst, sums = _global_forward(pooled_v, pooled_l, scale, _NORM_EPS, world, rank, group)
             out8 = torch.empty(8, **f32)
-            _lib.call("cfa_sparc_finalize", sums.data_ptr(), gst.Bg, part.data_ptr(), mask_u8.data_ptr(), B, T, gw, lw,
-                                             out8.data_ptr(), _lib.stream_ptr())
+            gst, sums = _global_forward(pooled_v, pooled_l, scale, _NORM_EPS, world, rank, group,
+                                        fused=(part, mask_u8, T, gw, lw, out8))
+            if world > 1:       # scalar epilogue after the cross-rank all-reduce of the CE sums
+                _lib.call("cfa_sparc_finalize", sums.data_ptr(), gst.Bg, part.data_ptr(), mask_u8.data_ptr(), B, T, gw,
+                          lw, out8.data_ptr(), _lib.stream_ptr())
         ctx.save_for_backward(v, l, mask_u8, lse_r, lse_c, out8, inv_norm)
         ctx.gst = gst
         ctx.hp = (thr, gw, lw, scale, code, path)
@@ -190,7 +170,7 @@ class _SparcFunction(torch.autograd.Function):
             coef = torch.empty(8, dtype=torch.float32, device=dev)
             _lib.call("cfa_sparc_coef", grad7.data_ptr(), gw, lw, gst.Bg, out8.data_ptr(), coef.data_ptr(),
                                          _lib.stream_ptr())
-            dpv, dpl = _global_backward(gst, coef[0:2], coef[4:6])
+            dpv, dpl = _global_backward(gst, coef[0:2])
             dv = torch.empty_like(v)
             dl = torch.empty_like(l)
             _lib.call("cfa_sparc_bwd", v.data_ptr(), l.data_ptr(), mask_u8.data_ptr(), B, P, T, D, code, thr, scale,
@@ -208,28 +188,20 @@ class _PairwiseFunction(torch.autograd.Function):
         a32 = a.detach().to(torch.float32).contiguous()
         b32 = b.detach().to(torch.float32).contiguous()
         with torch.cuda.device(dev):
-            ah, an = _rows_normalize(a32, eps)
-            bh, bn = _rows_normalize(b32, eps)
-            lse_a, ce_a = _infonce_fwd(ah, bh, 0, scale)
-            sums = _sum2(ce_a, ce_a)
-        ctx.save_for_backward(ah, an, bh, bn, lse_a)
-        ctx.meta = (scale, a.dtype, b.dtype)
+            gst, sums = _global_forward(a32, b32, scale, eps, 1, 0, None)
+        ctx.gst = gst
+        ctx.dt = (a.dtype, b.dtype)
         return sums[0] / a.shape[0]
 
     @staticmethod
     def backward(ctx, g):
-        ah, an, bh, bn, lse_a = ctx.saved_tensors
-        scale, adt, bdt = ctx.meta
-        B = ah.shape[0]
-        with torch.cuda.device(ah.device):
-            z = torch.zeros(1, dtype=torch.float32, device=ah.device)
-            c = (g.to(torch.float32).reshape(1) / B)
-            coef_a = torch.cat([c, z])                 # rows of a: own-direction term only
-            coef_b = torch.cat([z, c])                 # rows of b see it through the columns
-            lse_dummy = torch.full((B,), 1e30, dtype=torch.float32, device=ah.device)   # exp(S - 1e30) == 0
-            da = _infonce_bwd(ah, an, bh, 0, scale, lse_a, lse_dummy, coef_a)
-            db = _infonce_bwd(bh, bn, ah, 0, scale, lse_dummy, lse_a, coef_b)
-        return da.to(adt), db.to(bdt), None, None
+        gst = ctx.gst
+        B = gst.a.shape[0]
+        with torch.cuda.device(gst.a.device):
+            z = torch.zeros(1, dtype=torch.float32, device=gst.a.device)
+            coef = torch.cat([g.to(torch.float32).reshape(1) / B, z])      # only the a-rows direction carries loss
+            da, db = _global_backward(gst, coef)
+        return da.to(ctx.dt[0]), db.to(ctx.dt[1]), None, None
 
 
 class SPARCLoss(nn.Module):
@@ -290,9 +262,9 @@ class _ClipFunction(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g):
         gst = ctx.gst
-        with torch.cuda.device(gst.ah.device):
+        with torch.cuda.device(gst.a.device):
             c = (g.to(torch.float32).reshape(1) * (0.5 / gst.Bg)).expand(2).contiguous()
-            da, db = _global_backward(gst, c, c)
+            da, db = _global_backward(gst, c)
         return da.to(ctx.dt[0]), db.to(ctx.dt[1]), None, None, None
 
 

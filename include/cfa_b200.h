@@ -83,36 +83,28 @@ int cfa_adamspd_step(const cfa_adamspd_tensor* d_tensors, int n_tensors,
                      double* d_reduce, float* d_stats, int dtype, int amsgrad, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
- * Row normalisation: F.normalize(x, dim=-1, eps) and its backward
- * (losses.py:17-18 with eps=0; :152-153, :207, :212 with eps=1e-12).
+ * Global (batch-level) InfoNCE, both directions per call (losses.py:14-36 CustomCLIPLoss; :145-163 and :207-217
+ * SPARCLoss.pairwise_contrastive_loss on the pooled embeddings).
+ *   a_loc, b_loc [B,D]  : this rank's RAW (un-normalised) fp32 rows (image / text)
+ *   a_all, b_all [Bg,D] : the all-gathered rows of every rank (== a_loc, b_loc when Bg == B)
+ *   row i of this rank is global row col_offset + i; logits = scale * normalize(rows) . normalize(cols)^T with
+ *   F.normalize's eps (1e-12 for SPARC, 0 for CustomCLIPLoss).  The B x Bg logits are never written to memory.
+ * Forward outputs: lse2 [2][B] (log-sum-exp of each local row, direction 0 = a rows vs b columns, 1 = b vs a),
+ *   norms2 [2][B] (max(|row|, eps)), sums2 [2] = sum over LOCAL rows of CE.  When out8 != NULL (single process,
+ *   Bg == B) the SPARC scalar epilogue cfa_sparc_finalize is fused in.
+ * Backward: gradient w.r.t. the raw local rows of  coef2[0] * sum_i CE_a(i) + coef2[1] * sum_j CE_b(j)  taken over
+ *   the GLOBAL batch (both directions share the logits, so cross-rank terms only need the other direction's
+ *   gathered lse vector lse_all2 [2][Bg]).  coef2 is a DEVICE pointer (already divided by the global batch).
  * ---------------------------------------------------------------------------------------------- */
-int cfa_rows_normalize(const float* x, int rows, int D, float eps, float* x_hat, float* norm, void* stream);
-/* dx = (sum over n_partials of dxh[k] - x_hat * (x_hat . sum dxh)) / norm ; partial k at dxh + k*partial_stride */
-int cfa_rows_normalize_bwd(const float* x_hat, const float* norm, const float* dxh, int n_partials,
-                           size_t partial_stride, int rows, int D, float* dx, void* stream);
-
-/* ------------------------------------------------------------------------------------------------
- * InfoNCE, one direction: local rows a_hat [B,D] against global columns b_hat [Bg,D]
- * (losses.py:155-163 and :21-28).  Row i's target is column col_offset+i.
- * Outputs: lse[B] (log-sum-exp of row i of scale*a_hat.b_hat^T) and ce[B] = lse - logit[i, target].
- * The B x Bg logits are never written to memory.
- * ---------------------------------------------------------------------------------------------- */
-size_t cfa_infonce_fwd_workspace_bytes(int B, int Bg, int D);
-int cfa_infonce_fwd(const float* a_hat, int B, const float* b_hat, int Bg, int D, int col_offset, float scale,
-                    float* lse, float* ce, void* workspace, size_t workspace_bytes, void* stream);
-
-/*
- * Gradient w.r.t. a_hat of  sum_i coef[0]*CE_a(i) + sum_j coef[1]*CE_b(j)  (both directions share the logits):
- *   da_hat[i,:] = scale * sum_j ( coef[0]*exp(S_ij - lse_a[i]) + coef[1]*exp(S_ij - lse_b[j])
- *                                 - (coef[0]+coef[1])*[j == col_offset+i] ) * b_hat[j,:]
- * coef is a DEVICE pointer to 2 floats (already divided by the global batch).  lse_b has Bg entries.
- * Result is written as n_partials partial sums [n_partials][B][D] into the workspace; the query returns
- * n_partials via *n_partials and cfa_rows_normalize_bwd folds them.
- */
-size_t cfa_infonce_bwd_workspace_bytes(int B, int Bg, int D, int* n_partials);
-int cfa_infonce_bwd(const float* a_hat, int B, const float* b_hat, int Bg, int D, int col_offset, float scale,
-                    const float* lse_a, const float* lse_b, const float* coef,
-                    void* workspace, size_t workspace_bytes, void* stream);
+size_t cfa_global_infonce_workspace_bytes(int B, int Bg, int D);
+int cfa_global_infonce_fwd(const float* a_loc, const float* b_loc, const float* a_all, const float* b_all, int B, int Bg,
+                           int D, int col_offset, float scale, float eps, float* lse2, float* norms2, float* sums2,
+                           const float* local_partial, const uint8_t* mask, int T, float gw, float lw, float* out8,
+                           void* workspace, size_t workspace_bytes, void* stream);
+int cfa_global_infonce_bwd(const float* a_loc, const float* b_loc, const float* a_all, const float* b_all, int B, int Bg,
+                           int D, int col_offset, float scale, float eps, const float* lse_loc2, const float* lse_all2,
+                           const float* norms2, const float* coef2, float* da, float* db, void* workspace,
+                           size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * SPARC fine-grained path, one CTA per sample (losses.py:207-212 pooling and :221-252 local loss).
@@ -152,9 +144,8 @@ int cfa_sparc_max_patches(int T, int backward);
  * Scalar epilogue (losses.py:163,196,217,252-264): sums the per-row / per-sample partials and writes
  * out[0..6] = global_loss, local_loss, total_loss, loss_vl, loss_lv, loss_vl_local, loss_lv_local and
  * out[7] = n_valid (sum of mask).  global_sums: DEVICE [2] = sum_i CE_vl(i), sum_j CE_lv(j) over the GLOBAL
- * batch (after the cross-rank all-reduce when distributed); cfa_sum2 produces the local part.
+ * batch (after the cross-rank all-reduce of cfa_global_infonce_fwd's sums2 when distributed).
  */
-int cfa_sum2(const float* x0, const float* x1, int n, float* out2, void* stream);
 int cfa_sparc_finalize(const float* global_sums, int global_batch, const float* local_partial,
                        const uint8_t* mask, int B, int T, float gw, float lw, float* out8, void* stream);
 
@@ -175,6 +166,8 @@ int cfa_sparc_coef(const float* grad7, float gw, float lw, int global_batch, con
  * b_mode: 0 = B[N,K] via TMA K-major, 1 = B^T[K,64] via TMA read MN-major (N = 64), 2 = B[N,K] interleaved
  * K-major, 3 = B^T[K,N] interleaved MN-major.  D[n] = sum_k A[m,k] * B[n,k].  bf16 in, fp32 out.
  * ---------------------------------------------------------------------------------------------- */
+/* tuning aid: device buffer [B][32] int64 receiving clock64 phase stamps of the tensor-core backward (NULL = off) */
+int cfa_debug_set_profile_buffer(void* device_buffer);
 int cfa_tc_selftest(int a_mode, int b_mode, int N, int K, const void* A, const void* B, float* D, void* stream);
 
 #ifdef __cplusplus

@@ -195,34 +195,42 @@ def test_pairwise_helper_vs_reference_golden():
 
 
 def test_gathered_global_loss_emulated_ranks():
-    """The N-rank gathered InfoNCE kernels (col_offset / Bg arguments of the C ABI) on ONE GPU: each 'rank'
-    scores its row block against all columns; the union must equal the single-process result."""
-    from clip_finegrained_alignment_b200 import losses as L
+    """The N-rank gathered InfoNCE (col_offset / Bg arguments of the C ABI) on ONE GPU: each 'rank' scores its row
+    block against all columns; the union must equal the single-process result on the concatenated batch."""
+    from clip_finegrained_alignment_b200 import _lib
     g = torch.Generator().manual_seed(77)
     N, B, D, s = 4, 48, 96, 5.0
     a = torch.randn(N * B, D, generator=g)
     b = torch.randn(N * B, D, generator=g)
-    ah, an = L._rows_normalize(a.cuda(), 1e-12)
-    bh, bn = L._rows_normalize(b.cuda(), 1e-12)
     f1 = lo.infonce_forward(a.double(), b.double(), s)
     f2 = lo.infonce_forward(b.double(), a.double(), s)
     da_ref, db_ref = lo.symmetric_infonce_backward(f1["ah"], f1["an"], f1["bh"], f1["bn"], f1["lse"], f2["lse"], s,
                                                    0.5, 0.5, float(N * B))
-    lse_a, lse_b, ce = [], [], 0.0
+    ac, bc = a.cuda(), b.cuda()
+    Bg = N * B
+    ws_bytes = _lib.lib.cfa_global_infonce_workspace_bytes(B, Bg, D)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device="cuda")
+    lse, norms, sums = [], [], torch.zeros(2, device="cuda")
     for r in range(N):
-        la, ca = L._infonce_fwd(ah[r * B:(r + 1) * B].contiguous(), bh, r * B, s)
-        lb, cb = L._infonce_fwd(bh[r * B:(r + 1) * B].contiguous(), ah, r * B, s)
-        lse_a.append(la); lse_b.append(lb)
-        ce += float(ca.sum() + cb.sum())
-    ref_loss = float(0.5 * (f1["loss_sum"] + f2["loss_sum"]) / (N * B))
-    assert abs(0.5 * ce / (N * B) - ref_loss) <= 1e-5 * ref_loss
-    lse_a, lse_b = torch.cat(lse_a), torch.cat(lse_b)
-    torch.testing.assert_close(lse_a.cpu().double(), f1["lse"], rtol=1e-5, atol=1e-5)
-    coef = torch.full((2,), 0.5 / (N * B), device="cuda")
+        l2 = torch.empty(2, B, device="cuda"); n2 = torch.empty(2, B, device="cuda"); s2 = torch.empty(2, device="cuda")
+        al, bl = ac[r * B:(r + 1) * B].contiguous(), bc[r * B:(r + 1) * B].contiguous()
+        _lib.call("cfa_global_infonce_fwd", al.data_ptr(), bl.data_ptr(), ac.data_ptr(), bc.data_ptr(), B, Bg, D, r * B, s,
+                  1e-12, l2.data_ptr(), n2.data_ptr(), s2.data_ptr(), 0, 0, 0, 0.0, 0.0, 0, ws.data_ptr(), ws_bytes,
+                  _lib.stream_ptr())
+        lse.append(l2); norms.append(n2); sums += s2            # "all-reduce" of the CE sums
+    ref_loss = float(0.5 * (f1["loss_sum"] + f2["loss_sum"]) / Bg)
+    assert abs(float(0.5 * sums.sum() / Bg) - ref_loss) <= 1e-5 * ref_loss
+    lse_all = torch.cat(lse, dim=1).contiguous()                # "all-gather" of the LSE vectors -> [2, Bg]
+    torch.testing.assert_close(lse_all[0].cpu().double(), f1["lse"], rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(lse_all[1].cpu().double(), f2["lse"], rtol=1e-5, atol=1e-5)
+    coef = torch.full((2,), 0.5 / Bg, device="cuda")
     for r in range(N):
         sl = slice(r * B, (r + 1) * B)
-        da = L._infonce_bwd(ah[sl].contiguous(), an[sl].contiguous(), bh, r * B, s, lse_a[sl].contiguous(), lse_b, coef)
-        db = L._infonce_bwd(bh[sl].contiguous(), bn[sl].contiguous(), ah, r * B, s, lse_b[sl].contiguous(), lse_a, coef)
+        al, bl = ac[sl].contiguous(), bc[sl].contiguous()
+        da = torch.empty(B, D, device="cuda"); db = torch.empty(B, D, device="cuda")
+        _lib.call("cfa_global_infonce_bwd", al.data_ptr(), bl.data_ptr(), ac.data_ptr(), bc.data_ptr(), B, Bg, D, r * B, s,
+                  1e-12, lse[r].data_ptr(), lse_all.data_ptr(), norms[r].data_ptr(), coef.data_ptr(), da.data_ptr(),
+                  db.data_ptr(), ws.data_ptr(), ws_bytes, _lib.stream_ptr())
         assert_grad_close(da, da_ref[sl], 2e-5, f"da rank {r}")
         assert_grad_close(db, db_ref[sl], 2e-5, f"db rank {r}")
 
