@@ -16,6 +16,6 @@ int sparc_bwd_simt(const void* v, const void* l, const uint8_t* mask, int B, int
 bool sparc_tc_supported(int P, int T, int D, int dtype);
 int sparc_fwd_tc_launch(const void* v, const void* l, const uint8_t* mask, int B, int P, int T, int D, float thr,
                         float scale, float* row_inv_norm, float* pooled_v, float* pooled_l, float* lse_row,
-                        float* lse_col, float* local_partial, cudaStream_t st);
+                        float* lse_col, float* local_partial, float* tt_logits, float* g_inv_norm, cudaStream_t st);
 
 }  // namespace cfa

@@ -140,6 +140,8 @@ struct TcFwdParams {
   float* lse_row;
   float* lse_col;
   float* local_partial;
+  float* tt_logits;     // [B][T][T] masked, scaled logits (saved for the backward), may be NULL
+  float* g_inv_norm;    // [B][T]   1 / max(||G_t||, eps)
 };
 
 __global__ void __launch_bounds__(kTcThreads, 1)
@@ -380,6 +382,7 @@ sparc_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_consta
         rmax = fmaxf(rmax, y);
       }
     }
+    if (p.g_inv_norm && row < T) p.g_inv_norm[(size_t)b * T + row] = ign;
     float ce_r = 0.f, ce_c = 0.f;
     if (valid) {
       float s = 0.f;
@@ -408,6 +411,10 @@ sparc_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_consta
     if (row == 0) {
       p.local_partial[2 * b] = red[0] + red[1] + red[2] + red[3];
       p.local_partial[2 * b + 1] = red[4] + red[5] + red[6] + red[7];
+    }
+    if (p.tt_logits) {                                   // coalesced copy of the T x T logits for the backward
+      float* dst = p.tt_logits + (size_t)b * T * T;
+      for (int idx = threadIdx.x - 64; idx < T * T; idx += 128) { const int i = idx / T, j = idx - i * T; dst[idx] = Lb[i * ldl + j]; }
     }
     tc_fence_before();
   }
@@ -441,7 +448,7 @@ int sparc_prep_launch(const void* v, const void* l, const uint8_t* mask, int B, 
 
 int sparc_fwd_tc_launch(const void* v, const void* l, const uint8_t* mask, int B, int P, int T, int D, float thr,
                         float scale, float* row_inv_norm, float* pooled_v, float* pooled_l, float* lse_row,
-                        float* lse_col, float* local_partial, cudaStream_t st) {
+                        float* lse_col, float* local_partial, float* tt_logits, float* g_inv_norm, cudaStream_t st) {
   float* inv_vn = row_inv_norm;
   float* inv_ln = row_inv_norm + (size_t)B * P;
   int rc = sparc_prep_launch(v, l, mask, B, P, T, D, inv_vn, inv_ln, pooled_v, pooled_l, st);
@@ -451,7 +458,7 @@ int sparc_fwd_tc_launch(const void* v, const void* l, const uint8_t* mask, int B
   CUtensorMap tmV, tmL;
   if ((rc = make_tmap_bf16_3d(&tmV, v, D, P, B, 64, L.NP)) != CFA_OK) return rc;
   if ((rc = make_tmap_bf16_3d(&tmL, l, D, T, B, 64, L.NT)) != CFA_OK) return rc;
-  TcFwdParams prm{P, T, D, NS, thr, scale, mask, inv_vn, inv_ln, lse_row, lse_col, local_partial};
+  TcFwdParams prm{P, T, D, NS, thr, scale, mask, inv_vn, inv_ln, lse_row, lse_col, local_partial, tt_logits, g_inv_norm};
   const size_t smem = L.total + 1024;
   CFA_CUDA_TRY(cudaFuncSetAttribute(sparc_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   sparc_fwd_tc_kernel<<<B, kTcThreads, smem, st>>>(tmV, tmL, prm);
@@ -505,6 +512,8 @@ struct TcBwdParams {
   const float* lse_row;
   const float* lse_col;
   const float* coef;
+  const float* tt_logits;   // [B][T][T] from the forward
+  const float* g_inv_norm;  // [B][T]
   const float* dpool_v;
   const float* dpool_l;
   const bf16* v;
@@ -604,7 +613,7 @@ sparc_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_consta
   if (warp == 0) {
     // =============================== TMA producer ===============================
     if (lane == 0) {
-      for (int u = 0; u < 4 * KB; ++u) {
+      for (int u = 0; u < 3 * KB; ++u) {
         const int slot = u % NS, kb = u % KB;
         mbar_wait(empty + slot, ((u / NS) & 1) ^ 1);
         uint8_t* st = base + (size_t)slot * L.stage_bytes;
@@ -662,35 +671,19 @@ sparc_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_consta
         umma_commit(gfull + buf);
       };
 
-      // ---- pass 2: L += G_kb . l_kb^T
+      // (the T x T logits and ||G|| come from the forward: no second pass)
       mbar_wait(w_ready, 0);
       tc_fence_after();
       stamp();
-      issue_gx(1, 0, g_full2, g_free2, false);
-      for (int kb = 0; kb < KB; ++kb) {
-        if (kb + 1 < KB) issue_gx(1, kb + 1, g_full2, g_free2, false);
-        const int u = KB + kb, slot = u % NS, buf = kb & 1;
-        mbar_wait(gs_ready2 + buf, (kb >> 1) & 1);
-        tc_fence_after();
-        const uint32_t sl = smem_u32(base + (size_t)slot * L.stage_bytes);
-        for (int half = 0; half < 2; ++half)
-#pragma unroll
-          for (int k = 0; k < 2; ++k)
-            umma_ss(tmem + cL, il_k(Gb + (size_t)(2 * buf + half) * L.g_bytes, k), sw_k(sl, k), id_l, (kb | half | k) != 0);
-        umma_commit(gs_free2 + buf);
-        umma_commit(empty + slot);
-      }
-      umma_commit(l_full);
       stamp();
-
       // ---- pass 3: dW += dG_kb . v_kb^T
       mbar_wait(dl_ready, 0);
       tc_fence_after();
       stamp();
-      issue_gx(2, 0, g_full3, g_free3, true);
+      issue_gx(1, 0, g_full3, g_free3, true);
       for (int kb = 0; kb < KB; ++kb) {
-        if (kb + 1 < KB) issue_gx(2, kb + 1, g_full3, g_free3, true);
-        const int u = 2 * KB + kb, slot = u % NS, buf = kb & 1;
+        if (kb + 1 < KB) issue_gx(1, kb + 1, g_full3, g_free3, true);
+        const int u = KB + kb, slot = u % NS, buf = kb & 1;
         mbar_wait(dg_ready3 + buf, (kb >> 1) & 1);
         tc_fence_after();
         const uint32_t sv = smem_u32(base + (size_t)slot * L.stage_bytes) + L.l_bytes;
@@ -710,10 +703,10 @@ sparc_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_consta
       stamp();
       const uint8_t* Ghi = Gb; const uint8_t* Glo = Gb + L.g_bytes;
       const uint8_t* dGhi = Gb + 2 * L.g_bytes; const uint8_t* dGlo = Gb + 3 * L.g_bytes;
-      issue_gx(3, 0, g_full4, g_free4, true);
+      issue_gx(2, 0, g_full4, g_free4, true);
       for (int kb = 0; kb < KB; ++kb) {
-        if (kb + 1 < KB) issue_gx(3, kb + 1, g_full4, g_free4, true);
-        const int u = 3 * KB + kb, slot = u % NS, buf = kb & 1;
+        if (kb + 1 < KB) issue_gx(2, kb + 1, g_full4, g_free4, true);
+        const int u = 2 * KB + kb, slot = u % NS, buf = kb & 1;
         mbar_wait(gs_ready4, kb & 1);
         mbar_wait(out_free + buf, ((kb >> 1) & 1) ^ 1);
         tc_fence_after();
@@ -758,6 +751,15 @@ sparc_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_consta
     int pi = 0;
     auto stamp = [&]() { if (pf) pf[pi++] = clock64(); };
     stamp();
+    // T x T logits of the forward -> fp32 scratch (aliases the dShat region, free until phase 5); overlaps pass 1
+    float* Sc = reinterpret_cast<float*>(DShi);         // [T][NT+1]
+    const int ldl = NT + 1;
+    {
+      const float* src = p.tt_logits + (size_t)b * T * T;
+      for (int idx = threadIdx.x - 64; idx < T * T; idx += 128) { const int i = idx / T, j = idx - i * T; Sc[i * ldl + j] = __ldg(src + idx); }
+    }
+    const float ign = (row < T) ? p.g_inv_norm[(size_t)b * T + row] : 0.f;
+    epi_bar_sync();
 
     // ---- phase 1: S -> W, row stats   (branch-free)
     mbar_wait(s_full, 0);
@@ -820,64 +822,25 @@ sparc_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_consta
     if (lane == 0) mbar_arrive(w_ready);
     stamp();
 
-    // ---- pass 2 epilogue: G_kb -> ||G||^2 and the A operand of the logits MMA
-    float gn2 = 0.f;
-    for (int kb = 0; kb < KB; ++kb) {
-      const int buf = kb & 1;
-      mbar_wait(g_full2 + buf, (kb >> 1) & 1);
-      tc_fence_after();
-      float x[32];
-      tmem_ld32(trow + cG + 32 * buf, x);
-      tmem_ld_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(g_free2 + buf);
-      mbar_wait(gs_free2 + buf, ((kb >> 1) & 1) ^ 1);
-      if (row < NT) {
-        uint8_t* gh = Gb + (size_t)(2 * buf) * L.g_bytes;
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          float y[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) { y[j] = valid ? x[8 * g + j] : 0.f; gn2 = fmaf(y[j], y[j], gn2); }
-          uint4 hi, lo;
-          split_bf16x8(y, hi, lo);
-          const uint32_t off = il_offset(NT, row, 8 * g);
-          *reinterpret_cast<uint4*>(gh + off) = hi;
-          *reinterpret_cast<uint4*>(gh + L.g_bytes + off) = lo;
-        }
-      }
-      fence_proxy_async();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(gs_ready2 + buf);
-    }
-    const float gnc = fmaxf(sqrtf(gn2), kTcNormEps);
-    const float ign = 1.f / gnc;
-
-    // ---- phase 3: L -> dLhat (hi/lo), gdot_i, ldotL_j        (scratch aliases the dShat region)
+    // ---- phase 3: saved logits -> dLhat (hi/lo), gdot_i, ldotL_j
     stamp();
-    mbar_wait(l_full, 0);
-    tc_fence_after();
     stamp();
-    float* Sc = reinterpret_cast<float*>(DShi);         // [T][NT+1] products dL_ij * L_ij
-    const int ldl = NT + 1;
     float gdot = 0.f;
     const float lr = (row < NT) ? lser[row] : 0.f;
     for (int c0 = 0; c0 < NT; c0 += 16) {
       float x[16];
-      tmem_ld_chunk(trow + cL + c0, 16, x);
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
         const int col = c0 + j;
-        const bool on = valid && msk[col] != 0.f;            // msk / iln are 0 beyond T
+        const bool on = valid && col < T && msk[col] != 0.f;
+        const float y = on ? Sc[row * ldl + col] : 0.f;
         const float den = ign * iln[col];
-        const float y = p.scale * (x[j] * den);
         float g = c_r * __expf(fminf(y - lr, 0.f)) + c_c * __expf(fminf(y - lsec[col], 0.f));
         g -= (col == row) ? (c_r + c_c) : 0.f;
         g = on ? g : 0.f;
-        const float pr = on ? g * y : 0.f;
+        const float pr = g * y;
         gdot += pr;
-        if (row < T) Sc[row * ldl + col] = pr;
+        if (row < T && col < T) Sc[row * ldl + col] = pr;
         x[j] = p.scale * g * den;
       }
       if (row < NT) {
@@ -1153,7 +1116,8 @@ bool sparc_tc_bwd_supported(int P, int T, int D, int dtype) {
 
 int sparc_bwd_tc_launch(const void* v, const void* l, const uint8_t* mask, int B, int P, int T, int D, float thr,
                         float scale, const float* row_inv_norm, const float* lse_row, const float* lse_col,
-                        const float* coef, const float* dpv, const float* dpl, void* dv, void* dl, cudaStream_t st) {
+                        const float* coef, const float* tt_logits, const float* g_inv_norm, const float* dpv,
+                        const float* dpl, void* dv, void* dl, cudaStream_t st) {
   const int NS = tc_bwd_pick_stages(P, T, D);
   const TcBwdLayout L = tc_bwd_layout(P, T, D, NS);
   CUtensorMap tmV, tmL;
@@ -1161,7 +1125,7 @@ int sparc_bwd_tc_launch(const void* v, const void* l, const uint8_t* mask, int B
   if ((rc = make_tmap_bf16_3d(&tmV, v, D, P, B, 32, L.NP)) != CFA_OK) return rc;
   if ((rc = make_tmap_bf16_3d(&tmL, l, D, T, B, 32, L.NT)) != CFA_OK) return rc;
   TcBwdParams prm{g_prof_buffer, P, T, D, NS, thr, scale, mask, row_inv_norm, row_inv_norm + (size_t)B * P, lse_row, lse_col, coef,
-                  dpv, dpl, (const bf16*)v, (const bf16*)l, (bf16*)dv, (bf16*)dl};
+                  tt_logits, g_inv_norm, dpv, dpl, (const bf16*)v, (const bf16*)l, (bf16*)dv, (bf16*)dl};
   const size_t smem = L.total + 1024;
   CFA_CUDA_TRY(cudaFuncSetAttribute(sparc_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   sparc_bwd_tc_kernel<<<B, kTcThreads, smem, st>>>(tmV, tmL, prm);
@@ -1195,14 +1159,15 @@ extern "C" int cfa_sparc_bwd_path(int P, int T, int D, int dtype, int path) {
 
 extern "C" int cfa_sparc_fwd(const void* v, const void* l, const uint8_t* mask, int B, int P, int T, int D, int dtype,
                              float thr, float scale, float* row_inv_norm, float* pooled_v, float* pooled_l,
-                             float* lse_row, float* lse_col, float* local_partial, int path, void* stream) {
+                             float* lse_row, float* lse_col, float* local_partial, float* tt_logits, float* g_inv_norm,
+                             int path, void* stream) {
   if (B <= 0 || P <= 0 || T <= 0 || D <= 0 || !v || !l || !mask) return CFA_ERR_BAD_ARG;
   const int which = cfa_sparc_path(P, T, D, dtype, path);
   if (which < 0) return which;
   if (which == 2) {
     if (!row_inv_norm) return CFA_ERR_WORKSPACE;
     return sparc_fwd_tc_launch(v, l, mask, B, P, T, D, thr, scale, row_inv_norm, pooled_v, pooled_l, lse_row, lse_col,
-                               local_partial, (cudaStream_t)stream);
+                               local_partial, tt_logits, g_inv_norm, (cudaStream_t)stream);
   }
   return sparc_fwd_simt(v, l, mask, B, P, T, D, dtype, thr, scale, pooled_v, pooled_l, lse_row, lse_col, local_partial,
                         stream);
@@ -1210,15 +1175,15 @@ extern "C" int cfa_sparc_fwd(const void* v, const void* l, const uint8_t* mask, 
 
 extern "C" int cfa_sparc_bwd(const void* v, const void* l, const uint8_t* mask, int B, int P, int T, int D, int dtype,
                              float thr, float scale, const float* row_inv_norm, const float* lse_row,
-                             const float* lse_col, const float* coef, const float* dpooled_v, const float* dpooled_l,
-                             void* dv, void* dl, int path, void* stream) {
+                             const float* lse_col, const float* tt_logits, const float* g_inv_norm, const float* coef,
+                             const float* dpooled_v, const float* dpooled_l, void* dv, void* dl, int path, void* stream) {
   if (B <= 0 || P <= 0 || T <= 0 || D <= 0 || !v || !l || !mask || !coef || !dv || !dl) return CFA_ERR_BAD_ARG;
   const int which = cfa_sparc_bwd_path(P, T, D, dtype, path);
   if (which < 0) return which;
   if (which == 2) {
-    if (!row_inv_norm) return CFA_ERR_WORKSPACE;
-    return sparc_bwd_tc_launch(v, l, mask, B, P, T, D, thr, scale, row_inv_norm, lse_row, lse_col, coef, dpooled_v,
-                               dpooled_l, dv, dl, (cudaStream_t)stream);
+    if (!row_inv_norm || !tt_logits || !g_inv_norm) return CFA_ERR_WORKSPACE;
+    return sparc_bwd_tc_launch(v, l, mask, B, P, T, D, thr, scale, row_inv_norm, lse_row, lse_col, coef, tt_logits,
+                               g_inv_norm, dpooled_v, dpooled_l, dv, dl, (cudaStream_t)stream);
   }
   return sparc_bwd_simt(v, l, mask, B, P, T, D, dtype, thr, scale, lse_row, lse_col, coef, dpooled_v, dpooled_l, dv, dl,
                         stream);

@@ -140,11 +140,13 @@ class _SparcFunction(torch.autograd.Function):
         lse_r = torch.empty(B, T, **f32)
         lse_c = torch.empty(B, T, **f32)
         part = torch.empty(B, 2, **f32)
-        inv_norm = torch.empty(B * (P + T), **f32)
+        # one fp32 block of state saved for the backward: row inverse norms | T x T logits | 1/|G_t|
+        saved = torch.empty(B * (P + T) + B * T * T + B * T, **f32)
+        inv_norm, tt_logits, g_inv = saved[:B * (P + T)], saved[B * (P + T):B * (P + T) + B * T * T], saved[B * (P + T) + B * T * T:]
         with torch.cuda.device(dev):
             _lib.call("cfa_sparc_fwd", v.data_ptr(), l.data_ptr(), mask_u8.data_ptr(), B, P, T, D, code, thr, scale,
                       inv_norm.data_ptr(), pooled_v.data_ptr(), pooled_l.data_ptr(), lse_r.data_ptr(), lse_c.data_ptr(),
-                      part.data_ptr(), path, _lib.stream_ptr())
+                      part.data_ptr(), tt_logits.data_ptr(), g_inv.data_ptr(), path, _lib.stream_ptr())
             world, rank, group = _dist_ctx(group, gather)
             out8 = torch.empty(8, **f32)
             gst, sums = _global_forward(pooled_v, pooled_l, scale, _NORM_EPS, world, rank, group,
@@ -152,19 +154,20 @@ class _SparcFunction(torch.autograd.Function):
             if world > 1:       # scalar epilogue after the cross-rank all-reduce of the CE sums
                 _lib.call("cfa_sparc_finalize", sums.data_ptr(), gst.Bg, part.data_ptr(), mask_u8.data_ptr(), B, T, gw,
                           lw, out8.data_ptr(), _lib.stream_ptr())
-        ctx.save_for_backward(v, l, mask_u8, lse_r, lse_c, out8, inv_norm)
+        ctx.save_for_backward(v, l, mask_u8, lse_r, lse_c, out8, saved)
         ctx.gst = gst
         ctx.hp = (thr, gw, lw, scale, code, path)
         return out8[:7].clone()
 
     @staticmethod
     def backward(ctx, grad7):
-        v, l, mask_u8, lse_r, lse_c, out8, inv_norm = ctx.saved_tensors
+        v, l, mask_u8, lse_r, lse_c, out8, saved = ctx.saved_tensors
         thr, gw, lw, scale, code, path = ctx.hp
         gst = ctx.gst
         B, P, D = v.shape
         T = l.shape[1]
         dev = v.device
+        inv_norm, tt_logits, g_inv = saved[:B * (P + T)], saved[B * (P + T):B * (P + T) + B * T * T], saved[B * (P + T) + B * T * T:]
         grad7 = grad7.to(torch.float32).contiguous()
         with torch.cuda.device(dev):
             coef = torch.empty(8, dtype=torch.float32, device=dev)
@@ -174,8 +177,9 @@ class _SparcFunction(torch.autograd.Function):
             dv = torch.empty_like(v)
             dl = torch.empty_like(l)
             _lib.call("cfa_sparc_bwd", v.data_ptr(), l.data_ptr(), mask_u8.data_ptr(), B, P, T, D, code, thr, scale,
-                      inv_norm.data_ptr(), lse_r.data_ptr(), lse_c.data_ptr(), coef[2:4].data_ptr(), dpv.data_ptr(),
-                      dpl.data_ptr(), dv.data_ptr(), dl.data_ptr(), path, _lib.stream_ptr())
+                      inv_norm.data_ptr(), lse_r.data_ptr(), lse_c.data_ptr(), tt_logits.data_ptr(), g_inv.data_ptr(),
+                      coef[2:4].data_ptr(), dpv.data_ptr(), dpl.data_ptr(), dv.data_ptr(), dl.data_ptr(), path,
+                      _lib.stream_ptr())
         return dv, dl, None, None, None, None, None, None, None, None
 
 

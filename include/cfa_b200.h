@@ -118,22 +118,24 @@ int cfa_global_infonce_bwd(const float* a_loc, const float* b_loc, const float* 
  * ---------------------------------------------------------------------------------------------- */
 int cfa_sparc_fwd(const void* v, const void* l, const uint8_t* mask, int B, int P, int T, int D, int dtype,
                   float thr, float scale, float* row_inv_norm, float* pooled_v, float* pooled_l, float* lse_row,
-                  float* lse_col, float* local_partial, int path, void* stream);
+                  float* lse_col, float* local_partial, float* tt_logits, float* g_inv_norm, int path, void* stream);
 
 /*
  * Backward of the above.  coef: DEVICE pointer to 2 floats = upstream coefficient of loss_vl_local and
  * loss_lv_local, already divided by n_valid.  dpooled_v / dpooled_l [B,D]: gradient w.r.t. the pooled
  * means (from the global InfoNCE), may be NULL.  dv [B,P,D], dl [B,T,D] are written in `dtype`.
  *
- * row_inv_norm: [B*(P+T)] floats of scratch saved between forward and backward (1/max(|v_p|,eps) then
- * 1/max(|l_t|,eps)); written by cfa_sparc_fwd, read by cfa_sparc_bwd.
+ * Saved between forward and backward (written by cfa_sparc_fwd, read by cfa_sparc_bwd; the CUDA-core path
+ * ignores them): row_inv_norm [B*(P+T)] = 1/max(|v_p|,eps) then 1/max(|l_t|,eps); tt_logits [B*T*T] = the masked,
+ * scaled token x token logits (fp32, 24 KB per sample — NOT the T x P similarity, which never leaves the SM);
+ * g_inv_norm [B*T] = 1/max(|G_t|,eps).
  * path: 0 = auto, 1 = fp32-exact CUDA-core kernels, 2 = tcgen05 tensor-core kernels (bf16, D % 256 == 0,
  * P <= 256, T <= 128; CFA_ERR_UNSUPPORTED otherwise).  cfa_sparc_path reports what `auto` resolves to.
  */
 int cfa_sparc_bwd(const void* v, const void* l, const uint8_t* mask, int B, int P, int T, int D, int dtype,
                   float thr, float scale, const float* row_inv_norm, const float* lse_row, const float* lse_col,
-                  const float* coef, const float* dpooled_v, const float* dpooled_l, void* dv, void* dl, int path,
-                  void* stream);
+                  const float* tt_logits, const float* g_inv_norm, const float* coef, const float* dpooled_v,
+                  const float* dpooled_l, void* dv, void* dl, int path, void* stream);
 int cfa_sparc_path(int P, int T, int D, int dtype, int path);
 int cfa_sparc_bwd_path(int P, int T, int D, int dtype, int path);   /* backward: tensor cores need P <= ~224 at T = 77 */
 
