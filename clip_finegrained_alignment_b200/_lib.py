@@ -53,6 +53,7 @@ SIGNATURES = {
     "cfa_sparc_coef": (C.c_int, [_vp, _f, _f, _i, _vp, _vp, _vp]),
     "cfa_debug_set_profile_buffer": (C.c_int, [_vp]),
     "cfa_tc_selftest": (C.c_int, [_i, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    "cfa_tc_selftest_timed": (C.c_int, [_i, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _vp]),
 }
 
 for _name, (_res, _args) in SIGNATURES.items():

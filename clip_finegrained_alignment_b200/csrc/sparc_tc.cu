@@ -22,6 +22,7 @@ using namespace tc;
 typedef __nv_bfloat16 bf16;
 
 constexpr int kTcThreads = 192;
+constexpr int kTcBwdThreads = 320;      // + 4 warps that only write dv / dl in the last pass
 constexpr float kTcNormEps = 1e-12f, kTcMinMaxEps = 1e-8f, kTcClampEps = 1e-8f;
 constexpr uint32_t kTmemCols = 512, kTmemG = 256, kTmemL = 384;
 
@@ -205,65 +206,66 @@ sparc_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_consta
       }
     }
   } else if (warp == 1) {
-    // =============================== MMA issuer ===============================
-    if (lane == 0) {
+    // =============================== MMA issuer (warp-uniform control flow, one elected lane issues) ===============================
+    const bool leader = elect_one();
+    {
       const uint32_t idesc_s = make_idesc_bf16(128, NP, false, false);
       const uint32_t idesc_g = make_idesc_bf16(128, 64, false, true);
       const uint32_t idesc_l = make_idesc_bf16(128, NT, false, false);
       const uint32_t il_lbo = (uint32_t)NT * 16;      // interleaved operand: next 8-wide k chunk
+      // Descriptors are built once; the issue loops only add to the 14-bit start-address field (units of 16 B),
+      // so the single issuing thread spends a handful of instructions per MMA.
+      const uint64_t sw0 = make_smem_desc(0, 16, 1024, kLayoutSw128);
+      const uint64_t ilk_whi = make_smem_desc(smem_u32(Whi), il_lbo, 128, kLayoutNone);
+      const uint64_t ilk_wlo = make_smem_desc(smem_u32(Wlo), il_lbo, 128, kLayoutNone);
+      const uint32_t ilk_step = (2 * il_lbo) >> 4;
       // ---- pass 0: S = l . v^T
       for (int u = 0; u < KB; ++u) {
         const int slot = u % NS;
         mbar_wait(full + slot, (u / NS) & 1);
         tc_fence_after();
         const uint32_t sl = smem_u32(base + (size_t)slot * L.stage_bytes), sv = sl + L.l_bytes;
+        const uint64_t dl0 = sw0 | (sl >> 4), dv0 = sw0 | (sv >> 4);
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_ss(tmem, make_smem_desc(sl + k * 32, 16, 1024, kLayoutSw128), make_smem_desc(sv + k * 32, 16, 1024, kLayoutSw128),
-                  idesc_s, (u | k) != 0);
-        umma_commit(empty + slot);
+        for (int k = 0; k < 4; ++k) umma_ss_w(leader, tmem, dl0 + 2 * k, dv0 + 2 * k, idesc_s, (u | k) != 0);
+        umma_commit_w(leader, empty + slot);
       }
-      umma_commit(s_full);
+      umma_commit_w(leader, s_full);
       // ---- pass 1: G_kb = W . v_kb ; L += G_kb . l_kb^T   (G issued one block ahead of L)
       mbar_wait(w_ready, 0);
       tc_fence_after();
+      const int nks = NP / 16;
       auto issue_g = [&](int kb) {
         const int u = KB + kb, slot = u % NS, buf = kb & 1;
         mbar_wait(full + slot, (u / NS) & 1);
         mbar_wait(g_free + buf, ((kb >> 1) & 1) ^ 1);
         tc_fence_after();
-        const uint32_t sv = smem_u32(base + (size_t)slot * L.stage_bytes) + L.l_bytes;
+        const uint64_t dv0 = sw0 | ((smem_u32(base + (size_t)slot * L.stage_bytes) + L.l_bytes) >> 4);
         const uint32_t d = tmem + kTmemG + 64 * buf;
-        const int nks = NP / 16;
-        for (int half = 0; half < 2; ++half) {
-          const uint32_t wa = smem_u32(half ? Wlo : Whi);
-          for (int ks = 0; ks < nks; ++ks)
-            umma_ss(d, make_smem_desc(wa + ks * 2 * il_lbo, il_lbo, 128, kLayoutNone),
-                    make_smem_desc(sv + ks * 2048, 16, 1024, kLayoutSw128), idesc_g, (half | ks) != 0);
-        }
-        umma_commit(g_full + buf);
+        for (int ks = 0; ks < nks; ++ks) umma_ss_w(leader, d, ilk_whi + ks * ilk_step, dv0 + ks * 128, idesc_g, ks != 0);
+        for (int ks = 0; ks < nks; ++ks) umma_ss_w(leader, d, ilk_wlo + ks * ilk_step, dv0 + ks * 128, idesc_g, true);
+        umma_commit_w(leader, g_full + buf);
       };
       auto issue_l = [&](int kb) {
         const int u = KB + kb, slot = u % NS, buf = kb & 1;
         mbar_wait(gs_ready + buf, (kb >> 1) & 1);
         tc_fence_after();
-        const uint32_t sl = smem_u32(base + (size_t)slot * L.stage_bytes);
-        for (int half = 0; half < 2; ++half) {
-          const uint32_t ga = smem_u32(Gs + (size_t)(2 * buf + half) * L.g_bytes);
+        const uint64_t dl0 = sw0 | (smem_u32(base + (size_t)slot * L.stage_bytes) >> 4);
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_ss(tmem + kTmemL, make_smem_desc(ga + k * 2 * il_lbo, il_lbo, 128, kLayoutNone),
-                    make_smem_desc(sl + k * 32, 16, 1024, kLayoutSw128), idesc_l, (kb | half | k) != 0);
+        for (int half = 0; half < 2; ++half) {
+          const uint64_t ga = make_smem_desc(smem_u32(Gs + (size_t)(2 * buf + half) * L.g_bytes), il_lbo, 128, kLayoutNone);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_ss_w(leader, tmem + kTmemL, ga + k * ilk_step, dl0 + 2 * k, idesc_l, (kb | half | k) != 0);
         }
-        umma_commit(gs_free + buf);
-        umma_commit(empty + slot);
+        umma_commit_w(leader, gs_free + buf);
+        umma_commit_w(leader, empty + slot);
       };
       issue_g(0);
       for (int kb = 0; kb < KB; ++kb) {
         if (kb + 1 < KB) issue_g(kb + 1);
         issue_l(kb);
       }
-      umma_commit(l_full);
+      umma_commit_w(leader, l_full);
     }
   } else {
     // =============================== epilogue (4 warps, thread = token row) ===============================
@@ -494,7 +496,7 @@ __host__ __device__ inline TcBwdLayout tc_bwd_layout(int P, int T, int D, int NS
   L.off_dl = L.off_w + 2 * L.w_bytes + (2 * L.w_bytes > sc_bytes ? 2 * L.w_bytes : ((sc_bytes + 15) & ~15u));   // dLhi, dLlo
   L.off_g = L.off_dl + 2 * L.dl_bytes;                // 4 operand buffers of g_bytes
   L.off_f = L.off_g + 4 * L.g_bytes + 1024;           // phantom rows of the last buffer stay in bounds
-  L.off_bar = (L.off_f + 4 * (2 * (L.NP + 32) + 5 * L.NT + 32) + 7) & ~7u;
+  L.off_bar = (L.off_f + 4 * (2 * (L.NP + 32) + 6 * L.NT + 2 * D + 32) + 7) & ~7u;
   L.total = L.off_bar + 8 * (2 * L.NS + 34) + 16;
   return L;
 }
@@ -539,7 +541,7 @@ __device__ __forceinline__ uint4 pack_bf16x8(const float* f) {
   return make_uint4(w[0], w[1], w[2], w[3]);
 }
 
-__global__ void __launch_bounds__(kTcThreads, 1)
+__global__ void __launch_bounds__(kTcBwdThreads, 1)
 sparc_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmL, const TcBwdParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* base = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -562,6 +564,8 @@ sparc_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_consta
   float* lser = msk + NT;                              // [NT]
   float* lsec = lser + NT;                             // [NT]
   float* ldot = lsec + NT;                             // [NT]
+  float* lfacs = ldot + NT;                            // [NT]   (l^_t . dl^_t) / |l_t|^2
+  float* dpool = lfacs + NT;                           // [2][D] gradient w.r.t. the pooled means of this sample
   uint64_t* bars = (uint64_t*)(base + L.off_bar);
   uint64_t* full = bars;
   uint64_t* empty = bars + NS;
@@ -589,7 +593,11 @@ sparc_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_consta
     tma_prefetch_desc(&tmL);
   }
   if (warp == 1) tmem_alloc(tmem_slot, kTmemCols);
-  for (int i = threadIdx.x; i < 2 * (NP + 32) + 5 * NT; i += kTcThreads) {
+  for (int i = threadIdx.x; i < 2 * D; i += kTcBwdThreads) {
+    const float* src = (i < D) ? p.dpool_v : p.dpool_l;
+    dpool[i] = src ? src[(size_t)b * D + (i < D ? i : i - D)] : 0.f;
+  }
+  for (int i = threadIdx.x; i < 2 * (NP + 32) + 5 * NT; i += kTcBwdThreads) {
     if (i < NP + 32) ivn[i] = (i < P) ? p.inv_vn[(size_t)b * P + i] : 0.f;
     else if (i < 2 * (NP + 32)) vdot[i - NP - 32] = 0.f;
     else {
@@ -623,21 +631,27 @@ sparc_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_consta
       }
     }
   } else if (warp == 1) {
-    // =============================== MMA issuer ===============================
-    if (lane == 0) {
+    // =============================== MMA issuer (warp-uniform control flow, one elected lane issues) ===============================
+    const bool leader = elect_one();
+    {
       const uint32_t id_s = make_idesc_bf16(128, NP, false, false);     // [T x NP]  K-major x K-major
       const uint32_t id_kn32 = make_idesc_bf16(128, 32, false, true);   // A K-major, B MN-major, N = 32
       const uint32_t id_nn32 = make_idesc_bf16(128, 32, true, true);    // A MN-major, B MN-major, N = 32
-      const uint32_t id_l = make_idesc_bf16(128, NT, false, false);
       const int nksP = NP / 16, nksT = NT / 16;
-      auto il_k = [&](const uint8_t* a, int ks) { return make_smem_desc(smem_u32(a) + ks * 2 * il_lbo, il_lbo, 128, kLayoutNone); };
-      auto il_mn = [&](const uint8_t* a, int ks, int mtile) {
-        return make_smem_desc(smem_u32(a) + mtile * 16 * il_lbo + ks * 256, 128, il_lbo, kLayoutNone);
-      };
-      auto sw_k = [&](uint32_t s, int k) { return make_smem_desc(s + k * 32, 16, 512, kLayoutSw64); };
-      auto sw_mn = [&](uint32_t s, int ks) { return make_smem_desc(s + ks * 1024, 16, 512, kLayoutSw64); };
-
-      long long* pf = p.prof ? p.prof + (size_t)b * 32 : nullptr;
+      // Base descriptors built once; issue loops only add to the start-address field (units of 16 B).
+      const uint64_t sw0 = make_smem_desc(0, 16, 512, kLayoutSw64);     // TMA tiles, K-major and MN-major alike
+      auto ilk = [&](const uint8_t* a) { return make_smem_desc(smem_u32(a), il_lbo, 128, kLayoutNone); };   // interleaved, K-major
+      auto ilm = [&](const uint8_t* a) { return make_smem_desc(smem_u32(a), 128, il_lbo, kLayoutNone); };   // interleaved, MN-major
+      const uint32_t ks_k = (2 * il_lbo) >> 4;       // K-major interleaved: two 8-wide chunks per k-step
+      const uint32_t ks_m = 256 >> 4;                // MN-major interleaved: 16 k-rows of 16 B
+      const uint32_t mt_m = il_lbo;                  // MN-major interleaved: second 128-row M tile = 16 groups * il_lbo / 16
+      const uint64_t k_whi = ilk(Whi), k_wlo = ilk(Wlo), k_dshi = ilk(DShi), k_dslo = ilk(DSlo);
+      const uint64_t k_dlhi = ilk(dLhi), k_dllo = ilk(dLlo);
+      const uint64_t m_whi = ilm(Whi), m_wlo = ilm(Wlo), m_dshi = ilm(DShi), m_dslo = ilm(DSlo);
+      const uint64_t m_dlhi = ilm(dLhi), m_dllo = ilm(dLlo);
+      const uint64_t k_g0 = ilk(Gb), k_g1 = ilk(Gb + L.g_bytes), k_g2 = ilk(Gb + 2 * L.g_bytes), k_g3 = ilk(Gb + 3 * L.g_bytes);
+      const uint64_t m_g0 = ilm(Gb), m_g1 = ilm(Gb + L.g_bytes), m_g2 = ilm(Gb + 2 * L.g_bytes), m_g3 = ilm(Gb + 3 * L.g_bytes);
+      long long* pf = (p.prof && leader) ? p.prof + (size_t)b * 32 : nullptr;
       int pi = 0;
       auto stamp = [&]() { if (pf) pf[pi++] = clock64(); };
       stamp();
@@ -647,28 +661,28 @@ sparc_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_consta
         mbar_wait(full + slot, (u / NS) & 1);
         tc_fence_after();
         const uint32_t sl = smem_u32(base + (size_t)slot * L.stage_bytes), sv = sl + L.l_bytes;
+        const uint64_t dl0 = sw0 | (sl >> 4), dv0 = sw0 | (sv >> 4);
 #pragma unroll
-        for (int k = 0; k < 2; ++k) umma_ss(tmem + cS, sw_k(sl, k), sw_k(sv, k), id_s, (u | k) != 0);
-        umma_commit(empty + slot);
+        for (int k = 0; k < 2; ++k) umma_ss_w(leader, tmem + cS, dl0 + 2 * k, dv0 + 2 * k, id_s, (u | k) != 0);
+        umma_commit_w(leader, empty + slot);
       }
-      umma_commit(s_full);
+      umma_commit_w(leader, s_full);
       stamp();
 
-      // G_kb = W . v_kb (hi, lo) into TMEM cG[buf]; optionally X_kb = dLhat . l_kb into cX[buf]
-      auto issue_gx = [&](int pass, int kb, uint64_t* gfull, uint64_t* gfree, bool with_x) {
+      // G_kb = W . v_kb (hi, lo) into TMEM cG[buf]; X_kb = dLhat . l_kb into cX[buf]
+      auto issue_gx = [&](int pass, int kb, uint64_t* gfull, uint64_t* gfree) {
         const int u = pass * KB + kb, slot = u % NS, buf = kb & 1;
         mbar_wait(full + slot, (u / NS) & 1);
         mbar_wait(gfree + buf, ((kb >> 1) & 1) ^ 1);
         tc_fence_after();
         const uint32_t sl = smem_u32(base + (size_t)slot * L.stage_bytes), sv = sl + L.l_bytes;
-        for (int half = 0; half < 2; ++half)
-          for (int ks = 0; ks < nksP; ++ks)
-            umma_ss(tmem + cG + 32 * buf, il_k(half ? Wlo : Whi, ks), sw_mn(sv, ks), id_kn32, (half | ks) != 0);
-        if (with_x)
-          for (int half = 0; half < 2; ++half)
-            for (int ks = 0; ks < nksT; ++ks)
-              umma_ss(tmem + cX + 32 * buf, il_k(half ? dLlo : dLhi, ks), sw_mn(sl, ks), id_kn32, (half | ks) != 0);
-        umma_commit(gfull + buf);
+        const uint64_t dl0 = sw0 | (sl >> 4), dv0 = sw0 | (sv >> 4);
+        const uint32_t dg = tmem + cG + 32 * buf, dx = tmem + cX + 32 * buf;
+        for (int ks = 0; ks < nksP; ++ks) umma_ss_w(leader, dg, k_whi + ks * ks_k, dv0 + ks * 64, id_kn32, ks != 0);
+        for (int ks = 0; ks < nksP; ++ks) umma_ss_w(leader, dg, k_wlo + ks * ks_k, dv0 + ks * 64, id_kn32, true);
+        for (int ks = 0; ks < nksT; ++ks) umma_ss_w(leader, dx, k_dlhi + ks * ks_k, dl0 + ks * 64, id_kn32, ks != 0);
+        for (int ks = 0; ks < nksT; ++ks) umma_ss_w(leader, dx, k_dllo + ks * ks_k, dl0 + ks * 64, id_kn32, true);
+        umma_commit_w(leader, gfull + buf);
       };
 
       // (the T x T logits and ||G|| come from the forward: no second pass)
@@ -680,67 +694,63 @@ sparc_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_consta
       mbar_wait(dl_ready, 0);
       tc_fence_after();
       stamp();
-      issue_gx(1, 0, g_full3, g_free3, true);
+      issue_gx(1, 0, g_full3, g_free3);
       for (int kb = 0; kb < KB; ++kb) {
-        if (kb + 1 < KB) issue_gx(1, kb + 1, g_full3, g_free3, true);
+        if (kb + 1 < KB) issue_gx(1, kb + 1, g_full3, g_free3);
         const int u = KB + kb, slot = u % NS, buf = kb & 1;
         mbar_wait(dg_ready3 + buf, (kb >> 1) & 1);
         tc_fence_after();
-        const uint32_t sv = smem_u32(base + (size_t)slot * L.stage_bytes) + L.l_bytes;
-        for (int half = 0; half < 2; ++half)
+        const uint64_t dv0 = sw0 | ((smem_u32(base + (size_t)slot * L.stage_bytes) + L.l_bytes) >> 4);
+        const uint64_t a_hi = buf ? k_g2 : k_g0, a_lo = buf ? k_g3 : k_g1;
 #pragma unroll
-          for (int k = 0; k < 2; ++k)
-            umma_ss(tmem + cS, il_k(Gb + (size_t)(2 * buf + half) * L.g_bytes, k), sw_k(sv, k), id_s, (kb | half | k) != 0);
-        umma_commit(dg_free3 + buf);
-        umma_commit(empty + slot);
+        for (int k = 0; k < 2; ++k) umma_ss_w(leader, tmem + cS, a_hi + k * ks_k, dv0 + 2 * k, id_s, (kb | k) != 0);
+#pragma unroll
+        for (int k = 0; k < 2; ++k) umma_ss_w(leader, tmem + cS, a_lo + k * ks_k, dv0 + 2 * k, id_s, true);
+        umma_commit_w(leader, dg_free3 + buf);
+        umma_commit_w(leader, empty + slot);
       }
-      umma_commit(dw_full);
+      umma_commit_w(leader, dw_full);
       stamp();
 
-      // ---- pass 4: dv_kb, dl_kb
+      // ---- pass 4: dv_kb, dl_kb      (smem operands: G = Gb[0,1], dG = Gb[2,3], hi / lo)
       mbar_wait(ds_ready, 0);
       tc_fence_after();
       stamp();
-      const uint8_t* Ghi = Gb; const uint8_t* Glo = Gb + L.g_bytes;
-      const uint8_t* dGhi = Gb + 2 * L.g_bytes; const uint8_t* dGlo = Gb + 3 * L.g_bytes;
-      issue_gx(2, 0, g_full4, g_free4, true);
+      issue_gx(2, 0, g_full4, g_free4);
       for (int kb = 0; kb < KB; ++kb) {
-        if (kb + 1 < KB) issue_gx(2, kb + 1, g_full4, g_free4, true);
+        if (kb + 1 < KB) issue_gx(2, kb + 1, g_full4, g_free4);
         const int u = 2 * KB + kb, slot = u % NS, buf = kb & 1;
         mbar_wait(gs_ready4, kb & 1);
         mbar_wait(out_free + buf, ((kb >> 1) & 1) ^ 1);
         tc_fence_after();
         const uint32_t sl = smem_u32(base + (size_t)slot * L.stage_bytes), sv = sl + L.l_bytes;
+        const uint64_t dl0 = sw0 | (sl >> 4), dv0 = sw0 | (sv >> 4);
+#pragma unroll
         for (int m = 0; m < 2; ++m) {                 // dv rows p = 128 m ...
           const uint32_t d = tmem + cDV + 64 * buf + 32 * m;
-          bool acc = false;
-          for (int half = 0; half < 2; ++half)
-            for (int ks = 0; ks < nksT; ++ks) { umma_ss(d, il_mn(half ? DSlo : DShi, ks, m), sw_mn(sl, ks), id_nn32, acc); acc = true; }
-          for (int c = 0; c < 3; ++c) {               // W^T . dG : hi.hi + hi.lo + lo.hi
-            const uint8_t* wa = (c == 2) ? Wlo : Whi;
-            const uint8_t* ga = (c == 1) ? dGlo : dGhi;
-            for (int ks = 0; ks < nksT; ++ks) umma_ss(d, il_mn(wa, ks, m), il_mn(ga, ks, 0), id_nn32, true);
-          }
+          const uint32_t mo = m * mt_m;
+          for (int ks = 0; ks < nksT; ++ks) umma_ss_w(leader, d, m_dshi + mo + ks * ks_m, dl0 + ks * 64, id_nn32, ks != 0);
+          for (int ks = 0; ks < nksT; ++ks) umma_ss_w(leader, d, m_dslo + mo + ks * ks_m, dl0 + ks * 64, id_nn32, true);
+          for (int ks = 0; ks < nksT; ++ks) umma_ss_w(leader, d, m_whi + mo + ks * ks_m, m_g2 + ks * ks_m, id_nn32, true);   // W^T . dG: hi.hi
+          for (int ks = 0; ks < nksT; ++ks) umma_ss_w(leader, d, m_whi + mo + ks * ks_m, m_g3 + ks * ks_m, id_nn32, true);   //          hi.lo
+          for (int ks = 0; ks < nksT; ++ks) umma_ss_w(leader, d, m_wlo + mo + ks * ks_m, m_g2 + ks * ks_m, id_nn32, true);   //          lo.hi
         }
         {                                             // dl rows t
           const uint32_t d = tmem + cDL + 32 * buf;
-          bool acc = false;
-          for (int half = 0; half < 2; ++half)
-            for (int ks = 0; ks < nksP; ++ks) { umma_ss(d, il_k(half ? DSlo : DShi, ks), sw_mn(sv, ks), id_kn32, acc); acc = true; }
-          for (int c = 0; c < 3; ++c) {               // dLhat^T . G
-            const uint8_t* la = (c == 2) ? dLlo : dLhi;
-            const uint8_t* ga = (c == 1) ? Glo : Ghi;
-            for (int ks = 0; ks < nksT; ++ks) umma_ss(d, il_mn(la, ks, 0), il_mn(ga, ks, 0), id_nn32, true);
-          }
+          for (int ks = 0; ks < nksP; ++ks) umma_ss_w(leader, d, k_dshi + ks * ks_k, dv0 + ks * 64, id_kn32, ks != 0);
+          for (int ks = 0; ks < nksP; ++ks) umma_ss_w(leader, d, k_dslo + ks * ks_k, dv0 + ks * 64, id_kn32, true);
+          for (int ks = 0; ks < nksT; ++ks) umma_ss_w(leader, d, m_dlhi + ks * ks_m, m_g0 + ks * ks_m, id_nn32, true);       // dLhat^T . G
+          for (int ks = 0; ks < nksT; ++ks) umma_ss_w(leader, d, m_dlhi + ks * ks_m, m_g1 + ks * ks_m, id_nn32, true);
+          for (int ks = 0; ks < nksT; ++ks) umma_ss_w(leader, d, m_dllo + ks * ks_m, m_g0 + ks * ks_m, id_nn32, true);
         }
-        umma_commit(out_full + buf);
-        umma_commit(gs_free4);
-        umma_commit(empty + slot);
+        umma_commit_w(leader, out_full + buf);
+        umma_commit_w(leader, gs_free4);
+        umma_commit_w(leader, empty + slot);
       }
       stamp();
     }
-  } else {
-    // =============================== epilogue (4 warps, thread = TMEM lane) ===============================
+  } else if (warp < 6) {
+    // =============================== epilogue A (4 warps, thread = TMEM lane) ===============================
     const int q = warp & 3;
     const int row = 32 * q + lane;
     const uint32_t trow = tmem + ((uint32_t)(32 * q) << 16);
@@ -996,69 +1006,17 @@ sparc_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_consta
       }
       if (c0 + lane < NP) atomicAdd(vdot + c0 + lane, mine);
     }
-    const float lfac = (sdot + ldl_j) * il * il;        // (l^_t . dl^_t) / ||l_t||^2
+    if (row < NT) lfacs[row] = (sdot + ldl_j) * il * il;   // (l^_t . dl^_t) / ||l_t||^2
     epi_bar_sync();
     for (int i = threadIdx.x - 64; i < NP; i += 128) vdot[i] = vdot[i] * ivn[i] * ivn[i];   // -> vfac_p
-    epi_bar_sync();
+    asm volatile("bar.sync 2, 256;" ::: "memory");      // vfac / lfac visible to the output warps (epilogue B)
     tc_fence_before();
     fence_proxy_async();
     __syncwarp();
     if (lane == 0) mbar_arrive(ds_ready);
     stamp();
 
-    // ---- pass 4 epilogue: operands G_kb, dG_kb (hi/lo) -> smem; outputs dv_kb, dl_kb -> global
-    float cnt = 0.f;
-    for (int t = 0; t < T; ++t) cnt += msk[t];
-    const float invc = 1.f / fmaxf(cnt, kTcClampEps), invP = 1.f / (float)P;
-    const float mrow = (row < NT) ? msk[row] : 0.f;
-    auto output = [&](int kb) {
-      const int buf = kb & 1, d0 = kb * 32;
-      mbar_wait(out_full + buf, (kb >> 1) & 1);
-      tc_fence_after();
-      float x[32];
-#pragma unroll
-      for (int m = 0; m < 2; ++m) {
-        const int pr = 128 * m + row;
-        tmem_ld32(trow + cDV + 64 * buf + 32 * m, x);
-        tmem_ld_wait();
-        if (pr < P) {
-          const bf16* vsrc = p.v + ((size_t)b * P + pr) * D + d0;
-          bf16* dst = p.dv + ((size_t)b * P + pr) * D + d0;
-          const float vf = vdot[pr];
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            float vv[8], o[8];
-            unpack_bf16x8(__ldg(reinterpret_cast<const uint4*>(vsrc) + g), vv);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              o[j] = fmaf(-vv[j], vf, x[8 * g + j]);
-              if (p.dpool_v) o[j] = fmaf(__ldg(p.dpool_v + (size_t)b * D + d0 + 8 * g + j), invP, o[j]);
-            }
-            reinterpret_cast<uint4*>(dst)[g] = pack_bf16x8(o);
-          }
-        }
-      }
-      tmem_ld32(trow + cDL + 32 * buf, x);
-      tmem_ld_wait();
-      if (row < T) {
-        const bf16* lsrc = p.l + ((size_t)b * T + row) * D + d0;
-        bf16* dst = p.dl + ((size_t)b * T + row) * D + d0;
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          float lv[8], o[8];
-          unpack_bf16x8(__ldg(reinterpret_cast<const uint4*>(lsrc) + g), lv);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            o[j] = fmaf(-lv[j], lfac, x[8 * g + j]);
-            if (p.dpool_l) o[j] = fmaf(__ldg(p.dpool_l + (size_t)b * D + d0 + 8 * g + j) * mrow, invc, o[j]);
-          }
-          reinterpret_cast<uint4*>(dst)[g] = pack_bf16x8(o);
-        }
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(out_free + buf);
-    };
+    // ---- pass 4, epilogue A: operands G_kb, dG_kb (hi/lo) -> smem (B operands of the dv / dl MMAs)
     for (int kb = 0; kb < KB; ++kb) {
       const int buf = kb & 1;
       mbar_wait(g_full4 + buf, (kb >> 1) & 1);
@@ -1093,11 +1051,70 @@ sparc_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_consta
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(gs_ready4);
-      if (kb > 0) output(kb - 1);
     }
-    output(KB - 1);
     stamp();
     tc_fence_before();
+  } else {
+    // =============================== epilogue B (4 warps): dv_kb, dl_kb -> global ===============================
+    const int q = warp & 3;
+    const int row = 32 * q + lane;
+    const uint32_t trow = tmem + ((uint32_t)(32 * q) << 16);
+    asm volatile("bar.sync 2, 256;" ::: "memory");      // wait for vfac / lfac
+    float cnt = 0.f;
+    for (int t = 0; t < T; ++t) cnt += msk[t];
+    const float invc = 1.f / fmaxf(cnt, kTcClampEps), invP = 1.f / (float)P;
+    const float mrow = (row < NT) ? msk[row] * invc : 0.f;
+    const float lfac = (row < NT) ? lfacs[row] : 0.f;
+    const float vf0 = (row < P) ? vdot[row] : 0.f, vf1 = (128 + row < P) ? vdot[128 + row] : 0.f;
+    for (int kb = 0; kb < KB; ++kb) {
+      const int buf = kb & 1, d0 = kb * 32;
+      mbar_wait(out_full + buf, (kb >> 1) & 1);
+      tc_fence_after();
+      float x0[32], x1[32], x2[32];
+      tmem_ld32(trow + cDV + 64 * buf, x0);
+      tmem_ld32(trow + cDV + 64 * buf + 32, x1);
+      tmem_ld32(trow + cDL + 32 * buf, x2);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(out_free + buf);        // TMEM buffers are free as soon as they are in registers
+#pragma unroll
+      for (int m = 0; m < 2; ++m) {
+        const int pr = 128 * m + row;
+        if (pr < P) {
+          const float* x = m ? x1 : x0;
+          const float vf = m ? vf1 : vf0;
+          const bf16* vsrc = p.v + ((size_t)b * P + pr) * D + d0;
+          bf16* dst = p.dv + ((size_t)b * P + pr) * D + d0;
+          uint4 raw[4];
+#pragma unroll
+          for (int g = 0; g < 4; ++g) raw[g] = __ldg(reinterpret_cast<const uint4*>(vsrc) + g);
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            float vv[8], o[8];
+            unpack_bf16x8(raw[g], vv);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] = fmaf(dpool[d0 + 8 * g + j], invP, fmaf(-vv[j], vf, x[8 * g + j]));
+            reinterpret_cast<uint4*>(dst)[g] = pack_bf16x8(o);
+          }
+        }
+      }
+      if (row < T) {
+        const bf16* lsrc = p.l + ((size_t)b * T + row) * D + d0;
+        bf16* dst = p.dl + ((size_t)b * T + row) * D + d0;
+        uint4 raw[4];
+#pragma unroll
+        for (int g = 0; g < 4; ++g) raw[g] = __ldg(reinterpret_cast<const uint4*>(lsrc) + g);
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          float lv[8], o[8];
+          unpack_bf16x8(raw[g], lv);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] = fmaf(dpool[D + d0 + 8 * g + j], mrow, fmaf(-lv[j], lfac, x2[8 * g + j]));
+          reinterpret_cast<uint4*>(dst)[g] = pack_bf16x8(o);
+        }
+      }
+    }
   }
   __syncthreads();
   if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem, kTmemCols); }
@@ -1128,7 +1145,7 @@ int sparc_bwd_tc_launch(const void* v, const void* l, const uint8_t* mask, int B
                   tt_logits, g_inv_norm, dpv, dpl, (const bf16*)v, (const bf16*)l, (bf16*)dv, (bf16*)dl};
   const size_t smem = L.total + 1024;
   CFA_CUDA_TRY(cudaFuncSetAttribute(sparc_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  sparc_bwd_tc_kernel<<<B, kTcThreads, smem, st>>>(tmV, tmL, prm);
+  sparc_bwd_tc_kernel<<<B, kTcBwdThreads, smem, st>>>(tmV, tmL, prm);
   return launch_status();
 }
 

@@ -112,6 +112,17 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, bool a_mn_m
          ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+// one lane of a converged warp
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\t"
+      "elect.sync rx|px, 0xFFFFFFFF;\n\t"
+      "selp.u32 %0, 1, 0, px;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // D[tmem] (+)= A[smem] . B[smem]   (one thread issues)
 __device__ __forceinline__ void umma_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, bool accumulate) {
   asm volatile(
@@ -120,6 +131,26 @@ __device__ __forceinline__ void umma_ss(uint32_t d_tmem, uint64_t a_desc, uint64
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"((uint32_t)accumulate) : "memory");
 }
+// Warp-uniform variants: call from ALL lanes of a converged warp; `leader` (from elect_one(), fixed for the
+// whole kernel so that commits track the same thread's MMAs) predicates the instruction itself, so descriptor
+// arithmetic stays in the uniform datapath instead of being shuffled into uniform registers per instruction.
+__device__ __forceinline__ void umma_ss_w(bool leader, uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                          bool accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "setp.ne.b32 q, %5, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"((uint32_t)accumulate), "r"((uint32_t)leader) : "memory");
+}
+__device__ __forceinline__ void umma_commit_w(bool leader, uint64_t* bar) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "setp.ne.b32 q, %1, 0;\n\t"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}"
+      ::"r"(smem_u32(bar)), "r"((uint32_t)leader) : "memory");
+}
+
 // arrive on an mbarrier when every previously issued MMA of this thread has completed
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");

@@ -10,7 +10,7 @@ typedef __nv_bfloat16 bf16;
 __global__ void __launch_bounds__(128, 1)
 tc_selftest_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                    const bf16* __restrict__ A, const bf16* __restrict__ B, float* __restrict__ D, int a_mode,
-                   int b_mode, int N, int K) {
+                   int b_mode, int N, int K, int repeat, long long* cycles) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* base = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* As = base;                 // 64 KB
@@ -62,24 +62,38 @@ tc_selftest_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   if (tx_bytes) mbar_wait(&bar_tma, 0);
   tc_fence_after();
 
-  // ---- issue
-  if (tid == 0) {
+  // ---- issue: warp 0, warp-uniform control flow, descriptors advanced by adds on the start-address field
+  if (warp == 0) {
+    const bool leader = elect_one();
     const uint32_t idesc = make_idesc_bf16(128, N, a_mode == 2, b_mode == 1 || b_mode == 3 || b_mode == 5);
-    for (int ks = 0; ks < K / 16; ++ks) {
-      uint64_t da, db;
-      if (a_mode == 0) da = make_smem_desc(smem_u32(As) + (ks >> 2) * 16384 + (ks & 3) * 32, 16, 1024, kLayoutSw128);
-      else if (a_mode == 4) da = make_smem_desc(smem_u32(As) + (ks >> 1) * 8192 + (ks & 1) * 32, 16, 512, kLayoutSw64);
-      else if (a_mode == 1) da = make_smem_desc(smem_u32(As) + ks * 2 * (128 * 16), 128 * 16, 128, kLayoutNone);
-      else da = make_smem_desc(smem_u32(As) + ks * 256, 128, K * 16, kLayoutNone);
-      if (b_mode == 0) db = make_smem_desc(smem_u32(Bs) + (ks >> 2) * N * 128 + (ks & 3) * 32, 16, 1024, kLayoutSw128);
-      else if (b_mode == 1) db = make_smem_desc(smem_u32(Bs) + ks * 2048, 16, 1024, kLayoutSw128);
-      else if (b_mode == 4) db = make_smem_desc(smem_u32(Bs) + (ks >> 1) * N * 64 + (ks & 1) * 32, 16, 512, kLayoutSw64);
-      else if (b_mode == 5) db = make_smem_desc(smem_u32(Bs) + ks * 1024, 16, 512, kLayoutSw64);
-      else if (b_mode == 2) db = make_smem_desc(smem_u32(Bs) + ks * 2 * (N * 16), N * 16, 128, kLayoutNone);
-      else db = make_smem_desc(smem_u32(Bs) + ks * 256, 128, K * 16, kLayoutNone);
-      umma_ss(tmem, da, db, idesc, ks > 0);
-    }
-    umma_commit(&bar_mma);
+    // per k-step increments (units of 16 B) and per-K-block jumps for the TMA-tiled flavours
+    uint64_t da0, db0;
+    uint32_t a_ks, b_ks, a_blk = 0, b_blk = 0, a_per = 1 << 30, b_per = 1 << 30;
+    if (a_mode == 0) { da0 = make_smem_desc(smem_u32(As), 16, 1024, kLayoutSw128); a_ks = 2; a_per = 4; a_blk = 16384 >> 4; }
+    else if (a_mode == 4) { da0 = make_smem_desc(smem_u32(As), 16, 512, kLayoutSw64); a_ks = 2; a_per = 2; a_blk = 8192 >> 4; }
+    else if (a_mode == 1) { da0 = make_smem_desc(smem_u32(As), 128 * 16, 128, kLayoutNone); a_ks = (2 * 128 * 16) >> 4; }
+    else { da0 = make_smem_desc(smem_u32(As), 128, K * 16, kLayoutNone); a_ks = 256 >> 4; }
+    if (b_mode == 0) { db0 = make_smem_desc(smem_u32(Bs), 16, 1024, kLayoutSw128); b_ks = 2; b_per = 4; b_blk = (N * 128) >> 4; }
+    else if (b_mode == 4) { db0 = make_smem_desc(smem_u32(Bs), 16, 512, kLayoutSw64); b_ks = 2; b_per = 2; b_blk = (N * 64) >> 4; }
+    else if (b_mode == 1) { db0 = make_smem_desc(smem_u32(Bs), 16, 1024, kLayoutSw128); b_ks = 2048 >> 4; }
+    else if (b_mode == 5) { db0 = make_smem_desc(smem_u32(Bs), 16, 512, kLayoutSw64); b_ks = 1024 >> 4; }
+    else if (b_mode == 2) { db0 = make_smem_desc(smem_u32(Bs), N * 16, 128, kLayoutNone); b_ks = (2 * N * 16) >> 4; }
+    else { db0 = make_smem_desc(smem_u32(Bs), 128, K * 16, kLayoutNone); b_ks = 256 >> 4; }
+    const int nks = K / 16;
+    const long long t0 = clock64();
+    if (repeat > 1) {                       // throughput probe: same operands every time, no address arithmetic
+#pragma unroll 8
+      for (int i = 0; i < repeat * nks; ++i) umma_ss_w(leader, tmem, da0, db0, idesc, true);
+    } else
+    for (int rep = 0; rep < repeat; ++rep)
+      for (int ks = 0; ks < nks; ++ks) {
+        const uint64_t da = da0 + (ks / a_per) * a_blk + (ks % a_per) * a_ks;
+        const uint64_t db = db0 + (ks / b_per) * b_blk + (ks % b_per) * b_ks;
+        umma_ss_w(leader, tmem, da, db, idesc, ks > 0);
+      }
+    umma_commit_w(leader, &bar_mma);
+    mbar_wait(&bar_mma, 0);
+    if (cycles && leader) *cycles = clock64() - t0;
   }
   mbar_wait(&bar_mma, 0);
   tc_fence_after();
@@ -102,7 +116,16 @@ tc_selftest_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 using namespace cfa;
 
 // Debug / validation entry point (not part of the product surface; declared in include/cfa_b200.h).
+extern "C" int cfa_tc_selftest_timed(int a_mode, int b_mode, int N, int K, const void* A, const void* B, float* D,
+                                     int repeat, long long* d_cycles, void* stream);
+
 extern "C" int cfa_tc_selftest(int a_mode, int b_mode, int N, int K, const void* A, const void* B, float* D, void* stream) {
+  return cfa_tc_selftest_timed(a_mode, b_mode, N, K, A, B, D, 1, nullptr, stream);
+}
+
+// same, issuing the whole K loop `repeat` times back to back and reporting the issuing thread's clock64 span
+extern "C" int cfa_tc_selftest_timed(int a_mode, int b_mode, int N, int K, const void* A, const void* B, float* D,
+                                     int repeat, long long* d_cycles, void* stream) {
   if (N % 16 || N < 16 || N > 256 || K % 16 || K < 16 || K > 256) return CFA_ERR_BAD_ARG;
   if ((a_mode == 0 || b_mode == 0) && K % 64) return CFA_ERR_BAD_ARG;
   if ((a_mode == 4 || b_mode == 4) && K % 32) return CFA_ERR_BAD_ARG;
@@ -120,6 +143,6 @@ extern "C" int cfa_tc_selftest(int a_mode, int b_mode, int N, int K, const void*
   if (b_mode == 5 && (rc = make_tmap_bf16_3d(&tmB, B, 32, K, 1, 32, K)) != CFA_OK) return rc;
   const size_t smem = 2 * 65536 + 1024;
   CFA_CUDA_TRY(cudaFuncSetAttribute(tc_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  tc_selftest_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(tmA, tmB, (const bf16*)A, (const bf16*)B, D, a_mode, b_mode, N, K);
+  tc_selftest_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(tmA, tmB, (const bf16*)A, (const bf16*)B, D, a_mode, b_mode, N, K, repeat, d_cycles);
   return launch_status();
 }

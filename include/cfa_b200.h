@@ -171,6 +171,8 @@ int cfa_sparc_coef(const float* grad7, float gw, float lw, int global_batch, con
 /* tuning aid: device buffer [B][32] int64 receiving clock64 phase stamps of the tensor-core backward (NULL = off) */
 int cfa_debug_set_profile_buffer(void* device_buffer);
 int cfa_tc_selftest(int a_mode, int b_mode, int N, int K, const void* A, const void* B, float* D, void* stream);
+int cfa_tc_selftest_timed(int a_mode, int b_mode, int N, int K, const void* A, const void* B, float* D, int repeat,
+                          long long* d_cycles, void* stream);   /* tcgen05 issue/throughput microbenchmark */
 
 #ifdef __cplusplus
 }
