@@ -145,6 +145,7 @@ struct TcFwdParams {
   float* g_inv_norm;    // [B][T]   1 / max(||G_t||, eps)
 };
 
+template <int kNks>
 __global__ void __launch_bounds__(kTcThreads, 1)
 sparc_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmL, const TcFwdParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -234,7 +235,7 @@ sparc_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_consta
       // ---- pass 1: G_kb = W . v_kb ; L += G_kb . l_kb^T   (G issued one block ahead of L)
       mbar_wait(w_ready, 0);
       tc_fence_after();
-      const int nks = NP / 16;
+      const int nks = kNks ? kNks : NP / 16;
       auto issue_g = [&](int kb) {
         const int u = KB + kb, slot = u % NS, buf = kb & 1;
         mbar_wait(full + slot, (u / NS) & 1);
@@ -242,8 +243,8 @@ sparc_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_consta
         tc_fence_after();
         const uint64_t dv0 = sw0 | ((smem_u32(base + (size_t)slot * L.stage_bytes) + L.l_bytes) >> 4);
         const uint32_t d = tmem + kTmemG + 64 * buf;
-        for (int ks = 0; ks < nks; ++ks) umma_ss_w(leader, d, ilk_whi + ks * ilk_step, dv0 + ks * 128, idesc_g, ks != 0);
-        for (int ks = 0; ks < nks; ++ks) umma_ss_w(leader, d, ilk_wlo + ks * ilk_step, dv0 + ks * 128, idesc_g, true);
+        _Pragma("unroll") for (int ks = 0; ks < nks; ++ks) umma_ss_w(leader, d, ilk_whi + ks * ilk_step, dv0 + ks * 128, idesc_g, ks != 0);
+        _Pragma("unroll") for (int ks = 0; ks < nks; ++ks) umma_ss_w(leader, d, ilk_wlo + ks * ilk_step, dv0 + ks * 128, idesc_g, true);
         umma_commit_w(leader, g_full + buf);
       };
       auto issue_l = [&](int kb) {
@@ -462,8 +463,13 @@ int sparc_fwd_tc_launch(const void* v, const void* l, const uint8_t* mask, int B
   if ((rc = make_tmap_bf16_3d(&tmL, l, D, T, B, 64, L.NT)) != CFA_OK) return rc;
   TcFwdParams prm{P, T, D, NS, thr, scale, mask, inv_vn, inv_ln, lse_row, lse_col, local_partial, tt_logits, g_inv_norm};
   const size_t smem = L.total + 1024;
-  CFA_CUDA_TRY(cudaFuncSetAttribute(sparc_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  sparc_fwd_tc_kernel<<<B, kTcThreads, smem, st>>>(tmV, tmL, prm);
+  if (L.NP == 208) {
+    CFA_CUDA_TRY(cudaFuncSetAttribute(sparc_fwd_tc_kernel<13>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    sparc_fwd_tc_kernel<13><<<B, kTcThreads, smem, st>>>(tmV, tmL, prm);
+  } else {
+    CFA_CUDA_TRY(cudaFuncSetAttribute(sparc_fwd_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    sparc_fwd_tc_kernel<0><<<B, kTcThreads, smem, st>>>(tmV, tmL, prm);
+  }
   return launch_status();
 }
 
@@ -541,6 +547,9 @@ __device__ __forceinline__ uint4 pack_bf16x8(const float* f) {
   return make_uint4(w[0], w[1], w[2], w[3]);
 }
 
+// kNksP / kNksT: NP/16 and NT/16 as compile-time constants (fully unrolled issue loops with immediate descriptor
+// increments), or 0 = runtime trip counts for other shapes.
+template <int kNksP, int kNksT>
 __global__ void __launch_bounds__(kTcBwdThreads, 1)
 sparc_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmL, const TcBwdParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -575,15 +584,16 @@ sparc_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_consta
   uint64_t* l_full = bb + 10; uint64_t* dl_ready = bb + 11;
   uint64_t* g_full3 = bb + 12; uint64_t* g_free3 = bb + 14; uint64_t* dg_ready3 = bb + 16; uint64_t* dg_free3 = bb + 18;
   uint64_t* dw_full = bb + 20; uint64_t* ds_ready = bb + 21;
-  uint64_t* g_full4 = bb + 22; uint64_t* g_free4 = bb + 24; uint64_t* gs_ready4 = bb + 26; uint64_t* gs_free4 = bb + 27;
-  uint64_t* out_full = bb + 28; uint64_t* out_free = bb + 30;
-  uint32_t* tmem_slot = (uint32_t*)(bb + 32);
+  uint64_t* g_full4 = bb + 22; uint64_t* g_free4 = bb + 24; uint64_t* gs_ready4 = bb + 26; uint64_t* gs_free4 = bb + 28;
+  uint64_t* out_full = bb + 30; uint64_t* out_free = bb + 32;
+  uint32_t* tmem_slot = (uint32_t*)(bb + 36);
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < NS; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, 1); }
     mbar_init(s_full, 1); mbar_init(w_ready, 4); mbar_init(l_full, 1); mbar_init(dl_ready, 4);
-    mbar_init(dw_full, 1); mbar_init(ds_ready, 4); mbar_init(gs_ready4, 4); mbar_init(gs_free4, 1);
+    mbar_init(dw_full, 1); mbar_init(ds_ready, 4);
     for (int i = 0; i < 2; ++i) {
+      mbar_init(gs_ready4 + i, 4); mbar_init(gs_free4 + i, 1);
       mbar_init(g_full2 + i, 1); mbar_init(g_free2 + i, 4); mbar_init(gs_ready2 + i, 4); mbar_init(gs_free2 + i, 1);
       mbar_init(g_full3 + i, 1); mbar_init(g_free3 + i, 4); mbar_init(dg_ready3 + i, 4); mbar_init(dg_free3 + i, 1);
       mbar_init(g_full4 + i, 1); mbar_init(g_free4 + i, 4); mbar_init(out_full + i, 1); mbar_init(out_free + i, 4);
@@ -615,7 +625,7 @@ sparc_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  constexpr uint32_t cS = 0, cG = 256, cX = 320, cL = 384, cDV = 0, cDL = 128;
+  constexpr uint32_t cS = 0, cG = 256, cX = 320, cZ = 256, cDV = 0, cDL = 128;
   const uint32_t il_lbo = (uint32_t)NT * 16;           // interleaved operand: K-major chunk stride == MN-major group stride
 
   if (warp == 0) {
@@ -637,7 +647,7 @@ sparc_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_consta
       const uint32_t id_s = make_idesc_bf16(128, NP, false, false);     // [T x NP]  K-major x K-major
       const uint32_t id_kn32 = make_idesc_bf16(128, 32, false, true);   // A K-major, B MN-major, N = 32
       const uint32_t id_nn32 = make_idesc_bf16(128, 32, true, true);    // A MN-major, B MN-major, N = 32
-      const int nksP = NP / 16, nksT = NT / 16;
+      const int nksP = kNksP ? kNksP : NP / 16, nksT = kNksT ? kNksT : NT / 16;
       // Base descriptors built once; issue loops only add to the start-address field (units of 16 B).
       const uint64_t sw0 = make_smem_desc(0, 16, 512, kLayoutSw64);     // TMA tiles, K-major and MN-major alike
       auto ilk = [&](const uint8_t* a) { return make_smem_desc(smem_u32(a), il_lbo, 128, kLayoutNone); };   // interleaved, K-major
@@ -678,10 +688,10 @@ sparc_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_consta
         const uint32_t sl = smem_u32(base + (size_t)slot * L.stage_bytes), sv = sl + L.l_bytes;
         const uint64_t dl0 = sw0 | (sl >> 4), dv0 = sw0 | (sv >> 4);
         const uint32_t dg = tmem + cG + 32 * buf, dx = tmem + cX + 32 * buf;
-        for (int ks = 0; ks < nksP; ++ks) umma_ss_w(leader, dg, k_whi + ks * ks_k, dv0 + ks * 64, id_kn32, ks != 0);
-        for (int ks = 0; ks < nksP; ++ks) umma_ss_w(leader, dg, k_wlo + ks * ks_k, dv0 + ks * 64, id_kn32, true);
-        for (int ks = 0; ks < nksT; ++ks) umma_ss_w(leader, dx, k_dlhi + ks * ks_k, dl0 + ks * 64, id_kn32, ks != 0);
-        for (int ks = 0; ks < nksT; ++ks) umma_ss_w(leader, dx, k_dllo + ks * ks_k, dl0 + ks * 64, id_kn32, true);
+        _Pragma("unroll") for (int ks = 0; ks < nksP; ++ks) umma_ss_w(leader, dg, k_whi + ks * ks_k, dv0 + ks * 64, id_kn32, ks != 0);
+        _Pragma("unroll") for (int ks = 0; ks < nksP; ++ks) umma_ss_w(leader, dg, k_wlo + ks * ks_k, dv0 + ks * 64, id_kn32, true);
+        _Pragma("unroll") for (int ks = 0; ks < nksT; ++ks) umma_ss_w(leader, dx, k_dlhi + ks * ks_k, dl0 + ks * 64, id_kn32, ks != 0);
+        _Pragma("unroll") for (int ks = 0; ks < nksT; ++ks) umma_ss_w(leader, dx, k_dllo + ks * ks_k, dl0 + ks * 64, id_kn32, true);
         umma_commit_w(leader, gfull + buf);
       };
 
@@ -709,42 +719,59 @@ sparc_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_consta
         umma_commit_w(leader, dg_free3 + buf);
         umma_commit_w(leader, empty + slot);
       }
+      // Z = dLhat^T . W  [T x NP]: folds  dl += dLhat^T . G  and the dLhat part of  dv += W^T . dG  into dShat' = dShat + Z
+      {
+        const uint32_t id_z = make_idesc_bf16(128, NP, true, true);
+        _Pragma("unroll") for (int ks = 0; ks < nksT; ++ks) umma_ss_w(leader, tmem + cZ, m_dlhi + ks * ks_m, m_whi + ks * ks_m, id_z, ks != 0);
+        _Pragma("unroll") for (int ks = 0; ks < nksT; ++ks) umma_ss_w(leader, tmem + cZ, m_dlhi + ks * ks_m, m_wlo + ks * ks_m, id_z, true);
+        _Pragma("unroll") for (int ks = 0; ks < nksT; ++ks) umma_ss_w(leader, tmem + cZ, m_dllo + ks * ks_m, m_whi + ks * ks_m, id_z, true);
+      }
       umma_commit_w(leader, dw_full);
       stamp();
 
-      // ---- pass 4: dv_kb, dl_kb      (smem operands: G = Gb[0,1], dG = Gb[2,3], hi / lo)
+      // ---- pass 4: dv_kb = dShat'^T . l_kb + W^T . G'_kb ,  dl_kb = dShat' . v_kb      (G'_kb = -gfac * G_kb, hi/lo in Gb[2*buf..])
       mbar_wait(ds_ready, 0);
       tc_fence_after();
       stamp();
-      issue_gx(2, 0, g_full4, g_free4);
-      for (int kb = 0; kb < KB; ++kb) {
-        if (kb + 1 < KB) issue_gx(2, kb + 1, g_full4, g_free4);
+      auto issue_g4 = [&](int kb) {
         const int u = 2 * KB + kb, slot = u % NS, buf = kb & 1;
-        mbar_wait(gs_ready4, kb & 1);
+        mbar_wait(full + slot, (u / NS) & 1);
+        mbar_wait(g_free4 + buf, ((kb >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint64_t dv0 = sw0 | ((smem_u32(base + (size_t)slot * L.stage_bytes) + L.l_bytes) >> 4);
+        const uint32_t dg = tmem + cG + 32 * buf;
+        _Pragma("unroll") for (int ks = 0; ks < nksP; ++ks) umma_ss_w(leader, dg, k_whi + ks * ks_k, dv0 + ks * 64, id_kn32, ks != 0);
+        _Pragma("unroll") for (int ks = 0; ks < nksP; ++ks) umma_ss_w(leader, dg, k_wlo + ks * ks_k, dv0 + ks * 64, id_kn32, true);
+        umma_commit_w(leader, g_full4 + buf);
+      };
+      issue_g4(0);
+      for (int kb = 0; kb < KB; ++kb) {
+        if (kb + 1 < KB) issue_g4(kb + 1);
+        const int u = 2 * KB + kb, slot = u % NS, buf = kb & 1;
         mbar_wait(out_free + buf, ((kb >> 1) & 1) ^ 1);
         tc_fence_after();
         const uint32_t sl = smem_u32(base + (size_t)slot * L.stage_bytes), sv = sl + L.l_bytes;
         const uint64_t dl0 = sw0 | (sl >> 4), dv0 = sw0 | (sv >> 4);
+        const uint64_t g_hi = buf ? m_g2 : m_g0, g_lo = buf ? m_g3 : m_g1;
+        {                                             // dl rows t: issued first, it does not need G' (overlaps its conversion)
+          const uint32_t d = tmem + cDL + 32 * buf;
+          _Pragma("unroll") for (int ks = 0; ks < nksP; ++ks) umma_ss_w(leader, d, k_dshi + ks * ks_k, dv0 + ks * 64, id_kn32, ks != 0);
+          _Pragma("unroll") for (int ks = 0; ks < nksP; ++ks) umma_ss_w(leader, d, k_dslo + ks * ks_k, dv0 + ks * 64, id_kn32, true);
+        }
+        mbar_wait(gs_ready4 + buf, (kb >> 1) & 1);
+        tc_fence_after();
 #pragma unroll
         for (int m = 0; m < 2; ++m) {                 // dv rows p = 128 m ...
           const uint32_t d = tmem + cDV + 64 * buf + 32 * m;
           const uint32_t mo = m * mt_m;
-          for (int ks = 0; ks < nksT; ++ks) umma_ss_w(leader, d, m_dshi + mo + ks * ks_m, dl0 + ks * 64, id_nn32, ks != 0);
-          for (int ks = 0; ks < nksT; ++ks) umma_ss_w(leader, d, m_dslo + mo + ks * ks_m, dl0 + ks * 64, id_nn32, true);
-          for (int ks = 0; ks < nksT; ++ks) umma_ss_w(leader, d, m_whi + mo + ks * ks_m, m_g2 + ks * ks_m, id_nn32, true);   // W^T . dG: hi.hi
-          for (int ks = 0; ks < nksT; ++ks) umma_ss_w(leader, d, m_whi + mo + ks * ks_m, m_g3 + ks * ks_m, id_nn32, true);   //          hi.lo
-          for (int ks = 0; ks < nksT; ++ks) umma_ss_w(leader, d, m_wlo + mo + ks * ks_m, m_g2 + ks * ks_m, id_nn32, true);   //          lo.hi
-        }
-        {                                             // dl rows t
-          const uint32_t d = tmem + cDL + 32 * buf;
-          for (int ks = 0; ks < nksP; ++ks) umma_ss_w(leader, d, k_dshi + ks * ks_k, dv0 + ks * 64, id_kn32, ks != 0);
-          for (int ks = 0; ks < nksP; ++ks) umma_ss_w(leader, d, k_dslo + ks * ks_k, dv0 + ks * 64, id_kn32, true);
-          for (int ks = 0; ks < nksT; ++ks) umma_ss_w(leader, d, m_dlhi + ks * ks_m, m_g0 + ks * ks_m, id_nn32, true);       // dLhat^T . G
-          for (int ks = 0; ks < nksT; ++ks) umma_ss_w(leader, d, m_dlhi + ks * ks_m, m_g1 + ks * ks_m, id_nn32, true);
-          for (int ks = 0; ks < nksT; ++ks) umma_ss_w(leader, d, m_dllo + ks * ks_m, m_g0 + ks * ks_m, id_nn32, true);
+          _Pragma("unroll") for (int ks = 0; ks < nksT; ++ks) umma_ss_w(leader, d, m_dshi + mo + ks * ks_m, dl0 + ks * 64, id_nn32, ks != 0);
+          _Pragma("unroll") for (int ks = 0; ks < nksT; ++ks) umma_ss_w(leader, d, m_dslo + mo + ks * ks_m, dl0 + ks * 64, id_nn32, true);
+          _Pragma("unroll") for (int ks = 0; ks < nksT; ++ks) umma_ss_w(leader, d, m_whi + mo + ks * ks_m, g_hi + ks * ks_m, id_nn32, true);   // W^T . G': hi.hi
+          _Pragma("unroll") for (int ks = 0; ks < nksT; ++ks) umma_ss_w(leader, d, m_whi + mo + ks * ks_m, g_lo + ks * ks_m, id_nn32, true);   //           hi.lo
+          _Pragma("unroll") for (int ks = 0; ks < nksT; ++ks) umma_ss_w(leader, d, m_wlo + mo + ks * ks_m, g_hi + ks * ks_m, id_nn32, true);   //           lo.hi
         }
         umma_commit_w(leader, out_full + buf);
-        umma_commit_w(leader, gs_free4);
+        umma_commit_w(leader, gs_free4 + buf);
         umma_commit_w(leader, empty + slot);
       }
       stamp();
@@ -959,8 +986,9 @@ sparc_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_consta
     const float dmn = a1 * inv_rng, dmx = -a2 * inv_rng;
     float sdot = 0.f;
     for (int c0 = 0; c0 < NP; c0 += 32) {
-      float x[32], pr[32];
+      float x[32], pr[32], z[32];
       tmem_ld32(trow + cS + c0, x);
+      tmem_ld32(trow + cZ + c0, z);
       tmem_ld_wait();
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
@@ -979,7 +1007,7 @@ sparc_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_consta
             const float prod = (valid && pc < P) ? ds * sv : 0.f;   // phantom rows may hold NaN/Inf: select, never 0*x
             sdot += prod;
             pr[8 * g + j] = prod;
-            x[8 * g + j] = (valid && pc < P) ? ds * il * ivn[pc] : 0.f;
+            x[8 * g + j] = (valid && pc < P) ? fmaf(ds * il, ivn[pc], z[8 * g + j]) : 0.f;   // dShat' = dShat + Z
           }
         } else {
 #pragma unroll
@@ -1016,41 +1044,36 @@ sparc_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_consta
     if (lane == 0) mbar_arrive(ds_ready);
     stamp();
 
-    // ---- pass 4, epilogue A: operands G_kb, dG_kb (hi/lo) -> smem (B operands of the dv / dl MMAs)
+    // ---- pass 4, epilogue A: G'_kb = -gfac * G_kb (hi/lo) -> smem, double buffered (B operand of W^T . G')
     for (int kb = 0; kb < KB; ++kb) {
       const int buf = kb & 1;
       mbar_wait(g_full4 + buf, (kb >> 1) & 1);
       tc_fence_after();
-      float x[32], gx[32];
+      float gx[32];
       tmem_ld32(trow + cG + 32 * buf, gx);
-      tmem_ld32(trow + cX + 32 * buf, x);
       tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(g_free4 + buf);
-      mbar_wait(gs_free4, (kb & 1) ^ 1);
+      mbar_wait(gs_free4 + buf, ((kb >> 1) & 1) ^ 1);
       if (row < NT) {
+        uint8_t* gh = Gb + (size_t)(2 * buf) * L.g_bytes;
+        const float ng = valid ? -gfac : 0.f;
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
-          float y[8], z[8];
+          float y[8];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            y[j] = valid ? gx[8 * g + j] : 0.f;
-            z[j] = valid ? fmaf(-gx[8 * g + j], gfac, x[8 * g + j]) : 0.f;
-          }
+          for (int j = 0; j < 8; ++j) y[j] = valid ? gx[8 * g + j] * ng : 0.f;
           uint4 hi, lo;
-          const uint32_t off = il_offset(NT, row, 8 * g);
           split_bf16x8(y, hi, lo);
-          *reinterpret_cast<uint4*>(Gb + off) = hi;
-          *reinterpret_cast<uint4*>(Gb + L.g_bytes + off) = lo;
-          split_bf16x8(z, hi, lo);
-          *reinterpret_cast<uint4*>(Gb + 2 * L.g_bytes + off) = hi;
-          *reinterpret_cast<uint4*>(Gb + 3 * L.g_bytes + off) = lo;
+          const uint32_t off = il_offset(NT, row, 8 * g);
+          *reinterpret_cast<uint4*>(gh + off) = hi;
+          *reinterpret_cast<uint4*>(gh + L.g_bytes + off) = lo;
         }
       }
       fence_proxy_async();
       __syncwarp();
-      if (lane == 0) mbar_arrive(gs_ready4);
+      if (lane == 0) mbar_arrive(gs_ready4 + buf);
     }
     stamp();
     tc_fence_before();
@@ -1144,8 +1167,13 @@ int sparc_bwd_tc_launch(const void* v, const void* l, const uint8_t* mask, int B
   TcBwdParams prm{g_prof_buffer, P, T, D, NS, thr, scale, mask, row_inv_norm, row_inv_norm + (size_t)B * P, lse_row, lse_col, coef,
                   tt_logits, g_inv_norm, dpv, dpl, (const bf16*)v, (const bf16*)l, (bf16*)dv, (bf16*)dl};
   const size_t smem = L.total + 1024;
-  CFA_CUDA_TRY(cudaFuncSetAttribute(sparc_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  sparc_bwd_tc_kernel<<<B, kTcBwdThreads, smem, st>>>(tmV, tmL, prm);
+  if (L.NP == 208 && L.NT == 80) {          // ViT-B/16 (P = 196 / 197, T = 77): fully unrolled issue loops
+    CFA_CUDA_TRY(cudaFuncSetAttribute(sparc_bwd_tc_kernel<13, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    sparc_bwd_tc_kernel<13, 5><<<B, kTcBwdThreads, smem, st>>>(tmV, tmL, prm);
+  } else {
+    CFA_CUDA_TRY(cudaFuncSetAttribute(sparc_bwd_tc_kernel<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    sparc_bwd_tc_kernel<0, 0><<<B, kTcBwdThreads, smem, st>>>(tmV, tmL, prm);
+  }
   return launch_status();
 }
 

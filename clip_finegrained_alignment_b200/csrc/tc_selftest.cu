@@ -83,7 +83,8 @@ tc_selftest_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     const long long t0 = clock64();
     if (repeat > 1) {                       // throughput probe: same operands every time, no address arithmetic
 #pragma unroll 8
-      for (int i = 0; i < repeat * nks; ++i) umma_ss_w(leader, tmem, da0, db0, idesc, true);
+      for (int i = 0; i < repeat * nks; ++i)       // cycle through 4 consecutive k-steps: distinct operand addresses, cheap arithmetic
+        umma_ss_w(leader, tmem, da0 + (uint32_t)(i & 3) * a_ks, db0 + (uint32_t)(i & 3) * b_ks, idesc, true);
     } else
     for (int rep = 0; rep < repeat; ++rep)
       for (int ks = 0; ks < nks; ++ks) {
