@@ -502,7 +502,7 @@ __host__ __device__ inline TcBwdLayout tc_bwd_layout(int P, int T, int D, int NS
   L.off_dl = L.off_w + 2 * L.w_bytes + (2 * L.w_bytes > sc_bytes ? 2 * L.w_bytes : ((sc_bytes + 15) & ~15u));   // dLhi, dLlo
   L.off_g = L.off_dl + 2 * L.dl_bytes;                // 4 operand buffers of g_bytes
   L.off_f = L.off_g + 4 * L.g_bytes + 1024;           // phantom rows of the last buffer stay in bounds
-  L.off_bar = (L.off_f + 4 * (2 * (L.NP + 32) + 6 * L.NT + 2 * D + 32) + 7) & ~7u;
+  L.off_bar = (L.off_f + 4 * (2 * (L.NP + 32) + 7 * L.NT + 2 * D + 32) + 7) & ~7u;
   L.total = L.off_bar + 8 * (2 * L.NS + 34) + 16;
   return L;
 }
@@ -574,7 +574,8 @@ sparc_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_consta
   float* lsec = lser + NT;                             // [NT]
   float* ldot = lsec + NT;                             // [NT]
   float* lfacs = ldot + NT;                            // [NT]   (l^_t . dl^_t) / |l_t|^2
-  float* dpool = lfacs + NT;                           // [2][D] gradient w.r.t. the pooled means of this sample
+  float* gfacs = lfacs + NT;                           // [NT]   (g^_t . dg^_t) / |G_t|^2
+  float* dpool = gfacs + NT;                           // [2][D] gradient w.r.t. the pooled means of this sample
   uint64_t* bars = (uint64_t*)(base + L.off_bar);
   uint64_t* full = bars;
   uint64_t* empty = bars + NS;
@@ -788,16 +789,6 @@ sparc_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_consta
     int pi = 0;
     auto stamp = [&]() { if (pf) pf[pi++] = clock64(); };
     stamp();
-    // T x T logits of the forward -> fp32 scratch (aliases the dShat region, free until phase 5); overlaps pass 1
-    float* Sc = reinterpret_cast<float*>(DShi);         // [T][NT+1]
-    const int ldl = NT + 1;
-    {
-      const float* src = p.tt_logits + (size_t)b * T * T;
-      for (int idx = threadIdx.x - 64; idx < T * T; idx += 128) { const int i = idx / T, j = idx - i * T; Sc[i * ldl + j] = __ldg(src + idx); }
-    }
-    const float ign = (row < T) ? p.g_inv_norm[(size_t)b * T + row] : 0.f;
-    epi_bar_sync();
-
     // ---- phase 1: S -> W, row stats   (branch-free)
     mbar_wait(s_full, 0);
     tc_fence_after();
@@ -859,47 +850,12 @@ sparc_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_consta
     if (lane == 0) mbar_arrive(w_ready);
     stamp();
 
-    // ---- phase 3: saved logits -> dLhat (hi/lo), gdot_i, ldotL_j
+    // ---- phase 3 (dLhat, gfac, ldotL) is done by the epilogue-B warps concurrently with pass 1 / phase 1
     stamp();
     stamp();
-    float gdot = 0.f;
-    const float lr = (row < NT) ? lser[row] : 0.f;
-    for (int c0 = 0; c0 < NT; c0 += 16) {
-      float x[16];
-#pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const int col = c0 + j;
-        const bool on = valid && col < T && msk[col] != 0.f;
-        const float y = on ? Sc[row * ldl + col] : 0.f;
-        const float den = ign * iln[col];
-        float g = c_r * __expf(fminf(y - lr, 0.f)) + c_c * __expf(fminf(y - lsec[col], 0.f));
-        g -= (col == row) ? (c_r + c_c) : 0.f;
-        g = on ? g : 0.f;
-        const float pr = g * y;
-        gdot += pr;
-        if (row < T && col < T) Sc[row * ldl + col] = pr;
-        x[j] = p.scale * g * den;
-      }
-      if (row < NT) {
-#pragma unroll
-        for (int g = 0; g < 2; ++g) {
-          uint4 hi, lo;
-          split_bf16x8(x + 8 * g, hi, lo);
-          const uint32_t off = il_offset(NT, row, c0 + 8 * g);
-          *reinterpret_cast<uint4*>(dLhi + off) = hi;
-          *reinterpret_cast<uint4*>(dLlo + off) = lo;
-        }
-      }
-    }
-    const float gfac = gdot * ign * ign;                // (g^_i . dg^_i) / ||G_i||^2
-    epi_bar_sync();
-    float ldl_j = 0.f;
-    if (row < T) for (int i = 0; i < T; ++i) ldl_j += Sc[i * ldl + row];
-    epi_bar_sync();                                     // scratch reads done before dShat is written later
-    tc_fence_before();
-    fence_proxy_async();
-    __syncwarp();
-    if (lane == 0) mbar_arrive(dl_ready);
+    asm volatile("bar.sync 3, 256;" ::: "memory");
+    const float gfac = (row < NT) ? gfacs[row] : 0.f;
+    const float ldl_j = (row < NT) ? ldot[row] : 0.f;
     stamp();
 
     // ---- pass 3 epilogue: dG_kb = (X_kb - G_kb gfac) -> A operand of the dW MMA
@@ -1078,10 +1034,61 @@ sparc_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_consta
     stamp();
     tc_fence_before();
   } else {
-    // =============================== epilogue B (4 warps): dv_kb, dl_kb -> global ===============================
+    // =============================== epilogue B (4 warps): phase 3, then dv_kb, dl_kb -> global ===============================
     const int q = warp & 3;
     const int row = 32 * q + lane;
     const uint32_t trow = tmem + ((uint32_t)(32 * q) << 16);
+    {
+      // ---- phase 3: saved T x T logits -> dLhat (hi/lo), gfac_i, ldotL_j   (overlaps pass 1 and phase 1)
+      const bool valid = row < T && msk[row < NT ? row : 0] != 0.f;
+      const float c_r = p.coef[0], c_c = p.coef[1];
+      float* Sc = reinterpret_cast<float*>(DShi);       // [T][NT+1] fp32 scratch, aliases the dShat region (free until phase 5)
+      const int ldl = NT + 1;
+      {
+        const float* src = p.tt_logits + (size_t)b * T * T;
+        for (int idx = threadIdx.x - 192; idx < T * T; idx += 128) { const int i = idx / T, j = idx - i * T; Sc[i * ldl + j] = __ldg(src + idx); }
+      }
+      const float ign = (row < T) ? p.g_inv_norm[(size_t)b * T + row] : 0.f;
+      asm volatile("bar.sync 4, 128;" ::: "memory");
+      float gdot = 0.f;
+      const float lr = (row < NT) ? lser[row] : 0.f;
+      for (int c0 = 0; c0 < NT; c0 += 16) {
+        float x[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const int col = c0 + j;
+          const bool on = valid && col < T && msk[col] != 0.f;
+          const float y = on ? Sc[row * ldl + col] : 0.f;
+          const float den = ign * iln[col];
+          float g = c_r * __expf(fminf(y - lr, 0.f)) + c_c * __expf(fminf(y - lsec[col], 0.f));
+          g -= (col == row) ? (c_r + c_c) : 0.f;
+          g = on ? g : 0.f;
+          const float pr = g * y;
+          gdot += pr;
+          if (row < T && col < T) Sc[row * ldl + col] = pr;
+          x[j] = p.scale * g * den;
+        }
+        if (row < NT) {
+#pragma unroll
+          for (int g = 0; g < 2; ++g) {
+            uint4 hi, lo;
+            split_bf16x8(x + 8 * g, hi, lo);
+            const uint32_t off = il_offset(NT, row, c0 + 8 * g);
+            *reinterpret_cast<uint4*>(dLhi + off) = hi;
+            *reinterpret_cast<uint4*>(dLlo + off) = lo;
+          }
+        }
+      }
+      if (row < NT) gfacs[row] = gdot * ign * ign;      // (g^_i . dg^_i) / ||G_i||^2
+      asm volatile("bar.sync 4, 128;" ::: "memory");
+      float ldl_j = 0.f;
+      if (row < T) for (int i = 0; i < T; ++i) ldl_j += Sc[i * ldl + row];
+      if (row < NT) ldot[row] = ldl_j;
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(dl_ready);
+      asm volatile("bar.sync 3, 256;" ::: "memory");    // gfac / ldotL visible to epilogue A
+    }
     asm volatile("bar.sync 2, 256;" ::: "memory");      // wait for vfac / lfac
     float cnt = 0.f;
     for (int t = 0; t < T; ++t) cnt += msk[t];
