@@ -67,15 +67,24 @@ sparc_prep_kernel(const bf16* __restrict__ v, const bf16* __restrict__ l, const 
 #pragma unroll
       for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
     float cnt = 0.f;
-    for (int r = warp; r < rows; r += 8) {
-      const float m = which ? (mask[(size_t)b * T + r] ? 1.f : 0.f) : 1.f;
-      float ss = 0.f;
+    // 4 rows per warp iteration: all loads of the 4 rows are issued before any is consumed (memory-level parallelism)
+    for (int r0 = warp * 4; r0 < rows; r0 += 32) {
+      uint4 u[4][4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int g = lane + 32 * i;
-        if (g < ng) {
-          const uint4 u = __ldg(reinterpret_cast<const uint4*>(src + (size_t)r * D + 8 * g));
-          const bf16* h = reinterpret_cast<const bf16*>(&u);
+      for (int k = 0; k < 4; ++k)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int g = lane + 32 * i, r = r0 + k;
+          u[k][i] = (g < ng && r < rows) ? __ldg(reinterpret_cast<const uint4*>(src + (size_t)r * D + 8 * g)) : make_uint4(0, 0, 0, 0);
+        }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int r = r0 + k;
+        const float m = (r < rows) ? (which ? (mask[(size_t)b * T + r] ? 1.f : 0.f) : 1.f) : 0.f;
+        float ss = 0.f;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const bf16* h = reinterpret_cast<const bf16*>(&u[k][i]);
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const float f = __bfloat162float(h[j]);
@@ -83,9 +92,9 @@ sparc_prep_kernel(const bf16* __restrict__ v, const bf16* __restrict__ l, const 
             acc[i][j] = fmaf(m, f, acc[i][j]);
           }
         }
+        ss = warp_sum(ss);
+        if (lane == 0 && r < rows) (which ? inv_ln + (size_t)b * T : inv_vn + (size_t)b * P)[r] = 1.f / fmaxf(sqrtf(ss), kTcNormEps);
       }
-      ss = warp_sum(ss);
-      if (lane == 0) (which ? inv_ln + (size_t)b * T : inv_vn + (size_t)b * P)[r] = 1.f / fmaxf(sqrtf(ss), kTcNormEps);
     }
     if (which) for (int t = 0; t < T; ++t) cnt += mask[(size_t)b * T + t] ? 1.f : 0.f;
     __syncthreads();
