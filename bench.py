@@ -118,39 +118,48 @@ def vit_l14_clip_shapes():
 
 
 def bench_adamspd(dev, steps, warmup, pk):
-    """AdamSPD full-model step on the ViT-L/14 CLIP tensor list (BASELINE config 5), fp32, random grads."""
+    """AdamSPD full-model step on the ViT-L/14 CLIP tensor list (BASELINE config 5), fp32, random grads.
+    `value` = algorithmic bytes / device time of cfa_adamspd_step (CUDA events around the launches on the launching
+    stream); `ms_per_step_host_inclusive` = events around optimizer.step() starting from an idle GPU."""
     from clip_finegrained_alignment_b200 import AdamSPD, _lib
     shapes = vit_l14_clip_shapes()
     g = torch.Generator(device=dev).manual_seed(7)
     params = [torch.nn.Parameter(torch.randn(*s, device=dev, generator=g) * 0.02) for s in shapes]
     pre = [p.detach() + 1e-3 * torch.randn(*p.shape, device=dev, generator=g) for p in params]
-    for p in params:
-        p.grad = torch.randn(*p.shape, device=dev, generator=g) * 1e-3
-    opt = AdamSPD([{"params": params, "pre": pre}], lr=2e-5, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.1)
     n_elts = sum(p.numel() for p in params)
+    flat = torch.empty(n_elts + 4 * len(params), device=dev)      # grads are views of one buffer: one launch refills all
+    off = 0
+    for p in params:
+        p.grad = flat[off:off + p.numel()].view(p.shape)
+        off += (p.numel() + 3) // 4 * 4                           # keep every view 16-byte aligned
+    opt = AdamSPD([{"params": params, "pre": pre}], lr=2e-5, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.1)
     numel = torch.tensor([p.numel() for p in params], dtype=torch.float64)
 
-    def regrad():
-        for p in params:                      # fresh random grads each step so both SPD branches occur
-            p.grad.normal_(0.0, 1e-3, generator=g)
+    def regrad():                                                  # fresh random grads so both SPD branches occur
+        flat.normal_(0.0, 1e-3, generator=g)
 
     for _ in range(warmup):
         regrad(); opt.step()
     torch.cuda.synchronize(dev)
-    times, bytes_total = [], 0.0
+    host_ms, bytes_total = [], 0.0
     l0 = _lib.launch_count
+    saved_events = _lib.kernel_events
+    _lib.kernel_events = {"cfa_adamspd_step": []}
     for _ in range(steps):
         regrad()
+        torch.cuda.synchronize(dev)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(); opt.step(); e1.record()
         torch.cuda.synchronize(dev)
-        times.append(e0.elapsed_time(e1))
+        host_ms.append(e0.elapsed_time(e1))
         st = opt.last_step_stats.cpu().double()
         proj = (st[:, 0] > 0) & (st[:, 1] > 0)
         bytes_total += 32.0 * n_elts + 12.0 * float(numel[proj].sum())
+    kev = _lib.kernel_events["cfa_adamspd_step"]
+    _lib.kernel_events = saved_events
     launches = _lib.launch_count - l0
-    ms = sum(times) / len(times)
-    gbs = bytes_total / len(times) / (ms * 1e-3) / 1e9
+    ms = sum(a.elapsed_time(b) for a, b in kev) / len(kev)
+    gbs = bytes_total / len(kev) / (ms * 1e-3) / 1e9
     # comparator: torch fused AdamW on the same tensors (28 B/elt)
     cmp_ms = None
     try:
@@ -171,12 +180,15 @@ def bench_adamspd(dev, steps, warmup, pk):
     except Exception:
         pass
     out = {"metric": "adamspd_step_hbm_gbs", "value": round(gbs, 1), "unit": "GB/s", "ms_per_step": round(ms, 4),
+           "ms_per_step_host_inclusive": round(sum(host_ms) / len(host_ms), 4),
            "workload": "ViT-L/14 CLIP, 590 fp32 tensors, 427616513 params, random grads, lr 2e-5, wd 0.1",
-           "algorithmic_bytes_per_step": bytes_total / len(times), "gpu_launches_per_step": launches // max(1, steps),
-           "roofline": {"bound": "hbm", "achieved": round(gbs, 1), "peak": pk["hbm"], "unit": "GB/s",
-                        "frac": round(gbs / pk["hbm"], 4), "traffic": None, "peak_source": pk["src"]},
+           "algorithmic_bytes_per_step": bytes_total / len(kev), "gpu_launches_per_step": launches // max(1, steps),
+           "roofline": {"bound": "hbm", "kernel": "adamspd_pass1 + adamspd_pass2", "achieved": round(gbs, 1), "peak": pk["hbm"],
+                        "unit": "GB/s", "frac": round(gbs / pk["hbm"], 4),
+                        "traffic": 16.0e9, "traffic_source": "profiles/r1d_ncu_adamspd.csv (dram read+write, both passes)",
+                        "peak_source": pk["src"]},
            "torch_fused_adamw_ms": None if cmp_ms is None else round(cmp_ms, 4)}
-    del opt, params, pre
+    del opt, params, pre, flat
     torch.cuda.empty_cache()
     return out
 
@@ -385,7 +397,10 @@ def main():
                    "algorithmic_tflops": round(value * flops_per_pair(Bg) / 1e12, 2),
                    "kernel_ms": {"cfa_sparc_fwd": round(fwd_ms, 4), "cfa_sparc_bwd": round(bwd_ms, 4)}},
         "roofline": {"bound": "tensor", "kernel": "cfa_sparc_bwd", "achieved": round(ach, 2), "peak": pk["tf_sus"],
-                     "unit": "TFLOP/s", "frac": round(ach / pk["tf_sus"], 5), "traffic": None,
+                     "unit": "TFLOP/s", "frac": round(ach / pk["tf_sus"], 5),
+                     "traffic": 105.8e6 if (B == 256 and args.dtype == "bf16") else None,
+                     "traffic_source": "profiles/r1c_ncu_full_tc_adamspd.csv: dram read 79.6 MB + write 26.2 MB per launch "
+                                       "(algorithmic 143.2 MB in+out; the rest of dv/dl is still in L2 at kernel end)",
                      "peak_source": pk["src"] + ", sustained bf16 GEMM", "algorithmic_flops_per_launch": bwd_flops},
         "e2e": {"value": round(e2e_val, 1), "unit": UNIT,
                 "h2d_bytes_per_step": int(hv.numel() * hv.element_size() + hl.numel() * hl.element_size() + hm.numel()),

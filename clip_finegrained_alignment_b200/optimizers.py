@@ -24,33 +24,55 @@ assert _TENSOR_DT.itemsize == 88
 
 
 class _Plan:
-    """Cached launch plan for one set of (param, state, pre) tensors: the static half of the
-    descriptor table and the chunk table live here; per step only `g` and the step scalars change."""
+    """Cached launch plan for one pattern of (param has grad) over all param groups.  The static half of the
+    descriptor table (p, m, v, pre, vmax pointers, sizes) and the chunk table are built once; per step only the
+    gradient pointers and a handful of per-(group, step) scalars are refreshed."""
 
-    def __init__(self, entries, amsgrad, device):
-        n = len(entries)
-        self.n = n
-        self.key = tuple((id(p), p.data_ptr(), p.numel()) for p, _, _ in entries)
+    def __init__(self, opt, all_params, has_grad, amsgrad, device):
+        self.all_params = all_params
+        self.has_grad = has_grad
         self.amsgrad = amsgrad
+        entries, combo_key, combo_index = [], {}, []
+        k = 0
+        for gi, group in enumerate(opt.param_groups):
+            pre_list = group["pre"]
+            for j, p in enumerate(group["params"]):
+                if has_grad[k]:
+                    st = opt.state[p]
+                    pre = pre_list[j] if pre_list is not None else None
+                    entries.append((p, st, pre))
+                    key = (gi, st["step"])                      # params of one group normally share the step count
+                    combo_index.append(combo_key.setdefault(key, len(combo_key)))
+                k += 1
+        self.entries = entries
+        self.states = [e[1] for e in entries]
+        self.grad_params = [e[0] for e in entries]
+        self.combos = list(combo_key.keys())                     # (group index, step count at plan time)
+        self.combo_index = np.asarray(combo_index, dtype=np.int64)
+        self.steps_since_build = 0
+        n = self.n = len(entries)
         chunk = _lib.lib.cfa_adamspd_chunk_elems()
         tab = np.zeros(n, dtype=_TENSOR_DT)
         chunks = []
-        for k, (p, st, pre) in enumerate(entries):
-            tab["p"][k] = p.data_ptr()
-            tab["m"][k] = st["exp_avg"].data_ptr()
-            tab["v"][k] = st["exp_avg_sq"].data_ptr()
-            tab["pre"][k] = 0 if pre is None else pre.data_ptr()
-            tab["vmax"][k] = st["max_exp_avg_sq"].data_ptr() if amsgrad else 0
-            tab["numel"][k] = p.numel()
+        for i, (p, st, pre) in enumerate(entries):
+            tab["p"][i] = p.data_ptr()
+            tab["m"][i] = st["exp_avg"].data_ptr()
+            tab["v"][i] = st["exp_avg_sq"].data_ptr()
+            tab["pre"][i] = 0 if pre is None else pre.data_ptr()
+            tab["vmax"][i] = st["max_exp_avg_sq"].data_ptr() if amsgrad else 0
+            tab["numel"][i] = p.numel()
             nc = (p.numel() + chunk - 1) // chunk
-            chunks.append(np.stack([np.full(nc, k, dtype=np.int32), np.arange(nc, dtype=np.int32)], axis=1))
+            chunks.append(np.stack([np.full(nc, i, dtype=np.int32), np.arange(nc, dtype=np.int32)], axis=1))
         self.static = tab
+        self.static_key = (tab["p"].tobytes(), tab["m"].tobytes(), tab["pre"].tobytes())
         ch = np.concatenate(chunks, axis=0) if chunks else np.zeros((0, 2), np.int32)
         self.n_chunks = int(ch.shape[0])
         self.d_chunks = torch.from_numpy(np.ascontiguousarray(ch)).to(device)
         # two pinned staging buffers so that refilling never races the previous step's async copy
         self.h_tab = [torch.empty(n * _TENSOR_DT.itemsize, dtype=torch.uint8).pin_memory() for _ in range(2)]
         self.h_np = [t.numpy().view(_TENSOR_DT) for t in self.h_tab]
+        for a in self.h_np:
+            a[:] = tab
         self.h_evt = [torch.cuda.Event() for _ in range(2)]
         self.h_used = [False, False]
         self.flip = 0
@@ -98,21 +120,45 @@ class AdamSPD(Optimizer):
             with torch.enable_grad():
                 loss = closure()
 
-        entries = []      # (param, state, pre) for every param with a grad, reference visiting order
-        grads = []
-        hyper = []        # (beta1, beta2, eps, lr, wd, step) per entry
-        amsgrad_all = None
+        plan = self._plan
+        if plan is None:
+            all_params = [p for group in self.param_groups for p in group["params"]]
+        else:
+            all_params = plan.all_params
+        grads_all = [p.grad for p in all_params]
+        has_grad = tuple(g is not None for g in grads_all)
+        if not any(has_grad):
+            return loss
+        grads = [g for g in grads_all if g is not None]
+        if plan is None or plan.has_grad != has_grad or len(all_params) != sum(len(g["params"]) for g in self.param_groups):
+            plan = self._build_plan(grads)
+        for g in grads:
+            if not g.is_contiguous() or g.dtype != torch.float32 or g.is_sparse:
+                plan = self._build_plan(grads)           # slow path re-validates and raises the reference's errors
+                grads = [g if g.is_contiguous() else g.contiguous() for g in grads]
+                break
+        for st in plan.states:                          # optimizers.py:81
+            st["step"] += 1
+        plan.steps_since_build += 1
+        self._launch(plan, grads)
+        return loss
+
+    # ------------------------------------------------------------------
+    def _build_plan(self, grads):
+        """Slow path: (re)validate everything like the reference does, lazily create state, build the tables."""
+        all_params, has_grad, amsgrad_all = [], [], None
         for group in self.param_groups:
-            beta1, beta2 = group["betas"]
             ams = bool(group["amsgrad"])
-            have_grad = False
-            for j, p in enumerate(group["params"]):
+            any_grad = False
+            for p in group["params"]:
+                all_params.append(p)
                 g = p.grad
+                has_grad.append(g is not None)
                 if g is None:
                     continue
                 if g.is_sparse:
                     raise RuntimeError("Adam does not support sparse gradients, please consider SparseAdam instead")
-                have_grad = True
+                any_grad = True
                 state = self.state[p]
                 if len(state) == 0:       # lazy init, optimizers.py:61-70
                     state["step"] = 0
@@ -121,69 +167,67 @@ class AdamSPD(Optimizer):
                     state["hyper"] = torch.zeros_like(p, memory_format=torch.preserve_format)
                     if ams:
                         state["max_exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
-                state["step"] += 1        # optimizers.py:81
-                pre_list = group["pre"]   # KeyError('pre') like the reference (optimizers.py:146)
-                pre = pre_list[j] if pre_list is not None else None
-                entries.append((p, state, pre))
-                grads.append(g)
-                hyper.append((beta1, beta2, group["eps"], group["lr"], group["weight_decay"], state["step"]))
-            if have_grad:
+            if any_grad:
+                group["pre"]              # KeyError('pre') like the reference (optimizers.py:146)
                 if amsgrad_all is None:
                     amsgrad_all = ams
                 elif amsgrad_all != ams:
                     raise _lib.CfaError("AdamSPD: mixing amsgrad and non-amsgrad groups in one optimizer is unsupported")
-        if not entries:
-            return loss
-        self._launch(entries, grads, hyper, bool(amsgrad_all))
-        return loss
+        k = 0
+        tensors = []
+        for group in self.param_groups:
+            pre_list = group["pre"] if any(p.grad is not None for p in group["params"]) else None
+            for j, p in enumerate(group["params"]):
+                if p.grad is not None:
+                    pre = pre_list[j] if pre_list is not None else None
+                    st = self.state[p]
+                    tensors += [p, p.grad, pre]
+                    if p.dtype != torch.float32 or p.grad.dtype != torch.float32:
+                        raise _lib.CfaError("AdamSPD kernels are fp32 (the reference keeps fp32 master params); got "
+                                            f"{p.dtype}/{p.grad.dtype}")
+                    if not p.is_contiguous() or not st["exp_avg"].is_contiguous() or not st["exp_avg_sq"].is_contiguous():
+                        raise _lib.CfaError("AdamSPD: parameters and optimizer state must be contiguous")
+                    if pre is not None and (pre.shape != p.shape or not pre.is_contiguous() or pre.dtype != p.dtype
+                                            or pre.device != p.device):
+                        raise _lib.CfaError("AdamSPD: group['pre'][j] must match its parameter (shape, dtype, device, contiguous)")
+                k += 1
+        dev = _lib.require_cuda(*tensors)
+        self._plan = _Plan(self, all_params, tuple(has_grad), bool(amsgrad_all), dev)
+        return self._plan
 
-    # ------------------------------------------------------------------
-    def _launch(self, entries, grads, hyper, amsgrad):
-        p0 = entries[0][0]
-        dev = _lib.require_cuda(*[e[0] for e in entries], *grads, *[e[2] for e in entries])
-        for (p, st, pre), g in zip(entries, grads):
-            if p.dtype != torch.float32 or g.dtype != torch.float32:
-                raise _lib.CfaError("AdamSPD kernels are fp32 (the reference keeps fp32 master params); got "
-                                    f"{p.dtype}/{g.dtype}")
-            if not p.is_contiguous() or not st["exp_avg"].is_contiguous() or not st["exp_avg_sq"].is_contiguous():
-                raise _lib.CfaError("AdamSPD: parameters and optimizer state must be contiguous")
-            if pre is not None and (pre.shape != p.shape or not pre.is_contiguous() or pre.dtype != p.dtype
-                                    or pre.device != p.device):
-                raise _lib.CfaError("AdamSPD: group['pre'][j] must match its parameter (shape, dtype, device, contiguous)")
-        grads = [g if g.is_contiguous() else g.contiguous() for g in grads]
-
-        plan = self._plan
-        key = tuple((id(p), p.data_ptr(), p.numel()) for p, _, _ in entries)
-        if plan is None or plan.key != key or plan.amsgrad != amsgrad:
-            plan = self._plan = _Plan(entries, amsgrad, dev)
-
+    def _launch(self, plan, grads):
         k = plan.flip
         plan.flip ^= 1
         if plan.h_used[k]:
             plan.h_evt[k].synchronize()      # normally long finished: two steps ago
         tab = plan.h_np[k]
-        tab[:] = plan.static
         tab["g"] = np.fromiter((g.data_ptr() for g in grads), dtype=np.uint64, count=plan.n)
+        # parameters may have been re-pointed (p.data = ...): refresh the static pointers if any changed
+        pptr = np.fromiter((p.data_ptr() for p in plan.grad_params), dtype=np.uint64, count=plan.n)
+        if not np.array_equal(pptr, plan.static["p"]):
+            self._plan = None
+            plan = self._build_plan(grads)
+            for st in plan.states:
+                pass
+            return self._launch(plan, grads)
         # per-step scalars: Python doubles like the reference (optimizers.py:123-124,139), rounded once to fp32
-        cache = {}
-        cols = np.empty((plan.n, 8), dtype=np.float32)
-        for i, h in enumerate(hyper):
-            row = cache.get(h)
-            if row is None:
-                beta1, beta2, eps, lr, wd, step = h
-                bc1 = 1 - beta1 ** step
-                bc2 = 1 - beta2 ** step
-                row = (beta1, 1 - beta1, beta2, 1 - beta2, eps, lr / bc1, math.sqrt(bc2), wd)
-                cache[h] = row
-            cols[i] = row
+        rows = np.empty((len(plan.combos), 8), dtype=np.float32)
+        for ci, (gi, step0) in enumerate(plan.combos):
+            group = self.param_groups[gi]
+            beta1, beta2 = group["betas"]
+            step = step0 + plan.steps_since_build
+            bc1 = 1 - beta1 ** step
+            bc2 = 1 - beta2 ** step
+            rows[ci] = (beta1, 1 - beta1, beta2, 1 - beta2, group["eps"], group["lr"] / bc1, math.sqrt(bc2),
+                        group["weight_decay"])
+        cols = rows[plan.combo_index]
         for c, name in enumerate(("beta1", "omb1", "beta2", "omb2", "eps", "step_size", "sqrt_bc2", "wd")):
             tab[name] = cols[:, c]
-
+        dev = plan.d_tab.device
         with torch.cuda.device(dev):
             plan.d_tab.copy_(plan.h_tab[k], non_blocking=True)
             plan.h_evt[k].record()
             plan.h_used[k] = True
             _lib.call("cfa_adamspd_step", plan.d_tab.data_ptr(), plan.n, plan.d_chunks.data_ptr(), plan.n_chunks,
-                      plan.d_reduce.data_ptr(), plan.d_stats.data_ptr(), 0, int(amsgrad), _lib.stream_ptr())
+                      plan.d_reduce.data_ptr(), plan.d_stats.data_ptr(), 0, int(plan.amsgrad), _lib.stream_ptr())
         self._keepalive = grads      # contiguous copies (if any) must outlive the async launch
-        del p0
