@@ -11,16 +11,17 @@
 
 namespace cfa {
 
-constexpr int kGR = 32, kGC = 64, kGK = 32, kGLd = kGK + 1;     // forward tile: 32 rows x 64 cols, K chunks of 32
+constexpr int kGR = 32, kGC = 64, kGK = 128, kGLd = kGK + 1;    // forward tile: 32 rows x 64 cols, K chunks of 128 (few, long loads)
 
 __global__ void __launch_bounds__(kNT)
 global_fwd_kernel(const float* __restrict__ a_loc, const float* __restrict__ b_loc, const float* __restrict__ a_all,
                   const float* __restrict__ b_all, int B, int Bg, int D, int col_offset, float scale, float eps,
                   float* __restrict__ part_m, float* __restrict__ part_l, float* __restrict__ diag,
                   float* __restrict__ norms /* [2][B] clamped row norms */) {
-  __shared__ float stA[kGR * kGLd];
-  __shared__ float stB[kGC * kGLd];
-  __shared__ float nrm[kGR + kGC];
+  extern __shared__ float gsm[];
+  float* stA = gsm;                        // [32 x 129]
+  float* stB = stA + kGR * kGLd;           // [64 x 129]
+  float* nrm = stB + kGC * kGLd;           // [96]
   const int dir = blockIdx.z, split = blockIdx.y, nsplit = gridDim.y, r0 = blockIdx.x * kGR;
   const float* rows = dir ? b_loc : a_loc;
   const float* cols = dir ? a_all : b_all;
@@ -144,7 +145,7 @@ global_combine_kernel(const float* __restrict__ part_m, const float* __restrict_
 //   dS_ij = c_self exp(S_ij - lse_self[i]) + c_other exp(S_ij - lse_other[j]) - (c_self + c_other) [j == off + i]
 // and accumulate  sum_j (dS_ij / |col_j|) col_j  for a 256-wide slice of D.  Partials per column split.
 // ------------------------------------------------------------------------------------------------
-constexpr int kBR = 32, kBC = 32, kBK = 32, kBLd = 33, kBDz = 256, kBLdB = kBDz + 1;
+constexpr int kBR = 32, kBC = 32, kBK = 128, kBLd = kBK + 1, kBDz = 256, kBLdB = kBDz + 1, kBLdS = 33;
 
 __global__ void __launch_bounds__(kNT)
 global_bwd_kernel(const float* __restrict__ a_loc, const float* __restrict__ b_loc, const float* __restrict__ a_all,
@@ -153,10 +154,10 @@ global_bwd_kernel(const float* __restrict__ a_loc, const float* __restrict__ b_l
                   const float* __restrict__ norms /* [2][B] */, const float* __restrict__ coef /* c_a, c_b */,
                   float* __restrict__ out /* [2][nsplit][B][D] */) {
   extern __shared__ float smem[];
-  float* stA = smem;                       // [32 x 33]
-  float* stB = stA + kBR * kBLd;           // [32 x 33]
+  float* stA = smem;                       // [32 x 129]
+  float* stB = stA + kBR * kBLd;           // [32 x 129]
   float* dS = stB + kBC * kBLd;            // [32 x 33]
-  float* bt = dS + kBR * kBLd;             // [32 x 257]
+  float* bt = dS + kBR * kBLdS;            // [32 x 257]
   float* cn = bt + kBC * kBLdB;            // [32] column norms
   const int rb = (B + kBR - 1) / kBR;
   const int dir = blockIdx.x / rb, r0 = (blockIdx.x - dir * rb) * kBR;
@@ -212,11 +213,11 @@ global_bwd_kernel(const float* __restrict__ a_loc, const float* __restrict__ b_l
             if (gcol == col_offset + grow) g -= (c_self + c_other);
             g /= cn[n];                                           // d/d(col_hat) -> raw column, first factor
           }
-          dS[m * kBLd + n] = g;
+          dS[m * kBLdS + n] = g;
         }
     }
     __syncthreads();
-    tile_mac<2, 16>(oacc, 0, 0, kBR, dzn, kBC, [&](int m, int k) { return dS[m * kBLd + k]; },
+    tile_mac<2, 16>(oacc, 0, 0, kBR, dzn, kBC, [&](int m, int k) { return dS[m * kBLdS + k]; },
                     [&](int k, int n) { return bt[k * kBLdB + n]; });
   }
   tile_foreach<2, 16>(oacc, 0, 0, rows_valid, dzn, [&](int m, int n, float x) {
@@ -290,7 +291,13 @@ extern "C" int cfa_global_infonce_fwd(const float* a_loc, const float* b_loc, co
   float* diag = part_l + (size_t)2 * ns * B;
   cudaStream_t st = (cudaStream_t)stream;
   dim3 grid((B + kGR - 1) / kGR, ns, 2);
-  global_fwd_kernel<<<grid, kNT, 0, st>>>(a_loc, b_loc, a_all, b_all, B, Bg, D, col_offset, scale, eps, part_m, part_l,
+  const size_t fsmem = sizeof(float) * ((kGR + kGC) * kGLd + kGR + kGC);
+  static bool fattr = false;
+  if (!fattr) {
+    CFA_CUDA_TRY(cudaFuncSetAttribute(global_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
+    fattr = true;
+  }
+  global_fwd_kernel<<<grid, kNT, fsmem, st>>>(a_loc, b_loc, a_all, b_all, B, Bg, D, col_offset, scale, eps, part_m, part_l,
                                           diag, norms2);
   CFA_CUDA_TRY(cudaGetLastError());
   global_combine_kernel<<<1, kNT, 0, st>>>(part_m, part_l, diag, B, ns, lse2, sums2, Bg, local_partial, mask, T, gw, lw, out8);
@@ -304,7 +311,7 @@ extern "C" int cfa_global_infonce_bwd(const float* a_loc, const float* b_loc, co
   if (B <= 0 || Bg <= 0 || D <= 0 || D > 1024 || col_offset < 0 || col_offset + B > Bg) return CFA_ERR_BAD_ARG;
   if (!workspace || workspace_bytes < cfa_global_infonce_workspace_bytes(B, Bg, D)) return CFA_ERR_WORKSPACE;
   const int ns = gb_splits(B, Bg, D);
-  const size_t smem = sizeof(float) * (3 * kBR * kBLd + kBC * kBLdB + kBC);
+  const size_t smem = sizeof(float) * (2 * kBR * kBLd + kBR * kBLdS + kBC * kBLdB + kBC);
   static bool attr_set = false;
   if (!attr_set) {
     CFA_CUDA_TRY(cudaFuncSetAttribute(global_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
