@@ -346,31 +346,51 @@ def main():
     bwd_ms = statistics.mean(a.elapsed_time(b) for a, b in kev["cfa_sparc_bwd"])
     fwd_ms = statistics.mean(a.elapsed_time(b) for a, b in kev["cfa_sparc_fwd"])
 
-    # ---- end to end through the public API with HOST buffers (pinned), H2D + loss read-back inside the timing
+    # ---- end to end through the public API with HOST buffers (pinned): every step copies ITS inputs host->device and
+    # reads its loss back device->host inside the timed region.  Like any input pipeline, the copy of step i+1 is
+    # issued on a copy stream while step i computes (two device buffers); nothing is cached across steps.
     hv = torch.randn(B, P, D).to(dt).pin_memory()
     hl = torch.randn(B, T, D).to(dt).pin_memory()
     hm = torch.ones(B, T, dtype=torch.bool).pin_memory()
-    dv_ = torch.empty(B, P, D, dtype=dt, device=dev)
-    dl_ = torch.empty(B, T, D, dtype=dt, device=dev)
-    dm_ = torch.empty(B, T, dtype=torch.bool, device=dev)
+    bufs = [(torch.empty(B, P, D, dtype=dt, device=dev), torch.empty(B, T, D, dtype=dt, device=dev),
+             torch.empty(B, T, dtype=torch.bool, device=dev)) for _ in range(2)]
+    copy_stream = torch.cuda.Stream(device=dev)
+    copied = [torch.cuda.Event() for _ in range(2)]
+    consumed = [torch.cuda.Event() for _ in range(2)]
+    main = torch.cuda.current_stream(dev)
 
-    def e2e_step():
-        dv_.copy_(hv, non_blocking=True); dl_.copy_(hl, non_blocking=True); dm_.copy_(hm, non_blocking=True)
-        v = dv_.detach().requires_grad_(True); l = dl_.detach().requires_grad_(True)
-        out = crit(v, l, dm_)
-        out["total_loss"].backward()
-        return float(out["total_loss"].item())            # D2H read of the step's result
+    def issue_copy(k):
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(consumed[k])            # previous user of this buffer is done
+            bufs[k][0].copy_(hv, non_blocking=True); bufs[k][1].copy_(hl, non_blocking=True)
+            bufs[k][2].copy_(hm, non_blocking=True)
+            copied[k].record(copy_stream)
 
-    for _ in range(3):
-        e2e_step()
+    def e2e_run(n):
+        losses_h = torch.empty(n, dtype=torch.float32).pin_memory()
+        for k in range(2):
+            consumed[k].record(main)
+        issue_copy(0)
+        for i in range(n):
+            k = i & 1
+            if i + 1 < n:
+                issue_copy(k ^ 1)
+            main.wait_event(copied[k])
+            v = bufs[k][0].detach().requires_grad_(True); l = bufs[k][1].detach().requires_grad_(True)
+            out = crit(v, l, bufs[k][2])
+            out["total_loss"].backward()
+            consumed[k].record(main)
+            losses_h[i:i + 1].copy_(out["total_loss"].detach().reshape(1), non_blocking=True)   # D2H read of the result
+        return losses_h
+
+    e2e_run(3)
     sync_all()
     e2e_steps = max(5, min(args.steps, 20))
-    t0 = time.perf_counter()
     e0.record()
-    for _ in range(e2e_steps):
-        e2e_step()
+    lh = e2e_run(e2e_steps)
     e1.record()
     sync_all()
+    assert bool(torch.isfinite(lh).all())
     e2e_ms = e0.elapsed_time(e1)
     t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
     if world > 1:
@@ -404,7 +424,8 @@ def main():
                      "peak_source": pk["src"] + ", sustained bf16 GEMM", "algorithmic_flops_per_launch": bwd_flops},
         "e2e": {"value": round(e2e_val, 1), "unit": UNIT,
                 "h2d_bytes_per_step": int(hv.numel() * hv.element_size() + hl.numel() * hl.element_size() + hm.numel()),
-                "d2h_bytes_per_step": 4, "steps": e2e_steps},
+                "d2h_bytes_per_step": 4, "steps": e2e_steps,
+                "note": "pinned host buffers; H2D of step i+1 overlaps compute of step i (copy stream); PCIe-bound"},
         "gpu_launches": launches, "clocks": clocks,
     }
     del vs, ls

@@ -45,72 +45,80 @@ def _dist_ctx(group, gather: bool):
     return dist.get_world_size(group), dist.get_rank(group), group
 
 
-def _all_gather_rows(x: torch.Tensor, world: int, group) -> torch.Tensor:
-    """NCCL all-gather of equally sized row blocks (the one exchange step of the path)."""
+def _gather_embeddings(ab: torch.Tensor, world: int, group):
+    """Collective 1 of 2: all-gather of the [2, B, D] (image | text) local rows -> ([Bg, D], [Bg, D]) with
+    rank-major global row order.  NCCL over NVLink on the GPU box; gloo on CPU in tests/test_dist_gloo.py."""
     if world == 1:
-        return x
+        return ab[0], ab[1]
     import torch.distributed as dist
-    out = torch.empty((world * x.shape[0],) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
-    dist.all_gather_into_tensor(out, x.contiguous(), group=group)
-    return out
+    _, B, D = ab.shape
+    gathered = torch.empty(world * 2, B, D, dtype=ab.dtype, device=ab.device)       # concatenated along dim 0
+    dist.all_gather_into_tensor(gathered, ab.contiguous(), group=group)
+    ab_all = gathered.view(world, 2, B, D).permute(1, 0, 2, 3).reshape(2, world * B, D).contiguous()
+    return ab_all[0], ab_all[1]
 
 
-def _gather_lse(lse2: torch.Tensor, world: int, group) -> torch.Tensor:
-    """[2, B] per rank -> [2, world * B] with global row order (rank-major)."""
+def _gather_lse_and_sums(pack: torch.Tensor, B: int, world: int, group):
+    """Collective 2 of 2: all-gather of [lse_a | lse_b | sum CE_a, sum CE_b] (2B+2 floats per rank) ->
+    (lse_all [2, Bg] rank-major, sums2 [2] over the global batch).  The backward needs nothing else."""
     if world == 1:
-        return lse2
-    g = _all_gather_rows(lse2, world, group)                 # [world * 2, B]
-    B = lse2.shape[1]
-    return g.view(world, 2, B).permute(1, 0, 2).reshape(2, world * B).contiguous()
+        return pack[:2 * B].view(2, B), pack[2 * B:]
+    import torch.distributed as dist
+    g = torch.empty(world * (2 * B + 2), dtype=pack.dtype, device=pack.device)
+    dist.all_gather_into_tensor(g, pack.contiguous(), group=group)
+    g = g.view(world, 2 * B + 2)
+    sums2 = g[:, 2 * B:].sum(dim=0)
+    lse_all = g[:, :2 * B].view(world, 2, B).permute(1, 0, 2).reshape(2, world * B).contiguous()
+    return lse_all, sums2
 
 
 class _GlobalState:
-    __slots__ = ("a", "b", "a_all", "b_all", "lse2", "norms2", "off", "world", "group", "scale", "eps", "Bg", "ws")
+    __slots__ = ("a", "b", "a_all", "b_all", "lse2", "lse_all", "norms2", "off", "world", "group", "scale", "eps", "Bg", "ws")
 
 
-def _global_forward(a, b, scale, eps, world, rank, group, fused=None):
-    """a, b: local RAW fp32 [B, D].  Returns (state, sums2) with sums2 = (sum_i CE_a, sum_j CE_b) over the GLOBAL
-    batch (all-reduced when world > 1).  `fused` = (local_partial, mask_u8, T, gw, lw, out8) fuses the SPARC scalar
-    epilogue into the same call when the loss is rank-local."""
+def _global_forward(ab, scale, eps, world, rank, group, fused=None):
+    """ab: local RAW fp32 [2, B, D] (image rows, text rows).  Returns (state, sums2) with sums2 = (sum_i CE_a,
+    sum_j CE_b) over the GLOBAL batch.  Two collectives per step when world > 1: one all-gather of the embeddings
+    and one all-gather of [lse | CE sums] (which also serves the backward, so the backward has no collective).
+    `fused` = (local_partial, mask_u8, T, gw, lw, out8) fuses the SPARC scalar epilogue into the same call when the
+    loss is rank-local."""
     st = _GlobalState()
-    B, D = a.shape
+    _, B, D = ab.shape
+    dev = ab.device
     st.world, st.group, st.scale, st.eps = world, group, scale, eps
     st.off, st.Bg = rank * B, world * B
-    st.a, st.b = a, b
-    st.a_all = _all_gather_rows(a, world, group)
-    st.b_all = _all_gather_rows(b, world, group)
-    f32 = dict(dtype=torch.float32, device=a.device)
-    st.lse2 = torch.empty(2, B, **f32)
+    st.a, st.b = ab[0], ab[1]
+    st.a_all, st.b_all = _gather_embeddings(ab, world, group)
+    f32 = dict(dtype=torch.float32, device=dev)
+    pack = torch.empty(2 * B + 2, **f32)                  # [lse_a | lse_b | sum CE_a, sum CE_b]: one message
+    st.lse2 = pack[:2 * B].view(2, B)
+    sums2 = pack[2 * B:]
     st.norms2 = torch.empty(2, B, **f32)
-    sums2 = torch.empty(2, **f32)
     ws_bytes = _L.cfa_global_infonce_workspace_bytes(B, st.Bg, D)
-    st.ws = torch.empty(ws_bytes, dtype=torch.uint8, device=a.device)
+    st.ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
     if fused is not None and world == 1:
         part, mask_u8, T, gw, lw, out8 = fused
-        _lib.call("cfa_global_infonce_fwd", a.data_ptr(), b.data_ptr(), st.a_all.data_ptr(), st.b_all.data_ptr(), B, st.Bg,
-                  D, st.off, scale, eps, st.lse2.data_ptr(), st.norms2.data_ptr(), sums2.data_ptr(), part.data_ptr(),
+        _lib.call("cfa_global_infonce_fwd", st.a.data_ptr(), st.b.data_ptr(), st.a_all.data_ptr(), st.b_all.data_ptr(), B,
+                  st.Bg, D, st.off, scale, eps, st.lse2.data_ptr(), st.norms2.data_ptr(), sums2.data_ptr(), part.data_ptr(),
                   mask_u8.data_ptr(), T, gw, lw, out8.data_ptr(), st.ws.data_ptr(), ws_bytes, _lib.stream_ptr())
+        st.lse_all = st.lse2
     else:
-        _lib.call("cfa_global_infonce_fwd", a.data_ptr(), b.data_ptr(), st.a_all.data_ptr(), st.b_all.data_ptr(), B, st.Bg,
-                  D, st.off, scale, eps, st.lse2.data_ptr(), st.norms2.data_ptr(), sums2.data_ptr(), 0, 0, 0, 0.0, 0.0, 0,
-                  st.ws.data_ptr(), ws_bytes, _lib.stream_ptr())
-        if world > 1:
-            import torch.distributed as dist
-            dist.all_reduce(sums2, group=group)
+        _lib.call("cfa_global_infonce_fwd", st.a.data_ptr(), st.b.data_ptr(), st.a_all.data_ptr(), st.b_all.data_ptr(), B,
+                  st.Bg, D, st.off, scale, eps, st.lse2.data_ptr(), st.norms2.data_ptr(), sums2.data_ptr(), 0, 0, 0, 0.0,
+                  0.0, 0, st.ws.data_ptr(), ws_bytes, _lib.stream_ptr())
+        st.lse_all, sums2 = _gather_lse_and_sums(pack, B, world, group)
     return st, sums2
 
 
 def _global_backward(st: _GlobalState, coef2: torch.Tensor):
-    """coef2 = device [2] (c_a, c_b)/Bg.  Returns (da, db) w.r.t. the local raw rows; cross-rank terms come
-    from the other direction's gathered LSE vector."""
+    """coef2 = device [2] (c_a, c_b)/Bg.  Returns (da, db) w.r.t. the local raw rows; cross-rank terms come from
+    the other direction's LSE vector gathered in the forward — no collective here."""
     B, D = st.a.shape
-    lse_all = _gather_lse(st.lse2, st.world, st.group)
-    da = torch.empty_like(st.a)
-    db = torch.empty_like(st.b)
+    dab = torch.empty(2, B, D, dtype=torch.float32, device=st.a.device)
     _lib.call("cfa_global_infonce_bwd", st.a.data_ptr(), st.b.data_ptr(), st.a_all.data_ptr(), st.b_all.data_ptr(), B,
-              st.Bg, D, st.off, st.scale, st.eps, st.lse2.data_ptr(), lse_all.data_ptr(), st.norms2.data_ptr(),
-              coef2.data_ptr(), da.data_ptr(), db.data_ptr(), st.ws.data_ptr(), st.ws.numel(), _lib.stream_ptr())
-    return da, db
+              st.Bg, D, st.off, st.scale, st.eps, st.lse2.data_ptr(), st.lse_all.data_ptr(), st.norms2.data_ptr(),
+              coef2.data_ptr(), dab[0].data_ptr(), dab[1].data_ptr(), st.ws.data_ptr(), st.ws.numel(), _lib.stream_ptr())
+    return dab[0], dab[1]
 
 
 # ----------------------------------------------------------------------------------------------
@@ -135,8 +143,8 @@ class _SparcFunction(torch.autograd.Function):
         T = l.shape[1]
         code = _lib.DTYPE_CODE[v.dtype]
         f32 = dict(dtype=torch.float32, device=dev)
-        pooled_v = torch.empty(B, D, **f32)
-        pooled_l = torch.empty(B, D, **f32)
+        pooled = torch.empty(2, B, D, **f32)               # [image | text] pooled means: one all-gather message
+        pooled_v, pooled_l = pooled[0], pooled[1]
         lse_r = torch.empty(B, T, **f32)
         lse_c = torch.empty(B, T, **f32)
         part = torch.empty(B, 2, **f32)
@@ -149,7 +157,7 @@ class _SparcFunction(torch.autograd.Function):
                       part.data_ptr(), tt_logits.data_ptr(), g_inv.data_ptr(), path, _lib.stream_ptr())
             world, rank, group = _dist_ctx(group, gather)
             out8 = torch.empty(8, **f32)
-            gst, sums = _global_forward(pooled_v, pooled_l, scale, _NORM_EPS, world, rank, group,
+            gst, sums = _global_forward(pooled, scale, _NORM_EPS, world, rank, group,
                                         fused=(part, mask_u8, T, gw, lw, out8))
             if world > 1:       # scalar epilogue after the cross-rank all-reduce of the CE sums
                 _lib.call("cfa_sparc_finalize", sums.data_ptr(), gst.Bg, part.data_ptr(), mask_u8.data_ptr(), B, T, gw,
@@ -192,7 +200,7 @@ class _PairwiseFunction(torch.autograd.Function):
         a32 = a.detach().to(torch.float32).contiguous()
         b32 = b.detach().to(torch.float32).contiguous()
         with torch.cuda.device(dev):
-            gst, sums = _global_forward(a32, b32, scale, eps, 1, 0, None)
+            gst, sums = _global_forward(torch.stack([a32, b32]), scale, eps, 1, 0, None)
         ctx.gst = gst
         ctx.dt = (a.dtype, b.dtype)
         return sums[0] / a.shape[0]
@@ -252,12 +260,11 @@ class _ClipFunction(torch.autograd.Function):
         dev = _lib.require_cuda(img, txt)
         if img.dim() != 2 or img.shape != txt.shape:
             raise _lib.CfaError(f"CustomCLIPLoss: expected two [B,D] tensors, got {tuple(img.shape)}, {tuple(txt.shape)}")
-        a = img.detach().to(torch.float32).contiguous()
-        b = txt.detach().to(torch.float32).contiguous()
+        ab = torch.stack([img.detach().to(torch.float32), txt.detach().to(torch.float32)])
         with torch.cuda.device(dev):
             world, rank, group = _dist_ctx(group, gather)
             # x / x.norm(): no eps in this loss (losses.py:17-18)
-            gst, sums = _global_forward(a, b, 1.0 / temperature, 0.0, world, rank, group)
+            gst, sums = _global_forward(ab, 1.0 / temperature, 0.0, world, rank, group)
             loss = (sums[0] + sums[1]) * (0.5 / gst.Bg)            # mean CE both ways, averaged (losses.py:27-29)
         ctx.gst = gst
         ctx.dt = (img.dtype, txt.dtype)

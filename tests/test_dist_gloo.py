@@ -1,5 +1,5 @@
 """World-size-2 gloo test of the host-side plumbing of the gathered global InfoNCE:
-_dist_ctx / _all_gather_rows / _gather_lse and the all-reduce of the CE sums, with the per-rank kernel math
+_dist_ctx / _gather_embeddings / _gather_lse_and_sums (the two collectives of a step), with the per-rank kernel math
 stood in by the oracle (the CUDA kernels themselves are covered by tests/test_gpu_losses.py on one GPU with
 emulated ranks).  Runs on CPU."""
 import os
@@ -38,16 +38,13 @@ def _worker(rank, world, port, q):
         w, r, grp = L._dist_ctx(None, True)
         assert (w, r) == (world, rank)
         assert L._dist_ctx(None, False) == (1, 0, None)
-        a_all = L._all_gather_rows(a, w, grp)
-        b_all = L._all_gather_rows(b, w, grp)
+        a_all, b_all = L._gather_embeddings(torch.stack([a, b]), w, grp)
         assert torch.equal(a_all, a_full) and torch.equal(b_all, b_full)
         # per-rank "kernel" (oracle stand-in): local rows vs global columns, both directions
         fa, fb, bwd = lo.gathered_infonce_rank(a, b, a_all, b_all, rank, s, 0.5, 0.5)
-        sums = torch.stack([fa["loss_sum"], fb["loss_sum"]])
-        dist.all_reduce(sums)                                   # what _global_forward does with sums2
+        pack = torch.cat([fa["lse"], fb["lse"], torch.stack([fa["loss_sum"], fb["loss_sum"]])])   # kernel's [lse | sums]
+        lse_all, sums = L._gather_lse_and_sums(pack, B, w, grp)   # [2, world*B] rank-major rows, global CE sums
         loss = 0.5 * sums.sum() / (world * B)
-        lse2 = torch.stack([fa["lse"], fb["lse"]])              # [2, B] like the kernel's lse2
-        lse_all = L._gather_lse(lse2, w, grp)                   # [2, world*B], rank-major rows
         da, db = bwd(lse_all[0], lse_all[1])
         # single-process reference on the concatenated batch
         f1 = lo.infonce_forward(a_full, b_full, s)
