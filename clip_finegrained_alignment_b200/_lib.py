@@ -96,7 +96,8 @@ def ptr(t) -> int:
 
 
 def stream_ptr() -> int:
-    return torch.cuda.current_stream().cuda_stream
+    # torch.cuda.current_stream() costs ~20 us of Python per call; the raw query is ~1 us
+    return torch._C._cuda_getCurrentRawStream(torch._C._cuda_getDevice())
 
 
 def require_cuda(*tensors) -> torch.device:

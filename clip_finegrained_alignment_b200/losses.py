@@ -22,6 +22,8 @@ from __future__ import annotations
 
 from typing import Dict, Optional
 
+import contextlib
+
 import torch
 import torch.nn as nn
 
@@ -89,23 +91,25 @@ def _global_forward(ab, scale, eps, world, rank, group, fused=None):
     st.off, st.Bg = rank * B, world * B
     st.a, st.b = ab[0], ab[1]
     st.a_all, st.b_all = _gather_embeddings(ab, world, group)
-    f32 = dict(dtype=torch.float32, device=dev)
-    pack = torch.empty(2 * B + 2, **f32)                  # [lse_a | lse_b | sum CE_a, sum CE_b]: one message
+    # one allocation: [lse_a | lse_b | sum CE_a, sum CE_b] (= one collective message) | norms2 | kernel workspace
+    ws_bytes = _L.cfa_global_infonce_workspace_bytes(B, st.Bg, D)
+    nf = 4 * B + 4
+    buf = torch.empty(nf + (ws_bytes + 3) // 4, dtype=torch.float32, device=dev)
+    pack = buf[:2 * B + 2]
     st.lse2 = pack[:2 * B].view(2, B)
     sums2 = pack[2 * B:]
-    st.norms2 = torch.empty(2, B, **f32)
-    ws_bytes = _L.cfa_global_infonce_workspace_bytes(B, st.Bg, D)
-    st.ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    st.norms2 = buf[2 * B + 4:4 * B + 4].view(2, B)
+    st.ws = buf[nf:]
     if fused is not None and world == 1:
         part, mask_u8, T, gw, lw, out8 = fused
         _lib.call("cfa_global_infonce_fwd", st.a.data_ptr(), st.b.data_ptr(), st.a_all.data_ptr(), st.b_all.data_ptr(), B,
                   st.Bg, D, st.off, scale, eps, st.lse2.data_ptr(), st.norms2.data_ptr(), sums2.data_ptr(), part.data_ptr(),
-                  mask_u8.data_ptr(), T, gw, lw, out8.data_ptr(), st.ws.data_ptr(), ws_bytes, _lib.stream_ptr())
+                  mask_u8.data_ptr(), T, gw, lw, out8.data_ptr(), st.ws.data_ptr(), st.ws.numel() * 4, _lib.stream_ptr())
         st.lse_all = st.lse2
     else:
         _lib.call("cfa_global_infonce_fwd", st.a.data_ptr(), st.b.data_ptr(), st.a_all.data_ptr(), st.b_all.data_ptr(), B,
                   st.Bg, D, st.off, scale, eps, st.lse2.data_ptr(), st.norms2.data_ptr(), sums2.data_ptr(), 0, 0, 0, 0.0,
-                  0.0, 0, st.ws.data_ptr(), ws_bytes, _lib.stream_ptr())
+                  0.0, 0, st.ws.data_ptr(), st.ws.numel() * 4, _lib.stream_ptr())
         st.lse_all, sums2 = _gather_lse_and_sums(pack, B, world, group)
     return st, sums2
 
@@ -117,7 +121,8 @@ def _global_backward(st: _GlobalState, coef2: torch.Tensor):
     dab = torch.empty(2, B, D, dtype=torch.float32, device=st.a.device)
     _lib.call("cfa_global_infonce_bwd", st.a.data_ptr(), st.b.data_ptr(), st.a_all.data_ptr(), st.b_all.data_ptr(), B,
               st.Bg, D, st.off, st.scale, st.eps, st.lse2.data_ptr(), st.lse_all.data_ptr(), st.norms2.data_ptr(),
-              coef2.data_ptr(), dab[0].data_ptr(), dab[1].data_ptr(), st.ws.data_ptr(), st.ws.numel(), _lib.stream_ptr())
+              coef2.data_ptr(), dab.data_ptr(), dab.data_ptr() + 4 * B * D, st.ws.data_ptr(), st.ws.numel() * 4,
+              _lib.stream_ptr())
     return dab[0], dab[1]
 
 
@@ -142,52 +147,54 @@ class _SparcFunction(torch.autograd.Function):
         B, P, D = v.shape
         T = l.shape[1]
         code = _lib.DTYPE_CODE[v.dtype]
-        f32 = dict(dtype=torch.float32, device=dev)
-        pooled = torch.empty(2, B, D, **f32)               # [image | text] pooled means: one all-gather message
-        pooled_v, pooled_l = pooled[0], pooled[1]
-        lse_r = torch.empty(B, T, **f32)
-        lse_c = torch.empty(B, T, **f32)
-        part = torch.empty(B, 2, **f32)
-        # one fp32 block of state saved for the backward: row inverse norms | T x T logits | 1/|G_t|
-        saved = torch.empty(B * (P + T) + B * T * T + B * T, **f32)
-        inv_norm, tt_logits, g_inv = saved[:B * (P + T)], saved[B * (P + T):B * (P + T) + B * T * T], saved[B * (P + T) + B * T * T:]
-        with torch.cuda.device(dev):
+        # ONE fp32 allocation, carved by pointer arithmetic (host time matters at ~0.5 ms per step):
+        # pooled [2,B,D] | out8 | lse_row [B,T] | lse_col [B,T] | local_partial [B,2] | row_inv_norm [B(P+T)] |
+        # tt_logits [B,T,T] | g_inv_norm [B,T]
+        sizes = (2 * B * D, 8, B * T, B * T, 2 * B, B * (P + T), B * T * T, B * T)
+        blk = torch.empty(sum(sizes), dtype=torch.float32, device=dev)
+        base = blk.data_ptr()
+        off = [0]
+        for n in sizes:
+            off.append(off[-1] + n)
+        ptr = [base + 4 * o for o in off]
+        pooled = blk[:2 * B * D].view(2, B, D)
+        out8 = blk[off[1]:off[2]]
+        part_t = blk[off[4]:off[5]]
+        same_dev = torch.cuda.current_device() == dev.index
+        with (contextlib.nullcontext() if same_dev else torch.cuda.device(dev)):
             _lib.call("cfa_sparc_fwd", v.data_ptr(), l.data_ptr(), mask_u8.data_ptr(), B, P, T, D, code, thr, scale,
-                      inv_norm.data_ptr(), pooled_v.data_ptr(), pooled_l.data_ptr(), lse_r.data_ptr(), lse_c.data_ptr(),
-                      part.data_ptr(), tt_logits.data_ptr(), g_inv.data_ptr(), path, _lib.stream_ptr())
+                      ptr[5], ptr[0], ptr[0] + 4 * B * D, ptr[2], ptr[3], ptr[4], ptr[6], ptr[7], path, _lib.stream_ptr())
             world, rank, group = _dist_ctx(group, gather)
-            out8 = torch.empty(8, **f32)
             gst, sums = _global_forward(pooled, scale, _NORM_EPS, world, rank, group,
-                                        fused=(part, mask_u8, T, gw, lw, out8))
-            if world > 1:       # scalar epilogue after the cross-rank all-reduce of the CE sums
-                _lib.call("cfa_sparc_finalize", sums.data_ptr(), gst.Bg, part.data_ptr(), mask_u8.data_ptr(), B, T, gw,
-                          lw, out8.data_ptr(), _lib.stream_ptr())
-        ctx.save_for_backward(v, l, mask_u8, lse_r, lse_c, out8, saved)
+                                        fused=(part_t, mask_u8, T, gw, lw, out8))
+            if world > 1:       # scalar epilogue after the cross-rank gather of the CE sums
+                _lib.call("cfa_sparc_finalize", sums.data_ptr(), gst.Bg, ptr[4], mask_u8.data_ptr(), B, T, gw, lw, ptr[1],
+                          _lib.stream_ptr())
+        ctx.save_for_backward(v, l, mask_u8, blk)
         ctx.gst = gst
-        ctx.hp = (thr, gw, lw, scale, code, path)
+        ctx.hp = (thr, gw, lw, scale, code, path, ptr)
         return out8[:7].clone()
 
     @staticmethod
     def backward(ctx, grad7):
-        v, l, mask_u8, lse_r, lse_c, out8, saved = ctx.saved_tensors
-        thr, gw, lw, scale, code, path = ctx.hp
+        v, l, mask_u8, blk = ctx.saved_tensors
+        thr, gw, lw, scale, code, path, ptr = ctx.hp
         gst = ctx.gst
         B, P, D = v.shape
         T = l.shape[1]
         dev = v.device
-        inv_norm, tt_logits, g_inv = saved[:B * (P + T)], saved[B * (P + T):B * (P + T) + B * T * T], saved[B * (P + T) + B * T * T:]
-        grad7 = grad7.to(torch.float32).contiguous()
-        with torch.cuda.device(dev):
+        if grad7.dtype != torch.float32 or not grad7.is_contiguous():
+            grad7 = grad7.to(torch.float32).contiguous()
+        same_dev = torch.cuda.current_device() == dev.index
+        with (contextlib.nullcontext() if same_dev else torch.cuda.device(dev)):
             coef = torch.empty(8, dtype=torch.float32, device=dev)
-            _lib.call("cfa_sparc_coef", grad7.data_ptr(), gw, lw, gst.Bg, out8.data_ptr(), coef.data_ptr(),
-                                         _lib.stream_ptr())
-            dpv, dpl = _global_backward(gst, coef[0:2])
+            _lib.call("cfa_sparc_coef", grad7.data_ptr(), gw, lw, gst.Bg, ptr[1], coef.data_ptr(), _lib.stream_ptr())
+            dpv, dpl = _global_backward(gst, coef)
             dv = torch.empty_like(v)
             dl = torch.empty_like(l)
             _lib.call("cfa_sparc_bwd", v.data_ptr(), l.data_ptr(), mask_u8.data_ptr(), B, P, T, D, code, thr, scale,
-                      inv_norm.data_ptr(), lse_r.data_ptr(), lse_c.data_ptr(), tt_logits.data_ptr(), g_inv.data_ptr(),
-                      coef[2:4].data_ptr(), dpv.data_ptr(), dpl.data_ptr(), dv.data_ptr(), dl.data_ptr(), path,
-                      _lib.stream_ptr())
+                      ptr[5], ptr[2], ptr[3], ptr[6], ptr[7], coef.data_ptr() + 8, dpv.data_ptr(), dpl.data_ptr(),
+                      dv.data_ptr(), dl.data_ptr(), path, _lib.stream_ptr())
         return dv, dl, None, None, None, None, None, None, None, None
 
 
@@ -248,7 +255,7 @@ class SPARCLoss(nn.Module):
         out = _SparcFunction.apply(v_patch_embed, l_token_embed, language_mask, float(self.similarity_threshold),
                                    float(self.global_loss_weight), float(self.local_loss_weight),
                                    float(self.inverse_temperature), self.gather, self.process_group, self.kernel_path)
-        return {k: out[i] for i, k in enumerate(SPARC_KEYS)}
+        return dict(zip(SPARC_KEYS, out.unbind(0)))        # one autograd node for the 7 views
 
 
 # ----------------------------------------------------------------------------------------------
