@@ -268,6 +268,17 @@ static int gb_splits(int B, int Bg, int D) {
   return s;
 }
 
+// tensor-core implementation (global_infonce_tc.cu)
+bool global_tc_supported(int B, int Bg, int D);
+size_t global_tc_workspace_bytes(int B, int Bg, int D);
+int global_tc_fwd(const float* a_loc, const float* b_loc, const float* a_all, const float* b_all, int B, int Bg, int D,
+                  int col_offset, float scale, float eps, float* norms2, float** part_m, float** part_l, float** diag,
+                  int* nsplit, void* ws, cudaStream_t st);
+int global_tc_bwd(int B, int Bg, int D, int col_offset, float scale, const float* lse_loc2, const float* lse_all2,
+                  const float* coef2, float** dpart, int* nsplit, void* ws, cudaStream_t st);
+
+static bool use_tc(int B, int Bg, int D, int path) { return path != 1 && global_tc_supported(B, Bg, D); }
+
 }  // namespace cfa
 
 using namespace cfa;
@@ -275,16 +286,36 @@ using namespace cfa;
 extern "C" size_t cfa_global_infonce_workspace_bytes(int B, int Bg, int D) {
   const size_t fwd = ((size_t)4 * gf_splits(B, Bg) * B + 2 * (size_t)B) * sizeof(float);
   const size_t bwd = (size_t)2 * gb_splits(B, Bg, D) * B * D * sizeof(float);
-  return fwd > bwd ? fwd : bwd;
+  size_t n = fwd > bwd ? fwd : bwd;
+  if (global_tc_supported(B, Bg, D)) { const size_t t = global_tc_workspace_bytes(B, Bg, D); if (t > n) n = t; }
+  return n;
+}
+
+// path: 0 = auto (tensor cores when D % 64 == 0 and D <= 512), 1 = fp32-exact CUDA cores, 2 = tensor cores
+extern "C" int cfa_global_infonce_path(int B, int Bg, int D, int path) {
+  if (path == 2 && !global_tc_supported(B, Bg, D)) return CFA_ERR_UNSUPPORTED;
+  return use_tc(B, Bg, D, path) ? 2 : 1;
 }
 
 extern "C" int cfa_global_infonce_fwd(const float* a_loc, const float* b_loc, const float* a_all, const float* b_all, int B,
                                       int Bg, int D, int col_offset, float scale, float eps, float* lse2, float* norms2,
                                       float* sums2, const float* local_partial, const uint8_t* mask, int T, float gw,
-                                      float lw, float* out8, void* workspace, size_t workspace_bytes, void* stream) {
+                                      float lw, float* out8, void* workspace, size_t workspace_bytes, int path,
+                                      void* stream) {
   if (B <= 0 || Bg <= 0 || D <= 0 || col_offset < 0 || col_offset + B > Bg) return CFA_ERR_BAD_ARG;
   if (!workspace || workspace_bytes < cfa_global_infonce_workspace_bytes(B, Bg, D)) return CFA_ERR_WORKSPACE;
   if (out8 && (Bg != B || !local_partial || !mask)) return CFA_ERR_BAD_ARG;   // fused scalar epilogue: single process only
+  if (path == 2 && !global_tc_supported(B, Bg, D)) return CFA_ERR_UNSUPPORTED;
+  if (use_tc(B, Bg, D, path)) {
+    float *pm, *pl, *dg;
+    int nsp;
+    const int rc = global_tc_fwd(a_loc, b_loc, a_all, b_all, B, Bg, D, col_offset, scale, eps, norms2, &pm, &pl, &dg, &nsp,
+                                 workspace, (cudaStream_t)stream);
+    if (rc != CFA_OK) return rc;
+    global_combine_kernel<<<1, kNT, 0, (cudaStream_t)stream>>>(pm, pl, dg, B, nsp, lse2, sums2, Bg, local_partial, mask, T, gw,
+                                                               lw, out8);
+    return launch_status();
+  }
   const int ns = gf_splits(B, Bg);
   float* part_m = (float*)workspace;
   float* part_l = part_m + (size_t)2 * ns * B;
@@ -307,9 +338,19 @@ extern "C" int cfa_global_infonce_fwd(const float* a_loc, const float* b_loc, co
 extern "C" int cfa_global_infonce_bwd(const float* a_loc, const float* b_loc, const float* a_all, const float* b_all, int B,
                                       int Bg, int D, int col_offset, float scale, float eps, const float* lse_loc2,
                                       const float* lse_all2, const float* norms2, const float* coef2, float* da, float* db,
-                                      void* workspace, size_t workspace_bytes, void* stream) {
+                                      void* workspace, size_t workspace_bytes, int path, void* stream) {
   if (B <= 0 || Bg <= 0 || D <= 0 || D > 1024 || col_offset < 0 || col_offset + B > Bg) return CFA_ERR_BAD_ARG;
   if (!workspace || workspace_bytes < cfa_global_infonce_workspace_bytes(B, Bg, D)) return CFA_ERR_WORKSPACE;
+  if (path == 2 && !global_tc_supported(B, Bg, D)) return CFA_ERR_UNSUPPORTED;
+  if (use_tc(B, Bg, D, path)) {       // needs the SAME workspace the forward call used (normalised hi/lo operands live there)
+    float* dpart;
+    int nsp;
+    const int rc = global_tc_bwd(B, Bg, D, col_offset, scale, lse_loc2, lse_all2, coef2, &dpart, &nsp, workspace,
+                                 (cudaStream_t)stream);
+    if (rc != CFA_OK) return rc;
+    global_norm_bwd_kernel<<<dim3(B, 2), 128, 0, (cudaStream_t)stream>>>(a_loc, b_loc, norms2, dpart, nsp, B, D, da, db);
+    return launch_status();
+  }
   const int ns = gb_splits(B, Bg, D);
   const size_t smem = sizeof(float) * (2 * kBR * kBLd + kBR * kBLdS + kBC * kBLdB + kBC);
   static bool attr_set = false;

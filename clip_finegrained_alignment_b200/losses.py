@@ -75,10 +75,11 @@ def _gather_lse_and_sums(pack: torch.Tensor, B: int, world: int, group):
 
 
 class _GlobalState:
-    __slots__ = ("a", "b", "a_all", "b_all", "lse2", "lse_all", "norms2", "off", "world", "group", "scale", "eps", "Bg", "ws")
+    __slots__ = ("a", "b", "a_all", "b_all", "lse2", "lse_all", "norms2", "off", "world", "group", "scale", "eps", "Bg", "ws",
+                 "path")
 
 
-def _global_forward(ab, scale, eps, world, rank, group, fused=None):
+def _global_forward(ab, scale, eps, world, rank, group, fused=None, path=0):
     """ab: local RAW fp32 [2, B, D] (image rows, text rows).  Returns (state, sums2) with sums2 = (sum_i CE_a,
     sum_j CE_b) over the GLOBAL batch.  Two collectives per step when world > 1: one all-gather of the embeddings
     and one all-gather of [lse | CE sums] (which also serves the backward, so the backward has no collective).
@@ -87,7 +88,7 @@ def _global_forward(ab, scale, eps, world, rank, group, fused=None):
     st = _GlobalState()
     _, B, D = ab.shape
     dev = ab.device
-    st.world, st.group, st.scale, st.eps = world, group, scale, eps
+    st.world, st.group, st.scale, st.eps, st.path = world, group, scale, eps, path
     st.off, st.Bg = rank * B, world * B
     st.a, st.b = ab[0], ab[1]
     st.a_all, st.b_all = _gather_embeddings(ab, world, group)
@@ -104,12 +105,12 @@ def _global_forward(ab, scale, eps, world, rank, group, fused=None):
         part, mask_u8, T, gw, lw, out8 = fused
         _lib.call("cfa_global_infonce_fwd", st.a.data_ptr(), st.b.data_ptr(), st.a_all.data_ptr(), st.b_all.data_ptr(), B,
                   st.Bg, D, st.off, scale, eps, st.lse2.data_ptr(), st.norms2.data_ptr(), sums2.data_ptr(), part.data_ptr(),
-                  mask_u8.data_ptr(), T, gw, lw, out8.data_ptr(), st.ws.data_ptr(), st.ws.numel() * 4, _lib.stream_ptr())
+                  mask_u8.data_ptr(), T, gw, lw, out8.data_ptr(), st.ws.data_ptr(), st.ws.numel() * 4, path, _lib.stream_ptr())
         st.lse_all = st.lse2
     else:
         _lib.call("cfa_global_infonce_fwd", st.a.data_ptr(), st.b.data_ptr(), st.a_all.data_ptr(), st.b_all.data_ptr(), B,
                   st.Bg, D, st.off, scale, eps, st.lse2.data_ptr(), st.norms2.data_ptr(), sums2.data_ptr(), 0, 0, 0, 0.0,
-                  0.0, 0, st.ws.data_ptr(), st.ws.numel() * 4, _lib.stream_ptr())
+                  0.0, 0, st.ws.data_ptr(), st.ws.numel() * 4, path, _lib.stream_ptr())
         st.lse_all, sums2 = _gather_lse_and_sums(pack, B, world, group)
     return st, sums2
 
@@ -122,7 +123,7 @@ def _global_backward(st: _GlobalState, coef2: torch.Tensor):
     _lib.call("cfa_global_infonce_bwd", st.a.data_ptr(), st.b.data_ptr(), st.a_all.data_ptr(), st.b_all.data_ptr(), B,
               st.Bg, D, st.off, st.scale, st.eps, st.lse2.data_ptr(), st.lse_all.data_ptr(), st.norms2.data_ptr(),
               coef2.data_ptr(), dab.data_ptr(), dab.data_ptr() + 4 * B * D, st.ws.data_ptr(), st.ws.numel() * 4,
-              _lib.stream_ptr())
+              st.path, _lib.stream_ptr())
     return dab[0], dab[1]
 
 
@@ -165,8 +166,9 @@ class _SparcFunction(torch.autograd.Function):
             _lib.call("cfa_sparc_fwd", v.data_ptr(), l.data_ptr(), mask_u8.data_ptr(), B, P, T, D, code, thr, scale,
                       ptr[5], ptr[0], ptr[0] + 4 * B * D, ptr[2], ptr[3], ptr[4], ptr[6], ptr[7], path, _lib.stream_ptr())
             world, rank, group = _dist_ctx(group, gather)
+            gpath = 1 if (v.dtype == torch.float32 or path == 1) else 0      # fp32 inputs keep the fp32-exact global kernels
             gst, sums = _global_forward(pooled, scale, _NORM_EPS, world, rank, group,
-                                        fused=(part_t, mask_u8, T, gw, lw, out8))
+                                        fused=(part_t, mask_u8, T, gw, lw, out8), path=gpath)
             if world > 1:       # scalar epilogue after the cross-rank gather of the CE sums
                 _lib.call("cfa_sparc_finalize", sums.data_ptr(), gst.Bg, ptr[4], mask_u8.data_ptr(), B, T, gw, lw, ptr[1],
                           _lib.stream_ptr())
@@ -207,7 +209,8 @@ class _PairwiseFunction(torch.autograd.Function):
         a32 = a.detach().to(torch.float32).contiguous()
         b32 = b.detach().to(torch.float32).contiguous()
         with torch.cuda.device(dev):
-            gst, sums = _global_forward(torch.stack([a32, b32]), scale, eps, 1, 0, None)
+            gst, sums = _global_forward(torch.stack([a32, b32]), scale, eps, 1, 0, None,
+                                        path=1 if a.dtype == torch.float32 else 0)
         ctx.gst = gst
         ctx.dt = (a.dtype, b.dtype)
         return sums[0] / a.shape[0]
@@ -271,7 +274,8 @@ class _ClipFunction(torch.autograd.Function):
         with torch.cuda.device(dev):
             world, rank, group = _dist_ctx(group, gather)
             # x / x.norm(): no eps in this loss (losses.py:17-18)
-            gst, sums = _global_forward(ab, 1.0 / temperature, 0.0, world, rank, group)
+            gst, sums = _global_forward(ab, 1.0 / temperature, 0.0, world, rank, group,
+                                        path=1 if img.dtype == torch.float32 else 0)
             loss = (sums[0] + sums[1]) * (0.5 / gst.Bg)            # mean CE both ways, averaged (losses.py:27-29)
         ctx.gst = gst
         ctx.dt = (img.dtype, txt.dtype)

@@ -100,11 +100,15 @@ size_t cfa_global_infonce_workspace_bytes(int B, int Bg, int D);
 int cfa_global_infonce_fwd(const float* a_loc, const float* b_loc, const float* a_all, const float* b_all, int B, int Bg,
                            int D, int col_offset, float scale, float eps, float* lse2, float* norms2, float* sums2,
                            const float* local_partial, const uint8_t* mask, int T, float gw, float lw, float* out8,
-                           void* workspace, size_t workspace_bytes, void* stream);
+                           void* workspace, size_t workspace_bytes, int path, void* stream);
 int cfa_global_infonce_bwd(const float* a_loc, const float* b_loc, const float* a_all, const float* b_all, int B, int Bg,
                            int D, int col_offset, float scale, float eps, const float* lse_loc2, const float* lse_all2,
                            const float* norms2, const float* coef2, float* da, float* db, void* workspace,
-                           size_t workspace_bytes, void* stream);
+                           size_t workspace_bytes, int path, void* stream);
+/* path: 0 = auto (tcgen05 logits tiles with bf16 hi/lo-split normalised operands when D % 64 == 0 and D <= 512),
+ * 1 = fp32-exact CUDA-core tiles, 2 = tensor cores or CFA_ERR_UNSUPPORTED.  The backward must be given the SAME
+ * workspace (and path) as the forward: the tensor-core path keeps its normalised operands there. */
+int cfa_global_infonce_path(int B, int Bg, int D, int path);
 
 /* ------------------------------------------------------------------------------------------------
  * SPARC fine-grained path, one CTA per sample (losses.py:207-212 pooling and :221-252 local loss).
@@ -170,6 +174,9 @@ int cfa_sparc_coef(const float* grad7, float gw, float lw, int global_batch, con
  * ---------------------------------------------------------------------------------------------- */
 /* tuning aid: device buffer [B][32] int64 receiving clock64 phase stamps of the tensor-core backward (NULL = off) */
 int cfa_debug_set_profile_buffer(void* device_buffer);
+/* debugging aid: host-mapped (pinned) int32 buffer [cta][8 warps] receiving progress markers of the tensor-core
+ * global InfoNCE backward, readable from the host while a kernel is stuck (NULL = off) */
+int cfa_debug_set_marker_buffer(void* mapped_buffer);
 int cfa_tc_selftest(int a_mode, int b_mode, int N, int K, const void* A, const void* B, float* D, void* stream);
 int cfa_tc_selftest_timed(int a_mode, int b_mode, int N, int K, const void* A, const void* B, float* D, int repeat,
                           long long* d_cycles, void* stream);   /* tcgen05 issue/throughput microbenchmark */

@@ -117,3 +117,66 @@ def test_sparc_tc_matches_simt_path():
         assert abs(float(a[k]) - float(b[k])) <= 2e-5 * max(1.0, abs(float(b[k]))), k
     assert rel_err(dva.float(), dvb.float()) <= 5e-3
     assert rel_err(dla.float(), dlb.float()) <= 5e-3
+
+
+# ----------------------------------------------------------------------------------------------
+# tensor-core global InfoNCE (tcgen05 logits tiles, bf16 hi/lo-split normalised operands)
+# ----------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("N,B,D,s", [(1, 256, 512, 1.0), (1, 100, 64, 14.285), (3, 70, 256, 5.0), (4, 128, 512, 2.0)])
+def test_global_infonce_tc_emulated_ranks(N, B, D, s):
+    """path=2 (tensor cores) through the C ABI: N emulated ranks of B rows against N*B gathered columns, both
+    directions, forward (lse, CE sums) and backward, vs the fp64 oracle on the concatenated batch."""
+    from clip_finegrained_alignment_b200 import _lib
+    g = torch.Generator().manual_seed(N * 1000 + B + D)
+    Bg = N * B
+    a = torch.randn(Bg, D, generator=g)
+    b = torch.randn(Bg, D, generator=g)
+    f1 = lo.infonce_forward(a.double(), b.double(), s)
+    f2 = lo.infonce_forward(b.double(), a.double(), s)
+    da_ref, db_ref = lo.symmetric_infonce_backward(f1["ah"], f1["an"], f1["bh"], f1["bn"], f1["lse"], f2["lse"], s,
+                                                   0.5, 0.5, float(Bg))
+    ac, bc = a.cuda(), b.cuda()
+    assert _lib.lib.cfa_global_infonce_path(B, Bg, D, 2) == 2
+    ws_bytes = _lib.lib.cfa_global_infonce_workspace_bytes(B, Bg, D)
+    wss, lse, norms = [], [], []
+    sums = torch.zeros(2, device="cuda")
+    for r in range(N):
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device="cuda")
+        l2 = torch.empty(2, B, device="cuda"); n2 = torch.empty(2, B, device="cuda"); s2 = torch.empty(2, device="cuda")
+        al, bl = ac[r * B:(r + 1) * B].contiguous(), bc[r * B:(r + 1) * B].contiguous()
+        _lib.call("cfa_global_infonce_fwd", al.data_ptr(), bl.data_ptr(), ac.data_ptr(), bc.data_ptr(), B, Bg, D, r * B, s,
+                  1e-12, l2.data_ptr(), n2.data_ptr(), s2.data_ptr(), 0, 0, 0, 0.0, 0.0, 0, ws.data_ptr(), ws_bytes, 2,
+                  _lib.stream_ptr())
+        wss.append(ws); lse.append(l2); norms.append(n2); sums += s2
+    ref_loss = float(0.5 * (f1["loss_sum"] + f2["loss_sum"]) / Bg)
+    assert abs(float(0.5 * sums.sum() / Bg) - ref_loss) <= 2e-5 * max(1.0, ref_loss)
+    lse_all = torch.cat(lse, dim=1).contiguous()
+    torch.testing.assert_close(lse_all[0].cpu().double(), f1["lse"], rtol=2e-5, atol=2e-5)
+    torch.testing.assert_close(lse_all[1].cpu().double(), f2["lse"], rtol=2e-5, atol=2e-5)
+    coef = torch.full((2,), 0.5 / Bg, device="cuda")
+    for r in range(N):
+        sl = slice(r * B, (r + 1) * B)
+        al, bl = ac[sl].contiguous(), bc[sl].contiguous()
+        da = torch.empty(B, D, device="cuda"); db = torch.empty(B, D, device="cuda")
+        _lib.call("cfa_global_infonce_bwd", al.data_ptr(), bl.data_ptr(), ac.data_ptr(), bc.data_ptr(), B, Bg, D, r * B, s,
+                  1e-12, lse[r].data_ptr(), lse_all.data_ptr(), norms[r].data_ptr(), coef.data_ptr(), da.data_ptr(),
+                  db.data_ptr(), wss[r].data_ptr(), ws_bytes, 2, _lib.stream_ptr())
+        torch.cuda.synchronize()
+        assert rel_err(da, da_ref[sl]) <= 2e-4, (r, rel_err(da, da_ref[sl]))
+        assert rel_err(db, db_ref[sl]) <= 2e-4, (r, rel_err(db, db_ref[sl]))
+
+
+def test_clip_loss_bf16_uses_tensor_cores():
+    from clip_finegrained_alignment_b200 import CustomCLIPLoss
+    g = torch.Generator().manual_seed(2)
+    B, D = 300, 512
+    a0 = torch.randn(B, D, generator=g).to(torch.bfloat16)
+    b0 = torch.randn(B, D, generator=g).to(torch.bfloat16)
+    a = a0.cuda().requires_grad_(True); b = b0.cuda().requires_grad_(True)
+    out = CustomCLIPLoss(0.07)(a, b)
+    out["total_loss"].backward()
+    o = lo.clip_loss_forward(a0.double(), b0.double(), 0.07)
+    da, db = lo.clip_loss_backward(o, 0.07)
+    assert abs(float(out["clip_loss"]) - float(o["clip_loss"])) <= 1e-4 * float(o["clip_loss"])
+    assert rel_err(a.grad.float(), da) <= 1e-3 + 2.0 ** -8
+    assert rel_err(b.grad.float(), db) <= 1e-3 + 2.0 ** -8
