@@ -152,6 +152,8 @@ struct TcFwdParams {
   float* local_partial;
   float* tt_logits;     // [B][T][T] masked, scaled logits (saved for the backward), may be NULL
   float* g_inv_norm;    // [B][T]   1 / max(||G_t||, eps)
+  bf16* g_split;        // [B][2][T][D] grouped embeddings G as bf16 hi | lo (saved for the backward), may be NULL
+  float* q_save;        // [B][T][NP]   Q = G . v^T (raw), saved for the backward, may be NULL
 };
 
 template <int kNks>
@@ -267,6 +269,15 @@ sparc_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_consta
 #pragma unroll
           for (int k = 0; k < 4; ++k) umma_ss_w(leader, tmem + kTmemL, ga + k * ilk_step, dl0 + 2 * k, idesc_l, (kb | half | k) != 0);
         }
+        if (p.q_save) {       // Q += G_kb . v_kb^T into the (dead) S columns: the backward's dW = dLhat . S_raw - gfac * Q
+          const uint64_t dv0 = sw0 | ((smem_u32(base + (size_t)slot * L.stage_bytes) + L.l_bytes) >> 4);
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            const uint64_t ga = make_smem_desc(smem_u32(Gs + (size_t)(2 * buf + half) * L.g_bytes), il_lbo, 128, kLayoutNone);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_ss_w(leader, tmem, ga + k * ilk_step, dv0 + 2 * k, idesc_s, (kb | half | k) != 0);
+          }
+        }
         umma_commit_w(leader, gs_free + buf);
         umma_commit_w(leader, empty + slot);
       };
@@ -368,6 +379,11 @@ sparc_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_consta
           const uint32_t off = il_offset(NT, row, 8 * g);
           *reinterpret_cast<uint4*>(gh + off) = hi;
           *reinterpret_cast<uint4*>(gl + off) = lo;
+          if (p.g_split && row < T) {
+            bf16* gdst = p.g_split + (((size_t)b * 2) * T + row) * p.D + kb * 64 + 8 * g;
+            *reinterpret_cast<uint4*>(gdst) = hi;
+            *reinterpret_cast<uint4*>(gdst + (size_t)T * p.D) = lo;
+          }
         }
       }
       fence_proxy_async();
@@ -424,6 +440,19 @@ sparc_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_consta
       p.local_partial[2 * b] = red[0] + red[1] + red[2] + red[3];
       p.local_partial[2 * b + 1] = red[4] + red[5] + red[6] + red[7];
     }
+    if (p.q_save) {                                      // Q (TMEM columns of the dead S) -> global, row stride NP
+      for (int c0 = 0; c0 < NP; c0 += 32) {
+        float x[32];
+        tmem_ld32(trow + c0, x);
+        tmem_ld_wait();
+        if (row < T) {
+          float* qd = p.q_save + ((size_t)b * T + row) * NP + c0;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            if (c0 + j < NP) *reinterpret_cast<float4*>(qd + j) = make_float4(x[j], x[j + 1], x[j + 2], x[j + 3]);
+        }
+      }
+    }
     if (p.tt_logits) {                                   // coalesced copy of the T x T logits for the backward
       float* dst = p.tt_logits + (size_t)b * T * T;
       for (int idx = threadIdx.x - 64; idx < T * T; idx += 128) { const int i = idx / T, j = idx - i * T; dst[idx] = Lb[i * ldl + j]; }
@@ -460,7 +489,8 @@ int sparc_prep_launch(const void* v, const void* l, const uint8_t* mask, int B, 
 
 int sparc_fwd_tc_launch(const void* v, const void* l, const uint8_t* mask, int B, int P, int T, int D, float thr,
                         float scale, float* row_inv_norm, float* pooled_v, float* pooled_l, float* lse_row,
-                        float* lse_col, float* local_partial, float* tt_logits, float* g_inv_norm, cudaStream_t st) {
+                        float* lse_col, float* local_partial, float* tt_logits, float* g_inv_norm, void* g_split,
+                        float* q_save, cudaStream_t st) {
   float* inv_vn = row_inv_norm;
   float* inv_ln = row_inv_norm + (size_t)B * P;
   int rc = sparc_prep_launch(v, l, mask, B, P, T, D, inv_vn, inv_ln, pooled_v, pooled_l, st);
@@ -470,7 +500,8 @@ int sparc_fwd_tc_launch(const void* v, const void* l, const uint8_t* mask, int B
   CUtensorMap tmV, tmL;
   if ((rc = make_tmap_bf16_3d(&tmV, v, D, P, B, 64, L.NP)) != CFA_OK) return rc;
   if ((rc = make_tmap_bf16_3d(&tmL, l, D, T, B, 64, L.NT)) != CFA_OK) return rc;
-  TcFwdParams prm{P, T, D, NS, thr, scale, mask, inv_vn, inv_ln, lse_row, lse_col, local_partial, tt_logits, g_inv_norm};
+  TcFwdParams prm{P, T, D, NS, thr, scale, mask, inv_vn, inv_ln, lse_row, lse_col, local_partial, tt_logits, g_inv_norm,
+                  (bf16*)g_split, q_save};
   const size_t smem = L.total + 1024;
   if (L.NP == 208) {
     CFA_CUDA_TRY(cudaFuncSetAttribute(sparc_fwd_tc_kernel<13>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1221,14 +1252,15 @@ extern "C" int cfa_sparc_bwd_path(int P, int T, int D, int dtype, int path) {
 extern "C" int cfa_sparc_fwd(const void* v, const void* l, const uint8_t* mask, int B, int P, int T, int D, int dtype,
                              float thr, float scale, float* row_inv_norm, float* pooled_v, float* pooled_l,
                              float* lse_row, float* lse_col, float* local_partial, float* tt_logits, float* g_inv_norm,
-                             int path, void* stream) {
+                             void* g_split, float* q_save, int path, void* stream) {
   if (B <= 0 || P <= 0 || T <= 0 || D <= 0 || !v || !l || !mask) return CFA_ERR_BAD_ARG;
   const int which = cfa_sparc_path(P, T, D, dtype, path);
   if (which < 0) return which;
   if (which == 2) {
     if (!row_inv_norm) return CFA_ERR_WORKSPACE;
+    if ((g_split == nullptr) != (q_save == nullptr)) return CFA_ERR_BAD_ARG;
     return sparc_fwd_tc_launch(v, l, mask, B, P, T, D, thr, scale, row_inv_norm, pooled_v, pooled_l, lse_row, lse_col,
-                               local_partial, tt_logits, g_inv_norm, (cudaStream_t)stream);
+                               local_partial, tt_logits, g_inv_norm, g_split, q_save, (cudaStream_t)stream);
   }
   return sparc_fwd_simt(v, l, mask, B, P, T, D, dtype, thr, scale, pooled_v, pooled_l, lse_row, lse_col, local_partial,
                         stream);
@@ -1236,13 +1268,18 @@ extern "C" int cfa_sparc_fwd(const void* v, const void* l, const uint8_t* mask, 
 
 extern "C" int cfa_sparc_bwd(const void* v, const void* l, const uint8_t* mask, int B, int P, int T, int D, int dtype,
                              float thr, float scale, const float* row_inv_norm, const float* lse_row,
-                             const float* lse_col, const float* tt_logits, const float* g_inv_norm, const float* coef,
-                             const float* dpooled_v, const float* dpooled_l, void* dv, void* dl, int path, void* stream) {
+                             const float* lse_col, const float* tt_logits, const float* g_inv_norm,
+                             const void* g_split, const float* q_save, const float* coef, const float* dpooled_v,
+                             const float* dpooled_l, void* dv, void* dl, int path, void* stream) {
   if (B <= 0 || P <= 0 || T <= 0 || D <= 0 || !v || !l || !mask || !coef || !dv || !dl) return CFA_ERR_BAD_ARG;
   const int which = cfa_sparc_bwd_path(P, T, D, dtype, path);
   if (which < 0) return which;
   if (which == 2) {
     if (!row_inv_norm || !tt_logits || !g_inv_norm) return CFA_ERR_WORKSPACE;
+    if (g_split && q_save && sparc_bwd2_supported(P, T, D, dtype))      // streaming backward on the saved G / Q
+      return sparc_bwd2_launch(v, l, mask, B, P, T, D, thr, scale, row_inv_norm, lse_row, lse_col, coef, tt_logits,
+                               g_inv_norm, g_split, q_save, dpooled_v, dpooled_l, dv, dl, g_prof_buffer,
+                               (cudaStream_t)stream);
     return sparc_bwd_tc_launch(v, l, mask, B, P, T, D, thr, scale, row_inv_norm, lse_row, lse_col, coef, tt_logits,
                                g_inv_norm, dpooled_v, dpooled_l, dv, dl, (cudaStream_t)stream);
   }

@@ -151,20 +151,26 @@ class _SparcFunction(torch.autograd.Function):
         # ONE fp32 allocation, carved by pointer arithmetic (host time matters at ~0.5 ms per step):
         # pooled [2,B,D] | out8 | lse_row [B,T] | lse_col [B,T] | local_partial [B,2] | row_inv_norm [B(P+T)] |
         # tt_logits [B,T,T] | g_inv_norm [B,T]
-        sizes = (2 * B * D, 8, B * T, B * T, 2 * B, B * (P + T), B * T * T, B * T)
-        blk = torch.empty(sum(sizes), dtype=torch.float32, device=dev)
-        base = blk.data_ptr()
+        # | g_split [B,2,T,D] bf16 | q_save [B,T,NP]   (every piece starts 128-byte aligned: TMA / float4 access)
+        NP = (P + 15) & ~15
+        saved = code == _lib.DTYPE_CODE[torch.bfloat16] and path != 1
+        sizes = (2 * B * D, 8, B * T, B * T, 2 * B, B * (P + T), B * T * T, B * T,
+                 B * T * D if saved else 0, B * T * NP if saved else 0)
         off = [0]
         for n in sizes:
-            off.append(off[-1] + n)
+            off.append(off[-1] + ((n + 31) & ~31))
+        blk = torch.empty(off[-1], dtype=torch.float32, device=dev)
+        base = blk.data_ptr()
         ptr = [base + 4 * o for o in off]
+        gq = (ptr[8], ptr[9]) if saved else (0, 0)
         pooled = blk[:2 * B * D].view(2, B, D)
         out8 = blk[off[1]:off[2]]
         part_t = blk[off[4]:off[5]]
         same_dev = torch.cuda.current_device() == dev.index
         with (contextlib.nullcontext() if same_dev else torch.cuda.device(dev)):
             _lib.call("cfa_sparc_fwd", v.data_ptr(), l.data_ptr(), mask_u8.data_ptr(), B, P, T, D, code, thr, scale,
-                      ptr[5], ptr[0], ptr[0] + 4 * B * D, ptr[2], ptr[3], ptr[4], ptr[6], ptr[7], path, _lib.stream_ptr())
+                      ptr[5], ptr[0], ptr[0] + 4 * B * D, ptr[2], ptr[3], ptr[4], ptr[6], ptr[7], gq[0], gq[1], path,
+                      _lib.stream_ptr())
             world, rank, group = _dist_ctx(group, gather)
             gpath = 1 if (v.dtype == torch.float32 or path == 1) else 0      # fp32 inputs keep the fp32-exact global kernels
             gst, sums = _global_forward(pooled, scale, _NORM_EPS, world, rank, group,
@@ -174,13 +180,13 @@ class _SparcFunction(torch.autograd.Function):
                           _lib.stream_ptr())
         ctx.save_for_backward(v, l, mask_u8, blk)
         ctx.gst = gst
-        ctx.hp = (thr, gw, lw, scale, code, path, ptr)
+        ctx.hp = (thr, gw, lw, scale, code, path, ptr, gq)
         return out8[:7].clone()
 
     @staticmethod
     def backward(ctx, grad7):
         v, l, mask_u8, blk = ctx.saved_tensors
-        thr, gw, lw, scale, code, path, ptr = ctx.hp
+        thr, gw, lw, scale, code, path, ptr, gq = ctx.hp
         gst = ctx.gst
         B, P, D = v.shape
         T = l.shape[1]
@@ -195,7 +201,7 @@ class _SparcFunction(torch.autograd.Function):
             dv = torch.empty_like(v)
             dl = torch.empty_like(l)
             _lib.call("cfa_sparc_bwd", v.data_ptr(), l.data_ptr(), mask_u8.data_ptr(), B, P, T, D, code, thr, scale,
-                      ptr[5], ptr[2], ptr[3], ptr[6], ptr[7], coef.data_ptr() + 8, dpv.data_ptr(), dpl.data_ptr(),
+                      ptr[5], ptr[2], ptr[3], ptr[6], ptr[7], gq[0], gq[1], coef.data_ptr() + 8, dpv.data_ptr(), dpl.data_ptr(),
                       dv.data_ptr(), dl.data_ptr(), path, _lib.stream_ptr())
         return dv, dl, None, None, None, None, None, None, None, None
 

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define CFA_ABI_VERSION 1
+#define CFA_ABI_VERSION 2
 
 #define CFA_DTYPE_F32 0
 #define CFA_DTYPE_BF16 1
@@ -122,7 +122,8 @@ int cfa_global_infonce_path(int B, int Bg, int D, int path);
  * ---------------------------------------------------------------------------------------------- */
 int cfa_sparc_fwd(const void* v, const void* l, const uint8_t* mask, int B, int P, int T, int D, int dtype,
                   float thr, float scale, float* row_inv_norm, float* pooled_v, float* pooled_l, float* lse_row,
-                  float* lse_col, float* local_partial, float* tt_logits, float* g_inv_norm, int path, void* stream);
+                  float* lse_col, float* local_partial, float* tt_logits, float* g_inv_norm, void* g_split,
+                  float* q_save, int path, void* stream);
 
 /*
  * Backward of the above.  coef: DEVICE pointer to 2 floats = upstream coefficient of loss_vl_local and
@@ -132,14 +133,18 @@ int cfa_sparc_fwd(const void* v, const void* l, const uint8_t* mask, int B, int 
  * Saved between forward and backward (written by cfa_sparc_fwd, read by cfa_sparc_bwd; the CUDA-core path
  * ignores them): row_inv_norm [B*(P+T)] = 1/max(|v_p|,eps) then 1/max(|l_t|,eps); tt_logits [B*T*T] = the masked,
  * scaled token x token logits (fp32, 24 KB per sample — NOT the T x P similarity, which never leaves the SM);
- * g_inv_norm [B*T] = 1/max(|G_t|,eps).
+ * g_inv_norm [B*T] = 1/max(|G_t|,eps); g_split [B][2][T][D] bf16 = the grouped embeddings G as bf16 hi | lo (16-byte
+ * aligned, read back through TMA); q_save [B][T][NP] fp32 with NP = (P+15)&~15 = Q = G . v^T (16-byte aligned).
+ * g_split / q_save are optional (both NULL or both set): with them the tensor-core backward runs as pure
+ * TMA -> tcgen05 streams (sparc_tc_bwd2.cu), without them it recomputes G per D-block (sparc_tc.cu).
  * path: 0 = auto, 1 = fp32-exact CUDA-core kernels, 2 = tcgen05 tensor-core kernels (bf16, D % 256 == 0,
  * P <= 256, T <= 128; CFA_ERR_UNSUPPORTED otherwise).  cfa_sparc_path reports what `auto` resolves to.
  */
 int cfa_sparc_bwd(const void* v, const void* l, const uint8_t* mask, int B, int P, int T, int D, int dtype,
                   float thr, float scale, const float* row_inv_norm, const float* lse_row, const float* lse_col,
-                  const float* tt_logits, const float* g_inv_norm, const float* coef, const float* dpooled_v,
-                  const float* dpooled_l, void* dv, void* dl, int path, void* stream);
+                  const float* tt_logits, const float* g_inv_norm, const void* g_split, const float* q_save,
+                  const float* coef, const float* dpooled_v, const float* dpooled_l, void* dv, void* dl, int path,
+                  void* stream);
 int cfa_sparc_path(int P, int T, int D, int dtype, int path);
 int cfa_sparc_bwd_path(int P, int T, int D, int dtype, int path);   /* backward: tensor cores need P <= ~224 at T = 77 */
 
