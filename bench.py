@@ -325,7 +325,7 @@ def main():
         step(i)
     sync_all()
     sampler = ClockSampler(local_rank) if rank == 0 else None
-    _lib.kernel_events = {"cfa_sparc_bwd": [], "cfa_sparc_fwd": []}
+    _lib.kernel_events = {name: [] for name in _lib.LAUNCHES if name != "cfa_adamspd_step"}
     l0 = _lib.launch_count
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -415,7 +415,7 @@ def main():
                    "global_batch": Bg, "l2": f"inputs rotated over {nbuf} sets ({nbuf * in_bytes >> 20} MiB > 2x L2)",
                    "algorithmic_flops_per_pair": flops_per_pair(Bg),
                    "algorithmic_tflops": round(value * flops_per_pair(Bg) / 1e12, 2),
-                   "kernel_ms": {"cfa_sparc_fwd": round(fwd_ms, 4), "cfa_sparc_bwd": round(bwd_ms, 4)}},
+                   "kernel_ms": {k: round(statistics.mean(a.elapsed_time(b) for a, b in ev), 4) for k, ev in kev.items() if ev}},
         "roofline": {"bound": "tensor", "kernel": "cfa_sparc_bwd", "achieved": round(ach, 2), "peak": pk["tf_sus"],
                      "unit": "TFLOP/s", "frac": round(ach / pk["tf_sus"], 5),
                      "traffic": 105.8e6 if (B == 256 and args.dtype == "bf16") else None,

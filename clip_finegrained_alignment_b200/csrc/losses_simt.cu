@@ -531,9 +531,33 @@ __global__ void sparc_coef_kernel(const float* grad7, float gw, float lw, int gl
   coef8[4] = clv; coef8[5] = cvl; coef8[6] = 0.f; coef8[7] = 0.f;
 }
 
+struct Grad7Ptrs { const float* g[7]; };
+
+// same as sparc_coef_kernel, the 7 upstream gradients arriving as separate 0-dim tensors (NULL = not used)
+__global__ void sparc_coef_ptrs_kernel(Grad7Ptrs gp, float gw, float lw, int global_batch, const float* out8, float* coef8) {
+  float u[7];
+  for (int k = 0; k < 7; ++k) u[k] = gp.g[k] ? *gp.g[k] : 0.f;
+  const float gl = 0.5f * (u[0] + gw * u[2]);
+  const float lo = 0.5f * (u[1] + lw * u[2]);
+  const float cvl = (u[3] + gl) / (float)global_batch, clv = (u[4] + gl) / (float)global_batch;
+  coef8[0] = cvl; coef8[1] = clv;
+  coef8[2] = (u[5] + lo) / out8[7];
+  coef8[3] = (u[6] + lo) / out8[7];
+  coef8[4] = clv; coef8[5] = cvl; coef8[6] = 0.f; coef8[7] = 0.f;
+}
+
 }  // namespace cfa
 
 using namespace cfa;
+
+extern "C" int cfa_sparc_coef_ptrs(const float* g_global, const float* g_local, const float* g_total, const float* g_vl,
+                                   const float* g_lv, const float* g_vl_local, const float* g_lv_local, float gw, float lw,
+                                   int global_batch, const float* out8, float* coef8, void* stream) {
+  if (!out8 || !coef8 || global_batch <= 0) return CFA_ERR_BAD_ARG;
+  Grad7Ptrs gp{{g_global, g_local, g_total, g_vl, g_lv, g_vl_local, g_lv_local}};
+  sparc_coef_ptrs_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(gp, gw, lw, global_batch, out8, coef8);
+  return launch_status();
+}
 
 extern "C" int cfa_sparc_max_patches(int T, int backward) {
   int best = 0;

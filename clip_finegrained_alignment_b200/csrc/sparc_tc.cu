@@ -1259,6 +1259,9 @@ extern "C" int cfa_sparc_fwd(const void* v, const void* l, const uint8_t* mask, 
   if (which == 2) {
     if (!row_inv_norm) return CFA_ERR_WORKSPACE;
     if ((g_split == nullptr) != (q_save == nullptr)) return CFA_ERR_BAD_ARG;
+    if (sparc_fwd2_supported(P, T, D, dtype))          // one kernel: norms / pooled means fused into the streaming pass
+      return sparc_fwd2_launch(v, l, mask, B, P, T, D, thr, scale, row_inv_norm, pooled_v, pooled_l, lse_row, lse_col,
+                               local_partial, tt_logits, g_inv_norm, g_split, q_save, (cudaStream_t)stream);
     return sparc_fwd_tc_launch(v, l, mask, B, P, T, D, thr, scale, row_inv_norm, pooled_v, pooled_l, lse_row, lse_col,
                                local_partial, tt_logits, g_inv_norm, g_split, q_save, (cudaStream_t)stream);
   }

@@ -87,19 +87,7 @@ struct Bwd2Params {
   bf16* dl;
 };
 
-__device__ __forceinline__ void b2_split8(const float* x, uint4& hi, uint4& lo) {
-  uint32_t h[4], l[4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const bf16 h0 = __float2bfloat16_rn(x[2 * i]), h1 = __float2bfloat16_rn(x[2 * i + 1]);
-    const bf16 l0 = __float2bfloat16_rn(x[2 * i] - __bfloat162float(h0));
-    const bf16 l1 = __float2bfloat16_rn(x[2 * i + 1] - __bfloat162float(h1));
-    h[i] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-    l[i] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
-  }
-  hi = make_uint4(h[0], h[1], h[2], h[3]);
-  lo = make_uint4(l[0], l[1], l[2], l[3]);
-}
+__device__ __forceinline__ void b2_split8(const float* x, uint4& hi, uint4& lo) { split_hilo8(x, hi, lo); }
 __device__ __forceinline__ void b2_unpack8(const uint4& u, float* f) {
   const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
@@ -111,9 +99,10 @@ __device__ __forceinline__ void b2_unpack8(const uint4& u, float* f) {
 __device__ __forceinline__ uint4 b2_pack8(const float* f) {
   uint32_t w[4];
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
-    w[i] = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(f[2 * i])) |
-           ((uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(f[2 * i + 1])) << 16);
+  for (int i = 0; i < 4; ++i) {
+    const __nv_bfloat162 t = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+    w[i] = *reinterpret_cast<const uint32_t*>(&t);
+  }
   return make_uint4(w[0], w[1], w[2], w[3]);
 }
 __device__ __forceinline__ void b2_epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
@@ -154,8 +143,8 @@ template <int kNksP, int kNksT>
 __global__ void __launch_bounds__(kB2Threads, 1)
 sparc_bwd2_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmL,
                   const __grid_constant__ CUtensorMap tmG, const Bwd2Params p) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* base = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* base = CFA_SMEM_BASE_1024(smem_raw);
   const Bwd2Layout L = bwd2_layout(p.P, p.T, p.D);
   const int NP = L.NP, NT = L.NT, KB = L.KB, P = p.P, T = p.T, D = p.D;
   const int b = blockIdx.x;
@@ -288,7 +277,8 @@ sparc_bwd2_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_constant
     mbar_wait(e1_ready, 0);
     tc_fence_after();
     stamp();
-    _Pragma("unroll") for (int ks = 0; ks < nksT; ++ks) umma_ss_w(leader, tmem + kB2cS, k_dlhi + ks * ks_k, m_srhi + ks * ks_m, id_dwa, ks != 0);
+    // (E1 left -gfac Q in the cS columns: every MMA accumulates, so cS ends up holding dW = dLhat . S_raw - gfac Q)
+    _Pragma("unroll") for (int ks = 0; ks < nksT; ++ks) umma_ss_w(leader, tmem + kB2cS, k_dlhi + ks * ks_k, m_srhi + ks * ks_m, id_dwa, true);
     _Pragma("unroll") for (int ks = 0; ks < nksT; ++ks) umma_ss_w(leader, tmem + kB2cS, k_dlhi + ks * ks_k, m_srlo + ks * ks_m, id_dwa, true);
     _Pragma("unroll") for (int ks = 0; ks < nksT; ++ks) umma_ss_w(leader, tmem + kB2cS, k_dllo + ks * ks_k, m_srhi + ks * ks_m, id_dwa, true);
     _Pragma("unroll") for (int ks = 0; ks < nksT; ++ks) umma_ss_w(leader, tmem + kB2cZ, m_dlhi + ks * ks_m, m_whi + ks * ks_m, id_z, ks != 0);
@@ -459,30 +449,57 @@ sparc_bwd2_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_constant
     if (inT) sum += xot0[0];
     const float sigma = fmaxf(sum, kB2ClampEps);
     const float inv_sigma = valid ? 1.f / sigma : 0.f;
-    for (int c0 = c_lo; c0 < c_hi; c0 += 16) {
-      float x[16], w[16];
-      tmem_ld16(trow + kB2cS + c0, x);
-      tmem_ld_wait();
+    // sweep 3 also parks -gfac Q in the S columns it has just consumed: the dWa MMAs then accumulate on top of it,
+    // so the backward never touches Q again (its L2 latency hides behind the two hi/lo splits of the previous chunk)
+    const float gfac = inT ? gfacs[row] : 0.f;          // visible: written before the barriers above
+    const float* qrow = p.q_save + ((size_t)b * T + (row < T ? row : 0)) * NP;
+    auto load_q16 = [&](int c, float* qv) {
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const float nn = (x[j] * il * ivn[c0 + j] - mn) * inv_rng;
-        const bool in = valid && c0 + j < P;
-        w[j] = (in && !(nn < p.thr)) ? nn * inv_sigma : 0.f;
-        x[j] = in ? x[j] : 0.f;
+      for (int g4 = 0; g4 < 4; ++g4) {
+        const float4 t4 = __ldg(reinterpret_cast<const float4*>(qrow + c) + g4);
+        qv[4 * g4] = t4.x; qv[4 * g4 + 1] = t4.y; qv[4 * g4 + 2] = t4.z; qv[4 * g4 + 3] = t4.w;
       }
-      if (inT) {
+    };
+    {
+      float qc[16], qn[16];
+      if (c_lo < c_hi) load_q16(c_lo, qc);
+      for (int c0 = c_lo; c0 < c_hi; c0 += 16) {
+        float x[16], w[16];
+        tmem_ld16(trow + kB2cS + c0, x);
+        if (c0 + 16 < c_hi) load_q16(c0 + 16, qn);
+        tmem_ld_wait();
 #pragma unroll
-        for (int g8 = 0; g8 < 2; ++g8) {
-          const uint32_t off = il_offset(NT, row, c0 + 8 * g8);
-          uint4 hi, lo;
-          b2_split8(w + 8 * g8, hi, lo);
-          *reinterpret_cast<uint4*>(Whi + off) = hi;
-          *reinterpret_cast<uint4*>(Wlo + off) = lo;
-          b2_split8(x + 8 * g8, hi, lo);
-          *reinterpret_cast<uint4*>(SRhi + off) = hi;
-          *reinterpret_cast<uint4*>(SRlo + off) = lo;
+        for (int j4 = 0; j4 < 4; ++j4) {
+          const float4 iv = *reinterpret_cast<const float4*>(ivn + c0 + 4 * j4);
+          const float ivv[4] = {iv.x, iv.y, iv.z, iv.w};
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj) {
+            const int j = 4 * j4 + jj;
+            const float nn = (x[j] * il * ivv[jj] - mn) * inv_rng;
+            const bool in = valid && c0 + j < P;
+            w[j] = (in && !(nn < p.thr)) ? nn * inv_sigma : 0.f;
+            x[j] = in ? x[j] : 0.f;
+            qc[j] = valid ? -gfac * qc[j] : 0.f;
+          }
         }
+        if (inT) {
+#pragma unroll
+          for (int g8 = 0; g8 < 2; ++g8) {
+            const uint32_t off = il_offset(NT, row, c0 + 8 * g8);
+            uint4 hi, lo;
+            b2_split8(w + 8 * g8, hi, lo);
+            *reinterpret_cast<uint4*>(Whi + off) = hi;
+            *reinterpret_cast<uint4*>(Wlo + off) = lo;
+            b2_split8(x + 8 * g8, hi, lo);
+            *reinterpret_cast<uint4*>(SRhi + off) = hi;
+            *reinterpret_cast<uint4*>(SRlo + off) = lo;
+          }
+        }
+        tmem_st16(trow + kB2cS + c0, qc);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) qc[j] = qn[j];
       }
+      tmem_st_wait();
     }
     tc_fence_before();
     fence_proxy_async();
@@ -491,10 +508,8 @@ sparc_bwd2_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_constant
     stamp();
 
     // ---- E3: dW = dWa - gfac Q -> renorm / threshold / min-max backward -> dShat' (hi/lo), Wg (hi/lo), lfac, vfac
-    const float gfac = inT ? gfacs[row] : 0.f;          // visible: written before the set-1 / set-0 barriers above
     const float isg = 1.f / sigma;
     const bool keep_all = p.thr <= 0.f;
-    const float* qrow = p.q_save + ((size_t)b * T + (row < T ? row : 0)) * NP;
     auto load_w16 = [&](int c, float* w) {               // this row's W[c .. c+16) = hi + lo
 #pragma unroll
       for (int g8 = 0; g8 < 2; ++g8) {
@@ -506,26 +521,18 @@ sparc_bwd2_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_constant
         for (int j = 0; j < 8; ++j) w[8 * g8 + j] = hh[j] + ll[j];
       }
     };
-    auto load_q16 = [&](int c, float* qv) {
-#pragma unroll
-      for (int g4 = 0; g4 < 4; ++g4) {
-        const float4 t4 = __ldg(reinterpret_cast<const float4*>(qrow + c) + g4);
-        qv[4 * g4] = t4.x; qv[4 * g4 + 1] = t4.y; qv[4 * g4 + 2] = t4.z; qv[4 * g4 + 3] = t4.w;
-      }
-    };
     mbar_wait(dw_full, 0);
     tc_fence_after();
     stamp();
     float wdot = 0.f, cx = 0.f, nk = 0.f;
     for (int c0 = c_lo; c0 < c_hi; c0 += 16) {
-      float x[16], w[16], qv[16];
+      float x[16], w[16];
       tmem_ld16(trow + kB2cS + c0, x);
-      load_q16(c0, qv);
       load_w16(c0, w);
       tmem_ld_wait();
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
-        const float dw = valid ? fmaf(-gfac, qv[j], x[j]) : 0.f;
+        const float dw = valid ? x[j] : 0.f;
         const bool kept = (keep_all || w[j] > 0.f) && (c0 + j < P) && valid;
         wdot = fmaf(w[j], dw, wdot);                    // W is 0 beyond P and on masked rows
         cx += kept ? dw : 0.f;
@@ -543,17 +550,16 @@ sparc_bwd2_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_constant
     const float dmn = -(cx - nk * wdot) * isg * inv_rng;
     float sdot = 0.f;
     for (int c0 = c_lo; c0 < c_hi; c0 += 16) {
-      float x[16], w[16], qv[16], z[16], pr[16];
+      float x[16], w[16], z[16], pr[16];
       tmem_ld16(trow + kB2cS + c0, x);
       tmem_ld16(trow + kB2cZ + c0, z);
-      load_q16(c0, qv);
       load_w16(c0, w);
       tmem_ld_wait();
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
         const int pc = c0 + j;
         const bool in = valid && pc < P;
-        const float dw = fmaf(-gfac, qv[j], x[j]);
+        const float dw = x[j];
         const bool kept = (keep_all || w[j] > 0.f) && in;
         float ds = kept ? ((dw - wdot) * isg) * inv_rng : 0.f;
         ds += (pc == imn) ? dmn : 0.f;
@@ -600,70 +606,79 @@ sparc_bwd2_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_constant
     const float lfac = inT ? lfacs[row] : 0.f;
     const float vf0 = (row < P) ? vdot[row] : 0.f, vf1 = (128 + row < P) ? vdot[128 + row] : 0.f;
     int o = 0;
-    for (int kb = 0; kb < KB; ++kb, ++o) {               // dl
-      const int buf = o & 1, d0 = kb * 64 + 32 * h;
-      mbar_wait(out_full + buf, (o >> 1) & 1);
-      tc_fence_after();
-      float x[32];
-      tmem_ld32(trow + kB2cDL + 64 * buf + 32 * h, x);
-      tmem_ld_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(out_free + buf);        // the TMEM buffer is free as soon as it is in registers
-      if (row < T) {
-        const bf16* lsrc = p.l + ((size_t)b * T + row) * D + d0;
-        bf16* dst = p.dl + ((size_t)b * T + row) * D + d0;
-        uint4 raw[4];
+    // pooled-mean gradients of this sample -> shared memory (the dLhat region is dead once dWa / Z are done)
+    float* dps = reinterpret_cast<float*>(dLhi);         // [2][D]: dvbar, dlbar
+    for (int i = tid; i < 2 * D; i += 256) {
+      const float* src = (i < D) ? p.dpool_v : p.dpool_l;
+      dps[i] = src ? __ldg(src + (size_t)b * D + (i < D ? i : i - D)) : 0.f;
+    }
+    b2_epi_bar();
+    // raw rows (needed for the - x fac terms) are fetched one block AHEAD of the accumulator they are combined with,
+    // so their L2 latency overlaps the tensor-core work
+    auto load_raw = [&](const bf16* src, uint4* r) {
 #pragma unroll
-        for (int g = 0; g < 4; ++g) raw[g] = __ldg(reinterpret_cast<const uint4*>(lsrc) + g);
+      for (int g = 0; g < 4; ++g) r[g] = __ldg(reinterpret_cast<const uint4*>(src) + g);
+    };
+    auto emit = [&](const float* x, const uint4* rw, const float* dp, float fac, float dscale, bf16* dst) {
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          float lv[8], ov[8];
-          b2_unpack8(raw[g], lv);
+      for (int g = 0; g < 4; ++g) {
+        float rv[8], ov[8];
+        b2_unpack8(rw[g], rv);
+        const float4 d0v = *reinterpret_cast<const float4*>(dp + 8 * g), d1v = *reinterpret_cast<const float4*>(dp + 8 * g + 4);
+        const float dpv[8] = {d0v.x, d0v.y, d0v.z, d0v.w, d1v.x, d1v.y, d1v.z, d1v.w};
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float dp = p.dpool_l ? __ldg(p.dpool_l + (size_t)b * D + d0 + 8 * g + j) : 0.f;
-            ov[j] = fmaf(dp, mrow, fmaf(-lv[j], lfac, x[8 * g + j]));
-          }
-          reinterpret_cast<uint4*>(dst)[g] = b2_pack8(ov);
-        }
+        for (int j = 0; j < 8; ++j) ov[j] = fmaf(dpv[j], dscale, fmaf(-rv[j], fac, x[8 * g + j]));
+        reinterpret_cast<uint4*>(dst)[g] = b2_pack8(ov);
+      }
+    };
+    {
+      uint4 raw[4];
+      const bf16* lrow = p.l + ((size_t)b * T + (row < T ? row : 0)) * D + 32 * h;
+      load_raw(lrow, raw);
+      for (int kb = 0; kb < KB; ++kb, ++o) {               // dl
+        const int buf = o & 1, d0 = kb * 64 + 32 * h;
+        uint4 rawn[4];
+        if (kb + 1 < KB) load_raw(lrow + (kb + 1) * 64, rawn);
+        mbar_wait(out_full + buf, (o >> 1) & 1);
+        tc_fence_after();
+        float x[32];
+        tmem_ld32(trow + kB2cDL + 64 * buf + 32 * h, x);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(out_free + buf);        // the TMEM buffer is free as soon as it is in registers
+        if (row < T) emit(x, raw, dps + D + d0, lfac, mrow, p.dl + ((size_t)b * T + row) * D + d0);
+#pragma unroll
+        for (int g = 0; g < 4; ++g) raw[g] = rawn[g];
       }
     }
     stamp();
-    for (int kb = 0; kb < KB; ++kb, ++o) {               // dv
-      const int buf = o & 1, d0 = kb * 64 + 32 * h;
-      mbar_wait(out_full + buf, (o >> 1) & 1);
-      tc_fence_after();
-      float x0[32], x1[32];
-      tmem_ld32(trow + kB2cDV + 128 * buf + 32 * h, x0);
-      tmem_ld32(trow + kB2cDV + 128 * buf + 64 + 32 * h, x1);
-      tmem_ld_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(out_free + buf);
+    {
+      const int ntile = NP > 128 ? 2 : 1;
+      const bool in0 = row < P, in1 = ntile > 1 && 128 + row < P;
+      const bf16* vrow0 = p.v + ((size_t)b * P + (in0 ? row : 0)) * D + 32 * h;
+      const bf16* vrow1 = p.v + ((size_t)b * P + (in1 ? 128 + row : 0)) * D + 32 * h;
+      uint4 raw0[4], raw1[4];
+      load_raw(vrow0, raw0);
+      load_raw(vrow1, raw1);
+      for (int kb = 0; kb < KB; ++kb, ++o) {               // dv
+        const int buf = o & 1, d0 = kb * 64 + 32 * h;
+        uint4 raw0n[4], raw1n[4];
+        if (kb + 1 < KB) { load_raw(vrow0 + (kb + 1) * 64, raw0n); load_raw(vrow1 + (kb + 1) * 64, raw1n); }
+        mbar_wait(out_full + buf, (o >> 1) & 1);
+        tc_fence_after();
+        float x[32];
+        tmem_ld32(trow + kB2cDV + 128 * buf + 32 * h, x);
+        tmem_ld_wait();
+        if (in0) emit(x, raw0, dps + d0, vf0, invP, p.dv + ((size_t)b * P + row) * D + d0);
+        tmem_ld32(trow + kB2cDV + 128 * buf + 64 + 32 * h, x);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(out_free + buf);
+        if (in1) emit(x, raw1, dps + d0, vf1, invP, p.dv + ((size_t)b * P + 128 + row) * D + d0);
 #pragma unroll
-      for (int m = 0; m < 2; ++m) {
-        const int pr = 128 * m + row;
-        if (pr < P) {
-          const float* x = m ? x1 : x0;
-          const float vf = m ? vf1 : vf0;
-          const bf16* vsrc = p.v + ((size_t)b * P + pr) * D + d0;
-          bf16* dst = p.dv + ((size_t)b * P + pr) * D + d0;
-          uint4 raw[4];
-#pragma unroll
-          for (int g = 0; g < 4; ++g) raw[g] = __ldg(reinterpret_cast<const uint4*>(vsrc) + g);
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            float vv[8], ov[8];
-            b2_unpack8(raw[g], vv);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float dp = p.dpool_v ? __ldg(p.dpool_v + (size_t)b * D + d0 + 8 * g + j) : 0.f;
-              ov[j] = fmaf(dp, invP, fmaf(-vv[j], vf, x[8 * g + j]));
-            }
-            reinterpret_cast<uint4*>(dst)[g] = b2_pack8(ov);
-          }
-        }
+        for (int g = 0; g < 4; ++g) { raw0[g] = raw0n[g]; raw1[g] = raw1n[g]; }
       }
     }
     stamp();

@@ -1,0 +1,523 @@
+// Tensor-core SPARC forward, second generation (tcgen05 / TMEM / TMA) for bf16 embeddings on sm_100a.
+//
+// One CTA per sample: warp 0 = TMA producer, warp 1 = MMA issuer, warps 2..9 = epilogue (two warps per TMEM lane
+// quarter, each owning half of the columns; thread = token row).  Compared with sparc_fwd_tc_kernel:
+//   - no separate prep kernel: while pass 0 streams the raw l / v tiles through shared memory, the epilogue warps
+//     read the same tiles and accumulate the row norms (losses.py:221-222) and the pooled means (losses.py:207-212);
+//   - twice the epilogue warps, shared-space LDS / STS, packed bf16 conversions, 3-deep TMA ring;
+//   - saves G (bf16 hi | lo) and Q = G . v^T for the streaming backward (sparc_tc_bwd2.cu).
+//
+//   pass 0   S[T,P] = sum_kb l_kb . v_kb^T                   (TMEM cS)      + row norms / pooled means from smem
+//   E1       min-max, threshold, renormalise -> W (hi/lo) in smem           (losses.py:228-243)
+//   pass 1   G_kb = W . v_kb (v tile read MN-major)                         (losses.py:245)
+//            epilogue: ||G||^2, G hi/lo -> smem operand + global
+//            L[T,T] += G_kb . l_kb^T ;  Q[T,P] += G_kb . v_kb^T             (losses.py:180)
+//   E3       masked row / column log-sum-exp and CE                         (losses.py:186-196)
+#include "tc_common.cuh"
+#include "sparc_paths.h"
+#include <math_constants.h>
+
+namespace cfa {
+using namespace tc;
+typedef __nv_bfloat16 bf16;
+
+constexpr int kF2Threads = 320;
+constexpr float kF2NormEps = 1e-12f, kF2MinMaxEps = 1e-8f, kF2ClampEps = 1e-8f;
+constexpr uint32_t kF2cS = 0, kF2cG = 256, kF2cL = 384;
+
+struct Fwd2Layout {
+  int NP, NT, KB, NS;
+  uint32_t l_bytes, v_bytes, slot, w_bytes, g_bytes;
+  uint32_t off_w, off_g, off_f, off_x, off_bar, total;
+};
+
+__host__ __device__ inline Fwd2Layout fwd2_layout(int P, int T, int D, int NS) {
+  Fwd2Layout L;
+  L.NP = (P + 15) & ~15; L.NT = (T + 15) & ~15; L.KB = D / 64; L.NS = NS;
+  L.l_bytes = L.NT * 128; L.v_bytes = L.NP * 128; L.slot = L.l_bytes + L.v_bytes;
+  L.w_bytes = (uint32_t)L.NP * L.NT * 2;            // one of hi / lo, interleaved [NP/8][NT][8]
+  L.g_bytes = 64u * L.NT * 2;                       // one of hi / lo of one G_kb operand buffer
+  L.off_w = L.NS * L.slot;
+  const uint32_t lb = (uint32_t)L.NT * (L.NT + 1) * 4;            // fp32 logits scratch aliases the W region
+  L.off_g = L.off_w + (((2 * L.w_bytes > lb ? 2 * L.w_bytes : lb) + 1023) & ~1023u);
+  L.off_f = L.off_g + 4 * L.g_bytes + 2048;         // phantom rows of the last interleaved chunk stay in bounds
+  L.off_x = L.off_f + 4 * ((L.NP + 32) + 3 * L.NT + 32);
+  L.off_bar = (L.off_x + 4 * (2 * 2 * L.NT * 4) + 7) & ~7u;
+  L.total = L.off_bar + 8 * (3 * L.NS + 12) + 16;
+  return L;
+}
+
+struct Fwd2Params {
+  int P, T, D, NS;
+  float thr, scale;
+  const uint8_t* mask;
+  float* inv_vn;        // [B][P]  out
+  float* inv_ln;        // [B][T]  out
+  float* pooled_v;      // [B][D]  out
+  float* pooled_l;      // [B][D]  out
+  float* lse_row;
+  float* lse_col;
+  float* local_partial;
+  float* tt_logits;     // [B][T][T] masked, scaled logits (saved for the backward), may be NULL
+  float* g_inv_norm;    // [B][T]
+  bf16* g_split;        // [B][2][T][D], may be NULL
+  float* q_save;        // [B][T][NP], may be NULL
+};
+
+__device__ __forceinline__ void f2_epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+// Column sums of 16 per-lane values over the 32 lanes of a warp (31 shuffles): every lane gets the sum of v[lane & 15].
+__device__ __forceinline__ float f2_colsum16(float* v, int lane) {
+#pragma unroll
+  for (int k = 0; k < 16; ++k) v[k] += __shfl_xor_sync(0xffffffffu, v[k], 16);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const bool up = lane & 8;
+    const float send = up ? v[k] : v[k + 8], keep = up ? v[k + 8] : v[k];
+    v[k] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const bool up = lane & 4;
+    const float send = up ? v[k] : v[k + 4], keep = up ? v[k + 4] : v[k];
+    v[k] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+  }
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const bool up = lane & 2;
+    const float send = up ? v[k] : v[k + 2], keep = up ? v[k + 2] : v[k];
+    v[k] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+  }
+  {
+    const bool up = lane & 1;
+    const float send = up ? v[0] : v[1], keep = up ? v[1] : v[0];
+    v[0] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
+  }
+  return v[0];
+}
+
+template <int kNksP>
+__global__ void __launch_bounds__(kF2Threads, 1)
+sparc_fwd2_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmL, const Fwd2Params p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* base = CFA_SMEM_BASE_1024(smem_raw);
+  const Fwd2Layout L = fwd2_layout(p.P, p.T, p.D, p.NS);
+  const int NP = L.NP, NT = L.NT, KB = L.KB, NS = L.NS, P = p.P, T = p.T, D = p.D;
+  const int b = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  uint8_t* Whi = base + L.off_w;
+  uint8_t* Wlo = Whi + L.w_bytes;
+  uint8_t* Gs = base + L.off_g;                       // [buf][hi|lo][g_bytes]
+  float* ivn = (float*)(base + L.off_f);              // [NP + 32]: sum of squares, then 1 / max(|v_p|, eps); zero beyond P
+  float* iln = ivn + NP + 32;                         // [NT]
+  float* msk = iln + NT;                              // [NT]
+  float* gnx = msk + NT;                              // [NT] spare
+  float* red = gnx + NT;                              // [32]
+  float* xch = (float*)(base + L.off_x);              // [2][2][NT][4]
+  uint64_t* bars = (uint64_t*)(base + L.off_bar);
+  uint64_t* full = bars;                              // [NS]
+  uint64_t* empty0 = bars + NS;                       // [NS] pass-0 uses: MMA commit + 8 epilogue warps
+  uint64_t* empty1 = bars + 2 * NS;                   // [NS] pass-1 uses: MMA commit
+  uint64_t* bb = bars + 3 * NS;
+  uint64_t* s_full = bb + 0;
+  uint64_t* w_ready = bb + 1;
+  uint64_t* g_full = bb + 2;                          // [2]
+  uint64_t* g_free = bb + 4;                          // [2]
+  uint64_t* gs_ready = bb + 6;                        // [2]
+  uint64_t* gs_free = bb + 8;                         // [2]
+  uint64_t* l_full = bb + 10;
+  uint32_t* tmem_slot = (uint32_t*)(bb + 11);
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < NS; ++i) { mbar_init(full + i, 1); mbar_init(empty0 + i, 9); mbar_init(empty1 + i, 1); }
+    mbar_init(s_full, 1); mbar_init(w_ready, 8); mbar_init(l_full, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(g_full + i, 1); mbar_init(g_free + i, 8); mbar_init(gs_ready + i, 8); mbar_init(gs_free + i, 1); }
+    fence_barrier_init();
+    tma_prefetch_desc(&tmV);
+    tma_prefetch_desc(&tmL);
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  for (int i = threadIdx.x; i < NP + 32 + 2 * NT; i += kF2Threads) {
+    if (i < NP + 32 + NT) ivn[i] = 0.f;               // ivn and iln start as sum-of-squares accumulators
+    else { const int t = i - NP - 32 - NT; msk[t] = (t < T && p.mask[(size_t)b * T + t]) ? 1.f : 0.f; }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  // slot use u: 0 .. KB-1 = pass 0, KB .. 2KB-1 = pass 1; slot = u % NS
+  auto first1 = [&](int s) { const int r = KB % NS; return KB + ((s - r) % NS + NS) % NS; };   // first pass-1 use of slot s
+
+  if (warp == 0) {
+    // =============================== TMA producer ===============================
+    if (lane == 0) {
+      for (int u = 0; u < 2 * KB; ++u) {
+        const int s = u % NS, kb = u % KB;
+        if (u >= NS) {                                // wait until the previous use of this slot has been consumed
+          const int pu = u - NS;
+          if (pu < KB) mbar_wait(empty0 + s, (pu / NS) & 1);
+          else mbar_wait(empty1 + s, ((pu - first1(s)) / NS) & 1);
+        }
+        uint8_t* st = base + (size_t)s * L.slot;
+        mbar_expect_tx(full + s, L.slot);
+        tma_load_3d(st, &tmL, full + s, kb * 64, 0, b);
+        tma_load_3d(st + L.l_bytes, &tmV, full + s, kb * 64, 0, b);
+      }
+    }
+  } else if (warp == 1) {
+    // =============================== MMA issuer (warp-uniform control flow, one elected lane issues) ===============================
+    const bool leader = elect_one();
+    const uint32_t idesc_s = make_idesc_bf16(128, NP, false, false);
+    const uint32_t idesc_g = make_idesc_bf16(128, 64, false, true);
+    const uint32_t idesc_l = make_idesc_bf16(128, NT, false, false);
+    const uint32_t il_lbo = (uint32_t)NT * 16;
+    const uint64_t sw0 = make_smem_desc(0, 16, 1024, kLayoutSw128);
+    const uint64_t ilk_whi = make_smem_desc(smem_u32(Whi), il_lbo, 128, kLayoutNone);
+    const uint64_t ilk_wlo = make_smem_desc(smem_u32(Wlo), il_lbo, 128, kLayoutNone);
+    const uint32_t ilk_step = (2 * il_lbo) >> 4;
+    // ---- pass 0: S = l . v^T
+    for (int u = 0; u < KB; ++u) {
+      const int s = u % NS;
+      mbar_wait(full + s, (u / NS) & 1);
+      tc_fence_after();
+      const uint32_t sl = smem_u32(base + (size_t)s * L.slot), sv = sl + L.l_bytes;
+      const uint64_t dl0 = sw0 | (sl >> 4), dv0 = sw0 | (sv >> 4);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) umma_ss_w(leader, tmem + kF2cS, dl0 + 2 * k, dv0 + 2 * k, idesc_s, (u | k) != 0);
+      umma_commit_w(leader, empty0 + s);
+    }
+    umma_commit_w(leader, s_full);
+    // ---- pass 1: G_kb = W . v_kb ; L += G_kb . l_kb^T ; Q += G_kb . v_kb^T   (G issued one block ahead)
+    mbar_wait(w_ready, 0);
+    tc_fence_after();
+    const int nks = kNksP ? kNksP : NP / 16;
+    auto issue_g = [&](int kb) {
+      const int u = KB + kb, s = u % NS, buf = kb & 1;
+      mbar_wait(full + s, (u / NS) & 1);
+      mbar_wait(g_free + buf, ((kb >> 1) & 1) ^ 1);
+      tc_fence_after();
+      const uint64_t dv0 = sw0 | ((smem_u32(base + (size_t)s * L.slot) + L.l_bytes) >> 4);
+      const uint32_t d = tmem + kF2cG + 64 * buf;
+      _Pragma("unroll") for (int ks = 0; ks < nks; ++ks) umma_ss_w(leader, d, ilk_whi + ks * ilk_step, dv0 + ks * 128, idesc_g, ks != 0);
+      _Pragma("unroll") for (int ks = 0; ks < nks; ++ks) umma_ss_w(leader, d, ilk_wlo + ks * ilk_step, dv0 + ks * 128, idesc_g, true);
+      umma_commit_w(leader, g_full + buf);
+    };
+    auto issue_l = [&](int kb) {
+      const int u = KB + kb, s = u % NS, buf = kb & 1;
+      mbar_wait(gs_ready + buf, (kb >> 1) & 1);
+      tc_fence_after();
+      const uint32_t sl = smem_u32(base + (size_t)s * L.slot);
+      const uint64_t dl0 = sw0 | (sl >> 4), dv0 = sw0 | ((sl + L.l_bytes) >> 4);
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const uint64_t ga = make_smem_desc(smem_u32(Gs + (size_t)(2 * buf + half) * L.g_bytes), il_lbo, 128, kLayoutNone);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_ss_w(leader, tmem + kF2cL, ga + k * ilk_step, dl0 + 2 * k, idesc_l, (kb | half | k) != 0);
+        if (p.q_save) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_ss_w(leader, tmem + kF2cS, ga + k * ilk_step, dv0 + 2 * k, idesc_s, (kb | half | k) != 0);
+        }
+      }
+      umma_commit_w(leader, gs_free + buf);
+      umma_commit_w(leader, empty1 + s);
+    };
+    issue_g(0);
+    for (int kb = 0; kb < KB; ++kb) {
+      if (kb + 1 < KB) issue_g(kb + 1);
+      issue_l(kb);
+    }
+    umma_commit_w(leader, l_full);
+  } else {
+    // =============================== epilogue: 8 warps, 2 per TMEM lane quarter ===============================
+    const int ew = warp - 2, q = warp & 3, h = ew >> 2;
+    const int row = 32 * q + lane;
+    const uint32_t trow = tmem + ((uint32_t)(32 * q) << 16);
+    const bool inT = row < NT;
+    const int tid = threadIdx.x - 64;
+    float* xme0 = xch + ((0 * 2 + h) * NT + (inT ? row : 0)) * 4;
+    float* xot0 = xch + ((0 * 2 + (1 - h)) * NT + (inT ? row : 0)) * 4;
+    const int xset = 2 * NT * 4;
+    float cnt = 0.f;
+    for (int t = 0; t < T; ++t) cnt += msk[t];
+    const float inv_cnt = 1.f / fmaxf(cnt, kF2ClampEps), invP = 1.f / (float)P;
+
+    // ---- pass 0 side job: row norms and pooled means straight from the TMA tiles.  Warp ew owns the ew-th 16-byte chunk
+    // (8 columns) of every row of the block, lane l the rows l, l+32, ...  (conflict-free under the 128-byte swizzle)
+    for (int u = 0; u < KB; ++u) {
+      const int s = u % NS;
+      mbar_wait(full + s, (u / NS) & 1);
+      const uint8_t* st = base + (size_t)s * L.slot;
+      float acc[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) acc[j] = 0.f;
+      for (int r = lane; r < NP; r += 32) {             // v rows
+        const uint4 raw = *reinterpret_cast<const uint4*>(st + L.l_bytes + r * 128 + ((ew ^ (r & 7)) << 4));
+        const uint32_t w4[4] = {raw.x, raw.y, raw.z, raw.w};
+        float ss = 0.f;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float f0 = __uint_as_float(w4[i] << 16), f1 = __uint_as_float(w4[i] & 0xffff0000u);
+          ss = fmaf(f0, f0, ss); ss = fmaf(f1, f1, ss);
+          acc[2 * i] += f0; acc[2 * i + 1] += f1;
+        }
+        atomicAdd(ivn + r, ss);
+      }
+      for (int r = lane; r < NT; r += 32) {             // l rows (zero beyond T)
+        const uint4 raw = *reinterpret_cast<const uint4*>(st + r * 128 + ((ew ^ (r & 7)) << 4));
+        const uint32_t w4[4] = {raw.x, raw.y, raw.z, raw.w};
+        const float m = msk[r];
+        float ss = 0.f;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float f0 = __uint_as_float(w4[i] << 16), f1 = __uint_as_float(w4[i] & 0xffff0000u);
+          ss = fmaf(f0, f0, ss); ss = fmaf(f1, f1, ss);
+          acc[8 + 2 * i] = fmaf(m, f0, acc[8 + 2 * i]); acc[8 + 2 * i + 1] = fmaf(m, f1, acc[8 + 2 * i + 1]);
+        }
+        atomicAdd(iln + r, ss);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(empty0 + s);           // this warp is done with the tile
+      const float cs = f2_colsum16(acc, lane);
+      const int d = u * 64 + 8 * ew + (lane & 7);
+      if (lane < 8) p.pooled_v[(size_t)b * D + d] = cs * invP;                    // losses.py:207
+      else if (lane < 16) p.pooled_l[(size_t)b * D + d] = cs * inv_cnt;           // losses.py:210-212
+    }
+    f2_epi_bar();                                       // every partial sum of squares has landed
+    for (int i = tid; i < NP + NT; i += 256) {
+      if (i < NP) {
+        const float n = (i < P) ? 1.f / fmaxf(sqrtf(ivn[i]), kF2NormEps) : 0.f;
+        ivn[i] = n;
+        if (i < P) p.inv_vn[(size_t)b * P + i] = n;
+      } else {
+        const int t = i - NP;
+        const float n = (t < T) ? 1.f / fmaxf(sqrtf(iln[t]), kF2NormEps) : 0.f;
+        iln[t] = n;
+        if (t < T) p.inv_ln[(size_t)b * T + t] = n;
+      }
+    }
+    f2_epi_bar();
+    const bool valid = row < T && msk[inT ? row : 0] != 0.f;
+    const float il = inT ? iln[row] : 0.f;
+
+    // ---- E1: S -> W   (column halves; row statistics exchanged through shared memory)
+    const int psplit = ((NP / 16 + 1) / 2) * 16;
+    const int c_lo = h ? psplit : 0, c_hi = h ? NP : psplit;
+    mbar_wait(s_full, 0);
+    tc_fence_after();
+    float mn = CUDART_INF_F, mx = -CUDART_INF_F;
+    for (int c0 = c_lo; c0 < c_hi; c0 += 16) {
+      float x[16];
+      tmem_ld16(trow + kF2cS + c0, x);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const float s = x[j] * il * ivn[c0 + j];
+        const bool in = c0 + j < P;
+        mn = fminf(mn, in ? s : CUDART_INF_F);
+        mx = fmaxf(mx, in ? s : -CUDART_INF_F);
+      }
+    }
+    {
+      float* xme = xme0 + xset;
+      float* xot = xot0 + xset;
+      if (inT) { xme[0] = mn; xme[1] = mx; }
+      f2_epi_bar();
+      if (inT) { mn = fminf(mn, xot[0]); mx = fmaxf(mx, xot[1]); }
+    }
+    const float inv_rng = 1.f / (mx - mn + kF2MinMaxEps);
+    float sum = 0.f;
+    for (int c0 = c_lo; c0 < c_hi; c0 += 16) {
+      float x[16];
+      tmem_ld16(trow + kF2cS + c0, x);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const float nn = (x[j] * il * ivn[c0 + j] - mn) * inv_rng;
+        sum += (c0 + j < P && !(nn < p.thr)) ? nn : 0.f;
+      }
+    }
+    if (inT) xme0[0] = sum;
+    f2_epi_bar();
+    if (inT) sum += xot0[0];
+    const float inv_sigma = valid ? 1.f / fmaxf(sum, kF2ClampEps) : 0.f;
+    for (int c0 = c_lo; c0 < c_hi; c0 += 16) {
+      float x[16];
+      tmem_ld16(trow + kF2cS + c0, x);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const float nn = (x[j] * il * ivn[c0 + j] - mn) * inv_rng;
+        x[j] = (valid && c0 + j < P && !(nn < p.thr)) ? nn * inv_sigma : 0.f;
+      }
+      if (inT) {
+#pragma unroll
+        for (int g8 = 0; g8 < 2; ++g8) {
+          uint4 hi, lo;
+          split_hilo8(x + 8 * g8, hi, lo);
+          const uint32_t off = il_offset(NT, row, c0 + 8 * g8);
+          *reinterpret_cast<uint4*>(Whi + off) = hi;
+          *reinterpret_cast<uint4*>(Wlo + off) = lo;
+        }
+      }
+    }
+    tc_fence_before();
+    fence_proxy_async();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(w_ready);
+
+    // ---- pass 1 epilogue: G_kb -> ||G||^2, bf16 hi/lo A operand (smem) + saved copy (global); 32 of the 64 columns per warp
+    float gn2 = 0.f;
+    for (int kb = 0; kb < KB; ++kb) {
+      const int buf = kb & 1;
+      mbar_wait(g_full + buf, (kb >> 1) & 1);
+      tc_fence_after();
+      float x[32];
+      tmem_ld32(trow + kF2cG + 64 * buf + 32 * h, x);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(g_free + buf);
+      mbar_wait(gs_free + buf, ((kb >> 1) & 1) ^ 1);
+      if (inT) {
+        uint8_t* gh = Gs + (size_t)(2 * buf) * L.g_bytes;
+        uint8_t* gl = gh + L.g_bytes;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          float y[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { y[j] = valid ? x[8 * g + j] : 0.f; gn2 = fmaf(y[j], y[j], gn2); }
+          uint4 hi, lo;
+          split_hilo8(y, hi, lo);
+          const uint32_t off = il_offset(NT, row, 32 * h + 8 * g);
+          *reinterpret_cast<uint4*>(gh + off) = hi;
+          *reinterpret_cast<uint4*>(gl + off) = lo;
+          if (p.g_split && row < T) {
+            bf16* gdst = p.g_split + (((size_t)b * 2) * T + row) * D + kb * 64 + 32 * h + 8 * g;
+            *reinterpret_cast<uint4*>(gdst) = hi;
+            *reinterpret_cast<uint4*>(gdst + (size_t)T * D) = lo;
+          }
+        }
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(gs_ready + buf);
+    }
+    {
+      float* xme = xme0 + xset;
+      float* xot = xot0 + xset;
+      if (inT) xme[0] = gn2;
+      f2_epi_bar();
+      if (inT) gn2 += xot[0];
+    }
+    const float ign = 1.f / fmaxf(sqrtf(gn2), kF2NormEps);
+
+    // ---- E3: masked logits.  Half 0: row pass (LSE in registers, logits -> smem); half 1: Q -> global meanwhile.
+    mbar_wait(l_full, 0);
+    tc_fence_after();
+    float* Lb = reinterpret_cast<float*>(Whi);          // [T][NT+1]  (the W region is free now)
+    const int ldl = NT + 1;
+    float ce = 0.f;
+    if (h == 0) {
+      float rmax = -CUDART_INF_F;
+      const float sc_row = valid ? p.scale * ign : 0.f;
+      for (int c0 = 0; c0 < NT; c0 += 16) {
+        float x[16];
+        tmem_ld16(trow + kF2cL + c0, x);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const int col = c0 + j;
+          const float y = (valid && msk[col] != 0.f) ? x[j] * sc_row * iln[col] : -CUDART_INF_F;   // msk/iln are 0 beyond T
+          if (row < T) Lb[row * ldl + col] = y;
+          rmax = fmaxf(rmax, y);
+        }
+      }
+      if (p.g_inv_norm && row < T) p.g_inv_norm[(size_t)b * T + row] = ign;
+      if (valid) {
+        float s = 0.f;
+        for (int col = 0; col < T; ++col) { const float y = Lb[row * ldl + col]; if (y != -CUDART_INF_F) s += expf(y - rmax); }
+        const float lse = rmax + logf(s);
+        p.lse_row[(size_t)b * T + row] = lse;
+        ce = lse - Lb[row * ldl + row];
+      } else if (row < T) {
+        p.lse_row[(size_t)b * T + row] = 0.f;
+      }
+    } else if (p.q_save) {
+      for (int c0 = 0; c0 < NP; c0 += 16) {             // Q (TMEM columns of the dead S) -> global, row stride NP
+        float x[16];
+        tmem_ld16(trow + kF2cS + c0, x);
+        tmem_ld_wait();
+        if (row < T) {
+          float* qd = p.q_save + ((size_t)b * T + row) * NP + c0;
+#pragma unroll
+          for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(qd + j) = make_float4(x[j], x[j + 1], x[j + 2], x[j + 3]);
+        }
+      }
+    }
+    f2_epi_bar();                                       // logits are in smem
+    if (h == 1) {                                       // column pass: thread `row` owns column `row`
+      if (valid) {
+        float cmax = -CUDART_INF_F;
+        for (int i = 0; i < T; ++i) cmax = fmaxf(cmax, Lb[i * ldl + row]);
+        float s = 0.f;
+        for (int i = 0; i < T; ++i) { const float y = Lb[i * ldl + row]; if (y != -CUDART_INF_F) s += expf(y - cmax); }
+        const float lse = cmax + logf(s);
+        p.lse_col[(size_t)b * T + row] = lse;
+        ce = lse - Lb[row * ldl + row];
+      } else if (row < T) {
+        p.lse_col[(size_t)b * T + row] = 0.f;
+      }
+    } else if (p.tt_logits) {                           // coalesced copy of the T x T logits for the backward
+      float* dst = p.tt_logits + (size_t)b * T * T;
+      for (int idx = (q * 32 + lane); idx < T * T; idx += 128) { const int i = idx / T, j = idx - i * T; dst[idx] = Lb[i * ldl + j]; }
+    }
+    ce = warp_sum(ce);
+    if (lane == 0) red[ew] = ce;                        // warps 0..3 (half 0): row direction, 4..7: column direction
+    f2_epi_bar();
+    if (tid == 0) {
+      p.local_partial[2 * b] = red[0] + red[1] + red[2] + red[3];
+      p.local_partial[2 * b + 1] = red[4] + red[5] + red[6] + red[7];
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem, 512); }
+}
+
+static int fwd2_pick_stages(int P, int T, int D) {
+  for (int ns = 4; ns >= 2; --ns)
+    if (fwd2_layout(P, T, D, ns).total + 1024 <= 227 * 1024) return ns;
+  return 0;
+}
+
+bool sparc_fwd2_supported(int P, int T, int D, int dtype) {
+  if (!sparc_tc_supported(P, T, D, dtype)) return false;
+  return fwd2_pick_stages(P, T, D) != 0;
+}
+
+int sparc_fwd2_launch(const void* v, const void* l, const uint8_t* mask, int B, int P, int T, int D, float thr,
+                      float scale, float* row_inv_norm, float* pooled_v, float* pooled_l, float* lse_row, float* lse_col,
+                      float* local_partial, float* tt_logits, float* g_inv_norm, void* g_split, float* q_save,
+                      cudaStream_t st) {
+  const int NS = fwd2_pick_stages(P, T, D);
+  if (NS == 0) return CFA_ERR_UNSUPPORTED;
+  const Fwd2Layout L = fwd2_layout(P, T, D, NS);
+  CUtensorMap tmV, tmL;
+  int rc;
+  if ((rc = make_tmap_bf16_3d(&tmV, v, D, P, B, 64, L.NP)) != CFA_OK) return rc;
+  if ((rc = make_tmap_bf16_3d(&tmL, l, D, T, B, 64, L.NT)) != CFA_OK) return rc;
+  Fwd2Params prm{P, T, D, NS, thr, scale, mask, row_inv_norm, row_inv_norm + (size_t)B * P, pooled_v, pooled_l, lse_row,
+                 lse_col, local_partial, tt_logits, g_inv_norm, (bf16*)g_split, q_save};
+  const size_t smem = L.total + 1024;
+  if (L.NP == 208) {
+    CFA_CUDA_TRY(cudaFuncSetAttribute(sparc_fwd2_kernel<13>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    sparc_fwd2_kernel<13><<<B, kF2Threads, smem, st>>>(tmV, tmL, prm);
+  } else {
+    CFA_CUDA_TRY(cudaFuncSetAttribute(sparc_fwd2_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    sparc_fwd2_kernel<0><<<B, kF2Threads, smem, st>>>(tmV, tmL, prm);
+  }
+  return launch_status();
+}
+
+}  // namespace cfa

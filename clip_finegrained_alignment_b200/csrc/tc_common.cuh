@@ -90,6 +90,35 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* r) {
                : "r"(taddr) : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// registers -> TMEM: thread i of the warp writes 16 consecutive fp32 columns of TMEM lane (lane_base + i)
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float* r) {
+  const uint32_t* u = reinterpret_cast<const uint32_t*>(r);
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+               ::"r"(taddr), "r"(u[0]), "r"(u[1]), "r"(u[2]), "r"(u[3]), "r"(u[4]), "r"(u[5]), "r"(u[6]), "r"(u[7]),
+                 "r"(u[8]), "r"(u[9]), "r"(u[10]), "r"(u[11]), "r"(u[12]), "r"(u[13]), "r"(u[14]), "r"(u[15])
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// dynamic shared memory base rounded up to 1024 B (SWIZZLE_128B tiles) WITHOUT leaving the shared address space:
+// pointer arithmetic on the __shared__ array keeps LDS / STS (a uintptr_t round trip degrades them to generic LD / ST)
+#define CFA_SMEM_BASE_1024(arr) ((arr) + ((1024u - (cfa::tc::smem_u32(arr) & 1023u)) & 1023u))
+
+// 8 floats -> bf16 hi (x ~ hi + lo) and lo parts, packed conversions (F2FP.BF16.F32.PACK_AB)
+__device__ __forceinline__ void split_hilo8(const float* x, uint4& hi, uint4& lo) {
+  uint32_t h[4], l[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const __nv_bfloat162 hh = __floats2bfloat162_rn(x[2 * i], x[2 * i + 1]);
+    const uint32_t hb = *reinterpret_cast<const uint32_t*>(&hh);
+    const __nv_bfloat162 ll = __floats2bfloat162_rn(x[2 * i] - __uint_as_float(hb << 16),
+                                                    x[2 * i + 1] - __uint_as_float(hb & 0xffff0000u));
+    h[i] = hb;
+    l[i] = *reinterpret_cast<const uint32_t*>(&ll);
+  }
+  hi = make_uint4(h[0], h[1], h[2], h[3]);
+  lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
 
 // ---------------------------------------------------------------- UMMA descriptors
 constexpr uint32_t kLayoutNone = 0, kLayoutSw128 = 2, kLayoutSw64 = 4;

@@ -131,8 +131,9 @@ def _global_backward(st: _GlobalState, coef2: torch.Tensor):
 # SPARC
 # ----------------------------------------------------------------------------------------------
 class _SparcFunction(torch.autograd.Function):
-    """Returns one [7] vector (SPARC_KEYS order); the module hands out its elements, so autograd delivers
-    a single [7] gradient vector to backward — no host synchronisation anywhere."""
+    """Returns the 7 losses (SPARC_KEYS order) as separate 0-dim outputs of ONE autograd node; backward receives
+    the 7 upstream gradients (None for unused outputs) and hands their device pointers to the coefficient kernel —
+    no host synchronisation, zero-fill or concatenation anywhere."""
 
     @staticmethod
     def forward(ctx, v, l, mask, thr, gw, lw, scale, gather, group, path):
@@ -181,22 +182,31 @@ class _SparcFunction(torch.autograd.Function):
         ctx.save_for_backward(v, l, mask_u8, blk)
         ctx.gst = gst
         ctx.hp = (thr, gw, lw, scale, code, path, ptr, gq)
-        return out8[:7].clone()
+        ctx.set_materialize_grads(False)               # unused outputs arrive as None: no zero-fill launches
+        return out8[:7].clone().unbind(0)
 
     @staticmethod
-    def backward(ctx, grad7):
+    def backward(ctx, *grads):
         v, l, mask_u8, blk = ctx.saved_tensors
         thr, gw, lw, scale, code, path, ptr, gq = ctx.hp
         gst = ctx.gst
         B, P, D = v.shape
         T = l.shape[1]
         dev = v.device
-        if grad7.dtype != torch.float32 or not grad7.is_contiguous():
-            grad7 = grad7.to(torch.float32).contiguous()
+        gptr = []
+        keep = []
+        for gk in grads:
+            if gk is None:
+                gptr.append(0)
+                continue
+            if gk.dtype != torch.float32 or gk.device != dev:
+                gk = gk.to(device=dev, dtype=torch.float32)
+            keep.append(gk)
+            gptr.append(gk.data_ptr())
         same_dev = torch.cuda.current_device() == dev.index
         with (contextlib.nullcontext() if same_dev else torch.cuda.device(dev)):
             coef = torch.empty(8, dtype=torch.float32, device=dev)
-            _lib.call("cfa_sparc_coef", grad7.data_ptr(), gw, lw, gst.Bg, ptr[1], coef.data_ptr(), _lib.stream_ptr())
+            _lib.call("cfa_sparc_coef_ptrs", *gptr, gw, lw, gst.Bg, ptr[1], coef.data_ptr(), _lib.stream_ptr())
             dpv, dpl = _global_backward(gst, coef)
             dv = torch.empty_like(v)
             dl = torch.empty_like(l)
@@ -264,7 +274,7 @@ class SPARCLoss(nn.Module):
         out = _SparcFunction.apply(v_patch_embed, l_token_embed, language_mask, float(self.similarity_threshold),
                                    float(self.global_loss_weight), float(self.local_loss_weight),
                                    float(self.inverse_temperature), self.gather, self.process_group, self.kernel_path)
-        return dict(zip(SPARC_KEYS, out.unbind(0)))        # one autograd node for the 7 views
+        return dict(zip(SPARC_KEYS, out))                  # one autograd node, 7 outputs
 
 
 # ----------------------------------------------------------------------------------------------

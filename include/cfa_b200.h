@@ -169,6 +169,11 @@ int cfa_sparc_finalize(const float* global_sums, int global_batch, const float* 
  */
 int cfa_sparc_coef(const float* grad7, float gw, float lw, int global_batch, const float* out8, float* coef8,
                    void* stream);
+/* same, the upstream gradients given as 7 separate DEVICE scalars in the out[] order (NULL = that output is unused):
+ * what torch.autograd hands a Function with 7 outputs — no zero-fill / concatenation launches on the way in */
+int cfa_sparc_coef_ptrs(const float* g_global, const float* g_local, const float* g_total, const float* g_vl,
+                        const float* g_lv, const float* g_vl_local, const float* g_lv_local, float gw, float lw,
+                        int global_batch, const float* out8, float* coef8, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Validation hook (not a reference replacement): one CTA computes D[128 x N] = A . B on the tcgen05 tensor
