@@ -54,6 +54,7 @@ SIGNATURES = {
     "cfa_sparc_coef": (C.c_int, [_vp, _f, _f, _i, _vp, _vp, _vp]),
     "cfa_sparc_coef_ptrs": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _f, _f, _i, _vp, _vp, _vp]),
     "cfa_debug_set_profile_buffer": (C.c_int, [_vp]),
+    "cfa_debug_set_profile_buffer_fwd": (C.c_int, [_vp]),
     "cfa_debug_set_marker_buffer": (C.c_int, [_vp]),
     "cfa_tc_selftest": (C.c_int, [_i, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "cfa_tc_selftest_timed": (C.c_int, [_i, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _vp]),
@@ -66,7 +67,7 @@ for _name, (_res, _args) in SIGNATURES.items():
 
 
 # kernels launched per C-ABI call (cudaMemsetAsync not counted); bench.py reports the running total
-LAUNCHES = {"cfa_adamspd_step": 2, "cfa_global_infonce_fwd": 4, "cfa_global_infonce_bwd": 2, "cfa_sparc_fwd": 1,
+LAUNCHES = {"cfa_adamspd_step": 2, "cfa_global_infonce_fwd": 2, "cfa_global_infonce_bwd": 2, "cfa_sparc_fwd": 1,
             "cfa_sparc_bwd": 1, "cfa_sparc_finalize": 1, "cfa_sparc_coef": 1, "cfa_sparc_coef_ptrs": 1}
 launch_count = 0
 kernel_events = None       # {abi name: [(start_event, end_event), ...]} while bench.py profiles; else None

@@ -277,7 +277,18 @@ int global_tc_fwd(const float* a_loc, const float* b_loc, const float* a_all, co
 int global_tc_bwd(int B, int Bg, int D, int col_offset, float scale, const float* lse_loc2, const float* lse_all2,
                   const float* coef2, float** dpart, int* nsplit, void* ws, cudaStream_t st);
 
-static bool use_tc(int B, int Bg, int D, int path) { return path != 1 && global_tc_supported(B, Bg, D); }
+// low-latency symmetric CUDA-core implementation for the rank-local case (global_infonce_sym.cu)
+bool global_sym_supported(int B, int Bg, int D);
+size_t global_sym_workspace_bytes(int B, int D);
+int global_sym_fwd(const float* a, const float* b, int B, int D, float scale, float eps, float* norms2, float** part_m,
+                   float** part_l, float** diag, int* nsplit, void* ws, cudaStream_t st);
+int global_sym_bwd(const float* a, const float* b, int B, int D, float scale, float eps, const float* lse2, const float* coef2,
+                   float** dpart, int* nsplit, void* ws, cudaStream_t st);
+
+// path 0 (auto): rank-local problems up to B = 512 -> symmetric fp32 tiles (latency-bound regime, one logits tile serves
+// both directions); otherwise tensor cores when the shape allows; path 1 keeps everything on fp32 CUDA cores.
+static bool use_sym(int B, int Bg, int D, int path) { return path != 2 && global_sym_supported(B, Bg, D); }
+static bool use_tc(int B, int Bg, int D, int path) { return path != 1 && !use_sym(B, Bg, D, path) && global_tc_supported(B, Bg, D); }
 
 }  // namespace cfa
 
@@ -288,13 +299,14 @@ extern "C" size_t cfa_global_infonce_workspace_bytes(int B, int Bg, int D) {
   const size_t bwd = (size_t)2 * gb_splits(B, Bg, D) * B * D * sizeof(float);
   size_t n = fwd > bwd ? fwd : bwd;
   if (global_tc_supported(B, Bg, D)) { const size_t t = global_tc_workspace_bytes(B, Bg, D); if (t > n) n = t; }
+  if (global_sym_supported(B, Bg, D)) { const size_t t = global_sym_workspace_bytes(B, D); if (t > n) n = t; }
   return n;
 }
 
 // path: 0 = auto (tensor cores when D % 64 == 0 and D <= 512), 1 = fp32-exact CUDA cores, 2 = tensor cores
 extern "C" int cfa_global_infonce_path(int B, int Bg, int D, int path) {
   if (path == 2 && !global_tc_supported(B, Bg, D)) return CFA_ERR_UNSUPPORTED;
-  return use_tc(B, Bg, D, path) ? 2 : 1;
+  return use_sym(B, Bg, D, path) ? 3 : (use_tc(B, Bg, D, path) ? 2 : 1);
 }
 
 extern "C" int cfa_global_infonce_fwd(const float* a_loc, const float* b_loc, const float* a_all, const float* b_all, int B,
@@ -306,6 +318,15 @@ extern "C" int cfa_global_infonce_fwd(const float* a_loc, const float* b_loc, co
   if (!workspace || workspace_bytes < cfa_global_infonce_workspace_bytes(B, Bg, D)) return CFA_ERR_WORKSPACE;
   if (out8 && (Bg != B || !local_partial || !mask)) return CFA_ERR_BAD_ARG;   // fused scalar epilogue: single process only
   if (path == 2 && !global_tc_supported(B, Bg, D)) return CFA_ERR_UNSUPPORTED;
+  if (use_sym(B, Bg, D, path)) {
+    float *pm, *pl, *dg;
+    int nsp;
+    const int rc = global_sym_fwd(a_loc, b_loc, B, D, scale, eps, norms2, &pm, &pl, &dg, &nsp, workspace, (cudaStream_t)stream);
+    if (rc != CFA_OK) return rc;
+    global_combine_kernel<<<1, kNT, 0, (cudaStream_t)stream>>>(pm, pl, dg, B, nsp, lse2, sums2, Bg, local_partial, mask, T, gw,
+                                                               lw, out8);
+    return launch_status();
+  }
   if (use_tc(B, Bg, D, path)) {
     float *pm, *pl, *dg;
     int nsp;
@@ -342,6 +363,14 @@ extern "C" int cfa_global_infonce_bwd(const float* a_loc, const float* b_loc, co
   if (B <= 0 || Bg <= 0 || D <= 0 || D > 1024 || col_offset < 0 || col_offset + B > Bg) return CFA_ERR_BAD_ARG;
   if (!workspace || workspace_bytes < cfa_global_infonce_workspace_bytes(B, Bg, D)) return CFA_ERR_WORKSPACE;
   if (path == 2 && !global_tc_supported(B, Bg, D)) return CFA_ERR_UNSUPPORTED;
+  if (use_sym(B, Bg, D, path)) {
+    float* dpart;
+    int nsp;
+    const int rc = global_sym_bwd(a_loc, b_loc, B, D, scale, eps, lse_loc2, coef2, &dpart, &nsp, workspace, (cudaStream_t)stream);
+    if (rc != CFA_OK) return rc;
+    global_norm_bwd_kernel<<<dim3(B, 2), 128, 0, (cudaStream_t)stream>>>(a_loc, b_loc, norms2, dpart, nsp, B, D, da, db);
+    return launch_status();
+  }
   if (use_tc(B, Bg, D, path)) {       // needs the SAME workspace the forward call used (normalised hi/lo operands live there)
     float* dpart;
     int nsp;

@@ -24,7 +24,7 @@ bool sparc_fwd2_supported(int P, int T, int D, int dtype);
 int sparc_fwd2_launch(const void* v, const void* l, const uint8_t* mask, int B, int P, int T, int D, float thr,
                       float scale, float* row_inv_norm, float* pooled_v, float* pooled_l, float* lse_row, float* lse_col,
                       float* local_partial, float* tt_logits, float* g_inv_norm, void* g_split, float* q_save,
-                      cudaStream_t st);
+                      long long* prof, cudaStream_t st);
 
 // restructured tcgen05 backward (sparc_tc_bwd2.cu): needs the forward's saved G (bf16 hi|lo) and Q = G . v^T
 bool sparc_bwd2_supported(int P, int T, int D, int dtype);

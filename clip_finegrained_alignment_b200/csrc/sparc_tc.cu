@@ -549,6 +549,7 @@ __host__ __device__ inline TcBwdLayout tc_bwd_layout(int P, int T, int D, int NS
 
 // optional phase timestamps (clock64) for tuning: [B][2][16] long long, set through cfa_debug_set_profile_buffer
 static long long* g_prof_buffer = nullptr;
+static long long* g_prof_fwd = nullptr;     // same for the forward (cfa_debug_set_profile_buffer_fwd)
 
 struct TcBwdParams {
   long long* prof;
@@ -1242,6 +1243,11 @@ extern "C" int cfa_debug_set_profile_buffer(void* device_buffer) {
   return CFA_OK;
 }
 
+extern "C" int cfa_debug_set_profile_buffer_fwd(void* device_buffer) {
+  g_prof_fwd = (long long*)device_buffer;
+  return CFA_OK;
+}
+
 // same for the backward (the tensor-core backward needs more shared memory than the forward)
 extern "C" int cfa_sparc_bwd_path(int P, int T, int D, int dtype, int path) {
   const int which = cfa_sparc_path(P, T, D, dtype, path);
@@ -1261,7 +1267,7 @@ extern "C" int cfa_sparc_fwd(const void* v, const void* l, const uint8_t* mask, 
     if ((g_split == nullptr) != (q_save == nullptr)) return CFA_ERR_BAD_ARG;
     if (sparc_fwd2_supported(P, T, D, dtype))          // one kernel: norms / pooled means fused into the streaming pass
       return sparc_fwd2_launch(v, l, mask, B, P, T, D, thr, scale, row_inv_norm, pooled_v, pooled_l, lse_row, lse_col,
-                               local_partial, tt_logits, g_inv_norm, g_split, q_save, (cudaStream_t)stream);
+                               local_partial, tt_logits, g_inv_norm, g_split, q_save, g_prof_fwd, (cudaStream_t)stream);
     return sparc_fwd_tc_launch(v, l, mask, B, P, T, D, thr, scale, row_inv_norm, pooled_v, pooled_l, lse_row, lse_col,
                                local_partial, tt_logits, g_inv_norm, g_split, q_save, (cudaStream_t)stream);
   }

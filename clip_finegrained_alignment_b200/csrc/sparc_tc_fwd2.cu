@@ -48,6 +48,7 @@ __host__ __device__ inline Fwd2Layout fwd2_layout(int P, int T, int D, int NS) {
 }
 
 struct Fwd2Params {
+  long long* prof;
   int P, T, D, NS;
   float thr, scale;
   const uint8_t* mask;
@@ -176,6 +177,10 @@ sparc_fwd2_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_constant
     const uint64_t ilk_whi = make_smem_desc(smem_u32(Whi), il_lbo, 128, kLayoutNone);
     const uint64_t ilk_wlo = make_smem_desc(smem_u32(Wlo), il_lbo, 128, kLayoutNone);
     const uint32_t ilk_step = (2 * il_lbo) >> 4;
+    long long* pf = (p.prof && leader) ? p.prof + (size_t)b * 32 : nullptr;
+    int pi = 0;
+    auto stamp = [&]() { if (pf) pf[pi++] = clock64(); };
+    stamp();
     // ---- pass 0: S = l . v^T
     for (int u = 0; u < KB; ++u) {
       const int s = u % NS;
@@ -188,9 +193,11 @@ sparc_fwd2_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_constant
       umma_commit_w(leader, empty0 + s);
     }
     umma_commit_w(leader, s_full);
+    stamp();
     // ---- pass 1: G_kb = W . v_kb ; L += G_kb . l_kb^T ; Q += G_kb . v_kb^T   (G issued one block ahead)
     mbar_wait(w_ready, 0);
     tc_fence_after();
+    stamp();
     const int nks = kNksP ? kNksP : NP / 16;
     auto issue_g = [&](int kb) {
       const int u = KB + kb, s = u % NS, buf = kb & 1;
@@ -228,6 +235,7 @@ sparc_fwd2_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_constant
       issue_l(kb);
     }
     umma_commit_w(leader, l_full);
+    stamp();
   } else {
     // =============================== epilogue: 8 warps, 2 per TMEM lane quarter ===============================
     const int ew = warp - 2, q = warp & 3, h = ew >> 2;
@@ -241,9 +249,18 @@ sparc_fwd2_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_constant
     float cnt = 0.f;
     for (int t = 0; t < T; ++t) cnt += msk[t];
     const float inv_cnt = 1.f / fmaxf(cnt, kF2ClampEps), invP = 1.f / (float)P;
+    long long* pf = (p.prof && row == 0 && h == 0) ? p.prof + (size_t)b * 32 + 16 : nullptr;
+    int pi = 0;
+    auto stamp = [&]() { if (pf) pf[pi++] = clock64(); };
+    stamp();
 
     // ---- pass 0 side job: row norms and pooled means straight from the TMA tiles.  Warp ew owns the ew-th 16-byte chunk
     // (8 columns) of every row of the block, lane l the rows l, l+32, ...  (conflict-free under the 128-byte swizzle)
+    float ssv[8], ssl[4];                               // this thread's rows: r = lane + 32 k  (NP <= 256, NT <= 128)
+#pragma unroll
+    for (int k = 0; k < 8; ++k) ssv[k] = 0.f;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) ssl[k] = 0.f;
     for (int u = 0; u < KB; ++u) {
       const int s = u % NS;
       mbar_wait(full + s, (u / NS) & 1);
@@ -251,30 +268,34 @@ sparc_fwd2_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_constant
       float acc[16];
 #pragma unroll
       for (int j = 0; j < 16; ++j) acc[j] = 0.f;
-      for (int r = lane; r < NP; r += 32) {             // v rows
-        const uint4 raw = *reinterpret_cast<const uint4*>(st + L.l_bytes + r * 128 + ((ew ^ (r & 7)) << 4));
-        const uint32_t w4[4] = {raw.x, raw.y, raw.z, raw.w};
-        float ss = 0.f;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const float f0 = __uint_as_float(w4[i] << 16), f1 = __uint_as_float(w4[i] & 0xffff0000u);
-          ss = fmaf(f0, f0, ss); ss = fmaf(f1, f1, ss);
-          acc[2 * i] += f0; acc[2 * i + 1] += f1;
+      for (int k = 0; k < 8; ++k) {                     // v rows
+        const int r = lane + 32 * k;
+        if (r < NP) {
+          const uint4 raw = *reinterpret_cast<const uint4*>(st + L.l_bytes + r * 128 + ((ew ^ (r & 7)) << 4));
+          const uint32_t w4[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float f0 = __uint_as_float(w4[i] << 16), f1 = __uint_as_float(w4[i] & 0xffff0000u);
+            ssv[k] = fmaf(f0, f0, ssv[k]); ssv[k] = fmaf(f1, f1, ssv[k]);
+            acc[2 * i] += f0; acc[2 * i + 1] += f1;
+          }
         }
-        atomicAdd(ivn + r, ss);
       }
-      for (int r = lane; r < NT; r += 32) {             // l rows (zero beyond T)
-        const uint4 raw = *reinterpret_cast<const uint4*>(st + r * 128 + ((ew ^ (r & 7)) << 4));
-        const uint32_t w4[4] = {raw.x, raw.y, raw.z, raw.w};
-        const float m = msk[r];
-        float ss = 0.f;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const float f0 = __uint_as_float(w4[i] << 16), f1 = __uint_as_float(w4[i] & 0xffff0000u);
-          ss = fmaf(f0, f0, ss); ss = fmaf(f1, f1, ss);
-          acc[8 + 2 * i] = fmaf(m, f0, acc[8 + 2 * i]); acc[8 + 2 * i + 1] = fmaf(m, f1, acc[8 + 2 * i + 1]);
+      for (int k = 0; k < 4; ++k) {                     // l rows (zero beyond T)
+        const int r = lane + 32 * k;
+        if (r < NT) {
+          const uint4 raw = *reinterpret_cast<const uint4*>(st + r * 128 + ((ew ^ (r & 7)) << 4));
+          const uint32_t w4[4] = {raw.x, raw.y, raw.z, raw.w};
+          const float m = msk[r];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float f0 = __uint_as_float(w4[i] << 16), f1 = __uint_as_float(w4[i] & 0xffff0000u);
+            ssl[k] = fmaf(f0, f0, ssl[k]); ssl[k] = fmaf(f1, f1, ssl[k]);
+            acc[8 + 2 * i] = fmaf(m, f0, acc[8 + 2 * i]); acc[8 + 2 * i + 1] = fmaf(m, f1, acc[8 + 2 * i + 1]);
+          }
         }
-        atomicAdd(iln + r, ss);
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(empty0 + s);           // this warp is done with the tile
@@ -283,20 +304,32 @@ sparc_fwd2_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_constant
       if (lane < 8) p.pooled_v[(size_t)b * D + d] = cs * invP;                    // losses.py:207
       else if (lane < 16) p.pooled_l[(size_t)b * D + d] = cs * inv_cnt;           // losses.py:210-212
     }
-    f2_epi_bar();                                       // every partial sum of squares has landed
-    for (int i = tid; i < NP + NT; i += 256) {
-      if (i < NP) {
-        const float n = (i < P) ? 1.f / fmaxf(sqrtf(ivn[i]), kF2NormEps) : 0.f;
-        ivn[i] = n;
-        if (i < P) p.inv_vn[(size_t)b * P + i] = n;
-      } else {
-        const int t = i - NP;
-        const float n = (t < T) ? 1.f / fmaxf(sqrtf(iln[t]), kF2NormEps) : 0.f;
-        iln[t] = n;
-        if (t < T) p.inv_ln[(size_t)b * T + t] = n;
+    stamp();
+    {
+      // each warp saw 8 of the 64 columns of every block: one cross-warp reduction (scratch = the still unused W region)
+      float* part = reinterpret_cast<float*>(Whi);      // [8][NP + NT]
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { const int r = lane + 32 * k; if (r < NP) part[ew * (NP + NT) + r] = ssv[k]; }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { const int r = lane + 32 * k; if (r < NT) part[ew * (NP + NT) + NP + r] = ssl[k]; }
+      f2_epi_bar();
+      for (int i = tid; i < NP + NT; i += 256) {
+        float ss = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) ss += part[w * (NP + NT) + i];
+        if (i < NP) {
+          const float n = (i < P) ? 1.f / fmaxf(sqrtf(ss), kF2NormEps) : 0.f;
+          ivn[i] = n;
+          if (i < P) p.inv_vn[(size_t)b * P + i] = n;
+        } else {
+          const int t = i - NP;
+          const float n = (t < T) ? 1.f / fmaxf(sqrtf(ss), kF2NormEps) : 0.f;
+          iln[t] = n;
+          if (t < T) p.inv_ln[(size_t)b * T + t] = n;
+        }
       }
+      f2_epi_bar();
     }
-    f2_epi_bar();
     const bool valid = row < T && msk[inT ? row : 0] != 0.f;
     const float il = inT ? iln[row] : 0.f;
 
@@ -305,6 +338,7 @@ sparc_fwd2_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_constant
     const int c_lo = h ? psplit : 0, c_hi = h ? NP : psplit;
     mbar_wait(s_full, 0);
     tc_fence_after();
+    stamp();
     float mn = CUDART_INF_F, mx = -CUDART_INF_F;
     for (int c0 = c_lo; c0 < c_hi; c0 += 16) {
       float x[16];
@@ -365,6 +399,7 @@ sparc_fwd2_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_constant
     fence_proxy_async();
     __syncwarp();
     if (lane == 0) mbar_arrive(w_ready);
+    stamp();
 
     // ---- pass 1 epilogue: G_kb -> ||G||^2, bf16 hi/lo A operand (smem) + saved copy (global); 32 of the 64 columns per warp
     float gn2 = 0.f;
@@ -411,40 +446,83 @@ sparc_fwd2_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_constant
       if (inT) gn2 += xot[0];
     }
     const float ign = 1.f / fmaxf(sqrtf(gn2), kF2NormEps);
+    stamp();
 
     // ---- E3: masked logits.  Half 0: row pass (LSE in registers, logits -> smem); half 1: Q -> global meanwhile.
     mbar_wait(l_full, 0);
     tc_fence_after();
+    stamp();
     float* Lb = reinterpret_cast<float*>(Whi);          // [T][NT+1]  (the W region is free now)
     const int ldl = NT + 1;
+    // row pass: each half owns part of the columns; (max, sum exp) pairs are merged through shared memory
+    const int tsplit = ((NT / 16 + 1) / 2) * 16;
+    const int t_lo = h ? tsplit : 0, t_hi = h ? NT : tsplit;
+    const float sc_row = valid ? p.scale * ign : 0.f;
+    float rmax = -CUDART_INF_F, rsum = 0.f, diag = 0.f;
+    for (int c0 = t_lo; c0 < t_hi; c0 += 16) {
+      float x[16];
+      tmem_ld16(trow + kF2cL + c0, x);
+      tmem_ld_wait();
+      float cm = -CUDART_INF_F;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const int col = c0 + j;
+        x[j] = (valid && msk[col] != 0.f) ? x[j] * sc_row * iln[col] : -CUDART_INF_F;   // msk/iln are 0 beyond T
+        if (row < T) Lb[row * ldl + col] = x[j];
+        cm = fmaxf(cm, x[j]);
+        diag = (col == row) ? x[j] : diag;
+      }
+      const float nm = fmaxf(rmax, cm);
+      float sx = 0.f;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) sx += (x[j] == -CUDART_INF_F) ? 0.f : __expf(x[j] - nm);
+      rsum = rsum * ((rmax == -CUDART_INF_F) ? 0.f : __expf(rmax - nm)) + sx;
+      rmax = nm;
+    }
+    if (inT) { xme0[0] = rmax; xme0[1] = rsum; xme0[2] = diag; }
+    f2_epi_bar();                                       // exchange set 0; the logits are in smem
     float ce = 0.f;
     if (h == 0) {
-      float rmax = -CUDART_INF_F;
-      const float sc_row = valid ? p.scale * ign : 0.f;
-      for (int c0 = 0; c0 < NT; c0 += 16) {
-        float x[16];
-        tmem_ld16(trow + kF2cL + c0, x);
-        tmem_ld_wait();
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const int col = c0 + j;
-          const float y = (valid && msk[col] != 0.f) ? x[j] * sc_row * iln[col] : -CUDART_INF_F;   // msk/iln are 0 beyond T
-          if (row < T) Lb[row * ldl + col] = y;
-          rmax = fmaxf(rmax, y);
-        }
-      }
-      if (p.g_inv_norm && row < T) p.g_inv_norm[(size_t)b * T + row] = ign;
       if (valid) {
-        float s = 0.f;
-        for (int col = 0; col < T; ++col) { const float y = Lb[row * ldl + col]; if (y != -CUDART_INF_F) s += expf(y - rmax); }
-        const float lse = rmax + logf(s);
+        const float om = xot0[0], os = xot0[1];
+        const float M = fmaxf(rmax, om);
+        const float ssum = rsum * __expf(rmax - M) + ((om == -CUDART_INF_F) ? 0.f : os * __expf(om - M));
+        const float lse = M + logf(ssum);
         p.lse_row[(size_t)b * T + row] = lse;
-        ce = lse - Lb[row * ldl + row];
+        ce = lse - ((row < tsplit) ? diag : xot0[2]);
       } else if (row < T) {
         p.lse_row[(size_t)b * T + row] = 0.f;
       }
-    } else if (p.q_save) {
-      for (int c0 = 0; c0 < NP; c0 += 16) {             // Q (TMEM columns of the dead S) -> global, row stride NP
+      if (p.g_inv_norm && row < T) p.g_inv_norm[(size_t)b * T + row] = ign;
+    }
+    // column pass: thread `row` of half h covers rows [i_lo, i_hi) of column `row`
+    {
+      const int isplit = (T + 1) / 2;
+      const int i_lo = h ? isplit : 0, i_hi = h ? T : isplit;
+      float cmax = -CUDART_INF_F, csum = 0.f;
+      if (valid) {
+        for (int i = i_lo; i < i_hi; ++i) cmax = fmaxf(cmax, Lb[i * ldl + row]);
+        for (int i = i_lo; i < i_hi; ++i) { const float y = Lb[i * ldl + row]; csum += (y == -CUDART_INF_F) ? 0.f : __expf(y - cmax); }
+      }
+      float* xme = xme0 + xset;
+      float* xot = xot0 + xset;
+      if (inT) { xme[0] = cmax; xme[1] = csum; }
+      f2_epi_bar();                                     // exchange set 1
+      if (h == 1) {
+        if (valid) {
+          const float om = xot[0], os = xot[1];
+          const float M = fmaxf(cmax, om);
+          const float ssum = ((cmax == -CUDART_INF_F) ? 0.f : csum * __expf(cmax - M)) + ((om == -CUDART_INF_F) ? 0.f : os * __expf(om - M));
+          const float lse = M + logf(ssum);
+          p.lse_col[(size_t)b * T + row] = lse;
+          ce = lse - Lb[row * ldl + row];
+        } else if (row < T) {
+          p.lse_col[(size_t)b * T + row] = 0.f;
+        }
+      }
+    }
+    if (p.q_save) {                                     // Q (TMEM columns of the dead S) -> global, row stride NP; column halves
+      for (int c0 = c_lo; c0 < c_hi; c0 += 16) {
         float x[16];
         tmem_ld16(trow + kF2cS + c0, x);
         tmem_ld_wait();
@@ -455,22 +533,10 @@ sparc_fwd2_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_constant
         }
       }
     }
-    f2_epi_bar();                                       // logits are in smem
-    if (h == 1) {                                       // column pass: thread `row` owns column `row`
-      if (valid) {
-        float cmax = -CUDART_INF_F;
-        for (int i = 0; i < T; ++i) cmax = fmaxf(cmax, Lb[i * ldl + row]);
-        float s = 0.f;
-        for (int i = 0; i < T; ++i) { const float y = Lb[i * ldl + row]; if (y != -CUDART_INF_F) s += expf(y - cmax); }
-        const float lse = cmax + logf(s);
-        p.lse_col[(size_t)b * T + row] = lse;
-        ce = lse - Lb[row * ldl + row];
-      } else if (row < T) {
-        p.lse_col[(size_t)b * T + row] = 0.f;
-      }
-    } else if (p.tt_logits) {                           // coalesced copy of the T x T logits for the backward
+    if (p.tt_logits) {                                  // coalesced copy of the T x T logits for the backward
       float* dst = p.tt_logits + (size_t)b * T * T;
-      for (int idx = (q * 32 + lane); idx < T * T; idx += 128) { const int i = idx / T, j = idx - i * T; dst[idx] = Lb[i * ldl + j]; }
+      for (int i = ew; i < T; i += 8)
+        for (int j = lane; j < T; j += 32) dst[i * T + j] = Lb[i * ldl + j];
     }
     ce = warp_sum(ce);
     if (lane == 0) red[ew] = ce;                        // warps 0..3 (half 0): row direction, 4..7: column direction
@@ -479,6 +545,7 @@ sparc_fwd2_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_constant
       p.local_partial[2 * b] = red[0] + red[1] + red[2] + red[3];
       p.local_partial[2 * b + 1] = red[4] + red[5] + red[6] + red[7];
     }
+    stamp();
     tc_fence_before();
   }
   __syncthreads();
@@ -499,7 +566,7 @@ bool sparc_fwd2_supported(int P, int T, int D, int dtype) {
 int sparc_fwd2_launch(const void* v, const void* l, const uint8_t* mask, int B, int P, int T, int D, float thr,
                       float scale, float* row_inv_norm, float* pooled_v, float* pooled_l, float* lse_row, float* lse_col,
                       float* local_partial, float* tt_logits, float* g_inv_norm, void* g_split, float* q_save,
-                      cudaStream_t st) {
+                      long long* prof, cudaStream_t st) {
   const int NS = fwd2_pick_stages(P, T, D);
   if (NS == 0) return CFA_ERR_UNSUPPORTED;
   const Fwd2Layout L = fwd2_layout(P, T, D, NS);
@@ -507,7 +574,7 @@ int sparc_fwd2_launch(const void* v, const void* l, const uint8_t* mask, int B, 
   int rc;
   if ((rc = make_tmap_bf16_3d(&tmV, v, D, P, B, 64, L.NP)) != CFA_OK) return rc;
   if ((rc = make_tmap_bf16_3d(&tmL, l, D, T, B, 64, L.NT)) != CFA_OK) return rc;
-  Fwd2Params prm{P, T, D, NS, thr, scale, mask, row_inv_norm, row_inv_norm + (size_t)B * P, pooled_v, pooled_l, lse_row,
+  Fwd2Params prm{prof, P, T, D, NS, thr, scale, mask, row_inv_norm, row_inv_norm + (size_t)B * P, pooled_v, pooled_l, lse_row,
                  lse_col, local_partial, tt_logits, g_inv_norm, (bf16*)g_split, q_save};
   const size_t smem = L.total + 1024;
   if (L.NP == 208) {

@@ -105,8 +105,10 @@ int cfa_global_infonce_bwd(const float* a_loc, const float* b_loc, const float* 
                            int D, int col_offset, float scale, float eps, const float* lse_loc2, const float* lse_all2,
                            const float* norms2, const float* coef2, float* da, float* db, void* workspace,
                            size_t workspace_bytes, int path, void* stream);
-/* path: 0 = auto (tcgen05 logits tiles with bf16 hi/lo-split normalised operands when D % 64 == 0 and D <= 512),
- * 1 = fp32-exact CUDA-core tiles, 2 = tensor cores or CFA_ERR_UNSUPPORTED.  The backward must be given the SAME
+/* path: 0 = auto (rank-local problems, Bg == B <= 512: low-latency symmetric fp32 tiles, one logits tile serving both
+ * directions; otherwise tcgen05 logits tiles with bf16 hi/lo-split normalised operands when D % 64 == 0 and D <= 512),
+ * 1 = fp32-exact CUDA-core tiles, 2 = tensor cores or CFA_ERR_UNSUPPORTED.  cfa_global_infonce_path reports what a
+ * request resolves to: 1 = CUDA-core tiles, 2 = tensor cores, 3 = symmetric rank-local tiles.  The backward must be given the SAME
  * workspace (and path) as the forward: the tensor-core path keeps its normalised operands there. */
 int cfa_global_infonce_path(int B, int Bg, int D, int path);
 
@@ -184,6 +186,7 @@ int cfa_sparc_coef_ptrs(const float* g_global, const float* g_local, const float
  * ---------------------------------------------------------------------------------------------- */
 /* tuning aid: device buffer [B][32] int64 receiving clock64 phase stamps of the tensor-core backward (NULL = off) */
 int cfa_debug_set_profile_buffer(void* device_buffer);
+int cfa_debug_set_profile_buffer_fwd(void* device_buffer);   /* same for the tensor-core forward */
 /* debugging aid: host-mapped (pinned) int32 buffer [cta][8 warps] receiving progress markers of the tensor-core
  * global InfoNCE backward, readable from the host while a kernel is stuck (NULL = off) */
 int cfa_debug_set_marker_buffer(void* mapped_buffer);
