@@ -44,9 +44,10 @@ SIGNATURES = {
                                          _sz, _i, _vp]),
     "cfa_global_infonce_path": (C.c_int, [_i, _i, _i, _i]),
     "cfa_sparc_fwd": (C.c_int, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
-                                _vp, _vp, _i, _vp]),
+                                _vp, _vp, _vp, _sz, _i, _vp]),
     "cfa_sparc_bwd": (C.c_int, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
-                                _vp, _vp, _vp, _vp, _i, _vp]),
+                                _vp, _vp, _vp, _vp, _vp, _sz, _i, _vp]),
+    "cfa_sparc_scratch_bytes": (_sz, [_i, _i, _i, _i]),
     "cfa_sparc_path": (C.c_int, [_i, _i, _i, _i, _i]),
     "cfa_sparc_bwd_path": (C.c_int, [_i, _i, _i, _i, _i]),
     "cfa_sparc_max_patches": (C.c_int, [_i, _i]),

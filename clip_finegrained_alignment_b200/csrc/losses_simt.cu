@@ -23,14 +23,18 @@ constexpr float kClampEps = 1e-8f;   // losses.py:211,242
 struct SparcSmem {
   int ldS, ldT, db, ld;   // strides: S rows, logits rows (odd), D-block width, staging row stride (db+1)
   size_t S, dW, L, stV, stL, stG, stDG, vn, ln, gn2, msk, rs, cs, misc, total;   // float offsets
+  float* gS;              // when the T x P tiles do not fit in shared memory (ViT-L/14@336: P = 577) they live in a
+  float* gdW;             // per-CTA slice of a global scratch buffer (L2-resident); NULL = shared memory
 };
 
-__host__ __device__ inline SparcSmem sparc_layout(int P, int T, int db, bool backward) {
+// in_global: S (and dW) are kept in global scratch instead of shared memory
+__host__ __device__ inline SparcSmem sparc_layout(int P, int T, int db, bool backward, bool in_global = false) {
   SparcSmem s;
+  s.gS = nullptr; s.gdW = nullptr;
   s.ldS = P; s.ldT = T | 1; s.db = db; s.ld = db + 1;
   size_t o = 0;
-  s.S = o; o += (size_t)T * s.ldS;
-  s.dW = o; if (backward) o += (size_t)T * s.ldS;
+  s.S = o; if (!in_global) o += (size_t)T * s.ldS;
+  s.dW = o; if (backward && !in_global) o += (size_t)T * s.ldS;
   s.L = o; o += (size_t)T * s.ldT;
   s.stV = o; o += (size_t)P * s.ld;
   s.stL = o; o += (size_t)T * s.ld;
@@ -47,9 +51,9 @@ __host__ __device__ inline SparcSmem sparc_layout(int P, int T, int db, bool bac
   return s;
 }
 
-static int sparc_pick_db(int P, int T, bool backward, size_t limit_bytes) {
+static int sparc_pick_db(int P, int T, bool backward, size_t limit_bytes, bool in_global = false) {
   for (int db = 32; db >= 8; db >>= 1)
-    if (sparc_layout(P, T, db, backward).total * sizeof(float) <= limit_bytes) return db;
+    if (sparc_layout(P, T, db, backward, in_global).total * sizeof(float) <= limit_bytes) return db;
   return 0;
 }
 
@@ -59,7 +63,7 @@ constexpr size_t kSmemLimit = 227 * 1024;
 template <typename T, bool kPool>
 __device__ __forceinline__ void sparc_phase_similarity(const SparcSmem& L, float* sm, const T* vb, const T* lb, int P,
                                                        int Tn, int D, float* pooled_v, float* pooled_l, float cnt) {
-  float* S = sm + L.S; float* stV = sm + L.stV; float* stL = sm + L.stL;
+  float* S = L.gS ? L.gS : sm + L.S; float* stV = sm + L.stV; float* stL = sm + L.stL;
   float* vn = sm + L.vn; float* ln = sm + L.ln; float* msk = sm + L.msk; float* red = sm + L.misc;
   const int ld = L.ld, kc = L.db;
   for (int i = threadIdx.x; i < P + Tn; i += kNT) { if (i < P) vn[i] = 0.f; else ln[i - P] = 0.f; }
@@ -117,7 +121,7 @@ __device__ __forceinline__ void sparc_phase_similarity(const SparcSmem& L, float
 // Phase 2: row-wise min-max, threshold, renormalise (losses.py:228-243).  S_raw -> W in place.
 // rs[t*8 + {0:sigma, 1:range, 2:min, 3:imin, 4:imax}] saved for the backward.
 __device__ __forceinline__ void sparc_phase_weights(const SparcSmem& L, float* sm, int P, int Tn, float thr) {
-  float* S = sm + L.S; float* vn = sm + L.vn; float* ln = sm + L.ln; float* msk = sm + L.msk; float* rs = sm + L.rs;
+  float* S = L.gS ? L.gS : sm + L.S; float* vn = sm + L.vn; float* ln = sm + L.ln; float* msk = sm + L.msk; float* rs = sm + L.rs;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   for (int t = w; t < Tn; t += kNT / 32) {
     float* row = S + t * L.ldS;
@@ -163,7 +167,7 @@ __device__ __forceinline__ void sparc_phase_weights(const SparcSmem& L, float* s
 
 // G_blk = W . v_blk for the staged D-block (losses.py:245), rows of masked tokens zeroed -> stG.
 __device__ __forceinline__ void sparc_group_block(const SparcSmem& L, float* sm, int P, int Tn) {
-  float* W = sm + L.S; float* stV = sm + L.stV; float* stG = sm + L.stG; float* msk = sm + L.msk;
+  float* W = L.gS ? L.gS : sm + L.S; float* stV = sm + L.stV; float* stG = sm + L.stG; float* msk = sm + L.msk;
   const int ld = L.ld, db = L.db;
   for (int m0 = 0; m0 < Tn; m0 += 80) {
     float acc[5][2];
@@ -215,10 +219,12 @@ template <typename T>
 __global__ void __launch_bounds__(kNT, 1)
 sparc_fwd_kernel(const T* __restrict__ v, const T* __restrict__ l, const uint8_t* __restrict__ mask, int P, int Tn,
                  int D, int db, float thr, float scale, float* __restrict__ pooled_v, float* __restrict__ pooled_l,
-                 float* __restrict__ lse_row, float* __restrict__ lse_col, float* __restrict__ local_partial) {
+                 float* __restrict__ lse_row, float* __restrict__ lse_col, float* __restrict__ local_partial,
+                 float* scratch) {
   extern __shared__ float sm[];
-  const SparcSmem L = sparc_layout(P, Tn, db, false);
+  SparcSmem L = sparc_layout(P, Tn, db, false, scratch != nullptr);
   const int b = blockIdx.x;
+  if (scratch) L.gS = scratch + (size_t)b * Tn * L.ldS;
   const T* vb = v + (size_t)b * P * D;
   const T* lb = l + (size_t)b * Tn * D;
   float* msk = sm + L.msk; float* ln = sm + L.ln; float* gn = sm + L.gn2; float* Lg = sm + L.L;
@@ -298,15 +304,16 @@ __global__ void __launch_bounds__(kNT, 1)
 sparc_bwd_kernel(const T* __restrict__ v, const T* __restrict__ l, const uint8_t* __restrict__ mask, int P, int Tn,
                  int D, int db, float thr, float scale, const float* __restrict__ lse_row,
                  const float* __restrict__ lse_col, const float* __restrict__ coef, const float* __restrict__ dpool_v,
-                 const float* __restrict__ dpool_l, T* __restrict__ dv, T* __restrict__ dl) {
+                 const float* __restrict__ dpool_l, T* __restrict__ dv, T* __restrict__ dl, float* scratch) {
   extern __shared__ float sm[];
-  const SparcSmem L = sparc_layout(P, Tn, db, true);
+  SparcSmem L = sparc_layout(P, Tn, db, true, scratch != nullptr);
   const int b = blockIdx.x;
+  if (scratch) { L.gS = scratch + (size_t)b * 2 * Tn * L.ldS; L.gdW = L.gS + (size_t)Tn * L.ldS; }
   const T* vb = v + (size_t)b * P * D;
   const T* lb = l + (size_t)b * Tn * D;
   T* dvb = dv + (size_t)b * P * D;
   T* dlb = dl + (size_t)b * Tn * D;
-  float* W = sm + L.S; float* dW = sm + L.dW; float* Lg = sm + L.L;
+  float* W = L.gS ? L.gS : sm + L.S; float* dW = L.gdW ? L.gdW : sm + L.dW; float* Lg = sm + L.L;
   float* stV = sm + L.stV; float* stL = sm + L.stL; float* stG = sm + L.stG; float* stDG = sm + L.stDG;
   float* vn = sm + L.vn; float* ln = sm + L.ln; float* gn = sm + L.gn2; float* msk = sm + L.msk;
   float* rs = sm + L.rs; float* cs = sm + L.cs;
@@ -559,10 +566,17 @@ extern "C" int cfa_sparc_coef_ptrs(const float* g_global, const float* g_local, 
   return launch_status();
 }
 
+// bytes of global scratch the CUDA-core path needs for this shape (0 when the T x P tiles fit in shared memory)
+extern "C" size_t cfa_sparc_scratch_bytes(int B, int P, int T, int backward) {
+  if (B <= 0 || P <= 0 || T <= 0) return 0;
+  if (sparc_pick_db(P, T, backward != 0, kSmemLimit) != 0) return 0;
+  return (size_t)(backward ? 2 : 1) * B * T * P * sizeof(float);
+}
+
 extern "C" int cfa_sparc_max_patches(int T, int backward) {
   int best = 0;
-  for (int P = 1; P <= 4096; ++P) {
-    if (sparc_pick_db(P, T, backward != 0, kSmemLimit) == 0) break;
+  for (int P = 1; P <= 4096; ++P) {          // with the T x P tiles in global scratch only the staging tiles bound P
+    if (sparc_pick_db(P, T, backward != 0, kSmemLimit) == 0 && sparc_pick_db(P, T, backward != 0, kSmemLimit, true) == 0) break;
     best = P;
   }
   return best;
@@ -571,25 +585,32 @@ extern "C" int cfa_sparc_max_patches(int T, int backward) {
 template <typename T>
 static int sparc_fwd_launch(const void* v, const void* l, const uint8_t* mask, int B, int P, int Tn, int D, float thr,
                             float scale, float* pooled_v, float* pooled_l, float* lse_row, float* lse_col,
-                            float* local_partial, cudaStream_t st) {
-  const int db = sparc_pick_db(P, Tn, false, kSmemLimit);
-  if (db == 0) return CFA_ERR_UNSUPPORTED;
-  const size_t smem = sparc_layout(P, Tn, db, false).total * sizeof(float);
+                            float* local_partial, float* scratch, size_t scratch_bytes, cudaStream_t st) {
+  int db = sparc_pick_db(P, Tn, false, kSmemLimit);
+  bool in_global = false;
+  if (db == 0) {                                   // T x P tile too large for shared memory: global scratch
+    db = sparc_pick_db(P, Tn, false, kSmemLimit, true);
+    if (db == 0) return CFA_ERR_UNSUPPORTED;
+    if (!scratch || scratch_bytes < (size_t)B * Tn * P * sizeof(float)) return CFA_ERR_WORKSPACE;
+    in_global = true;
+  }
+  const size_t smem = sparc_layout(P, Tn, db, false, in_global).total * sizeof(float);
   CFA_CUDA_TRY(cudaFuncSetAttribute(sparc_fwd_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   sparc_fwd_kernel<T><<<B, kNT, smem, st>>>((const T*)v, (const T*)l, mask, P, Tn, D, db, thr, scale, pooled_v,
-                                            pooled_l, lse_row, lse_col, local_partial);
+                                            pooled_l, lse_row, lse_col, local_partial, in_global ? scratch : nullptr);
   return launch_status();
 }
 
 int cfa::sparc_fwd_simt(const void* v, const void* l, const uint8_t* mask, int B, int P, int T, int D, int dtype,
                              float thr, float scale, float* pooled_v, float* pooled_l, float* lse_row, float* lse_col,
-                             float* local_partial, void* stream) {
+                             float* local_partial, void* scratch, size_t scratch_bytes, void* stream) {
   if (B <= 0 || P <= 0 || T <= 0 || D <= 0 || !v || !l || !mask) return CFA_ERR_BAD_ARG;
   cudaStream_t st = (cudaStream_t)stream;
+  float* sc = (float*)scratch;
   switch (dtype) {
-    case CFA_DTYPE_F32: return sparc_fwd_launch<float>(v, l, mask, B, P, T, D, thr, scale, pooled_v, pooled_l, lse_row, lse_col, local_partial, st);
-    case CFA_DTYPE_BF16: return sparc_fwd_launch<__nv_bfloat16>(v, l, mask, B, P, T, D, thr, scale, pooled_v, pooled_l, lse_row, lse_col, local_partial, st);
-    case CFA_DTYPE_F16: return sparc_fwd_launch<__half>(v, l, mask, B, P, T, D, thr, scale, pooled_v, pooled_l, lse_row, lse_col, local_partial, st);
+    case CFA_DTYPE_F32: return sparc_fwd_launch<float>(v, l, mask, B, P, T, D, thr, scale, pooled_v, pooled_l, lse_row, lse_col, local_partial, sc, scratch_bytes, st);
+    case CFA_DTYPE_BF16: return sparc_fwd_launch<__nv_bfloat16>(v, l, mask, B, P, T, D, thr, scale, pooled_v, pooled_l, lse_row, lse_col, local_partial, sc, scratch_bytes, st);
+    case CFA_DTYPE_F16: return sparc_fwd_launch<__half>(v, l, mask, B, P, T, D, thr, scale, pooled_v, pooled_l, lse_row, lse_col, local_partial, sc, scratch_bytes, st);
     default: return CFA_ERR_UNSUPPORTED;
   }
 }
@@ -597,25 +618,34 @@ int cfa::sparc_fwd_simt(const void* v, const void* l, const uint8_t* mask, int B
 template <typename T>
 static int sparc_bwd_launch(const void* v, const void* l, const uint8_t* mask, int B, int P, int Tn, int D, float thr,
                             float scale, const float* lse_row, const float* lse_col, const float* coef,
-                            const float* dpv, const float* dpl, void* dv, void* dl, cudaStream_t st) {
-  const int db = sparc_pick_db(P, Tn, true, kSmemLimit);
-  if (db == 0) return CFA_ERR_UNSUPPORTED;
-  const size_t smem = sparc_layout(P, Tn, db, true).total * sizeof(float);
+                            const float* dpv, const float* dpl, void* dv, void* dl, float* scratch, size_t scratch_bytes,
+                            cudaStream_t st) {
+  int db = sparc_pick_db(P, Tn, true, kSmemLimit);
+  bool in_global = false;
+  if (db == 0) {
+    db = sparc_pick_db(P, Tn, true, kSmemLimit, true);
+    if (db == 0) return CFA_ERR_UNSUPPORTED;
+    if (!scratch || scratch_bytes < (size_t)2 * B * Tn * P * sizeof(float)) return CFA_ERR_WORKSPACE;
+    in_global = true;
+  }
+  const size_t smem = sparc_layout(P, Tn, db, true, in_global).total * sizeof(float);
   CFA_CUDA_TRY(cudaFuncSetAttribute(sparc_bwd_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   sparc_bwd_kernel<T><<<B, kNT, smem, st>>>((const T*)v, (const T*)l, mask, P, Tn, D, db, thr, scale, lse_row, lse_col,
-                                            coef, dpv, dpl, (T*)dv, (T*)dl);
+                                            coef, dpv, dpl, (T*)dv, (T*)dl, in_global ? scratch : nullptr);
   return launch_status();
 }
 
 int cfa::sparc_bwd_simt(const void* v, const void* l, const uint8_t* mask, int B, int P, int T, int D, int dtype,
                              float thr, float scale, const float* lse_row, const float* lse_col, const float* coef,
-                             const float* dpooled_v, const float* dpooled_l, void* dv, void* dl, void* stream) {
+                             const float* dpooled_v, const float* dpooled_l, void* dv, void* dl, void* scratch,
+                             size_t scratch_bytes, void* stream) {
   if (B <= 0 || P <= 0 || T <= 0 || D <= 0 || !v || !l || !mask || !coef || !dv || !dl) return CFA_ERR_BAD_ARG;
   cudaStream_t st = (cudaStream_t)stream;
+  float* sc = (float*)scratch;
   switch (dtype) {
-    case CFA_DTYPE_F32: return sparc_bwd_launch<float>(v, l, mask, B, P, T, D, thr, scale, lse_row, lse_col, coef, dpooled_v, dpooled_l, dv, dl, st);
-    case CFA_DTYPE_BF16: return sparc_bwd_launch<__nv_bfloat16>(v, l, mask, B, P, T, D, thr, scale, lse_row, lse_col, coef, dpooled_v, dpooled_l, dv, dl, st);
-    case CFA_DTYPE_F16: return sparc_bwd_launch<__half>(v, l, mask, B, P, T, D, thr, scale, lse_row, lse_col, coef, dpooled_v, dpooled_l, dv, dl, st);
+    case CFA_DTYPE_F32: return sparc_bwd_launch<float>(v, l, mask, B, P, T, D, thr, scale, lse_row, lse_col, coef, dpooled_v, dpooled_l, dv, dl, sc, scratch_bytes, st);
+    case CFA_DTYPE_BF16: return sparc_bwd_launch<__nv_bfloat16>(v, l, mask, B, P, T, D, thr, scale, lse_row, lse_col, coef, dpooled_v, dpooled_l, dv, dl, sc, scratch_bytes, st);
+    case CFA_DTYPE_F16: return sparc_bwd_launch<__half>(v, l, mask, B, P, T, D, thr, scale, lse_row, lse_col, coef, dpooled_v, dpooled_l, dv, dl, sc, scratch_bytes, st);
     default: return CFA_ERR_UNSUPPORTED;
   }
 }

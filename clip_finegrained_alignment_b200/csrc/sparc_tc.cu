@@ -1258,7 +1258,7 @@ extern "C" int cfa_sparc_bwd_path(int P, int T, int D, int dtype, int path) {
 extern "C" int cfa_sparc_fwd(const void* v, const void* l, const uint8_t* mask, int B, int P, int T, int D, int dtype,
                              float thr, float scale, float* row_inv_norm, float* pooled_v, float* pooled_l,
                              float* lse_row, float* lse_col, float* local_partial, float* tt_logits, float* g_inv_norm,
-                             void* g_split, float* q_save, int path, void* stream) {
+                             void* g_split, float* q_save, void* scratch, size_t scratch_bytes, int path, void* stream) {
   if (B <= 0 || P <= 0 || T <= 0 || D <= 0 || !v || !l || !mask) return CFA_ERR_BAD_ARG;
   const int which = cfa_sparc_path(P, T, D, dtype, path);
   if (which < 0) return which;
@@ -1272,14 +1272,15 @@ extern "C" int cfa_sparc_fwd(const void* v, const void* l, const uint8_t* mask, 
                                local_partial, tt_logits, g_inv_norm, g_split, q_save, (cudaStream_t)stream);
   }
   return sparc_fwd_simt(v, l, mask, B, P, T, D, dtype, thr, scale, pooled_v, pooled_l, lse_row, lse_col, local_partial,
-                        stream);
+                        scratch, scratch_bytes, stream);
 }
 
 extern "C" int cfa_sparc_bwd(const void* v, const void* l, const uint8_t* mask, int B, int P, int T, int D, int dtype,
                              float thr, float scale, const float* row_inv_norm, const float* lse_row,
                              const float* lse_col, const float* tt_logits, const float* g_inv_norm,
                              const void* g_split, const float* q_save, const float* coef, const float* dpooled_v,
-                             const float* dpooled_l, void* dv, void* dl, int path, void* stream) {
+                             const float* dpooled_l, void* dv, void* dl, void* scratch, size_t scratch_bytes, int path,
+                             void* stream) {
   if (B <= 0 || P <= 0 || T <= 0 || D <= 0 || !v || !l || !mask || !coef || !dv || !dl) return CFA_ERR_BAD_ARG;
   const int which = cfa_sparc_bwd_path(P, T, D, dtype, path);
   if (which < 0) return which;
@@ -1293,5 +1294,5 @@ extern "C" int cfa_sparc_bwd(const void* v, const void* l, const uint8_t* mask, 
                                g_inv_norm, dpooled_v, dpooled_l, dv, dl, (cudaStream_t)stream);
   }
   return sparc_bwd_simt(v, l, mask, B, P, T, D, dtype, thr, scale, lse_row, lse_col, coef, dpooled_v, dpooled_l, dv, dl,
-                        stream);
+                        scratch, scratch_bytes, stream);
 }

@@ -164,14 +164,19 @@ class _SparcFunction(torch.autograd.Function):
         base = blk.data_ptr()
         ptr = [base + 4 * o for o in off]
         gq = (ptr[8], ptr[9]) if saved else (0, 0)
+        # CUDA-core path with P too large for shared-memory residency (ViT-L/14@336): L2-resident global scratch
+        tc = path != 1 and _L.cfa_sparc_path(P, T, D, code, path) == 2
+        sbytes = 0 if tc else _L.cfa_sparc_scratch_bytes(B, P, T, 1)
+        scratch = torch.empty(sbytes, dtype=torch.uint8, device=dev) if sbytes else None
+        sptr = scratch.data_ptr() if sbytes else 0
         pooled = blk[:2 * B * D].view(2, B, D)
         out8 = blk[off[1]:off[2]]
         part_t = blk[off[4]:off[5]]
         same_dev = torch.cuda.current_device() == dev.index
         with (contextlib.nullcontext() if same_dev else torch.cuda.device(dev)):
             _lib.call("cfa_sparc_fwd", v.data_ptr(), l.data_ptr(), mask_u8.data_ptr(), B, P, T, D, code, thr, scale,
-                      ptr[5], ptr[0], ptr[0] + 4 * B * D, ptr[2], ptr[3], ptr[4], ptr[6], ptr[7], gq[0], gq[1], path,
-                      _lib.stream_ptr())
+                      ptr[5], ptr[0], ptr[0] + 4 * B * D, ptr[2], ptr[3], ptr[4], ptr[6], ptr[7], gq[0], gq[1], sptr, sbytes,
+                      path, _lib.stream_ptr())
             world, rank, group = _dist_ctx(group, gather)
             gpath = 1 if (v.dtype == torch.float32 or path == 1) else 0      # fp32 inputs keep the fp32-exact global kernels
             gst, sums = _global_forward(pooled, scale, _NORM_EPS, world, rank, group,
@@ -182,6 +187,7 @@ class _SparcFunction(torch.autograd.Function):
         ctx.save_for_backward(v, l, mask_u8, blk)
         ctx.gst = gst
         ctx.hp = (thr, gw, lw, scale, code, path, ptr, gq)
+        ctx.scratch = scratch                          # reused by the backward (same size class)
         ctx.set_materialize_grads(False)               # unused outputs arrive as None: no zero-fill launches
         return out8[:7].clone().unbind(0)
 
@@ -210,9 +216,11 @@ class _SparcFunction(torch.autograd.Function):
             dpv, dpl = _global_backward(gst, coef)
             dv = torch.empty_like(v)
             dl = torch.empty_like(l)
+            sbytes = ctx.scratch.numel() if ctx.scratch is not None else 0
+            sptr = ctx.scratch.data_ptr() if sbytes else 0
             _lib.call("cfa_sparc_bwd", v.data_ptr(), l.data_ptr(), mask_u8.data_ptr(), B, P, T, D, code, thr, scale,
                       ptr[5], ptr[2], ptr[3], ptr[6], ptr[7], gq[0], gq[1], coef.data_ptr() + 8, dpv.data_ptr(), dpl.data_ptr(),
-                      dv.data_ptr(), dl.data_ptr(), path, _lib.stream_ptr())
+                      dv.data_ptr(), dl.data_ptr(), sptr, sbytes, path, _lib.stream_ptr())
         return dv, dl, None, None, None, None, None, None, None, None
 
 

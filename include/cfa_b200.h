@@ -125,7 +125,7 @@ int cfa_global_infonce_path(int B, int Bg, int D, int path);
 int cfa_sparc_fwd(const void* v, const void* l, const uint8_t* mask, int B, int P, int T, int D, int dtype,
                   float thr, float scale, float* row_inv_norm, float* pooled_v, float* pooled_l, float* lse_row,
                   float* lse_col, float* local_partial, float* tt_logits, float* g_inv_norm, void* g_split,
-                  float* q_save, int path, void* stream);
+                  float* q_save, void* scratch, size_t scratch_bytes, int path, void* stream);
 
 /*
  * Backward of the above.  coef: DEVICE pointer to 2 floats = upstream coefficient of loss_vl_local and
@@ -145,12 +145,16 @@ int cfa_sparc_fwd(const void* v, const void* l, const uint8_t* mask, int B, int 
 int cfa_sparc_bwd(const void* v, const void* l, const uint8_t* mask, int B, int P, int T, int D, int dtype,
                   float thr, float scale, const float* row_inv_norm, const float* lse_row, const float* lse_col,
                   const float* tt_logits, const float* g_inv_norm, const void* g_split, const float* q_save,
-                  const float* coef, const float* dpooled_v, const float* dpooled_l, void* dv, void* dl, int path,
-                  void* stream);
+                  const float* coef, const float* dpooled_v, const float* dpooled_l, void* dv, void* dl, void* scratch,
+                  size_t scratch_bytes, int path, void* stream);
 int cfa_sparc_path(int P, int T, int D, int dtype, int path);
 int cfa_sparc_bwd_path(int P, int T, int D, int dtype, int path);   /* backward: tensor cores need P <= ~224 at T = 77 */
 
-/* largest P the SPARC kernels accept for a given T (shared-memory residency of the T x P tiles) */
+/* Global scratch of the CUDA-core path: when the T x P tiles (S, and dW in the backward) do not fit in shared memory
+ * (ViT-L/14@336: P = 576 / 577) they live in a per-CTA slice of `scratch` (stays L2-resident); 0 = not needed. */
+size_t cfa_sparc_scratch_bytes(int B, int P, int T, int backward);
+
+/* largest P the SPARC kernels accept for a given T (staging tiles in shared memory) */
 int cfa_sparc_max_patches(int T, int backward);
 
 /*

@@ -87,7 +87,8 @@ def test_sparc_every_output_is_differentiable(key):
 
 
 @pytest.mark.parametrize("P,T,D,B", [(50, 77, 512, 4), (196, 77, 512, 3), (197, 77, 512, 2), (257, 77, 768, 2),
-                                     (7, 5, 20, 2), (64, 77, 36, 3)])
+                                     (7, 5, 20, 2), (64, 77, 36, 3),
+                                     (576, 77, 768, 2), (577, 77, 768, 2)])      # BASELINE config 4 (ViT-L/14@336)
 def test_sparc_fp32_shapes_vs_oracle(P, T, D, B):
     g = torch.Generator().manual_seed(P * 1000 + D)
     v = torch.randn(B, P, D, generator=g)
@@ -120,6 +121,24 @@ def test_sparc_low_precision_inputs(dtype, rtol):
     out_round = 2.0 ** -8 if dtype == torch.bfloat16 else 2.0 ** -11
     assert rel_err(dv.float(), rv) <= rtol + out_round
     assert rel_err(dl.float(), rl) <= rtol + out_round
+
+
+def test_sparc_config4_bf16_vit_l14_336():
+    """BASELINE config 4 shapes (P = 576, D = 768) with bf16 inputs: the T x P tiles live in L2-resident global scratch."""
+    g = torch.Generator().manual_seed(44)
+    B, P, T, D = 3, 576, 77, 768
+    v = torch.randn(B, P, D, generator=g).to(torch.bfloat16)
+    l = torch.randn(B, T, D, generator=g).to(torch.bfloat16)
+    m = torch.ones(B, T, dtype=torch.bool)
+    m[1, 50:] = False                                   # one padded caption (truncate semantics)
+    out, dv, dl = run_sparc(v, l, m, cfg(1.0 / P, 1.0, 1.0, 1.0))
+    o = lo.sparc_forward(v.double(), l.double(), m, float(torch.tensor(1.0 / P, dtype=torch.float32)), 1.0, 1.0, 1.0,
+                         mask_semantics="truncate")
+    rv, rl = lo.sparc_backward(o)
+    for k in lo.SPARC_KEYS:
+        assert abs(float(out[k]) - float(o[k])) <= 1e-4 * max(1.0, abs(float(o[k]))), k
+    assert rel_err(dv.float(), rv) <= 1e-3 + 2.0 ** -8
+    assert rel_err(dl.float(), rl) <= 1e-3 + 2.0 ** -8
 
 
 def test_sparc_padded_mask_truncate_semantics():
