@@ -48,6 +48,8 @@ SIGNATURES = {
     "cfa_sparc_bwd": (C.c_int, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                 _vp, _vp, _vp, _vp, _vp, _sz, _i, _vp]),
     "cfa_sparc_scratch_bytes": (_sz, [_i, _i, _i, _i]),
+    "cfa_masked_pairwise_fwd": (C.c_int, [_vp, _vp, _vp, _i, _i, _i, _i, _f, _vp, _vp, _vp, _vp]),
+    "cfa_masked_pairwise_bwd": (C.c_int, [_vp, _vp, _vp, _i, _i, _i, _i, _f, _vp, _vp, _vp, _vp, _vp, _vp]),
     "cfa_sparc_path": (C.c_int, [_i, _i, _i, _i, _i]),
     "cfa_sparc_bwd_path": (C.c_int, [_i, _i, _i, _i, _i]),
     "cfa_sparc_max_patches": (C.c_int, [_i, _i]),
@@ -69,7 +71,8 @@ for _name, (_res, _args) in SIGNATURES.items():
 
 # kernels launched per C-ABI call (cudaMemsetAsync not counted); bench.py reports the running total
 LAUNCHES = {"cfa_adamspd_step": 2, "cfa_global_infonce_fwd": 2, "cfa_global_infonce_bwd": 2, "cfa_sparc_fwd": 1,
-            "cfa_sparc_bwd": 1, "cfa_sparc_finalize": 1, "cfa_sparc_coef": 1, "cfa_sparc_coef_ptrs": 1}
+            "cfa_sparc_bwd": 1, "cfa_sparc_finalize": 1, "cfa_sparc_coef": 1, "cfa_sparc_coef_ptrs": 1,
+            "cfa_masked_pairwise_fwd": 2, "cfa_masked_pairwise_bwd": 1}
 launch_count = 0
 kernel_events = None       # {abi name: [(start_event, end_event), ...]} while bench.py profiles; else None
 

@@ -250,6 +250,44 @@ class _PairwiseFunction(torch.autograd.Function):
         return da.to(ctx.dt[0]), db.to(ctx.dt[1]), None, None
 
 
+class _MaskedPairwiseFunction(torch.autograd.Function):
+    """SPARCLoss.masked_pairwise_contrastive_loss(a[B,T,D], b[B,T,D], mask[B,T]) (losses.py:165-197)."""
+
+    @staticmethod
+    def forward(ctx, a, b, mask, scale):
+        dev = _lib.require_cuda(a, b, mask)
+        if a.dtype != b.dtype or a.dtype not in _lib.DTYPE_CODE:
+            raise _lib.CfaError(f"masked_pairwise_contrastive_loss: a, b must share a dtype in fp32/bf16/fp16, got {a.dtype}, {b.dtype}")
+        if a.dim() != 3 or a.shape != b.shape or mask.shape != a.shape[:2]:
+            raise _lib.CfaError(f"masked_pairwise_contrastive_loss: bad shapes a{tuple(a.shape)} b{tuple(b.shape)} mask{tuple(mask.shape)}")
+        a = a.contiguous()
+        b = b.contiguous()
+        mask_u8 = mask.contiguous().view(torch.uint8) if mask.dtype == torch.bool else (mask != 0).contiguous().view(torch.uint8)
+        B, T, D = a.shape
+        buf = torch.empty(B * T + B + 2, dtype=torch.float32, device=dev)       # lse_row | partial | (loss, n_valid)
+        p0 = buf.data_ptr()
+        with torch.cuda.device(dev):
+            _lib.call("cfa_masked_pairwise_fwd", a.data_ptr(), b.data_ptr(), mask_u8.data_ptr(), B, T, D,
+                      _lib.DTYPE_CODE[a.dtype], scale, p0, p0 + 4 * B * T, p0 + 4 * (B * T + B), _lib.stream_ptr())
+        ctx.save_for_backward(a, b, mask_u8, buf)
+        ctx.scale = scale
+        return buf[B * T + B].clone()
+
+    @staticmethod
+    def backward(ctx, g):
+        a, b, mask_u8, buf = ctx.saved_tensors
+        B, T, D = a.shape
+        p0 = buf.data_ptr()
+        g = g.to(device=a.device, dtype=torch.float32).contiguous()
+        da = torch.empty_like(a)
+        db = torch.empty_like(b)
+        with torch.cuda.device(a.device):
+            _lib.call("cfa_masked_pairwise_bwd", a.data_ptr(), b.data_ptr(), mask_u8.data_ptr(), B, T, D,
+                      _lib.DTYPE_CODE[a.dtype], ctx.scale, p0, p0 + 4 * (B * T + B), g.data_ptr(), da.data_ptr(),
+                      db.data_ptr(), _lib.stream_ptr())
+        return da, db, None, None
+
+
 class SPARCLoss(nn.Module):
     """SPARC loss (https://arxiv.org/abs/2401.09865), reference API: finetune/losses.py:136-264."""
 
@@ -270,9 +308,10 @@ class SPARCLoss(nn.Module):
         return _PairwiseFunction.apply(a, b, float(self.inverse_temperature), _NORM_EPS)
 
     def masked_pairwise_contrastive_loss(self, a: torch.Tensor, b: torch.Tensor, mask: torch.Tensor) -> torch.Tensor:
-        raise NotImplementedError(
-            "masked_pairwise_contrastive_loss is fused into SPARCLoss.forward (cfa_sparc_fwd/bwd); a standalone "
-            "[B,T,D]x[B,T,D] entry point is not exported yet")
+        """a, b: [B, T, D], mask: [B, T] -> masked token-level CE(sum over valid tokens) / (mask.sum() + 1e-8)."""
+        if mask.dtype not in (torch.bool, torch.uint8, torch.int8, torch.int16, torch.int32, torch.int64):
+            raise TypeError(f"mask must be bool or integer, got {mask.dtype}")
+        return _MaskedPairwiseFunction.apply(a, b, mask, float(self.inverse_temperature))
 
     def forward(self, v_patch_embed: torch.Tensor, l_token_embed: torch.Tensor,
                 language_mask: torch.Tensor) -> Dict[str, torch.Tensor]:

@@ -158,6 +158,19 @@ size_t cfa_sparc_scratch_bytes(int B, int P, int T, int backward);
 int cfa_sparc_max_patches(int T, int backward);
 
 /*
+ * SPARCLoss.masked_pairwise_contrastive_loss on its own (losses.py:165-197): a, b [B,T,D] in `dtype`, mask [B,T] bytes.
+ * One direction: rows of a against the columns of b of the same sample, target = same token index.
+ *   out2[0] = sum_b sum_{valid i} CE_i / n_valid,  out2[1] = n_valid = sum(mask) + 1e-8 (fp32);
+ *   lse_row [B,T] and out2 are what the backward needs; partial [B] is scratch.
+ * Backward: grad = DEVICE scalar d(loss); da, db [B,T,D] are written in `dtype`.  fp32 CUDA-core tiles (the fused
+ * tensor-core version of the same computation lives inside cfa_sparc_fwd / cfa_sparc_bwd).
+ */
+int cfa_masked_pairwise_fwd(const void* a, const void* b, const uint8_t* mask, int B, int T, int D, int dtype, float scale,
+                            float* lse_row, float* partial, float* out2, void* stream);
+int cfa_masked_pairwise_bwd(const void* a, const void* b, const uint8_t* mask, int B, int T, int D, int dtype, float scale,
+                            const float* lse_row, const float* out2, const float* grad, void* da, void* db, void* stream);
+
+/*
  * Scalar epilogue (losses.py:163,196,217,252-264): sums the per-row / per-sample partials and writes
  * out[0..6] = global_loss, local_loss, total_loss, loss_vl, loss_lv, loss_vl_local, loss_lv_local and
  * out[7] = n_valid (sum of mask).  global_sums: DEVICE [2] = sum_i CE_vl(i), sum_j CE_lv(j) over the GLOBAL

@@ -313,6 +313,42 @@ def sparc_backward(fwd: Dict[str, torch.Tensor], grads: Optional[Dict[str, float
     return dv, dl
 
 
+def masked_pairwise_forward(a: torch.Tensor, b: torch.Tensor, mask: torch.Tensor, s: float,
+                            mask_semantics: str = "truncate") -> Dict[str, torch.Tensor]:
+    """SPARCLoss.masked_pairwise_contrastive_loss restated (finetune/losses.py:165-197): a, b [B,T,D], mask [B,T].
+    "reference" semantics reproduce the NaN of the reference for padded masks; "truncate" skips masked tokens."""
+    T = a.shape[1]
+    ah, an = l2_normalize(a)                                             # losses.py:173-174
+    bh, bn = l2_normalize(b)
+    m2 = mask[:, :, None] & mask[:, None, :]                             # losses.py:177
+    L = torch.einsum("bid,bjd->bij", ah, bh) * s                         # losses.py:180
+    Lm = L.masked_fill(~m2, -float("inf"))                               # losses.py:186
+    lse = _lse(Lm, dim=2)
+    ar = torch.arange(T)
+    diag = Lm[:, ar, ar]
+    mf = mask.to(a.dtype)
+    if mask_semantics == "truncate":
+        ce = torch.where(mask, lse - diag, torch.zeros_like(diag))
+    else:
+        ce = (lse - diag) * mf                                           # losses.py:189-196
+    n_valid = (mask.sum() + NVALID_EPS).to(a.dtype)
+    return {"loss": ce.sum() / n_valid, "_cache": dict(ah=ah, an=an, bh=bh, bn=bn, Lm=Lm, lse=lse, m2=m2, mf=mf,
+                                                       n_valid=n_valid, s=s)}
+
+
+def masked_pairwise_backward(fwd: Dict[str, torch.Tensor], grad_out: float = 1.0):
+    c = fwd["_cache"]
+    T = c["Lm"].shape[1]
+    Pr = torch.where(c["m2"], torch.exp(c["Lm"] - c["lse"][:, :, None]), torch.zeros_like(c["Lm"]))
+    dL = Pr.clone()
+    ar = torch.arange(T)
+    dL[:, ar, ar] -= c["mf"]
+    dL = dL * (grad_out / c["n_valid"])
+    dah = c["s"] * torch.einsum("bij,bjd->bid", dL, c["bh"])
+    dbh = c["s"] * torch.einsum("bij,bid->bjd", dL, c["ah"])
+    return l2_normalize_bwd(c["ah"], c["an"], dah), l2_normalize_bwd(c["bh"], c["bn"], dbh)
+
+
 def sparc_reference_truncated(ref_loss_module, v, l, mask):
     """Per-sample-truncated evaluation of the *reference module* (used to pin the
     "truncate" semantics): local terms are evaluated on each sample's valid tokens only

@@ -104,6 +104,37 @@ def pairwise_case(ref_losses, name, B, D, s, seed):
     print("pairwise", name, float(loss))
 
 
+def masked_pairwise_case(ref_losses, name, B, T, D, s, seed):
+    """SPARCLoss.masked_pairwise_contrastive_loss alone (losses.py:165-197), all-True mask (the only case where the
+    reference is finite) plus the per-sample-truncated evaluation of a padded mask (pins the 'truncate' semantics)."""
+    g = torch.Generator().manual_seed(seed)
+    a = torch.randn(B, T, D, generator=g, dtype=torch.float64).requires_grad_(True)
+    b = torch.randn(B, T, D, generator=g, dtype=torch.float64).requires_grad_(True)
+    mod = ref_losses.SPARCLoss(cfg(0.5, 1.0, 1.0, s))
+    full = torch.ones(B, T, dtype=torch.bool)
+    loss = mod.masked_pairwise_contrastive_loss(a, b, full)
+    loss.backward()
+    out = dict(name=name, a=a.detach().float(), b=b.detach().float(), s=s, loss=loss.detach(), da=a.grad.clone(),
+               db=b.grad.clone())
+    # padded mask, truncated per sample: sum of per-sample (mean CE * count) / total count
+    lens = torch.randint(2, T + 1, (B,), generator=g)
+    lens[0] = T
+    mask = torch.arange(T)[None, :] < lens[:, None]
+    a2 = a.detach().clone().requires_grad_(True)
+    b2 = b.detach().clone().requires_grad_(True)
+    tot = 0.0
+    for i in range(B):
+        n = int(lens[i])
+        tot = tot + mod.masked_pairwise_contrastive_loss(a2[i:i + 1, :n], b2[i:i + 1, :n], torch.ones(1, n, dtype=torch.bool)) * n
+    n_valid = float(torch.tensor(int(lens.sum())) + 1e-8)
+    lt = tot / n_valid
+    lt.backward()
+    out.update(mask=mask, loss_trunc=lt.detach(), da_trunc=a2.grad.clone(), db_trunc=b2.grad.clone(),
+               ref_padded_is_nan=bool(torch.isnan(mod.masked_pairwise_contrastive_loss(a.detach(), b.detach(), mask))))
+    torch.save(out, os.path.join(HERE, f"maskedpair_{name}.pt"))
+    print("masked pairwise", name, float(loss), float(lt), "ref padded NaN:", out["ref_padded_is_nan"])
+
+
 def adamspd_case(ref_opt, name, sizes, steps, lr, betas, eps, wd, amsgrad, seed, with_pre=True, none_grad_idx=()):
     g = torch.Generator().manual_seed(seed)
     p0 = [torch.randn(*s, generator=g) * 0.02 for s in sizes]
@@ -131,6 +162,9 @@ def main():
     torch.manual_seed(0)
     torch.set_num_threads(4)
     ref_losses, ref_opt = import_reference()
+    if "--only-masked-pairwise" in sys.argv:
+        masked_pairwise_case(ref_losses, "b3_t20_d48", 3, 20, 48, 3.0, seed=12)
+        return
     # SPARC: thr = 1/P is well conditioned (SURVEY finding 2); one trainer-default case (thr=.5, s=.07)
     sparc_case(ref_losses, "b4_p50_d64_thrP", 4, 50, 77, 64, 1.0 / 50, 1.0, 1.0, 1.0, seed=1)
     sparc_case(ref_losses, "b3_p197_d32_thrP_w", 3, 197, 77, 32, 1.0 / 197, 0.7, 1.3, 2.5, seed=2)
@@ -141,6 +175,7 @@ def main():
     clip_case(ref_losses, "b16_d64", 16, 64, 0.07, seed=6)
     clip_case(ref_losses, "b5_d40_t1", 5, 40, 1.0, seed=7)
     pairwise_case(ref_losses, "b12_d32", 12, 32, 4.0, seed=8)
+    masked_pairwise_case(ref_losses, "b3_t20_d48", 3, 20, 48, 3.0, seed=12)
     sizes = [(1,), (7,), (33, 31), (4099,), (64, 64)]
     adamspd_case(ref_opt, "s20", sizes, 20, 2e-5, (0.9, 0.999), 1e-8, 0.1, False, seed=9)
     adamspd_case(ref_opt, "s12_ams_lr1e3", sizes, 12, 1e-3, (0.9, 0.98), 5e-6, 0.2, True, seed=10)

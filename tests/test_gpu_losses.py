@@ -141,6 +141,37 @@ def test_sparc_config4_bf16_vit_l14_336():
     assert rel_err(dl.float(), rl) <= 1e-3 + 2.0 ** -8
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_masked_pairwise_helper(dtype):
+    """SPARCLoss.masked_pairwise_contrastive_loss as a standalone call (losses.py:165-197) vs the reference fixture
+    (all-True mask, fp32) and vs the oracle (padded mask, larger shape, bf16 inputs)."""
+    from clip_finegrained_alignment_b200 import SPARCLoss
+    f = load_golden("maskedpair_b3_t20_d48.pt")
+    mod = SPARCLoss(cfg(0.5, 1.0, 1.0, f["s"]))
+    if dtype == torch.float32:
+        for mask, lk, ak, bk in ((torch.ones(3, 20, dtype=torch.bool), "loss", "da", "db"),
+                                 (f["mask"], "loss_trunc", "da_trunc", "db_trunc")):
+            a = f["a"].cuda().requires_grad_(True); b = f["b"].cuda().requires_grad_(True)
+            loss = mod.masked_pairwise_contrastive_loss(a, b, mask.cuda())
+            loss.backward()
+            assert abs(float(loss) - float(f[lk])) <= 1e-5 * max(1.0, abs(float(f[lk])))
+            assert_grad_close(a.grad, f[ak], 2e-5, ak)
+            assert_grad_close(b.grad, f[bk], 2e-5, bk)
+    g = torch.Generator().manual_seed(9)
+    B, T, D = 5, 77, 512
+    a0 = torch.randn(B, T, D, generator=g).to(dtype); b0 = torch.randn(B, T, D, generator=g).to(dtype)
+    mask = torch.ones(B, T, dtype=torch.bool); mask[2, 31:] = False; mask[4, 3:] = False
+    a = a0.cuda().requires_grad_(True); b = b0.cuda().requires_grad_(True)
+    loss = SPARCLoss(cfg(0.5, 1.0, 1.0, 7.0)).masked_pairwise_contrastive_loss(a, b, mask.cuda())
+    (2.5 * loss).backward()
+    fw = lo.masked_pairwise_forward(a0.double(), b0.double(), mask, 7.0)
+    da, db = lo.masked_pairwise_backward(fw, 2.5)
+    tol = 2e-5 if dtype == torch.float32 else 1e-3 + 2.0 ** -8
+    assert abs(float(loss) - float(fw["loss"])) <= (1e-5 if dtype == torch.float32 else 1e-4) * float(fw["loss"])
+    assert rel_err(a.grad.float(), da) <= tol and rel_err(b.grad.float(), db) <= tol
+    assert a.grad.dtype == dtype
+
+
 def test_sparc_padded_mask_truncate_semantics():
     f = load_golden("sparc_masked_b4_p50_d64.pt")
     out, dv, dl = run_sparc(f["v"], f["l"], f["mask"], cfg(f["thr"], 1.0, 1.0, f["s"]))

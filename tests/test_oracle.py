@@ -123,6 +123,25 @@ def test_pairwise_oracle():
     assert rel_err(db, f["db"]) < 1e-5
 
 
+def test_masked_pairwise_oracle():
+    """masked_pairwise_contrastive_loss (losses.py:165-197) vs the reference: all-True mask, and the padded mask under
+    'truncate' semantics = the reference evaluated per sample on its valid tokens (the reference itself is NaN there)."""
+    f = load_golden("maskedpair_b3_t20_d48.pt")
+    a, b = f["a"].double(), f["b"].double()
+    full = torch.ones(a.shape[:2], dtype=torch.bool)
+    for sem in ("reference", "truncate"):
+        fw = lo.masked_pairwise_forward(a, b, full, f["s"], mask_semantics=sem)
+        assert abs(float(fw["loss"]) - float(f["loss"])) < 1e-6
+        da, db = lo.masked_pairwise_backward(fw)
+        assert rel_err(da, f["da"]) < 1e-5 and rel_err(db, f["db"]) < 1e-5
+    assert f["ref_padded_is_nan"]
+    assert torch.isnan(lo.masked_pairwise_forward(a, b, f["mask"], f["s"], mask_semantics="reference")["loss"])
+    fw = lo.masked_pairwise_forward(a, b, f["mask"], f["s"])
+    assert abs(float(fw["loss"]) - float(f["loss_trunc"])) < 1e-6
+    da, db = lo.masked_pairwise_backward(fw)
+    assert rel_err(da, f["da_trunc"]) < 1e-5 and rel_err(db, f["db_trunc"]) < 1e-5
+
+
 def test_gathered_infonce_equals_concatenated():
     """SURVEY §8e oracle: N ranks with gathered columns == single process on the concatenated batch."""
     g = torch.Generator().manual_seed(5)
