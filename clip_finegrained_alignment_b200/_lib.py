@@ -39,9 +39,9 @@ SIGNATURES = {
     "cfa_adamspd_step": (C.c_int, [_vp, _i, _vp, _i, _vp, _vp, _i, _i, _vp]),
     "cfa_global_infonce_workspace_bytes": (_sz, [_i, _i, _i]),
     "cfa_global_infonce_fwd": (C.c_int, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _f, _vp, _vp, _vp, _vp, _vp, _i, _f, _f,
-                                         _vp, _vp, _sz, _i, _vp]),
+                                         _vp, _vp, _sz, _i, _i, _vp]),
     "cfa_global_infonce_bwd": (C.c_int, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
-                                         _sz, _i, _vp]),
+                                         _sz, _i, _i, _vp]),
     "cfa_global_infonce_path": (C.c_int, [_i, _i, _i, _i]),
     "cfa_sparc_fwd": (C.c_int, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                 _vp, _vp, _vp, _sz, _i, _vp]),
@@ -53,7 +53,7 @@ SIGNATURES = {
     "cfa_sparc_path": (C.c_int, [_i, _i, _i, _i, _i]),
     "cfa_sparc_bwd_path": (C.c_int, [_i, _i, _i, _i, _i]),
     "cfa_sparc_max_patches": (C.c_int, [_i, _i]),
-    "cfa_sparc_finalize": (C.c_int, [_vp, _i, _vp, _vp, _i, _i, _f, _f, _vp, _vp]),
+    "cfa_sparc_finalize": (C.c_int, [_vp, _i, _vp, _vp, _i, _i, _f, _f, _vp, _i, _vp]),
     "cfa_sparc_coef": (C.c_int, [_vp, _f, _f, _i, _vp, _vp, _vp]),
     "cfa_sparc_coef_ptrs": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _f, _f, _i, _vp, _vp, _vp]),
     "cfa_debug_set_profile_buffer": (C.c_int, [_vp]),

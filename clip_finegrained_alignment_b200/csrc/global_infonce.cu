@@ -273,9 +273,9 @@ bool global_tc_supported(int B, int Bg, int D);
 size_t global_tc_workspace_bytes(int B, int Bg, int D);
 int global_tc_fwd(const float* a_loc, const float* b_loc, const float* a_all, const float* b_all, int B, int Bg, int D,
                   int col_offset, float scale, float eps, float* norms2, float** part_m, float** part_l, float** diag,
-                  int* nsplit, void* ws, cudaStream_t st);
+                  int* nsplit, void* ws, int gathered_ranks, cudaStream_t st);
 int global_tc_bwd(int B, int Bg, int D, int col_offset, float scale, const float* lse_loc2, const float* lse_all2,
-                  const float* coef2, float** dpart, int* nsplit, void* ws, cudaStream_t st);
+                  const float* coef2, float** dpart, int* nsplit, void* ws, int gathered_ranks, cudaStream_t st);
 
 // low-latency symmetric CUDA-core implementation for the rank-local case (global_infonce_sym.cu)
 bool global_sym_supported(int B, int Bg, int D);
@@ -313,8 +313,9 @@ extern "C" int cfa_global_infonce_fwd(const float* a_loc, const float* b_loc, co
                                       int Bg, int D, int col_offset, float scale, float eps, float* lse2, float* norms2,
                                       float* sums2, const float* local_partial, const uint8_t* mask, int T, float gw,
                                       float lw, float* out8, void* workspace, size_t workspace_bytes, int path,
-                                      void* stream) {
+                                      int gathered_ranks, void* stream) {
   if (B <= 0 || Bg <= 0 || D <= 0 || col_offset < 0 || col_offset + B > Bg) return CFA_ERR_BAD_ARG;
+  if (gathered_ranks > 1 && (gathered_ranks * B != Bg || !use_tc(B, Bg, D, path))) return CFA_ERR_UNSUPPORTED;
   if (!workspace || workspace_bytes < cfa_global_infonce_workspace_bytes(B, Bg, D)) return CFA_ERR_WORKSPACE;
   if (out8 && (Bg != B || !local_partial || !mask)) return CFA_ERR_BAD_ARG;   // fused scalar epilogue: single process only
   if (path == 2 && !global_tc_supported(B, Bg, D)) return CFA_ERR_UNSUPPORTED;
@@ -331,7 +332,7 @@ extern "C" int cfa_global_infonce_fwd(const float* a_loc, const float* b_loc, co
     float *pm, *pl, *dg;
     int nsp;
     const int rc = global_tc_fwd(a_loc, b_loc, a_all, b_all, B, Bg, D, col_offset, scale, eps, norms2, &pm, &pl, &dg, &nsp,
-                                 workspace, (cudaStream_t)stream);
+                                 workspace, gathered_ranks, (cudaStream_t)stream);
     if (rc != CFA_OK) return rc;
     global_combine_kernel<<<1, kNT, 0, (cudaStream_t)stream>>>(pm, pl, dg, B, nsp, lse2, sums2, Bg, local_partial, mask, T, gw,
                                                                lw, out8);
@@ -359,8 +360,9 @@ extern "C" int cfa_global_infonce_fwd(const float* a_loc, const float* b_loc, co
 extern "C" int cfa_global_infonce_bwd(const float* a_loc, const float* b_loc, const float* a_all, const float* b_all, int B,
                                       int Bg, int D, int col_offset, float scale, float eps, const float* lse_loc2,
                                       const float* lse_all2, const float* norms2, const float* coef2, float* da, float* db,
-                                      void* workspace, size_t workspace_bytes, int path, void* stream) {
+                                      void* workspace, size_t workspace_bytes, int path, int gathered_ranks, void* stream) {
   if (B <= 0 || Bg <= 0 || D <= 0 || D > 1024 || col_offset < 0 || col_offset + B > Bg) return CFA_ERR_BAD_ARG;
+  if (gathered_ranks > 1 && (gathered_ranks * B != Bg || !use_tc(B, Bg, D, path))) return CFA_ERR_UNSUPPORTED;
   if (!workspace || workspace_bytes < cfa_global_infonce_workspace_bytes(B, Bg, D)) return CFA_ERR_WORKSPACE;
   if (path == 2 && !global_tc_supported(B, Bg, D)) return CFA_ERR_UNSUPPORTED;
   if (use_sym(B, Bg, D, path)) {
@@ -375,7 +377,7 @@ extern "C" int cfa_global_infonce_bwd(const float* a_loc, const float* b_loc, co
     float* dpart;
     int nsp;
     const int rc = global_tc_bwd(B, Bg, D, col_offset, scale, lse_loc2, lse_all2, coef2, &dpart, &nsp, workspace,
-                                 (cudaStream_t)stream);
+                                 gathered_ranks, (cudaStream_t)stream);
     if (rc != CFA_OK) return rc;
     global_norm_bwd_kernel<<<dim3(B, 2), 128, 0, (cudaStream_t)stream>>>(a_loc, b_loc, norms2, dpart, nsp, B, D, da, db);
     return launch_status();

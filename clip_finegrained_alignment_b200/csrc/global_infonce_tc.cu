@@ -25,10 +25,12 @@ constexpr int kGtStages = 2;
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 gt_split_kernel(const float* __restrict__ a, const float* __restrict__ b, int rows, int D, float eps,
-                bf16* __restrict__ out, float* __restrict__ norms /* [2][rows] or NULL */) {
+                bf16* __restrict__ out, float* __restrict__ norms /* [2][rows] or NULL */, int rank_rows, size_t rank_stride) {
+  // rank_rows / rank_stride: global row g = r * rank_rows + i lives at base + r * rank_stride + i * D (the raw output of
+  // an all-gather of per-rank [2][B][D] blocks); rank_rows == rows, rank_stride == 0 for a plain [rows][D] matrix
   const int r = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31, which = blockIdx.y;
   if (r >= rows) return;
-  const float* x = (which ? b : a) + (size_t)r * D;
+  const float* x = (which ? b : a) + (size_t)(r / rank_rows) * rank_stride + (size_t)(r % rank_rows) * D;
   float ss = 0.f;
   for (int d = lane; d < D; d += 32) ss = fmaf(x[d], x[d], ss);
   ss = warp_sum(ss);
@@ -51,10 +53,11 @@ struct GtParams {
   float* part_m; float* part_l; float* diag;
   // backward
   const float* lse_loc; const float* lse_all; const float* coef; float* dpart;
+  int lse_rank_rows, lse_rank_stride;   // > 0: lse_all is the raw all-gather of per-rank [lse_a | lse_b | 2 sums] packs
   volatile int* dbg;      // optional host-mapped progress markers (cfa_debug_set_marker_buffer), [cta][8 warps]
 };
 static int* g_gt_dbg = nullptr;
-#define GT_MARK(v) do { if (p.dbg && lane == 0) { p.dbg[(((blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 8 + warp)] = (v); __threadfence_system(); } } while (0)
+#define GT_MARK(v) do { if (p.dbg && lane == 0) { p.dbg[((((blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 8 + warp) * 32) + (v)] = (int)(clock64() - gt_t0); } } while (0)
 
 
 struct GtSmem {
@@ -192,9 +195,11 @@ gt_bwd_kernel(const __grid_constant__ CUtensorMap tmLoc, const __grid_constant__
   uint64_t* full = bars; uint64_t* empty = bars + 2; uint64_t* s_full = bars + 4; uint64_t* ds_ready = bars + 5;
   uint64_t* ofull = bars + 6; uint64_t* oempty = bars + 8; uint64_t* o_done = bars + 10;
   uint32_t* tmem_slot = (uint32_t*)(bars + 11);
+  float* lse_s = (float*)(bars + 16);                  // [kGtN] the other direction's LSE of this tile's columns
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int dir = blockIdx.z, row0 = blockIdx.x * kGtM, ct = blockIdx.y, col0 = ct * kGtN, nct = gridDim.y;
   const int D = p.D, KB = D / 64;
+  const long long gt_t0 = clock64();
   const int ra = dir ? 2 : 0, ca = dir ? 0 : 2;
   if (threadIdx.x == 0) {
     for (int i = 0; i < 2; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, 1); mbar_init(ofull + i, 1); mbar_init(oempty + i, 1); }
@@ -262,7 +267,13 @@ gt_bwd_kernel(const __grid_constant__ CUtensorMap tmLoc, const __grid_constant__
     const uint32_t trow = tmem + ((uint32_t)(32 * q) << 16);
     const float c_self = p.coef[dir], c_other = p.coef[1 - dir];
     const float lse_self = (grow < p.B) ? p.lse_loc[(size_t)dir * p.B + grow] : 0.f;
-    const float* lse_other = p.lse_all + (size_t)(1 - dir) * p.Bg;
+    const float* lse_other = p.lse_all + (p.lse_rank_rows ? (size_t)(1 - dir) * p.lse_rank_rows : (size_t)(1 - dir) * p.Bg);
+    {
+      // one coalesced load per thread now (overlaps phase A) instead of 128 dependent global loads inside the dS loop
+      const int gcol = col0 + row;
+      const int gidx = p.lse_rank_rows ? (gcol / p.lse_rank_rows) * p.lse_rank_stride + gcol % p.lse_rank_rows : gcol;
+      lse_s[row] = (gcol < p.Bg) ? __ldg(lse_other + gidx) : 0.f;
+    }
     // ---- phase B: dS (hi/lo) -> smem (A operand, K = 128 columns of this tile)
     mbar_wait(s_full, 0);
     tc_fence_after();
@@ -282,7 +293,7 @@ gt_bwd_kernel(const __grid_constant__ CUtensorMap tmLoc, const __grid_constant__
         const int gcol = col0 + 32 * c + j;
         const bool on = grow < p.B && gcol < p.Bg;
         const float s = xs[c][j] * p.scale;
-        const float lo_ = on ? __ldg(lse_other + gcol) : 0.f;
+        const float lo_ = lse_s[32 * c + j];
         float g = c_self * __expf(fminf(s - lse_self, 0.f)) + c_other * __expf(fminf(s - lo_, 0.f));
         g -= (gcol == p.col_offset + grow) ? (c_self + c_other) : 0.f;
         xs[c][j] = on ? g : 0.f;
@@ -305,17 +316,25 @@ gt_bwd_kernel(const __grid_constant__ CUtensorMap tmLoc, const __grid_constant__
     tc_fence_after();
     GT_MARK(14);
     const int dcols = D;
-    // tcgen05.ld is warp-collective (.sync.aligned): every lane loads, only rows < B store
-    float* dst = p.dpart + (((size_t)dir * nct + ct) * p.B + (grow < p.B ? grow : 0)) * D;
+    // TMEM -> registers -> per-warp smem transpose tile -> global: every store instruction writes one 128-byte row
+    // segment (lane = column) instead of 32 scattered ones (lane = row).  tcgen05.ld is warp-collective: all lanes load.
+    float* tile = reinterpret_cast<float*>(ostg) + (warp - 2) * (32 * 36);       // phase-C operand stages are dead now
+    const int rr = lane >> 3, c4 = (lane & 7) * 4;
     for (int c0 = 0; c0 < dcols; c0 += 32) {
       float x[32];
       tmem_ld32(trow + c0, x);
       tmem_ld_wait();
-      if (grow < p.B) {
 #pragma unroll
-        for (int j = 0; j < 32; j += 4)
-          *reinterpret_cast<float4*>(dst + c0 + j) = make_float4(x[j] * p.scale, x[j + 1] * p.scale, x[j + 2] * p.scale, x[j + 3] * p.scale);
+      for (int j = 0; j < 32; j += 4)
+        *reinterpret_cast<float4*>(tile + lane * 36 + j) = make_float4(x[j] * p.scale, x[j + 1] * p.scale, x[j + 2] * p.scale, x[j + 3] * p.scale);
+      __syncwarp();
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {                   // one instruction = 4 rows x 128 contiguous bytes
+        const int r = it * 4 + rr, gr = row0 + 32 * q + r;
+        const float4 v4 = *reinterpret_cast<const float4*>(tile + r * 36 + c4);
+        if (gr < p.B) *reinterpret_cast<float4*>(p.dpart + (((size_t)dir * nct + ct) * p.B + gr) * D + c0 + c4) = v4;
       }
+      __syncwarp();
     }
     tc_fence_before();
     GT_MARK(15);
@@ -361,10 +380,13 @@ static int gt_maps(const GtHost& h, int B, int Bg, int D, CUtensorMap* tmLoc, CU
 
 int global_tc_fwd(const float* a_loc, const float* b_loc, const float* a_all, const float* b_all, int B, int Bg, int D,
                   int col_offset, float scale, float eps, float* norms2, float** part_m, float** part_l, float** diag,
-                  int* nsplit, void* ws, cudaStream_t st) {
+                  int* nsplit, void* ws, int gathered_ranks, cudaStream_t st) {
   const GtHost h = gt_carve(ws, B, Bg, D);
-  gt_split_kernel<<<dim3((Bg + 7) / 8, 2), 256, 0, st>>>(a_all, b_all, Bg, D, eps, h.all_split, nullptr);
-  gt_split_kernel<<<dim3((B + 7) / 8, 2), 256, 0, st>>>(a_loc, b_loc, B, D, eps, h.loc_split, norms2);
+  if (gathered_ranks > 1)
+    gt_split_kernel<<<dim3((Bg + 7) / 8, 2), 256, 0, st>>>(a_all, b_all, Bg, D, eps, h.all_split, nullptr, B, (size_t)2 * B * D);
+  else
+    gt_split_kernel<<<dim3((Bg + 7) / 8, 2), 256, 0, st>>>(a_all, b_all, Bg, D, eps, h.all_split, nullptr, Bg, 0);
+  gt_split_kernel<<<dim3((B + 7) / 8, 2), 256, 0, st>>>(a_loc, b_loc, B, D, eps, h.loc_split, norms2, B, 0);
   CFA_CUDA_TRY(cudaGetLastError());
   CUtensorMap tmLoc, tmAll;
   int rc = gt_maps(h, B, Bg, D, &tmLoc, &tmAll);
@@ -372,7 +394,7 @@ int global_tc_fwd(const float* a_loc, const float* b_loc, const float* a_all, co
   GtParams p{};
   p.B = B; p.Bg = Bg; p.D = D; p.col_offset = col_offset; p.scale = scale;
   p.part_m = h.scratch; p.part_l = p.part_m + (size_t)2 * h.nct * B; p.diag = p.part_l + (size_t)2 * h.nct * B;
-  const size_t smem = kGtStages * kGtStage + 256 + 1024;
+  const size_t smem = kGtStages * kGtStage + 1024 + 1024;
   static bool attr = false;
   if (!attr) { CFA_CUDA_TRY(cudaFuncSetAttribute(gt_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
   gt_fwd_kernel<<<dim3((B + kGtM - 1) / kGtM, h.nct, 2), kGtThreads, smem, st>>>(tmLoc, tmAll, p);
@@ -381,7 +403,7 @@ int global_tc_fwd(const float* a_loc, const float* b_loc, const float* a_all, co
 }
 
 int global_tc_bwd(int B, int Bg, int D, int col_offset, float scale, const float* lse_loc2, const float* lse_all2,
-                  const float* coef2, float** dpart, int* nsplit, void* ws, cudaStream_t st) {
+                  const float* coef2, float** dpart, int* nsplit, void* ws, int gathered_ranks, cudaStream_t st) {
   // the split operands written by the forward are still in the workspace
   const GtHost h = gt_carve(ws, B, Bg, D);
   CUtensorMap tmLoc, tmAll;
@@ -390,7 +412,8 @@ int global_tc_bwd(int B, int Bg, int D, int col_offset, float scale, const float
   GtParams p{};
   p.B = B; p.Bg = Bg; p.D = D; p.col_offset = col_offset; p.scale = scale;
   p.lse_loc = lse_loc2; p.lse_all = lse_all2; p.coef = coef2; p.dpart = h.scratch; p.dbg = g_gt_dbg;
-  const size_t smem = kGtStages * kGtStage + 256 + 1024;
+  p.lse_rank_rows = gathered_ranks > 1 ? B : 0; p.lse_rank_stride = gathered_ranks > 1 ? 2 * B + 2 : 0;
+  const size_t smem = kGtStages * kGtStage + 1024 + 1024;
   static bool attr = false;
   if (!attr) { CFA_CUDA_TRY(cudaFuncSetAttribute(gt_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
   gt_bwd_kernel<<<dim3((B + kGtM - 1) / kGtM, h.nct, 2), kGtThreads, smem, st>>>(tmLoc, tmAll, p);

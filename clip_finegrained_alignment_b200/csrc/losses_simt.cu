@@ -505,7 +505,7 @@ __device__ __forceinline__ float block_sum_256(float x, float* red) {
 
 __global__ void __launch_bounds__(kNT)
 sparc_finalize_kernel(const float* global_sums, int global_batch, const float* local_partial, const uint8_t* mask,
-                      int B, int Tn, float gw, float lw, float* out8) {
+                      int B, int Tn, float gw, float lw, float* out8, int gathered_ranks) {
   __shared__ float red[8];
   float nv = 0.f, a = 0.f, c = 0.f;
   for (int i = threadIdx.x; i < B * Tn; i += kNT) nv += mask[i] ? 1.f : 0.f;
@@ -516,8 +516,13 @@ sparc_finalize_kernel(const float* global_sums, int global_batch, const float* l
   if (threadIdx.x == 0) {
     // mask.sum() + 1e-8 is evaluated in fp32 by the reference: the eps vanishes for counts >= 1 (losses.py:196)
     const float n_valid = nv + 1e-8f;
-    const float vl = global_sums[0] / (float)global_batch;        // losses.py:163
-    const float lv = global_sums[1] / (float)global_batch;
+    float sa = global_sums[0], sb = global_sums[1];
+    if (gathered_ranks > 1) {                                     // raw all-gather of per-rank [lse_a | lse_b | sum_a, sum_b]
+      sa = 0.f; sb = 0.f;
+      for (int r = 0; r < gathered_ranks; ++r) { sa += global_sums[(size_t)r * (2 * B + 2) + 2 * B]; sb += global_sums[(size_t)r * (2 * B + 2) + 2 * B + 1]; }
+    }
+    const float vl = sa / (float)global_batch;                    // losses.py:163
+    const float lv = sb / (float)global_batch;
     const float vll = a / n_valid, lvl = c / n_valid;             // losses.py:196
     const float g = 0.5f * (vl + lv), lo = 0.5f * (vll + lvl);    // losses.py:217,252
     out8[0] = g; out8[1] = lo; out8[2] = gw * g + lw * lo;        // losses.py:254
@@ -651,10 +656,11 @@ int cfa::sparc_bwd_simt(const void* v, const void* l, const uint8_t* mask, int B
 }
 
 extern "C" int cfa_sparc_finalize(const float* global_sums, int global_batch, const float* local_partial,
-                                  const uint8_t* mask, int B, int T, float gw, float lw, float* out8, void* stream) {
+                                  const uint8_t* mask, int B, int T, float gw, float lw, float* out8, int gathered_ranks,
+                                  void* stream) {
   if (B <= 0 || T <= 0 || global_batch <= 0) return CFA_ERR_BAD_ARG;
   sparc_finalize_kernel<<<1, kNT, 0, (cudaStream_t)stream>>>(global_sums, global_batch, local_partial, mask, B, T, gw,
-                                                             lw, out8);
+                                                             lw, out8, gathered_ranks);
   return launch_status();
 }
 

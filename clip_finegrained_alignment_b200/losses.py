@@ -47,27 +47,34 @@ def _dist_ctx(group, gather: bool):
     return dist.get_world_size(group), dist.get_rank(group), group
 
 
-def _gather_embeddings(ab: torch.Tensor, world: int, group):
-    """Collective 1 of 2: all-gather of the [2, B, D] (image | text) local rows -> ([Bg, D], [Bg, D]) with
-    rank-major global row order.  NCCL over NVLink on the GPU box; gloo on CPU in tests/test_dist_gloo.py."""
+def _gather_embeddings(ab: torch.Tensor, world: int, group, raw: bool):
+    """Collective 1 of 2: all-gather of the [2, B, D] (image | text) local rows.  raw=True (tensor-core path): returns the
+    NCCL output [world, 2, B, D] untouched — the kernels index it as it is, no re-layout launch; raw=False: two
+    contiguous [Bg, D] matrices in rank-major global row order.  NCCL over NVLink on the GPU box; gloo on CPU in
+    tests/test_dist_gloo.py."""
     if world == 1:
         return ab[0], ab[1]
     import torch.distributed as dist
     _, B, D = ab.shape
     gathered = torch.empty(world * 2, B, D, dtype=ab.dtype, device=ab.device)       # concatenated along dim 0
     dist.all_gather_into_tensor(gathered, ab.contiguous(), group=group)
+    if raw:
+        return gathered[0], gathered[1]            # rank 0's image / text blocks; rank r's sit 2*B*D*r elements further
     ab_all = gathered.view(world, 2, B, D).permute(1, 0, 2, 3).reshape(2, world * B, D).contiguous()
     return ab_all[0], ab_all[1]
 
 
-def _gather_lse_and_sums(pack: torch.Tensor, B: int, world: int, group):
-    """Collective 2 of 2: all-gather of [lse_a | lse_b | sum CE_a, sum CE_b] (2B+2 floats per rank) ->
+def _gather_lse_and_sums(pack: torch.Tensor, B: int, world: int, group, raw: bool):
+    """Collective 2 of 2: all-gather of [lse_a | lse_b | sum CE_a, sum CE_b] (2B+2 floats per rank).  raw=True: returns
+    the gathered [world, 2B+2] buffer twice (the kernels read lse and sums straight out of it); raw=False:
     (lse_all [2, Bg] rank-major, sums2 [2] over the global batch).  The backward needs nothing else."""
     if world == 1:
         return pack[:2 * B].view(2, B), pack[2 * B:]
     import torch.distributed as dist
     g = torch.empty(world * (2 * B + 2), dtype=pack.dtype, device=pack.device)
     dist.all_gather_into_tensor(g, pack.contiguous(), group=group)
+    if raw:
+        return g, g
     g = g.view(world, 2 * B + 2)
     sums2 = g[:, 2 * B:].sum(dim=0)
     lse_all = g[:, :2 * B].view(world, 2, B).permute(1, 0, 2).reshape(2, world * B).contiguous()
@@ -76,10 +83,10 @@ def _gather_lse_and_sums(pack: torch.Tensor, B: int, world: int, group):
 
 class _GlobalState:
     __slots__ = ("a", "b", "a_all", "b_all", "lse2", "lse_all", "norms2", "off", "world", "group", "scale", "eps", "Bg", "ws",
-                 "path")
+                 "path", "ranks")
 
 
-def _global_forward(ab, scale, eps, world, rank, group, fused=None, path=0):
+def _global_forward(ab, scale, eps, world, rank, group, fused=None, path=0, raw_sums=False):
     """ab: local RAW fp32 [2, B, D] (image rows, text rows).  Returns (state, sums2) with sums2 = (sum_i CE_a,
     sum_j CE_b) over the GLOBAL batch.  Two collectives per step when world > 1: one all-gather of the embeddings
     and one all-gather of [lse | CE sums] (which also serves the backward, so the backward has no collective).
@@ -91,7 +98,10 @@ def _global_forward(ab, scale, eps, world, rank, group, fused=None, path=0):
     st.world, st.group, st.scale, st.eps, st.path = world, group, scale, eps, path
     st.off, st.Bg = rank * B, world * B
     st.a, st.b = ab[0], ab[1]
-    st.a_all, st.b_all = _gather_embeddings(ab, world, group)
+    # raw all-gather buffers are consumed as they are when the tensor-core kernels run (cfa_global_infonce_path == 2)
+    raw = world > 1 and ab.is_cuda and _L.cfa_global_infonce_path(B, world * B, D, path) == 2
+    st.ranks = world if raw else 0
+    st.a_all, st.b_all = _gather_embeddings(ab, world, group, raw)
     # one allocation: [lse_a | lse_b | sum CE_a, sum CE_b] (= one collective message) | norms2 | kernel workspace
     ws_bytes = _L.cfa_global_infonce_workspace_bytes(B, st.Bg, D)
     nf = 4 * B + 4
@@ -105,13 +115,16 @@ def _global_forward(ab, scale, eps, world, rank, group, fused=None, path=0):
         part, mask_u8, T, gw, lw, out8 = fused
         _lib.call("cfa_global_infonce_fwd", st.a.data_ptr(), st.b.data_ptr(), st.a_all.data_ptr(), st.b_all.data_ptr(), B,
                   st.Bg, D, st.off, scale, eps, st.lse2.data_ptr(), st.norms2.data_ptr(), sums2.data_ptr(), part.data_ptr(),
-                  mask_u8.data_ptr(), T, gw, lw, out8.data_ptr(), st.ws.data_ptr(), st.ws.numel() * 4, path, _lib.stream_ptr())
+                  mask_u8.data_ptr(), T, gw, lw, out8.data_ptr(), st.ws.data_ptr(), st.ws.numel() * 4, path, 0,
+                  _lib.stream_ptr())
         st.lse_all = st.lse2
     else:
         _lib.call("cfa_global_infonce_fwd", st.a.data_ptr(), st.b.data_ptr(), st.a_all.data_ptr(), st.b_all.data_ptr(), B,
                   st.Bg, D, st.off, scale, eps, st.lse2.data_ptr(), st.norms2.data_ptr(), sums2.data_ptr(), 0, 0, 0, 0.0,
-                  0.0, 0, st.ws.data_ptr(), st.ws.numel() * 4, path, _lib.stream_ptr())
-        st.lse_all, sums2 = _gather_lse_and_sums(pack, B, world, group)
+                  0.0, 0, st.ws.data_ptr(), st.ws.numel() * 4, path, st.ranks, _lib.stream_ptr())
+        st.lse_all, sums2 = _gather_lse_and_sums(pack, B, world, group, raw)
+        if raw and not raw_sums:                       # caller wants the two global CE sums as a [2] tensor
+            sums2 = sums2.view(world, 2 * B + 2)[:, 2 * B:].sum(dim=0)
     return st, sums2
 
 
@@ -123,7 +136,7 @@ def _global_backward(st: _GlobalState, coef2: torch.Tensor):
     _lib.call("cfa_global_infonce_bwd", st.a.data_ptr(), st.b.data_ptr(), st.a_all.data_ptr(), st.b_all.data_ptr(), B,
               st.Bg, D, st.off, st.scale, st.eps, st.lse2.data_ptr(), st.lse_all.data_ptr(), st.norms2.data_ptr(),
               coef2.data_ptr(), dab.data_ptr(), dab.data_ptr() + 4 * B * D, st.ws.data_ptr(), st.ws.numel() * 4,
-              st.path, _lib.stream_ptr())
+              st.path, st.ranks, _lib.stream_ptr())
     return dab[0], dab[1]
 
 
@@ -180,10 +193,10 @@ class _SparcFunction(torch.autograd.Function):
             world, rank, group = _dist_ctx(group, gather)
             gpath = 1 if (v.dtype == torch.float32 or path == 1) else 0      # fp32 inputs keep the fp32-exact global kernels
             gst, sums = _global_forward(pooled, scale, _NORM_EPS, world, rank, group,
-                                        fused=(part_t, mask_u8, T, gw, lw, out8), path=gpath)
+                                        fused=(part_t, mask_u8, T, gw, lw, out8), path=gpath, raw_sums=True)
             if world > 1:       # scalar epilogue after the cross-rank gather of the CE sums
                 _lib.call("cfa_sparc_finalize", sums.data_ptr(), gst.Bg, ptr[4], mask_u8.data_ptr(), B, T, gw, lw, ptr[1],
-                          _lib.stream_ptr())
+                          gst.ranks, _lib.stream_ptr())
         ctx.save_for_backward(v, l, mask_u8, blk)
         ctx.gst = gst
         ctx.hp = (thr, gw, lw, scale, code, path, ptr, gq)

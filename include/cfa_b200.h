@@ -100,11 +100,17 @@ size_t cfa_global_infonce_workspace_bytes(int B, int Bg, int D);
 int cfa_global_infonce_fwd(const float* a_loc, const float* b_loc, const float* a_all, const float* b_all, int B, int Bg,
                            int D, int col_offset, float scale, float eps, float* lse2, float* norms2, float* sums2,
                            const float* local_partial, const uint8_t* mask, int T, float gw, float lw, float* out8,
-                           void* workspace, size_t workspace_bytes, int path, void* stream);
+                           void* workspace, size_t workspace_bytes, int path, int gathered_ranks, void* stream);
 int cfa_global_infonce_bwd(const float* a_loc, const float* b_loc, const float* a_all, const float* b_all, int B, int Bg,
                            int D, int col_offset, float scale, float eps, const float* lse_loc2, const float* lse_all2,
                            const float* norms2, const float* coef2, float* da, float* db, void* workspace,
-                           size_t workspace_bytes, int path, void* stream);
+                           size_t workspace_bytes, int path, int gathered_ranks, void* stream);
+/* gathered_ranks > 1 (tensor-core path only): the "all" arrays are the RAW outputs of the two NCCL all-gathers, so no
+ * re-layout kernel runs between the collective and the loss:
+ *   forward : a_all / b_all point at rank 0's image / text block inside the gathered [ranks][2][B][D] buffer
+ *             (global row r*B + i of a_all lives at a_all + r*2*B*D + i*D);
+ *   backward: lse_all2 is the gathered [ranks][2B+2] buffer of per-rank packs [lse_a (B) | lse_b (B) | sum CE_a, sum CE_b].
+ * gathered_ranks <= 1: plain [Bg][D] / [2][Bg] arrays. */
 /* path: 0 = auto (rank-local problems, Bg == B <= 512: low-latency symmetric fp32 tiles, one logits tile serving both
  * directions; otherwise tcgen05 logits tiles with bf16 hi/lo-split normalised operands when D % 64 == 0 and D <= 512),
  * 1 = fp32-exact CUDA-core tiles, 2 = tensor cores or CFA_ERR_UNSUPPORTED.  cfa_global_infonce_path reports what a
@@ -177,7 +183,8 @@ int cfa_masked_pairwise_bwd(const void* a, const void* b, const uint8_t* mask, i
  * batch (after the cross-rank all-reduce of cfa_global_infonce_fwd's sums2 when distributed).
  */
 int cfa_sparc_finalize(const float* global_sums, int global_batch, const float* local_partial,
-                       const uint8_t* mask, int B, int T, float gw, float lw, float* out8, void* stream);
+                       const uint8_t* mask, int B, int T, float gw, float lw, float* out8, int gathered_ranks, void* stream);
+/* gathered_ranks > 1: global_sums is the gathered [ranks][2B+2] pack buffer above; the two CE sums are added over ranks. */
 
 /*
  * Upstream gradient of the 7 outputs -> kernel coefficients (device side, no sync).

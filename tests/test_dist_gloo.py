@@ -38,12 +38,23 @@ def _worker(rank, world, port, q):
         w, r, grp = L._dist_ctx(None, True)
         assert (w, r) == (world, rank)
         assert L._dist_ctx(None, False) == (1, 0, None)
-        a_all, b_all = L._gather_embeddings(torch.stack([a, b]), w, grp)
+        a_all, b_all = L._gather_embeddings(torch.stack([a, b]), w, grp, False)
         assert torch.equal(a_all, a_full) and torch.equal(b_all, b_full)
+        # raw layout handed to the tensor-core kernels: the untouched collective output [world, 2, B, D]
+        ra, rb = L._gather_embeddings(torch.stack([a, b]), w, grp, True)
+        raw4 = ra._base.view(world, 2, B, D)
+        assert ra.data_ptr() == raw4.data_ptr() and rb.data_ptr() == raw4[0, 1].data_ptr()
+        assert all(torch.equal(raw4[k, 0], a_full[k * B:(k + 1) * B]) and torch.equal(raw4[k, 1], b_full[k * B:(k + 1) * B])
+                   for k in range(world))
         # per-rank "kernel" (oracle stand-in): local rows vs global columns, both directions
         fa, fb, bwd = lo.gathered_infonce_rank(a, b, a_all, b_all, rank, s, 0.5, 0.5)
         pack = torch.cat([fa["lse"], fb["lse"], torch.stack([fa["loss_sum"], fb["loss_sum"]])])   # kernel's [lse | sums]
-        lse_all, sums = L._gather_lse_and_sums(pack, B, w, grp)   # [2, world*B] rank-major rows, global CE sums
+        lse_all, sums = L._gather_lse_and_sums(pack, B, w, grp, False)   # [2, world*B] rank-major rows, global CE sums
+        rawp, rawp2 = L._gather_lse_and_sums(pack, B, w, grp, True)        # raw [world, 2B+2] packs (kernel-side indexing)
+        assert rawp is rawp2
+        rp = rawp.view(world, 2 * B + 2)
+        assert torch.equal(rp[:, :B].reshape(-1), lse_all[0]) and torch.equal(rp[:, B:2 * B].reshape(-1), lse_all[1])
+        assert torch.allclose(rp[:, 2 * B:].sum(0), sums)
         loss = 0.5 * sums.sum() / (world * B)
         da, db = bwd(lse_all[0], lse_all[1])
         # single-process reference on the concatenated batch

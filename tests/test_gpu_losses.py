@@ -266,7 +266,7 @@ def test_gathered_global_loss_emulated_ranks():
         al, bl = ac[r * B:(r + 1) * B].contiguous(), bc[r * B:(r + 1) * B].contiguous()
         _lib.call("cfa_global_infonce_fwd", al.data_ptr(), bl.data_ptr(), ac.data_ptr(), bc.data_ptr(), B, Bg, D, r * B, s,
                   1e-12, l2.data_ptr(), n2.data_ptr(), s2.data_ptr(), 0, 0, 0, 0.0, 0.0, 0, ws.data_ptr(), ws_bytes, 1,
-                  _lib.stream_ptr())
+                  0, _lib.stream_ptr())
         lse.append(l2); norms.append(n2); sums += s2            # "all-reduce" of the CE sums
     ref_loss = float(0.5 * (f1["loss_sum"] + f2["loss_sum"]) / Bg)
     assert abs(float(0.5 * sums.sum() / Bg) - ref_loss) <= 1e-5 * ref_loss
@@ -280,7 +280,7 @@ def test_gathered_global_loss_emulated_ranks():
         da = torch.empty(B, D, device="cuda"); db = torch.empty(B, D, device="cuda")
         _lib.call("cfa_global_infonce_bwd", al.data_ptr(), bl.data_ptr(), ac.data_ptr(), bc.data_ptr(), B, Bg, D, r * B, s,
                   1e-12, lse[r].data_ptr(), lse_all.data_ptr(), norms[r].data_ptr(), coef.data_ptr(), da.data_ptr(),
-                  db.data_ptr(), ws.data_ptr(), ws_bytes, 1, _lib.stream_ptr())
+                  db.data_ptr(), ws.data_ptr(), ws_bytes, 1, 0, _lib.stream_ptr())
         assert_grad_close(da, da_ref[sl], 2e-5, f"da rank {r}")
         assert_grad_close(db, db_ref[sl], 2e-5, f"db rank {r}")
 

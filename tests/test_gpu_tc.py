@@ -146,7 +146,7 @@ def test_global_infonce_tc_emulated_ranks(N, B, D, s):
         al, bl = ac[r * B:(r + 1) * B].contiguous(), bc[r * B:(r + 1) * B].contiguous()
         _lib.call("cfa_global_infonce_fwd", al.data_ptr(), bl.data_ptr(), ac.data_ptr(), bc.data_ptr(), B, Bg, D, r * B, s,
                   1e-12, l2.data_ptr(), n2.data_ptr(), s2.data_ptr(), 0, 0, 0, 0.0, 0.0, 0, ws.data_ptr(), ws_bytes, 2,
-                  _lib.stream_ptr())
+                  0, _lib.stream_ptr())
         wss.append(ws); lse.append(l2); norms.append(n2); sums += s2
     ref_loss = float(0.5 * (f1["loss_sum"] + f2["loss_sum"]) / Bg)
     assert abs(float(0.5 * sums.sum() / Bg) - ref_loss) <= 2e-5 * max(1.0, ref_loss)
@@ -160,10 +160,56 @@ def test_global_infonce_tc_emulated_ranks(N, B, D, s):
         da = torch.empty(B, D, device="cuda"); db = torch.empty(B, D, device="cuda")
         _lib.call("cfa_global_infonce_bwd", al.data_ptr(), bl.data_ptr(), ac.data_ptr(), bc.data_ptr(), B, Bg, D, r * B, s,
                   1e-12, lse[r].data_ptr(), lse_all.data_ptr(), norms[r].data_ptr(), coef.data_ptr(), da.data_ptr(),
-                  db.data_ptr(), wss[r].data_ptr(), ws_bytes, 2, _lib.stream_ptr())
+                  db.data_ptr(), wss[r].data_ptr(), ws_bytes, 2, 0, _lib.stream_ptr())
         torch.cuda.synchronize()
         assert rel_err(da, da_ref[sl]) <= 2e-4, (r, rel_err(da, da_ref[sl]))
         assert rel_err(db, db_ref[sl]) <= 2e-4, (r, rel_err(db, db_ref[sl]))
+
+
+def test_global_infonce_tc_raw_allgather_layout():
+    """gathered_ranks > 1: the kernels consume the RAW all-gather outputs ([ranks][2][B][D] embeddings and
+    [ranks][2B+2] lse/sum packs) — same numbers as the re-laid-out path, no copy kernels in between."""
+    from clip_finegrained_alignment_b200 import _lib
+    N, B, D, s = 3, 96, 256, 4.0
+    Bg = N * B
+    g = torch.Generator().manual_seed(77)
+    a = torch.randn(Bg, D, generator=g); b = torch.randn(Bg, D, generator=g)
+    f1 = lo.infonce_forward(a.double(), b.double(), s)
+    f2 = lo.infonce_forward(b.double(), a.double(), s)
+    da_ref, db_ref = lo.symmetric_infonce_backward(f1["ah"], f1["an"], f1["bh"], f1["bn"], f1["lse"], f2["lse"], s,
+                                                   0.5, 0.5, float(Bg))
+    gathered = torch.stack([torch.stack([a[r * B:(r + 1) * B], b[r * B:(r + 1) * B]]) for r in range(N)]).cuda()   # [N,2,B,D]
+    packs = torch.zeros(N, 2 * B + 2, device="cuda")
+    ws_bytes = _lib.lib.cfa_global_infonce_workspace_bytes(B, Bg, D)
+    wss, norms = [], []
+    for r in range(N):
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device="cuda")
+        n2 = torch.empty(2, B, device="cuda")
+        loc = gathered[r]
+        _lib.call("cfa_global_infonce_fwd", loc[0].data_ptr(), loc[1].data_ptr(), gathered[0, 0].data_ptr(),
+                  gathered[0, 1].data_ptr(), B, Bg, D, r * B, s, 1e-12, packs[r].data_ptr(), n2.data_ptr(),
+                  packs[r].data_ptr() + 8 * B, 0, 0, 0, 0.0, 0.0, 0, ws.data_ptr(), ws_bytes, 2, N, _lib.stream_ptr())
+        wss.append(ws); norms.append(n2)
+    torch.cuda.synchronize()
+    ref_loss = float(0.5 * (f1["loss_sum"] + f2["loss_sum"]) / Bg)
+    assert abs(float(0.5 * packs[:, 2 * B:].sum() / Bg) - ref_loss) <= 2e-5 * max(1.0, ref_loss)
+    coef = torch.full((2,), 0.5 / Bg, device="cuda")
+    for r in range(N):
+        loc = gathered[r]
+        da = torch.empty(B, D, device="cuda"); db = torch.empty(B, D, device="cuda")
+        _lib.call("cfa_global_infonce_bwd", loc[0].data_ptr(), loc[1].data_ptr(), gathered[0, 0].data_ptr(),
+                  gathered[0, 1].data_ptr(), B, Bg, D, r * B, s, 1e-12, packs[r].data_ptr(), packs.data_ptr(),
+                  norms[r].data_ptr(), coef.data_ptr(), da.data_ptr(), db.data_ptr(), wss[r].data_ptr(), ws_bytes, 2, N,
+                  _lib.stream_ptr())
+        torch.cuda.synchronize()
+        sl = slice(r * B, (r + 1) * B)
+        assert rel_err(da, da_ref[sl]) <= 2e-4 and rel_err(db, db_ref[sl]) <= 2e-4
+    # scalar epilogue straight from the gathered packs
+    out8 = torch.zeros(8, device="cuda")
+    part = torch.zeros(B, 2, device="cuda"); mask = torch.ones(B, 5, dtype=torch.uint8, device="cuda")
+    _lib.call("cfa_sparc_finalize", packs.data_ptr(), Bg, part.data_ptr(), mask.data_ptr(), B, 5, 1.0, 1.0, out8.data_ptr(), N,
+              _lib.stream_ptr())
+    assert abs(float(out8[0]) - ref_loss) <= 2e-5 * max(1.0, ref_loss)
 
 
 def test_clip_loss_bf16_uses_tensor_cores():
