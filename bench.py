@@ -340,8 +340,11 @@ def main():
     # per-ABI-call device times: a separate short pass with CUDA events around every call (kept out of the timed region:
     # the extra event records cost host time)
     _lib.kernel_events = {name: [] for name in _lib.LAUNCHES if name != "cfa_adamspd_step"}
+    crit_stages = SPARCLoss(cfg(1.0 / P), gather=world > 1, fused_calls=False)      # same kernels, one call per stage
     for i in range(min(10, args.steps)):
-        step(i)
+        v, l = vs[i % nbuf], ls[i % nbuf]
+        v.grad = None; l.grad = None
+        crit_stages(v, l, mask)["total_loss"].backward()
     sync_all()
     kev = _lib.kernel_events
     _lib.kernel_events = None

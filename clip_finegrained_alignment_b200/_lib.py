@@ -48,6 +48,10 @@ SIGNATURES = {
     "cfa_sparc_bwd": (C.c_int, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                 _vp, _vp, _vp, _vp, _vp, _sz, _i, _vp]),
     "cfa_sparc_scratch_bytes": (_sz, [_i, _i, _i, _i]),
+    "cfa_sparc_loss_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i]),
+    "cfa_sparc_loss_fwd": (C.c_int, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _f, _f, _f, _vp, _sz, _i, _vp]),
+    "cfa_sparc_loss_bwd": (C.c_int, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _f, _f, _f, _vp, _sz, _vp, _vp, _vp, _vp, _vp, _vp,
+                                     _vp, _vp, _vp, _i, _vp]),
     "cfa_masked_pairwise_fwd": (C.c_int, [_vp, _vp, _vp, _i, _i, _i, _i, _f, _vp, _vp, _vp, _vp]),
     "cfa_masked_pairwise_bwd": (C.c_int, [_vp, _vp, _vp, _i, _i, _i, _i, _f, _vp, _vp, _vp, _vp, _vp, _vp]),
     "cfa_sparc_path": (C.c_int, [_i, _i, _i, _i, _i]),
@@ -72,7 +76,8 @@ for _name, (_res, _args) in SIGNATURES.items():
 # kernels launched per C-ABI call (cudaMemsetAsync not counted); bench.py reports the running total
 LAUNCHES = {"cfa_adamspd_step": 2, "cfa_global_infonce_fwd": 2, "cfa_global_infonce_bwd": 2, "cfa_sparc_fwd": 1,
             "cfa_sparc_bwd": 1, "cfa_sparc_finalize": 1, "cfa_sparc_coef": 1, "cfa_sparc_coef_ptrs": 1,
-            "cfa_masked_pairwise_fwd": 2, "cfa_masked_pairwise_bwd": 1}
+            "cfa_masked_pairwise_fwd": 2, "cfa_masked_pairwise_bwd": 1,
+            "cfa_sparc_loss_fwd": 3, "cfa_sparc_loss_bwd": 4}
 launch_count = 0
 kernel_events = None       # {abi name: [(start_event, end_event), ...]} while bench.py profiles; else None
 

@@ -143,13 +143,16 @@ def _global_backward(st: _GlobalState, coef2: torch.Tensor):
 # ----------------------------------------------------------------------------------------------
 # SPARC
 # ----------------------------------------------------------------------------------------------
+_WS_BYTES = {}      # (B, P, T, D, dtype, path) -> cfa_sparc_loss_workspace_bytes
+
+
 class _SparcFunction(torch.autograd.Function):
     """Returns the 7 losses (SPARC_KEYS order) as separate 0-dim outputs of ONE autograd node; backward receives
     the 7 upstream gradients (None for unused outputs) and hands their device pointers to the coefficient kernel —
     no host synchronisation, zero-fill or concatenation anywhere."""
 
     @staticmethod
-    def forward(ctx, v, l, mask, thr, gw, lw, scale, gather, group, path):
+    def forward(ctx, v, l, mask, thr, gw, lw, scale, gather, group, path, fused=True):
         dev = _lib.require_cuda(v, l, mask)
         if v.dtype != l.dtype or v.dtype not in _lib.DTYPE_CODE:
             raise _lib.CfaError(f"SPARCLoss: embeddings must share a dtype in fp32/bf16/fp16, got {v.dtype}, {l.dtype}")
@@ -162,6 +165,24 @@ class _SparcFunction(torch.autograd.Function):
         B, P, D = v.shape
         T = l.shape[1]
         code = _lib.DTYPE_CODE[v.dtype]
+        world, rank, group = _dist_ctx(group, gather)
+        ctx.set_materialize_grads(False)               # unused outputs arrive as None: no zero-fill launches
+        if world == 1 and fused:
+            # rank-local loss: ONE library call and ONE allocation per direction (cfa_sparc_loss_fwd / _bwd); the
+            # workspace layout is private to the library, its first 8 floats are the outputs
+            key = (B, P, T, D, code, path)
+            nbytes = _WS_BYTES.get(key)
+            if nbytes is None:
+                nbytes = _WS_BYTES[key] = _L.cfa_sparc_loss_workspace_bytes(B, P, T, D, code, path)
+            ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+            same_dev = torch.cuda.current_device() == dev.index
+            with (contextlib.nullcontext() if same_dev else torch.cuda.device(dev)):
+                _lib.call("cfa_sparc_loss_fwd", v.data_ptr(), l.data_ptr(), mask_u8.data_ptr(), B, P, T, D, code, thr, scale,
+                          gw, lw, ws.data_ptr(), nbytes, path, _lib.stream_ptr())
+            ctx.save_for_backward(v, l, mask_u8, ws)
+            ctx.gst = None
+            ctx.hp = (thr, gw, lw, scale, code, path, None, None)
+            return ws[:28].view(torch.float32).clone().unbind(0)
         # ONE fp32 allocation, carved by pointer arithmetic (host time matters at ~0.5 ms per step):
         # pooled [2,B,D] | out8 | lse_row [B,T] | lse_col [B,T] | local_partial [B,2] | row_inv_norm [B(P+T)] |
         # tt_logits [B,T,T] | g_inv_norm [B,T]
@@ -190,7 +211,6 @@ class _SparcFunction(torch.autograd.Function):
             _lib.call("cfa_sparc_fwd", v.data_ptr(), l.data_ptr(), mask_u8.data_ptr(), B, P, T, D, code, thr, scale,
                       ptr[5], ptr[0], ptr[0] + 4 * B * D, ptr[2], ptr[3], ptr[4], ptr[6], ptr[7], gq[0], gq[1], sptr, sbytes,
                       path, _lib.stream_ptr())
-            world, rank, group = _dist_ctx(group, gather)
             gpath = 1 if (v.dtype == torch.float32 or path == 1) else 0      # fp32 inputs keep the fp32-exact global kernels
             gst, sums = _global_forward(pooled, scale, _NORM_EPS, world, rank, group,
                                         fused=(part_t, mask_u8, T, gw, lw, out8), path=gpath, raw_sums=True)
@@ -201,7 +221,6 @@ class _SparcFunction(torch.autograd.Function):
         ctx.gst = gst
         ctx.hp = (thr, gw, lw, scale, code, path, ptr, gq)
         ctx.scratch = scratch                          # reused by the backward (same size class)
-        ctx.set_materialize_grads(False)               # unused outputs arrive as None: no zero-fill launches
         return out8[:7].clone().unbind(0)
 
     @staticmethod
@@ -223,6 +242,13 @@ class _SparcFunction(torch.autograd.Function):
             keep.append(gk)
             gptr.append(gk.data_ptr())
         same_dev = torch.cuda.current_device() == dev.index
+        if gst is None:                                # rank-local: one call (coefficients + global + fine-grained backward)
+            dv = torch.empty_like(v)
+            dl = torch.empty_like(l)
+            with (contextlib.nullcontext() if same_dev else torch.cuda.device(dev)):
+                _lib.call("cfa_sparc_loss_bwd", v.data_ptr(), l.data_ptr(), mask_u8.data_ptr(), B, P, T, D, code, thr, scale,
+                          gw, lw, blk.data_ptr(), blk.numel(), *gptr, dv.data_ptr(), dl.data_ptr(), path, _lib.stream_ptr())
+            return dv, dl, None, None, None, None, None, None, None, None, None
         with (contextlib.nullcontext() if same_dev else torch.cuda.device(dev)):
             coef = torch.empty(8, dtype=torch.float32, device=dev)
             _lib.call("cfa_sparc_coef_ptrs", *gptr, gw, lw, gst.Bg, ptr[1], coef.data_ptr(), _lib.stream_ptr())
@@ -234,7 +260,7 @@ class _SparcFunction(torch.autograd.Function):
             _lib.call("cfa_sparc_bwd", v.data_ptr(), l.data_ptr(), mask_u8.data_ptr(), B, P, T, D, code, thr, scale,
                       ptr[5], ptr[2], ptr[3], ptr[6], ptr[7], gq[0], gq[1], coef.data_ptr() + 8, dpv.data_ptr(), dpl.data_ptr(),
                       dv.data_ptr(), dl.data_ptr(), sptr, sbytes, path, _lib.stream_ptr())
-        return dv, dl, None, None, None, None, None, None, None, None
+        return dv, dl, None, None, None, None, None, None, None, None, None
 
 
 class _PairwiseFunction(torch.autograd.Function):
@@ -304,8 +330,12 @@ class _MaskedPairwiseFunction(torch.autograd.Function):
 class SPARCLoss(nn.Module):
     """SPARC loss (https://arxiv.org/abs/2401.09865), reference API: finetune/losses.py:136-264."""
 
-    def __init__(self, config, gather: bool = False, process_group=None, kernel_path: str = "auto"):
+    def __init__(self, config, gather: bool = False, process_group=None, kernel_path: str = "auto",
+                 fused_calls: bool = True):
         super().__init__()
+        # fused_calls: rank-local loss through one library call per direction (cfa_sparc_loss_fwd / _bwd); False keeps
+        # the per-stage entry points (same kernels, same numbers; used to time the stages separately)
+        self.fused_calls = fused_calls
         # "auto": tcgen05 tensor-core kernels for bf16 inputs of supported shapes, fp32-exact CUDA-core kernels
         # otherwise; "simt" / "tc" force one of them (tests, benchmarks)
         self.kernel_path = {"auto": 0, "simt": 1, "tc": 2}[kernel_path]
@@ -333,7 +363,8 @@ class SPARCLoss(nn.Module):
             raise TypeError(f"language_mask must be bool or integer, got {language_mask.dtype}")
         out = _SparcFunction.apply(v_patch_embed, l_token_embed, language_mask, float(self.similarity_threshold),
                                    float(self.global_loss_weight), float(self.local_loss_weight),
-                                   float(self.inverse_temperature), self.gather, self.process_group, self.kernel_path)
+                                   float(self.inverse_temperature), self.gather, self.process_group, self.kernel_path,
+                                   self.fused_calls)
         return dict(zip(SPARC_KEYS, out))                  # one autograd node, 7 outputs
 
 

@@ -164,6 +164,38 @@ size_t cfa_sparc_scratch_bytes(int B, int P, int T, int backward);
 int cfa_sparc_max_patches(int T, int backward);
 
 /*
+ * Rank-local SPARC loss in ONE call per direction (what SPARCLoss.forward / .backward issue when the global InfoNCE is
+ * not all-gathered): cfa_sparc_fwd + cfa_global_infonce_fwd (fused scalar epilogue), and cfa_sparc_coef_ptrs +
+ * cfa_global_infonce_bwd + cfa_sparc_bwd, over one 128-byte-aligned workspace of cfa_sparc_loss_workspace_bytes() whose
+ * layout is private to the library.  After the forward the first 8 floats of the workspace hold out[0..7] (see
+ * cfa_sparc_finalize); the backward must be given the same, untouched workspace.  g_*: DEVICE scalars, the upstream
+ * gradients of the 7 outputs (NULL = unused).  Saves ~4 host calls and ~4 allocations per step.
+ */
+size_t cfa_sparc_loss_workspace_bytes(int B, int P, int T, int D, int dtype, int path);
+int cfa_sparc_loss_fwd(const void* v, const void* l, const uint8_t* mask, int B, int P, int T, int D, int dtype, float thr,
+                       float scale, float gw, float lw, void* workspace, size_t workspace_bytes, int path, void* stream);
+int cfa_sparc_loss_bwd(const void* v, const void* l, const uint8_t* mask, int B, int P, int T, int D, int dtype, float thr,
+                       float scale, float gw, float lw, void* workspace, size_t workspace_bytes, const float* g_global,
+                       const float* g_local, const float* g_total, const float* g_vl, const float* g_lv,
+                       const float* g_vl_local, const float* g_lv_local, void* dv, void* dl, int path, void* stream);
+
+/*
+ * Rank-local SPARC loss in ONE call per direction (what SPARCLoss.forward / .backward issue when the global InfoNCE is
+ * not all-gathered): cfa_sparc_fwd + cfa_global_infonce_fwd (fused scalar epilogue), and cfa_sparc_coef_ptrs +
+ * cfa_global_infonce_bwd + cfa_sparc_bwd, over one 128-byte-aligned workspace of cfa_sparc_loss_workspace_bytes() whose
+ * layout is private to the library.  After the forward the first 8 floats of the workspace hold out[0..7] (see
+ * cfa_sparc_finalize); the backward must be given the same, untouched workspace.  g_*: DEVICE scalars, the upstream
+ * gradients of the 7 outputs (NULL = unused).  Saves ~4 host calls and ~4 allocations per step.
+ */
+size_t cfa_sparc_loss_workspace_bytes(int B, int P, int T, int D, int dtype, int path);
+int cfa_sparc_loss_fwd(const void* v, const void* l, const uint8_t* mask, int B, int P, int T, int D, int dtype, float thr,
+                       float scale, float gw, float lw, void* workspace, size_t workspace_bytes, int path, void* stream);
+int cfa_sparc_loss_bwd(const void* v, const void* l, const uint8_t* mask, int B, int P, int T, int D, int dtype, float thr,
+                       float scale, float gw, float lw, void* workspace, size_t workspace_bytes, const float* g_global,
+                       const float* g_local, const float* g_total, const float* g_vl, const float* g_lv,
+                       const float* g_vl_local, const float* g_lv_local, void* dv, void* dl, int path, void* stream);
+
+/*
  * SPARCLoss.masked_pairwise_contrastive_loss on its own (losses.py:165-197): a, b [B,T,D] in `dtype`, mask [B,T] bytes.
  * One direction: rows of a against the columns of b of the same sample, target = same token index.
  *   out2[0] = sum_b sum_{valid i} CE_i / n_valid,  out2[1] = n_valid = sum(mask) + 1e-8 (fp32);

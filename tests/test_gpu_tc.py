@@ -119,6 +119,25 @@ def test_sparc_tc_matches_simt_path():
     assert rel_err(dla.float(), dlb.float()) <= 5e-3
 
 
+@pytest.mark.parametrize("dtype,P,D", [(torch.bfloat16, 196, 512), (torch.float32, 50, 64), (torch.bfloat16, 576, 768)])
+def test_fused_calls_equal_staged_calls(dtype, P, D):
+    """cfa_sparc_loss_fwd / _bwd (one library call per direction) run the same kernels as the per-stage entry points:
+    bit-identical losses and gradients, for the tensor-core, the CUDA-core and the global-scratch (config 4) paths."""
+    from clip_finegrained_alignment_b200 import SPARCLoss
+    g = torch.Generator().manual_seed(3)
+    B, T = 5, 77
+    v0 = torch.randn(B, P, D, generator=g).to(dtype); l0 = torch.randn(B, T, D, generator=g).to(dtype)
+    m = torch.ones(B, T, dtype=torch.bool); m[1, 40:] = False
+    res = []
+    for fused in (True, False):
+        v = v0.cuda().requires_grad_(True); l = l0.cuda().requires_grad_(True)
+        out = SPARCLoss(_cfg(1.0 / P, 0.7, 1.3, 2.0), fused_calls=fused)(v, l, m.cuda())
+        (out["total_loss"] * 3.0 + out["loss_vl_local"]).backward()
+        res.append(({k: float(x) for k, x in out.items()}, v.grad.clone(), l.grad.clone()))
+    assert res[0][0] == res[1][0]
+    assert torch.equal(res[0][1], res[1][1]) and torch.equal(res[0][2], res[1][2])
+
+
 # ----------------------------------------------------------------------------------------------
 # tensor-core global InfoNCE (tcgen05 logits tiles, bf16 hi/lo-split normalised operands)
 # ----------------------------------------------------------------------------------------------
