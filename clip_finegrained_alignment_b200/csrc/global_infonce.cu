@@ -126,7 +126,22 @@ global_combine_kernel(const float* __restrict__ part_m, const float* __restrict_
   if (out8) {
     float nv = 0.f, a = 0.f, c = 0.f;
     const int nb = (int)((size_t)global_batch);     // single process: global_batch == B
-    for (int i = threadIdx.x; i < nb * T; i += kNT) nv += mask[i] ? 1.f : 0.f;
+    {                                                 // count of valid tokens: 16 mask bytes per load when the layout allows
+      const int n = nb * T;
+      int cnt = 0;
+      if ((((uintptr_t)mask) & 15) == 0) {
+        const int n16 = n >> 4;
+        for (int i = threadIdx.x; i < n16; i += kNT) {
+          const uint4 w = __ldg(reinterpret_cast<const uint4*>(mask) + i);
+          cnt += __popc(__vcmpne4(w.x, 0u) & 0x01010101u) + __popc(__vcmpne4(w.y, 0u) & 0x01010101u) +
+                 __popc(__vcmpne4(w.z, 0u) & 0x01010101u) + __popc(__vcmpne4(w.w, 0u) & 0x01010101u);
+        }
+        for (int i = (n16 << 4) + threadIdx.x; i < n; i += kNT) cnt += mask[i] ? 1 : 0;
+      } else {
+        for (int i = threadIdx.x; i < n; i += kNT) cnt += mask[i] ? 1 : 0;
+      }
+      nv = (float)cnt;                                // exact: counts < 2^24 per thread
+    }
     for (int i = threadIdx.x; i < nb; i += kNT) { a += local_partial[2 * i]; c += local_partial[2 * i + 1]; }
     nv = block_sum(nv, red); a = block_sum(a, red); c = block_sum(c, red);
     if (threadIdx.x == 0) {

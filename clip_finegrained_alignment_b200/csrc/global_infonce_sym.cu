@@ -31,24 +31,28 @@ __device__ __forceinline__ float4 sy_ld4(const float* __restrict__ src, int row,
   }
   return x;
 }
-template <bool kNorm>
-__device__ __forceinline__ void sy_load_chunks(float* __restrict__ As, float* __restrict__ Bs, const float* __restrict__ a,
-                                               const float* __restrict__ b, int r0, int c0, int rows, int D, int d0,
-                                               float* ssa, float* ssb, int warp, int lane) {
-  float4 xa[4], xb[4];
+// global -> registers (all eight loads in flight), registers -> smem (+ optional squared row norms) as separate steps so
+// that the loads of chunk k+1 can be issued before the arithmetic of chunk k (register double buffering)
+struct SyRegs { float4 a[4], b[4]; };
+__device__ __forceinline__ void sy_fetch(SyRegs& x, const float* __restrict__ a, const float* __restrict__ b, int r0, int c0,
+                                         int rows, int D, int d0, int warp, int lane) {
   const int d = d0 + 4 * lane;
 #pragma unroll
-  for (int i = 0; i < 4; ++i) { xa[i] = sy_ld4(a, r0 + warp + 8 * i, rows, D, d); xb[i] = sy_ld4(b, c0 + warp + 8 * i, rows, D, d); }
+  for (int i = 0; i < 4; ++i) { x.a[i] = sy_ld4(a, r0 + warp + 8 * i, rows, D, d); x.b[i] = sy_ld4(b, c0 + warp + 8 * i, rows, D, d); }
+}
+template <bool kNorm>
+__device__ __forceinline__ void sy_commit(const SyRegs& x, float* __restrict__ As, float* __restrict__ Bs, float* ssa, float* ssb,
+                                          int warp, int lane) {
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    *reinterpret_cast<float4*>(As + (warp + 8 * i) * kSyLd + 4 * lane) = xa[i];
-    *reinterpret_cast<float4*>(Bs + (warp + 8 * i) * kSyLd + 4 * lane) = xb[i];
+    *reinterpret_cast<float4*>(As + (warp + 8 * i) * kSyLd + 4 * lane) = x.a[i];
+    *reinterpret_cast<float4*>(Bs + (warp + 8 * i) * kSyLd + 4 * lane) = x.b[i];
   }
   if (kNorm) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      ssa[i] += warp_sum(fmaf(xa[i].x, xa[i].x, fmaf(xa[i].y, xa[i].y, fmaf(xa[i].z, xa[i].z, xa[i].w * xa[i].w))));
-      ssb[i] += warp_sum(fmaf(xb[i].x, xb[i].x, fmaf(xb[i].y, xb[i].y, fmaf(xb[i].z, xb[i].z, xb[i].w * xb[i].w))));
+      ssa[i] += warp_sum(fmaf(x.a[i].x, x.a[i].x, fmaf(x.a[i].y, x.a[i].y, fmaf(x.a[i].z, x.a[i].z, x.a[i].w * x.a[i].w))));
+      ssb[i] += warp_sum(fmaf(x.b[i].x, x.b[i].x, fmaf(x.b[i].y, x.b[i].y, fmaf(x.b[i].z, x.b[i].z, x.b[i].w * x.b[i].w))));
     }
   }
 }
@@ -76,11 +80,15 @@ __device__ __forceinline__ void sy_logits_tile(const float* __restrict__ a, cons
   const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
   float ssa[4] = {0.f, 0.f, 0.f, 0.f}, ssb[4] = {0.f, 0.f, 0.f, 0.f};
   acc[0][0] = acc[0][1] = acc[1][0] = acc[1][1] = 0.f;
+  SyRegs cur, nxt;
+  sy_fetch(cur, a, b, r0, c0, B, D, 0, warp, lane);
   for (int d0 = 0; d0 < D; d0 += kSyK) {
     __syncthreads();
-    sy_load_chunks<true>(As, Bs, a, b, r0, c0, B, D, d0, ssa, ssb, warp, lane);
+    sy_commit<true>(cur, As, Bs, ssa, ssb, warp, lane);
+    if (d0 + kSyK < D) sy_fetch(nxt, a, b, r0, c0, B, D, d0 + kSyK, warp, lane);     // in flight during the MACs below
     __syncthreads();
     sy_mac_chunk(As, Bs, acc, ty, tx);
+    cur = nxt;
   }
   if (lane == 0) {
 #pragma unroll
@@ -198,9 +206,13 @@ global_sym_bwd_kernel(const float* __restrict__ a, const float* __restrict__ b, 
   // share a row read / write 128 contiguous bytes per access (conflict-free float4 smem reads, coalesced stores)
   const int r = threadIdx.x >> 3, cg = (threadIdx.x & 7) * 4;
   float* ssd = nullptr;
-  for (int d0 = dz0; d0 < min(dz0 + kSyDz, D); d0 += kSyK) {
+  const int dz1 = min(dz0 + kSyDz, D);
+  SyRegs cur, nxt;
+  sy_fetch(cur, a, b, r0, c0, B, D, dz0, warp, lane);
+  for (int d0 = dz0; d0 < dz1; d0 += kSyK) {
     __syncthreads();
-    sy_load_chunks<false>(As, Bs, a, b, r0, c0, B, D, d0, ssd, ssd, warp, lane);
+    sy_commit<false>(cur, As, Bs, ssd, ssd, warp, lane);
+    if (d0 + kSyK < dz1) sy_fetch(nxt, a, b, r0, c0, B, D, d0 + kSyK, warp, lane);
     __syncthreads();
     float oa[16], ob[16];
 #pragma unroll
@@ -240,6 +252,7 @@ global_sym_bwd_kernel(const float* __restrict__ a, const float* __restrict__ b, 
           for (int e = 0; e < 4; ++e) if (d + 32 * c4 + e < D) dst[32 * c4 + e] = ob[4 * c4 + e] * scale;
       }
     }
+    cur = nxt;
   }
 }
 

@@ -53,7 +53,8 @@ __host__ __device__ inline Bwd2Layout bwd2_layout(int P, int T, int D) {
   L.off_w = ring;
   L.off_s = L.off_w + wreg;
   L.off_dl = L.off_s + sreg;
-  L.off_f = L.off_dl + 2 * L.dl_bytes;
+  const uint32_t p4 = b2_up(2u * (uint32_t)D * 4u, 128) + 8u * 32u * 80u;   // P4: pooled gradients [2][D] + 8 per-warp transpose tiles
+  L.off_f = L.off_dl + (2 * L.dl_bytes > p4 ? 2 * L.dl_bytes : p4);
   L.off_x = L.off_f + 4 * (2 * (L.NP + 32) + 7 * L.NT);
   L.off_bar = (L.off_x + 4 * (2 * 2 * L.NT * 4) + 7) & ~7u;              // exchange buffer: [2 sets][2 halves][NT][4]
   L.total = L.off_bar + 8 * 16 + 16;
@@ -290,10 +291,14 @@ sparc_bwd2_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_constant
     tc_fence_after();
     stamp();
     int o = 0;
+    long long wfull = 0, wfree = 0;
     for (int kb = 0; kb < KB; ++kb, ++u, ++o) {
       const int s = u & 1, buf = o & 1;
+      const long long w0 = clock64();
       mbar_wait(full + s, (u >> 1) & 1);
+      const long long w1 = clock64();
       mbar_wait(out_free + buf, ((o >> 1) & 1) ^ 1);
+      wfull += w1 - w0; wfree += clock64() - w1;
       tc_fence_after();
       const uint64_t dv0 = sw0 | (smem_u32(ring + (size_t)s * L.slot4) >> 4);
       const uint32_t d = tmem + kB2cDL + 64 * buf;
@@ -303,11 +308,16 @@ sparc_bwd2_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_constant
       umma_commit_w(leader, empty + s);
     }
     stamp();
+    if (pf) { pf[8] = wfull; pf[9] = wfree; }
+    wfull = 0; wfree = 0;
     // ---- P4b: dv_kb = dShat'^T . l_kb + Wg^T . G_kb
     for (int kb = 0; kb < KB; ++kb, ++u, ++o) {
       const int s = u & 1, buf = o & 1;
+      const long long w0 = clock64();
       mbar_wait(full + s, (u >> 1) & 1);
+      const long long w1 = clock64();
       mbar_wait(out_free + buf, ((o >> 1) & 1) ^ 1);
+      wfull += w1 - w0; wfree += clock64() - w1;
       tc_fence_after();
       const uint32_t sl = smem_u32(ring + (size_t)s * L.slot4);
       const uint64_t dl0 = sw0 | (sl >> 4), gh0 = sw0 | ((sl + L.l_bytes) >> 4), gl0 = sw0 | ((sl + 2 * L.l_bytes) >> 4);
@@ -325,6 +335,7 @@ sparc_bwd2_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_constant
       umma_commit_w(leader, empty + s);
     }
     stamp();
+    if (pf) { pf[10] = wfull; pf[11] = wfree; }
   } else {
     // =============================== epilogue: 8 warps, 2 per TMEM lane quarter, each owns half of the columns ===============================
     const int q = warp & 3, h = (warp - 2) >> 2;
@@ -613,32 +624,53 @@ sparc_bwd2_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_constant
       dps[i] = src ? __ldg(src + (size_t)b * D + (i < D ? i : i - D)) : 0.f;
     }
     b2_epi_bar();
-    // raw rows (needed for the - x fac terms) are fetched one block AHEAD of the accumulator they are combined with,
-    // so their L2 latency overlaps the tensor-core work
-    auto load_raw = [&](const bf16* src, uint4* r) {
+    // Raw rows (needed for the - x fac terms) are fetched one block AHEAD of the accumulator they are combined with, and
+    // every global access of the epilogue is TRANSPOSED through a per-warp shared-memory tile: thread = row for the
+    // arithmetic (TMEM layout), but lane -> (row = 8 it + lane / 4, 16-byte chunk = lane % 4) for LDG / STG, so one
+    // instruction touches 8 rows x 64 contiguous bytes instead of 32 rows x 16 bytes (4x fewer L1 wavefronts: the
+    // output phases were LSU-bound, not tensor-bound).
+    uint8_t* sc = dLhi + b2_up(2u * (uint32_t)D * 4u, 128) + (warp - 2) * (32 * 80);
+    const int tr = lane >> 2, tc16 = (lane & 3) * 16, tc8 = (lane & 3) * 8;
+    auto load_raw = [&](const bf16* gtile, int nrows, uint4* r4) {
 #pragma unroll
-      for (int g = 0; g < 4; ++g) r[g] = __ldg(reinterpret_cast<const uint4*>(src) + g);
+      for (int it = 0; it < 4; ++it) {
+        const int r = it * 8 + tr;
+        r4[it] = (r < nrows) ? __ldg(reinterpret_cast<const uint4*>(gtile + (size_t)r * D + tc8)) : make_uint4(0, 0, 0, 0);
+      }
     };
-    auto emit = [&](const float* x, const uint4* rw, const float* dp, float fac, float dscale, bf16* dst) {
+    auto emit = [&](const float* x, const uint4* rawT, const float* dp, float fac, float dscale, bf16* gtile, int nrows) {
+#pragma unroll
+      for (int it = 0; it < 4; ++it) *reinterpret_cast<uint4*>(sc + (it * 8 + tr) * 80 + tc16) = rawT[it];
+      __syncwarp();
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
         float rv[8], ov[8];
-        b2_unpack8(rw[g], rv);
+        b2_unpack8(*reinterpret_cast<const uint4*>(sc + lane * 80 + g * 16), rv);
         const float4 d0v = *reinterpret_cast<const float4*>(dp + 8 * g), d1v = *reinterpret_cast<const float4*>(dp + 8 * g + 4);
         const float dpv[8] = {d0v.x, d0v.y, d0v.z, d0v.w, d1v.x, d1v.y, d1v.z, d1v.w};
 #pragma unroll
         for (int j = 0; j < 8; ++j) ov[j] = fmaf(dpv[j], dscale, fmaf(-rv[j], fac, x[8 * g + j]));
-        reinterpret_cast<uint4*>(dst)[g] = b2_pack8(ov);
+        *reinterpret_cast<uint4*>(sc + lane * 80 + g * 16) = b2_pack8(ov);
       }
+      __syncwarp();
+#pragma unroll
+      for (int it = 0; it < 4; ++it) {
+        const int r = it * 8 + tr;
+        const uint4 ov4 = *reinterpret_cast<const uint4*>(sc + r * 80 + tc16);
+        if (r < nrows) *reinterpret_cast<uint4*>(gtile + (size_t)r * D + tc8) = ov4;
+      }
+      __syncwarp();
     };
     {
+      const int nrows = min(32, max(0, T - 32 * q));
+      const bf16* lt = p.l + ((size_t)b * T + 32 * q) * D + 32 * h;
+      bf16* dlt = p.dl + ((size_t)b * T + 32 * q) * D + 32 * h;
       uint4 raw[4];
-      const bf16* lrow = p.l + ((size_t)b * T + (row < T ? row : 0)) * D + 32 * h;
-      load_raw(lrow, raw);
+      load_raw(lt, nrows, raw);
       for (int kb = 0; kb < KB; ++kb, ++o) {               // dl
         const int buf = o & 1, d0 = kb * 64 + 32 * h;
         uint4 rawn[4];
-        if (kb + 1 < KB) load_raw(lrow + (kb + 1) * 64, rawn);
+        if (kb + 1 < KB) load_raw(lt + (kb + 1) * 64, nrows, rawn);
         mbar_wait(out_full + buf, (o >> 1) & 1);
         tc_fence_after();
         float x[32];
@@ -647,7 +679,7 @@ sparc_bwd2_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_constant
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(out_free + buf);        // the TMEM buffer is free as soon as it is in registers
-        if (row < T) emit(x, raw, dps + D + d0, lfac, mrow, p.dl + ((size_t)b * T + row) * D + d0);
+        if (nrows > 0) emit(x, raw, dps + D + d0, lfac, mrow, dlt + kb * 64, nrows);
 #pragma unroll
         for (int g = 0; g < 4; ++g) raw[g] = rawn[g];
       }
@@ -655,28 +687,30 @@ sparc_bwd2_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_constant
     stamp();
     {
       const int ntile = NP > 128 ? 2 : 1;
-      const bool in0 = row < P, in1 = ntile > 1 && 128 + row < P;
-      const bf16* vrow0 = p.v + ((size_t)b * P + (in0 ? row : 0)) * D + 32 * h;
-      const bf16* vrow1 = p.v + ((size_t)b * P + (in1 ? 128 + row : 0)) * D + 32 * h;
+      const int nr0 = min(32, max(0, P - 32 * q)), nr1 = ntile > 1 ? min(32, max(0, P - 128 - 32 * q)) : 0;
+      const bf16* vt0 = p.v + ((size_t)b * P + 32 * q) * D + 32 * h;
+      const bf16* vt1 = vt0 + (size_t)128 * D;
+      bf16* dvt0 = p.dv + ((size_t)b * P + 32 * q) * D + 32 * h;
+      bf16* dvt1 = dvt0 + (size_t)128 * D;
       uint4 raw0[4], raw1[4];
-      load_raw(vrow0, raw0);
-      load_raw(vrow1, raw1);
+      load_raw(vt0, nr0, raw0);
+      load_raw(vt1, nr1, raw1);
       for (int kb = 0; kb < KB; ++kb, ++o) {               // dv
         const int buf = o & 1, d0 = kb * 64 + 32 * h;
         uint4 raw0n[4], raw1n[4];
-        if (kb + 1 < KB) { load_raw(vrow0 + (kb + 1) * 64, raw0n); load_raw(vrow1 + (kb + 1) * 64, raw1n); }
+        if (kb + 1 < KB) { load_raw(vt0 + (kb + 1) * 64, nr0, raw0n); load_raw(vt1 + (kb + 1) * 64, nr1, raw1n); }
         mbar_wait(out_full + buf, (o >> 1) & 1);
         tc_fence_after();
         float x[32];
         tmem_ld32(trow + kB2cDV + 128 * buf + 32 * h, x);
         tmem_ld_wait();
-        if (in0) emit(x, raw0, dps + d0, vf0, invP, p.dv + ((size_t)b * P + row) * D + d0);
+        if (nr0 > 0) emit(x, raw0, dps + d0, vf0, invP, dvt0 + kb * 64, nr0);
         tmem_ld32(trow + kB2cDV + 128 * buf + 64 + 32 * h, x);
         tmem_ld_wait();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(out_free + buf);
-        if (in1) emit(x, raw1, dps + d0, vf1, invP, p.dv + ((size_t)b * P + 128 + row) * D + d0);
+        if (nr1 > 0) emit(x, raw1, dps + d0, vf1, invP, dvt1 + kb * 64, nr1);
 #pragma unroll
         for (int g = 0; g < 4; ++g) { raw0[g] = raw0n[g]; raw1[g] = raw1n[g]; }
       }

@@ -24,5 +24,6 @@ names_m = ['start','P1 issued','e1/dl ready seen','ds_ready seen','P4a issued','
 names_e = ['start','phase0 done','s_full seen','E1 done','dw_full seen','E3 done','dl written','dv written']
 print('B =', B, ' MMA thread (cycles since start, median over CTAs):')
 for i,n in enumerate(names_m): print(f'  {n:18s} {float(((mma[:,i:i+1]-t0)).median()):10.0f}')
+print('  MMA waits: P4a full %.0f free %.0f | P4b full %.0f free %.0f' % tuple(float(t[:,k].median()) for k in (8,9,10,11)))
 print('epilogue thread row 0, half 0:')
 for i,n in enumerate(names_e): print(f'  {n:18s} {float(((epi[:,i:i+1]-t0)).median()):10.0f}')
