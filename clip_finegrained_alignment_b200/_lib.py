@@ -74,10 +74,10 @@ for _name, (_res, _args) in SIGNATURES.items():
 
 
 # kernels launched per C-ABI call (cudaMemsetAsync not counted); bench.py reports the running total
-LAUNCHES = {"cfa_adamspd_step": 2, "cfa_global_infonce_fwd": 2, "cfa_global_infonce_bwd": 2, "cfa_sparc_fwd": 1,
+LAUNCHES = {"cfa_adamspd_step": 2, "cfa_global_infonce_fwd": 1, "cfa_global_infonce_bwd": 2, "cfa_sparc_fwd": 1,
             "cfa_sparc_bwd": 1, "cfa_sparc_finalize": 1, "cfa_sparc_coef": 1, "cfa_sparc_coef_ptrs": 1,
             "cfa_masked_pairwise_fwd": 2, "cfa_masked_pairwise_bwd": 1,
-            "cfa_sparc_loss_fwd": 3, "cfa_sparc_loss_bwd": 4}
+            "cfa_sparc_loss_fwd": 2, "cfa_sparc_loss_bwd": 4}
 launch_count = 0
 kernel_events = None       # {abi name: [(start_event, end_event), ...]} while bench.py profiles; else None
 

@@ -7,6 +7,7 @@
 //   direction 0: rows = a_loc, columns = b_all  (image -> text);   direction 1: rows = b_loc, columns = a_all.
 #include "common.cuh"
 #include "simt_tile.cuh"
+#include "global_combine.cuh"
 #include <math_constants.h>
 
 namespace cfa {
@@ -89,70 +90,13 @@ global_fwd_kernel(const float* __restrict__ a_loc, const float* __restrict__ b_l
   }
 }
 
-__device__ __forceinline__ float block_sum(float x, float* red) {
-  x = warp_sum(x);
-  __syncthreads();
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = x;
-  __syncthreads();
-  float s = 0.f;
-  for (int k = 0; k < kNT / 32; ++k) s += red[k];
-  return s;
-}
-
-// One CTA: merge the per-split online-softmax partials -> lse[2][B], sums2 = (sum CE_a, sum CE_b) over the LOCAL rows.
-// If out8 != NULL (single process) it also performs the SPARC scalar epilogue (losses.py:163,196,217,252-264).
 __global__ void __launch_bounds__(kNT)
 global_combine_kernel(const float* __restrict__ part_m, const float* __restrict__ part_l, const float* __restrict__ diag,
                       int B, int nsplit, float* __restrict__ lse, float* __restrict__ sums2, int global_batch,
                       const float* __restrict__ local_partial, const uint8_t* __restrict__ mask, int T, float gw, float lw,
                       float* __restrict__ out8) {
   __shared__ float red[8];
-  float ce[2] = {0.f, 0.f};
-  for (int idx = threadIdx.x; idx < 2 * B; idx += kNT) {
-    const int dir = idx / B, i = idx - dir * B;
-    float M = -CUDART_INF_F;
-    for (int s = 0; s < nsplit; ++s) M = fmaxf(M, part_m[((size_t)dir * nsplit + s) * B + i]);
-    float Lsum = 0.f;
-    for (int s = 0; s < nsplit; ++s) {
-      const float m = part_m[((size_t)dir * nsplit + s) * B + i];
-      if (m != -CUDART_INF_F) Lsum += part_l[((size_t)dir * nsplit + s) * B + i] * expf(m - M);
-    }
-    const float x = M + logf(Lsum);
-    lse[idx] = x;
-    ce[dir] += x - diag[idx];
-  }
-  const float sa = block_sum(ce[0], red), sb = block_sum(ce[1], red);
-  if (threadIdx.x == 0) { sums2[0] = sa; sums2[1] = sb; }
-  if (out8) {
-    float nv = 0.f, a = 0.f, c = 0.f;
-    const int nb = (int)((size_t)global_batch);     // single process: global_batch == B
-    {                                                 // count of valid tokens: 16 mask bytes per load when the layout allows
-      const int n = nb * T;
-      int cnt = 0;
-      if ((((uintptr_t)mask) & 15) == 0) {
-        const int n16 = n >> 4;
-        for (int i = threadIdx.x; i < n16; i += kNT) {
-          const uint4 w = __ldg(reinterpret_cast<const uint4*>(mask) + i);
-          cnt += __popc(__vcmpne4(w.x, 0u) & 0x01010101u) + __popc(__vcmpne4(w.y, 0u) & 0x01010101u) +
-                 __popc(__vcmpne4(w.z, 0u) & 0x01010101u) + __popc(__vcmpne4(w.w, 0u) & 0x01010101u);
-        }
-        for (int i = (n16 << 4) + threadIdx.x; i < n; i += kNT) cnt += mask[i] ? 1 : 0;
-      } else {
-        for (int i = threadIdx.x; i < n; i += kNT) cnt += mask[i] ? 1 : 0;
-      }
-      nv = (float)cnt;                                // exact: counts < 2^24 per thread
-    }
-    for (int i = threadIdx.x; i < nb; i += kNT) { a += local_partial[2 * i]; c += local_partial[2 * i + 1]; }
-    nv = block_sum(nv, red); a = block_sum(a, red); c = block_sum(c, red);
-    if (threadIdx.x == 0) {
-      const float n_valid = nv + 1e-8f;               // evaluated in fp32 like the reference (losses.py:196)
-      const float vl = sa / (float)global_batch, lv = sb / (float)global_batch;
-      const float vll = a / n_valid, lvl = c / n_valid;
-      const float g = 0.5f * (vl + lv), lo = 0.5f * (vll + lvl);
-      out8[0] = g; out8[1] = lo; out8[2] = gw * g + lw * lo;
-      out8[3] = vl; out8[4] = lv; out8[5] = vll; out8[6] = lvl; out8[7] = n_valid;
-    }
-  }
+  global_combine_body(part_m, part_l, diag, B, nsplit, lse, sums2, global_batch, local_partial, mask, T, gw, lw, out8, red);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -295,8 +239,9 @@ int global_tc_bwd(int B, int Bg, int D, int col_offset, float scale, const float
 // low-latency symmetric CUDA-core implementation for the rank-local case (global_infonce_sym.cu)
 bool global_sym_supported(int B, int Bg, int D);
 size_t global_sym_workspace_bytes(int B, int D);
-int global_sym_fwd(const float* a, const float* b, int B, int D, float scale, float eps, float* norms2, float** part_m,
-                   float** part_l, float** diag, int* nsplit, void* ws, cudaStream_t st);
+int global_sym_fwd(const float* a, const float* b, int B, int D, float scale, float eps, float* norms2, float* lse2,
+                   float* sums2, const float* local_partial, const uint8_t* mask, int T, float gw, float lw, float* out8,
+                   void* ws, cudaStream_t st);
 int global_sym_bwd(const float* a, const float* b, int B, int D, float scale, float eps, const float* lse2, const float* coef2,
                    float** dpart, int* nsplit, void* ws, cudaStream_t st);
 
@@ -334,15 +279,9 @@ extern "C" int cfa_global_infonce_fwd(const float* a_loc, const float* b_loc, co
   if (!workspace || workspace_bytes < cfa_global_infonce_workspace_bytes(B, Bg, D)) return CFA_ERR_WORKSPACE;
   if (out8 && (Bg != B || !local_partial || !mask)) return CFA_ERR_BAD_ARG;   // fused scalar epilogue: single process only
   if (path == 2 && !global_tc_supported(B, Bg, D)) return CFA_ERR_UNSUPPORTED;
-  if (use_sym(B, Bg, D, path)) {
-    float *pm, *pl, *dg;
-    int nsp;
-    const int rc = global_sym_fwd(a_loc, b_loc, B, D, scale, eps, norms2, &pm, &pl, &dg, &nsp, workspace, (cudaStream_t)stream);
-    if (rc != CFA_OK) return rc;
-    global_combine_kernel<<<1, kNT, 0, (cudaStream_t)stream>>>(pm, pl, dg, B, nsp, lse2, sums2, Bg, local_partial, mask, T, gw,
-                                                               lw, out8);
-    return launch_status();
-  }
+  if (use_sym(B, Bg, D, path))          // one launch: the last CTA merges the partials and writes the scalar outputs
+    return global_sym_fwd(a_loc, b_loc, B, D, scale, eps, norms2, lse2, sums2, local_partial, mask, T, gw, lw, out8, workspace,
+                          (cudaStream_t)stream);
   if (use_tc(B, Bg, D, path)) {
     float *pm, *pl, *dg;
     int nsp;

@@ -10,9 +10,19 @@
 // Row norms (F.normalize, losses.py:152-153) are accumulated while the K chunks stream through shared memory.
 // Partials are merged by global_combine_kernel / global_norm_bwd_kernel (global_infonce.cu).
 #include "common.cuh"
+#include "global_combine.cuh"
 #include <math_constants.h>
 
 namespace cfa {
+
+// ticket counter of global_sym_fwd_kernel: the CTA that draws the last ticket merges the partials (global_combine_body)
+// and resets the counter, so no separate single-CTA launch is needed.  One forward at a time per device (the loss
+// kernels all run on one stream).
+__device__ unsigned int g_sym_ticket = 0;
+
+struct SymCombine {
+  float* lse; float* sums2; const float* local_partial; const uint8_t* mask; int T; float gw, lw; float* out8;
+};
 
 constexpr int kSyT = 32;             // tile rows = tile cols
 constexpr int kSyK = 128;            // K chunk
@@ -105,8 +115,7 @@ __device__ __forceinline__ void sy_logits_tile(const float* __restrict__ a, cons
 // ------------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kSyThreads)
 global_sym_fwd_kernel(const float* __restrict__ a, const float* __restrict__ b, int B, int D, float scale, float eps,
-                      float* __restrict__ part_m, float* __restrict__ part_l, float* __restrict__ diag,
-                      float* __restrict__ norms /* [2][B] */) {
+                      float* part_m, float* part_l, float* diag, float* __restrict__ norms /* [2][B] */, const SymCombine cb) {
   __shared__ __align__(16) float As[kSyT * kSyLd];
   __shared__ __align__(16) float Bs[kSyT * kSyLd];
   __shared__ float nrm[64];
@@ -162,6 +171,22 @@ global_sym_fwd_kernel(const float* __restrict__ a, const float* __restrict__ b, 
       part_m[((size_t)1 * nt + rt) * B + gcol] = tmax;
       part_l[((size_t)1 * nt + rt) * B + gcol] = s;
     }
+  }
+  // last CTA: merge the partials of the whole grid (classic threadfence-reduction hand-off)
+  __shared__ unsigned int s_last;
+  __shared__ float red[8];
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int total = gridDim.x * gridDim.y;
+    const unsigned int t = atomicAdd(&g_sym_ticket, 1u);
+    s_last = (t == total - 1) ? 1u : 0u;
+    if (s_last) g_sym_ticket = 0;
+  }
+  __syncthreads();
+  if (s_last) {
+    __threadfence();
+    global_combine_body(part_m, part_l, diag, B, nt, cb.lse, cb.sums2, B, cb.local_partial, cb.mask, cb.T, cb.gw, cb.lw, cb.out8, red);
   }
 }
 
@@ -269,14 +294,16 @@ size_t global_sym_workspace_bytes(int B, int D) {
   return fwd > bwd ? fwd : bwd;
 }
 
-int global_sym_fwd(const float* a, const float* b, int B, int D, float scale, float eps, float* norms2, float** part_m,
-                   float** part_l, float** diag, int* nsplit, void* ws, cudaStream_t st) {
+// forward including the merge of the partials (and the optional SPARC scalar epilogue): ONE launch
+int global_sym_fwd(const float* a, const float* b, int B, int D, float scale, float eps, float* norms2, float* lse2,
+                   float* sums2, const float* local_partial, const uint8_t* mask, int T, float gw, float lw, float* out8,
+                   void* ws, cudaStream_t st) {
   const int nt = global_sym_tiles(B);
-  *part_m = (float*)ws;
-  *part_l = *part_m + (size_t)2 * nt * B;
-  *diag = *part_l + (size_t)2 * nt * B;
-  *nsplit = nt;
-  global_sym_fwd_kernel<<<dim3(nt, nt), kSyThreads, 0, st>>>(a, b, B, D, scale, eps, *part_m, *part_l, *diag, norms2);
+  float* part_m = (float*)ws;
+  float* part_l = part_m + (size_t)2 * nt * B;
+  float* diag = part_l + (size_t)2 * nt * B;
+  const SymCombine cb{lse2, sums2, local_partial, mask, T, gw, lw, out8};
+  global_sym_fwd_kernel<<<dim3(nt, nt), kSyThreads, 0, st>>>(a, b, B, D, scale, eps, part_m, part_l, diag, norms2, cb);
   return launch_status();
 }
 
