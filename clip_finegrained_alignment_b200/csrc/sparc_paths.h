@@ -24,13 +24,13 @@ bool sparc_fwd2_supported(int P, int T, int D, int dtype);
 int sparc_fwd2_launch(const void* v, const void* l, const uint8_t* mask, int B, int P, int T, int D, float thr,
                       float scale, float* row_inv_norm, float* pooled_v, float* pooled_l, float* lse_row, float* lse_col,
                       float* local_partial, float* tt_logits, float* g_inv_norm, void* g_split, float* q_save,
-                      long long* prof, cudaStream_t st);
+                      long long* prof, int dtype, cudaStream_t st);
 
 // restructured tcgen05 backward (sparc_tc_bwd2.cu): needs the forward's saved G (bf16 hi|lo) and Q = G . v^T
 bool sparc_bwd2_supported(int P, int T, int D, int dtype);
 int sparc_bwd2_launch(const void* v, const void* l, const uint8_t* mask, int B, int P, int T, int D, float thr, float scale,
                       const float* row_inv_norm, const float* lse_row, const float* lse_col, const float* coef,
                       const float* tt_logits, const float* g_inv_norm, const void* g_split, const float* q_save,
-                      const float* dpv, const float* dpl, void* dv, void* dl, long long* prof, cudaStream_t st);
+                      const float* dpv, const float* dpl, void* dv, void* dl, long long* prof, int dtype, cudaStream_t st);
 
 }  // namespace cfa

@@ -1232,7 +1232,7 @@ using namespace cfa;
 // path: 0 = auto (tensor cores when the shape/dtype allows, else CUDA cores), 1 = CUDA cores, 2 = tensor cores
 extern "C" int cfa_sparc_path(int P, int T, int D, int dtype, int path) {
   if (path == 1) return 1;
-  const bool ok = sparc_tc_supported(P, T, D, dtype);
+  const bool ok = sparc_tc_supported(P, T, D, dtype);     // bf16 only (fp16: see sparc_fwd2_supported)
   if (path == 2) return ok ? 2 : CFA_ERR_UNSUPPORTED;
   return ok ? 2 : 1;
 }
@@ -1252,7 +1252,8 @@ extern "C" int cfa_debug_set_profile_buffer_fwd(void* device_buffer) {
 extern "C" int cfa_sparc_bwd_path(int P, int T, int D, int dtype, int path) {
   const int which = cfa_sparc_path(P, T, D, dtype, path);
   if (which != 2) return which;
-  return sparc_tc_bwd_supported(P, T, D, dtype) ? 2 : 1;
+  if (dtype == CFA_DTYPE_F16) return 2;
+  return (sparc_tc_bwd_supported(P, T, D, dtype) || sparc_bwd2_supported(P, T, D, dtype)) ? 2 : 1;
 }
 
 extern "C" int cfa_sparc_fwd(const void* v, const void* l, const uint8_t* mask, int B, int P, int T, int D, int dtype,
@@ -1267,7 +1268,7 @@ extern "C" int cfa_sparc_fwd(const void* v, const void* l, const uint8_t* mask, 
     if ((g_split == nullptr) != (q_save == nullptr)) return CFA_ERR_BAD_ARG;
     if (sparc_fwd2_supported(P, T, D, dtype))          // one kernel: norms / pooled means fused into the streaming pass
       return sparc_fwd2_launch(v, l, mask, B, P, T, D, thr, scale, row_inv_norm, pooled_v, pooled_l, lse_row, lse_col,
-                               local_partial, tt_logits, g_inv_norm, g_split, q_save, g_prof_fwd, (cudaStream_t)stream);
+                               local_partial, tt_logits, g_inv_norm, g_split, q_save, g_prof_fwd, dtype, (cudaStream_t)stream);
     return sparc_fwd_tc_launch(v, l, mask, B, P, T, D, thr, scale, row_inv_norm, pooled_v, pooled_l, lse_row, lse_col,
                                local_partial, tt_logits, g_inv_norm, g_split, q_save, (cudaStream_t)stream);
   }
@@ -1286,9 +1287,10 @@ extern "C" int cfa_sparc_bwd(const void* v, const void* l, const uint8_t* mask, 
   if (which < 0) return which;
   if (which == 2) {
     if (!row_inv_norm || !tt_logits || !g_inv_norm) return CFA_ERR_WORKSPACE;
+    if (dtype == CFA_DTYPE_F16 && (!g_split || !q_save)) return CFA_ERR_WORKSPACE;      // fp16: second generation only
     if (g_split && q_save && sparc_bwd2_supported(P, T, D, dtype))      // streaming backward on the saved G / Q
       return sparc_bwd2_launch(v, l, mask, B, P, T, D, thr, scale, row_inv_norm, lse_row, lse_col, coef, tt_logits,
-                               g_inv_norm, g_split, q_save, dpooled_v, dpooled_l, dv, dl, g_prof_buffer,
+                               g_inv_norm, g_split, q_save, dpooled_v, dpooled_l, dv, dl, g_prof_buffer, dtype,
                                (cudaStream_t)stream);
     return sparc_bwd_tc_launch(v, l, mask, B, P, T, D, thr, scale, row_inv_norm, lse_row, lse_col, coef, tt_logits,
                                g_inv_norm, dpooled_v, dpooled_l, dv, dl, (cudaStream_t)stream);

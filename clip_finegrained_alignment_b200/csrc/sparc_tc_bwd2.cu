@@ -140,7 +140,8 @@ __device__ __forceinline__ float b2_colsum16(float* v, int lane) {
 }
 
 // kNksP / kNksT: NP/16 and NT/16 as compile-time constants (fully unrolled issue loops), or 0 = runtime trip counts.
-template <int kNksP, int kNksT>
+// kHalf: the raw embeddings (and dv, dl) are fp16 instead of bf16; on-chip operands and the saved G stay bf16 hi/lo.
+template <int kNksP, int kNksT, bool kHalf>
 __global__ void __launch_bounds__(kB2Threads, 1)
 sparc_bwd2_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmL,
                   const __grid_constant__ CUtensorMap tmG, const Bwd2Params p) {
@@ -241,11 +242,12 @@ sparc_bwd2_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_constant
     // =============================== MMA issuer (warp-uniform control flow, one elected lane issues) ===============================
     const bool leader = elect_one();
     const int nksP = kNksP ? kNksP : NP / 16, nksT = kNksT ? kNksT : NT / 16;
-    const uint32_t id_s = make_idesc_bf16(128, NP, false, false);      // S: K-major x K-major
-    const uint32_t id_dwa = make_idesc_bf16(128, NP, false, true);     // dLhat (K-major) x S_raw (MN-major)
-    const uint32_t id_z = make_idesc_bf16(128, NP, true, true);        // dLhat^T x W
-    const uint32_t id_kn64 = make_idesc_bf16(128, 64, false, true);    // dShat' (K-major) x v tile (MN-major)
-    const uint32_t id_nn64 = make_idesc_bf16(128, 64, true, true);     // dShat'^T / Wg^T (MN-major) x l / G tile (MN-major)
+    const uint32_t id_s = make_idesc16(128, NP, false, false, kHalf, kHalf);      // S: raw l (K-major) x raw v (K-major)
+    const uint32_t id_dwa = make_idesc16(128, NP, false, true, false, false);     // dLhat (K-major) x S_raw (MN-major), bf16 hi/lo
+    const uint32_t id_z = make_idesc16(128, NP, true, true, false, false);        // dLhat^T x W
+    const uint32_t id_kn64 = make_idesc16(128, 64, false, true, false, kHalf);    // dShat' (K-major) x raw v tile (MN-major)
+    const uint32_t id_nn64 = make_idesc16(128, 64, true, true, false, kHalf);     // dShat'^T (MN-major) x raw l tile (MN-major)
+    const uint32_t id_ng64 = make_idesc16(128, 64, true, true, false, false);     // Wg^T (MN-major) x saved G hi/lo tile (bf16)
     const uint64_t sw0 = make_smem_desc(0, 16, 1024, kLayoutSw128);
     auto ilk = [&](const uint8_t* a) { return make_smem_desc(smem_u32(a), il_lbo, 128, kLayoutNone); };   // interleaved, K-major
     auto ilm = [&](const uint8_t* a) { return make_smem_desc(smem_u32(a), 128, il_lbo, kLayoutNone); };   // interleaved, MN-major
@@ -327,9 +329,9 @@ sparc_bwd2_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_constant
         const uint32_t mo = m * mt_m;
         _Pragma("unroll") for (int ks = 0; ks < nksT; ++ks) umma_ss_w(leader, d, m_srhi + mo + ks * ks_m, dl0 + ks * 128, id_nn64, ks != 0);
         _Pragma("unroll") for (int ks = 0; ks < nksT; ++ks) umma_ss_w(leader, d, m_srlo + mo + ks * ks_m, dl0 + ks * 128, id_nn64, true);
-        _Pragma("unroll") for (int ks = 0; ks < nksT; ++ks) umma_ss_w(leader, d, m_whi + mo + ks * ks_m, gh0 + ks * 128, id_nn64, true);
-        _Pragma("unroll") for (int ks = 0; ks < nksT; ++ks) umma_ss_w(leader, d, m_whi + mo + ks * ks_m, gl0 + ks * 128, id_nn64, true);
-        _Pragma("unroll") for (int ks = 0; ks < nksT; ++ks) umma_ss_w(leader, d, m_wlo + mo + ks * ks_m, gh0 + ks * 128, id_nn64, true);
+        _Pragma("unroll") for (int ks = 0; ks < nksT; ++ks) umma_ss_w(leader, d, m_whi + mo + ks * ks_m, gh0 + ks * 128, id_ng64, true);
+        _Pragma("unroll") for (int ks = 0; ks < nksT; ++ks) umma_ss_w(leader, d, m_whi + mo + ks * ks_m, gl0 + ks * 128, id_ng64, true);
+        _Pragma("unroll") for (int ks = 0; ks < nksT; ++ks) umma_ss_w(leader, d, m_wlo + mo + ks * ks_m, gh0 + ks * 128, id_ng64, true);
       }
       umma_commit_w(leader, out_full + buf);
       umma_commit_w(leader, empty + s);
@@ -645,12 +647,12 @@ sparc_bwd2_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_constant
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
         float rv[8], ov[8];
-        b2_unpack8(*reinterpret_cast<const uint4*>(sc + lane * 80 + g * 16), rv);
+        unpack_raw8<kHalf>(*reinterpret_cast<const uint4*>(sc + lane * 80 + g * 16), rv);
         const float4 d0v = *reinterpret_cast<const float4*>(dp + 8 * g), d1v = *reinterpret_cast<const float4*>(dp + 8 * g + 4);
         const float dpv[8] = {d0v.x, d0v.y, d0v.z, d0v.w, d1v.x, d1v.y, d1v.z, d1v.w};
 #pragma unroll
         for (int j = 0; j < 8; ++j) ov[j] = fmaf(dpv[j], dscale, fmaf(-rv[j], fac, x[8 * g + j]));
-        *reinterpret_cast<uint4*>(sc + lane * 80 + g * 16) = b2_pack8(ov);
+        *reinterpret_cast<uint4*>(sc + lane * 80 + g * 16) = pack_raw8<kHalf>(ov);
       }
       __syncwarp();
 #pragma unroll
@@ -723,7 +725,8 @@ sparc_bwd2_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_constant
 }
 
 bool sparc_bwd2_supported(int P, int T, int D, int dtype) {
-  if (!sparc_tc_supported(P, T, D, dtype)) return false;
+  if (dtype != CFA_DTYPE_BF16) return false;           // see sparc_fwd2_supported: mixed fp16 x bf16 MMAs are illegal
+  if (!sparc_tc_supported(P, T, D, CFA_DTYPE_BF16)) return false;
   const Bwd2Layout L = bwd2_layout(P, T, D);
   if (L.NP > 256 || L.NT > 128 || D % 64) return false;
   return L.total + 1024 <= 227 * 1024;
@@ -732,23 +735,29 @@ bool sparc_bwd2_supported(int P, int T, int D, int dtype) {
 int sparc_bwd2_launch(const void* v, const void* l, const uint8_t* mask, int B, int P, int T, int D, float thr, float scale,
                       const float* row_inv_norm, const float* lse_row, const float* lse_col, const float* coef,
                       const float* tt_logits, const float* g_inv_norm, const void* g_split, const float* q_save,
-                      const float* dpv, const float* dpl, void* dv, void* dl, long long* prof, cudaStream_t st) {
+                      const float* dpv, const float* dpl, void* dv, void* dl, long long* prof, int dtype, cudaStream_t st) {
+  const bool half = dtype == CFA_DTYPE_F16;
+  if (half) return CFA_ERR_UNSUPPORTED;
   const Bwd2Layout L = bwd2_layout(P, T, D);
   CUtensorMap tmV, tmL, tmG;
   int rc;
-  if ((rc = make_tmap_bf16_3d(&tmV, v, D, P, B, 64, L.NP)) != CFA_OK) return rc;
-  if ((rc = make_tmap_bf16_3d(&tmL, l, D, T, B, 64, L.NT)) != CFA_OK) return rc;
+  if ((rc = make_tmap_bf16_3d(&tmV, v, D, P, B, 64, L.NP, half)) != CFA_OK) return rc;
+  if ((rc = make_tmap_bf16_3d(&tmL, l, D, T, B, 64, L.NT, half)) != CFA_OK) return rc;
   if ((rc = make_tmap_bf16_3d(&tmG, g_split, D, T, 2 * (uint64_t)B, 64, L.NT)) != CFA_OK) return rc;
   Bwd2Params prm{prof, P, T, D, thr, scale, mask, row_inv_norm, row_inv_norm + (size_t)B * P, lse_row, lse_col, coef,
                  tt_logits, g_inv_norm, q_save, dpv, dpl, (const bf16*)v, (const bf16*)l, (bf16*)dv, (bf16*)dl};
   const size_t smem = L.total + 1024;
+#define CFA_B2_LAUNCH(NP_, NT_, HALF)                                                                                     \
+  do {                                                                                                                    \
+    CFA_CUDA_TRY(cudaFuncSetAttribute(sparc_bwd2_kernel<NP_, NT_, HALF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    sparc_bwd2_kernel<NP_, NT_, HALF><<<B, kB2Threads, smem, st>>>(tmV, tmL, tmG, prm);                                   \
+  } while (0)
   if (L.NP == 208 && L.NT == 80) {          // ViT-B/16 (P = 196 / 197, T = 77): fully unrolled issue loops
-    CFA_CUDA_TRY(cudaFuncSetAttribute(sparc_bwd2_kernel<13, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    sparc_bwd2_kernel<13, 5><<<B, kB2Threads, smem, st>>>(tmV, tmL, tmG, prm);
+    CFA_B2_LAUNCH(13, 5, false);
   } else {
-    CFA_CUDA_TRY(cudaFuncSetAttribute(sparc_bwd2_kernel<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    sparc_bwd2_kernel<0, 0><<<B, kB2Threads, smem, st>>>(tmV, tmL, tmG, prm);
+    CFA_B2_LAUNCH(0, 0, false);
   }
+#undef CFA_B2_LAUNCH
   return launch_status();
 }
 

@@ -97,7 +97,8 @@ __device__ __forceinline__ float f2_colsum16(float* v, int lane) {
   return v[0];
 }
 
-template <int kNksP>
+// kHalf: the raw embeddings are fp16 (torch.autocast's default) instead of bf16; on-chip operands stay bf16 hi/lo
+template <int kNksP, bool kHalf>
 __global__ void __launch_bounds__(kF2Threads, 1)
 sparc_fwd2_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmL, const Fwd2Params p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -169,9 +170,10 @@ sparc_fwd2_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_constant
   } else if (warp == 1) {
     // =============================== MMA issuer (warp-uniform control flow, one elected lane issues) ===============================
     const bool leader = elect_one();
-    const uint32_t idesc_s = make_idesc_bf16(128, NP, false, false);
-    const uint32_t idesc_g = make_idesc_bf16(128, 64, false, true);
-    const uint32_t idesc_l = make_idesc_bf16(128, NT, false, false);
+    const uint32_t idesc_s = make_idesc16(128, NP, false, false, kHalf, kHalf);     // raw l x raw v
+    const uint32_t idesc_g = make_idesc16(128, 64, false, true, false, kHalf);      // W (bf16 hi/lo) x raw v
+    const uint32_t idesc_l = make_idesc16(128, NT, false, false, false, kHalf);     // G (bf16 hi/lo) x raw l
+    const uint32_t idesc_q = make_idesc16(128, NP, false, false, false, kHalf);     // G (bf16 hi/lo) x raw v
     const uint32_t il_lbo = (uint32_t)NT * 16;
     const uint64_t sw0 = make_smem_desc(0, 16, 1024, kLayoutSw128);
     const uint64_t ilk_whi = make_smem_desc(smem_u32(Whi), il_lbo, 128, kLayoutNone);
@@ -223,7 +225,7 @@ sparc_fwd2_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_constant
         for (int k = 0; k < 4; ++k) umma_ss_w(leader, tmem + kF2cL, ga + k * ilk_step, dl0 + 2 * k, idesc_l, (kb | half | k) != 0);
         if (p.q_save) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) umma_ss_w(leader, tmem + kF2cS, ga + k * ilk_step, dv0 + 2 * k, idesc_s, (kb | half | k) != 0);
+          for (int k = 0; k < 4; ++k) umma_ss_w(leader, tmem + kF2cS, ga + k * ilk_step, dv0 + 2 * k, idesc_q, (kb | half | k) != 0);
         }
       }
       umma_commit_w(leader, gs_free + buf);
@@ -273,13 +275,10 @@ sparc_fwd2_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_constant
         const int r = lane + 32 * k;
         if (r < NP) {
           const uint4 raw = *reinterpret_cast<const uint4*>(st + L.l_bytes + r * 128 + ((ew ^ (r & 7)) << 4));
-          const uint32_t w4[4] = {raw.x, raw.y, raw.z, raw.w};
+          float f8[8];
+          unpack_raw8<kHalf>(raw, f8);
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const float f0 = __uint_as_float(w4[i] << 16), f1 = __uint_as_float(w4[i] & 0xffff0000u);
-            ssv[k] = fmaf(f0, f0, ssv[k]); ssv[k] = fmaf(f1, f1, ssv[k]);
-            acc[2 * i] += f0; acc[2 * i + 1] += f1;
-          }
+          for (int i = 0; i < 8; ++i) { ssv[k] = fmaf(f8[i], f8[i], ssv[k]); acc[i] += f8[i]; }
         }
       }
 #pragma unroll
@@ -287,14 +286,11 @@ sparc_fwd2_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_constant
         const int r = lane + 32 * k;
         if (r < NT) {
           const uint4 raw = *reinterpret_cast<const uint4*>(st + r * 128 + ((ew ^ (r & 7)) << 4));
-          const uint32_t w4[4] = {raw.x, raw.y, raw.z, raw.w};
           const float m = msk[r];
+          float f8[8];
+          unpack_raw8<kHalf>(raw, f8);
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const float f0 = __uint_as_float(w4[i] << 16), f1 = __uint_as_float(w4[i] & 0xffff0000u);
-            ssl[k] = fmaf(f0, f0, ssl[k]); ssl[k] = fmaf(f1, f1, ssl[k]);
-            acc[8 + 2 * i] = fmaf(m, f0, acc[8 + 2 * i]); acc[8 + 2 * i + 1] = fmaf(m, f1, acc[8 + 2 * i + 1]);
-          }
+          for (int i = 0; i < 8; ++i) { ssl[k] = fmaf(f8[i], f8[i], ssl[k]); acc[8 + i] = fmaf(m, f8[i], acc[8 + i]); }
         }
       }
       __syncwarp();
@@ -559,31 +555,38 @@ static int fwd2_pick_stages(int P, int T, int D) {
 }
 
 bool sparc_fwd2_supported(int P, int T, int D, int dtype) {
-  if (!sparc_tc_supported(P, T, D, dtype)) return false;
+  // bf16 only: tcgen05 kind::f16 rejects MIXED operand formats (an fp16 raw tile against the bf16 hi/lo operands produced
+  // on chip raises "illegal instruction" on sm_100a — measured), and fp16 hi/lo operands have too little range for the
+  // gradient tiles.  fp16 embeddings therefore run on the fp32-exact CUDA-core path.  (The kHalf template parameter is
+  // kept for the day the on-chip operands move to fp16 with range scaling; it is never instantiated.)
+  if (dtype != CFA_DTYPE_BF16) return false;
+  if (!sparc_tc_supported(P, T, D, CFA_DTYPE_BF16)) return false;           // shape limits of the tensor-core layouts
   return fwd2_pick_stages(P, T, D) != 0;
 }
 
 int sparc_fwd2_launch(const void* v, const void* l, const uint8_t* mask, int B, int P, int T, int D, float thr,
                       float scale, float* row_inv_norm, float* pooled_v, float* pooled_l, float* lse_row, float* lse_col,
                       float* local_partial, float* tt_logits, float* g_inv_norm, void* g_split, float* q_save,
-                      long long* prof, cudaStream_t st) {
+                      long long* prof, int dtype, cudaStream_t st) {
+  const bool half = dtype == CFA_DTYPE_F16;
   const int NS = fwd2_pick_stages(P, T, D);
   if (NS == 0) return CFA_ERR_UNSUPPORTED;
   const Fwd2Layout L = fwd2_layout(P, T, D, NS);
   CUtensorMap tmV, tmL;
   int rc;
-  if ((rc = make_tmap_bf16_3d(&tmV, v, D, P, B, 64, L.NP)) != CFA_OK) return rc;
-  if ((rc = make_tmap_bf16_3d(&tmL, l, D, T, B, 64, L.NT)) != CFA_OK) return rc;
+  if ((rc = make_tmap_bf16_3d(&tmV, v, D, P, B, 64, L.NP, half)) != CFA_OK) return rc;
+  if ((rc = make_tmap_bf16_3d(&tmL, l, D, T, B, 64, L.NT, half)) != CFA_OK) return rc;
   Fwd2Params prm{prof, P, T, D, NS, thr, scale, mask, row_inv_norm, row_inv_norm + (size_t)B * P, pooled_v, pooled_l, lse_row,
                  lse_col, local_partial, tt_logits, g_inv_norm, (bf16*)g_split, q_save};
   const size_t smem = L.total + 1024;
-  if (L.NP == 208) {
-    CFA_CUDA_TRY(cudaFuncSetAttribute(sparc_fwd2_kernel<13>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    sparc_fwd2_kernel<13><<<B, kF2Threads, smem, st>>>(tmV, tmL, prm);
-  } else {
-    CFA_CUDA_TRY(cudaFuncSetAttribute(sparc_fwd2_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    sparc_fwd2_kernel<0><<<B, kF2Threads, smem, st>>>(tmV, tmL, prm);
-  }
+#define CFA_F2_LAUNCH(NKS, HALF)                                                                                          \
+  do {                                                                                                                    \
+    CFA_CUDA_TRY(cudaFuncSetAttribute(sparc_fwd2_kernel<NKS, HALF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    sparc_fwd2_kernel<NKS, HALF><<<B, kF2Threads, smem, st>>>(tmV, tmL, prm);                                             \
+  } while (0)
+  if (half) return CFA_ERR_UNSUPPORTED;
+  if (L.NP == 208) CFA_F2_LAUNCH(13, false); else CFA_F2_LAUNCH(0, false);
+#undef CFA_F2_LAUNCH
   return launch_status();
 }
 

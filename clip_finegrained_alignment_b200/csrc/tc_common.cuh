@@ -141,6 +141,44 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, bool a_mn_m
          ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+// same with the two operand formats chosen independently (true = fp16, false = bf16): raw fp16 embedding tiles (what
+// torch.autocast hands the loss by default) are multiplied with the bf16 hi/lo operands produced on chip
+__host__ __device__ constexpr uint32_t make_idesc16(int M, int N, bool a_mn_major, bool b_mn_major, bool a_f16, bool b_f16) {
+  return (1u << 4) | ((a_f16 ? 0u : 1u) << 7) | ((b_f16 ? 0u : 1u) << 10) | ((a_mn_major ? 1u : 0u) << 15) |
+         ((b_mn_major ? 1u : 0u) << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// 8 raw 16-bit embedding values (bf16 or fp16) <-> fp32
+template <bool kHalf>
+__device__ __forceinline__ void unpack_raw8(const uint4& u, float* f) {
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    if (kHalf) {
+      const float2 t = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
+      f[2 * i] = t.x; f[2 * i + 1] = t.y;
+    } else {
+      f[2 * i] = __uint_as_float(w[i] << 16);
+      f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+    }
+  }
+}
+template <bool kHalf>
+__device__ __forceinline__ uint4 pack_raw8(const float* f) {
+  uint32_t w[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    if (kHalf) {
+      const __half2 t = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
+      w[i] = *reinterpret_cast<const uint32_t*>(&t);
+    } else {
+      const __nv_bfloat162 t = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+      w[i] = *reinterpret_cast<const uint32_t*>(&t);
+    }
+  }
+  return make_uint4(w[0], w[1], w[2], w[3]);
+}
+
 // one lane of a converged warp
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
@@ -220,14 +258,14 @@ static inline PFN_tmapEncodeTiled get_tmap_encoder() {
 // bf16 tensor [d2][d1][d0] (d0 contiguous), box [1][box1][box0], zero fill out of bounds.
 // box0 = 64 elements -> 128-byte swizzle, box0 = 32 elements -> 64-byte swizzle.
 static inline int make_tmap_bf16_3d(CUtensorMap* m, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint32_t box0,
-                                    uint32_t box1) {
+                                    uint32_t box1, bool f16 = false) {
   PFN_tmapEncodeTiled enc = get_tmap_encoder();
   if (!enc) return CFA_ERR_UNSUPPORTED;
   cuuint64_t dims[3] = {d0, d1, d2};
   cuuint64_t strides[2] = {d0 * 2, d0 * d1 * 2};
   cuuint32_t box[3] = {box0, box1, 1};
   cuuint32_t estr[3] = {1, 1, 1};
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+  CUresult r = enc(m, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, box0 == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);

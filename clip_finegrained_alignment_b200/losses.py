@@ -188,7 +188,7 @@ class _SparcFunction(torch.autograd.Function):
         # tt_logits [B,T,T] | g_inv_norm [B,T]
         # | g_split [B,2,T,D] bf16 | q_save [B,T,NP]   (every piece starts 128-byte aligned: TMA / float4 access)
         NP = (P + 15) & ~15
-        saved = code == _lib.DTYPE_CODE[torch.bfloat16] and path != 1
+        saved = path != 1 and _L.cfa_sparc_path(P, T, D, code, path) == 2      # tensor-core path saves G (hi|lo) and Q
         sizes = (2 * B * D, 8, B * T, B * T, 2 * B, B * (P + T), B * T * T, B * T,
                  B * T * D if saved else 0, B * T * NP if saved else 0)
         off = [0]

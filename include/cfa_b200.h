@@ -146,7 +146,8 @@ int cfa_sparc_fwd(const void* v, const void* l, const uint8_t* mask, int B, int 
  * g_split / q_save are optional (both NULL or both set): with them the tensor-core backward runs as pure
  * TMA -> tcgen05 streams (sparc_tc_bwd2.cu), without them it recomputes G per D-block (sparc_tc.cu).
  * path: 0 = auto, 1 = fp32-exact CUDA-core kernels, 2 = tcgen05 tensor-core kernels (bf16, D % 256 == 0,
- * P <= 256, T <= 128; CFA_ERR_UNSUPPORTED otherwise).  cfa_sparc_path reports what `auto` resolves to.
+ * P <= 256, T <= 128; CFA_ERR_UNSUPPORTED otherwise).  cfa_sparc_path reports what `auto` resolves to.  fp16 embeddings
+ * run on the CUDA-core kernels: tcgen05 rejects mixed fp16 x bf16 operand formats and the on-chip operands are bf16 hi/lo.
  */
 int cfa_sparc_bwd(const void* v, const void* l, const uint8_t* mask, int B, int P, int T, int D, int dtype,
                   float thr, float scale, const float* row_inv_norm, const float* lse_row, const float* lse_col,

@@ -88,6 +88,30 @@ def test_sparc_tc_vs_oracle(B, P, T, D, s):
     assert rel_err(dl.float(), rl) <= 1e-3 + 2.0 ** -8
 
 
+def test_sparc_fp16_inputs_route_to_cuda_cores():
+    """fp16 embeddings (torch.autocast's default; finetuner.py:120-134 with GradScaler): tcgen05 rejects mixed
+    fp16 x bf16 operand formats, so they run on the fp32-exact CUDA-core kernels; gradients come back in fp16.  The
+    upstream gradient is scaled like GradScaler does (2^16)."""
+    from clip_finegrained_alignment_b200 import SPARCLoss, _lib
+    B, P, T, D, s = 3, 197, 77, 512, 14.0
+    g = torch.Generator().manual_seed(B * 31 + P)
+    v0 = (torch.randn(B, P, D, generator=g) * 0.5).to(torch.float16)
+    l0 = (torch.randn(B, T, D, generator=g) * 0.5).to(torch.float16)
+    m = torch.ones(B, T, dtype=torch.bool)
+    assert _lib.lib.cfa_sparc_path(P, T, D, _lib.DTYPE_CODE[torch.float16], 0) == 1
+    assert _lib.lib.cfa_sparc_path(P, T, D, _lib.DTYPE_CODE[torch.bfloat16], 0) == 2
+    v = v0.cuda().requires_grad_(True); l = l0.cuda().requires_grad_(True)
+    out = SPARCLoss(_cfg(1.0 / P, 1.0, 1.0, s))(v, l, m.cuda())
+    (out["total_loss"] * 65536.0).backward()
+    thr = float(torch.tensor(1.0 / P, dtype=torch.float32))
+    o = lo.sparc_forward(v0.double(), l0.double(), m, thr, 1.0, 1.0, s)
+    rv, rl = lo.sparc_backward(o, {"total_loss": 65536.0})
+    for k in lo.SPARC_KEYS:
+        assert abs(float(out[k]) - float(o[k])) <= 1e-4 * max(1.0, abs(float(o[k]))), k
+    assert v.grad.dtype == torch.float16 and torch.isfinite(v.grad).all() and torch.isfinite(l.grad).all()
+    assert rel_err(v.grad.float(), rv) <= 1e-3 and rel_err(l.grad.float(), rl) <= 1e-3
+
+
 def test_sparc_tc_padded_mask():
     g = torch.Generator().manual_seed(3)
     B, P, T, D = 4, 196, 77, 256
