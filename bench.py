@@ -295,7 +295,7 @@ def main():
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG", "WARN")        # keep NCCL's version banner off stdout (one JSON line only)
+        os.environ["NCCL_DEBUG"] = os.environ.get("CFA_NCCL_DEBUG", "WARN")   # keep NCCL's version banner off stdout (one JSON line only)
         dist.init_process_group("nccl", device_id=dev)
     from clip_finegrained_alignment_b200 import SPARCLoss, _lib
     pk = peaks()

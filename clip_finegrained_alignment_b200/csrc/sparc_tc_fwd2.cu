@@ -201,10 +201,14 @@ sparc_fwd2_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_constant
     tc_fence_after();
     stamp();
     const int nks = kNksP ? kNksP : NP / 16;
+    long long wfull = 0, wgfree = 0, wgs = 0;
     auto issue_g = [&](int kb) {
       const int u = KB + kb, s = u % NS, buf = kb & 1;
+      const long long w0 = clock64();
       mbar_wait(full + s, (u / NS) & 1);
+      const long long w1 = clock64();
       mbar_wait(g_free + buf, ((kb >> 1) & 1) ^ 1);
+      wfull += w1 - w0; wgfree += clock64() - w1;
       tc_fence_after();
       const uint64_t dv0 = sw0 | ((smem_u32(base + (size_t)s * L.slot) + L.l_bytes) >> 4);
       const uint32_t d = tmem + kF2cG + 64 * buf;
@@ -214,7 +218,9 @@ sparc_fwd2_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_constant
     };
     auto issue_l = [&](int kb) {
       const int u = KB + kb, s = u % NS, buf = kb & 1;
+      const long long w0 = clock64();
       mbar_wait(gs_ready + buf, (kb >> 1) & 1);
+      wgs += clock64() - w0;
       tc_fence_after();
       const uint32_t sl = smem_u32(base + (size_t)s * L.slot);
       const uint64_t dl0 = sw0 | (sl >> 4), dv0 = sw0 | ((sl + L.l_bytes) >> 4);
@@ -238,6 +244,7 @@ sparc_fwd2_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_constant
     }
     umma_commit_w(leader, l_full);
     stamp();
+    if (pf) { pf[8] = wfull; pf[9] = wgfree; pf[10] = wgs; }
   } else {
     // =============================== epilogue: 8 warps, 2 per TMEM lane quarter ===============================
     const int ew = warp - 2, q = warp & 3, h = ew >> 2;
