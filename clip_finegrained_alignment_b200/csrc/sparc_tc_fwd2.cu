@@ -21,7 +21,7 @@ namespace cfa {
 using namespace tc;
 typedef __nv_bfloat16 bf16;
 
-constexpr int kF2Threads = 320;
+constexpr int kF2Threads = 352;      // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue, warp 10 pooled means
 constexpr float kF2NormEps = 1e-12f, kF2MinMaxEps = 1e-8f, kF2ClampEps = 1e-8f;
 constexpr uint32_t kF2cS = 0, kF2cG = 256, kF2cL = 384;
 
@@ -119,7 +119,7 @@ sparc_fwd2_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_constant
   float* xch = (float*)(base + L.off_x);              // [2][2][NT][4]
   uint64_t* bars = (uint64_t*)(base + L.off_bar);
   uint64_t* full = bars;                              // [NS]
-  uint64_t* empty0 = bars + NS;                       // [NS] pass-0 uses: MMA commit + 8 epilogue warps
+  uint64_t* empty0 = bars + NS;                       // [NS] pass-0 uses: MMA commit + 8 epilogue warps + pool warp
   uint64_t* empty1 = bars + 2 * NS;                   // [NS] pass-1 uses: MMA commit
   uint64_t* bb = bars + 3 * NS;
   uint64_t* s_full = bb + 0;
@@ -132,7 +132,7 @@ sparc_fwd2_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_constant
   uint32_t* tmem_slot = (uint32_t*)(bb + 11);
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < NS; ++i) { mbar_init(full + i, 1); mbar_init(empty0 + i, 9); mbar_init(empty1 + i, 1); }
+    for (int i = 0; i < NS; ++i) { mbar_init(full + i, 1); mbar_init(empty0 + i, 10); mbar_init(empty1 + i, 1); }
     mbar_init(s_full, 1); mbar_init(w_ready, 8); mbar_init(l_full, 1);
     for (int i = 0; i < 2; ++i) { mbar_init(g_full + i, 1); mbar_init(g_free + i, 8); mbar_init(gs_ready + i, 8); mbar_init(gs_free + i, 1); }
     fence_barrier_init();
@@ -245,6 +245,59 @@ sparc_fwd2_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_constant
     umma_commit_w(leader, l_full);
     stamp();
     if (pf) { pf[8] = wfull; pf[9] = wgfree; pf[10] = wgs; }
+  } else if (warp == 10) {
+    // =============================== pooled means (losses.py:207-212), pass 0 only ===============================
+    // lane -> (16-byte chunk c = lane % 8, row group g = lane / 8): rows r = g, g+4, ... of the tile, 8 columns each
+    // (conflict-free under the 128-byte swizzle, 20 independent 128-bit loads per block), then two shuffle steps over the
+    // 4 row groups.  The text mean always comes from here; the image mean only when there is no spare MMA row (see E1).
+    const bool pool_tc = T < NT;
+    float cnt = 0.f;
+    for (int t = 0; t < T; ++t) cnt += msk[t];
+    const float inv_cnt = 1.f / fmaxf(cnt, kF2ClampEps), invP = 1.f / (float)P;
+    const int c = lane & 7, g = lane >> 3;
+    for (int u = 0; u < KB; ++u) {
+      const int s = u % NS;
+      mbar_wait(full + s, (u / NS) & 1);
+      const uint8_t* st = base + (size_t)s * L.slot;
+      float al[8], av[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { al[i] = 0.f; av[i] = 0.f; }
+#pragma unroll 5
+      for (int r = g; r < NT; r += 4) {                 // rows beyond T are zero-filled by TMA and have msk = 0
+        float f8[8];
+        unpack_raw8<kHalf>(*reinterpret_cast<const uint4*>(st + r * 128 + ((c ^ (r & 7)) << 4)), f8);
+        const float m = msk[r];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) al[i] = fmaf(m, f8[i], al[i]);
+      }
+      if (!pool_tc) {
+#pragma unroll 4
+        for (int r = g; r < NP; r += 4) {
+          float f8[8];
+          unpack_raw8<kHalf>(*reinterpret_cast<const uint4*>(st + L.l_bytes + r * 128 + ((c ^ (r & 7)) << 4)), f8);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) av[i] += f8[i];
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(empty0 + s);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        al[i] += __shfl_xor_sync(0xffffffffu, al[i], 8);
+        al[i] += __shfl_xor_sync(0xffffffffu, al[i], 16);
+        if (!pool_tc) { av[i] += __shfl_xor_sync(0xffffffffu, av[i], 8); av[i] += __shfl_xor_sync(0xffffffffu, av[i], 16); }
+      }
+      if (g == 0) {
+        float* pl = p.pooled_l + (size_t)b * D + u * 64 + 8 * c;
+        *reinterpret_cast<float4*>(pl) = make_float4(al[0] * inv_cnt, al[1] * inv_cnt, al[2] * inv_cnt, al[3] * inv_cnt);
+        *reinterpret_cast<float4*>(pl + 4) = make_float4(al[4] * inv_cnt, al[5] * inv_cnt, al[6] * inv_cnt, al[7] * inv_cnt);
+        if (!pool_tc) {
+          float* pv = p.pooled_v + (size_t)b * D + u * 64 + 8 * c;
+          *reinterpret_cast<float4*>(pv) = make_float4(av[0] * invP, av[1] * invP, av[2] * invP, av[3] * invP);
+          *reinterpret_cast<float4*>(pv + 4) = make_float4(av[4] * invP, av[5] * invP, av[6] * invP, av[7] * invP);
+        }
+      }
+    }
   } else {
     // =============================== epilogue: 8 warps, 2 per TMEM lane quarter ===============================
     const int ew = warp - 2, q = warp & 3, h = ew >> 2;
@@ -265,6 +318,7 @@ sparc_fwd2_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_constant
 
     // ---- pass 0 side job: row norms and pooled means straight from the TMA tiles.  Warp ew owns the ew-th 16-byte chunk
     // (8 columns) of every row of the block, lane l the rows l, l+32, ...  (conflict-free under the 128-byte swizzle)
+    const bool pool_tc = T < NT;                        // a spare MMA row exists (T not a multiple of 16): see E1
     float ssv[8], ssl[4];                               // this thread's rows: r = lane + 32 k  (NP <= 256, NT <= 128)
 #pragma unroll
     for (int k = 0; k < 8; ++k) ssv[k] = 0.f;
@@ -274,9 +328,8 @@ sparc_fwd2_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_constant
       const int s = u % NS;
       mbar_wait(full + s, (u / NS) & 1);
       const uint8_t* st = base + (size_t)s * L.slot;
-      float acc[16];
-#pragma unroll
-      for (int j = 0; j < 16; ++j) acc[j] = 0.f;
+      // (the pooled IMAGE mean comes out of the tensor core — spare MMA row, see E1 — so this job stays short: a longer
+      // hold on the pass-0 slots throttles the TMA stream)
 #pragma unroll
       for (int k = 0; k < 8; ++k) {                     // v rows
         const int r = lane + 32 * k;
@@ -284,8 +337,8 @@ sparc_fwd2_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_constant
           const uint4 raw = *reinterpret_cast<const uint4*>(st + L.l_bytes + r * 128 + ((ew ^ (r & 7)) << 4));
           float f8[8];
           unpack_raw8<kHalf>(raw, f8);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) { ssv[k] = fmaf(f8[i], f8[i], ssv[k]); acc[i] += f8[i]; }
+          ssv[k] += (f8[0] * f8[0] + f8[1] * f8[1]) + (f8[2] * f8[2] + f8[3] * f8[3]) +
+                    ((f8[4] * f8[4] + f8[5] * f8[5]) + (f8[6] * f8[6] + f8[7] * f8[7]));
         }
       }
 #pragma unroll
@@ -293,19 +346,14 @@ sparc_fwd2_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_constant
         const int r = lane + 32 * k;
         if (r < NT) {
           const uint4 raw = *reinterpret_cast<const uint4*>(st + r * 128 + ((ew ^ (r & 7)) << 4));
-          const float m = msk[r];
           float f8[8];
           unpack_raw8<kHalf>(raw, f8);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) { ssl[k] = fmaf(f8[i], f8[i], ssl[k]); acc[8 + i] = fmaf(m, f8[i], acc[8 + i]); }
+          ssl[k] += (f8[0] * f8[0] + f8[1] * f8[1]) + (f8[2] * f8[2] + f8[3] * f8[3]) +
+                    ((f8[4] * f8[4] + f8[5] * f8[5]) + (f8[6] * f8[6] + f8[7] * f8[7]));
         }
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(empty0 + s);           // this warp is done with the tile
-      const float cs = f2_colsum16(acc, lane);
-      const int d = u * 64 + 8 * ew + (lane & 7);
-      if (lane < 8) p.pooled_v[(size_t)b * D + d] = cs * invP;                    // losses.py:207
-      else if (lane < 16) p.pooled_l[(size_t)b * D + d] = cs * inv_cnt;           // losses.py:210-212
     }
     stamp();
     {
@@ -335,6 +383,7 @@ sparc_fwd2_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_constant
     }
     const bool valid = row < T && msk[inT ? row : 0] != 0.f;
     const float il = inT ? iln[row] : 0.f;
+    const bool pool_row = pool_tc && row == T;
 
     // ---- E1: S -> W   (column halves; row statistics exchanged through shared memory)
     const int psplit = ((NP / 16 + 1) / 2) * 16;
@@ -386,6 +435,9 @@ sparc_fwd2_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_constant
       for (int j = 0; j < 16; ++j) {
         const float nn = (x[j] * il * ivn[c0 + j] - mn) * inv_rng;
         x[j] = (valid && c0 + j < P && !(nn < p.thr)) ? nn * inv_sigma : 0.f;
+        // the first unused MMA row (t = T < NT) carries 1/P: G[T] = W[T] . v is then the pooled image embedding
+        // (losses.py:207) for free — the tensor core computes all 128 rows anyway
+        if (pool_row) x[j] = (c0 + j < P) ? invP : 0.f;
       }
       if (inT) {
 #pragma unroll
@@ -417,6 +469,11 @@ sparc_fwd2_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_constant
       __syncwarp();
       if (lane == 0) mbar_arrive(g_free + buf);
       mbar_wait(gs_free + buf, ((kb >> 1) & 1) ^ 1);
+      if (pool_row) {                                   // G[T] = mean_p v[p] for this warp's 32 columns
+        float* pv = p.pooled_v + (size_t)b * D + kb * 64 + 32 * h;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(pv + j) = make_float4(x[j], x[j + 1], x[j + 2], x[j + 3]);
+      }
       if (inT) {
         uint8_t* gh = Gs + (size_t)(2 * buf) * L.g_bytes;
         uint8_t* gl = gh + L.g_bytes;
@@ -430,16 +487,28 @@ sparc_fwd2_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_constant
           const uint32_t off = il_offset(NT, row, 32 * h + 8 * g);
           *reinterpret_cast<uint4*>(gh + off) = hi;
           *reinterpret_cast<uint4*>(gl + off) = lo;
-          if (p.g_split && row < T) {
-            bf16* gdst = p.g_split + (((size_t)b * 2) * T + row) * D + kb * 64 + 32 * h + 8 * g;
-            *reinterpret_cast<uint4*>(gdst) = hi;
-            *reinterpret_cast<uint4*>(gdst + (size_t)T * D) = lo;
-          }
         }
       }
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(gs_ready + buf);
+      // saved copy for the backward, OFF the critical chain and transposed: this warp re-reads the 32 rows x 4 chunks it
+      // has just written (lane -> row 8 it + lane / 4, chunk lane % 4), so one STG covers 8 rows x 64 contiguous bytes
+      // instead of 32 rows x 16 bytes.  The buffer is only overwritten by this same warp two blocks later.
+      if (p.g_split) {
+        const uint8_t* gh = Gs + (size_t)(2 * buf) * L.g_bytes;
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+          const int r = 32 * q + it * 8 + (lane >> 2), c = 4 * h + (lane & 3);
+          if (r < T) {
+            const uint32_t off = il_offset(NT, r, 8 * c);
+            const uint4 hi = *reinterpret_cast<const uint4*>(gh + off), lo = *reinterpret_cast<const uint4*>(gh + L.g_bytes + off);
+            bf16* gdst = p.g_split + (((size_t)b * 2) * T + r) * D + kb * 64 + 8 * c;
+            *reinterpret_cast<uint4*>(gdst) = hi;
+            *reinterpret_cast<uint4*>(gdst + (size_t)T * D) = lo;
+          }
+        }
+      }
     }
     {
       float* xme = xme0 + xset;
@@ -483,7 +552,9 @@ sparc_fwd2_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_constant
       rmax = nm;
     }
     if (inT) { xme0[0] = rmax; xme0[1] = rsum; xme0[2] = diag; }
+    stamp();
     f2_epi_bar();                                       // exchange set 0; the logits are in smem
+    stamp();
     float ce = 0.f;
     if (h == 0) {
       if (valid) {
@@ -510,7 +581,9 @@ sparc_fwd2_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_constant
       float* xme = xme0 + xset;
       float* xot = xot0 + xset;
       if (inT) { xme[0] = cmax; xme[1] = csum; }
+      stamp();
       f2_epi_bar();                                     // exchange set 1
+      stamp();
       if (h == 1) {
         if (valid) {
           const float om = xot[0], os = xot[1];
@@ -524,18 +597,26 @@ sparc_fwd2_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_constant
         }
       }
     }
-    if (p.q_save) {                                     // Q (TMEM columns of the dead S) -> global, row stride NP; column halves
+    if (p.q_save) {       // Q (TMEM columns of the dead S) -> global, row stride NP; column halves; transposed through a
+      // per-warp smem tile (behind the logits scratch in the W region) so that one STG covers 8 rows x 64 bytes
+      float* tile = reinterpret_cast<float*>(Whi + (((uint32_t)NT * (NT + 1) * 4 + 127) & ~127u)) + ew * (32 * 20);
       for (int c0 = c_lo; c0 < c_hi; c0 += 16) {
         float x[16];
         tmem_ld16(trow + kF2cS + c0, x);
         tmem_ld_wait();
-        if (row < T) {
-          float* qd = p.q_save + ((size_t)b * T + row) * NP + c0;
 #pragma unroll
-          for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(qd + j) = make_float4(x[j], x[j + 1], x[j + 2], x[j + 3]);
+        for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(tile + lane * 20 + j) = make_float4(x[j], x[j + 1], x[j + 2], x[j + 3]);
+        __syncwarp();
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+          const int rl = it * 8 + (lane >> 2), r = 32 * q + rl;
+          const float4 v4 = *reinterpret_cast<const float4*>(tile + rl * 20 + 4 * (lane & 3));
+          if (r < T) *reinterpret_cast<float4*>(p.q_save + ((size_t)b * T + r) * NP + c0 + 4 * (lane & 3)) = v4;
         }
+        __syncwarp();
       }
     }
+    stamp();
     if (p.tt_logits) {                                  // coalesced copy of the T x T logits for the backward
       float* dst = p.tt_logits + (size_t)b * T * T;
       for (int i = ew; i < T; i += 8)

@@ -20,7 +20,7 @@ t = buf.cpu().double()
 mma = t[:,:8]; epi = t[:,16:28]
 t0 = mma[:,0:1]
 names_m = ['start','pass0 issued','w_ready seen','pass1 issued']
-names_e = ['start','side job done','s_full seen','E1 done','G epilogue done','l_full seen','E3 done']
+names_e = ['start','side job done','s_full seen','E1 done','G epilogue done','l_full seen','row pass','bar','col pass','bar','Q stored','E3 done']
 print('FWD B =', B, ' MMA thread (cycles since start, median over CTAs):')
 for i,n in enumerate(names_m): print(f'  {n:18s} {float(((mma[:,i:i+1]-t0)).median()):10.0f}')
 print('  MMA waits in pass 1: full %.0f g_free %.0f gs_ready %.0f' % tuple(float(t[:,k].median()) for k in (8,9,10)))
