@@ -561,6 +561,7 @@ sparc_bwd2_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_constant
     }
     // a2 = sum dn * nn vanishes identically (W is invariant to the scale of N), a1 = sum dn (nn - 1) = -sum_kept dn
     const float dmn = -(cx - nk * wdot) * isg * inv_rng;
+    float* vq = reinterpret_cast<float*>(dLhi);         // [4 quarters][NP] column partials (dLhat is dead: dWa / Z are done)
     float sdot = 0.f;
     for (int c0 = c_lo; c0 < c_hi; c0 += 16) {
       float x[16], w[16], z[16], pr[16];
@@ -598,12 +599,12 @@ sparc_bwd2_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_constant
         }
       }
       const float cs = b2_colsum16(pr, lane);           // column sums over this warp's 32 rows
-      if (lane < 16) atomicAdd(vdot + c0 + lane, cs);
+      if (lane < 16) vq[q * NP + c0 + lane] = cs;       // per-quarter partial (fixed-order sum below: deterministic bits)
     }
     if (inT) xme0[0] = sdot;                            // exchange set 0
     b2_epi_bar();                                       // also: every vdot atomic has landed
     if (inT && h == 0) lfacs[row] = (sdot + xot0[0] + ldot[row]) * il * il;    // (l^_t . dl^_t) / ||l_t||^2
-    for (int i = tid; i < NP; i += 256) vdot[i] = vdot[i] * ivn[i] * ivn[i];    // -> vfac_p
+    for (int i = tid; i < NP; i += 256) vdot[i] = ((vq[i] + vq[NP + i]) + (vq[2 * NP + i] + vq[3 * NP + i])) * ivn[i] * ivn[i];    // -> vfac_p
     b2_epi_bar();
     tc_fence_before();
     fence_proxy_async();

@@ -65,6 +65,19 @@ struct Fwd2Params {
   float* q_save;        // [B][T][NP], may be NULL
 };
 
+// log-depth reductions of 16 register values (the epilogues run one or two warps per scheduler: a 16-long dependent
+// chain of FADD / FMNMX costs more than the arithmetic it carries)
+__device__ __forceinline__ float f2_max16(const float* x) {
+  const float a = fmaxf(fmaxf(x[0], x[1]), fmaxf(x[2], x[3])), b = fmaxf(fmaxf(x[4], x[5]), fmaxf(x[6], x[7]));
+  const float c = fmaxf(fmaxf(x[8], x[9]), fmaxf(x[10], x[11])), d = fmaxf(fmaxf(x[12], x[13]), fmaxf(x[14], x[15]));
+  return fmaxf(fmaxf(a, b), fmaxf(c, d));
+}
+__device__ __forceinline__ float f2_sum16(const float* x) {
+  const float a = (x[0] + x[1]) + (x[2] + x[3]), b = (x[4] + x[5]) + (x[6] + x[7]);
+  const float c = (x[8] + x[9]) + (x[10] + x[11]), d = (x[12] + x[13]) + (x[14] + x[15]);
+  return (a + b) + (c + d);
+}
+
 __device__ __forceinline__ void f2_epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
 // Column sums of 16 per-lane values over the 32 lanes of a warp (31 shuffles): every lane gets the sum of v[lane & 15].
@@ -393,16 +406,18 @@ sparc_fwd2_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_constant
     stamp();
     float mn = CUDART_INF_F, mx = -CUDART_INF_F;
     for (int c0 = c_lo; c0 < c_hi; c0 += 16) {
-      float x[16];
+      float x[16], lo16[16], hi16[16];
       tmem_ld16(trow + kF2cS + c0, x);
       tmem_ld_wait();
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
         const float s = x[j] * il * ivn[c0 + j];
         const bool in = c0 + j < P;
-        mn = fminf(mn, in ? s : CUDART_INF_F);
-        mx = fmaxf(mx, in ? s : -CUDART_INF_F);
+        lo16[j] = in ? -s : -CUDART_INF_F;             // min via max of the negated values
+        hi16[j] = in ? s : -CUDART_INF_F;
       }
+      mn = fminf(mn, -f2_max16(lo16));
+      mx = fmaxf(mx, f2_max16(hi16));
     }
     {
       float* xme = xme0 + xset;
@@ -420,8 +435,9 @@ sparc_fwd2_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_constant
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
         const float nn = (x[j] * il * ivn[c0 + j] - mn) * inv_rng;
-        sum += (c0 + j < P && !(nn < p.thr)) ? nn : 0.f;
+        x[j] = (c0 + j < P && !(nn < p.thr)) ? nn : 0.f;
       }
+      sum += f2_sum16(x);
     }
     if (inT) xme0[0] = sum;
     f2_epi_bar();
@@ -535,20 +551,23 @@ sparc_fwd2_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_constant
       float x[16];
       tmem_ld16(trow + kF2cL + c0, x);
       tmem_ld_wait();
-      float cm = -CUDART_INF_F;
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const int col = c0 + j;
-        x[j] = (valid && msk[col] != 0.f) ? x[j] * sc_row * iln[col] : -CUDART_INF_F;   // msk/iln are 0 beyond T
-        if (row < T) Lb[row * ldl + col] = x[j];
-        cm = fmaxf(cm, x[j]);
-        diag = (col == row) ? x[j] : diag;
+      for (int j4 = 0; j4 < 16; j4 += 4) {
+        const float4 mk = *reinterpret_cast<const float4*>(msk + c0 + j4), ik = *reinterpret_cast<const float4*>(iln + c0 + j4);
+        const float mv[4] = {mk.x, mk.y, mk.z, mk.w}, iv[4] = {ik.x, ik.y, ik.z, ik.w};
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+          const int j = j4 + jj, col = c0 + j;
+          x[j] = (valid && mv[jj] != 0.f) ? x[j] * sc_row * iv[jj] : -CUDART_INF_F;   // msk/iln are 0 beyond T
+          if (row < T) Lb[row * ldl + col] = x[j];
+          diag = (col == row) ? x[j] : diag;
+        }
       }
-      const float nm = fmaxf(rmax, cm);
-      float sx = 0.f;
+      const float nm = fmaxf(rmax, f2_max16(x));
+      float ex[16];
 #pragma unroll
-      for (int j = 0; j < 16; ++j) sx += (x[j] == -CUDART_INF_F) ? 0.f : __expf(x[j] - nm);
-      rsum = rsum * ((rmax == -CUDART_INF_F) ? 0.f : __expf(rmax - nm)) + sx;
+      for (int j = 0; j < 16; ++j) ex[j] = (x[j] == -CUDART_INF_F) ? 0.f : __expf(x[j] - nm);
+      rsum = rsum * ((rmax == -CUDART_INF_F) ? 0.f : __expf(rmax - nm)) + f2_sum16(ex);
       rmax = nm;
     }
     if (inT) { xme0[0] = rmax; xme0[1] = rsum; xme0[2] = diag; }
@@ -574,9 +593,22 @@ sparc_fwd2_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_constant
       const int isplit = (T + 1) / 2;
       const int i_lo = h ? isplit : 0, i_hi = h ? T : isplit;
       float cmax = -CUDART_INF_F, csum = 0.f;
-      if (valid) {
-        for (int i = i_lo; i < i_hi; ++i) cmax = fmaxf(cmax, Lb[i * ldl + row]);
-        for (int i = i_lo; i < i_hi; ++i) { const float y = Lb[i * ldl + row]; csum += (y == -CUDART_INF_F) ? 0.f : __expf(y - cmax); }
+      if (valid) {                                       // 4 independent chains per loop
+        float m4[4] = {-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F}, s4[4] = {0.f, 0.f, 0.f, 0.f};
+        int i = i_lo;
+        for (; i + 3 < i_hi; i += 4) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) m4[k] = fmaxf(m4[k], Lb[(i + k) * ldl + row]);
+        }
+        for (; i < i_hi; ++i) m4[0] = fmaxf(m4[0], Lb[i * ldl + row]);
+        cmax = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+        i = i_lo;
+        for (; i + 3 < i_hi; i += 4) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) { const float y = Lb[(i + k) * ldl + row]; s4[k] += (y == -CUDART_INF_F) ? 0.f : __expf(y - cmax); }
+        }
+        for (; i < i_hi; ++i) { const float y = Lb[i * ldl + row]; s4[0] += (y == -CUDART_INF_F) ? 0.f : __expf(y - cmax); }
+        csum = (s4[0] + s4[1]) + (s4[2] + s4[3]);
       }
       float* xme = xme0 + xset;
       float* xot = xot0 + xset;

@@ -162,6 +162,27 @@ def test_fused_calls_equal_staged_calls(dtype, P, D):
     assert torch.equal(res[0][1], res[1][1]) and torch.equal(res[0][2], res[1][2])
 
 
+def test_sparc_tc_bitwise_deterministic():
+    """No atomics with run-dependent ordering anywhere on the tensor-core path: repeated evaluations of the same step
+    (32 samples -> many CTAs in flight) return identical bits.  Catches races as well."""
+    from clip_finegrained_alignment_b200 import SPARCLoss
+    g = torch.Generator().manual_seed(21)
+    B, P, T, D = 32, 196, 77, 512
+    v0 = torch.randn(B, P, D, generator=g).to(torch.bfloat16).cuda(); l0 = torch.randn(B, T, D, generator=g).to(torch.bfloat16).cuda()
+    m = torch.ones(B, T, dtype=torch.bool, device="cuda")
+    crit = SPARCLoss(_cfg(1.0 / P))
+    ref = None
+    for _ in range(6):
+        v = v0.clone().requires_grad_(True); l = l0.clone().requires_grad_(True)
+        out = crit(v, l, m)
+        out["total_loss"].backward()
+        cur = (torch.stack([out[k].detach() for k in lo.SPARC_KEYS]), v.grad, l.grad)
+        if ref is None:
+            ref = cur
+        else:
+            assert all(torch.equal(a, b) for a, b in zip(ref, cur))
+
+
 # ----------------------------------------------------------------------------------------------
 # tensor-core global InfoNCE (tcgen05 logits tiles, bf16 hi/lo-split normalised operands)
 # ----------------------------------------------------------------------------------------------
