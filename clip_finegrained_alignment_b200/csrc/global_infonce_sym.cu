@@ -15,13 +15,12 @@
 
 namespace cfa {
 
-// ticket counter of global_sym_fwd_kernel: the CTA that draws the last ticket merges the partials (global_combine_body)
-// and resets the counter, so no separate single-CTA launch is needed.  One forward at a time per device (the loss
-// kernels all run on one stream).
-__device__ unsigned int g_sym_ticket = 0;
-
+// global_sym_fwd_kernel draws tickets from a counter that lives in the CALLER's workspace (zeroed by a memset node in
+// front of the launch): the CTA that draws the last ticket merges the partials (global_combine_body), so no separate
+// single-CTA launch is needed and concurrent forwards on different streams do not interfere.
 struct SymCombine {
   float* lse; float* sums2; const float* local_partial; const uint8_t* mask; int T; float gw, lw; float* out8;
+  unsigned int* ticket;
 };
 
 constexpr int kSyT = 32;             // tile rows = tile cols
@@ -179,9 +178,8 @@ global_sym_fwd_kernel(const float* __restrict__ a, const float* __restrict__ b, 
   __syncthreads();
   if (threadIdx.x == 0) {
     const unsigned int total = gridDim.x * gridDim.y;
-    const unsigned int t = atomicAdd(&g_sym_ticket, 1u);
+    const unsigned int t = atomicAdd(cb.ticket, 1u);
     s_last = (t == total - 1) ? 1u : 0u;
-    if (s_last) g_sym_ticket = 0;
   }
   __syncthreads();
   if (s_last) {
@@ -289,7 +287,7 @@ int global_sym_tiles(int B) { return (B + kSyT - 1) / kSyT; }
 
 size_t global_sym_workspace_bytes(int B, int D) {
   const size_t nt = global_sym_tiles(B);
-  const size_t fwd = ((size_t)4 * nt * B + 2 * (size_t)B) * sizeof(float);
+  const size_t fwd = ((size_t)4 * nt * B + 2 * (size_t)B) * sizeof(float) + 128;      // + ticket counter
   const size_t bwd = (size_t)2 * nt * B * D * sizeof(float);
   return fwd > bwd ? fwd : bwd;
 }
@@ -302,7 +300,9 @@ int global_sym_fwd(const float* a, const float* b, int B, int D, float scale, fl
   float* part_m = (float*)ws;
   float* part_l = part_m + (size_t)2 * nt * B;
   float* diag = part_l + (size_t)2 * nt * B;
-  const SymCombine cb{lse2, sums2, local_partial, mask, T, gw, lw, out8};
+  unsigned int* ticket = reinterpret_cast<unsigned int*>(diag + (((size_t)2 * B + 31) & ~(size_t)31));
+  CFA_CUDA_TRY(cudaMemsetAsync(ticket, 0, sizeof(unsigned int), st));
+  const SymCombine cb{lse2, sums2, local_partial, mask, T, gw, lw, out8, ticket};
   global_sym_fwd_kernel<<<dim3(nt, nt), kSyThreads, 0, st>>>(a, b, B, D, scale, eps, part_m, part_l, diag, norms2, cb);
   return launch_status();
 }
