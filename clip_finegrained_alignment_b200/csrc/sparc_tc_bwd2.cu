@@ -537,32 +537,12 @@ sparc_bwd2_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_constant
     mbar_wait(dw_full, 0);
     tc_fence_after();
     stamp();
-    float wdot = 0.f, cx = 0.f, nk = 0.f;
-    for (int c0 = c_lo; c0 < c_hi; c0 += 16) {
-      float x[16], w[16];
-      tmem_ld16(trow + kB2cS + c0, x);
-      load_w16(c0, w);
-      tmem_ld_wait();
-#pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const float dw = valid ? x[j] : 0.f;
-        const bool kept = (keep_all || w[j] > 0.f) && (c0 + j < P) && valid;
-        wdot = fmaf(w[j], dw, wdot);                    // W is 0 beyond P and on masked rows
-        cx += kept ? dw : 0.f;
-        nk += kept ? 1.f : 0.f;
-      }
-    }
-    {
-      float* xme = xme0 + xset;                        // exchange set 1
-      float* xot = xot0 + xset;
-      if (inT) { xme[0] = wdot; xme[1] = cx; xme[2] = nk; }
-      b2_epi_bar();
-      if (inT) { wdot += xot[0]; cx += xot[1]; nk += xot[2]; }
-    }
-    // a2 = sum dn * nn vanishes identically (W is invariant to the scale of N), a1 = sum dn (nn - 1) = -sum_kept dn
-    const float dmn = -(cx - nk * wdot) * isg * inv_rng;
+    // Renorm / threshold / min-max backward in ONE sweep.  Two identities make that possible:
+    //   sum_p W dW = dG . G = 0   (dG = J_n(G)^T dg^ is orthogonal to G), so  dTheta = dW / sigma  without a prior row sum;
+    //   sum_p dN N = 0            (W is invariant to the scale of N), so only the arg-MIN element receives a scatter
+    //                             term, dmn = -(sum_kept dW) / (sigma rng), which is patched in after the sweep.
     float* vq = reinterpret_cast<float*>(dLhi);         // [4 quarters][NP] column partials (dLhat is dead: dWa / Z are done)
-    float sdot = 0.f;
+    float cx = 0.f, sdot = 0.f;
     for (int c0 = c_lo; c0 < c_hi; c0 += 16) {
       float x[16], w[16], z[16], pr[16];
       tmem_ld16(trow + kB2cS + c0, x);
@@ -573,13 +553,12 @@ sparc_bwd2_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_constant
       for (int j = 0; j < 16; ++j) {
         const int pc = c0 + j;
         const bool in = valid && pc < P;
-        const float dw = x[j];
         const bool kept = (keep_all || w[j] > 0.f) && in;
-        float ds = kept ? ((dw - wdot) * isg) * inv_rng : 0.f;
-        ds += (pc == imn) ? dmn : 0.f;
-        ds = in ? ds : 0.f;
-        const float sv = kept ? fmaf(w[j] * sigma, rng, mn) : mn;              // only read where ds != 0
-        const float prod = in ? ds * sv : 0.f;          // phantom rows may hold NaN/Inf: select, never 0*x
+        const float dw = kept ? x[j] : 0.f;              // phantom rows may hold NaN/Inf: select, never 0*x
+        cx += dw;
+        const float ds = (dw * isg) * inv_rng;
+        const float sv = fmaf(w[j] * sigma, rng, mn);    // normalised similarity of a kept element
+        const float prod = kept ? ds * sv : 0.f;         // select, never 0 * x (phantom rows hold garbage statistics)
         sdot += prod;
         pr[j] = prod;
         x[j] = in ? fmaf(ds * il, ivn[pc], z[j]) : 0.f;    // dShat' = dShat + Z
@@ -601,10 +580,39 @@ sparc_bwd2_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_constant
       const float cs = b2_colsum16(pr, lane);           // column sums over this warp's 32 rows
       if (lane < 16) vq[q * NP + c0 + lane] = cs;       // per-quarter partial (fixed-order sum below: deterministic bits)
     }
-    if (inT) xme0[0] = sdot;                            // exchange set 0
-    b2_epi_bar();                                       // also: every vdot atomic has landed
-    if (inT && h == 0) lfacs[row] = (sdot + xot0[0] + ldot[row]) * il * il;    // (l^_t . dl^_t) / ||l_t||^2
-    for (int i = tid; i < NP; i += 256) vdot[i] = ((vq[i] + vq[NP + i]) + (vq[2 * NP + i] + vq[3 * NP + i])) * ivn[i] * ivn[i];    // -> vfac_p
+    stamp();
+    int* fixi = reinterpret_cast<int*>(lser);           // [NT] arg-min column of each row (-1: none); lser / lsec are dead
+    float* fixv = lsec;                                 // [NT] its contribution to the column sum
+    {
+      float* xme = xme0 + xset;                        // exchange set 1
+      float* xot = xot0 + xset;
+      if (inT) { xme[0] = cx; xme[1] = sdot; }
+      b2_epi_bar();
+      if (inT) { cx += xot[0]; sdot += xot[1]; }
+    }
+    const float dmn = valid ? -cx * isg * inv_rng : 0.f;
+    if (valid && imn >= c_lo && imn < c_hi) {           // the half that owns the arg-min column patches dShat'[t][imn]
+      const uint32_t off = il_offset(NT, row, imn);
+      bf16* ph = reinterpret_cast<bf16*>(SRhi + off);
+      bf16* pl = reinterpret_cast<bf16*>(SRlo + off);
+      const float f = (__bfloat162float(*ph) + __bfloat162float(*pl)) + dmn * il * ivn[imn];
+      const bf16 nh = __float2bfloat16_rn(f);
+      *ph = nh;
+      *pl = __float2bfloat16_rn(f - __bfloat162float(nh));
+    }
+    if (inT && h == 0) {
+      fixi[row] = valid ? imn : -1;
+      fixv[row] = dmn * mn;                             // ds[imn] * s[imn], s[imn] = mn
+      lfacs[row] = (sdot + dmn * mn + ldot[row]) * il * il;        // (l^_t . dl^_t) / ||l_t||^2
+    }
+    stamp();
+    b2_epi_bar();
+    stamp();
+    for (int i = tid; i < NP; i += 256) {               // -> vfac_p
+      float acc = (vq[i] + vq[NP + i]) + (vq[2 * NP + i] + vq[3 * NP + i]);
+      for (int t = 0; t < T; ++t) acc += (fixi[t] == i) ? fixv[t] : 0.f;
+      vdot[i] = acc * ivn[i] * ivn[i];
+    }
     b2_epi_bar();
     tc_fence_before();
     fence_proxy_async();

@@ -21,7 +21,7 @@ t = buf.cpu().double()
 mma = t[:,:8]; epi = t[:,16:28]
 t0 = mma[:,0:1]
 names_m = ['start','P1 issued','e1/dl ready seen','ds_ready seen','P4a issued','P4b issued']
-names_e = ['start','phase0 done','s_full seen','E1 done','dw_full seen','E3 done','dl written','dv written']
+names_e = ['start','phase0 done','s_full seen','E1 done','dw_full seen','E3 sweep done','E3 fixup done','bar','E3 done','dl written','dv written']
 print('B =', B, ' MMA thread (cycles since start, median over CTAs):')
 for i,n in enumerate(names_m): print(f'  {n:18s} {float(((mma[:,i:i+1]-t0)).median()):10.0f}')
 print('  MMA waits: P4a full %.0f free %.0f | P4b full %.0f free %.0f' % tuple(float(t[:,k].median()) for k in (8,9,10,11)))
