@@ -278,6 +278,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=256, help="pairs per GPU (BASELINE config 2: 256)")
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "f32", "f16"])
+    ap.add_argument("--collective", default="peer", choices=["peer", "nccl"],
+                    help="N > 1: exchange of the gathered global InfoNCE (peer memory over NVLink, or NCCL all-gathers)")
     ap.add_argument("--no-adamspd", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -308,7 +310,7 @@ def main():
     vs = [torch.randn(B, P, D, device=dev).to(dt).requires_grad_(True) for _ in range(nbuf)]
     ls = [torch.randn(B, T, D, device=dev).to(dt).requires_grad_(True) for _ in range(nbuf)]
     mask = torch.ones(B, T, dtype=torch.bool, device=dev)
-    crit = SPARCLoss(cfg(1.0 / P), gather=world > 1)
+    crit = SPARCLoss(cfg(1.0 / P), gather=(True if args.collective == "peer" else "nccl") if world > 1 else False)
 
     def step(i):
         v, l = vs[i % nbuf], ls[i % nbuf]
@@ -414,6 +416,12 @@ def main():
             dist.destroy_process_group()
         return
 
+    collective = "none (1 GPU)"
+    if world > 1:
+        from clip_finegrained_alignment_b200 import peer as _peer
+        collective = ("peer memory: pooled embeddings and [lse | CE sums] packs read in place from the peers' HBM "
+                      "(CUDA IPC over NVLink), 2 in-stream device barriers per step, no NCCL call on the step path"
+                      if any(e.ok for e in _peer._EXCHANGES.values()) else "NCCL all-gather x2 per step")
     # roofline of the dominant kernel (cfa_sparc_bwd): algorithmic backward FLOPs of the fine-grained part per launch
     bwd_flops = B * (8 * T * P * D + 4 * T * T * D)
     ach = bwd_flops / (bwd_ms * 1e-3) / 1e12
@@ -423,7 +431,7 @@ def main():
         "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
         "config": {"workload": f"BASELINE config 2: ViT-B/16 SPARC + global InfoNCE fwd+bwd, B={B}/GPU, P={P}, T={T}, "
                                f"D={D}, thr=1/P, s=1, all-True mask" + (", all-gathered global InfoNCE" if world > 1 else ""),
-                   "global_batch": Bg, "l2": f"inputs rotated over {nbuf} sets ({nbuf * in_bytes >> 20} MiB > 2x L2)",
+                   "global_batch": Bg, "collective": collective, "l2": f"inputs rotated over {nbuf} sets ({nbuf * in_bytes >> 20} MiB > 2x L2)",
                    "algorithmic_flops_per_pair": flops_per_pair(Bg),
                    "algorithmic_tflops": round(value * flops_per_pair(Bg) / 1e12, 2),
                    "kernel_ms": {k: round(statistics.mean(a.elapsed_time(b) for a, b in ev), 4) for k, ev in kev.items() if ev}},

@@ -14,6 +14,14 @@ namespace cfa {
 
 constexpr int kWarp = 32;
 
+// Peer-memory gather (peer_exchange.cu): base[r] = rank r's exchange block mapped into this process (CUDA IPC over
+// NVLink); n == 0: not used.  Passed by value to the kernels that read remote rows directly.
+constexpr int kMaxPeers = 16;
+struct PeerTable {
+  const float* base[kMaxPeers];
+  int n;
+};
+
 #define CFA_CUDA_TRY(expr)                         \
   do {                                             \
     cudaError_t _e = (expr);                       \

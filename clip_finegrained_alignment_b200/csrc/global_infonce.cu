@@ -8,6 +8,7 @@
 #include "common.cuh"
 #include "simt_tile.cuh"
 #include "global_combine.cuh"
+#include "sparc_paths.h"
 #include <math_constants.h>
 
 namespace cfa {
@@ -232,7 +233,7 @@ bool global_tc_supported(int B, int Bg, int D);
 size_t global_tc_workspace_bytes(int B, int Bg, int D);
 int global_tc_fwd(const float* a_loc, const float* b_loc, const float* a_all, const float* b_all, int B, int Bg, int D,
                   int col_offset, float scale, float eps, float* norms2, float** part_m, float** part_l, float** diag,
-                  int* nsplit, void* ws, int gathered_ranks, cudaStream_t st);
+                  int* nsplit, void* ws, int gathered_ranks, const PeerTable* peers, cudaStream_t st);
 int global_tc_bwd(int B, int Bg, int D, int col_offset, float scale, const float* lse_loc2, const float* lse_all2,
                   const float* coef2, float** dpart, int* nsplit, void* ws, int gathered_ranks, cudaStream_t st);
 
@@ -274,11 +275,24 @@ extern "C" int cfa_global_infonce_fwd(const float* a_loc, const float* b_loc, co
                                       float* sums2, const float* local_partial, const uint8_t* mask, int T, float gw,
                                       float lw, float* out8, void* workspace, size_t workspace_bytes, int path,
                                       int gathered_ranks, void* stream) {
+  return cfa::global_infonce_fwd_peers(a_loc, b_loc, a_all, b_all, B, Bg, D, col_offset, scale, eps, lse2, norms2, sums2,
+                                       local_partial, mask, T, gw, lw, out8, workspace, workspace_bytes, path, gathered_ranks,
+                                       nullptr, stream);
+}
+
+// peers != NULL (peer_exchange.cu): the "all" rows are read from every rank's exchange block through the table; a_all /
+// b_all are ignored
+int cfa::global_infonce_fwd_peers(const float* a_loc, const float* b_loc, const float* a_all, const float* b_all, int B,
+                                  int Bg, int D, int col_offset, float scale, float eps, float* lse2, float* norms2,
+                                  float* sums2, const float* local_partial, const uint8_t* mask, int T, float gw, float lw,
+                                  float* out8, void* workspace, size_t workspace_bytes, int path, int gathered_ranks,
+                                  const PeerTable* peers, void* stream) {
   if (B <= 0 || Bg <= 0 || D <= 0 || col_offset < 0 || col_offset + B > Bg) return CFA_ERR_BAD_ARG;
   if (gathered_ranks > 1 && (gathered_ranks * B != Bg || !use_tc(B, Bg, D, path))) return CFA_ERR_UNSUPPORTED;
   if (!workspace || workspace_bytes < cfa_global_infonce_workspace_bytes(B, Bg, D)) return CFA_ERR_WORKSPACE;
   if (out8 && (Bg != B || !local_partial || !mask)) return CFA_ERR_BAD_ARG;   // fused scalar epilogue: single process only
   if (path == 2 && !global_tc_supported(B, Bg, D)) return CFA_ERR_UNSUPPORTED;
+  if (peers && !use_tc(B, Bg, D, path)) return CFA_ERR_UNSUPPORTED;
   if (use_sym(B, Bg, D, path))          // one launch: the last CTA merges the partials and writes the scalar outputs
     return global_sym_fwd(a_loc, b_loc, B, D, scale, eps, norms2, lse2, sums2, local_partial, mask, T, gw, lw, out8, workspace,
                           (cudaStream_t)stream);
@@ -286,7 +300,7 @@ extern "C" int cfa_global_infonce_fwd(const float* a_loc, const float* b_loc, co
     float *pm, *pl, *dg;
     int nsp;
     const int rc = global_tc_fwd(a_loc, b_loc, a_all, b_all, B, Bg, D, col_offset, scale, eps, norms2, &pm, &pl, &dg, &nsp,
-                                 workspace, gathered_ranks, (cudaStream_t)stream);
+                                 workspace, gathered_ranks, peers, (cudaStream_t)stream);
     if (rc != CFA_OK) return rc;
     global_combine_kernel<<<1, kNT, 0, (cudaStream_t)stream>>>(pm, pl, dg, B, nsp, lse2, sums2, Bg, local_partial, mask, T, gw,
                                                                lw, out8);

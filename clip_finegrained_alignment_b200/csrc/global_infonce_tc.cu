@@ -25,12 +25,16 @@ constexpr int kGtStages = 2;
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 gt_split_kernel(const float* __restrict__ a, const float* __restrict__ b, int rows, int D, float eps,
-                bf16* __restrict__ out, float* __restrict__ norms /* [2][rows] or NULL */, int rank_rows, size_t rank_stride) {
+                bf16* __restrict__ out, float* __restrict__ norms /* [2][rows] or NULL */, int rank_rows, size_t rank_stride,
+                const PeerTable peers) {
   // rank_rows / rank_stride: global row g = r * rank_rows + i lives at base + r * rank_stride + i * D (the raw output of
   // an all-gather of per-rank [2][B][D] blocks); rank_rows == rows, rank_stride == 0 for a plain [rows][D] matrix
   const int r = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31, which = blockIdx.y;
   if (r >= rows) return;
-  const float* x = (which ? b : a) + (size_t)(r / rank_rows) * rank_stride + (size_t)(r % rank_rows) * D;
+  // peers.n > 0: rank q's [2][rank_rows][D] block is read where it lives, in q's HBM over NVLink (the gather is fused
+  // into this, its only consumer)
+  const float* x = peers.n ? peers.base[r / rank_rows] + ((size_t)which * rank_rows + (size_t)(r % rank_rows)) * D
+                           : (which ? b : a) + (size_t)(r / rank_rows) * rank_stride + (size_t)(r % rank_rows) * D;
   float ss = 0.f;
   for (int d = lane; d < D; d += 32) ss = fmaf(x[d], x[d], ss);
   ss = warp_sum(ss);
@@ -380,13 +384,16 @@ static int gt_maps(const GtHost& h, int B, int Bg, int D, CUtensorMap* tmLoc, CU
 
 int global_tc_fwd(const float* a_loc, const float* b_loc, const float* a_all, const float* b_all, int B, int Bg, int D,
                   int col_offset, float scale, float eps, float* norms2, float** part_m, float** part_l, float** diag,
-                  int* nsplit, void* ws, int gathered_ranks, cudaStream_t st) {
+                  int* nsplit, void* ws, int gathered_ranks, const PeerTable* peers, cudaStream_t st) {
   const GtHost h = gt_carve(ws, B, Bg, D);
-  if (gathered_ranks > 1)
-    gt_split_kernel<<<dim3((Bg + 7) / 8, 2), 256, 0, st>>>(a_all, b_all, Bg, D, eps, h.all_split, nullptr, B, (size_t)2 * B * D);
+  PeerTable none{};
+  if (peers && peers->n > 1)
+    gt_split_kernel<<<dim3((Bg + 7) / 8, 2), 256, 0, st>>>(nullptr, nullptr, Bg, D, eps, h.all_split, nullptr, B, 0, *peers);
+  else if (gathered_ranks > 1)
+    gt_split_kernel<<<dim3((Bg + 7) / 8, 2), 256, 0, st>>>(a_all, b_all, Bg, D, eps, h.all_split, nullptr, B, (size_t)2 * B * D, none);
   else
-    gt_split_kernel<<<dim3((Bg + 7) / 8, 2), 256, 0, st>>>(a_all, b_all, Bg, D, eps, h.all_split, nullptr, Bg, 0);
-  gt_split_kernel<<<dim3((B + 7) / 8, 2), 256, 0, st>>>(a_loc, b_loc, B, D, eps, h.loc_split, norms2, B, 0);
+    gt_split_kernel<<<dim3((Bg + 7) / 8, 2), 256, 0, st>>>(a_all, b_all, Bg, D, eps, h.all_split, nullptr, Bg, 0, none);
+  gt_split_kernel<<<dim3((B + 7) / 8, 2), 256, 0, st>>>(a_loc, b_loc, B, D, eps, h.loc_split, norms2, B, 0, none);
   CFA_CUDA_TRY(cudaGetLastError());
   CUtensorMap tmLoc, tmAll;
   int rc = gt_maps(h, B, Bg, D, &tmLoc, &tmAll);

@@ -33,4 +33,11 @@ int sparc_bwd2_launch(const void* v, const void* l, const uint8_t* mask, int B, 
                       const float* tt_logits, const float* g_inv_norm, const void* g_split, const float* q_save,
                       const float* dpv, const float* dpl, void* dv, void* dl, long long* prof, int dtype, cudaStream_t st);
 
+// cfa_global_infonce_fwd with the gathered rows read through a peer table (global_infonce.cu)
+int global_infonce_fwd_peers(const float* a_loc, const float* b_loc, const float* a_all, const float* b_all, int B, int Bg,
+                             int D, int col_offset, float scale, float eps, float* lse2, float* norms2, float* sums2,
+                             const float* local_partial, const uint8_t* mask, int T, float gw, float lw, float* out8,
+                             void* workspace, size_t workspace_bytes, int path, int gathered_ranks, const PeerTable* peers,
+                             void* stream);
+
 }  // namespace cfa

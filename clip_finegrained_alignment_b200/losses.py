@@ -9,9 +9,11 @@ Every returned entry is a 0-dim CUDA tensor attached to autograd; the backward i
 finetuner.py:120-134); gradients come back in the input dtype.
 
 Beyond the reference: `gather=True` (or an explicit `process_group`) turns the *global* InfoNCE into
-the all-gathered variant — image/text embeddings are all-gathered with NCCL and every rank scores its
-local rows against the global columns.  The fine-grained loss stays rank-local, as in
-dist_finetuner.py.
+the all-gathered variant — every rank scores its local rows against the rows of all ranks (SURVEY.md
+§8e).  On one NVLink/NVSwitch box the kernels read the peers' pooled embeddings in place through
+CUDA-IPC-mapped exchange blocks (two in-stream device barriers per step, no collective call);
+`gather="nccl"` (or a shape the tensor-core global kernels do not take) all-gathers with NCCL instead.
+The fine-grained loss stays rank-local, as in dist_finetuner.py.
 
 Padded masks: the reference's local loss is NaN as soon as one mask entry is False (SURVEY finding 3).
 The kernels implement the evidently intended semantics instead ("truncate": masked tokens are skipped,
@@ -167,6 +169,31 @@ class _SparcFunction(torch.autograd.Function):
         code = _lib.DTYPE_CODE[v.dtype]
         world, rank, group = _dist_ctx(group, gather)
         ctx.set_materialize_grads(False)               # unused outputs arrive as None: no zero-fill launches
+        ctx.peer = None
+        if world > 1 and fused and gather != "nccl":
+            # gathered loss over peer memory: one library call per direction, no collective call (csrc/peer_exchange.cu)
+            gpath = 1 if (v.dtype == torch.float32 or path == 1) else 0
+            ex = None
+            if _L.cfa_global_infonce_path(B, world * B, D, gpath) == 2:
+                from . import peer as _peer
+                with torch.cuda.device(dev):
+                    ex = _peer.get_exchange(B, D, group)
+            if ex is not None:
+                key = (B, P, T, D, code, path, world)
+                nbytes = _WS_BYTES.get(key)
+                if nbytes is None:
+                    nbytes = _WS_BYTES[key] = _L.cfa_sparc_loss_gathered_workspace_bytes(B, P, T, D, code, path, world)
+                ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+                same_dev = torch.cuda.current_device() == dev.index
+                with (contextlib.nullcontext() if same_dev else torch.cuda.device(dev)):
+                    _lib.call("cfa_sparc_loss_gathered_fwd", v.data_ptr(), l.data_ptr(), mask_u8.data_ptr(), B, P, T, D, code,
+                              thr, scale, gw, lw, ws.data_ptr(), nbytes, path, world, rank, ex.blocks, ex.next_step(),
+                              _lib.stream_ptr())
+                ctx.save_for_backward(v, l, mask_u8, ws)
+                ctx.gst = None
+                ctx.peer = (world, rank)
+                ctx.hp = (thr, gw, lw, scale, code, path, None, None)
+                return ws[:28].view(torch.float32).clone().unbind(0)
         if world == 1 and fused:
             # rank-local loss: ONE library call and ONE allocation per direction (cfa_sparc_loss_fwd / _bwd); the
             # workspace layout is private to the library, its first 8 floats are the outputs
@@ -246,8 +273,14 @@ class _SparcFunction(torch.autograd.Function):
             dv = torch.empty_like(v)
             dl = torch.empty_like(l)
             with (contextlib.nullcontext() if same_dev else torch.cuda.device(dev)):
-                _lib.call("cfa_sparc_loss_bwd", v.data_ptr(), l.data_ptr(), mask_u8.data_ptr(), B, P, T, D, code, thr, scale,
-                          gw, lw, blk.data_ptr(), blk.numel(), *gptr, dv.data_ptr(), dl.data_ptr(), path, _lib.stream_ptr())
+                if ctx.peer is not None:
+                    _lib.call("cfa_sparc_loss_gathered_bwd", v.data_ptr(), l.data_ptr(), mask_u8.data_ptr(), B, P, T, D, code,
+                              thr, scale, gw, lw, blk.data_ptr(), blk.numel(), *gptr, dv.data_ptr(), dl.data_ptr(), path,
+                              ctx.peer[0], ctx.peer[1], _lib.stream_ptr())
+                else:
+                    _lib.call("cfa_sparc_loss_bwd", v.data_ptr(), l.data_ptr(), mask_u8.data_ptr(), B, P, T, D, code, thr,
+                              scale, gw, lw, blk.data_ptr(), blk.numel(), *gptr, dv.data_ptr(), dl.data_ptr(), path,
+                              _lib.stream_ptr())
             return dv, dl, None, None, None, None, None, None, None, None, None
         with (contextlib.nullcontext() if same_dev else torch.cuda.device(dev)):
             coef = torch.empty(8, dtype=torch.float32, device=dev)
@@ -330,9 +363,11 @@ class _MaskedPairwiseFunction(torch.autograd.Function):
 class SPARCLoss(nn.Module):
     """SPARC loss (https://arxiv.org/abs/2401.09865), reference API: finetune/losses.py:136-264."""
 
-    def __init__(self, config, gather: bool = False, process_group=None, kernel_path: str = "auto",
+    def __init__(self, config, gather=False, process_group=None, kernel_path: str = "auto",
                  fused_calls: bool = True):
         super().__init__()
+        # gather: False = rank-local global loss (the reference under DDP); True = all-gathered over peer memory when the
+        # ranks share an NVLink box and the shape allows, else over NCCL; "nccl" = always the NCCL all-gather path
         # fused_calls: rank-local loss through one library call per direction (cfa_sparc_loss_fwd / _bwd); False keeps
         # the per-stage entry points (same kernels, same numbers; used to time the stages separately)
         self.fused_calls = fused_calls

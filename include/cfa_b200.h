@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define CFA_ABI_VERSION 2
+#define CFA_ABI_VERSION 3
 
 #define CFA_DTYPE_F32 0
 #define CFA_DTYPE_BF16 1
@@ -181,20 +181,38 @@ int cfa_sparc_loss_bwd(const void* v, const void* l, const uint8_t* mask, int B,
                        const float* g_vl_local, const float* g_lv_local, void* dv, void* dl, int path, void* stream);
 
 /*
- * Rank-local SPARC loss in ONE call per direction (what SPARCLoss.forward / .backward issue when the global InfoNCE is
- * not all-gathered): cfa_sparc_fwd + cfa_global_infonce_fwd (fused scalar epilogue), and cfa_sparc_coef_ptrs +
- * cfa_global_infonce_bwd + cfa_sparc_bwd, over one 128-byte-aligned workspace of cfa_sparc_loss_workspace_bytes() whose
- * layout is private to the library.  After the forward the first 8 floats of the workspace hold out[0..7] (see
- * cfa_sparc_finalize); the backward must be given the same, untouched workspace.  g_*: DEVICE scalars, the upstream
- * gradients of the 7 outputs (NULL = unused).  Saves ~4 host calls and ~4 allocations per step.
+ * All-gathered SPARC loss over PEER MEMORY (the reference's dist_finetuner.py:164-176 keeps the loss
+ * rank-local — the gathered global InfoNCE is this library's extension).  One rank = one process = one GPU of one
+ * NVLink/NVSwitch box.  Every rank owns an exchange block (cfa_peer_alloc: cudaMalloc + CUDA IPC handle) that its peers
+ * map with cfa_peer_open; h_peer_blocks is a HOST array of `world` device pointers, entry r = rank r's block as mapped
+ * in THIS process (entry `rank` = the own allocation).  The fine-grained loss stays rank-local; the global InfoNCE
+ * scores the local rows against the rows of every rank, read in place from the peers' HBM, and the per-rank
+ * [lse | CE sums] packs travel the same way.  Two in-stream device barriers per forward, none in the backward, no NCCL
+ * call and no host synchronisation; a rank that never arrives turns the losses into NaN after 20 s instead of hanging.
+ * `step` = number of gathered forwards issued so far on this exchange (identical on every rank).
+ * Shapes the tensor-core global InfoNCE does not take (D % 64 != 0, D > 512, fp32 inputs) return CFA_ERR_UNSUPPORTED:
+ * the caller then uses cfa_global_infonce_fwd/_bwd with NCCL-gathered buffers.
  */
-size_t cfa_sparc_loss_workspace_bytes(int B, int P, int T, int D, int dtype, int path);
-int cfa_sparc_loss_fwd(const void* v, const void* l, const uint8_t* mask, int B, int P, int T, int D, int dtype, float thr,
-                       float scale, float gw, float lw, void* workspace, size_t workspace_bytes, int path, void* stream);
-int cfa_sparc_loss_bwd(const void* v, const void* l, const uint8_t* mask, int B, int P, int T, int D, int dtype, float thr,
-                       float scale, float gw, float lw, void* workspace, size_t workspace_bytes, const float* g_global,
-                       const float* g_local, const float* g_total, const float* g_vl, const float* g_lv,
-                       const float* g_vl_local, const float* g_lv_local, void* dv, void* dl, int path, void* stream);
+size_t cfa_peer_exchange_bytes(int B, int D);
+int cfa_peer_alloc(size_t bytes, void** dev_ptr, unsigned char handle_out[64]);
+int cfa_peer_open(const unsigned char handle[64], void** dev_ptr);
+int cfa_peer_close(void* dev_ptr);
+int cfa_peer_free(void* dev_ptr);
+/* one barrier on its own: push `push_words` floats into the own block at word offset push_off_words, signal `epoch`
+ * to every peer, wait for theirs, then pull `pull_words` floats from word offset pull_off_words of EVERY block into
+ * pull_dst [world][pull_words].  Word offsets >= 64 (the header holds the flags). */
+int cfa_peer_sync(void* const* h_peer_blocks, int world, int rank, uint32_t epoch, const float* push_src,
+                  size_t push_off_words, size_t push_words, size_t pull_off_words, int pull_words, float* pull_dst,
+                  void* stream);
+size_t cfa_sparc_loss_gathered_workspace_bytes(int B, int P, int T, int D, int dtype, int path, int world);
+int cfa_sparc_loss_gathered_fwd(const void* v, const void* l, const uint8_t* mask, int B, int P, int T, int D, int dtype,
+                                float thr, float scale, float gw, float lw, void* workspace, size_t workspace_bytes,
+                                int path, int world, int rank, void* const* h_peer_blocks, uint32_t step, void* stream);
+int cfa_sparc_loss_gathered_bwd(const void* v, const void* l, const uint8_t* mask, int B, int P, int T, int D, int dtype,
+                                float thr, float scale, float gw, float lw, void* workspace, size_t workspace_bytes,
+                                const float* g_global, const float* g_local, const float* g_total, const float* g_vl,
+                                const float* g_lv, const float* g_vl_local, const float* g_lv_local, void* dv, void* dl,
+                                int path, int world, int rank, void* stream);
 
 /*
  * SPARCLoss.masked_pairwise_contrastive_loss on its own (losses.py:165-197): a, b [B,T,D] in `dtype`, mask [B,T] bytes.

@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
     for s in syms:
         assert hasattr(raw, s), f"{s} declared in include/cfa_b200.h but not exported"
         assert s in _lib.SIGNATURES, f"{s} has no ctypes signature"
-    assert _lib.lib.cfa_abi_version() == 2
+    assert _lib.lib.cfa_abi_version() == 3
     assert _lib.lib.cfa_error_string(-2).startswith(b"cfa:")
     assert _lib.lib.cfa_adamspd_chunk_elems() == 8192
 
