@@ -179,6 +179,38 @@ def bench_adamspd(dev, steps, warmup, pk):
         del ref, ref_params
     except Exception:
         pass
+    # ---- AMP prologue folded into the step: amp_step vs unscale_ + clip_grad_norm_ + scaler.step
+    amp = None
+    try:
+        scaler = torch.amp.GradScaler("cuda", init_scale=1024.0)
+        scaler.scale(torch.zeros(1, device=dev))
+
+        def timed(fn, n=3):
+            ts = []
+            for _ in range(n):
+                regrad()
+                torch.cuda.synchronize(dev)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(); fn(); e1.record()
+                torch.cuda.synchronize(dev)
+                ts.append(e0.elapsed_time(e1))
+            return min(ts)
+
+        def fused():
+            opt.amp_step(scaler, 1.0); scaler.update()
+
+        def unfused():
+            scaler.unscale_(opt); torch.nn.utils.clip_grad_norm_(params, 1.0); scaler.step(opt); scaler.update()
+
+        fused(); unfused()
+        f_ms, u_ms = timed(fused), timed(unfused)
+        amp = {"amp_step_ms": round(f_ms, 4), "unscale_clip_step_ms": round(u_ms, 4),
+               "amp_step_gbs": round((36.0 * n_elts + 12.0 * float(numel[proj].sum())) / (f_ms * 1e-3) / 1e9, 1),
+               "note": "amp_step = cfa_adamspd_step_amp (one extra read of g: 36 B/elt + 12 B/elt projected, 4 launches, no "
+                       "host sync); comparator = GradScaler.unscale_ + clip_grad_norm_ + GradScaler.step around the same "
+                       "cfa_adamspd_step (finetuner.py:150-152)"}
+    except Exception as e:      # keep the headline line even if the AMP leg fails
+        amp = {"error": repr(e)[:200]}
     out = {"metric": "adamspd_step_hbm_gbs", "value": round(gbs, 1), "unit": "GB/s", "ms_per_step": round(ms, 4),
            "ms_per_step_host_inclusive": round(sum(host_ms) / len(host_ms), 4),
            "workload": "ViT-L/14 CLIP, 590 fp32 tensors, 427616513 params, random grads, lr 2e-5, wd 0.1",
@@ -187,7 +219,7 @@ def bench_adamspd(dev, steps, warmup, pk):
                         "unit": "GB/s", "frac": round(gbs / pk["hbm"], 4),
                         "traffic": 16.0e9, "traffic_source": "profiles/r1d_ncu_adamspd.csv (dram read+write, both passes)",
                         "peak_source": pk["src"]},
-           "torch_fused_adamw_ms": None if cmp_ms is None else round(cmp_ms, 4)}
+           "torch_fused_adamw_ms": None if cmp_ms is None else round(cmp_ms, 4), "amp": amp}
     del opt, params, pre, flat
     torch.cuda.empty_cache()
     return out

@@ -37,6 +37,7 @@ SIGNATURES = {
     "cfa_error_string": (C.c_char_p, [_i]),
     "cfa_adamspd_chunk_elems": (C.c_int, []),
     "cfa_adamspd_step": (C.c_int, [_vp, _i, _vp, _i, _vp, _vp, _i, _i, _vp]),
+    "cfa_adamspd_step_amp": (C.c_int, [_vp, _i, _vp, _i, _vp, _vp, _vp, _f, _vp, _i, _i, _vp]),
     "cfa_global_infonce_workspace_bytes": (_sz, [_i, _i, _i]),
     "cfa_global_infonce_fwd": (C.c_int, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _f, _vp, _vp, _vp, _vp, _vp, _i, _f, _f,
                                          _vp, _vp, _sz, _i, _i, _vp]),
@@ -85,7 +86,7 @@ for _name, (_res, _args) in SIGNATURES.items():
 
 
 # kernels launched per C-ABI call (cudaMemsetAsync not counted); bench.py reports the running total
-LAUNCHES = {"cfa_adamspd_step": 2, "cfa_global_infonce_fwd": 1, "cfa_global_infonce_bwd": 2, "cfa_sparc_fwd": 1,
+LAUNCHES = {"cfa_adamspd_step": 2, "cfa_adamspd_step_amp": 4, "cfa_global_infonce_fwd": 1, "cfa_global_infonce_bwd": 2, "cfa_sparc_fwd": 1,
             "cfa_sparc_bwd": 1, "cfa_sparc_finalize": 1, "cfa_sparc_coef": 1, "cfa_sparc_coef_ptrs": 1,
             "cfa_peer_exchange_bytes": (_sz, [_i, _i]),
     "cfa_peer_alloc": (C.c_int, [_sz, _vp, _vp]),

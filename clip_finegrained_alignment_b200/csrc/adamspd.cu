@@ -48,10 +48,18 @@ __device__ __forceinline__ void adam_elem(const AdamScalars& h, float p, float g
   s_old = fmaf(d_old, d_old, s_old);                  // ||param-pre||^2             (:155)
 }
 
-template <bool kAms>
+// kAmp: gradients are consumed as (g * inv_scale) * clip_coef (GradScaler.unscale_ followed by clip_grad_norm_,
+// finetuner.py:150-151, same two fp32 roundings) and the whole step is skipped when a non-finite gradient was found
+// (what GradScaler.step does on the host, finetuner.py:152) — amp = {inv_scale, clip_coef, total_norm, found_inf}.
+template <bool kAms, bool kAmp>
 __global__ void __launch_bounds__(kAdamThreads)
 adamspd_pass1(const cfa_adamspd_tensor* __restrict__ tensors, const cfa_adamspd_chunk* __restrict__ chunks,
-              double* __restrict__ reduce) {
+              double* __restrict__ reduce, const float* __restrict__ amp) {
+  float gs0 = 1.f, gs1 = 1.f;
+  if (kAmp) {
+    if (amp[3] != 0.f) return;
+    gs0 = amp[0]; gs1 = amp[1];
+  }
   const cfa_adamspd_chunk ck = chunks[blockIdx.x];
   const cfa_adamspd_tensor t = tensors[ck.tensor];
   const AdamScalars h{t.beta1, t.one_minus_beta1, t.beta2, t.one_minus_beta2, t.eps, t.step_size, t.sqrt_bc2};
@@ -79,6 +87,10 @@ adamspd_pass1(const cfa_adamspd_tensor* __restrict__ tensors, const cfa_adamspd_
         const int idx = (half * 4 + u) * kAdamThreads + threadIdx.x;
         P[u] = ld_rw((const float4*)p + idx);
         G[u] = ld_stream((const float4*)g + idx);
+        if (kAmp) {
+          G[u].x = __fmul_rn(__fmul_rn(G[u].x, gs0), gs1); G[u].y = __fmul_rn(__fmul_rn(G[u].y, gs0), gs1);
+          G[u].z = __fmul_rn(__fmul_rn(G[u].z, gs0), gs1); G[u].w = __fmul_rn(__fmul_rn(G[u].w, gs0), gs1);
+        }
         M[u] = ld_rw((const float4*)m + idx);
         V[u] = ld_rw((const float4*)v + idx);
         R[u] = pre ? ld_stream((const float4*)pre + idx) : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -110,7 +122,8 @@ adamspd_pass1(const cfa_adamspd_tensor* __restrict__ tensors, const cfa_adamspd_
         if (i < n) {
           float mm = m[i], vv = v[i], np;
           float vm = kAms ? vmax[i] : 0.f;
-          adam_elem(h, p[i], g[i], mm, vv, kAms ? &vm : nullptr, pre ? pre[i] : 0.f, np, s_cond, s_new, s_old);
+          const float gi = kAmp ? __fmul_rn(__fmul_rn(g[i], gs0), gs1) : g[i];
+          adam_elem(h, p[i], gi, mm, vv, kAms ? &vm : nullptr, pre ? pre[i] : 0.f, np, s_cond, s_new, s_old);
           p[i] = np; m[i] = mm; v[i] = vv;
           if (kAms) vmax[i] = vm;
         }
@@ -130,6 +143,84 @@ adamspd_pass1(const cfa_adamspd_tensor* __restrict__ tensors, const cfa_adamspd_
 #pragma unroll
     for (int i = 0; i < kAdamThreads / kWarp; ++i) s += red[threadIdx.x][i];
     atomicAdd(reduce + 3 * (int64_t)ck.tensor + threadIdx.x, s);
+  }
+}
+
+// ---- AMP prologue: GradScaler.unscale_ + clip_grad_norm_ folded into the step ----------------
+// pass 0: per-tensor sum of squares of the UNSCALED gradient g * inv_scale and the non-finite check of
+// torch._amp_foreach_non_finite_check_and_unscale_ (on the raw value) — one read of g (4 B/elt), nothing written back.
+__global__ void __launch_bounds__(kAdamThreads)
+adamspd_gradnorm(const cfa_adamspd_tensor* __restrict__ tensors, const cfa_adamspd_chunk* __restrict__ chunks,
+                 const float* __restrict__ grad_scale, double* __restrict__ gsum /* [n_tensors] */, float* __restrict__ amp) {
+  const cfa_adamspd_chunk ck = chunks[blockIdx.x];
+  const cfa_adamspd_tensor t = tensors[ck.tensor];
+  const float inv = grad_scale ? (float)(1.0 / (double)*grad_scale) : 1.f;      // _scale.double().reciprocal().float()
+  const int64_t base = (int64_t)ck.chunk * kAdamChunk;
+  const int64_t remain = t.numel - base;
+  const int n = remain < kAdamChunk ? (int)remain : kAdamChunk;
+  const float* g = (const float*)t.g + base;
+  float ss = 0.f;
+  bool bad = false;
+  if ((((uintptr_t)g) & 15) == 0 && n == kAdamChunk) {
+    float4 G[kAdamVecPerThread];
+#pragma unroll
+    for (int u = 0; u < kAdamVecPerThread; ++u) G[u] = __ldg((const float4*)g + u * kAdamThreads + threadIdx.x);
+#pragma unroll
+    for (int u = 0; u < kAdamVecPerThread; ++u) {
+      const float x[4] = {G[u].x, G[u].y, G[u].z, G[u].w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        bad |= !isfinite(x[j]);
+        const float y = __fmul_rn(x[j], inv);
+        ss = fmaf(y, y, ss);
+      }
+    }
+  } else {
+    for (int i = threadIdx.x; i < n; i += kAdamThreads) {
+      const float x = g[i];
+      bad |= !isfinite(x);
+      const float y = __fmul_rn(x, inv);
+      ss = fmaf(y, y, ss);
+    }
+  }
+  __shared__ double red[kAdamThreads / kWarp];
+  double a = warp_sum((double)ss);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (lane == 0) red[w] = a;
+  const bool any_bad = __syncthreads_or(bad);
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < kAdamThreads / kWarp; ++i) s += red[i];
+    atomicAdd(gsum + ck.tensor, s);
+    if (any_bad) amp[3] = 1.f;
+  }
+}
+
+// one CTA: total_norm = || (||g_t||)_t ||_2 as clip_grad_norm_ forms it (per-tensor fp32 norms, then the norm of the stack),
+// clip_coef = min(max_norm / (total_norm + 1e-6), 1)   (torch/nn/utils/clip_grad.py)
+__global__ void __launch_bounds__(kAdamThreads)
+adamspd_clipcoef(const double* __restrict__ gsum, int n_tensors, const float* __restrict__ grad_scale, float max_norm,
+                 float* __restrict__ amp) {
+  __shared__ double red[kAdamThreads / kWarp];
+  double a = 0.0;
+  for (int i = threadIdx.x; i < n_tensors; i += kAdamThreads) {
+    const float nt = sqrtf((float)gsum[i]);
+    a += (double)nt * (double)nt;
+  }
+  a = warp_sum(a);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = a;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < kAdamThreads / kWarp; ++i) s += red[i];
+    const float total = (float)sqrt(s);
+    float coef = 1.f;
+    if (max_norm > 0.f) coef = fminf(__fdiv_rn(max_norm, __fadd_rn(total, 1e-6f)), 1.f);
+    amp[0] = grad_scale ? (float)(1.0 / (double)*grad_scale) : 1.f;
+    amp[1] = coef;
+    amp[2] = total;
   }
 }
 
@@ -204,8 +295,28 @@ extern "C" int cfa_adamspd_step(const cfa_adamspd_tensor* d_tensors, int n_tenso
   const bool ams = amsgrad != 0;
   cudaStream_t st = (cudaStream_t)stream;
   CFA_CUDA_TRY(cudaMemsetAsync(d_reduce, 0, sizeof(double) * 3 * (size_t)n_tensors, st));
-  if (ams) cfa::adamspd_pass1<true><<<n_chunks, cfa::kAdamThreads, 0, st>>>(d_tensors, d_chunks, d_reduce);
-  else cfa::adamspd_pass1<false><<<n_chunks, cfa::kAdamThreads, 0, st>>>(d_tensors, d_chunks, d_reduce);
+  if (ams) cfa::adamspd_pass1<true, false><<<n_chunks, cfa::kAdamThreads, 0, st>>>(d_tensors, d_chunks, d_reduce, nullptr);
+  else cfa::adamspd_pass1<false, false><<<n_chunks, cfa::kAdamThreads, 0, st>>>(d_tensors, d_chunks, d_reduce, nullptr);
+  CFA_CUDA_TRY(cudaGetLastError());
+  cfa::adamspd_pass2<<<n_chunks, cfa::kAdamThreads, 0, st>>>(d_tensors, d_chunks, d_reduce, d_stats);
+  return cfa::launch_status();
+}
+
+extern "C" int cfa_adamspd_step_amp(const cfa_adamspd_tensor* d_tensors, int n_tensors, const cfa_adamspd_chunk* d_chunks,
+                                    int n_chunks, double* d_reduce, float* d_stats, const float* d_grad_scale,
+                                    float max_grad_norm, float* d_amp, int dtype, int amsgrad, void* stream) {
+  if (dtype != CFA_DTYPE_F32) return CFA_ERR_UNSUPPORTED;
+  if (n_tensors < 0 || n_chunks < 0 || !d_amp || (n_tensors > 0 && (!d_tensors || !d_chunks || !d_reduce))) return CFA_ERR_BAD_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  CFA_CUDA_TRY(cudaMemsetAsync(d_amp, 0, 4 * sizeof(float), st));
+  if (n_tensors == 0 || n_chunks == 0) return CFA_OK;
+  const bool ams = amsgrad != 0;
+  CFA_CUDA_TRY(cudaMemsetAsync(d_reduce, 0, sizeof(double) * 4 * (size_t)n_tensors, st));
+  double* gsum = d_reduce + 3 * (size_t)n_tensors;
+  cfa::adamspd_gradnorm<<<n_chunks, cfa::kAdamThreads, 0, st>>>(d_tensors, d_chunks, d_grad_scale, gsum, d_amp);
+  cfa::adamspd_clipcoef<<<1, cfa::kAdamThreads, 0, st>>>(gsum, n_tensors, d_grad_scale, max_grad_norm, d_amp);
+  if (ams) cfa::adamspd_pass1<true, true><<<n_chunks, cfa::kAdamThreads, 0, st>>>(d_tensors, d_chunks, d_reduce, d_amp);
+  else cfa::adamspd_pass1<false, true><<<n_chunks, cfa::kAdamThreads, 0, st>>>(d_tensors, d_chunks, d_reduce, d_amp);
   CFA_CUDA_TRY(cudaGetLastError());
   cfa::adamspd_pass2<<<n_chunks, cfa::kAdamThreads, 0, st>>>(d_tensors, d_chunks, d_reduce, d_stats);
   return cfa::launch_status();

@@ -77,7 +77,9 @@ class _Plan:
         self.h_used = [False, False]
         self.flip = 0
         self.d_tab = torch.empty(n * _TENSOR_DT.itemsize, dtype=torch.uint8, device=device)
-        self.d_reduce = torch.empty(3 * n, dtype=torch.float64, device=device)
+        self.d_reduce = torch.empty(4 * n, dtype=torch.float64, device=device)      # 3 SPD sums + (amp) grad sum of squares
+        self.h_flag = torch.zeros(1, dtype=torch.float32).pin_memory()
+        self.d_amp = torch.zeros(4, dtype=torch.float32, device=device)             # inv_scale, clip_coef, total_norm, found_inf
         self.d_stats = torch.zeros(n, 2, dtype=torch.float32, device=device)
 
 
@@ -99,6 +101,7 @@ class AdamSPD(Optimizer):
         defaults = dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, amsgrad=amsgrad)
         super().__init__(params, defaults)
         self._plan = None
+        self._pending_skip = None       # (event, pinned found_inf) of the last amp_step: settles the host step counters
 
     def __setstate__(self, state):
         super().__setstate__(state)
@@ -113,8 +116,41 @@ class AdamSPD(Optimizer):
         params-with-grad were visited.  Reading it on the host synchronises; step() itself never does."""
         return None if self._plan is None else self._plan.d_stats
 
+    def _settle_skipped_step(self):
+        """amp_step decides on the DEVICE whether the step is skipped (non-finite gradients); the host-side `step`
+        counters (Python ints, as in the reference state_dict) are corrected here, one call later, when the flag has
+        long arrived in pinned memory — no stall on the step path."""
+        pend = self._pending_skip
+        if pend is None:
+            return
+        self._pending_skip = None
+        evt, flag, plan = pend
+        evt.synchronize()
+        if float(flag[0]) != 0.0:
+            for st in plan.states:
+                st["step"] -= 1
+            plan.steps_since_build -= 1
+
+    def state_dict(self):
+        self._settle_skipped_step()
+        return super().state_dict()
+
+    @torch.no_grad()
+    def amp_step(self, grad_scaler=None, max_grad_norm=None, closure=None):
+        """`scaler.unscale_(opt); clip_grad_norm_(params, max_grad_norm); scaler.step(opt)` (finetuner.py:150-152) in
+        one call: the unscale and clip passes over the gradients are folded into the multi-tensor step
+        (cfa_adamspd_step_amp: one extra READ of g instead of two read-modify-write passes, no host sync; the
+        reference's GradScaler.step synchronises on found_inf every step).  Gradients stay as they are in memory
+        (still scaled) — the reference zeroes them right after (finetuner.py:154).  Returns the total gradient norm
+        (0-dim device tensor), like clip_grad_norm_.  `scaler.update()` is called by the caller as before."""
+        return self._step_impl(closure, amp=(grad_scaler, max_grad_norm))
+
     @torch.no_grad()
     def step(self, closure=None):
+        return self._step_impl(closure, amp=None)
+
+    def _step_impl(self, closure, amp):
+        self._settle_skipped_step()
         loss = None
         if closure is not None:
             with torch.enable_grad():
@@ -128,7 +164,7 @@ class AdamSPD(Optimizer):
         grads_all = [p.grad for p in all_params]
         has_grad = tuple(g is not None for g in grads_all)
         if not any(has_grad):
-            return loss
+            return loss if amp is None else torch.zeros(())
         grads = [g for g in grads_all if g is not None]
         if plan is None or plan.has_grad != has_grad or len(all_params) != sum(len(g["params"]) for g in self.param_groups):
             plan = self._build_plan(grads)
@@ -140,8 +176,8 @@ class AdamSPD(Optimizer):
         for st in plan.states:                          # optimizers.py:81
             st["step"] += 1
         plan.steps_since_build += 1
-        self._launch(plan, grads)
-        return loss
+        total_norm = self._launch(plan, grads, amp)
+        return loss if amp is None else total_norm
 
     # ------------------------------------------------------------------
     def _build_plan(self, grads):
@@ -195,7 +231,7 @@ class AdamSPD(Optimizer):
         self._plan = _Plan(self, all_params, tuple(has_grad), bool(amsgrad_all), dev)
         return self._plan
 
-    def _launch(self, plan, grads):
+    def _launch(self, plan, grads, amp=None):
         k = plan.flip
         plan.flip ^= 1
         if plan.h_used[k]:
@@ -207,9 +243,7 @@ class AdamSPD(Optimizer):
         if not np.array_equal(pptr, plan.static["p"]):
             self._plan = None
             plan = self._build_plan(grads)
-            for st in plan.states:
-                pass
-            return self._launch(plan, grads)
+            return self._launch(plan, grads, amp)
         # per-step scalars: Python doubles like the reference (optimizers.py:123-124,139), rounded once to fp32
         rows = np.empty((len(plan.combos), 8), dtype=np.float32)
         for ci, (gi, step0) in enumerate(plan.combos):
@@ -228,6 +262,41 @@ class AdamSPD(Optimizer):
             plan.d_tab.copy_(plan.h_tab[k], non_blocking=True)
             plan.h_evt[k].record()
             plan.h_used[k] = True
-            _lib.call("cfa_adamspd_step", plan.d_tab.data_ptr(), plan.n, plan.d_chunks.data_ptr(), plan.n_chunks,
-                      plan.d_reduce.data_ptr(), plan.d_stats.data_ptr(), 0, int(plan.amsgrad), _lib.stream_ptr())
+            total_norm = None
+            if amp is None:
+                _lib.call("cfa_adamspd_step", plan.d_tab.data_ptr(), plan.n, plan.d_chunks.data_ptr(), plan.n_chunks,
+                          plan.d_reduce.data_ptr(), plan.d_stats.data_ptr(), 0, int(plan.amsgrad), _lib.stream_ptr())
+            else:
+                scaler, max_norm = amp
+                scale_ptr = 0
+                enabled = scaler is not None and scaler.is_enabled()
+                if enabled:
+                    from torch.amp.grad_scaler import OptState
+                    ost = scaler._per_optimizer_states[id(self)]
+                    if ost["stage"] is OptState.UNSCALED:
+                        raise RuntimeError("amp_step() replaces scaler.unscale_(): the gradients of this optimizer were "
+                                           "already unscaled")
+                    if ost["stage"] is OptState.STEPPED:
+                        raise RuntimeError("amp_step() has already been called since the last update().")
+                    if scaler._scale is None:
+                        scaler._lazy_init_scale_growth_tracker(dev)
+                    scale = scaler._scale
+                    if scale.device != dev:
+                        scale = scale.to(dev, non_blocking=True)
+                    scale_ptr = scale.data_ptr()
+                _lib.call("cfa_adamspd_step_amp", plan.d_tab.data_ptr(), plan.n, plan.d_chunks.data_ptr(), plan.n_chunks,
+                          plan.d_reduce.data_ptr(), plan.d_stats.data_ptr(), scale_ptr,
+                          float(max_norm) if max_norm is not None else 0.0, plan.d_amp.data_ptr(), 0, int(plan.amsgrad),
+                          _lib.stream_ptr())
+                res = plan.d_amp.clone()             # this step's {inv_scale, clip_coef, total_norm, found_inf}
+                total_norm = res[2]
+                if enabled:                          # what scaler.update() reads (torch/amp/grad_scaler.py)
+                    ost["found_inf_per_device"] = {dev: res[3:4]}
+                    ost["stage"] = OptState.STEPPED
+                flag = plan.h_flag                   # settled at the start of the next call, so one buffer is enough
+                flag.copy_(res[3:4], non_blocking=True)
+                evt = torch.cuda.Event()
+                evt.record()
+                self._pending_skip = (evt, flag, plan)
         self._keepalive = grads      # contiguous copies (if any) must outlive the async launch
+        return total_norm

@@ -82,6 +82,20 @@ int cfa_adamspd_step(const cfa_adamspd_tensor* d_tensors, int n_tensors,
                      const cfa_adamspd_chunk* d_chunks, int n_chunks,
                      double* d_reduce, float* d_stats, int dtype, int amsgrad, void* stream);
 
+/*
+ * The same step with GradScaler.unscale_ and clip_grad_norm_ folded in (the reference issues them as two extra
+ * read-modify-write passes over every gradient right before the step, finetune/finetuner.py:150-152):
+ *   pass 0 reads g once: per-tensor ||g / scale||^2 and the non-finite check; one CTA forms total_norm and
+ *   clip_coef = min(max_grad_norm / (total_norm + 1e-6), 1); pass 1 consumes (g * inv_scale) * clip_coef (the
+ *   reference's two fp32 roundings) and is skipped entirely, like GradScaler.step, when a gradient is inf / NaN.
+ * Gradients are left untouched in memory.  d_grad_scale: DEVICE scalar (GradScaler's scale) or NULL = 1;
+ * max_grad_norm <= 0: no clipping.  d_amp: DEVICE [4] out = { inv_scale, clip_coef, total_norm, found_inf (0/1) }.
+ * d_reduce: [4*n_tensors] doubles here (the 4th block holds the gradient sums of squares).
+ */
+int cfa_adamspd_step_amp(const cfa_adamspd_tensor* d_tensors, int n_tensors, const cfa_adamspd_chunk* d_chunks,
+                         int n_chunks, double* d_reduce, float* d_stats, const float* d_grad_scale,
+                         float max_grad_norm, float* d_amp, int dtype, int amsgrad, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Global (batch-level) InfoNCE, both directions per call (losses.py:14-36 CustomCLIPLoss; :145-163 and :207-217
  * SPARCLoss.pairwise_contrastive_loss on the pooled embeddings).

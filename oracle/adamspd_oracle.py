@@ -55,3 +55,37 @@ def adamspd_step(params: List[torch.Tensor], grads: List[Optional[torch.Tensor]]
                                          steps[j], lr, betas[0], betas[1], eps, weight_decay,
                                          None if vmaxs is None else vmaxs[j]))
     return stats
+
+
+# --------------------------------------------------------------------------
+# AMP prologue folded into the step:
+#   scaler.unscale_(optimizer); clip_grad_norm_(params, max_norm); scaler.step(optimizer)
+# finetune/finetuner.py:150-152.  The arithmetic is torch's (torch/amp/grad_scaler.py,
+# torch/nn/utils/clip_grad.py, version of this image: 2.11); pinned by
+# tests/golden/ampstep_*.pt (made with the reference AdamSPD + torch.amp.GradScaler on CPU).
+# --------------------------------------------------------------------------
+def amp_unscale_clip(grads: List[Optional[torch.Tensor]], scale: float, max_norm: Optional[float]):
+    """Returns (effective grads or None when the step must be skipped, total_norm, found_inf).
+    unscale_: g *= (1/scale as double -> float), found_inf if any raw g is non-finite;
+    clip_grad_norm_: per-tensor fp32 2-norms, norm of their stack, g *= clamp(max_norm / (total + 1e-6), max=1)."""
+    inv = torch.tensor(scale, dtype=torch.float32).double().reciprocal().float()
+    present = [g for g in grads if g is not None]
+    found_inf = any(not bool(torch.isfinite(g).all()) for g in present)
+    un = [None if g is None else (g if float(inv) == 1.0 else g * inv) for g in grads]
+    norms = [torch.linalg.vector_norm(g, 2.0) for g in un if g is not None]
+    total = torch.linalg.vector_norm(torch.stack(norms), 2.0)
+    if max_norm is not None:
+        coef = torch.clamp(max_norm / (total + 1e-6), max=1.0)
+        un = [None if g is None else g * coef for g in un]
+    return (None if found_inf else un), float(total), found_inf
+
+
+def amp_scale_update(scale: float, growth_tracker: int, found_inf: bool, growth_factor: float = 2.0,
+                     backoff_factor: float = 0.5, growth_interval: int = 2000):
+    """GradScaler.update (torch._amp_update_scale_): back off on inf, grow after `growth_interval` clean steps."""
+    if found_inf:
+        return scale * backoff_factor, 0
+    growth_tracker += 1
+    if growth_tracker == growth_interval:
+        return scale * growth_factor, 0
+    return scale, growth_tracker

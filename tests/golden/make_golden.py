@@ -158,10 +158,52 @@ def adamspd_case(ref_opt, name, sizes, steps, lr, betas, eps, wd, amsgrad, seed,
     print("adamspd", name, "steps", steps, "p[0][:3]", params[0].detach().flatten()[:3].tolist())
 
 
+def adamspd_amp_case(ref_opt, name, sizes, steps, lr, wd, max_norm, seed, inf_steps=(5, 11)):
+    """The reference's update sequence under AMP (finetune/finetuner.py:147-154): scaler.unscale_ -> clip_grad_norm_ ->
+    scaler.step -> scaler.update, with the unmodified AdamSPD and torch's GradScaler on CPU.  Gradients are handed over
+    already multiplied by the current scale (what backward of the scaled loss produces); on `inf_steps` one gradient
+    holds an inf, so the step is skipped and the scale backs off."""
+    g = torch.Generator().manual_seed(seed)
+    p0 = [torch.randn(*s, generator=g) * 0.02 for s in sizes]
+    pre = [p + 1e-3 * torch.randn(*p.shape, generator=g) for p in p0]
+    mags = [float(0.5 + 3.0 * torch.rand(1, generator=g)) for _ in range(steps)]       # some steps clip, some do not
+    grads = [[torch.randn(*s, generator=g) * 1e-3 * mags[t] for s in sizes] for t in range(steps)]
+    params = [torch.nn.Parameter(p.clone()) for p in p0]
+    opt = ref_opt.AdamSPD([{"params": params, "pre": pre}], lr=lr, betas=(0.9, 0.999), eps=1e-8, weight_decay=wd)
+    scaler = torch.amp.GradScaler("cpu", init_scale=1024.0, growth_interval=3)
+    scaler.scale(torch.zeros(1))                                   # lazy init of the scale tensor
+    snaps, norms, scales, skipped = {}, [], [], []
+    for t in range(steps):
+        scale = float(scaler.get_scale())
+        scales.append(scale)
+        for j, p in enumerate(params):
+            p.grad = grads[t][j] * scale
+        if t in inf_steps:
+            params[2].grad.view(-1)[3] = float("inf")
+        scaler.unscale_(opt)
+        norms.append(float(torch.nn.utils.clip_grad_norm_(params, max_norm)))
+        before = params[0].detach().clone()
+        scaler.step(opt)
+        scaler.update()
+        skipped.append(bool(torch.equal(before, params[0].detach())))
+        if t + 1 in (1, 2, 6, 7, 12, steps):
+            snaps[t + 1] = [p.detach().clone() for p in params]
+    state_steps = [opt.state[p]["step"] for p in params]
+    torch.save(dict(name=name, sizes=sizes, steps=steps, lr=lr, wd=wd, max_norm=max_norm, p0=p0, pre=pre, grads=grads,
+                    inf_steps=tuple(inf_steps), snaps=snaps, norms=norms, scales=scales, skipped=skipped,
+                    state_steps=state_steps, final_scale=float(scaler.get_scale())),
+               os.path.join(HERE, f"ampstep_{name}.pt"))
+    print("adamspd amp", name, "clipped steps", sum(n > max_norm for n in norms if n == n and n != float("inf")),
+          "skipped", sum(skipped), "final scale", float(scaler.get_scale()), "steps", state_steps[0])
+
+
 def main():
     torch.manual_seed(0)
     torch.set_num_threads(4)
     ref_losses, ref_opt = import_reference()
+    if "--only-adamspd-amp" in sys.argv:
+        adamspd_amp_case(ref_opt, "s16", [(1,), (7,), (33, 31), (4099,), (64, 64), (8193,)], 16, 2e-5, 0.1, 0.2, seed=21)
+        return
     if "--only-masked-pairwise" in sys.argv:
         masked_pairwise_case(ref_losses, "b3_t20_d48", 3, 20, 48, 3.0, seed=12)
         return
@@ -181,6 +223,7 @@ def main():
     adamspd_case(ref_opt, "s12_ams_lr1e3", sizes, 12, 1e-3, (0.9, 0.98), 5e-6, 0.2, True, seed=10)
     adamspd_case(ref_opt, "s8_nopre_nonegrad", sizes, 8, 1e-3, (0.9, 0.999), 1e-8, 0.1, False, seed=11,
                  with_pre=False, none_grad_idx=(1, 3))
+    adamspd_amp_case(ref_opt, "s16", [(1,), (7,), (33, 31), (4099,), (64, 64), (8193,)], 16, 2e-5, 0.1, 0.2, seed=21)
 
 
 if __name__ == "__main__":

@@ -117,3 +117,59 @@ def test_adamspd_state_dict_roundtrip_and_unaligned_views():
     p.grad = torch.randn(10000, device="cuda") * 1e-2
     opt2.step()
     assert opt2.state[p]["step"] == 4
+
+
+def test_amp_step_matches_reference_sequence_golden():
+    """AdamSPD.amp_step(scaler, max_norm) == scaler.unscale_ + clip_grad_norm_ + scaler.step of the reference
+    (finetuner.py:150-152; fixture: reference AdamSPD + torch GradScaler on CPU).  Covers clipped and unclipped steps,
+    two skipped (inf) steps with scale back-off, scale growth, and the host step counters.  Bar: |p - p_ref| <= 1e-6."""
+    from clip_finegrained_alignment_b200 import AdamSPD
+    f = load_golden("ampstep_s16.pt")
+    params = [torch.nn.Parameter(x.clone().cuda()) for x in f["p0"]]
+    opt = AdamSPD([{"params": params, "pre": [x.cuda() for x in f["pre"]]}], lr=f["lr"], betas=(0.9, 0.999), eps=1e-8,
+                  weight_decay=f["wd"])
+    scaler = torch.amp.GradScaler("cuda", init_scale=1024.0, growth_interval=3)
+    scaler.scale(torch.zeros(1, device="cuda"))
+    for t in range(f["steps"]):
+        scale = float(scaler.get_scale())
+        assert scale == f["scales"][t], (t, scale)
+        for j, p in enumerate(params):
+            p.grad = (f["grads"][t][j] * scale).cuda()
+        if t in f["inf_steps"]:
+            params[2].grad.view(-1)[3] = float("inf")
+        raw = [p.grad.clone() for p in params]
+        total = opt.amp_step(scaler, f["max_norm"])
+        scaler.update()
+        for p, r in zip(params, raw):                      # gradients are left untouched
+            assert torch.equal(p.grad, r) or t in f["inf_steps"]
+        if not f["skipped"][t]:
+            assert abs(float(total) - f["norms"][t]) <= 1e-5 * f["norms"][t], (t, float(total), f["norms"][t])
+        if t + 1 in f["snaps"]:
+            for x, r in zip(params, f["snaps"][t + 1]):
+                assert (x.detach().cpu() - r).abs().max().item() <= 1e-6, t
+    sd = opt.state_dict()                                   # settles the device-side skip decisions
+    assert [sd["state"][j]["step"] for j in range(len(params))] == f["state_steps"]
+    assert float(scaler.get_scale()) == f["final_scale"]
+
+
+def test_amp_step_without_scaler_equals_clip_then_step():
+    """No GradScaler (fp32 training, finetuner.py:156-183 path): amp_step(None, max_norm) == clip_grad_norm_ + step."""
+    from clip_finegrained_alignment_b200 import AdamSPD
+    torch.manual_seed(5)
+    shapes = [(70001,), (300, 41), (8192,)]
+    w = [torch.randn(*s, device="cuda") * 0.02 for s in shapes]
+    pre = [x + 1e-3 * torch.randn_like(x) for x in w]
+    pa = [torch.nn.Parameter(x.clone()) for x in w]
+    pb = [torch.nn.Parameter(x.clone()) for x in w]
+    oa = AdamSPD([{"params": pa, "pre": pre}], lr=2e-5, weight_decay=0.1)
+    ob = AdamSPD([{"params": pb, "pre": pre}], lr=2e-5, weight_decay=0.1)
+    for t in range(6):
+        gs = [torch.randn(*s, device="cuda") * (1e-3 if t % 2 else 1e-1) for s in shapes]
+        for p, q, g in zip(pa, pb, gs):
+            p.grad = g.clone(); q.grad = g.clone()
+        na = oa.amp_step(None, 1.0)
+        nb = torch.nn.utils.clip_grad_norm_(pb, 1.0)
+        ob.step()
+        assert abs(float(na) - float(nb)) <= 1e-5 * float(nb)
+    for p, q in zip(pa, pb):
+        assert (p - q).abs().max().item() <= 1e-7

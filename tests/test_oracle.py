@@ -188,6 +188,32 @@ def test_adamspd_oracle_matches_reference(fname):
         assert took > 0          # the SPD branch (optimizers.py:148-150) was exercised
 
 
+def test_amp_step_oracle_matches_reference_sequence():
+    """unscale_ -> clip_grad_norm_ -> scaler.step -> update (finetuner.py:150-153), restated, vs the fixture made with
+    the reference AdamSPD and torch's GradScaler: bit-exact parameters, norms, scales, skipped steps."""
+    f = load_golden("ampstep_s16.pt")
+    p = [x.clone() for x in f["p0"]]
+    m = [torch.zeros_like(x) for x in p]
+    v = [torch.zeros_like(x) for x in p]
+    steps = [0] * len(p)
+    scale, tracker = 1024.0, 0
+    for t in range(f["steps"]):
+        assert scale == f["scales"][t]
+        grads = [g * scale for g in f["grads"][t]]
+        if t in f["inf_steps"]:
+            grads[2].view(-1)[3] = float("inf")
+        eff, total, found = ao.amp_unscale_clip(grads, scale, f["max_norm"])
+        assert found == f["skipped"][t]
+        if not found:
+            assert abs(total - f["norms"][t]) <= 1e-6 * f["norms"][t]
+            ao.adamspd_step(p, eff, m, v, f["pre"], steps, f["lr"], (0.9, 0.999), 1e-8, f["wd"])
+        scale, tracker = ao.amp_scale_update(scale, tracker, found, growth_interval=3)
+        if t + 1 in f["snaps"]:
+            for x, r in zip(p, f["snaps"][t + 1]):
+                assert torch.equal(x, r), t
+    assert steps == f["state_steps"] and scale == f["final_scale"]
+
+
 def test_live_reference_if_present():
     mods = reference_modules()
     if mods is None:
