@@ -446,3 +446,125 @@ class CustomCLIPLoss(nn.Module):
         clip_loss = _ClipFunction.apply(image_features, text_features, float(self.temperature), self.gather,
                                         self.process_group)
         return {"clip_loss": clip_loss, "total_loss": clip_loss}
+
+
+# ----------------------------------------------------------------------------------------------
+# Counting losses: CLIPCountLoss (losses.py:39-133), CountLoss (losses.py:267-309)
+# ----------------------------------------------------------------------------------------------
+class _LogitsCEFunction(torch.autograd.Function):
+    """(CE(img_logits, arange) + CE(text_logits, arange)) / 2 on caller-provided [B,B] logits (losses.py:276-279)."""
+
+    @staticmethod
+    def forward(ctx, la, lb):
+        dev = _lib.require_cuda(la, lb)
+        if la.dim() != 2 or la.shape[0] != la.shape[1] or lb.shape != la.shape or la.dtype != lb.dtype \
+                or la.dtype not in _lib.DTYPE_CODE:
+            raise _lib.CfaError(f"CountLoss: expected two [B,B] logits of one dtype, got {tuple(la.shape)}, {tuple(lb.shape)}")
+        la = la.contiguous(); lb = lb.contiguous()
+        B = la.shape[0]
+        buf = torch.empty(4 * B + 1, dtype=torch.float32, device=dev)          # lse2 [2,B] | ce2 [2,B] | out
+        p0 = buf.data_ptr()
+        with torch.cuda.device(dev):
+            _lib.call("cfa_logits_ce_fwd", la.data_ptr(), lb.data_ptr(), B, _lib.DTYPE_CODE[la.dtype], p0, p0 + 8 * B,
+                      p0 + 16 * B, _lib.stream_ptr())
+        ctx.save_for_backward(la, lb, buf)
+        return buf[4 * B].clone()
+
+    @staticmethod
+    def backward(ctx, g):
+        la, lb, buf = ctx.saved_tensors
+        B = la.shape[0]
+        g = g.to(device=la.device, dtype=torch.float32).contiguous()
+        da, db = torch.empty_like(la), torch.empty_like(lb)
+        with torch.cuda.device(la.device):
+            _lib.call("cfa_logits_ce_bwd", la.data_ptr(), lb.data_ptr(), B, _lib.DTYPE_CODE[la.dtype], buf.data_ptr(),
+                      g.data_ptr(), da.data_ptr(), db.data_ptr(), _lib.stream_ptr())
+        return da, db
+
+
+class _CountContrastiveFunction(torch.autograd.Function):
+    """mean_b [ log sum_c exp(e_i . e_cf[c] / T) - e_i . e_k / T ] on L2-normalised rows (losses.py:281-301)."""
+
+    @staticmethod
+    def forward(ctx, ei, ek, ek_cf, temperature, include_pos):
+        dev = _lib.require_cuda(ei, ek, ek_cf)
+        if ei.dim() != 2 or ek.shape != ei.shape or ek_cf.dim() != 3 or ek_cf.shape[0] != ei.shape[0] \
+                or ek_cf.shape[2] != ei.shape[1]:
+            raise _lib.CfaError(f"CountLoss: bad shapes ei{tuple(ei.shape)} ek{tuple(ek.shape)} ek_cf{tuple(ek_cf.shape)}")
+        if not (ei.dtype == ek.dtype == ek_cf.dtype) or ei.dtype not in _lib.DTYPE_CODE:
+            raise _lib.CfaError("CountLoss: embeddings must share a dtype in fp32/bf16/fp16")
+        ei = ei.contiguous(); ek = ek.contiguous(); ek_cf = ek_cf.contiguous()
+        B, D = ei.shape
+        C = ek_cf.shape[1]
+        buf = torch.empty(B + 1, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            _lib.call("cfa_count_contrastive_fwd", ei.data_ptr(), ek.data_ptr(), ek_cf.data_ptr(), B, C, D,
+                      _lib.DTYPE_CODE[ei.dtype], temperature, int(include_pos), buf.data_ptr(), buf.data_ptr() + 4 * B,
+                      _lib.stream_ptr())
+        ctx.save_for_backward(ei, ek, ek_cf)
+        ctx.hp = (temperature, int(include_pos))
+        return buf[B].clone()
+
+    @staticmethod
+    def backward(ctx, g):
+        ei, ek, ek_cf = ctx.saved_tensors
+        B, D = ei.shape
+        C = ek_cf.shape[1]
+        g = g.to(device=ei.device, dtype=torch.float32).contiguous()
+        dei, dek, dcf = torch.empty_like(ei), torch.empty_like(ek), torch.empty_like(ek_cf)
+        with torch.cuda.device(ei.device):
+            _lib.call("cfa_count_contrastive_bwd", ei.data_ptr(), ek.data_ptr(), ek_cf.data_ptr(), B, C, D,
+                      _lib.DTYPE_CODE[ei.dtype], ctx.hp[0], ctx.hp[1], g.data_ptr(), dei.data_ptr(), dek.data_ptr(),
+                      dcf.data_ptr(), _lib.stream_ptr())
+        return dei, dek, dcf, None, None
+
+
+class CountLoss(nn.Module):
+    """Reference API: finetune/losses.py:267-309 (used by count_finetuner.py:125-131).
+    forward(img_logits[B,B], text_logits[B,B], ei[B,D], ek[B,D], ek_cf[B,C,D]) -> clip_loss, count_loss, total_loss."""
+
+    def __init__(self, temperature: float = 0.07, alpha=1.0):
+        super().__init__()
+        self.temperature = temperature
+        self.alpha = alpha
+
+    def forward(self, img_logits, text_logits, ei, ek, ek_cf) -> Dict[str, torch.Tensor]:
+        clip_loss = _LogitsCEFunction.apply(img_logits, text_logits)
+        count_loss = _CountContrastiveFunction.apply(ei, ek, ek_cf, float(self.temperature), False)
+        total_loss = clip_loss + self.alpha * count_loss                          # losses.py:303
+        return {"clip_loss": clip_loss, "count_loss": count_loss, "total_loss": total_loss}
+
+
+class CLIPCountLoss(nn.Module):
+    """Reference API: finetune/losses.py:39-133.  image_features [B,D], text_features [E,D] with E = B * templates:
+    the image rows are repeated per template and the CLIP InfoNCE runs on the expanded E x E problem (global InfoNCE
+    kernels).  The reference's count term groups `counts.size(0) // E` captions per expanded row out of the SAME [E,D]
+    text matrix (:51,:69-86): with one count per caption the group is the positive alone and the term is exactly 0 (its
+    gradient too); any other group size indexes past the text matrix and raises IndexError in the reference — kept."""
+
+    def __init__(self, temperature: float = 0.07, count_alpha: float = 0.5, gather: bool = False, process_group=None):
+        super().__init__()
+        self.temperature = temperature
+        self.count_alpha = count_alpha
+        self.gather = gather
+        self.process_group = process_group
+
+    def count_loss(self, ei: torch.Tensor, ek: torch.Tensor, counts: torch.Tensor) -> torch.Tensor:
+        batch_size = ei.size(0)
+        group_size = counts.size(0) // batch_size
+        if group_size != 1:
+            raise IndexError("index 0 is out of bounds for dimension 0 with size 0")     # what losses.py:76 ends in
+        return torch.zeros((), dtype=torch.float64, device=ei.device)                    # -log(num / (num + 0)), fp64 (:55)
+
+    def forward(self, image_features: torch.Tensor, text_features: torch.Tensor,
+                count_features: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
+        batch_size = image_features.size(0)
+        expanded = text_features.size(0)
+        num_templates = expanded // batch_size                                            # losses.py:100-101
+        image_exp = image_features.repeat_interleave(num_templates, dim=0)                # losses.py:104
+        clip_loss = _ClipFunction.apply(image_exp, text_features, float(self.temperature), self.gather, self.process_group)
+        count_loss = torch.tensor(0.0, device=image_features.device)                     # losses.py:117
+        if count_features is not None:
+            count_loss = self.count_loss(image_exp, text_features, count_features) * self.count_alpha
+        total_loss = clip_loss + count_loss
+        return {"clip_loss": clip_loss, "count_loss": count_loss, "total_loss": total_loss}

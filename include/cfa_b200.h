@@ -242,6 +242,25 @@ int cfa_masked_pairwise_bwd(const void* a, const void* b, const uint8_t* mask, i
                             const float* lse_row, const float* out2, const float* grad, void* da, void* db, void* stream);
 
 /*
+ * Counting losses (fp32 CUDA-core kernels, any of the three dtypes in and out).
+ * cfa_count_contrastive_*: CountLoss's counterfactual term (losses.py:281-301).  ei, ek [B,D], ek_cf [B,C,D];
+ *   rows are L2-normalised (no eps); per_sample[b] = log sum_c exp(e_i.e_cf[c] / T) - e_i.e_k / T; *out = mean_b.
+ *   include_pos != 0 also puts exp(e_i.e_k / T) in the denominator (the grouping of CLIPCountLoss.count_loss, :69-86).
+ *   Backward: grad = DEVICE scalar d(out); dei, dek [B,D], dek_cf [B,C,D] in `dtype`.
+ * cfa_logits_ce_*: CountLoss's CLIP term on caller-provided logits (losses.py:276-279): logits_a, logits_b [B,B];
+ *   *out = (mean_i CE(a_i, i) + mean_i CE(b_i, i)) / 2; lse2, ce2: [2][B] floats (lse2 feeds the backward).
+ */
+int cfa_count_contrastive_fwd(const void* ei, const void* ek, const void* ek_cf, int B, int C, int D, int dtype,
+                              float temperature, int include_pos, float* per_sample, float* out, void* stream);
+int cfa_count_contrastive_bwd(const void* ei, const void* ek, const void* ek_cf, int B, int C, int D, int dtype,
+                              float temperature, int include_pos, const float* grad, void* dei, void* dek, void* dek_cf,
+                              void* stream);
+int cfa_logits_ce_fwd(const void* logits_a, const void* logits_b, int B, int dtype, float* lse2, float* ce2, float* out,
+                      void* stream);
+int cfa_logits_ce_bwd(const void* logits_a, const void* logits_b, int B, int dtype, const float* lse2, const float* grad,
+                      void* dlogits_a, void* dlogits_b, void* stream);
+
+/*
  * Scalar epilogue (losses.py:163,196,217,252-264): sums the per-row / per-sample partials and writes
  * out[0..6] = global_loss, local_loss, total_loss, loss_vl, loss_lv, loss_vl_local, loss_lv_local and
  * out[7] = n_valid (sum of mask).  global_sums: DEVICE [2] = sum_i CE_vl(i), sum_j CE_lv(j) over the GLOBAL

@@ -369,3 +369,75 @@ def sparc_reference_truncated(ref_loss_module, v, l, mask):
         n += idx.numel()
     n_valid = float(torch.tensor(n) + NVALID_EPS)      # fp32 promotion as in losses.py:196
     return tot_vl / n_valid, tot_lv / n_valid
+
+
+# --------------------------------------------------------------------------
+# Counting losses (finetune/losses.py:39-133 CLIPCountLoss, :267-309 CountLoss) — SURVEY.md §8f rank 3
+# --------------------------------------------------------------------------
+def logits_ce_forward(la: torch.Tensor, lb: torch.Tensor) -> Dict[str, torch.Tensor]:
+    """(CE(la, arange) + CE(lb, arange)) / 2, mean reduction (losses.py:276-279)."""
+    B = la.shape[0]
+    ar = torch.arange(B)
+    lse_a, lse_b = _lse(la, 1), _lse(lb, 1)
+    loss = 0.5 * ((lse_a - la[ar, ar]).mean() + (lse_b - lb[ar, ar]).mean())
+    return {"loss": loss, "lse_a": lse_a, "lse_b": lse_b}
+
+
+def logits_ce_backward(la, lb, fwd, grad_out: float = 1.0):
+    B = la.shape[0]
+    eye = torch.eye(B, dtype=la.dtype)
+    c = grad_out * 0.5 / B
+    return c * (torch.exp(la - fwd["lse_a"][:, None]) - eye), c * (torch.exp(lb - fwd["lse_b"][:, None]) - eye)
+
+
+def count_contrastive_forward(ei, ek, ek_cf, temperature: float, include_pos: bool = False):
+    """losses.py:281-301: rows normalised without eps; loss_b = -log(exp(pos) / sum_c exp(cf_c)), mean over b.
+    include_pos adds exp(pos) to the denominator (the grouping of CLIPCountLoss.count_loss, losses.py:78-86)."""
+    ih, inn = l2_normalize(ei, 0.0)
+    kh, kn = l2_normalize(ek, 0.0)
+    ch, cn = l2_normalize(ek_cf, 0.0)
+    pos = (ih * kh).sum(1) / temperature                        # :289
+    cfs = (ih[:, None, :] * ch).sum(2) / temperature            # :297
+    allc = torch.cat([pos[:, None], cfs], dim=1) if include_pos else cfs
+    lse = _lse(allc, 1)
+    loss = (lse - pos).mean()                                   # :301-303
+    return {"loss": loss, "_c": dict(ih=ih, inn=inn, kh=kh, kn=kn, ch=ch, cn=cn, pos=pos, cfs=cfs, lse=lse,
+                                     T=temperature, include_pos=include_pos)}
+
+
+def count_contrastive_backward(fwd, grad_out: float = 1.0):
+    c = fwd["_c"]
+    B = c["pos"].shape[0]
+    gb = grad_out / B
+    dcf = gb * torch.exp(c["cfs"] - c["lse"][:, None])          # d loss / d cf score
+    dpos = torch.full_like(c["pos"], -gb)
+    if c["include_pos"]:
+        dpos = dpos + gb * torch.exp(c["pos"] - c["lse"])
+    dih = (dpos[:, None] * c["kh"] + (dcf[:, :, None] * c["ch"]).sum(1)) / c["T"]
+    dkh = dpos[:, None] * c["ih"] / c["T"]
+    dch = dcf[:, :, None] * c["ih"][:, None, :] / c["T"]
+    return (l2_normalize_bwd(c["ih"], c["inn"], dih), l2_normalize_bwd(c["kh"], c["kn"], dkh),
+            l2_normalize_bwd(c["ch"], c["cn"], dch))
+
+
+def count_loss_forward(img_logits, text_logits, ei, ek, ek_cf, temperature: float, alpha: float):
+    """CountLoss.forward (losses.py:273-309)."""
+    f1 = logits_ce_forward(img_logits, text_logits)
+    f2 = count_contrastive_forward(ei, ek, ek_cf, temperature)
+    return {"clip_loss": f1["loss"], "count_loss": f2["loss"], "total_loss": f1["loss"] + alpha * f2["loss"],
+            "_f1": f1, "_f2": f2}
+
+
+def clip_count_forward(img, txt, temperature: float):
+    """CLIPCountLoss.forward (losses.py:91-133) for one count per caption: the CLIP loss on the template-expanded
+    batch (image rows repeated, :104); the count term is exactly 0 (group of one, :69-86)."""
+    nt = txt.shape[0] // img.shape[0]
+    f = clip_loss_forward(img.repeat_interleave(nt, dim=0), txt, temperature)
+    return {"clip_loss": f["clip_loss"], "count_loss": torch.zeros((), dtype=torch.float64), "total_loss": f["clip_loss"],
+            "_f": f, "_nt": nt}
+
+
+def clip_count_backward(fwd, temperature: float, grad_out: float = 1.0):
+    da_exp, db = clip_loss_backward(fwd["_f"], temperature, grad_out)
+    nt = fwd["_nt"]
+    return da_exp.view(-1, nt, da_exp.shape[1]).sum(1), db      # repeat_interleave backward: sum over the copies

@@ -158,6 +158,35 @@ def adamspd_case(ref_opt, name, sizes, steps, lr, betas, eps, wd, amsgrad, seed,
     print("adamspd", name, "steps", steps, "p[0][:3]", params[0].detach().flatten()[:3].tolist())
 
 
+def count_cases(ref_losses):
+    """CountLoss (losses.py:267-309) and CLIPCountLoss (:39-133) on seeded inputs, fp64 and fp32, autograd gradients."""
+    g = torch.Generator().manual_seed(31)
+    B, C, D, T, alpha = 6, 5, 32, 0.07, 0.7
+    out = dict(B=B, C=C, D=D, T=T, alpha=alpha)
+    base = dict(la=torch.randn(B, B, generator=g, dtype=torch.float64) * 3, lb=torch.randn(B, B, generator=g, dtype=torch.float64) * 3,
+                ei=torch.randn(B, D, generator=g, dtype=torch.float64), ek=torch.randn(B, D, generator=g, dtype=torch.float64),
+                cf=torch.randn(B, C, D, generator=g, dtype=torch.float64))
+    out["inputs"] = base
+    for dt in (torch.float64, torch.float32):
+        xs = {k: v.to(dt).clone().requires_grad_(True) for k, v in base.items()}
+        res = ref_losses.CountLoss(T, alpha)(xs["la"], xs["lb"], xs["ei"], xs["ek"], xs["cf"])
+        res["total_loss"].backward()
+        out[str(dt)] = dict(losses={k: v.detach().clone() for k, v in res.items()}, grads={k: v.grad.clone() for k, v in xs.items()})
+    torch.save(out, os.path.join(HERE, "countloss_b6_c5_d32.pt"))
+    print("countloss", {k: float(v) for k, v in out["torch.float64"]["losses"].items()})
+    Bi, nt, D2 = 4, 3, 24
+    img = torch.randn(Bi, D2, generator=g, dtype=torch.float64)
+    txt = torch.randn(Bi * nt, D2, generator=g, dtype=torch.float64)
+    out2 = dict(B=Bi, nt=nt, D=D2, T=0.07, img=img, txt=txt)
+    for dt in (torch.float64, torch.float32):
+        a = img.to(dt).clone().requires_grad_(True); b = txt.to(dt).clone().requires_grad_(True)
+        res = ref_losses.CLIPCountLoss(0.07, 0.5)(a, b, torch.arange(Bi * nt))
+        res["total_loss"].backward()
+        out2[str(dt)] = dict(losses={k: v.detach().clone() for k, v in res.items()}, da=a.grad.clone(), db=b.grad.clone())
+    torch.save(out2, os.path.join(HERE, "clipcount_b4_t3_d24.pt"))
+    print("clipcount", {k: (float(v), str(v.dtype)) for k, v in out2["torch.float32"]["losses"].items()})
+
+
 def adamspd_amp_case(ref_opt, name, sizes, steps, lr, wd, max_norm, seed, inf_steps=(5, 11)):
     """The reference's update sequence under AMP (finetune/finetuner.py:147-154): scaler.unscale_ -> clip_grad_norm_ ->
     scaler.step -> scaler.update, with the unmodified AdamSPD and torch's GradScaler on CPU.  Gradients are handed over
@@ -201,6 +230,9 @@ def main():
     torch.manual_seed(0)
     torch.set_num_threads(4)
     ref_losses, ref_opt = import_reference()
+    if "--only-count" in sys.argv:
+        count_cases(ref_losses)
+        return
     if "--only-adamspd-amp" in sys.argv:
         adamspd_amp_case(ref_opt, "s16", [(1,), (7,), (33, 31), (4099,), (64, 64), (8193,)], 16, 2e-5, 0.1, 0.2, seed=21)
         return
@@ -218,6 +250,7 @@ def main():
     clip_case(ref_losses, "b5_d40_t1", 5, 40, 1.0, seed=7)
     pairwise_case(ref_losses, "b12_d32", 12, 32, 4.0, seed=8)
     masked_pairwise_case(ref_losses, "b3_t20_d48", 3, 20, 48, 3.0, seed=12)
+    count_cases(ref_losses)
     sizes = [(1,), (7,), (33, 31), (4099,), (64, 64)]
     adamspd_case(ref_opt, "s20", sizes, 20, 2e-5, (0.9, 0.999), 1e-8, 0.1, False, seed=9)
     adamspd_case(ref_opt, "s12_ams_lr1e3", sizes, 12, 1e-3, (0.9, 0.98), 5e-6, 0.2, True, seed=10)

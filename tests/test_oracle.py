@@ -188,6 +188,38 @@ def test_adamspd_oracle_matches_reference(fname):
         assert took > 0          # the SPD branch (optimizers.py:148-150) was exercised
 
 
+def test_count_losses_oracle_matches_reference():
+    """CountLoss / CLIPCountLoss restatement vs reference outputs and autograd gradients (fp64: 1e-11)."""
+    f = load_golden("countloss_b6_c5_d32.pt")
+    x = f["inputs"]
+    ref = f["torch.float64"]
+    fw = lo.count_loss_forward(x["la"], x["lb"], x["ei"], x["ek"], x["cf"], f["T"], f["alpha"])
+    for k in ("clip_loss", "count_loss", "total_loss"):
+        assert abs(float(fw[k]) - float(ref["losses"][k])) < 1e-12
+    dla, dlb = lo.logits_ce_backward(x["la"], x["lb"], fw["_f1"])
+    dei, dek, dcf = lo.count_contrastive_backward(fw["_f2"], f["alpha"])
+    for got, key in ((dla, "la"), (dlb, "lb"), (dei, "ei"), (dek, "ek"), (dcf, "cf")):
+        assert rel_err(got, ref["grads"][key]) < 1e-11, key
+    f = load_golden("clipcount_b4_t3_d24.pt")
+    ref = f["torch.float64"]
+    fw = lo.clip_count_forward(f["img"], f["txt"], f["T"])
+    assert abs(float(fw["clip_loss"]) - float(ref["losses"]["clip_loss"])) < 1e-12
+    assert float(ref["losses"]["count_loss"]) == 0.0 and float(fw["count_loss"]) == 0.0
+    da, db = lo.clip_count_backward(fw, f["T"])
+    assert rel_err(da, ref["da"]) < 1e-11 and rel_err(db, ref["db"]) < 1e-11
+    # the positive-in-denominator variant is what CLIPCountLoss.count_loss computes per group (losses.py:78-86)
+    g = torch.Generator().manual_seed(3)
+    ei = torch.randn(3, 8, generator=g, dtype=torch.float64); ek = torch.randn(3, 8, generator=g, dtype=torch.float64)
+    cf = torch.randn(3, 4, 8, generator=g, dtype=torch.float64)
+    fw = lo.count_contrastive_forward(ei, ek, cf, 0.07, include_pos=True)
+    n = lambda t: t / t.norm(dim=-1, keepdim=True)
+    want = 0.0
+    for i in range(3):
+        pos = torch.dot(n(ei)[i], n(ek)[i]); neg = n(cf)[i] @ n(ei)[i]
+        num = torch.exp(pos / 0.07); want += -torch.log(num / (num + torch.exp(neg / 0.07).sum()))
+    assert abs(float(fw["loss"]) - float(want / 3)) < 1e-12
+
+
 def test_amp_step_oracle_matches_reference_sequence():
     """unscale_ -> clip_grad_norm_ -> scaler.step -> update (finetuner.py:150-153), restated, vs the fixture made with
     the reference AdamSPD and torch's GradScaler: bit-exact parameters, norms, scales, skipped steps."""
