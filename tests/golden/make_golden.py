@@ -158,6 +158,22 @@ def adamspd_case(ref_opt, name, sizes, steps, lr, betas, eps, wd, amsgrad, seed,
     print("adamspd", name, "steps", steps, "p[0][:3]", params[0].detach().flatten()[:3].tolist())
 
 
+def statedict_case(ref_opt):
+    """optimizer.state_dict() of the reference AdamSPD after 3 steps (checkpoint compatibility, finetuner.py:256-273)."""
+    g = torch.Generator().manual_seed(41)
+    sizes = [(5,), (3, 4)]
+    params = [torch.nn.Parameter(torch.randn(*s, generator=g)) for s in sizes]
+    pre = [p.detach().clone() + 0.01 for p in params]
+    opt = ref_opt.AdamSPD([{"params": params, "pre": pre}], lr=1e-3, weight_decay=0.1, amsgrad=True)
+    for _ in range(3):
+        for p in params:
+            p.grad = torch.randn(*p.shape, generator=g)
+        opt.step()
+    torch.save(dict(state_dict=opt.state_dict(), params=[p.detach().clone() for p in params], sizes=sizes),
+               os.path.join(HERE, "statedict_ref.pt"))
+    print("state_dict keys", sorted(opt.state_dict()["state"][0].keys()), sorted(opt.state_dict()["param_groups"][0].keys()))
+
+
 def count_cases(ref_losses):
     """CountLoss (losses.py:267-309) and CLIPCountLoss (:39-133) on seeded inputs, fp64 and fp32, autograd gradients."""
     g = torch.Generator().manual_seed(31)
@@ -230,6 +246,9 @@ def main():
     torch.manual_seed(0)
     torch.set_num_threads(4)
     ref_losses, ref_opt = import_reference()
+    if "--only-statedict" in sys.argv:
+        statedict_case(ref_opt)
+        return
     if "--only-count" in sys.argv:
         count_cases(ref_losses)
         return
@@ -251,6 +270,7 @@ def main():
     pairwise_case(ref_losses, "b12_d32", 12, 32, 4.0, seed=8)
     masked_pairwise_case(ref_losses, "b3_t20_d48", 3, 20, 48, 3.0, seed=12)
     count_cases(ref_losses)
+    statedict_case(ref_opt)
     sizes = [(1,), (7,), (33, 31), (4099,), (64, 64)]
     adamspd_case(ref_opt, "s20", sizes, 20, 2e-5, (0.9, 0.999), 1e-8, 0.1, False, seed=9)
     adamspd_case(ref_opt, "s12_ams_lr1e3", sizes, 12, 1e-3, (0.9, 0.98), 5e-6, 0.2, True, seed=10)

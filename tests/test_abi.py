@@ -57,6 +57,33 @@ def test_adamspd_constructor_errors_match_reference():
     assert opt.step(lambda: torch.tensor(3.0)) == 3.0
 
 
+def test_state_dict_is_interchangeable_with_the_reference():
+    """Checkpoint compatibility (finetuner.py:256-273 saves optimizer.state_dict()): a state_dict made
+    by the reference AdamSPD loads into this one and back, including group['pre'] and the unused 'hyper' state."""
+    from conftest import load_golden, reference_modules
+    from clip_finegrained_alignment_b200 import AdamSPD
+    f = load_golden("statedict_ref.pt")
+    sd = f["state_dict"]
+    params = [torch.nn.Parameter(x.clone()) for x in f["params"]]
+    opt = AdamSPD([{"params": params, "pre": [torch.zeros_like(p) for p in params]}], lr=5.0, amsgrad=False)
+    opt.load_state_dict(sd)
+    grp = opt.param_groups[0]
+    assert grp["lr"] == 1e-3 and grp["weight_decay"] == 0.1 and grp["amsgrad"] is True
+    assert len(grp["pre"]) == 2 and torch.equal(grp["pre"][0], sd["param_groups"][0]["pre"][0])
+    for j, p in enumerate(params):
+        st = opt.state[p]
+        assert st["step"] == 3 and isinstance(st["step"], int)
+        assert set(st.keys()) == {"step", "exp_avg", "exp_avg_sq", "hyper", "max_exp_avg_sq"}
+        assert torch.equal(st["exp_avg"], sd["state"][j]["exp_avg"])
+    out = opt.state_dict()
+    assert out["state"].keys() == sd["state"].keys() and out["param_groups"][0].keys() == sd["param_groups"][0].keys()
+    mods = reference_modules()
+    if mods is not None:                                  # and back into the unmodified reference optimizer
+        ref = mods[1].AdamSPD([{"params": params, "pre": None}], lr=1.0)
+        ref.load_state_dict(out)
+        assert ref.state[params[1]]["step"] == 3 and ref.param_groups[0]["amsgrad"] is True
+
+
 def test_no_cpu_fallback():
     from clip_finegrained_alignment_b200 import AdamSPD, CustomCLIPLoss, SPARCLoss, _lib
     import types
