@@ -23,13 +23,17 @@ __device__ __forceinline__ float block_sum(float x, float* red) {
 // One CTA: merge the per-split online-softmax partials -> lse[2][B], sums2 = (sum CE_a, sum CE_b) over the LOCAL rows.
 // If out8 != NULL (single process) it also performs the SPARC scalar epilogue (losses.py:163,196,217,252-264).
 static __device__ void global_combine_body(const float* part_m, const float* part_l,
-                                    const float* diag, int B, int nsplit, float* __restrict__ lse,
+                                    const float* diag, int B, int nsplit, float* lse,
                                     float* __restrict__ sums2, int global_batch, const float* __restrict__ local_partial,
                                     const uint8_t* __restrict__ mask, int T, float gw, float lw, float* __restrict__ out8,
                                     float* red /* shared [8] */) {
   float ce[2] = {0.f, 0.f};
   for (int idx = threadIdx.x; idx < 2 * B; idx += kNT) {
     const int dir = idx / B, i = idx - dir * B;
+    if (nsplit == 0) {                                // rows already merged by global_merge_rows_kernel: lse holds the result
+      ce[dir] += __ldcg(lse + idx) - __ldcg(diag + idx);
+      continue;
+    }
     float M = -CUDART_INF_F;
     for (int s = 0; s < nsplit; ++s) M = fmaxf(M, __ldcg(part_m + ((size_t)dir * nsplit + s) * B + i));
     float Lsum = 0.f;

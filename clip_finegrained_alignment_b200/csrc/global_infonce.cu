@@ -100,6 +100,42 @@ global_combine_kernel(const float* __restrict__ part_m, const float* __restrict_
   global_combine_body(part_m, part_l, diag, B, nsplit, lse, sums2, global_batch, local_partial, mask, T, gw, lw, out8, red);
 }
 
+// Many column splits (gathered problems: Bg / 128 tiles per row): merge the online-softmax partials with one thread per
+// (direction, row) over a whole grid first; the single-CTA kernel then only sums 2B cross-entropies (nsplit = 0).
+// block = 32 rows x 8 split groups: loads are coalesced along the rows, every thread merges nsplit / 8 partials and the
+// 8 group results of a row are merged through shared memory in a fixed order.
+__global__ void __launch_bounds__(256)
+global_merge_rows_kernel(const float* __restrict__ part_m, const float* __restrict__ part_l, int B, int nsplit,
+                         float* __restrict__ lse) {
+  __shared__ float sm[8][32], sl[8][32];
+  const int tx = threadIdx.x & 31, sg = threadIdx.x >> 5;
+  const int idx = blockIdx.x * 32 + tx;
+  float M = -CUDART_INF_F, Lq = 0.f;
+  if (idx < 2 * B) {
+    const int dir = idx / B, i = idx - dir * B;
+    const float* pm = part_m + (size_t)dir * nsplit * B + i;
+    const float* pl = part_l + (size_t)dir * nsplit * B + i;
+    for (int s = sg; s < nsplit; s += 8) {
+      const float m = pm[(size_t)s * B], l = pl[(size_t)s * B];
+      if (m == -CUDART_INF_F) continue;
+      const float nm = fmaxf(M, m);
+      Lq = Lq * ((M == -CUDART_INF_F) ? 0.f : expf(M - nm)) + l * expf(m - nm);
+      M = nm;
+    }
+  }
+  sm[sg][tx] = M; sl[sg][tx] = Lq;
+  __syncthreads();
+  if (sg == 0 && idx < 2 * B) {
+    float Mx = -CUDART_INF_F;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) Mx = fmaxf(Mx, sm[k][tx]);
+    float L = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) if (sm[k][tx] != -CUDART_INF_F) L += sl[k][tx] * expf(sm[k][tx] - Mx);
+    lse[idx] = Mx + logf(L);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // backward: per 32 x 32 logits tile recompute S (with on-the-fly norms), form
 //   dS_ij = c_self exp(S_ij - lse_self[i]) + c_other exp(S_ij - lse_other[j]) - (c_self + c_other) [j == off + i]
@@ -302,6 +338,10 @@ int cfa::global_infonce_fwd_peers(const float* a_loc, const float* b_loc, const 
     const int rc = global_tc_fwd(a_loc, b_loc, a_all, b_all, B, Bg, D, col_offset, scale, eps, norms2, &pm, &pl, &dg, &nsp,
                                  workspace, gathered_ranks, peers, (cudaStream_t)stream);
     if (rc != CFA_OK) return rc;
+    if (nsp > 8) {
+      global_merge_rows_kernel<<<(2 * B + 31) / 32, 256, 0, (cudaStream_t)stream>>>(pm, pl, B, nsp, lse2);
+      nsp = 0;
+    }
     global_combine_kernel<<<1, kNT, 0, (cudaStream_t)stream>>>(pm, pl, dg, B, nsp, lse2, sums2, Bg, local_partial, mask, T, gw,
                                                                lw, out8);
     return launch_status();

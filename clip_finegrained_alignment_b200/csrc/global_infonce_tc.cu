@@ -6,7 +6,8 @@
 //                  the B x Bg logits never reach memory (losses.py:160-162, :21-28)
 //   backward     : recompute the tile, dS = c_self softmax_row + c_other softmax_col - (c_self + c_other) I as bf16 hi/lo
 //                  in shared memory (A operand), then dA_hat[128 x D] += dS . B_hat (B tiles read MN-major) in TMEM
-// Warp roles as in sparc_tc.cu: warp 0 TMA, warp 1 MMA issue (warp-uniform, elected lane), warps 2-5 epilogue.
+// Warp roles as in sparc_tc_fwd2.cu: warp 0 TMA, warp 1 MMA issue (warp-uniform, elected lane), warps 2-9 epilogue
+// (two per TMEM lane quarter, each owning half of the tile columns: the epilogues are latency-bound, not throughput-bound).
 #include "tc_common.cuh"
 #include <math_constants.h>
 
@@ -14,7 +15,7 @@ namespace cfa {
 using namespace tc;
 typedef __nv_bfloat16 bf16;
 
-constexpr int kGtThreads = 192;
+constexpr int kGtThreads = 320;          // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue: 2 per TMEM lane quarter, half the columns each
 constexpr int kGtM = 128, kGtN = 128;
 constexpr uint32_t kGtTileA = kGtM * 128, kGtTileB = kGtN * 128;                 // one 64-wide bf16 block of a tile
 constexpr uint32_t kGtStage = 2 * kGtTileA + 2 * kGtTileB;                       // A_hi A_lo B_hi B_lo = 64 KB
@@ -35,18 +36,29 @@ gt_split_kernel(const float* __restrict__ a, const float* __restrict__ b, int ro
   // into this, its only consumer)
   const float* x = peers.n ? peers.base[r / rank_rows] + ((size_t)which * rank_rows + (size_t)(r % rank_rows)) * D
                            : (which ? b : a) + (size_t)(r / rank_rows) * rank_stride + (size_t)(r % rank_rows) * D;
+  // the row is read ONCE (it may live in a peer's HBM): D <= 1024 -> up to 32 values per lane stay in registers
+  float xr[32];
   float ss = 0.f;
-  for (int d = lane; d < D; d += 32) ss = fmaf(x[d], x[d], ss);
+#pragma unroll
+  for (int k = 0; k < 32; ++k) {
+    const int d = lane + 32 * k;
+    xr[k] = d < D ? x[d] : 0.f;
+    ss = fmaf(xr[k], xr[k], ss);
+  }
   ss = warp_sum(ss);
   const float n = fmaxf(sqrtf(ss), eps);
   if (norms && lane == 0) norms[(size_t)which * rows + r] = n;
   bf16* hi = out + ((size_t)(2 * which) * rows + r) * D;
   bf16* lo = out + ((size_t)(2 * which + 1) * rows + r) * D;
-  for (int d = lane; d < D; d += 32) {
-    const float y = x[d] / n;
-    const bf16 h = __float2bfloat16_rn(y);
-    hi[d] = h;
-    lo[d] = __float2bfloat16_rn(y - __bfloat162float(h));
+#pragma unroll
+  for (int k = 0; k < 32; ++k) {
+    const int d = lane + 32 * k;
+    if (d < D) {
+      const float y = xr[k] / n;
+      const bf16 h = __float2bfloat16_rn(y);
+      hi[d] = h;
+      lo[d] = __float2bfloat16_rn(y - __bfloat162float(h));
+    }
   }
 }
 
@@ -57,11 +69,12 @@ struct GtParams {
   float* part_m; float* part_l; float* diag;
   // backward
   const float* lse_loc; const float* lse_all; const float* coef; float* dpart;
+  int dpart_atomic;                     // != 0: dpart is ONE zeroed [2][B][D] accumulator, column tiles add into it (red.global)
   int lse_rank_rows, lse_rank_stride;   // > 0: lse_all is the raw all-gather of per-rank [lse_a | lse_b | 2 sums] packs
-  volatile int* dbg;      // optional host-mapped progress markers (cfa_debug_set_marker_buffer), [cta][8 warps]
+  volatile int* dbg;      // optional host-mapped progress markers (cfa_debug_set_marker_buffer), [cta][16 warps]
 };
 static int* g_gt_dbg = nullptr;
-#define GT_MARK(v) do { if (p.dbg && lane == 0) { p.dbg[((((blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 8 + warp) * 32) + (v)] = (int)(clock64() - gt_t0); } } while (0)
+#define GT_MARK(v) do { if (p.dbg && lane == 0) { p.dbg[((((blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 16 + warp) * 32) + (v)] = (int)(clock64() - gt_t0); } } while (0)
 
 
 struct GtSmem {
@@ -133,12 +146,12 @@ gt_fwd_kernel(const __grid_constant__ CUtensorMap tmLoc, const __grid_constant__
   const uint32_t tmem = *tmem_slot;
   gt_issue_logits(warp, lane, stages, full, empty, s_full, tmem, &tmLoc, &tmAll, row0, col0, dir ? 2 : 0, dir ? 0 : 2, p.D / 64);
   if (warp >= 2) {
-    const int q = warp & 3, row = 32 * q + lane, grow = row0 + row;
+    const int q = warp & 3, h = (warp - 2) >> 2, row = 32 * q + lane, grow = row0 + row;
     const uint32_t trow = tmem + ((uint32_t)(32 * q) << 16);
     mbar_wait(s_full, 0);
     tc_fence_after();
     float m = -CUDART_INF_F, l = 0.f;
-    for (int c0 = 0; c0 < kGtN; c0 += 32) {
+    for (int c0 = 64 * h; c0 < 64 * h + 64; c0 += 32) {
       float x[32];
       tmem_ld32(trow + c0, x);
       tmem_ld_wait();
@@ -157,9 +170,9 @@ gt_fwd_kernel(const __grid_constant__ CUtensorMap tmLoc, const __grid_constant__
       l = l * ((m == -CUDART_INF_F) ? 0.f : __expf(m - nm)) + s;
       m = nm;
     }
-    if (grow < p.B) {
-      p.part_m[((size_t)dir * nct + ct) * p.B + grow] = m;
-      p.part_l[((size_t)dir * nct + ct) * p.B + grow] = l;
+    if (grow < p.B) {                                  // one online-softmax partial per (column tile, half)
+      p.part_m[((size_t)dir * 2 * nct + 2 * ct + h) * p.B + grow] = m;
+      p.part_l[((size_t)dir * 2 * nct + 2 * ct + h) * p.B + grow] = l;
     }
     tc_fence_before();
   }
@@ -207,7 +220,7 @@ gt_bwd_kernel(const __grid_constant__ CUtensorMap tmLoc, const __grid_constant__
   const int ra = dir ? 2 : 0, ca = dir ? 0 : 2;
   if (threadIdx.x == 0) {
     for (int i = 0; i < 2; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, 1); mbar_init(ofull + i, 1); mbar_init(oempty + i, 1); }
-    mbar_init(s_full, 1); mbar_init(ds_ready, 4); mbar_init(o_done, 1);
+    mbar_init(s_full, 1); mbar_init(ds_ready, 8); mbar_init(o_done, 1);
     fence_barrier_init();
     tma_prefetch_desc(&tmLoc); tma_prefetch_desc(&tmAll);
   }
@@ -267,37 +280,38 @@ gt_bwd_kernel(const __grid_constant__ CUtensorMap tmLoc, const __grid_constant__
     umma_commit_w(leader, o_done);
     GT_MARK(6);
   } else {
-    const int q = warp & 3, row = 32 * q + lane, grow = row0 + row;
+    const int q = warp & 3, h = (warp - 2) >> 2, row = 32 * q + lane, grow = row0 + row;
     const uint32_t trow = tmem + ((uint32_t)(32 * q) << 16);
     const float c_self = p.coef[dir], c_other = p.coef[1 - dir];
     const float lse_self = (grow < p.B) ? p.lse_loc[(size_t)dir * p.B + grow] : 0.f;
     const float* lse_other = p.lse_all + (p.lse_rank_rows ? (size_t)(1 - dir) * p.lse_rank_rows : (size_t)(1 - dir) * p.Bg);
-    {
+    if (h == 0) {
       // one coalesced load per thread now (overlaps phase A) instead of 128 dependent global loads inside the dS loop
       const int gcol = col0 + row;
       const int gidx = p.lse_rank_rows ? (gcol / p.lse_rank_rows) * p.lse_rank_stride + gcol % p.lse_rank_rows : gcol;
       lse_s[row] = (gcol < p.Bg) ? __ldg(lse_other + gidx) : 0.f;
     }
-    // ---- phase B: dS (hi/lo) -> smem (A operand, K = 128 columns of this tile)
+    // ---- phase B: dS (hi/lo) -> smem (A operand, K = 128 columns of this tile); this warp owns columns [64 h, 64 h + 64)
     mbar_wait(s_full, 0);
     tc_fence_after();
     GT_MARK(10);
-    float xs[kGtN / 32][32];
+    float xs[2][32];
 #pragma unroll
-    for (int c = 0; c < kGtN / 32; ++c) tmem_ld32(trow + 32 * c, xs[c]);
+    for (int c = 0; c < 2; ++c) tmem_ld32(trow + 64 * h + 32 * c, xs[c]);
     tmem_ld_wait();
     tc_fence_before();
     GT_MARK(11);
-    asm volatile("bar.sync 1, 128;" ::: "memory");      // every epilogue warp has its logits in registers: stages may be reused
+    asm volatile("bar.sync 1, 256;" ::: "memory");      // every epilogue warp has its logits in registers: stages may be reused
     GT_MARK(12);
 #pragma unroll
-    for (int c = 0; c < kGtN / 32; ++c) {
+    for (int c = 0; c < 2; ++c) {
+      const int cb = 64 * h + 32 * c;
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
-        const int gcol = col0 + 32 * c + j;
+        const int gcol = col0 + cb + j;
         const bool on = grow < p.B && gcol < p.Bg;
         const float s = xs[c][j] * p.scale;
-        const float lo_ = lse_s[32 * c + j];
+        const float lo_ = lse_s[cb + j];
         float g = c_self * __expf(fminf(s - lse_self, 0.f)) + c_other * __expf(fminf(s - lo_, 0.f));
         g -= (gcol == p.col_offset + grow) ? (c_self + c_other) : 0.f;
         xs[c][j] = on ? g : 0.f;
@@ -306,7 +320,7 @@ gt_bwd_kernel(const __grid_constant__ CUtensorMap tmLoc, const __grid_constant__
       for (int g8 = 0; g8 < 4; ++g8) {
         uint4 hi, lo;
         gt_split8(&xs[c][8 * g8], hi, lo);
-        const uint32_t off = il_offset(kGtM, row, 32 * c + 8 * g8);
+        const uint32_t off = il_offset(kGtM, row, cb + 8 * g8);
         *reinterpret_cast<uint4*>(dShi + off) = hi;
         *reinterpret_cast<uint4*>(dSlo + off) = lo;
       }
@@ -315,7 +329,7 @@ gt_bwd_kernel(const __grid_constant__ CUtensorMap tmLoc, const __grid_constant__
     __syncwarp();
     if (lane == 0) mbar_arrive(ds_ready);
     GT_MARK(13);
-    // ---- phase C epilogue: dA_hat partial (this column tile's contribution) -> global
+    // ---- phase C epilogue: dA_hat partial (this column tile's contribution) -> global; this warp owns half of the D blocks
     mbar_wait(o_done, 0);
     tc_fence_after();
     GT_MARK(14);
@@ -324,7 +338,7 @@ gt_bwd_kernel(const __grid_constant__ CUtensorMap tmLoc, const __grid_constant__
     // segment (lane = column) instead of 32 scattered ones (lane = row).  tcgen05.ld is warp-collective: all lanes load.
     float* tile = reinterpret_cast<float*>(ostg) + (warp - 2) * (32 * 36);       // phase-C operand stages are dead now
     const int rr = lane >> 3, c4 = (lane & 7) * 4;
-    for (int c0 = 0; c0 < dcols; c0 += 32) {
+    for (int c0 = 32 * h; c0 < dcols; c0 += 64) {
       float x[32];
       tmem_ld32(trow + c0, x);
       tmem_ld_wait();
@@ -336,7 +350,17 @@ gt_bwd_kernel(const __grid_constant__ CUtensorMap tmLoc, const __grid_constant__
       for (int it = 0; it < 8; ++it) {                   // one instruction = 4 rows x 128 contiguous bytes
         const int r = it * 4 + rr, gr = row0 + 32 * q + r;
         const float4 v4 = *reinterpret_cast<const float4*>(tile + r * 36 + c4);
-        if (gr < p.B) *reinterpret_cast<float4*>(p.dpart + (((size_t)dir * nct + ct) * p.B + gr) * D + c0 + c4) = v4;
+        if (gr < p.B) {
+          if (p.dpart_atomic) {
+            // many column tiles (gathered problems): 64 per-tile partials of [B][D] would be 268 MB written and re-read at
+            // B = 1024, Bg = 8192 — accumulate in one L2-resident buffer instead (fp32 reductions, order not fixed)
+            float* dst = p.dpart + ((size_t)dir * p.B + gr) * D + c0 + c4;
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(v4.x), "f"(v4.y), "f"(v4.z), "f"(v4.w)
+                         : "memory");
+          } else {
+            *reinterpret_cast<float4*>(p.dpart + (((size_t)dir * nct + ct) * p.B + gr) * D + c0 + c4) = v4;
+          }
+        }
       }
       __syncwarp();
     }
@@ -356,7 +380,7 @@ bool global_tc_supported(int B, int Bg, int D) { return D % 64 == 0 && D >= 64 &
 size_t global_tc_workspace_bytes(int B, int Bg, int D) {
   const int nct = (Bg + kGtN - 1) / kGtN;
   const size_t split = (size_t)4 * Bg * D * sizeof(bf16) + (size_t)4 * B * D * sizeof(bf16);   // all + local, hi/lo x a/b
-  const size_t fwd = ((size_t)4 * nct * B + 2 * (size_t)B) * sizeof(float);
+  const size_t fwd = ((size_t)8 * nct * B + 2 * (size_t)B) * sizeof(float);      // 2 partials per column tile (one per half)
   const size_t bwd = (size_t)2 * nct * B * D * sizeof(float);
   return ((split + 255) & ~(size_t)255) + (fwd > bwd ? fwd : bwd);
 }
@@ -400,12 +424,12 @@ int global_tc_fwd(const float* a_loc, const float* b_loc, const float* a_all, co
   if (rc != CFA_OK) return rc;
   GtParams p{};
   p.B = B; p.Bg = Bg; p.D = D; p.col_offset = col_offset; p.scale = scale;
-  p.part_m = h.scratch; p.part_l = p.part_m + (size_t)2 * h.nct * B; p.diag = p.part_l + (size_t)2 * h.nct * B;
+  p.part_m = h.scratch; p.part_l = p.part_m + (size_t)4 * h.nct * B; p.diag = p.part_l + (size_t)4 * h.nct * B;
   const size_t smem = kGtStages * kGtStage + 1024 + 1024;
   static bool attr = false;
   if (!attr) { CFA_CUDA_TRY(cudaFuncSetAttribute(gt_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
   gt_fwd_kernel<<<dim3((B + kGtM - 1) / kGtM, h.nct, 2), kGtThreads, smem, st>>>(tmLoc, tmAll, p);
-  *part_m = p.part_m; *part_l = p.part_l; *diag = p.diag; *nsplit = h.nct;
+  *part_m = p.part_m; *part_l = p.part_l; *diag = p.diag; *nsplit = 2 * h.nct;
   return launch_status();
 }
 
@@ -419,12 +443,14 @@ int global_tc_bwd(int B, int Bg, int D, int col_offset, float scale, const float
   GtParams p{};
   p.B = B; p.Bg = Bg; p.D = D; p.col_offset = col_offset; p.scale = scale;
   p.lse_loc = lse_loc2; p.lse_all = lse_all2; p.coef = coef2; p.dpart = h.scratch; p.dbg = g_gt_dbg;
+  p.dpart_atomic = h.nct > 2;
+  if (p.dpart_atomic) CFA_CUDA_TRY(cudaMemsetAsync(h.scratch, 0, (size_t)2 * B * D * sizeof(float), st));
   p.lse_rank_rows = gathered_ranks > 1 ? B : 0; p.lse_rank_stride = gathered_ranks > 1 ? 2 * B + 2 : 0;
   const size_t smem = kGtStages * kGtStage + 1024 + 1024;
   static bool attr = false;
   if (!attr) { CFA_CUDA_TRY(cudaFuncSetAttribute(gt_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
   gt_bwd_kernel<<<dim3((B + kGtM - 1) / kGtM, h.nct, 2), kGtThreads, smem, st>>>(tmLoc, tmAll, p);
-  *dpart = h.scratch; *nsplit = h.nct;
+  *dpart = h.scratch; *nsplit = p.dpart_atomic ? 1 : h.nct;
   return launch_status();
 }
 

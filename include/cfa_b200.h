@@ -295,7 +295,7 @@ int cfa_sparc_coef_ptrs(const float* g_global, const float* g_local, const float
 /* tuning aid: device buffer [B][32] int64 receiving clock64 phase stamps of the tensor-core backward (NULL = off) */
 int cfa_debug_set_profile_buffer(void* device_buffer);
 int cfa_debug_set_profile_buffer_fwd(void* device_buffer);   /* same for the tensor-core forward */
-/* debugging aid: host-mapped (pinned) int32 buffer [cta][8 warps] receiving progress markers of the tensor-core
+/* debugging aid: host-mapped (pinned) int32 buffer [cta][16 warps] receiving progress markers of the tensor-core
  * global InfoNCE backward, readable from the host while a kernel is stuck (NULL = off) */
 int cfa_debug_set_marker_buffer(void* mapped_buffer);
 int cfa_tc_selftest(int a_mode, int b_mode, int N, int K, const void* A, const void* B, float* D, void* stream);
