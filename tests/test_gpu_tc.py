@@ -186,7 +186,9 @@ def test_sparc_tc_bitwise_deterministic():
 # ----------------------------------------------------------------------------------------------
 # tensor-core global InfoNCE (tcgen05 logits tiles, bf16 hi/lo-split normalised operands)
 # ----------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("N,B,D,s", [(1, 256, 512, 1.0), (1, 100, 64, 14.285), (3, 70, 256, 5.0), (4, 128, 512, 2.0)])
+# (19, 128, 64): 19 column tiles per row -> 38 softmax partials (> 32: global_merge_rows_kernel) and the red.global dA path
+@pytest.mark.parametrize("N,B,D,s", [(1, 256, 512, 1.0), (1, 100, 64, 14.285), (3, 70, 256, 5.0), (4, 128, 512, 2.0),
+                                     (19, 128, 64, 3.0)])
 def test_global_infonce_tc_emulated_ranks(N, B, D, s):
     """path=2 (tensor cores) through the C ABI: N emulated ranks of B rows against N*B gathered columns, both
     directions, forward (lse, CE sums) and backward, vs the fp64 oracle on the concatenated batch."""
