@@ -469,12 +469,12 @@ def main():
                    "kernel_ms": {k: round(statistics.mean(a.elapsed_time(b) for a, b in ev), 4) for k, ev in kev.items() if ev}},
         "roofline": {"bound": "tensor", "kernel": "cfa_sparc_bwd", "achieved": round(ach, 2), "peak": pk["tf_sus"],
                      "unit": "TFLOP/s", "frac": round(ach / pk["tf_sus"], 5),
-                     "traffic": 187.6e6 if (B == 256 and args.dtype == "bf16") else None,
-                     "traffic_source": "profiles/r1h_ncu_full_summary.csv (sparc_bwd2_kernel): dram read 141.2 MB + write 46.4 MB "
+                     "traffic": 183.6e6 if (B == 256 and args.dtype == "bf16") else None,
+                     "traffic_source": "profiles/r1i_ncu_full_summary.csv (sparc_bwd2_kernel): dram read 140.1 MB + write 43.5 MB "
                                        "per launch; algorithmic 206 MB = v,l 71.6 + saved G hi|lo 40.4 + Q 16.4 + T x T logits 6.1 "
                                        "read, dv,dl 71.6 written (part of dv/dl is still in L2 at kernel end; the second read "
                                        "of v,l hits L2)",
-                     "share_of_device_time": "profiles/r1h_launches.csv: sparc_bwd2 44.9 %, sparc_fwd2 33.6 %, global InfoNCE 20.5 %",
+                     "share_of_device_time": "profiles/r1i_launches.csv: sparc_bwd2 46.9 %, sparc_fwd2 31.1 %, global InfoNCE 22.0 %",
                      "peak_source": pk["src"] + ", sustained bf16 GEMM", "algorithmic_flops_per_launch": bwd_flops},
         "e2e": {"value": round(e2e_val, 1), "unit": UNIT,
                 "h2d_bytes_per_step": int(hv.numel() * hv.element_size() + hl.numel() * hl.element_size() + hm.numel()),
