@@ -310,11 +310,16 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=256, help="pairs per GPU (BASELINE config 2: 256)")
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "f32", "f16"])
+    ap.add_argument("--patches", type=int, default=196, help="vision tokens P (BASELINE config 4: 576)")
+    ap.add_argument("--dim", type=int, default=512, help="projection dim D (BASELINE config 4: 768)")
     ap.add_argument("--collective", default="peer", choices=["peer", "nccl"],
                     help="N > 1: exchange of the gathered global InfoNCE (peer memory over NVLink, or NCCL all-gathers)")
+    ap.add_argument("--cast-to-bf16", action="store_true", help="SPARCLoss(cast_to_bf16=True): fp16 / fp32 inputs on the tensor-core path")
     ap.add_argument("--no-adamspd", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    global P, D
+    P, D = args.patches, args.dim
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -342,7 +347,8 @@ def main():
     vs = [torch.randn(B, P, D, device=dev).to(dt).requires_grad_(True) for _ in range(nbuf)]
     ls = [torch.randn(B, T, D, device=dev).to(dt).requires_grad_(True) for _ in range(nbuf)]
     mask = torch.ones(B, T, dtype=torch.bool, device=dev)
-    crit = SPARCLoss(cfg(1.0 / P), gather=(True if args.collective == "peer" else "nccl") if world > 1 else False)
+    crit = SPARCLoss(cfg(1.0 / P), gather=(True if args.collective == "peer" else "nccl") if world > 1 else False,
+                     cast_to_bf16=args.cast_to_bf16)
 
     def step(i):
         v, l = vs[i % nbuf], ls[i % nbuf]
@@ -374,7 +380,7 @@ def main():
     # per-ABI-call device times: a separate short pass with CUDA events around every call (kept out of the timed region:
     # the extra event records cost host time)
     _lib.kernel_events = {name: [] for name in _lib.LAUNCHES if name != "cfa_adamspd_step"}
-    crit_stages = SPARCLoss(cfg(1.0 / P), gather=world > 1, fused_calls=False)      # same kernels, one call per stage
+    crit_stages = SPARCLoss(cfg(1.0 / P), gather=world > 1, fused_calls=False, cast_to_bf16=args.cast_to_bf16)      # same kernels, one call per stage
     for i in range(min(10, args.steps)):
         v, l = vs[i % nbuf], ls[i % nbuf]
         v.grad = None; l.grad = None
@@ -461,7 +467,8 @@ def main():
         "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": round(ms_step, 4), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
-        "config": {"workload": f"BASELINE config 2: ViT-B/16 SPARC + global InfoNCE fwd+bwd, B={B}/GPU, P={P}, T={T}, "
+        "config": {"workload": f"BASELINE config {2 if (P, D) == (196, 512) else ('4' if (P, D) == (576, 768) else 'shapes')}: "
+                               f"{'ViT-L/14@336' if P == 576 else 'ViT-B/16'} SPARC + global InfoNCE fwd+bwd, B={B}/GPU, P={P}, T={T}, "
                                f"D={D}, thr=1/P, s=1, all-True mask" + (", all-gathered global InfoNCE" if world > 1 else ""),
                    "global_batch": Bg, "collective": collective, "l2": f"inputs rotated over {nbuf} sets ({nbuf * in_bytes >> 20} MiB > 2x L2)",
                    "algorithmic_flops_per_pair": flops_per_pair(Bg),

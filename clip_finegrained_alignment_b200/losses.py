@@ -364,8 +364,14 @@ class SPARCLoss(nn.Module):
     """SPARC loss (https://arxiv.org/abs/2401.09865), reference API: finetune/losses.py:136-264."""
 
     def __init__(self, config, gather=False, process_group=None, kernel_path: str = "auto",
-                 fused_calls: bool = True):
+                 fused_calls: bool = True, cast_to_bf16: bool = False):
         super().__init__()
+        # cast_to_bf16 (opt-in): fp16 embeddings — what torch.autocast() hands the loss by default (finetuner.py:120) — and
+        # fp32 embeddings (use_amp off, finetuner.py:156) are rounded to bf16 on entry so that the tcgen05 kernels run
+        # (measured 17x faster at config 2 than the fp32-exact CUDA-core path those dtypes are otherwise routed to);
+        # gradients come back in the caller's dtype.  This changes the inputs by up to 2^-9 relative (exactly what
+        # autocast(dtype=torch.bfloat16) would have produced), so it is NOT within the parity bar and stays off by default.
+        self.cast_to_bf16 = cast_to_bf16
         # gather: False = rank-local global loss (the reference under DDP); True = all-gathered over peer memory when the
         # ranks share an NVLink box and the shape allows, else over NCCL; "nccl" = always the NCCL all-gather path
         # fused_calls: rank-local loss through one library call per direction (cfa_sparc_loss_fwd / _bwd); False keeps
@@ -396,6 +402,10 @@ class SPARCLoss(nn.Module):
         if language_mask.dtype not in (torch.bool, torch.uint8, torch.int8, torch.int16, torch.int32, torch.int64):
             # the reference fails in `~language_mask` for float masks (SURVEY §8b errors)
             raise TypeError(f"language_mask must be bool or integer, got {language_mask.dtype}")
+        if self.cast_to_bf16 and v_patch_embed.dtype in (torch.float16, torch.float32) \
+                and l_token_embed.dtype == v_patch_embed.dtype:
+            v_patch_embed = v_patch_embed.to(torch.bfloat16)       # autograd casts the bf16 gradients back
+            l_token_embed = l_token_embed.to(torch.bfloat16)
         out = _SparcFunction.apply(v_patch_embed, l_token_embed, language_mask, float(self.similarity_threshold),
                                    float(self.global_loss_weight), float(self.local_loss_weight),
                                    float(self.inverse_temperature), self.gather, self.process_group, self.kernel_path,

@@ -292,3 +292,24 @@ def test_clip_loss_bf16_uses_tensor_cores():
     assert abs(float(out["clip_loss"]) - float(o["clip_loss"])) <= 1e-4 * float(o["clip_loss"])
     assert rel_err(a.grad.float(), da) <= 1e-3 + 2.0 ** -8
     assert rel_err(b.grad.float(), db) <= 1e-3 + 2.0 ** -8
+
+
+def test_sparc_cast_to_bf16_opt_in():
+    """cast_to_bf16=True: fp16 (or fp32) inputs are rounded to bf16 and take the tensor-core kernels; the result equals the bf16
+    path on the rounded inputs exactly, and gradients come back in fp16."""
+    from clip_finegrained_alignment_b200 import SPARCLoss
+    g = torch.Generator().manual_seed(9)
+    B, P, T, D = 3, 50, 77, 256
+    v16 = torch.randn(B, P, D, generator=g).half().cuda()
+    l16 = torch.randn(B, T, D, generator=g).half().cuda()
+    m = torch.ones(B, T, dtype=torch.bool, device="cuda")
+    c = _cfg(1.0 / P)
+    va = v16.clone().requires_grad_(True); la = l16.clone().requires_grad_(True)
+    oa = SPARCLoss(c, cast_to_bf16=True)(va, la, m)
+    oa["total_loss"].backward()
+    vb = v16.to(torch.bfloat16).requires_grad_(True); lb = l16.to(torch.bfloat16).requires_grad_(True)
+    ob = SPARCLoss(c)(vb, lb, m)
+    ob["total_loss"].backward()
+    assert va.grad.dtype == torch.float16 and la.grad.dtype == torch.float16
+    assert float(oa["total_loss"]) == float(ob["total_loss"])
+    assert torch.equal(va.grad.float(), vb.grad.float().half().float()) and torch.equal(la.grad.float(), lb.grad.float().half().float())
