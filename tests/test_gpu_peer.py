@@ -66,14 +66,14 @@ def test_peer_sync_push_barrier_pull():
         ex.close()
 
 
-def _load_kernels(B, P, T, D, N):
+def _load_kernels(B, P, T, D, N, dtype=torch.bfloat16):
     """CUDA loads kernels lazily, and loading one synchronises the context: with all 'ranks' in ONE process that would
     wait for a barrier kernel that is itself waiting for the rank whose launch is being loaded.  (Across processes the
     peers keep running, so there is no such dependency.)  Run every kernel of the gathered path once, rank-locally."""
     from clip_finegrained_alignment_b200 import SPARCLoss, _lib
     L = _lib.lib
-    v = torch.randn(B, P, D, device="cuda").to(torch.bfloat16).requires_grad_(True)
-    l = torch.randn(B, T, D, device="cuda").to(torch.bfloat16).requires_grad_(True)
+    v = torch.randn(B, P, D, device="cuda").to(dtype).requires_grad_(True)
+    l = torch.randn(B, T, D, device="cuda").to(dtype).requires_grad_(True)
     m = torch.ones(B, T, dtype=torch.bool, device="cuda")
     cfg = types.SimpleNamespace(similarity_threshold=1.0 / P, global_loss_weight=1.0, local_loss_weight=1.0,
                                 inverse_temperature=1.0)
@@ -96,11 +96,11 @@ def _load_kernels(B, P, T, D, N):
     torch.cuda.synchronize()
 
 
-def _gathered_oracle(vs, ls, mask, thr, s):
+def _gathered_oracle(vs, ls, mask, thr, s, semantics="reference"):
     """fp64 oracle of N ranks' total_loss (gw = lw = 1) and of d total_r / d (v_r, l_r) with all-gather-with-grad
     semantics for the global InfoNCE (gradient of the GLOBAL mean loss w.r.t. the local rows)."""
     N, B, P = len(vs), vs[0].shape[0], vs[0].shape[1]
-    fw = [lo.sparc_forward(v.double(), l.double(), mask, thr, 0.0, 1.0, s) for v, l in zip(vs, ls)]
+    fw = [lo.sparc_forward(v.double(), l.double(), mask, thr, 0.0, 1.0, s, mask_semantics=semantics) for v, l in zip(vs, ls)]
     grads = [lo.sparc_backward(f) for f in fw]                                   # fine-grained part only (gw = 0)
     a = torch.cat([f["_cache"]["vbar_raw"] for f in fw])                         # pooled image rows of all ranks
     b = torch.cat([f["_cache"]["lbar_raw"] for f in fw])
@@ -120,21 +120,31 @@ def _gathered_oracle(vs, ls, mask, thr, s):
     return out
 
 
-@pytest.mark.parametrize("N,B,P,T,D,s", [(2, 64, 50, 20, 256, 1.0), (4, 24, 196, 77, 512, 2.0), (3, 130, 33, 20, 256, 1.0)])
-def test_gathered_sparc_loss_peer_memory_emulated_ranks(N, B, P, T, D, s):
+# last two cases: padded masks ("truncate" semantics) and fp16 embeddings (fine-grained part on the fp32-exact
+# CUDA-core kernels, global part on the tensor cores)
+@pytest.mark.parametrize("N,B,P,T,D,s,dtype,padded", [(2, 64, 50, 20, 256, 1.0, torch.bfloat16, False),
+                                                      (4, 24, 196, 77, 512, 2.0, torch.bfloat16, False),
+                                                      (3, 130, 33, 20, 256, 1.0, torch.bfloat16, False),
+                                                      (2, 40, 50, 20, 256, 1.0, torch.bfloat16, True),
+                                                      (2, 24, 50, 20, 128, 1.0, torch.float16, False)])
+def test_gathered_sparc_loss_peer_memory_emulated_ranks(N, B, P, T, D, s, dtype, padded):
     from clip_finegrained_alignment_b200 import _lib
     L = _lib.lib
     g = torch.Generator().manual_seed(1000 * N + B)
-    vs = [torch.randn(B, P, D, generator=g).to(torch.bfloat16) for _ in range(N)]
-    ls = [torch.randn(B, T, D, generator=g).to(torch.bfloat16) for _ in range(N)]
+    vs = [torch.randn(B, P, D, generator=g).to(dtype) for _ in range(N)]
+    ls = [torch.randn(B, T, D, generator=g).to(dtype) for _ in range(N)]
     mask = torch.ones(B, T, dtype=torch.bool)
+    if padded:
+        for b in range(0, B, 3):
+            mask[b, T - 1 - (b % 5):] = False
     thr = float(torch.tensor(1.0 / P, dtype=torch.float32))
-    ref = _gathered_oracle([v.float() for v in vs], [l.float() for l in ls], mask, thr, s)
+    ref = _gathered_oracle([v.float() for v in vs], [l.float() for l in ls], mask, thr, s,
+                           "truncate" if padded else "reference")
 
-    _load_kernels(B, P, T, D, N)
+    _load_kernels(B, P, T, D, N, dtype)
     ex = _LocalExchange(N, B, D)
     try:
-        code = _lib.DTYPE_CODE[torch.bfloat16]
+        code = _lib.DTYPE_CODE[dtype]
         nbytes = L.cfa_sparc_loss_gathered_workspace_bytes(B, P, T, D, code, 0, N)
         assert nbytes > L.cfa_sparc_loss_workspace_bytes(B, P, T, D, code, 0)
         streams = [torch.cuda.Stream() for _ in range(N)]
