@@ -360,8 +360,20 @@ sparc_bwd2_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_constant
     float* Sc = reinterpret_cast<float*>(SRhi);        // [T][NT+1] fp32 scratch (the S_raw region is free until E1)
     const int ldl = NT + 1;
     {
+      // 24 KB per sample, L2-cold at this point (the forward wrote it a whole kernel ago): issue the loads 12 deep per
+      // thread instead of one dependent round trip per element — phase 0 gates E1 (same warps) and was 21-25 k cycles
       const float* src = p.tt_logits + (size_t)b * T * T;
-      for (int idx = tid; idx < T * T; idx += 256) { const int i = idx / T, j = idx - i * T; Sc[i * ldl + j] = __ldg(src + idx); }
+      const int n = T * T;
+      for (int base = 0; base < n; base += 256 * 12) {
+        float tmp[12];
+#pragma unroll
+        for (int k = 0; k < 12; ++k) { const int idx = base + tid + 256 * k; tmp[k] = idx < n ? __ldg(src + idx) : 0.f; }
+#pragma unroll
+        for (int k = 0; k < 12; ++k) {
+          const int idx = base + tid + 256 * k;
+          if (idx < n) { const int i = idx / T, j = idx - i * T; Sc[i * ldl + j] = tmp[k]; }
+        }
+      }
     }
     const float ign = (row < T) ? p.g_inv_norm[(size_t)b * T + row] : 0.f;
     b2_epi_bar();
