@@ -334,7 +334,9 @@ def main():
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
     if world > 1:
-        os.environ["NCCL_DEBUG"] = os.environ.get("CFA_NCCL_DEBUG", "WARN")   # keep NCCL's version banner off stdout (one JSON line only)
+        # stdout carries ONE JSON line: NCCL's debug output (its version banner is printed at every level) goes to stderr
+        os.environ["NCCL_DEBUG"] = os.environ.get("CFA_NCCL_DEBUG", "WARN")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     from clip_finegrained_alignment_b200 import SPARCLoss, _lib
     pk = peaks()
@@ -362,6 +364,12 @@ def main():
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    # initialisation, not warm-up: the first calls load the kernels (CUDA loads modules lazily, with a context
+    # synchronisation each), size the allocator's pools and, with N > 1, create and map the peer exchange blocks
+    init_steps = 10 if world > 1 else 2
+    for i in range(init_steps):
+        step(i)
+    sync_all()
     for i in range(args.warmup):
         step(i)
     sync_all()
@@ -470,7 +478,7 @@ def main():
         "config": {"workload": f"BASELINE config {2 if (P, D) == (196, 512) else ('4' if (P, D) == (576, 768) else 'shapes')}: "
                                f"{'ViT-L/14@336' if P == 576 else 'ViT-B/16'} SPARC + global InfoNCE fwd+bwd, B={B}/GPU, P={P}, T={T}, "
                                f"D={D}, thr=1/P, s=1, all-True mask" + (", all-gathered global InfoNCE" if world > 1 else ""),
-                   "global_batch": Bg, "collective": collective, "l2": f"inputs rotated over {nbuf} sets ({nbuf * in_bytes >> 20} MiB > 2x L2)",
+                   "global_batch": Bg, "collective": collective, "init_steps_before_warmup": init_steps, "l2": f"inputs rotated over {nbuf} sets ({nbuf * in_bytes >> 20} MiB > 2x L2)",
                    "algorithmic_flops_per_pair": flops_per_pair(Bg),
                    "algorithmic_tflops": round(value * flops_per_pair(Bg) / 1e12, 2),
                    "kernel_ms": {k: round(statistics.mean(a.elapsed_time(b) for a, b in ev), 4) for k, ev in kev.items() if ev}},
