@@ -68,6 +68,9 @@ SIGNATURES = {
     "cfa_count_contrastive_bwd": (C.c_int, [_vp, _vp, _vp, _i, _i, _i, _i, _f, _i, _vp, _vp, _vp, _vp, _vp]),
     "cfa_logits_ce_fwd": (C.c_int, [_vp, _vp, _i, _i, _vp, _vp, _vp, _vp]),
     "cfa_logits_ce_bwd": (C.c_int, [_vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp]),
+    "cfa_global_infonce_gathered_workspace_bytes": (_sz, [_i, _i, _i]),
+    "cfa_global_infonce_gathered_fwd": (C.c_int, [_vp, _i, _i, _f, _f, _vp, _sz, _i, _i, _vp, C.c_uint32, _vp, _vp]),
+    "cfa_global_infonce_gathered_bwd": (C.c_int, [_vp, _i, _i, _f, _f, _vp, _sz, _vp, _vp, _i, _i, _vp]),
     "cfa_masked_pairwise_fwd": (C.c_int, [_vp, _vp, _vp, _i, _i, _i, _i, _f, _vp, _vp, _vp, _vp]),
     "cfa_masked_pairwise_bwd": (C.c_int, [_vp, _vp, _vp, _i, _i, _i, _i, _f, _vp, _vp, _vp, _vp, _vp, _vp]),
     "cfa_sparc_path": (C.c_int, [_i, _i, _i, _i, _i]),
@@ -110,7 +113,8 @@ LAUNCHES = {"cfa_adamspd_step": 2, "cfa_adamspd_step_amp": 4, "cfa_global_infonc
     "cfa_masked_pairwise_fwd": 2, "cfa_masked_pairwise_bwd": 1,
             "cfa_sparc_loss_fwd": 2, "cfa_sparc_loss_bwd": 4,
             "cfa_count_contrastive_fwd": 2, "cfa_count_contrastive_bwd": 1, "cfa_logits_ce_fwd": 2, "cfa_logits_ce_bwd": 1,
-            "cfa_sparc_loss_gathered_fwd": 8, "cfa_sparc_loss_gathered_bwd": 4, "cfa_peer_sync": 1}
+            "cfa_sparc_loss_gathered_fwd": 8, "cfa_sparc_loss_gathered_bwd": 4, "cfa_peer_sync": 1,
+            "cfa_global_infonce_gathered_fwd": 7, "cfa_global_infonce_gathered_bwd": 2}
 launch_count = 0
 kernel_events = None       # {abi name: [(start_event, end_event), ...]} while bench.py profiles; else None
 

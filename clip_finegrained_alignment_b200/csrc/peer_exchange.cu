@@ -50,7 +50,8 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
 // 3. pull  : pull_dst[r * pull_n + i] = peer r block[pull_off + i]   (last CTA only; small)
 __global__ void __launch_bounds__(1024)
 peer_sync_kernel(const PeerBlocks blocks, int world, int rank, unsigned epoch, const float* __restrict__ push_src,
-                 size_t push_off, size_t push_n, size_t pull_off, int pull_n, float* __restrict__ pull_dst) {
+                 size_t push_off, size_t push_n, size_t pull_off, int pull_n, float* __restrict__ pull_dst,
+                 float* __restrict__ tail2_sums /* optional [2]: sums over the ranks of the last two pulled words */) {
   float* own = blocks.base[rank];
   {
     float* dst = own + push_off;
@@ -93,10 +94,18 @@ peer_sync_kernel(const PeerBlocks blocks, int world, int rank, unsigned epoch, c
       const float x = ld_relaxed_sys(blocks.base[r] + pull_off + i);
       pull_dst[(size_t)r * pull_n + i] = bad ? __int_as_float(0x7fc00000) : x;    // a missing rank poisons the losses (NaN)
     }
+  if (tail2_sums && pull_n >= 2) {                       // the packs end in (sum CE_a, sum CE_b): global sums, fixed rank order
+    __syncthreads();
+    if (threadIdx.x < 2) {
+      float s = 0.f;
+      for (int r = 0; r < world; ++r) s += pull_dst[(size_t)r * pull_n + pull_n - 2 + threadIdx.x];
+      tail2_sums[threadIdx.x] = s;
+    }
+  }
 }
 
 int peer_sync(void* const* h_blocks, int world, int rank, uint32_t epoch, const float* push_src, size_t push_off, size_t push_n,
-              size_t pull_off, int pull_n, float* pull_dst, cudaStream_t st) {
+              size_t pull_off, int pull_n, float* pull_dst, cudaStream_t st, float* tail2_sums) {
   PeerBlocks pb{};
   for (int r = 0; r < world; ++r) {
     if (!h_blocks[r]) return CFA_ERR_BAD_ARG;
@@ -105,7 +114,7 @@ int peer_sync(void* const* h_blocks, int world, int rank, uint32_t epoch, const 
   int nblk = (int)((push_n / 4 + 1023) / 1024);
   if (nblk < 1) nblk = 1;
   if (nblk > 64) nblk = 64;
-  peer_sync_kernel<<<nblk, 1024, 0, st>>>(pb, world, rank, epoch, push_src, push_off, push_n, pull_off, pull_n, pull_dst);
+  peer_sync_kernel<<<nblk, 1024, 0, st>>>(pb, world, rank, epoch, push_src, push_off, push_n, pull_off, pull_n, pull_dst, tail2_sums);
   return launch_status();
 }
 
@@ -158,5 +167,5 @@ extern "C" int cfa_peer_sync(void* const* h_peer_blocks, int world, int rank, ui
                              float* pull_dst, void* stream) {
   if (!h_peer_blocks || world < 1 || world > kMaxPeers || rank < 0 || rank >= world) return CFA_ERR_BAD_ARG;
   return peer_sync(h_peer_blocks, world, rank, epoch, push_src, push_off_words, push_words, pull_off_words, pull_words,
-                   pull_dst, (cudaStream_t)stream);
+                   pull_dst, (cudaStream_t)stream, nullptr);
 }

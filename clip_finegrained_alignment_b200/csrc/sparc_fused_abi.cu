@@ -113,7 +113,7 @@ extern "C" int cfa_sparc_loss_bwd(const void* v, const void* l, const uint8_t* m
 // ---------------------------------------------------------------------------------------------------------------
 namespace cfa {
 int peer_sync(void* const* h_blocks, int world, int rank, uint32_t epoch, const float* push_src, size_t push_off, size_t push_n,
-              size_t pull_off, int pull_n, float* pull_dst, cudaStream_t st);
+              size_t pull_off, int pull_n, float* pull_dst, cudaStream_t st, float* tail2_sums = nullptr);
 size_t peer_slot_words(int B, int D);
 constexpr size_t kPeerHeaderWords = 64;
 }
@@ -195,4 +195,71 @@ extern "C" int cfa_sparc_loss_gathered_bwd(const void* v, const void* l, const u
   return cfa_sparc_bwd(v, l, mask, B, P, T, D, dtype, thr, scale, f + w.rin, f + w.lse_row, f + w.lse_col, f + w.tt, f + w.gin,
                        w.saved ? (const void*)(f + w.gsplit) : nullptr, w.saved ? f + w.qsave : nullptr, f + w.coef + 2, da, db,
                        dv, dl, w.scratch_bytes ? (void*)(f + w.scratch) : nullptr, w.scratch_bytes, path, stream);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// The gathered global InfoNCE on its own over peer memory (CustomCLIPLoss / CLIPCountLoss with gather=True,
+// losses.py:14-36 on the all-gathered batch): same exchange and kernels as the global part of the gathered SPARC loss.
+//   ab_loc [2][B][D] fp32 raw rows (image | text) -> sums2 [2] = sum over the GLOBAL batch of CE_a, CE_b
+// Workspace (floats): norms [2B] | packs [world][2B+2] | global kernel workspace.  The backward needs no exchange.
+// ---------------------------------------------------------------------------------------------------------------
+namespace cfa {
+struct GatherWs { size_t norms, gpack, gws, total, gws_bytes; };
+static GatherWs gather_ws_layout(int B, int D, int world) {
+  GatherWs w;
+  size_t o = 0;
+  w.norms = o; o += up32((size_t)2 * B);
+  w.gpack = o; o += up32((size_t)world * (2 * B + 2));
+  w.gws_bytes = cfa_global_infonce_workspace_bytes(B, world * B, D);
+  w.gws = o; o += up32((w.gws_bytes + 3) / 4);
+  w.total = o;
+  return w;
+}
+}  // namespace cfa
+
+extern "C" size_t cfa_global_infonce_gathered_workspace_bytes(int B, int D, int world) {
+  if (B <= 0 || D <= 0 || world < 1 || world > kMaxPeers) return 0;
+  return gather_ws_layout(B, D, world).total * sizeof(float);
+}
+
+extern "C" int cfa_global_infonce_gathered_fwd(const float* ab_loc, int B, int D, float scale, float eps, void* workspace,
+                                               size_t workspace_bytes, int world, int rank, void* const* h_peer_blocks,
+                                               uint32_t step, float* sums2, void* stream) {
+  if (B <= 0 || D <= 0 || !ab_loc || !workspace || !h_peer_blocks || !sums2) return CFA_ERR_BAD_ARG;
+  if (world < 2 || world > kMaxPeers || rank < 0 || rank >= world || ((uintptr_t)workspace & 127) != 0) return CFA_ERR_BAD_ARG;
+  if (cfa_global_infonce_path(B, world * B, D, 0) != 2) return CFA_ERR_UNSUPPORTED;
+  const GatherWs w = gather_ws_layout(B, D, world);
+  if (workspace_bytes < w.total * sizeof(float)) return CFA_ERR_WORKSPACE;
+  float* f = (float*)workspace;
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t slot = kPeerHeaderWords + (size_t)(step & 1) * peer_slot_words(B, D);
+  const size_t pack_off = slot + up32((size_t)2 * B * D);
+  int rc = peer_sync(h_peer_blocks, world, rank, 2 * step + 1, ab_loc, slot, (size_t)2 * B * D, 0, 0, nullptr, st);
+  if (rc != CFA_OK) return rc;
+  PeerTable pt{};
+  pt.n = world;
+  for (int r = 0; r < world; ++r) pt.base[r] = (const float*)h_peer_blocks[r] + slot;
+  float* pack = f + w.gpack + (size_t)rank * (2 * B + 2);
+  rc = global_infonce_fwd_peers(ab_loc, ab_loc + (size_t)B * D, nullptr, nullptr, B, world * B, D, rank * B, scale, eps, pack,
+                                f + w.norms, pack + 2 * B, nullptr, nullptr, 0, 0.f, 0.f, nullptr, f + w.gws, w.gws_bytes, 0, world,
+                                &pt, stream);
+  // the second barrier is issued even if the launch above failed: the peers are waiting for it
+  const int rcx = peer_sync(h_peer_blocks, world, rank, 2 * step + 2, pack, pack_off, (size_t)2 * B + 2, pack_off, 2 * B + 2,
+                            f + w.gpack, st, sums2);             // the same kernel adds up the ranks' CE sums
+  return rc != CFA_OK ? rc : rcx;
+}
+
+extern "C" int cfa_global_infonce_gathered_bwd(const float* ab_loc, int B, int D, float scale, float eps, void* workspace,
+                                               size_t workspace_bytes, const float* coef2, float* dab, int world, int rank,
+                                               void* stream) {
+  if (B <= 0 || D <= 0 || !ab_loc || !workspace || !coef2 || !dab) return CFA_ERR_BAD_ARG;
+  if (world < 2 || world > kMaxPeers || rank < 0 || rank >= world) return CFA_ERR_BAD_ARG;
+  const GatherWs w = gather_ws_layout(B, D, world);
+  if (workspace_bytes < w.total * sizeof(float)) return CFA_ERR_WORKSPACE;
+  float* f = (float*)workspace;
+  const float* a = ab_loc;
+  const float* b = ab_loc + (size_t)B * D;
+  const float* pack = f + w.gpack + (size_t)rank * (2 * B + 2);
+  return cfa_global_infonce_bwd(a, b, a, b, B, world * B, D, rank * B, scale, eps, pack, f + w.gpack, f + w.norms, coef2, dab,
+                                dab + (size_t)B * D, f + w.gws, w.gws_bytes, 0, world, stream);
 }

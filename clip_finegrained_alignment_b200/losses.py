@@ -423,8 +423,25 @@ class _ClipFunction(torch.autograd.Function):
         if img.dim() != 2 or img.shape != txt.shape:
             raise _lib.CfaError(f"CustomCLIPLoss: expected two [B,D] tensors, got {tuple(img.shape)}, {tuple(txt.shape)}")
         ab = torch.stack([img.detach().to(torch.float32), txt.detach().to(torch.float32)])
+        ctx.peer = None
         with torch.cuda.device(dev):
             world, rank, group = _dist_ctx(group, gather)
+            B, D = img.shape
+            if world > 1 and gather != "nccl" and img.dtype != torch.float32 \
+                    and _L.cfa_global_infonce_path(B, world * B, D, 0) == 2:
+                # all-gathered loss over peer memory (csrc/peer_exchange.cu): no collective call on the step path
+                from . import peer as _peer
+                ex = _peer.get_exchange(B, D, group)
+                if ex is not None:
+                    nbytes = _L.cfa_global_infonce_gathered_workspace_bytes(B, D, world)
+                    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+                    sums = torch.empty(2, dtype=torch.float32, device=dev)
+                    _lib.call("cfa_global_infonce_gathered_fwd", ab.data_ptr(), B, D, 1.0 / temperature, 0.0, ws.data_ptr(),
+                              nbytes, world, rank, ex.blocks, ex.next_step(), sums.data_ptr(), _lib.stream_ptr())
+                    ctx.peer = (world, rank, 1.0 / temperature)
+                    ctx.save_for_backward(ab, ws)
+                    ctx.dt = (img.dtype, txt.dtype)
+                    return (sums[0] + sums[1]) * (0.5 / (world * B))
             # x / x.norm(): no eps in this loss (losses.py:17-18)
             gst, sums = _global_forward(ab, 1.0 / temperature, 0.0, world, rank, group,
                                         path=1 if img.dtype == torch.float32 else 0)
@@ -435,6 +452,16 @@ class _ClipFunction(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g):
+        if ctx.peer is not None:
+            world, rank, scale = ctx.peer
+            ab, ws = ctx.saved_tensors
+            _, B, D = ab.shape
+            with torch.cuda.device(ab.device):
+                c = (g.to(torch.float32).reshape(1) * (0.5 / (world * B))).expand(2).contiguous()
+                dab = torch.empty_like(ab)
+                _lib.call("cfa_global_infonce_gathered_bwd", ab.data_ptr(), B, D, scale, 0.0, ws.data_ptr(), ws.numel(),
+                          c.data_ptr(), dab.data_ptr(), world, rank, _lib.stream_ptr())
+            return dab[0].to(ctx.dt[0]), dab[1].to(ctx.dt[1]), None, None, None
         gst = ctx.gst
         with torch.cuda.device(gst.a.device):
             c = (g.to(torch.float32).reshape(1) * (0.5 / gst.Bg)).expand(2).contiguous()

@@ -229,6 +229,20 @@ int cfa_sparc_loss_gathered_bwd(const void* v, const void* l, const uint8_t* mas
                                 int path, int world, int rank, void* stream);
 
 /*
+ * The gathered global InfoNCE alone over the same exchange blocks (CustomCLIPLoss / CLIPCountLoss with gather = True:
+ * losses.py:14-36 on the all-gathered batch).  ab_loc [2][B][D] fp32 = this rank's raw image | text rows;
+ * sums2 [2] (DEVICE) = sum over the GLOBAL batch of the two directions' cross-entropies.  Backward: gradient of
+ * coef2[0] * sum CE_a + coef2[1] * sum CE_b w.r.t. the local rows -> dab [2][B][D]; no exchange.  Same workspace for both.
+ */
+size_t cfa_global_infonce_gathered_workspace_bytes(int B, int D, int world);
+int cfa_global_infonce_gathered_fwd(const float* ab_loc, int B, int D, float scale, float eps, void* workspace,
+                                    size_t workspace_bytes, int world, int rank, void* const* h_peer_blocks,
+                                    uint32_t step, float* sums2, void* stream);
+int cfa_global_infonce_gathered_bwd(const float* ab_loc, int B, int D, float scale, float eps, void* workspace,
+                                    size_t workspace_bytes, const float* coef2, float* dab, int world, int rank,
+                                    void* stream);
+
+/*
  * SPARCLoss.masked_pairwise_contrastive_loss on its own (losses.py:165-197): a, b [B,T,D] in `dtype`, mask [B,T] bytes.
  * One direction: rows of a against the columns of b of the same sample, target = same token index.
  *   out2[0] = sum_b sum_{valid i} CE_i / n_valid,  out2[1] = n_valid = sum(mask) + 1e-8 (fp32);

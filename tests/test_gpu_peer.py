@@ -180,6 +180,64 @@ def test_gathered_sparc_loss_peer_memory_emulated_ranks(N, B, P, T, D, s, dtype,
         ex.close()
 
 
+@pytest.mark.parametrize("N,B,D,temp", [(3, 70, 256, 0.07), (2, 256, 512, 1.0)])
+def test_gathered_clip_loss_peer_memory_emulated_ranks(N, B, D, temp):
+    """cfa_global_infonce_gathered_fwd/_bwd (CustomCLIPLoss with gather=True): N ranks in one process, oracle =
+    CustomCLIPLoss restated on the concatenated batch (losses.py:14-36)."""
+    from clip_finegrained_alignment_b200 import _lib
+    L = _lib.lib
+    g = torch.Generator().manual_seed(17 * N + B)
+    img = torch.randn(N * B, D, generator=g); txt = torch.randn(N * B, D, generator=g)
+    fw = lo.clip_loss_forward(img.double(), txt.double(), temp)
+    da_ref, db_ref = lo.clip_loss_backward(fw, temp)
+    Bg = N * B
+    # load every kernel of the path first (see _load_kernels): tensor-core global forward + backward, rank-locally
+    a = img.cuda(); b = txt.cuda()
+    nb = L.cfa_global_infonce_workspace_bytes(B, Bg, D)
+    w0 = torch.empty(nb, dtype=torch.uint8, device="cuda")
+    pk = torch.zeros(N, 2 * B + 2, device="cuda"); n2 = torch.empty(2, B, device="cuda"); cf = torch.zeros(2, device="cuda")
+    d0 = torch.empty(2, B, D, device="cuda")
+    _lib.call("cfa_global_infonce_fwd", a.data_ptr(), b.data_ptr(), a.data_ptr(), b.data_ptr(), B, Bg, D, 0, 1.0, 0.0,
+              pk.data_ptr(), n2.data_ptr(), pk.data_ptr() + 8 * B, 0, 0, 0, 0.0, 0.0, 0, w0.data_ptr(), nb, 2, 0, _lib.stream_ptr())
+    _lib.call("cfa_global_infonce_bwd", a.data_ptr(), b.data_ptr(), a.data_ptr(), b.data_ptr(), B, Bg, D, 0, 1.0, 0.0,
+              pk.data_ptr(), pk.data_ptr(), n2.data_ptr(), cf.data_ptr(), d0.data_ptr(), d0[1].data_ptr(), w0.data_ptr(), nb, 2, 0,
+              _lib.stream_ptr())
+    blocks1 = _LocalExchange(1, B, D)
+    _lib.call("cfa_peer_sync", blocks1.blocks, 1, 0, 1, n2.data_ptr(), 64, 8, 64, 8, d0.data_ptr(), _lib.stream_ptr())
+    torch.cuda.synchronize()
+    blocks1.close()
+
+    ex = _LocalExchange(N, B, D)
+    try:
+        nbytes = L.cfa_global_infonce_gathered_workspace_bytes(B, D, N)
+        streams = [torch.cuda.Stream() for _ in range(N)]
+        ab = [torch.stack([img[r * B:(r + 1) * B], txt[r * B:(r + 1) * B]]).cuda().contiguous() for r in range(N)]
+        coef = torch.full((2,), 0.5 / Bg, device="cuda")
+        for step in range(2):
+            ws = [torch.empty(nbytes, dtype=torch.uint8, device="cuda") for _ in range(N)]
+            sums = [torch.zeros(2, device="cuda") for _ in range(N)]
+            dab = [torch.empty_like(x) for x in ab]
+            torch.cuda.synchronize()
+            for r in range(N):
+                with torch.cuda.stream(streams[r]):
+                    _lib.call("cfa_global_infonce_gathered_fwd", ab[r].data_ptr(), B, D, 1.0 / temp, 0.0, ws[r].data_ptr(), nbytes,
+                              N, r, ex.blocks, step, sums[r].data_ptr(), _lib.stream_ptr())
+            for r in range(N):
+                with torch.cuda.stream(streams[r]):
+                    _lib.call("cfa_global_infonce_gathered_bwd", ab[r].data_ptr(), B, D, 1.0 / temp, 0.0, ws[r].data_ptr(), nbytes,
+                              coef.data_ptr(), dab[r].data_ptr(), N, r, _lib.stream_ptr())
+            torch.cuda.synchronize()
+            want = float(fw["clip_loss"])
+            for r in range(N):
+                got = float(sums[r].sum()) * 0.5 / Bg
+                assert abs(got - want) <= 2e-5 * max(1.0, abs(want)), (step, r, got, want)
+                sl = slice(r * B, (r + 1) * B)
+                assert rel_err(dab[r][0], da_ref[sl]) <= 2e-4, (step, r, rel_err(dab[r][0], da_ref[sl]))
+                assert rel_err(dab[r][1], db_ref[sl]) <= 2e-4, (step, r, rel_err(dab[r][1], db_ref[sl]))
+    finally:
+        ex.close()
+
+
 def test_gathered_unsupported_shapes_are_refused():
     """fp32 inputs / D the tensor-core global kernels do not take: CFA_ERR_UNSUPPORTED (-2), caller keeps NCCL."""
     from clip_finegrained_alignment_b200 import _lib
@@ -218,10 +276,23 @@ for mode in (True, "nccl"):
         out["total_loss"].backward()
     torch.cuda.synchronize()
     res[str(mode)] = (out["total_loss"].item(), out["global_loss"].item(), v.grad.float().cpu(), l.grad.float().cpu())
-from clip_finegrained_alignment_b200 import peer
+from clip_finegrained_alignment_b200 import CustomCLIPLoss, peer
 used_peer = any(e.ok for e in peer._EXCHANGES.values())
+clip = {}
+i0 = torch.randn(B, D, device="cuda").to(torch.bfloat16); t0 = torch.randn(B, D, device="cuda").to(torch.bfloat16)
+for mode in (True, "nccl"):
+    crit = CustomCLIPLoss(0.07, gather=mode)
+    for it in range(2):
+        i1 = i0.clone().requires_grad_(True); t1 = t0.clone().requires_grad_(True)
+        o = crit(i1, t1)
+        o["total_loss"].backward()
+    torch.cuda.synchronize()
+    clip[str(mode)] = (o["clip_loss"].item(), i1.grad.float().cpu(), t1.grad.float().cpu())
+ca, cb = clip["True"], clip["nccl"]
+clip_ok = abs(ca[0] - cb[0]) <= 1e-6 * abs(cb[0]) and float((ca[1] - cb[1]).norm() / cb[1].norm()) <= 1e-4 \
+    and float((ca[2] - cb[2]).norm() / cb[2].norm()) <= 1e-4
 a, b = res["True"], res["nccl"]
-ok = used_peer and abs(a[0] - b[0]) <= 1e-6 * abs(b[0]) and abs(a[1] - b[1]) <= 1e-6 * abs(b[1]) \
+ok = used_peer and clip_ok and abs(a[0] - b[0]) <= 1e-6 * abs(b[0]) and abs(a[1] - b[1]) <= 1e-6 * abs(b[1]) \
     and float((a[2] - b[2]).norm() / b[2].norm()) <= 1e-4 and float((a[3] - b[3]).norm() / b[3].norm()) <= 1e-4
 print(json.dumps({"rank": rank, "ok": bool(ok), "used_peer": bool(used_peer), "total": a[0], "total_nccl": b[0]}), flush=True)
 dist.destroy_process_group()
