@@ -31,6 +31,20 @@ def test_library_exports_every_declared_symbol():
     assert _lib.lib.cfa_adamspd_chunk_elems() == 8192
 
 
+def test_header_is_plain_c(tmp_path):
+    """The boundary is a C ABI: include/cfa_b200.h must compile as C99 on its own (no C++ / CUDA / torch types)."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no gcc")
+    src = tmp_path / "h.c"
+    src.write_text('#include "cfa_b200.h"\nint main(void) { return cfa_abi_version() == CFA_ABI_VERSION ? 0 : 1; }\n')
+    r = subprocess.run([gcc, "-std=c99", "-Wall", "-Wextra", "-Werror", "-fsyntax-only", "-I", os.path.join(ROOT, "include"), str(src)],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+
+
 def test_descriptor_struct_matches_header():
     from clip_finegrained_alignment_b200.optimizers import _TENSOR_DT
     assert _TENSOR_DT.itemsize == 88
