@@ -10,6 +10,18 @@ def rnd(x, split):
         hi = x.to(torch.bfloat16).to(x.dtype); lo_ = (x - hi).to(torch.bfloat16).to(x.dtype); return hi + lo_
     if split == 'fp16': return x.to(torch.float16).to(x.dtype)
     if split == 'bf16': return x.to(torch.bfloat16).to(x.dtype)
+    if split in ('h16hilo', 'h16hilo_scaled'):
+        # fp16 hi + lo operands (what a same-format kind::f16 MMA needs when the raw embeddings are fp16).  'scaled':
+        # one power-of-two factor per sample puts the tile's maximum at 2^10 before the split (exact), undone afterwards.
+        if split == 'h16hilo_scaled':
+            amax = x.abs().flatten(1).max(dim=1).values.clamp_min(1e-300)
+            k = torch.floor(10.0 - torch.log2(amax)).view(-1, *([1] * (x.dim() - 1)))
+            sc = torch.pow(torch.tensor(2.0, dtype=x.dtype), k)
+        else:
+            sc = torch.ones((), dtype=x.dtype)
+        y = x * sc
+        hi = y.to(torch.float16).to(x.dtype); lo_ = (y - hi).to(torch.float16).to(x.dtype)
+        return (hi + lo_) / sc
 
 def emul(v, l, mask, thr, s, c_r, c_c, dpool_v, dpool_l, split='none', dt=torch.float64):
     B, P, D = v.shape; T = l.shape[1]
@@ -77,3 +89,10 @@ if __name__ == '__main__':
         for split in ['none', 'hilo', 'fp16', 'bf16']:
             dv, dl = emul(v, l, mask, thr, s, 0.5 / nv, 0.5 / nv, z, z, split)
             print((B, P, T, D, s), split, 'dv err %.3e  dl err %.3e' % (float((dv - rv).norm() / rv.norm()), float((dl - rl).norm() / rl.norm())))
+        # fp16 embeddings (torch.autocast's default): the exact route needs fp16 hi/lo on-chip operands
+        v16 = v.to(torch.float16).double(); l16 = l.to(torch.float16).double()
+        f = lo.sparc_forward(v16, l16, mask, thr, 0.0, 1.0, s)
+        rv, rl = lo.sparc_backward(f)
+        for split in ['h16hilo', 'h16hilo_scaled']:
+            dv, dl = emul(v16, l16, mask, thr, s, 0.5 / nv, 0.5 / nv, z, z, split)
+            print((B, P, T, D, s), 'fp16 inputs', split, 'dv err %.3e  dl err %.3e' % (float((dv - rv).norm() / rv.norm()), float((dl - rl).norm() / rl.norm())))
