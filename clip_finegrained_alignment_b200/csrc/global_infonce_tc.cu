@@ -26,8 +26,10 @@ constexpr int kGtStages = 2;
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 gt_split_kernel(const float* __restrict__ a, const float* __restrict__ b, int rows, int D, float eps,
-                bf16* __restrict__ out, float* __restrict__ norms /* [2][rows] or NULL */, int rank_rows, size_t rank_stride,
-                const PeerTable peers) {
+                bf16* __restrict__ out, float* __restrict__ norms /* [2][loc_rows] or NULL */, int rank_rows, size_t rank_stride,
+                const PeerTable peers, int loc_row0, int loc_rows) {
+  // norms are kept for the LOCAL rows only (global rows [loc_row0, loc_row0 + loc_rows)): the local operand tiles are a
+  // row window of the all-rows array, so one launch serves both
   // rank_rows / rank_stride: global row g = r * rank_rows + i lives at base + r * rank_stride + i * D (the raw output of
   // an all-gather of per-rank [2][B][D] blocks); rank_rows == rows, rank_stride == 0 for a plain [rows][D] matrix
   const int r = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31, which = blockIdx.y;
@@ -47,7 +49,7 @@ gt_split_kernel(const float* __restrict__ a, const float* __restrict__ b, int ro
   }
   ss = warp_sum(ss);
   const float n = fmaxf(sqrtf(ss), eps);
-  if (norms && lane == 0) norms[(size_t)which * rows + r] = n;
+  if (norms && lane == 0 && r >= loc_row0 && r < loc_row0 + loc_rows) norms[(size_t)which * loc_rows + (r - loc_row0)] = n;
   bf16* hi = out + ((size_t)(2 * which) * rows + r) * D;
   bf16* lo = out + ((size_t)(2 * which + 1) * rows + r) * D;
 #pragma unroll
@@ -398,10 +400,11 @@ static GtHost gt_carve(void* ws, int B, int Bg, int D) {
   return h;
 }
 
-static int gt_maps(const GtHost& h, int B, int Bg, int D, CUtensorMap* tmLoc, CUtensorMap* tmAll) {
-  // [which (a_hi, a_lo, b_hi, b_lo)][row][d]: the `which` index is the 3rd TMA coordinate
+static int gt_maps(const GtHost& h, int B, int Bg, int D, int col_offset, CUtensorMap* tmLoc, CUtensorMap* tmAll) {
+  // [which (a_hi, a_lo, b_hi, b_lo)][row][d]: the `which` index is the 3rd TMA coordinate.  The local rows are the window
+  // [col_offset, col_offset + B) of the all-rows array (rows beyond B are out of bounds of the window: zero fill).
   int rc;
-  if ((rc = make_tmap_bf16_3d(tmLoc, h.loc_split, D, B, 4, 64, kGtM)) != CFA_OK) return rc;
+  if ((rc = make_tmap_bf16_3d(tmLoc, h.all_split + (size_t)col_offset * D, D, B, 4, 64, kGtM, false, (uint64_t)Bg * D)) != CFA_OK) return rc;
   if ((rc = make_tmap_bf16_3d(tmAll, h.all_split, D, Bg, 4, 64, kGtN)) != CFA_OK) return rc;
   return CFA_OK;
 }
@@ -411,16 +414,16 @@ int global_tc_fwd(const float* a_loc, const float* b_loc, const float* a_all, co
                   int* nsplit, void* ws, int gathered_ranks, const PeerTable* peers, cudaStream_t st) {
   const GtHost h = gt_carve(ws, B, Bg, D);
   PeerTable none{};
+  // ONE launch: every global row is normalised and split once; the local rows' norms come out of the same pass
   if (peers && peers->n > 1)
-    gt_split_kernel<<<dim3((Bg + 7) / 8, 2), 256, 0, st>>>(nullptr, nullptr, Bg, D, eps, h.all_split, nullptr, B, 0, *peers);
+    gt_split_kernel<<<dim3((Bg + 7) / 8, 2), 256, 0, st>>>(nullptr, nullptr, Bg, D, eps, h.all_split, norms2, B, 0, *peers, col_offset, B);
   else if (gathered_ranks > 1)
-    gt_split_kernel<<<dim3((Bg + 7) / 8, 2), 256, 0, st>>>(a_all, b_all, Bg, D, eps, h.all_split, nullptr, B, (size_t)2 * B * D, none);
+    gt_split_kernel<<<dim3((Bg + 7) / 8, 2), 256, 0, st>>>(a_all, b_all, Bg, D, eps, h.all_split, norms2, B, (size_t)2 * B * D, none, col_offset, B);
   else
-    gt_split_kernel<<<dim3((Bg + 7) / 8, 2), 256, 0, st>>>(a_all, b_all, Bg, D, eps, h.all_split, nullptr, Bg, 0, none);
-  gt_split_kernel<<<dim3((B + 7) / 8, 2), 256, 0, st>>>(a_loc, b_loc, B, D, eps, h.loc_split, norms2, B, 0, none);
+    gt_split_kernel<<<dim3((Bg + 7) / 8, 2), 256, 0, st>>>(a_all, b_all, Bg, D, eps, h.all_split, norms2, Bg, 0, none, col_offset, B);
   CFA_CUDA_TRY(cudaGetLastError());
   CUtensorMap tmLoc, tmAll;
-  int rc = gt_maps(h, B, Bg, D, &tmLoc, &tmAll);
+  int rc = gt_maps(h, B, Bg, D, col_offset, &tmLoc, &tmAll);
   if (rc != CFA_OK) return rc;
   GtParams p{};
   p.B = B; p.Bg = Bg; p.D = D; p.col_offset = col_offset; p.scale = scale;
@@ -438,7 +441,7 @@ int global_tc_bwd(int B, int Bg, int D, int col_offset, float scale, const float
   // the split operands written by the forward are still in the workspace
   const GtHost h = gt_carve(ws, B, Bg, D);
   CUtensorMap tmLoc, tmAll;
-  int rc = gt_maps(h, B, Bg, D, &tmLoc, &tmAll);
+  int rc = gt_maps(h, B, Bg, D, col_offset, &tmLoc, &tmAll);
   if (rc != CFA_OK) return rc;
   GtParams p{};
   p.B = B; p.Bg = Bg; p.D = D; p.col_offset = col_offset; p.scale = scale;

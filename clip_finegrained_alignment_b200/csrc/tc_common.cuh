@@ -257,12 +257,14 @@ static inline PFN_tmapEncodeTiled get_tmap_encoder() {
 
 // bf16 tensor [d2][d1][d0] (d0 contiguous), box [1][box1][box0], zero fill out of bounds.
 // box0 = 64 elements -> 128-byte swizzle, box0 = 32 elements -> 64-byte swizzle.
+// plane_stride (elements, 0 = d0 * d1): distance between consecutive planes when the [d1 x d0] window is a row range of a
+// taller matrix (the local rows inside the all-gathered operand array)
 static inline int make_tmap_bf16_3d(CUtensorMap* m, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint32_t box0,
-                                    uint32_t box1, bool f16 = false) {
+                                    uint32_t box1, bool f16 = false, uint64_t plane_stride = 0) {
   PFN_tmapEncodeTiled enc = get_tmap_encoder();
   if (!enc) return CFA_ERR_UNSUPPORTED;
   cuuint64_t dims[3] = {d0, d1, d2};
-  cuuint64_t strides[2] = {d0 * 2, d0 * d1 * 2};
+  cuuint64_t strides[2] = {d0 * 2, (plane_stride ? plane_stride : d0 * d1) * 2};
   cuuint32_t box[3] = {box0, box1, 1};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = enc(m, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
