@@ -33,6 +33,21 @@ int sparc_bwd2_launch(const void* v, const void* l, const uint8_t* mask, int B, 
                       const float* tt_logits, const float* g_inv_norm, const void* g_split, const float* q_save,
                       const float* dpv, const float* dpl, void* dv, void* dl, long long* prof, int dtype, cudaStream_t st);
 
+// third-generation ("transposed") tcgen05 kernels (sparc_tc_fwd3.cu / sparc_tc_bwd3.cu): raw tiles are the A operand, on-chip
+// hi|lo operands are stacked along N; T <= 80, P <= 256, D % 128 == 0.  The forward leaves the per-token statistics
+// (min, 1/range, sigma, arg-min patch) in the first B*T*4 floats of the q_save buffer instead of Q.
+bool sparc_fwd3_supported(int P, int T, int D, int dtype);
+bool sparc_bwd3_supported(int P, int T, int D, int dtype);
+bool sparc_gen3_enabled(int P, int T, int D, int dtype);
+int sparc_fwd3_launch(const void* v, const void* l, const uint8_t* mask, int B, int P, int T, int D, float thr,
+                      float scale, float* row_inv_norm, float* pooled_v, float* pooled_l, float* lse_row, float* lse_col,
+                      float* local_partial, float* tt_logits, float* g_inv_norm, void* g_split, float* stats,
+                      long long* prof, int dtype, cudaStream_t st);
+int sparc_bwd3_launch(const void* v, const void* l, const uint8_t* mask, int B, int P, int T, int D, float thr, float scale,
+                      const float* row_inv_norm, const float* lse_row, const float* lse_col, const float* coef,
+                      const float* tt_logits, const float* g_inv_norm, const void* g_split, const float* stats,
+                      const float* dpv, const float* dpl, void* dv, void* dl, long long* prof, int dtype, cudaStream_t st);
+
 // cfa_global_infonce_fwd with the gathered rows read through a peer table (global_infonce.cu)
 int global_infonce_fwd_peers(const float* a_loc, const float* b_loc, const float* a_all, const float* b_all, int B, int Bg,
                              int D, int col_offset, float scale, float eps, float* lse2, float* norms2, float* sums2,

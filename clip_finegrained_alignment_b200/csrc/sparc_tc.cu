@@ -14,6 +14,7 @@
 //                     L[T,T] += G_kb . l_kb^T                             (losses.py:180)
 //            epilogue: masked row/column log-sum-exp and CE               (losses.py:186-196)
 #include "tc_common.cuh"
+#include <cstdlib>
 #include "sparc_paths.h"
 #include <math_constants.h>
 
@@ -1227,12 +1228,21 @@ int sparc_bwd_tc_launch(const void* v, const void* l, const uint8_t* mask, int B
 
 }  // namespace cfa
 
+namespace cfa {
+// generation switch (tuning aid): CFA_SPARC_GEN=2 keeps the second-generation kernels for A/B runs
+bool sparc_gen3_enabled(int P, int T, int D, int dtype) {
+  static int gen = -1;
+  if (gen < 0) { const char* e = getenv("CFA_SPARC_GEN"); gen = (e && e[0] == '2') ? 2 : 3; }
+  return gen == 3 && sparc_fwd3_supported(P, T, D, dtype) && sparc_bwd3_supported(P, T, D, dtype);
+}
+}  // namespace cfa
+
 using namespace cfa;
 
 // path: 0 = auto (tensor cores when the shape/dtype allows, else CUDA cores), 1 = CUDA cores, 2 = tensor cores
 extern "C" int cfa_sparc_path(int P, int T, int D, int dtype, int path) {
   if (path == 1) return 1;
-  const bool ok = sparc_tc_supported(P, T, D, dtype);     // bf16 only (fp16: see sparc_fwd2_supported)
+  const bool ok = sparc_tc_supported(P, T, D, dtype) || sparc_gen3_enabled(P, T, D, dtype);     // bf16 only (fp16: see sparc_fwd2_supported)
   if (path == 2) return ok ? 2 : CFA_ERR_UNSUPPORTED;
   return ok ? 2 : 1;
 }
@@ -1253,7 +1263,7 @@ extern "C" int cfa_sparc_bwd_path(int P, int T, int D, int dtype, int path) {
   const int which = cfa_sparc_path(P, T, D, dtype, path);
   if (which != 2) return which;
   if (dtype == CFA_DTYPE_F16) return 2;
-  return (sparc_tc_bwd_supported(P, T, D, dtype) || sparc_bwd2_supported(P, T, D, dtype)) ? 2 : 1;
+  return (sparc_gen3_enabled(P, T, D, dtype) || sparc_tc_bwd_supported(P, T, D, dtype) || sparc_bwd2_supported(P, T, D, dtype)) ? 2 : 1;
 }
 
 extern "C" int cfa_sparc_fwd(const void* v, const void* l, const uint8_t* mask, int B, int P, int T, int D, int dtype,
@@ -1266,6 +1276,10 @@ extern "C" int cfa_sparc_fwd(const void* v, const void* l, const uint8_t* mask, 
   if (which == 2) {
     if (!row_inv_norm) return CFA_ERR_WORKSPACE;
     if ((g_split == nullptr) != (q_save == nullptr)) return CFA_ERR_BAD_ARG;
+    if (g_split && sparc_gen3_enabled(P, T, D, dtype))   // third generation: transposed orientation, stacked hi|lo operands
+      return sparc_fwd3_launch(v, l, mask, B, P, T, D, thr, scale, row_inv_norm, pooled_v, pooled_l, lse_row, lse_col,
+                               local_partial, tt_logits, g_inv_norm, g_split, q_save, g_prof_fwd, dtype, (cudaStream_t)stream);
+    if (!sparc_tc_supported(P, T, D, dtype)) return CFA_ERR_WORKSPACE;     // third-generation-only shape without its buffers
     if (sparc_fwd2_supported(P, T, D, dtype))          // one kernel: norms / pooled means fused into the streaming pass
       return sparc_fwd2_launch(v, l, mask, B, P, T, D, thr, scale, row_inv_norm, pooled_v, pooled_l, lse_row, lse_col,
                                local_partial, tt_logits, g_inv_norm, g_split, q_save, g_prof_fwd, dtype, (cudaStream_t)stream);
@@ -1288,6 +1302,11 @@ extern "C" int cfa_sparc_bwd(const void* v, const void* l, const uint8_t* mask, 
   if (which == 2) {
     if (!row_inv_norm || !tt_logits || !g_inv_norm) return CFA_ERR_WORKSPACE;
     if (dtype == CFA_DTYPE_F16 && (!g_split || !q_save)) return CFA_ERR_WORKSPACE;      // fp16: second generation only
+    if (g_split && q_save && sparc_gen3_enabled(P, T, D, dtype))
+      return sparc_bwd3_launch(v, l, mask, B, P, T, D, thr, scale, row_inv_norm, lse_row, lse_col, coef, tt_logits,
+                               g_inv_norm, g_split, q_save, dpooled_v, dpooled_l, dv, dl, g_prof_buffer, dtype,
+                               (cudaStream_t)stream);
+    if (!sparc_tc_supported(P, T, D, dtype)) return CFA_ERR_WORKSPACE;
     if (g_split && q_save && sparc_bwd2_supported(P, T, D, dtype))      // streaming backward on the saved G / Q
       return sparc_bwd2_launch(v, l, mask, B, P, T, D, thr, scale, row_inv_norm, lse_row, lse_col, coef, tt_logits,
                                g_inv_norm, g_split, q_save, dpooled_v, dpooled_l, dv, dl, g_prof_buffer, dtype,

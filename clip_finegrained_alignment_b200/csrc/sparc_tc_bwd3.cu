@@ -1,0 +1,643 @@
+// Tensor-core SPARC backward, third generation ("transposed" orientation, see sparc_tc_fwd3.cu) for bf16 embeddings.
+//
+// Same mathematics as sparc_bwd2_kernel (SURVEY.md §8 a-bwd, gradients w.r.t. RAW dot products):
+//
+//   dG = dLhat . l - Gamma G             (Gamma = diag(gfac), the J_n term of normalize(G), losses.py:173)
+//   dW = dG . v^T = dLhat . S_raw - Gamma Q ,  Q = G . v^T                   (losses.py:245 backward)
+//   dv = (dShat + Z)^T . l + (-Gamma W)^T . G - v vfac + dvbar / P           Z = dLhat^T . W
+//   dl = (dShat + Z) . v   - l lfac + m dlbar / cnt
+//
+// but every product with a raw tile has the raw tile as the A operand (M = patches or feature columns) and the on-chip
+// bf16 hi|lo operand as B, stacked along N where that fits:
+//
+//   P1   [S^T | Qh^T | Ql^T][p, .] = v_kb . [l_kb ; Ghi_kb ; Glo_kb]^T       ONE N = 240 MMA per k-step: S_raw and Q = G . v^T
+//        phase 0 (overlaps P1): saved T x T logits -> dLhat (hi|lo operand), gfac_t, column sums
+//   E1   thread = patch: S^T -> W^T, S_raw^T (hi|lo operands [t/8][p][t%8]); -gfac Q parked in TMEM (tcgen05.st)
+//   M    dW^T += S_raw^T . dLhat^T (on top of -gfac Q) ;  Z^T = W^T . dLhat
+//   E3   renorm / threshold / min-max backward (one sweep, identities of sparc_bwd2) -> dShat'^T (hi|lo), -gfac W^T (hi|lo)
+//   P4   per 128-wide D block:  dl^T[d,t] = v^T . dShat'^T   (N = 160, hi|lo stacked)
+//                               dv^T[d,p] = l^T . dShat' + G^T . (-gfac W)      (N = NP; hi, lo operands in turn)
+//        epilogue: - x fac, pooled-mean terms, bf16 -> global; thread = feature column, 64 contiguous bytes per warp store
+#include "tc_common.cuh"
+#include "sparc_paths.h"
+#include <math_constants.h>
+
+namespace cfa {
+using namespace tc;
+typedef __nv_bfloat16 bf16;
+
+constexpr int kB3EpiWarps = 16;
+constexpr int kB3Threads = 32 * (2 + kB3EpiWarps);   // warp 0 TMA, warp 1 MMA, warps 2..17 epilogue
+constexpr float kB3ClampEps = 1e-8f;
+
+struct Bwd3Layout {
+  int NP, NT, MB, KB0, NBLK, CR0, NCH, NSP;
+  uint32_t v_bytes, l_bytes, slotP, slot4, plane, dlb;
+  uint32_t off_sr, off_w, off_ring4, off_ldp, off_dl, off_f, off_bar, total;
+};
+
+__host__ __device__ inline Bwd3Layout bwd3_layout(int P, int T, int D) {
+  Bwd3Layout L;
+  L.NP = (P + 15) & ~15; L.NT = (T + 15) & ~15; L.MB = L.NP > 128 ? 2 : 1; L.KB0 = D / 64; L.NBLK = D / 128;
+  L.NCH = L.NP > 128 ? 2 : 1;
+  L.CR0 = L.NCH == 2 ? 16 * ((L.NP + 31) / 32) : L.NP;
+  L.v_bytes = (uint32_t)L.NP * 128; L.l_bytes = (uint32_t)L.NT * 128;
+  L.slotP = L.v_bytes + 3 * L.l_bytes;
+  const uint32_t vch = 2u * L.CR0 * 128, ltl = 2u * L.l_bytes;
+  L.slot4 = vch > ltl ? vch : ltl;
+  L.plane = (uint32_t)L.NT * L.NP * 2;
+  L.dlb = (uint32_t)L.NT * L.NT * 2;
+  const uint32_t op = (2 * L.plane + 1023) & ~1023u;
+  L.off_sr = 0; L.off_w = op; L.off_ring4 = 2 * op;
+  const uint32_t ldp = (uint32_t)kB3EpiWarps * L.NT * 4;
+  const uint32_t nf = 2u * L.NP + 16u * L.NT + 64;
+  const uint32_t budget = 227u * 1024u - 1024u;
+  L.NSP = 3;
+  for (;;) {
+    uint32_t p1_end = L.NSP * L.slotP;
+    const uint32_t reach = (L.NSP - 1) * L.slotP + 256u * 128u;          // M block 1 of the last P1 slot
+    if (reach > p1_end) p1_end = reach;
+    uint32_t dl0 = L.off_ring4 + 2 * L.slot4;
+    if (p1_end + ldp > dl0) dl0 = p1_end + ldp;
+    dl0 = (dl0 + 127) & ~127u;
+    uint32_t end = dl0 + 2 * L.dlb;
+    // scratch of E3' (column partials [2][8][NT], row partials [2][NP]) lives in the dead dLhat region
+    const uint32_t e3 = (16u * L.NT + 2u * L.NP) * 4;
+    if (dl0 + e3 > end) end = dl0 + e3;
+    if (L.off_ring4 + 3 * L.slot4 > end) end = L.off_ring4 + 3 * L.slot4;
+    L.off_dl = dl0; L.off_ldp = dl0 - ldp;
+    L.off_f = (end + 127) & ~127u;
+    L.off_bar = (L.off_f + 4 * nf + 7) & ~7u;
+    L.total = L.off_bar + 8 * 32;
+    if (L.total <= budget || L.NSP == 2) break;
+    L.NSP = 2;
+  }
+  return L;
+}
+
+struct Bwd3Params {
+  long long* prof;
+  int P, T, D;
+  float thr, scale;
+  const uint8_t* mask;
+  const float* inv_vn;
+  const float* inv_ln;
+  const float* lse_row;
+  const float* lse_col;
+  const float* coef;
+  const float* tt_logits;   // [B][T][T] masked, scaled logits from the forward
+  const float* g_inv_norm;  // [B][T]
+  const float* stats;       // [B][T][4] min, 1/range, sigma, arg-min patch
+  const float* dpool_v;
+  const float* dpool_l;
+  const bf16* v;
+  const bf16* l;
+  bf16* dv;
+  bf16* dl;
+};
+
+__device__ __forceinline__ void b3_epi_bar() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
+__device__ __forceinline__ float b3_raw(const bf16* p) { return __bfloat162float(*p); }
+
+template <bool kHalf>
+__global__ void __launch_bounds__(kB3Threads, 1)
+sparc_bwd3_kernel(const __grid_constant__ CUtensorMap tmV0, const __grid_constant__ CUtensorMap tmV1,
+                  const __grid_constant__ CUtensorMap tmL, const __grid_constant__ CUtensorMap tmG, const Bwd3Params p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* base = CFA_SMEM_BASE_1024(smem_raw);
+  const Bwd3Layout L = bwd3_layout(p.P, p.T, p.D);
+  const int NP = L.NP, NT = L.NT, MB = L.MB, KB0 = L.KB0, NSP = L.NSP, P = p.P, T = p.T, D = p.D;
+  const int NT2 = 2 * NT, NT3 = 3 * NT;
+  const int b = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  uint8_t* SR = base + L.off_sr;                      // S_raw^T hi|lo, later dShat'^T hi|lo : [2 NT / 8][NP][8]
+  uint8_t* WT = base + L.off_w;                       // W^T hi|lo, later (-gfac W)^T hi|lo
+  uint8_t* ringP = base;                              // P1 slots [v tile | l tile | G hi tile | G lo tile]
+  uint8_t* ring4 = base + L.off_ring4;                // P4 slots: v chunk pair, or l / G hi / G lo tile pair
+  uint8_t* DLh = base + L.off_dl;                     // dLhat hi, lo : [NT / 8][NT][8] each
+  uint8_t* DLl = DLh + L.dlb;
+  float* ldpart = (float*)(base + L.off_ldp);         // [16][NT] phase-0 column partials
+  float* part_c = (float*)(base + L.off_dl);          // E3' scratch in the dead dLhat region: [8][NT] sum of kept dW
+  float* part_d = part_c + 8 * NT;                    //                                       [8][NT] sum of ds * s
+  float* vqp = part_d + 8 * NT;                       //                                       [2][NP] row partials
+  float* ivn = (float*)(base + L.off_f);              // [NP]
+  float* vfac = ivn + NP;                             // [NP]
+  float* iln = vfac + NP;                             // [NT] ...
+  float* msk = iln + NT;
+  float* lser = msk + NT;
+  float* lsec = lser + NT;
+  float* mnf = lsec + NT;
+  float* irf = mnf + NT;
+  float* sgm = irf + NT;                              // sigma
+  float* isgm = sgm + NT;                             // 1 / sigma, 0 for masked tokens
+  float* ignv = isgm + NT;
+  float* gfacs = ignv + NT;
+  float* ldot = gfacs + NT;
+  float* lfacs = ldot + NT;
+  float* dmns = lfacs + NT;
+  float* fixv = dmns + NT;
+  int* imn = (int*)(fixv + NT);
+  uint64_t* bars = (uint64_t*)(base + L.off_bar);
+  uint64_t* fullP = bars;           // [3]
+  uint64_t* emptyP = bars + 3;      // [3]
+  uint64_t* full4 = bars + 6;       // [3]
+  uint64_t* empty4 = bars + 9;      // [3]
+  uint64_t* s_full = bars + 12;
+  uint64_t* dl_ready = bars + 13;
+  uint64_t* e1_ready = bars + 14;
+  uint64_t* dw_full = bars + 15;
+  uint64_t* ds_ready = bars + 16;
+  uint64_t* oa_full = bars + 17;
+  uint64_t* oa_free = bars + 18;
+  uint64_t* ob_full = bars + 19;
+  uint64_t* ob_free = bars + 20;
+  uint32_t* tmem_slot = (uint32_t*)(bars + 22);
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 3; ++i) { mbar_init(fullP + i, 1); mbar_init(emptyP + i, 1); mbar_init(full4 + i, 1); mbar_init(empty4 + i, 1); }
+    mbar_init(s_full, 1); mbar_init(dl_ready, kB3EpiWarps); mbar_init(e1_ready, kB3EpiWarps); mbar_init(dw_full, 1);
+    mbar_init(ds_ready, kB3EpiWarps);
+    mbar_init(oa_full, 1); mbar_init(oa_free, kB3EpiWarps); mbar_init(ob_full, 1); mbar_init(ob_free, kB3EpiWarps);
+    fence_barrier_init();
+    tma_prefetch_desc(&tmV0); tma_prefetch_desc(&tmV1); tma_prefetch_desc(&tmL); tma_prefetch_desc(&tmG);
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  for (int i = threadIdx.x; i < NP + NT; i += kB3Threads) {
+    if (i < NP) ivn[i] = (i < P) ? p.inv_vn[(size_t)b * P + i] : 0.f;
+    else {
+      const int t = i - NP;
+      const bool in = t < T;
+      const bool on = in && p.mask[(size_t)b * T + t];
+      iln[t] = in ? p.inv_ln[(size_t)b * T + t] : 0.f;
+      msk[t] = on ? 1.f : 0.f;
+      lser[t] = in ? p.lse_row[(size_t)b * T + t] : 0.f;
+      lsec[t] = in ? p.lse_col[(size_t)b * T + t] : 0.f;
+      ignv[t] = in ? p.g_inv_norm[(size_t)b * T + t] : 0.f;
+      float4 st4 = make_float4(0.f, 0.f, 1.f, __int_as_float(0x7fffffff));
+      if (in) st4 = __ldg(reinterpret_cast<const float4*>(p.stats + ((size_t)b * T + t) * 4));
+      mnf[t] = st4.x; irf[t] = st4.y; sgm[t] = st4.z; isgm[t] = on ? 1.f / st4.z : 0.f; imn[t] = __float_as_int(st4.w);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t cDL = 0, cDV = (uint32_t)NT2;        // P4 accumulators
+
+  if (warp == 0) {
+    // =============================== TMA producer ===============================
+    if (lane == 0) {
+      for (int u = 0; u < KB0; ++u) {                  // P1: v | l | G hi | G lo
+        const int s = u % NSP;
+        if (u >= NSP) mbar_wait(emptyP + s, ((u / NSP) - 1) & 1);
+        uint8_t* st = ringP + (size_t)s * L.slotP;
+        mbar_expect_tx(fullP + s, L.slotP);
+        tma_load_3d(st, &tmV0, fullP + s, u * 64, 0, b);
+        tma_load_3d(st + L.v_bytes, &tmL, fullP + s, u * 64, 0, b);
+        tma_load_3d(st + L.v_bytes + L.l_bytes, &tmG, fullP + s, u * 64, 0, 2 * b);
+        tma_load_3d(st + L.v_bytes + 2 * L.l_bytes, &tmG, fullP + s, u * 64, 0, 2 * b + 1);
+      }
+      // P4 slots 0, 1 overlap the P1 ring and the phase-0 scratch; slot 2 overlaps dLhat and the E3' scratch
+      mbar_wait(s_full, 0);
+      mbar_wait(dl_ready, 0);
+      const int per = L.NCH + 3, n4 = L.NBLK * per;
+      for (int i = 0; i < n4; ++i) {
+        const int s = i % 3, blk = i / per, w = i % per;
+        if (i >= 3) mbar_wait(empty4 + s, ((i / 3) - 1) & 1);
+        if (i == 2) mbar_wait(ds_ready, 0);
+        uint8_t* st = ring4 + (size_t)s * L.slot4;
+        if (w < L.NCH) {
+          mbar_expect_tx(full4 + s, 2u * L.CR0 * 128);
+          tma_load_3d(st, &tmV1, full4 + s, blk * 128, w * L.CR0, b);
+          tma_load_3d(st + L.CR0 * 128, &tmV1, full4 + s, blk * 128 + 64, w * L.CR0, b);
+        } else {
+          const CUtensorMap* tm = (w == L.NCH) ? &tmL : &tmG;
+          const int pl = (w == L.NCH) ? b : (w == L.NCH + 1 ? 2 * b : 2 * b + 1);
+          mbar_expect_tx(full4 + s, 2 * L.l_bytes);
+          tma_load_3d(st, tm, full4 + s, blk * 128, 0, pl);
+          tma_load_3d(st + L.l_bytes, tm, full4 + s, blk * 128 + 64, 0, pl);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =============================== MMA issuer (warp-uniform control flow, one elected lane issues) ===============================
+    const bool leader = elect_one();
+    const uint32_t id_p1 = make_idesc16(128, NT3, false, false, kHalf, kHalf);      // raw v x [l ; G hi ; G lo], all K-major
+    const uint32_t id_dw = make_idesc16(128, NT, false, false, false, false);      // S_raw^T (K-major) x dLhat (K-major: N = t)
+    const uint32_t id_z = make_idesc16(128, NT, false, true, false, false);        // W^T (K-major) x dLhat (MN-major: N = j)
+    const uint32_t id_dl = make_idesc16(128, NT2, true, true, kHalf, false);       // raw v^T (MN-major) x dShat'^T hi|lo (MN-major)
+    const uint32_t id_dv = make_idesc16(128, NP, true, false, kHalf, false);       // raw l^T (MN-major) x dShat' (K-major: N = p)
+    const uint32_t id_dg = make_idesc16(128, NP, true, false, false, false);       // G^T (MN-major, bf16) x -gfac W (K-major)
+    const uint64_t sw0 = make_smem_desc(0, 16, 1024, kLayoutSw128);
+    long long* pf = (p.prof && leader) ? p.prof + (size_t)b * 32 : nullptr;
+    int pi = 0;
+    auto stamp = [&]() { if (pf) pf[pi++] = clock64(); };
+    stamp();
+    // ---- P1
+    for (int u = 0; u < KB0; ++u) {
+      const int s = u % NSP;
+      mbar_wait(fullP + s, (u / NSP) & 1);
+      tc_fence_after();
+      const uint32_t sv = smem_u32(ringP + (size_t)s * L.slotP), sb = sv + L.v_bytes;
+      const uint64_t dv0 = sw0 | (sv >> 4), db0 = sw0 | (sb >> 4);
+      for (int mb = 0; mb < MB; ++mb) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_ss_w(leader, tmem + mb * NT3, dv0 + mb * (16384 >> 4) + 2 * k, db0 + 2 * k, id_p1, (u | k) != 0);
+      }
+      umma_commit_w(leader, emptyP + s);
+    }
+    umma_commit_w(leader, s_full);
+    stamp();
+    // ---- M: dW^T (on top of the parked -gfac Q) and Z^T
+    mbar_wait(dl_ready, 0);
+    mbar_wait(e1_ready, 0);
+    tc_fence_after();
+    stamp();
+    const uint32_t np16 = (uint32_t)NP * 16, nt16 = (uint32_t)NT * 16;
+    // interleaved [k/8][rows][8] operands: K-major: LBO = rows * 16, SBO = 128; MN-major: LBO = 128, SBO = rows * 16
+    const uint64_t k_srh = make_smem_desc(smem_u32(SR), np16, 128, kLayoutNone), k_srl = make_smem_desc(smem_u32(SR) + L.plane, np16, 128, kLayoutNone);
+    const uint64_t k_wh = make_smem_desc(smem_u32(WT), np16, 128, kLayoutNone), k_wl = make_smem_desc(smem_u32(WT) + L.plane, np16, 128, kLayoutNone);
+    const uint64_t k_dlh = make_smem_desc(smem_u32(DLh), nt16, 128, kLayoutNone), k_dll = make_smem_desc(smem_u32(DLl), nt16, 128, kLayoutNone);
+    const uint64_t m_dlh = make_smem_desc(smem_u32(DLh), 128, nt16, kLayoutNone), m_dll = make_smem_desc(smem_u32(DLl), 128, nt16, kLayoutNone);
+    const uint32_t ksA = (2 * np16) >> 4;              // K-major interleaved with NP rows: two 8-wide chunks per k-step
+    const uint32_t ksB = (2 * nt16) >> 4;              // K-major interleaved with NT rows
+    const uint32_t mtile = (128u * 16u) >> 4;          // second 128-row M block of a K-major interleaved operand
+    const int nksT = NT / 16, nksP = NP / 16;
+    for (int mb = 0; mb < MB; ++mb) {
+      const uint32_t dw = tmem + mb * NT3 + NT, dz = tmem + mb * NT3 + NT2;
+      const uint32_t mo = mb * mtile;
+      for (int ks = 0; ks < nksT; ++ks) umma_ss_w(leader, dw, k_srh + mo + ks * ksA, k_dlh + ks * ksB, id_dw, true);
+      for (int ks = 0; ks < nksT; ++ks) umma_ss_w(leader, dw, k_srh + mo + ks * ksA, k_dll + ks * ksB, id_dw, true);
+      for (int ks = 0; ks < nksT; ++ks) umma_ss_w(leader, dw, k_srl + mo + ks * ksA, k_dlh + ks * ksB, id_dw, true);
+      for (int ks = 0; ks < nksT; ++ks) umma_ss_w(leader, dz, k_wh + mo + ks * ksA, m_dlh + ks * 16, id_z, ks != 0);
+      for (int ks = 0; ks < nksT; ++ks) umma_ss_w(leader, dz, k_wh + mo + ks * ksA, m_dll + ks * 16, id_z, true);
+      for (int ks = 0; ks < nksT; ++ks) umma_ss_w(leader, dz, k_wl + mo + ks * ksA, m_dlh + ks * 16, id_z, true);
+    }
+    umma_commit_w(leader, dw_full);
+    // ---- P4
+    mbar_wait(ds_ready, 0);
+    tc_fence_after();
+    stamp();
+    const uint64_t m_ds = make_smem_desc(smem_u32(SR), 128, np16, kLayoutNone);          // dShat'^T hi|lo, MN-major (N = t, K = p)
+    int i4 = 0;
+    for (int blk = 0; blk < L.NBLK; ++blk) {
+      // unit A: dl^T
+      mbar_wait(oa_free, (blk & 1) ^ 1);
+      tc_fence_after();
+      for (int ch = 0; ch < L.NCH; ++ch, ++i4) {
+        const int s = i4 % 3;
+        mbar_wait(full4 + s, (i4 / 3) & 1);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(ring4 + (size_t)s * L.slot4);
+        const uint64_t da = make_smem_desc(sa, (uint32_t)L.CR0 * 128, 1024, kLayoutSw128);
+        const int r0 = ch * L.CR0, nk = (ch == 0 ? L.CR0 : NP - L.CR0) / 16;
+        const uint64_t db = m_ds + (uint32_t)r0;
+        for (int ks = 0; ks < nk; ++ks) umma_ss_w(leader, tmem + cDL, da + ks * 128, db + ks * 16, id_dl, (ch | ks) != 0);
+        umma_commit_w(leader, empty4 + s);
+      }
+      umma_commit_w(leader, oa_full);
+      // unit B: dv^T
+      mbar_wait(ob_free, (blk & 1) ^ 1);
+      tc_fence_after();
+      for (int w = 0; w < 3; ++w, ++i4) {
+        const int s = i4 % 3;
+        mbar_wait(full4 + s, (i4 / 3) & 1);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(ring4 + (size_t)s * L.slot4);
+        const uint64_t da = make_smem_desc(sa, L.l_bytes, 1024, kLayoutSw128);             // [NT x 64] tile pair, MN-major (M = d)
+        if (w == 0) {
+          for (int ks = 0; ks < nksT; ++ks) umma_ss_w(leader, tmem + cDV, da + ks * 128, k_srh + ks * ksA, id_dv, ks != 0);
+          for (int ks = 0; ks < nksT; ++ks) umma_ss_w(leader, tmem + cDV, da + ks * 128, k_srl + ks * ksA, id_dv, true);
+        } else if (w == 1) {
+          for (int ks = 0; ks < nksT; ++ks) umma_ss_w(leader, tmem + cDV, da + ks * 128, k_wh + ks * ksA, id_dg, true);
+          for (int ks = 0; ks < nksT; ++ks) umma_ss_w(leader, tmem + cDV, da + ks * 128, k_wl + ks * ksA, id_dg, true);
+        } else {
+          for (int ks = 0; ks < nksT; ++ks) umma_ss_w(leader, tmem + cDV, da + ks * 128, k_wh + ks * ksA, id_dg, true);
+        }
+        umma_commit_w(leader, empty4 + s);
+      }
+      umma_commit_w(leader, ob_full);
+    }
+    (void)nksP;
+    stamp();
+  } else {
+    // =============================== epilogue: 16 warps = 4 TMEM lane quarters x 4 groups ===============================
+    const int ew = warp - 2, q = warp & 3, grp = ew >> 2;
+    const uint32_t tq = tmem + ((uint32_t)(32 * q) << 16);
+    const int tid = ew * 32 + lane;
+    const float c_r = p.coef[0], c_c = p.coef[1];
+    long long* pf = (p.prof && tid == 0) ? p.prof + (size_t)b * 32 + 16 : nullptr;
+    int pi = 0;
+    auto stamp = [&]() { if (pf) pf[pi++] = clock64(); };
+    stamp();
+
+    // ---- phase 0 (overlaps P1): saved T x T logits -> dLhat (hi|lo operand [j/8][t][j%8]), gfac_t, ldot_j.
+    // A warp covers rpp rows at a time: lane -> (row slot rs, 8-column chunk jc); fixed-order sums (deterministic bits).
+    {
+      const int nch = NT / 8, rpp = 32 / nch;
+      const int rs = lane / nch, jc = lane - rs * nch;
+      const bool lact = rs < rpp;
+      float cs[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) cs[k] = 0.f;
+      for (int t0 = ew * rpp; t0 < NT; t0 += kB3EpiWarps * rpp) {
+        const int t = t0 + rs;
+        const bool tact = lact && t < NT;
+        const bool vt = tact && t < T && msk[t] != 0.f;
+        float y[8], x[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) y[k] = 0.f;
+        if (vt) {
+          const float* src = p.tt_logits + ((size_t)b * T + t) * T + 8 * jc;
+#pragma unroll
+          for (int k = 0; k < 8; ++k) if (8 * jc + k < T) y[k] = __ldg(src + k);
+        }
+        const float lr = tact ? lser[t] : 0.f, ig = tact ? ignv[t] : 0.f;
+        float gd = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const int j = 8 * jc + k;
+          const bool on = vt && j < T && msk[j] != 0.f;
+          const float yy = on ? y[k] : 0.f;
+          float g = c_r * __expf(fminf(yy - lr, 0.f)) + c_c * __expf(fminf(yy - lsec[j], 0.f));
+          g -= (j == t) ? (c_r + c_c) : 0.f;
+          g = on ? g : 0.f;
+          const float pr = g * yy;
+          gd += pr;
+          cs[k] += pr;
+          x[k] = p.scale * g * ig * iln[j];
+        }
+        if (tact) {
+          uint4 hi, lo;
+          split_hilo8(x, hi, lo);
+          const uint32_t off = (uint32_t)(jc * NT + t) * 16;
+          *reinterpret_cast<uint4*>(DLh + off) = hi;
+          *reinterpret_cast<uint4*>(DLl + off) = lo;
+        }
+        // row sum over the nch chunk lanes of this row slot (fixed order)
+        float tot = 0.f;
+        for (int k = 0; k < nch; ++k) tot += __shfl_sync(0xffffffffu, gd, (rs < rpp ? rs : 0) * nch + k);
+        if (tact && jc == 0) gfacs[t] = tot * ig * ig;           // (g^_t . dg^_t) / ||G_t||^2
+      }
+      // column partials of this warp: add the rpp row slots in fixed order, then one slot per warp
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        float tot = 0.f;
+        for (int r = 0; r < rpp; ++r) tot += __shfl_sync(0xffffffffu, cs[k], r * nch + (lane < nch ? lane : 0));
+        if (lane < nch) ldpart[ew * NT + 8 * lane + k] = tot;
+      }
+      b3_epi_bar();
+      if (tid < NT) {
+        float s = 0.f;
+        for (int w = 0; w < kB3EpiWarps; ++w) s += ldpart[w * NT + tid];
+        ldot[tid] = s;
+      }
+      fence_proxy_async();
+      b3_epi_bar();
+      if (lane == 0) mbar_arrive(dl_ready);
+    }
+    stamp();
+
+    // ---- E1: thread = patch.  S^T -> W^T (hi|lo), S_raw^T (hi|lo); -gfac Q parked in the dW^T columns
+    const int mb = grp & 1, chh = grp >> 1;
+    const int prow = 128 * mb + 32 * q + lane;
+    const bool e_act = mb < MB;
+    const bool live = e_act && prow < P;
+    const float ivp = (e_act && prow < NP) ? ivn[prow] : 0.f;
+    const int cw = NT / 2, c_lo = chh * cw;
+    const int combo = mb * 4 + q;
+    const uint32_t tS = tq + mb * NT3, tW = tS + NT, tZ = tS + NT2;
+    mbar_wait(s_full, 0);
+    tc_fence_after();
+    stamp();
+    if (e_act) {
+      for (int c0 = c_lo; c0 < c_lo + cw; c0 += 8) {
+        float x[8], qh[8], ql[8], w[8];
+        tmem_ld8(tS + c0, x);
+        tmem_ld8(tW + c0, qh);
+        tmem_ld8(tZ + c0, ql);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int t = c0 + j;
+          const bool in = live && msk[t] != 0.f;
+          const float nn = (x[j] * ivp * iln[t] - mnf[t]) * irf[t];
+          w[j] = (in && !(nn < p.thr)) ? nn * isgm[t] : 0.f;
+          x[j] = in ? x[j] : 0.f;
+          qh[j] = in ? -gfacs[t] * (qh[j] + ql[j]) : 0.f;
+        }
+        if (prow < NP) {
+          uint4 hi, lo;
+          const uint32_t off = (uint32_t)((c0 >> 3) * NP + prow) * 16;
+          split_hilo8(w, hi, lo);
+          *reinterpret_cast<uint4*>(WT + off) = hi;
+          *reinterpret_cast<uint4*>(WT + L.plane + off) = lo;
+          split_hilo8(x, hi, lo);
+          *reinterpret_cast<uint4*>(SR + off) = hi;
+          *reinterpret_cast<uint4*>(SR + L.plane + off) = lo;
+        }
+        tmem_st8(tW + c0, qh);
+      }
+      tmem_st_wait();
+    }
+    tc_fence_before();
+    fence_proxy_async();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(e1_ready);
+    stamp();
+
+    // ---- E3': dW -> renorm / threshold / min-max backward -> dShat'^T = dShat^T + Z^T (hi|lo), (-gfac W)^T (hi|lo), lfac, vfac
+    // One sweep, with the two identities of sparc_bwd2:  sum_p W dW = 0  and  sum_p dN N = 0  (only the arg-min patch
+    // receives a scatter term, patched in afterwards).
+    mbar_wait(dw_full, 0);
+    tc_fence_after();
+    stamp();
+    float vq = 0.f;
+    if (e_act) {
+      for (int c0 = c_lo; c0 < c_lo + cw; c0 += 8) {
+        float x[8], dw[8], z[8], pr[8], wg[8];
+        tmem_ld8(tS + c0, x);
+        tmem_ld8(tW + c0, dw);
+        tmem_ld8(tZ + c0, z);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int t = c0 + j;
+          const bool in = live && msk[t] != 0.f;
+          const float s = x[j] * ivp * iln[t];
+          const float nn = (s - mnf[t]) * irf[t];
+          const bool kept = in && !(nn < p.thr);
+          const float d = kept ? dw[j] : 0.f;            // phantom lanes may hold NaN/Inf: select, never 0 * x
+          dw[j] = d;
+          const float ds = (d * isgm[t]) * irf[t];
+          const float prod = kept ? ds * s : 0.f;
+          pr[j] = prod;
+          vq += prod;
+          x[j] = in ? fmaf(ds * iln[t], ivp, z[j]) : 0.f;                 // dShat' = dShat + Z
+          wg[j] = kept ? -gfacs[t] * (nn * isgm[t]) : 0.f;                // -gfac W
+        }
+        if (prow < NP) {
+          uint4 hi, lo;
+          const uint32_t off = (uint32_t)((c0 >> 3) * NP + prow) * 16;
+          split_hilo8(x, hi, lo);
+          *reinterpret_cast<uint4*>(SR + off) = hi;
+          *reinterpret_cast<uint4*>(SR + L.plane + off) = lo;
+          split_hilo8(wg, hi, lo);
+          *reinterpret_cast<uint4*>(WT + off) = hi;
+          *reinterpret_cast<uint4*>(WT + L.plane + off) = lo;
+        }
+        const float c1 = warp_colsum8(dw, lane);
+        const float c2 = warp_colsum8(pr, lane);
+        if ((lane & 17) == 0) { part_c[combo * NT + c0 + (lane >> 1)] = c1; part_d[combo * NT + c0 + (lane >> 1)] = c2; }
+      }
+    }
+    b3_epi_bar();
+    if (tid < NT) {
+      float cx = 0.f, sd = 0.f;
+      for (int w = 0; w < 4 * MB; ++w) { cx += part_c[w * NT + tid]; sd += part_d[w * NT + tid]; }
+      const bool valid = msk[tid] != 0.f;
+      const float dmn = valid ? -cx * isgm[tid] * irf[tid] : 0.f;
+      dmns[tid] = dmn;
+      fixv[tid] = dmn * mnf[tid];                       // ds[imn] * s[imn], s[imn] = min
+      lfacs[tid] = (sd + dmn * mnf[tid] + ldot[tid]) * iln[tid] * iln[tid];      // (l^_t . dl^_t) / ||l_t||^2
+    }
+    b3_epi_bar();
+    if (e_act) {
+      for (int t = c_lo; t < c_lo + cw; ++t) {
+        if (imn[t] == prow && msk[t] != 0.f && live) {  // this thread owns the arg-min element of token t
+          const uint32_t off = (uint32_t)((t >> 3) * NP + prow) * 16 + (t & 7) * 2;
+          bf16* ph = reinterpret_cast<bf16*>(SR + off);
+          bf16* pl = reinterpret_cast<bf16*>(SR + L.plane + off);
+          const float f = (__bfloat162float(*ph) + __bfloat162float(*pl)) + dmns[t] * iln[t] * ivp;
+          const bf16 nh = __float2bfloat16_rn(f);
+          *ph = nh;
+          *pl = __float2bfloat16_rn(f - __bfloat162float(nh));
+          vq += fixv[t];
+        }
+      }
+      if (prow < NP) vqp[chh * NP + prow] = vq;
+    }
+    b3_epi_bar();
+    for (int i = tid; i < NP; i += 512) vfac[i] = (vqp[i] + vqp[NP + i]) * ivn[i] * ivn[i];
+    tc_fence_before();
+    fence_proxy_async();
+    b3_epi_bar();
+    if (lane == 0) mbar_arrive(ds_ready);
+    stamp();
+
+    // ---- P4 outputs: thread = feature column d of the block; group -> a quarter of the token / patch columns
+    float cnt = 0.f;
+    for (int t = 0; t < T; ++t) cnt += msk[t];
+    const float invc = 1.f / fmaxf(cnt, kB3ClampEps), invP = 1.f / (float)P;
+    const int tw = NT / 4, t_lo = grp * tw;              // multiple of 4
+    const int pw = NP / 4, p_lo = grp * pw;              // multiple of 4
+    const int dloc = 32 * q + lane;
+    for (int blk = 0; blk < L.NBLK; ++blk) {
+      const size_t dcol = (size_t)blk * 128 + dloc;
+      const float dpl = p.dpool_l ? __ldg(p.dpool_l + (size_t)b * D + dcol) * invc : 0.f;
+      const float dpv = p.dpool_v ? __ldg(p.dpool_v + (size_t)b * D + dcol) * invP : 0.f;
+      {   // unit A: dl[t][d] = dl^T[d][t] (hi-part + lo-part) - l[t][d] lfac_t + m_t dlbar[d] / cnt
+        const bf16* lsrc = p.l + (size_t)b * T * D + dcol;
+        bf16* ldst = p.dl + (size_t)b * T * D + dcol;
+        float raw[20];
+#pragma unroll
+        for (int k = 0; k < 20; ++k) raw[k] = (k < tw && t_lo + k < T) ? b3_raw(lsrc + (size_t)(t_lo + k) * D) : 0.f;
+        mbar_wait(oa_full, blk & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int c = 0; c < 20; c += 4) {
+          if (c < tw) {
+            float xh[4], xl[4];
+            tmem_ld4(tq + cDL + t_lo + c, xh);
+            tmem_ld4(tq + cDL + NT + t_lo + c, xl);
+            tmem_ld_wait();
+            if (c + 4 >= tw) {                           // last chunk: the accumulator is in registers
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(oa_free);
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const int t = t_lo + c + k;
+              if (t < T) {
+                const float o = fmaf(msk[t], dpl, fmaf(-raw[c + k], lfacs[t], xh[k] + xl[k]));
+                ldst[(size_t)t * D] = __float2bfloat16_rn(o);
+              }
+            }
+          }
+        }
+      }
+      {   // unit B: dv[p][d] = dv^T[d][p] - v[p][d] vfac_p + dvbar[d] / P
+        const bf16* vsrc = p.v + (size_t)b * P * D + dcol;
+        bf16* vdst = p.dv + (size_t)b * P * D + dcol;
+        float rawc[8], rawn[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) rawc[k] = (k < pw && p_lo + k < P) ? b3_raw(vsrc + (size_t)(p_lo + k) * D) : 0.f;
+        mbar_wait(ob_full, blk & 1);
+        tc_fence_after();
+        for (int c0 = 0; c0 < pw; c0 += 8) {
+          float x[8];
+          if (c0 + 8 <= pw) tmem_ld8(tq + cDV + p_lo + c0, x);
+          else tmem_ld4(tq + cDV + p_lo + c0, x);       // pw is a multiple of 4
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const int pn = p_lo + c0 + 8 + k;
+            rawn[k] = (c0 + 8 + k < pw && pn < P) ? b3_raw(vsrc + (size_t)pn * D) : 0.f;
+          }
+          tmem_ld_wait();
+          if (c0 + 8 >= pw) {                           // last chunk: the accumulator is in registers
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(ob_free);
+          }
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const int pc = p_lo + c0 + k;
+            if (c0 + k < pw && pc < P) {
+              const float o = fmaf(-rawc[k], vfac[pc], x[k]) + dpv;
+              vdst[(size_t)pc * D] = __float2bfloat16_rn(o);
+            }
+          }
+#pragma unroll
+          for (int k = 0; k < 8; ++k) rawc[k] = rawn[k];
+        }
+      }
+    }
+    stamp();
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem, 512); }
+}
+
+bool sparc_bwd3_supported(int P, int T, int D, int dtype) {
+  if (dtype != CFA_DTYPE_BF16) return false;
+  if (P < 1 || P > 256 || T < 1 || T > 80 || D % 128 || D < 128) return false;
+  const Bwd3Layout L = bwd3_layout(P, T, D);
+  return L.total + 1024 <= 227 * 1024;
+}
+
+int sparc_bwd3_launch(const void* v, const void* l, const uint8_t* mask, int B, int P, int T, int D, float thr, float scale,
+                      const float* row_inv_norm, const float* lse_row, const float* lse_col, const float* coef,
+                      const float* tt_logits, const float* g_inv_norm, const void* g_split, const float* stats,
+                      const float* dpv, const float* dpl, void* dv, void* dl, long long* prof, int dtype, cudaStream_t st) {
+  if (dtype != CFA_DTYPE_BF16) return CFA_ERR_UNSUPPORTED;
+  if (!g_split || !stats || !tt_logits || !g_inv_norm) return CFA_ERR_WORKSPACE;
+  const Bwd3Layout L = bwd3_layout(P, T, D);
+  CUtensorMap tmV0, tmV1, tmL, tmG;
+  int rc;
+  if ((rc = make_tmap_bf16_3d(&tmV0, v, D, P, B, 64, L.NP)) != CFA_OK) return rc;
+  if ((rc = make_tmap_bf16_3d(&tmV1, v, D, P, B, 64, L.CR0)) != CFA_OK) return rc;
+  if ((rc = make_tmap_bf16_3d(&tmL, l, D, T, B, 64, L.NT)) != CFA_OK) return rc;
+  if ((rc = make_tmap_bf16_3d(&tmG, g_split, D, T, 2 * (uint64_t)B, 64, L.NT)) != CFA_OK) return rc;
+  Bwd3Params prm{prof, P, T, D, thr, scale, mask, row_inv_norm, row_inv_norm + (size_t)B * P, lse_row, lse_col, coef,
+                 tt_logits, g_inv_norm, stats, dpv, dpl, (const bf16*)v, (const bf16*)l, (bf16*)dv, (bf16*)dl};
+  const size_t smem = L.total + 1024;
+  CFA_CUDA_TRY(cudaFuncSetAttribute(sparc_bwd3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  sparc_bwd3_kernel<false><<<B, kB3Threads, smem, st>>>(tmV0, tmV1, tmL, tmG, prm);
+  return launch_status();
+}
+
+}  // namespace cfa

@@ -14,7 +14,7 @@ tc_selftest_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   extern __shared__ uint8_t smem_raw[];
   uint8_t* base = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* As = base;                 // 64 KB
-  uint8_t* Bs = base + 65536;         // 64 KB
+  uint8_t* Bs = base + 65536;         // 96 KB
   __shared__ uint64_t bar_tma, bar_mma;
   __shared__ uint32_t tmem_base_s;
   const int tid = threadIdx.x, warp = tid >> 5;
@@ -34,6 +34,7 @@ tc_selftest_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   uint32_t tx_bytes = 0;
   if (a_mode == 0) tx_bytes += (K / 64) * 16384;
   if (a_mode == 4) tx_bytes += (K / 32) * 8192;
+  if (a_mode == 3) tx_bytes += 2 * K * 128;
   if (b_mode == 0) tx_bytes += (K / 64) * N * 128;
   if (b_mode == 1) tx_bytes += K * 128;
   if (b_mode == 4) tx_bytes += (K / 32) * N * 64;
@@ -41,6 +42,7 @@ tc_selftest_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   if (tid == 0 && tx_bytes) {
     mbar_expect_tx(&bar_tma, tx_bytes);
     if (a_mode == 0) for (int kb = 0; kb < K / 64; ++kb) tma_load_3d(As + kb * 16384, &tmA, &bar_tma, kb * 64, 0, 0);
+    if (a_mode == 3) { tma_load_3d(As, &tmA, &bar_tma, 0, 0, 0); tma_load_3d(As + K * 128, &tmA, &bar_tma, 64, 0, 0); }
     if (b_mode == 0) for (int kb = 0; kb < K / 64; ++kb) tma_load_3d(Bs + kb * N * 128, &tmB, &bar_tma, kb * 64, 0, 0);
     if (b_mode == 1) tma_load_3d(Bs, &tmB, &bar_tma, 0, 0, 0);
     if (a_mode == 4) for (int kb = 0; kb < K / 32; ++kb) tma_load_3d(As + kb * 8192, &tmA, &bar_tma, kb * 32, 0, 0);
@@ -65,13 +67,15 @@ tc_selftest_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   // ---- issue: warp 0, warp-uniform control flow, descriptors advanced by adds on the start-address field
   if (warp == 0) {
     const bool leader = elect_one();
-    const uint32_t idesc = make_idesc_bf16(128, N, a_mode == 2, b_mode == 1 || b_mode == 3 || b_mode == 5);
+    const uint32_t idesc = make_idesc_bf16(128, N, a_mode == 2 || a_mode == 3, b_mode == 1 || b_mode == 3 || b_mode == 5);
     // per k-step increments (units of 16 B) and per-K-block jumps for the TMA-tiled flavours
     uint64_t da0, db0;
     uint32_t a_ks, b_ks, a_blk = 0, b_blk = 0, a_per = 1 << 30, b_per = 1 << 30;
     if (a_mode == 0) { da0 = make_smem_desc(smem_u32(As), 16, 1024, kLayoutSw128); a_ks = 2; a_per = 4; a_blk = 16384 >> 4; }
     else if (a_mode == 4) { da0 = make_smem_desc(smem_u32(As), 16, 512, kLayoutSw64); a_ks = 2; a_per = 2; a_blk = 8192 >> 4; }
     else if (a_mode == 1) { da0 = make_smem_desc(smem_u32(As), 128 * 16, 128, kLayoutNone); a_ks = (2 * 128 * 16) >> 4; }
+    // At [K x 128] as two TMA sub-tiles [K x 64] (SWIZZLE_128B) read MN-major: LBO = distance between the two 64-wide atoms
+    else if (a_mode == 3) { da0 = make_smem_desc(smem_u32(As), (uint32_t)K * 128, 1024, kLayoutSw128); a_ks = 2048 >> 4; }
     else { da0 = make_smem_desc(smem_u32(As), 128, K * 16, kLayoutNone); a_ks = 256 >> 4; }
     if (b_mode == 0) { db0 = make_smem_desc(smem_u32(Bs), 16, 1024, kLayoutSw128); b_ks = 2; b_per = 4; b_blk = (N * 128) >> 4; }
     else if (b_mode == 4) { db0 = make_smem_desc(smem_u32(Bs), 16, 512, kLayoutSw64); b_ks = 2; b_per = 2; b_blk = (N * 64) >> 4; }
@@ -132,17 +136,20 @@ extern "C" int cfa_tc_selftest_timed(int a_mode, int b_mode, int N, int K, const
   if ((a_mode == 4 || b_mode == 4) && K % 32) return CFA_ERR_BAD_ARG;
   if (b_mode == 1 && N != 64) return CFA_ERR_BAD_ARG;
   if (b_mode == 5 && N != 32) return CFA_ERR_BAD_ARG;
+  if (a_mode == 3 && K % 8) return CFA_ERR_BAD_ARG;
+  if ((b_mode == 2 || b_mode == 3) && (size_t)N * K * 2 > 98304) return CFA_ERR_BAD_ARG;
   CUtensorMap tmA, tmB;
   memset(&tmA, 0, sizeof(tmA));
   memset(&tmB, 0, sizeof(tmB));
   int rc;
   if (a_mode == 0 && (rc = make_tmap_bf16_3d(&tmA, A, K, 128, 1, 64, 128)) != CFA_OK) return rc;
+  if (a_mode == 3 && (rc = make_tmap_bf16_3d(&tmA, A, 128, K, 1, 64, K)) != CFA_OK) return rc;
   if (b_mode == 0 && (rc = make_tmap_bf16_3d(&tmB, B, K, N, 1, 64, N)) != CFA_OK) return rc;
   if (b_mode == 1 && (rc = make_tmap_bf16_3d(&tmB, B, 64, K, 1, 64, K)) != CFA_OK) return rc;
   if (a_mode == 4 && (rc = make_tmap_bf16_3d(&tmA, A, K, 128, 1, 32, 128)) != CFA_OK) return rc;
   if (b_mode == 4 && (rc = make_tmap_bf16_3d(&tmB, B, K, N, 1, 32, N)) != CFA_OK) return rc;
   if (b_mode == 5 && (rc = make_tmap_bf16_3d(&tmB, B, 32, K, 1, 32, K)) != CFA_OK) return rc;
-  const size_t smem = 2 * 65536 + 1024;
+  const size_t smem = 65536 + 98304 + 1024;
   CFA_CUDA_TRY(cudaFuncSetAttribute(tc_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   tc_selftest_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(tmA, tmB, (const bf16*)A, (const bf16*)B, D, a_mode, b_mode, N, K, repeat, d_cycles);
   return launch_status();

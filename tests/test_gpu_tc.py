@@ -12,7 +12,7 @@ def _run(a_mode, b_mode, N, K):
     A = torch.randn(128, K, generator=g).to(torch.bfloat16)          # logical A[m, k]
     B = torch.randn(N, K, generator=g).to(torch.bfloat16)            # logical B[n, k]
     ref = A.float() @ B.float().t()
-    a_src = (A.t().contiguous() if a_mode == 2 else A).cuda()
+    a_src = (A.t().contiguous() if a_mode in (2, 3) else A).cuda()
     b_src = (B.t().contiguous() if b_mode in (1, 3, 5) else B).cuda()
     D = torch.full((128, N), float("nan"), device="cuda")
     _lib.call("cfa_tc_selftest", a_mode, b_mode, N, K, a_src.data_ptr(), b_src.data_ptr(), D.data_ptr(),
@@ -38,6 +38,14 @@ def _run(a_mode, b_mode, N, K):
     (1, 5, 32, 80),      # X_kb = dL . l_kb
     (2, 5, 32, 80),      # dv_kb = dS^T . l_kb
     (2, 3, 32, 80),      # dv_kb += W^T . dG_kb ; dl_kb += dL^T . G_kb
+    # third-generation ("transposed") kernels: raw tiles are the A operand, on-chip hi|lo operands are stacked along N
+    (3, 3, 160, 208),    # TMA tile pair read MN-major (M = 128 d over two swizzle atoms) x interleaved MN-major (G'^T = v^T . Theta^T)
+    (3, 3, 160, 96),
+    (3, 2, 208, 80),     # l^T / G^T (MN-major TMA) x interleaved K-major, N = p                      (dv^T)
+    (2, 3, 160, 208),    # interleaved MN-major A (M = token) x interleaved MN-major B                 (L' = Theta . S_raw^T)
+    (0, 0, 240, 128),    # v tile x stacked [l; G hi; G lo] tiles                                      (backward P1)
+    (1, 2, 80, 80),      # S_raw^T (interleaved K-major) x dLhat (interleaved K-major)                 (dW^T)
+    (1, 3, 80, 80),      # W^T (interleaved K-major) x dLhat (interleaved MN-major)                    (Z^T)
 ])
 def test_tcgen05_operand_modes(a_mode, b_mode, N, K):
     D, ref = _run(a_mode, b_mode, N, K)
