@@ -18,6 +18,8 @@
 //   P4   per 128-wide D block:  dl^T[d,t] = v^T . dShat'^T   (N = 160, hi|lo stacked)
 //                               dv^T[d,p] = l^T . dShat' + G^T . (-gfac W)      (N = NP; hi, lo operands in turn)
 //        epilogue: - x fac, pooled-mean terms, bf16 -> global; thread = feature column, 64 contiguous bytes per warp store
+//
+// Template parameters kNT / kNP / kD as in the forward (0 = run-time values).
 #include "tc_common.cuh"
 #include "sparc_paths.h"
 #include <math_constants.h>
@@ -50,7 +52,7 @@ __host__ __device__ inline Bwd3Layout bwd3_layout(int P, int T, int D) {
   const uint32_t op = (2 * L.plane + 1023) & ~1023u;
   L.off_sr = 0; L.off_w = op; L.off_ring4 = 2 * op;
   const uint32_t ldp = (uint32_t)kB3EpiWarps * L.NT * 4;
-  const uint32_t nf = 2u * L.NP + 16u * L.NT + 64;
+  const uint32_t nf = 2u * L.NP + 18u * L.NT + 64;
   const uint32_t budget = 227u * 1024u - 1024u;
   L.NSP = 3;
   for (;;) {
@@ -65,6 +67,8 @@ __host__ __device__ inline Bwd3Layout bwd3_layout(int P, int T, int D) {
     const uint32_t e3 = (16u * L.NT + 2u * L.NP) * 4;
     if (dl0 + e3 > end) end = dl0 + e3;
     if (L.off_ring4 + 3 * L.slot4 > end) end = L.off_ring4 + 3 * L.slot4;
+    // M block 1 of the K-major views of the interleaved operands reads up to row 255 of the last chunk
+    if (L.off_w + 2 * L.plane + 256u * 16u > end) end = L.off_w + 2 * L.plane + 256u * 16u;
     L.off_dl = dl0; L.off_ldp = dl0 - ldp;
     L.off_f = (end + 127) & ~127u;
     L.off_bar = (L.off_f + 4 * nf + 7) & ~7u;
@@ -97,17 +101,25 @@ struct Bwd3Params {
 };
 
 __device__ __forceinline__ void b3_epi_bar() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
-__device__ __forceinline__ float b3_raw(const bf16* p) { return __bfloat162float(*p); }
+__device__ __forceinline__ float b3_raw(const bf16* p) {
+  return __uint_as_float((uint32_t)(*reinterpret_cast<const unsigned short*>(p)) << 16);
+}
 
-template <bool kHalf>
+template <int kNT, int kNP, int kD, bool kHalf>
 __global__ void __launch_bounds__(kB3Threads, 1)
 sparc_bwd3_kernel(const __grid_constant__ CUtensorMap tmV0, const __grid_constant__ CUtensorMap tmV1,
                   const __grid_constant__ CUtensorMap tmL, const __grid_constant__ CUtensorMap tmG, const Bwd3Params p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* base = CFA_SMEM_BASE_1024(smem_raw);
-  const Bwd3Layout L = bwd3_layout(p.P, p.T, p.D);
-  const int NP = L.NP, NT = L.NT, MB = L.MB, KB0 = L.KB0, NSP = L.NSP, P = p.P, T = p.T, D = p.D;
+  const Bwd3Layout L = bwd3_layout(p.P, p.T, kD ? kD : p.D);
+  const int NP = kNP ? kNP : L.NP, NT = kNT ? kNT : L.NT, D = kD ? kD : p.D;
+  const int MB = NP > 128 ? 2 : 1, KB0 = D / 64, NBLK = D / 128, NCH = MB;
+  const int CR0 = NCH == 2 ? 16 * ((NP + 31) / 32) : NP;
+  const int NSP = L.NSP, P = p.P, T = p.T;
   const int NT2 = 2 * NT, NT3 = 3 * NT;
+  const uint32_t v_bytes = (uint32_t)NP * 128, l_bytes = (uint32_t)NT * 128, slotP = v_bytes + 3 * l_bytes;
+  const uint32_t slot4 = (2u * CR0 * 128 > 2u * l_bytes) ? 2u * CR0 * 128 : 2u * l_bytes;
+  const uint32_t plane = (uint32_t)NT * NP * 2, dlb = (uint32_t)NT * NT * 2;
   const int b = blockIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -116,28 +128,26 @@ sparc_bwd3_kernel(const __grid_constant__ CUtensorMap tmV0, const __grid_constan
   uint8_t* ringP = base;                              // P1 slots [v tile | l tile | G hi tile | G lo tile]
   uint8_t* ring4 = base + L.off_ring4;                // P4 slots: v chunk pair, or l / G hi / G lo tile pair
   uint8_t* DLh = base + L.off_dl;                     // dLhat hi, lo : [NT / 8][NT][8] each
-  uint8_t* DLl = DLh + L.dlb;
+  uint8_t* DLl = DLh + dlb;
   float* ldpart = (float*)(base + L.off_ldp);         // [16][NT] phase-0 column partials
   float* part_c = (float*)(base + L.off_dl);          // E3' scratch in the dead dLhat region: [8][NT] sum of kept dW
   float* part_d = part_c + 8 * NT;                    //                                       [8][NT] sum of ds * s
   float* vqp = part_d + 8 * NT;                       //                                       [2][NP] row partials
   float* ivn = (float*)(base + L.off_f);              // [NP]
   float* vfac = ivn + NP;                             // [NP]
-  float* iln = vfac + NP;                             // [NT] ...
-  float* msk = iln + NT;
+  float4* cA = (float4*)(vfac + NP);                  // [NT] {1/||l_t||, min (+inf: masked), 1/range, 1/(sigma range)}
+  float2* cD = (float2*)(cA + NT);                    // [NT] {1/sigma (0: masked), -gfac}
+  float* msk = (float*)(cD + NT);                     // [NT] ...
   float* lser = msk + NT;
   float* lsec = lser + NT;
   float* mnf = lsec + NT;
-  float* irf = mnf + NT;
-  float* sgm = irf + NT;                              // sigma
-  float* isgm = sgm + NT;                             // 1 / sigma, 0 for masked tokens
-  float* ignv = isgm + NT;
-  float* gfacs = ignv + NT;
-  float* ldot = gfacs + NT;
+  float* ignv = mnf + NT;
+  float* ldot = ignv + NT;
   float* lfacs = ldot + NT;
   float* dmns = lfacs + NT;
   float* fixv = dmns + NT;
-  int* imn = (int*)(fixv + NT);
+  float* mdl = fixv + NT;                             // msk / cnt
+  int* imn = (int*)(mdl + NT);
   uint64_t* bars = (uint64_t*)(base + L.off_bar);
   uint64_t* fullP = bars;           // [3]
   uint64_t* emptyP = bars + 3;      // [3]
@@ -169,14 +179,17 @@ sparc_bwd3_kernel(const __grid_constant__ CUtensorMap tmV0, const __grid_constan
       const int t = i - NP;
       const bool in = t < T;
       const bool on = in && p.mask[(size_t)b * T + t];
-      iln[t] = in ? p.inv_ln[(size_t)b * T + t] : 0.f;
       msk[t] = on ? 1.f : 0.f;
       lser[t] = in ? p.lse_row[(size_t)b * T + t] : 0.f;
       lsec[t] = in ? p.lse_col[(size_t)b * T + t] : 0.f;
       ignv[t] = in ? p.g_inv_norm[(size_t)b * T + t] : 0.f;
-      float4 st4 = make_float4(0.f, 0.f, 1.f, __int_as_float(0x7fffffff));
+      float4 st4 = make_float4(0.f, 1.f, 1.f, __int_as_float(0x7fffffff));      // finite 1/range: (s - inf) * 0 would be NaN
       if (in) st4 = __ldg(reinterpret_cast<const float4*>(p.stats + ((size_t)b * T + t) * 4));
-      mnf[t] = st4.x; irf[t] = st4.y; sgm[t] = st4.z; isgm[t] = on ? 1.f / st4.z : 0.f; imn[t] = __float_as_int(st4.w);
+      const float isg = on ? 1.f / st4.z : 0.f;
+      mnf[t] = st4.x;
+      imn[t] = __float_as_int(st4.w);
+      cA[t] = make_float4(in ? p.inv_ln[(size_t)b * T + t] : 0.f, on ? st4.x : CUDART_INF_F, st4.y, isg * st4.y);
+      cD[t].x = isg;
     }
   }
   tc_fence_before();
@@ -190,33 +203,33 @@ sparc_bwd3_kernel(const __grid_constant__ CUtensorMap tmV0, const __grid_constan
     if (lane == 0) {
       for (int u = 0; u < KB0; ++u) {                  // P1: v | l | G hi | G lo
         const int s = u % NSP;
-        if (u >= NSP) mbar_wait(emptyP + s, ((u / NSP) - 1) & 1);
-        uint8_t* st = ringP + (size_t)s * L.slotP;
-        mbar_expect_tx(fullP + s, L.slotP);
+        if (u >= NSP) mbar_wait_sleep(emptyP + s, ((u / NSP) - 1) & 1);
+        uint8_t* st = ringP + (size_t)s * slotP;
+        mbar_expect_tx(fullP + s, slotP);
         tma_load_3d(st, &tmV0, fullP + s, u * 64, 0, b);
-        tma_load_3d(st + L.v_bytes, &tmL, fullP + s, u * 64, 0, b);
-        tma_load_3d(st + L.v_bytes + L.l_bytes, &tmG, fullP + s, u * 64, 0, 2 * b);
-        tma_load_3d(st + L.v_bytes + 2 * L.l_bytes, &tmG, fullP + s, u * 64, 0, 2 * b + 1);
+        tma_load_3d(st + v_bytes, &tmL, fullP + s, u * 64, 0, b);
+        tma_load_3d(st + v_bytes + l_bytes, &tmG, fullP + s, u * 64, 0, 2 * b);
+        tma_load_3d(st + v_bytes + 2 * l_bytes, &tmG, fullP + s, u * 64, 0, 2 * b + 1);
       }
       // P4 slots 0, 1 overlap the P1 ring and the phase-0 scratch; slot 2 overlaps dLhat and the E3' scratch
-      mbar_wait(s_full, 0);
-      mbar_wait(dl_ready, 0);
-      const int per = L.NCH + 3, n4 = L.NBLK * per;
+      mbar_wait_sleep(s_full, 0);
+      mbar_wait_sleep(dl_ready, 0);
+      const int per = NCH + 3, n4 = NBLK * per;
       for (int i = 0; i < n4; ++i) {
         const int s = i % 3, blk = i / per, w = i % per;
-        if (i >= 3) mbar_wait(empty4 + s, ((i / 3) - 1) & 1);
-        if (i == 2) mbar_wait(ds_ready, 0);
-        uint8_t* st = ring4 + (size_t)s * L.slot4;
-        if (w < L.NCH) {
-          mbar_expect_tx(full4 + s, 2u * L.CR0 * 128);
-          tma_load_3d(st, &tmV1, full4 + s, blk * 128, w * L.CR0, b);
-          tma_load_3d(st + L.CR0 * 128, &tmV1, full4 + s, blk * 128 + 64, w * L.CR0, b);
+        if (i >= 3) mbar_wait_sleep(empty4 + s, ((i / 3) - 1) & 1);
+        if (i == 2) mbar_wait_sleep(ds_ready, 0);
+        uint8_t* st = ring4 + (size_t)s * slot4;
+        if (w < NCH) {
+          mbar_expect_tx(full4 + s, 2u * CR0 * 128);
+          tma_load_3d(st, &tmV1, full4 + s, blk * 128, w * CR0, b);
+          tma_load_3d(st + CR0 * 128, &tmV1, full4 + s, blk * 128 + 64, w * CR0, b);
         } else {
-          const CUtensorMap* tm = (w == L.NCH) ? &tmL : &tmG;
-          const int pl = (w == L.NCH) ? b : (w == L.NCH + 1 ? 2 * b : 2 * b + 1);
-          mbar_expect_tx(full4 + s, 2 * L.l_bytes);
+          const CUtensorMap* tm = (w == NCH) ? &tmL : &tmG;
+          const int pl = (w == NCH) ? b : (w == NCH + 1 ? 2 * b : 2 * b + 1);
+          mbar_expect_tx(full4 + s, 2 * l_bytes);
           tma_load_3d(st, tm, full4 + s, blk * 128, 0, pl);
-          tma_load_3d(st + L.l_bytes, tm, full4 + s, blk * 128 + 64, 0, pl);
+          tma_load_3d(st + l_bytes, tm, full4 + s, blk * 128 + 64, 0, pl);
         }
       }
     }
@@ -237,91 +250,115 @@ sparc_bwd3_kernel(const __grid_constant__ CUtensorMap tmV0, const __grid_constan
     // ---- P1
     for (int u = 0; u < KB0; ++u) {
       const int s = u % NSP;
-      mbar_wait(fullP + s, (u / NSP) & 1);
+      mbar_wait_sleep(fullP + s, (u / NSP) & 1);
       tc_fence_after();
-      const uint32_t sv = smem_u32(ringP + (size_t)s * L.slotP), sb = sv + L.v_bytes;
+      const uint32_t sv = smem_u32(ringP + (size_t)s * slotP), sb = sv + v_bytes;
       const uint64_t dv0 = sw0 | (sv >> 4), db0 = sw0 | (sb >> 4);
-      for (int mb = 0; mb < MB; ++mb) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_ss_w(leader, tmem + mb * NT3, dv0 + mb * (16384 >> 4) + 2 * k, db0 + 2 * k, id_p1, (u | k) != 0);
+      for (int mb = 0; mb < 2; ++mb) {
+        if (mb < MB) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_ss_w(leader, tmem + mb * NT3, dv0 + mb * (16384 >> 4) + 2 * k, db0 + 2 * k, id_p1, (u | k) != 0);
+        }
       }
       umma_commit_w(leader, emptyP + s);
     }
     umma_commit_w(leader, s_full);
     stamp();
     // ---- M: dW^T (on top of the parked -gfac Q) and Z^T
-    mbar_wait(dl_ready, 0);
-    mbar_wait(e1_ready, 0);
+    mbar_wait_sleep(dl_ready, 0);
+    mbar_wait_sleep(e1_ready, 0);
     tc_fence_after();
     stamp();
     const uint32_t np16 = (uint32_t)NP * 16, nt16 = (uint32_t)NT * 16;
     // interleaved [k/8][rows][8] operands: K-major: LBO = rows * 16, SBO = 128; MN-major: LBO = 128, SBO = rows * 16
-    const uint64_t k_srh = make_smem_desc(smem_u32(SR), np16, 128, kLayoutNone), k_srl = make_smem_desc(smem_u32(SR) + L.plane, np16, 128, kLayoutNone);
-    const uint64_t k_wh = make_smem_desc(smem_u32(WT), np16, 128, kLayoutNone), k_wl = make_smem_desc(smem_u32(WT) + L.plane, np16, 128, kLayoutNone);
+    const uint64_t k_srh = make_smem_desc(smem_u32(SR), np16, 128, kLayoutNone), k_srl = make_smem_desc(smem_u32(SR) + plane, np16, 128, kLayoutNone);
+    const uint64_t k_wh = make_smem_desc(smem_u32(WT), np16, 128, kLayoutNone), k_wl = make_smem_desc(smem_u32(WT) + plane, np16, 128, kLayoutNone);
     const uint64_t k_dlh = make_smem_desc(smem_u32(DLh), nt16, 128, kLayoutNone), k_dll = make_smem_desc(smem_u32(DLl), nt16, 128, kLayoutNone);
     const uint64_t m_dlh = make_smem_desc(smem_u32(DLh), 128, nt16, kLayoutNone), m_dll = make_smem_desc(smem_u32(DLl), 128, nt16, kLayoutNone);
     const uint32_t ksA = (2 * np16) >> 4;              // K-major interleaved with NP rows: two 8-wide chunks per k-step
     const uint32_t ksB = (2 * nt16) >> 4;              // K-major interleaved with NT rows
     const uint32_t mtile = (128u * 16u) >> 4;          // second 128-row M block of a K-major interleaved operand
-    const int nksT = NT / 16, nksP = NP / 16;
-    for (int mb = 0; mb < MB; ++mb) {
-      const uint32_t dw = tmem + mb * NT3 + NT, dz = tmem + mb * NT3 + NT2;
-      const uint32_t mo = mb * mtile;
-      for (int ks = 0; ks < nksT; ++ks) umma_ss_w(leader, dw, k_srh + mo + ks * ksA, k_dlh + ks * ksB, id_dw, true);
-      for (int ks = 0; ks < nksT; ++ks) umma_ss_w(leader, dw, k_srh + mo + ks * ksA, k_dll + ks * ksB, id_dw, true);
-      for (int ks = 0; ks < nksT; ++ks) umma_ss_w(leader, dw, k_srl + mo + ks * ksA, k_dlh + ks * ksB, id_dw, true);
-      for (int ks = 0; ks < nksT; ++ks) umma_ss_w(leader, dz, k_wh + mo + ks * ksA, m_dlh + ks * 16, id_z, ks != 0);
-      for (int ks = 0; ks < nksT; ++ks) umma_ss_w(leader, dz, k_wh + mo + ks * ksA, m_dll + ks * 16, id_z, true);
-      for (int ks = 0; ks < nksT; ++ks) umma_ss_w(leader, dz, k_wl + mo + ks * ksA, m_dlh + ks * 16, id_z, true);
+    const int nksT = NT / 16;
+#pragma unroll
+    for (int mb = 0; mb < 2; ++mb) {
+      if (mb < MB) {
+        const uint32_t dw = tmem + mb * NT3 + NT, dz = tmem + mb * NT3 + NT2;
+        const uint32_t mo = mb * mtile;
+#pragma unroll
+        for (int ks = 0; ks < 5; ++ks) if (ks < nksT) umma_ss_w(leader, dw, k_srh + mo + ks * ksA, k_dlh + ks * ksB, id_dw, true);
+#pragma unroll
+        for (int ks = 0; ks < 5; ++ks) if (ks < nksT) umma_ss_w(leader, dw, k_srh + mo + ks * ksA, k_dll + ks * ksB, id_dw, true);
+#pragma unroll
+        for (int ks = 0; ks < 5; ++ks) if (ks < nksT) umma_ss_w(leader, dw, k_srl + mo + ks * ksA, k_dlh + ks * ksB, id_dw, true);
+#pragma unroll
+        for (int ks = 0; ks < 5; ++ks) if (ks < nksT) umma_ss_w(leader, dz, k_wh + mo + ks * ksA, m_dlh + ks * 16, id_z, ks != 0);
+#pragma unroll
+        for (int ks = 0; ks < 5; ++ks) if (ks < nksT) umma_ss_w(leader, dz, k_wh + mo + ks * ksA, m_dll + ks * 16, id_z, true);
+#pragma unroll
+        for (int ks = 0; ks < 5; ++ks) if (ks < nksT) umma_ss_w(leader, dz, k_wl + mo + ks * ksA, m_dlh + ks * 16, id_z, true);
+      }
     }
     umma_commit_w(leader, dw_full);
     // ---- P4
-    mbar_wait(ds_ready, 0);
+    mbar_wait_sleep(ds_ready, 0);
     tc_fence_after();
     stamp();
     const uint64_t m_ds = make_smem_desc(smem_u32(SR), 128, np16, kLayoutNone);          // dShat'^T hi|lo, MN-major (N = t, K = p)
     int i4 = 0;
-    for (int blk = 0; blk < L.NBLK; ++blk) {
+    long long wfull = 0, wfree = 0;
+    for (int blk = 0; blk < NBLK; ++blk) {
       // unit A: dl^T
-      mbar_wait(oa_free, (blk & 1) ^ 1);
+      { const long long w0 = clock64(); mbar_wait_sleep(oa_free, (blk & 1) ^ 1); wfree += clock64() - w0; }
       tc_fence_after();
-      for (int ch = 0; ch < L.NCH; ++ch, ++i4) {
-        const int s = i4 % 3;
-        mbar_wait(full4 + s, (i4 / 3) & 1);
-        tc_fence_after();
-        const uint32_t sa = smem_u32(ring4 + (size_t)s * L.slot4);
-        const uint64_t da = make_smem_desc(sa, (uint32_t)L.CR0 * 128, 1024, kLayoutSw128);
-        const int r0 = ch * L.CR0, nk = (ch == 0 ? L.CR0 : NP - L.CR0) / 16;
-        const uint64_t db = m_ds + (uint32_t)r0;
-        for (int ks = 0; ks < nk; ++ks) umma_ss_w(leader, tmem + cDL, da + ks * 128, db + ks * 16, id_dl, (ch | ks) != 0);
-        umma_commit_w(leader, empty4 + s);
+#pragma unroll
+      for (int ch = 0; ch < 2; ++ch) {
+        if (ch < NCH) {
+          const int s = i4 % 3;
+          { const long long w0 = clock64(); mbar_wait_sleep(full4 + s, (i4 / 3) & 1); wfull += clock64() - w0; }
+          tc_fence_after();
+          const uint32_t sa = smem_u32(ring4 + (size_t)s * slot4);
+          const uint64_t da = make_smem_desc(sa, (uint32_t)CR0 * 128, 1024, kLayoutSw128);
+          const int r0 = ch * CR0, nk = (ch == 0 ? CR0 : NP - CR0) / 16;
+          const uint64_t db = m_ds + (uint32_t)r0;
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks) if (ks < nk) umma_ss_w(leader, tmem + cDL, da + ks * 128, db + ks * 16, id_dl, (ch | ks) != 0);
+          umma_commit_w(leader, empty4 + s);
+          ++i4;
+        }
       }
       umma_commit_w(leader, oa_full);
       // unit B: dv^T
-      mbar_wait(ob_free, (blk & 1) ^ 1);
+      { const long long w0 = clock64(); mbar_wait_sleep(ob_free, (blk & 1) ^ 1); wfree += clock64() - w0; }
       tc_fence_after();
+#pragma unroll
       for (int w = 0; w < 3; ++w, ++i4) {
         const int s = i4 % 3;
-        mbar_wait(full4 + s, (i4 / 3) & 1);
+        { const long long w0 = clock64(); mbar_wait_sleep(full4 + s, (i4 / 3) & 1); wfull += clock64() - w0; }
         tc_fence_after();
-        const uint32_t sa = smem_u32(ring4 + (size_t)s * L.slot4);
-        const uint64_t da = make_smem_desc(sa, L.l_bytes, 1024, kLayoutSw128);             // [NT x 64] tile pair, MN-major (M = d)
+        const uint32_t sa = smem_u32(ring4 + (size_t)s * slot4);
+        const uint64_t da = make_smem_desc(sa, l_bytes, 1024, kLayoutSw128);             // [NT x 64] tile pair, MN-major (M = d)
         if (w == 0) {
-          for (int ks = 0; ks < nksT; ++ks) umma_ss_w(leader, tmem + cDV, da + ks * 128, k_srh + ks * ksA, id_dv, ks != 0);
-          for (int ks = 0; ks < nksT; ++ks) umma_ss_w(leader, tmem + cDV, da + ks * 128, k_srl + ks * ksA, id_dv, true);
+#pragma unroll
+          for (int ks = 0; ks < 5; ++ks) if (ks < nksT) umma_ss_w(leader, tmem + cDV, da + ks * 128, k_srh + ks * ksA, id_dv, ks != 0);
+#pragma unroll
+          for (int ks = 0; ks < 5; ++ks) if (ks < nksT) umma_ss_w(leader, tmem + cDV, da + ks * 128, k_srl + ks * ksA, id_dv, true);
         } else if (w == 1) {
-          for (int ks = 0; ks < nksT; ++ks) umma_ss_w(leader, tmem + cDV, da + ks * 128, k_wh + ks * ksA, id_dg, true);
-          for (int ks = 0; ks < nksT; ++ks) umma_ss_w(leader, tmem + cDV, da + ks * 128, k_wl + ks * ksA, id_dg, true);
+#pragma unroll
+          for (int ks = 0; ks < 5; ++ks) if (ks < nksT) umma_ss_w(leader, tmem + cDV, da + ks * 128, k_wh + ks * ksA, id_dg, true);
+#pragma unroll
+          for (int ks = 0; ks < 5; ++ks) if (ks < nksT) umma_ss_w(leader, tmem + cDV, da + ks * 128, k_wl + ks * ksA, id_dg, true);
         } else {
-          for (int ks = 0; ks < nksT; ++ks) umma_ss_w(leader, tmem + cDV, da + ks * 128, k_wh + ks * ksA, id_dg, true);
+#pragma unroll
+          for (int ks = 0; ks < 5; ++ks) if (ks < nksT) umma_ss_w(leader, tmem + cDV, da + ks * 128, k_wh + ks * ksA, id_dg, true);
         }
         umma_commit_w(leader, empty4 + s);
       }
       umma_commit_w(leader, ob_full);
     }
-    (void)nksP;
     stamp();
+    if (pf) { pf[8] = wfull; pf[9] = wfree; }
   } else {
     // =============================== epilogue: 16 warps = 4 TMEM lane quarters x 4 groups ===============================
     const int ew = warp - 2, q = warp & 3, grp = ew >> 2;
@@ -367,7 +404,7 @@ sparc_bwd3_kernel(const __grid_constant__ CUtensorMap tmV0, const __grid_constan
           const float pr = g * yy;
           gd += pr;
           cs[k] += pr;
-          x[k] = p.scale * g * ig * iln[j];
+          x[k] = p.scale * g * ig * cA[j].x;
         }
         if (tact) {
           uint4 hi, lo;
@@ -379,7 +416,7 @@ sparc_bwd3_kernel(const __grid_constant__ CUtensorMap tmV0, const __grid_constan
         // row sum over the nch chunk lanes of this row slot (fixed order)
         float tot = 0.f;
         for (int k = 0; k < nch; ++k) tot += __shfl_sync(0xffffffffu, gd, (rs < rpp ? rs : 0) * nch + k);
-        if (tact && jc == 0) gfacs[t] = tot * ig * ig;           // (g^_t . dg^_t) / ||G_t||^2
+        if (tact && jc == 0) cD[t].y = -(tot * ig * ig);         // -gfac_t = -(g^_t . dg^_t) / ||G_t||^2
       }
       // column partials of this warp: add the rpp row slots in fixed order, then one slot per warp
 #pragma unroll
@@ -409,36 +446,41 @@ sparc_bwd3_kernel(const __grid_constant__ CUtensorMap tmV0, const __grid_constan
     const int cw = NT / 2, c_lo = chh * cw;
     const int combo = mb * 4 + q;
     const uint32_t tS = tq + mb * NT3, tW = tS + NT, tZ = tS + NT2;
-    mbar_wait(s_full, 0);
+    mbar_wait_sleep(s_full, 0);
     tc_fence_after();
     stamp();
     if (e_act) {
-      for (int c0 = c_lo; c0 < c_lo + cw; c0 += 8) {
-        float x[8], qh[8], ql[8], w[8];
-        tmem_ld8(tS + c0, x);
-        tmem_ld8(tW + c0, qh);
-        tmem_ld8(tZ + c0, ql);
-        tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int t = c0 + j;
-          const bool in = live && msk[t] != 0.f;
-          const float nn = (x[j] * ivp * iln[t] - mnf[t]) * irf[t];
-          w[j] = (in && !(nn < p.thr)) ? nn * isgm[t] : 0.f;
-          x[j] = in ? x[j] : 0.f;
-          qh[j] = in ? -gfacs[t] * (qh[j] + ql[j]) : 0.f;
+      for (int g8 = 0; g8 < 5; ++g8) {
+        const int c0 = c_lo + 8 * g8;
+        if (8 * g8 < cw) {
+          float x[8], qh[8], ql[8], w[8];
+          tmem_ld8(tS + c0, x);
+          tmem_ld8(tW + c0, qh);
+          tmem_ld8(tZ + c0, ql);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 a4 = cA[c0 + j];
+            const float2 d2 = cD[c0 + j];
+            const float raw = live ? x[j] : 0.f;
+            const float nn = __fmul_rn(__fsub_rn(__fmul_rn(__fmul_rn(raw, ivp), a4.x), a4.y), a4.z);   // the forward's roundings
+            w[j] = (live && !(nn < p.thr)) ? nn * d2.x : 0.f;
+            x[j] = raw;
+            qh[j] = d2.y * (qh[j] + ql[j]);              // -gfac Q (gfac = 0 for masked tokens)
+          }
+          if (prow < NP) {
+            uint4 hi, lo;
+            const uint32_t off = (uint32_t)((c0 >> 3) * NP + prow) * 16;
+            split_hilo8(w, hi, lo);
+            *reinterpret_cast<uint4*>(WT + off) = hi;
+            *reinterpret_cast<uint4*>(WT + plane + off) = lo;
+            split_hilo8(x, hi, lo);
+            *reinterpret_cast<uint4*>(SR + off) = hi;
+            *reinterpret_cast<uint4*>(SR + plane + off) = lo;
+          }
+          tmem_st8(tW + c0, qh);
         }
-        if (prow < NP) {
-          uint4 hi, lo;
-          const uint32_t off = (uint32_t)((c0 >> 3) * NP + prow) * 16;
-          split_hilo8(w, hi, lo);
-          *reinterpret_cast<uint4*>(WT + off) = hi;
-          *reinterpret_cast<uint4*>(WT + L.plane + off) = lo;
-          split_hilo8(x, hi, lo);
-          *reinterpret_cast<uint4*>(SR + off) = hi;
-          *reinterpret_cast<uint4*>(SR + L.plane + off) = lo;
-        }
-        tmem_st8(tW + c0, qh);
       }
       tmem_st_wait();
     }
@@ -451,57 +493,63 @@ sparc_bwd3_kernel(const __grid_constant__ CUtensorMap tmV0, const __grid_constan
     // ---- E3': dW -> renorm / threshold / min-max backward -> dShat'^T = dShat^T + Z^T (hi|lo), (-gfac W)^T (hi|lo), lfac, vfac
     // One sweep, with the two identities of sparc_bwd2:  sum_p W dW = 0  and  sum_p dN N = 0  (only the arg-min patch
     // receives a scatter term, patched in afterwards).
-    mbar_wait(dw_full, 0);
+    mbar_wait_sleep(dw_full, 0);
     tc_fence_after();
     stamp();
     float vq = 0.f;
     if (e_act) {
-      for (int c0 = c_lo; c0 < c_lo + cw; c0 += 8) {
-        float x[8], dw[8], z[8], pr[8], wg[8];
-        tmem_ld8(tS + c0, x);
-        tmem_ld8(tW + c0, dw);
-        tmem_ld8(tZ + c0, z);
-        tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int t = c0 + j;
-          const bool in = live && msk[t] != 0.f;
-          const float s = x[j] * ivp * iln[t];
-          const float nn = (s - mnf[t]) * irf[t];
-          const bool kept = in && !(nn < p.thr);
-          const float d = kept ? dw[j] : 0.f;            // phantom lanes may hold NaN/Inf: select, never 0 * x
-          dw[j] = d;
-          const float ds = (d * isgm[t]) * irf[t];
-          const float prod = kept ? ds * s : 0.f;
-          pr[j] = prod;
-          vq += prod;
-          x[j] = in ? fmaf(ds * iln[t], ivp, z[j]) : 0.f;                 // dShat' = dShat + Z
-          wg[j] = kept ? -gfacs[t] * (nn * isgm[t]) : 0.f;                // -gfac W
+      for (int g8 = 0; g8 < 5; ++g8) {
+        const int c0 = c_lo + 8 * g8;
+        if (8 * g8 < cw) {
+          float x[8], dw[8], z[8], pr[8], wg[8];
+          tmem_ld8(tS + c0, x);
+          tmem_ld8(tW + c0, dw);
+          tmem_ld8(tZ + c0, z);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 a4 = cA[c0 + j];
+            const float2 d2 = cD[c0 + j];
+            const float u = live ? __fmul_rn(x[j], ivp) : 0.f;      // phantom lanes may hold NaN/Inf: select, never 0 * x
+            const float s = __fmul_rn(u, a4.x);
+            const float nn = __fmul_rn(__fsub_rn(s, a4.y), a4.z);
+            const bool kept = live && !(nn < p.thr);
+            const float d = kept ? dw[j] : 0.f;
+            dw[j] = d;
+            const float ds = d * a4.w;                    // / (sigma range)
+            const float prod = ds * s;
+            pr[j] = prod;
+            vq += prod;
+            x[j] = fmaf(ds * a4.x, ivp, live ? z[j] : 0.f);             // dShat' = dShat + Z
+            wg[j] = kept ? (nn * d2.x) * d2.y : 0.f;                    // -gfac W
+          }
+          if (prow < NP) {
+            uint4 hi, lo;
+            const uint32_t off = (uint32_t)((c0 >> 3) * NP + prow) * 16;
+            split_hilo8(x, hi, lo);
+            *reinterpret_cast<uint4*>(SR + off) = hi;
+            *reinterpret_cast<uint4*>(SR + plane + off) = lo;
+            split_hilo8(wg, hi, lo);
+            *reinterpret_cast<uint4*>(WT + off) = hi;
+            *reinterpret_cast<uint4*>(WT + plane + off) = lo;
+          }
+          const float c1 = warp_colsum8(dw, lane);
+          const float c2 = warp_colsum8(pr, lane);
+          if ((lane & 17) == 0) { part_c[combo * NT + c0 + (lane >> 1)] = c1; part_d[combo * NT + c0 + (lane >> 1)] = c2; }
         }
-        if (prow < NP) {
-          uint4 hi, lo;
-          const uint32_t off = (uint32_t)((c0 >> 3) * NP + prow) * 16;
-          split_hilo8(x, hi, lo);
-          *reinterpret_cast<uint4*>(SR + off) = hi;
-          *reinterpret_cast<uint4*>(SR + L.plane + off) = lo;
-          split_hilo8(wg, hi, lo);
-          *reinterpret_cast<uint4*>(WT + off) = hi;
-          *reinterpret_cast<uint4*>(WT + L.plane + off) = lo;
-        }
-        const float c1 = warp_colsum8(dw, lane);
-        const float c2 = warp_colsum8(pr, lane);
-        if ((lane & 17) == 0) { part_c[combo * NT + c0 + (lane >> 1)] = c1; part_d[combo * NT + c0 + (lane >> 1)] = c2; }
       }
     }
     b3_epi_bar();
     if (tid < NT) {
       float cx = 0.f, sd = 0.f;
       for (int w = 0; w < 4 * MB; ++w) { cx += part_c[w * NT + tid]; sd += part_d[w * NT + tid]; }
+      const float4 a4 = cA[tid];
       const bool valid = msk[tid] != 0.f;
-      const float dmn = valid ? -cx * isgm[tid] * irf[tid] : 0.f;
+      const float dmn = valid ? -cx * a4.w : 0.f;
       dmns[tid] = dmn;
       fixv[tid] = dmn * mnf[tid];                       // ds[imn] * s[imn], s[imn] = min
-      lfacs[tid] = (sd + dmn * mnf[tid] + ldot[tid]) * iln[tid] * iln[tid];      // (l^_t . dl^_t) / ||l_t||^2
+      lfacs[tid] = (sd + dmn * mnf[tid] + ldot[tid]) * a4.x * a4.x;      // (l^_t . dl^_t) / ||l_t||^2
     }
     b3_epi_bar();
     if (e_act) {
@@ -509,8 +557,8 @@ sparc_bwd3_kernel(const __grid_constant__ CUtensorMap tmV0, const __grid_constan
         if (imn[t] == prow && msk[t] != 0.f && live) {  // this thread owns the arg-min element of token t
           const uint32_t off = (uint32_t)((t >> 3) * NP + prow) * 16 + (t & 7) * 2;
           bf16* ph = reinterpret_cast<bf16*>(SR + off);
-          bf16* pl = reinterpret_cast<bf16*>(SR + L.plane + off);
-          const float f = (__bfloat162float(*ph) + __bfloat162float(*pl)) + dmns[t] * iln[t] * ivp;
+          bf16* pl = reinterpret_cast<bf16*>(SR + plane + off);
+          const float f = (__bfloat162float(*ph) + __bfloat162float(*pl)) + dmns[t] * cA[t].x * ivp;
           const bf16 nh = __float2bfloat16_rn(f);
           *ph = nh;
           *pl = __float2bfloat16_rn(f - __bfloat162float(nh));
@@ -521,6 +569,12 @@ sparc_bwd3_kernel(const __grid_constant__ CUtensorMap tmV0, const __grid_constan
     }
     b3_epi_bar();
     for (int i = tid; i < NP; i += 512) vfac[i] = (vqp[i] + vqp[NP + i]) * ivn[i] * ivn[i];
+    {
+      float cnt = 0.f;
+      for (int t = 0; t < T; ++t) cnt += msk[t];
+      const float invc = 1.f / fmaxf(cnt, kB3ClampEps);
+      if (tid < NT) mdl[tid] = msk[tid] * invc;
+    }
     tc_fence_before();
     fence_proxy_async();
     b3_epi_bar();
@@ -528,23 +582,26 @@ sparc_bwd3_kernel(const __grid_constant__ CUtensorMap tmV0, const __grid_constan
     stamp();
 
     // ---- P4 outputs: thread = feature column d of the block; group -> a quarter of the token / patch columns
-    float cnt = 0.f;
-    for (int t = 0; t < T; ++t) cnt += msk[t];
-    const float invc = 1.f / fmaxf(cnt, kB3ClampEps), invP = 1.f / (float)P;
+    const float invP = 1.f / (float)P;
     const int tw = NT / 4, t_lo = grp * tw;              // multiple of 4
     const int pw = NP / 4, p_lo = grp * pw;              // multiple of 4
     const int dloc = 32 * q + lane;
-    for (int blk = 0; blk < L.NBLK; ++blk) {
+    const bf16* lsrc0 = p.l + ((size_t)b * T + t_lo) * D + dloc;
+    bf16* ldst0 = p.dl + ((size_t)b * T + t_lo) * D + dloc;
+    const bf16* vsrc0 = p.v + ((size_t)b * P + p_lo) * D + dloc;
+    bf16* vdst0 = p.dv + ((size_t)b * P + p_lo) * D + dloc;
+    const int tn = max(0, min(tw, T - t_lo)), pn = max(0, min(pw, P - p_lo));     // live tokens / patches of this group
+    for (int blk = 0; blk < NBLK; ++blk) {
       const size_t dcol = (size_t)blk * 128 + dloc;
-      const float dpl = p.dpool_l ? __ldg(p.dpool_l + (size_t)b * D + dcol) * invc : 0.f;
+      const float dpl = p.dpool_l ? __ldg(p.dpool_l + (size_t)b * D + dcol) : 0.f;
       const float dpv = p.dpool_v ? __ldg(p.dpool_v + (size_t)b * D + dcol) * invP : 0.f;
       {   // unit A: dl[t][d] = dl^T[d][t] (hi-part + lo-part) - l[t][d] lfac_t + m_t dlbar[d] / cnt
-        const bf16* lsrc = p.l + (size_t)b * T * D + dcol;
-        bf16* ldst = p.dl + (size_t)b * T * D + dcol;
+        const bf16* lsrc = lsrc0 + blk * 128;
+        bf16* ldst = ldst0 + blk * 128;
         float raw[20];
 #pragma unroll
-        for (int k = 0; k < 20; ++k) raw[k] = (k < tw && t_lo + k < T) ? b3_raw(lsrc + (size_t)(t_lo + k) * D) : 0.f;
-        mbar_wait(oa_full, blk & 1);
+        for (int k = 0; k < 20; ++k) raw[k] = (k < tn) ? b3_raw(lsrc + (size_t)k * D) : 0.f;
+        mbar_wait_sleep(oa_full, blk & 1);
         tc_fence_after();
 #pragma unroll
         for (int c = 0; c < 20; c += 4) {
@@ -552,57 +609,63 @@ sparc_bwd3_kernel(const __grid_constant__ CUtensorMap tmV0, const __grid_constan
             float xh[4], xl[4];
             tmem_ld4(tq + cDL + t_lo + c, xh);
             tmem_ld4(tq + cDL + NT + t_lo + c, xl);
+            const float4 lf4 = *reinterpret_cast<const float4*>(lfacs + t_lo + c);
+            const float4 md4 = *reinterpret_cast<const float4*>(mdl + t_lo + c);
             tmem_ld_wait();
             if (c + 4 >= tw) {                           // last chunk: the accumulator is in registers
               tc_fence_before();
               __syncwarp();
               if (lane == 0) mbar_arrive(oa_free);
             }
+            const float lfv[4] = {lf4.x, lf4.y, lf4.z, lf4.w}, mdv[4] = {md4.x, md4.y, md4.z, md4.w};
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-              const int t = t_lo + c + k;
-              if (t < T) {
-                const float o = fmaf(msk[t], dpl, fmaf(-raw[c + k], lfacs[t], xh[k] + xl[k]));
-                ldst[(size_t)t * D] = __float2bfloat16_rn(o);
+              if (c + k < tn) {
+                const float o = fmaf(mdv[k], dpl, fmaf(-raw[c + k], lfv[k], xh[k] + xl[k]));
+                ldst[(size_t)(c + k) * D] = __float2bfloat16_rn(o);
               }
             }
           }
         }
+        if (blk == 0) stamp();
       }
       {   // unit B: dv[p][d] = dv^T[d][p] - v[p][d] vfac_p + dvbar[d] / P
-        const bf16* vsrc = p.v + (size_t)b * P * D + dcol;
-        bf16* vdst = p.dv + (size_t)b * P * D + dcol;
+        const bf16* vsrc = vsrc0 + blk * 128;
+        bf16* vdst = vdst0 + blk * 128;
         float rawc[8], rawn[8];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) rawc[k] = (k < pw && p_lo + k < P) ? b3_raw(vsrc + (size_t)(p_lo + k) * D) : 0.f;
-        mbar_wait(ob_full, blk & 1);
+        for (int k = 0; k < 8; ++k) rawc[k] = (k < pn) ? b3_raw(vsrc + (size_t)k * D) : 0.f;
+        mbar_wait_sleep(ob_full, blk & 1);
         tc_fence_after();
-        for (int c0 = 0; c0 < pw; c0 += 8) {
-          float x[8];
-          if (c0 + 8 <= pw) tmem_ld8(tq + cDV + p_lo + c0, x);
-          else tmem_ld4(tq + cDV + p_lo + c0, x);       // pw is a multiple of 4
 #pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            const int pn = p_lo + c0 + 8 + k;
-            rawn[k] = (c0 + 8 + k < pw && pn < P) ? b3_raw(vsrc + (size_t)pn * D) : 0.f;
-          }
-          tmem_ld_wait();
-          if (c0 + 8 >= pw) {                           // last chunk: the accumulator is in registers
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(ob_free);
-          }
+        for (int c0 = 0; c0 < 64; c0 += 8) {
+          if (c0 < pw) {
+            float x[8];
+            if (c0 + 8 <= pw) tmem_ld8(tq + cDV + p_lo + c0, x);
+            else tmem_ld4(tq + cDV + p_lo + c0, x);     // pw is a multiple of 4
+            const float4 vf0 = *reinterpret_cast<const float4*>(vfac + p_lo + c0);
+            const float4 vf1 = (c0 + 8 <= pw) ? *reinterpret_cast<const float4*>(vfac + p_lo + c0 + 4) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            const int pc = p_lo + c0 + k;
-            if (c0 + k < pw && pc < P) {
-              const float o = fmaf(-rawc[k], vfac[pc], x[k]) + dpv;
-              vdst[(size_t)pc * D] = __float2bfloat16_rn(o);
+            for (int k = 0; k < 8; ++k) rawn[k] = (c0 + 8 + k < pn) ? b3_raw(vsrc + (size_t)(c0 + 8 + k) * D) : 0.f;
+            tmem_ld_wait();
+            if (c0 + 8 >= pw) {                         // last chunk: the accumulator is in registers
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(ob_free);
             }
-          }
+            const float vfv[8] = {vf0.x, vf0.y, vf0.z, vf0.w, vf1.x, vf1.y, vf1.z, vf1.w};
 #pragma unroll
-          for (int k = 0; k < 8; ++k) rawc[k] = rawn[k];
+            for (int k = 0; k < 8; ++k) {
+              if (c0 + k < pn) {
+                const float o = fmaf(-rawc[k], vfv[k], x[k] + dpv);
+                vdst[(size_t)(c0 + k) * D] = __float2bfloat16_rn(o);
+              }
+            }
+#pragma unroll
+            for (int k = 0; k < 8; ++k) rawc[k] = rawn[k];
+          }
         }
+        if (blk == 0) stamp();
       }
     }
     stamp();
@@ -635,8 +698,14 @@ int sparc_bwd3_launch(const void* v, const void* l, const uint8_t* mask, int B, 
   Bwd3Params prm{prof, P, T, D, thr, scale, mask, row_inv_norm, row_inv_norm + (size_t)B * P, lse_row, lse_col, coef,
                  tt_logits, g_inv_norm, stats, dpv, dpl, (const bf16*)v, (const bf16*)l, (bf16*)dv, (bf16*)dl};
   const size_t smem = L.total + 1024;
-  CFA_CUDA_TRY(cudaFuncSetAttribute(sparc_bwd3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  sparc_bwd3_kernel<false><<<B, kB3Threads, smem, st>>>(tmV0, tmV1, tmL, tmG, prm);
+#define CFA_B3_LAUNCH(NT_, NP_, D_)                                                                                         \
+  do {                                                                                                                      \
+    CFA_CUDA_TRY(cudaFuncSetAttribute(sparc_bwd3_kernel<NT_, NP_, D_, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    sparc_bwd3_kernel<NT_, NP_, D_, false><<<B, kB3Threads, smem, st>>>(tmV0, tmV1, tmL, tmG, prm);                          \
+  } while (0)
+  if (L.NT == 80 && L.NP == 208 && D == 512) CFA_B3_LAUNCH(80, 208, 512);      // ViT-B/16 (P = 196 / 197, T = 77)
+  else CFA_B3_LAUNCH(0, 0, 0);
+#undef CFA_B3_LAUNCH
   return launch_status();
 }
 

@@ -7,7 +7,8 @@
 // and the 77 -> 128 row padding of the token-major orientation disappears.
 //
 //   P0   S^T[p,t]  = sum_kb v_kb . l_kb^T          (A = v tile K-major, B = l tile; 64-wide D blocks)    losses.py:225
-//        side jobs on the same tiles: row norms (losses.py:221-222), pooled text mean (losses.py:210-212)
+//        on the same tiles: Gram diagonals v_kb . v_kb^T, l_kb . l_kb^T -> row norms on the tensor core  losses.py:221-222
+//        (the pipe is idle while P0 waits for HBM), pooled text mean by the epilogue warps               losses.py:210-212
 //   E1   thread = patch p: cross-lane min / max per token (CREDUX), threshold -> Theta^T (un-normalised weights, hi|lo)
 //        and S_raw^T (hi|lo) as [t/8][p][t%8] operands; sigma_t = sum_p Theta by shuffle transposition   losses.py:228-243
 //   P1   L'^T[j,t] = S_raw . Theta^T               (K = p; replaces G . l^T: L_raw = W . S_raw^T)         losses.py:180
@@ -15,6 +16,9 @@
 //        ||G_t||^2, G -> global as bf16 hi | lo planes (the backward's TMA operands); spare column t = T carries
 //        1/P: the pooled image mean (losses.py:207)                                                    losses.py:245
 //   E3   logits = s L' / (sigma_t ||G_t|| ||l_j||), masked row / column log-sum-exp, CE                 losses.py:186-196
+//
+// Template parameters kNT / kNP / kD: padded token / patch counts and D as compile-time constants (0 = run-time values):
+// the epilogues are instruction-issue bound, and run-time strides cost more integer instructions than the arithmetic.
 #include "tc_common.cuh"
 #include "sparc_paths.h"
 #include <math_constants.h>
@@ -30,7 +34,7 @@ constexpr float kF3NormEps = 1e-12f, kF3MinMaxEps = 1e-8f, kF3ClampEps = 1e-8f;
 struct Fwd3Layout {
   int NP, NT, MB, KB0, NBLK, CR0, NCH, NS0, NS1;
   uint32_t v_bytes, l_bytes, slot0, slot1, plane;      // plane = one of hi / lo of an interleaved [NT/8][NP][8] operand
-  uint32_t off_th, off_sr, off_ring1, off_f, off_bar, total;
+  uint32_t off_th, off_sr, off_ring0, off_ring1, off_f, off_bar, total;
 };
 
 __host__ __device__ inline Fwd3Layout fwd3_layout(int P, int T, int D) {
@@ -41,25 +45,29 @@ __host__ __device__ inline Fwd3Layout fwd3_layout(int P, int T, int D) {
   L.v_bytes = (uint32_t)L.NP * 128; L.l_bytes = (uint32_t)L.NT * 128; L.slot0 = L.v_bytes + L.l_bytes;
   L.slot1 = 2u * L.CR0 * 128;
   L.plane = (uint32_t)L.NT * L.NP * 2;
-  // the Theta^T region doubles as the P0 scratch: row-norm partials [8][NP + NT] and pooled-mean partials [4][D]
-  const uint32_t scratch = (8u * (L.NP + L.NT) + 4u * D) * 4;
+  // the Theta^T region doubles as the P0 scratch: pooled-mean partials [4][D]
+  const uint32_t scratch = 4u * D * 4;
   const uint32_t op = ((2 * L.plane > scratch ? 2 * L.plane : scratch) + 1023) & ~1023u;
   L.off_th = 0; L.off_sr = op; L.off_ring1 = 2 * op;
-  const uint32_t nf = (uint32_t)L.NP + 7 * L.NT + 8 * 2 * L.NT + 8 * L.NT + 64;
+  const uint32_t nf = (uint32_t)L.NP + 9 * L.NT + 8 * 2 * L.NT + 8 * L.NT + 64;
   const uint32_t fixed = 4 * nf + 8 * 32 + 1024;
   const uint32_t budget = 227u * 1024u;
   L.NS1 = 0; L.NS0 = 0; L.off_f = 0; L.off_bar = 0; L.total = 0;
   if (L.off_ring1 + fixed + 2 * L.slot1 > budget) return L;
   L.NS1 = (budget - L.off_ring1 - fixed) / L.slot1 >= 3 ? 3 : 2;
   uint32_t data_end = L.off_ring1 + L.NS1 * L.slot1;
-  // the P0 ring aliases the S_raw^T and P1-ring regions (both dead during P0); M block 1 of the last slot reads 128 rows
-  // past row 128 of its v tile, which must stay inside the allocation
-  int ns0 = (int)((data_end - L.off_sr) / L.slot0);
+  // the P0 ring aliases everything behind the P0 scratch (all dead during P0).  The tensor core reads whole 128-row operand
+  // tiles: M block 1 of the last slot's v tile and the phantom rows of its l tile must stay inside the allocation
+  L.off_ring0 = (scratch + 1023) & ~1023u;
+  int ns0 = (int)((data_end - L.off_ring0) / L.slot0);
   L.NS0 = ns0 > 4 ? 4 : ns0;
   if (L.NS0 >= 1) {
-    const uint32_t reach = L.off_sr + (L.NS0 - 1) * L.slot0 + 256u * 128u;
+    const uint32_t r1 = 256u * 128u, r2 = L.v_bytes + 128u * 128u;
+    const uint32_t reach = L.off_ring0 + (L.NS0 - 1) * L.slot0 + (r1 > r2 ? r1 : r2);
     if (reach > data_end) data_end = reach;
   }
+  // the MN-major A view of S_raw^T reads 16 chunks of NP rows
+  if (L.off_sr + 256u * L.NP > data_end) data_end = L.off_sr + 256u * L.NP;
   L.off_f = (data_end + 127) & ~127u;
   L.off_bar = (L.off_f + 4 * nf + 7) & ~7u;
   L.total = L.off_bar + 8 * 32;
@@ -86,29 +94,46 @@ struct Fwd3Params {
 
 __device__ __forceinline__ void f3_epi_bar() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
 
-template <bool kHalf>
+// r[lane] of a 32-register array without local memory (5 select levels)
+__device__ __forceinline__ float f3_pick32(const float* r, int lane) {
+  float a[16], b[8], c[4];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) a[i] = (lane & 16) ? r[16 + i] : r[i];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) b[i] = (lane & 8) ? a[8 + i] : a[i];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) c[i] = (lane & 4) ? b[4 + i] : b[i];
+  const float d0 = (lane & 2) ? c[2] : c[0], d1 = (lane & 2) ? c[3] : c[1];
+  return (lane & 1) ? d1 : d0;
+}
+
+template <int kNT, int kNP, int kD, bool kHalf>
 __global__ void __launch_bounds__(kF3Threads, 1)
 sparc_fwd3_kernel(const __grid_constant__ CUtensorMap tmV0, const __grid_constant__ CUtensorMap tmV1,
                   const __grid_constant__ CUtensorMap tmL, const Fwd3Params p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* base = CFA_SMEM_BASE_1024(smem_raw);
-  const Fwd3Layout L = fwd3_layout(p.P, p.T, p.D);
-  const int NP = L.NP, NT = L.NT, MB = L.MB, KB0 = L.KB0, NS0 = L.NS0, NS1 = L.NS1, P = p.P, T = p.T, D = p.D;
+  const Fwd3Layout L = fwd3_layout(p.P, p.T, kD ? kD : p.D);
+  const int NP = kNP ? kNP : L.NP, NT = kNT ? kNT : L.NT, D = kD ? kD : p.D;
+  const int MB = NP > 128 ? 2 : 1, KB0 = D / 64, NBLK = D / 128, NCH = MB;
+  const int CR0 = NCH == 2 ? 16 * ((NP + 31) / 32) : NP;
+  const int NS0 = L.NS0, NS1 = L.NS1, P = p.P, T = p.T;
+  const uint32_t v_bytes = (uint32_t)NP * 128, l_bytes = (uint32_t)NT * 128, slot0 = v_bytes + l_bytes, slot1 = 2u * CR0 * 128;
+  const uint32_t plane = (uint32_t)NT * NP * 2;
   const int b = blockIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   uint8_t* TH = base + L.off_th;                      // Theta^T  [2 NT / 8][NP][8]: hi chunks, then lo chunks
   uint8_t* SR = base + L.off_sr;                      // S_raw^T  same layout
-  uint8_t* ring0 = base + L.off_sr;                   // P0 slots [v tile | l tile]
+  uint8_t* ring0 = base + L.off_ring0;                // P0 slots [v tile | l tile] (behind the pooled-mean scratch)
   uint8_t* ring1 = base + L.off_ring1;                // P1 slots [v chunk, d 0..63 | v chunk, d 64..127]
   float* ivn = (float*)(base + L.off_f);              // [NP]
-  float* iln = ivn + NP;                              // [NT]
-  float* msk = iln + NT;                              // [NT]
+  float4* cst = (float4*)(ivn + NP);                  // [NT] {1/||l_t||, min (+inf: masked), 1/range, 0}
+  float* msk = (float*)(cst + NT);                    // [NT]
   float* mnf = msk + NT;                              // [NT] row minimum
-  float* irf = mnf + NT;                              // [NT] 1 / (max - min + eps)
-  float* isg = irf + NT;                              // [NT] 1 / sigma (0 for masked tokens)
-  float* ign = isg + NT;                              // [NT] 1 / ||G_t||
-  int* imn = (int*)(ign + NT);                        // [NT] arg-min patch
+  float* isg = mnf + NT;                              // [NT] 1 / sigma (0 for masked tokens)
+  float* csc = isg + NT;                              // [NT] scale / (sigma_t ||G_t||)
+  int* imn = (int*)(csc + NT);                        // [NT] arg-min patch
   float* part_mm = (float*)(imn + NT);                // [8][NT][2]
   float* part_s = part_mm + 8 * 2 * NT;               // [8][NT]   (later: ||G||^2 partials [4][NT])
   float* red = part_s + 8 * NT;                       // [64]
@@ -143,37 +168,39 @@ sparc_fwd3_kernel(const __grid_constant__ CUtensorMap tmV0, const __grid_constan
   const uint32_t tmem = *tmem_slot;
   const int NT2 = 2 * NT;
   const uint32_t cG = (uint32_t)NT2;                  // G'^T ping-pong buffers at columns NT2 and 2 NT2
+  const uint32_t cGV = (uint32_t)NT2, cGL = (uint32_t)NT2 + 128u * MB;   // P0 only: Gram tiles v . v^T (per M block), l . l^T
 
   if (warp == 0) {
     // =============================== TMA producer ===============================
     if (lane == 0) {
       for (int u = 0; u < KB0; ++u) {
         const int s = u % NS0;
-        if (u >= NS0) mbar_wait(empty0 + s, ((u / NS0) - 1) & 1);
-        uint8_t* st = ring0 + (size_t)s * L.slot0;
-        mbar_expect_tx(full0 + s, L.slot0);
+        if (u >= NS0) mbar_wait_sleep(empty0 + s, ((u / NS0) - 1) & 1);
+        uint8_t* st = ring0 + (size_t)s * slot0;
+        mbar_expect_tx(full0 + s, slot0);
         tma_load_3d(st, &tmV0, full0 + s, u * 64, 0, b);
-        tma_load_3d(st + L.v_bytes, &tmL, full0 + s, u * 64, 0, b);
+        tma_load_3d(st + v_bytes, &tmL, full0 + s, u * 64, 0, b);
       }
       // the P1 ring overlaps the P0 slots: every P0 use must have been released
       for (int s = 0; s < NS0 && s < KB0; ++s) {
         const int n_s = (KB0 - s + NS0 - 1) / NS0;
-        mbar_wait(empty0 + s, (n_s - 1) & 1);
+        mbar_wait_sleep(empty0 + s, (n_s - 1) & 1);
       }
-      const int n1 = L.NBLK * L.NCH;
+      const int n1 = NBLK * NCH;
       for (int i = 0; i < n1; ++i) {
-        const int s = i % NS1, blk = i / L.NCH, ch = i % L.NCH;
-        if (i >= NS1) mbar_wait(empty1 + s, ((i / NS1) - 1) & 1);
-        uint8_t* st = ring1 + (size_t)s * L.slot1;
-        mbar_expect_tx(full1 + s, L.slot1);
-        tma_load_3d(st, &tmV1, full1 + s, blk * 128, ch * L.CR0, b);
-        tma_load_3d(st + L.slot1 / 2, &tmV1, full1 + s, blk * 128 + 64, ch * L.CR0, b);
+        const int s = i % NS1, blk = i / NCH, ch = i % NCH;
+        if (i >= NS1) mbar_wait_sleep(empty1 + s, ((i / NS1) - 1) & 1);
+        uint8_t* st = ring1 + (size_t)s * slot1;
+        mbar_expect_tx(full1 + s, slot1);
+        tma_load_3d(st, &tmV1, full1 + s, blk * 128, ch * CR0, b);
+        tma_load_3d(st + slot1 / 2, &tmV1, full1 + s, blk * 128 + 64, ch * CR0, b);
       }
     }
   } else if (warp == 1) {
     // =============================== MMA issuer (warp-uniform control flow, one elected lane issues) ===============================
     const bool leader = elect_one();
     const uint32_t idesc_s = make_idesc16(128, NT, false, false, kHalf, kHalf);     // raw v (K-major) x raw l (K-major)
+    const uint32_t idesc_gv = make_idesc16(128, 128, false, false, kHalf, kHalf);   // Gram tile of one M block of v
     const uint32_t idesc_l2 = make_idesc16(128, NT2, true, true, false, false);     // S_raw^T (MN-major) x Theta^T hi|lo (MN-major)
     const uint32_t idesc_l1 = make_idesc16(128, NT, true, true, false, false);
     const uint32_t idesc_g = make_idesc16(128, NT2, true, true, kHalf, false);      // raw v^T (MN-major tile pair) x Theta^T hi|lo
@@ -182,50 +209,64 @@ sparc_fwd3_kernel(const __grid_constant__ CUtensorMap tmV0, const __grid_constan
     int pi = 0;
     auto stamp = [&]() { if (pf) pf[pi++] = clock64(); };
     stamp();
-    // ---- P0: S^T = v . l^T
+    // ---- P0: S^T = v . l^T, Gram tiles of v (per M block) and l
     for (int u = 0; u < KB0; ++u) {
       const int s = u % NS0;
-      mbar_wait(full0 + s, (u / NS0) & 1);
+      mbar_wait_sleep(full0 + s, (u / NS0) & 1);
       tc_fence_after();
-      const uint32_t sv = smem_u32(ring0 + (size_t)s * L.slot0), sl = sv + L.v_bytes;
+      const uint32_t sv = smem_u32(ring0 + (size_t)s * slot0), sl = sv + v_bytes;
       const uint64_t dv0 = sw0 | (sv >> 4), dl0 = sw0 | (sl >> 4);
-      for (int mb = 0; mb < MB; ++mb) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_ss_w(leader, tmem + mb * NT, dv0 + mb * (16384 >> 4) + 2 * k, dl0 + 2 * k, idesc_s, (u | k) != 0);
+      for (int mb = 0; mb < 2; ++mb) {
+        if (mb < MB) {
+          const uint64_t dvm = dv0 + mb * (16384 >> 4);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_ss_w(leader, tmem + mb * NT, dvm + 2 * k, dl0 + 2 * k, idesc_s, (u | k) != 0);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_ss_w(leader, tmem + cGV + mb * 128, dvm + 2 * k, dvm + 2 * k, idesc_gv, (u | k) != 0);
+        }
       }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) umma_ss_w(leader, tmem + cGL, dl0 + 2 * k, dl0 + 2 * k, idesc_s, (u | k) != 0);
       umma_commit_w(leader, empty0 + s);
     }
     umma_commit_w(leader, s_full);
     stamp();
     // ---- P1: L'^T = S_raw . Theta^T (into the dead S^T columns), then G'^T per 128-wide D block
-    mbar_wait(w_ready, 0);
+    mbar_wait_sleep(w_ready, 0);
     tc_fence_after();
     stamp();
     const uint32_t il_sbo = (uint32_t)NP * 16;
     const uint64_t m_th = make_smem_desc(smem_u32(TH), 128, il_sbo, kLayoutNone);
     const uint64_t m_srh = make_smem_desc(smem_u32(SR), 128, il_sbo, kLayoutNone);
-    const uint64_t m_srl = make_smem_desc(smem_u32(SR) + L.plane, 128, il_sbo, kLayoutNone);
+    const uint64_t m_srl = make_smem_desc(smem_u32(SR) + plane, 128, il_sbo, kLayoutNone);
     const int nksP = NP / 16;
-    for (int ks = 0; ks < nksP; ++ks) umma_ss_w(leader, tmem, m_srh + ks * 16, m_th + ks * 16, idesc_l2, ks != 0);
-    for (int ks = 0; ks < nksP; ++ks) umma_ss_w(leader, tmem, m_srl + ks * 16, m_th + ks * 16, idesc_l1, true);
+#pragma unroll
+    for (int ks = 0; ks < (kNP ? kNP / 16 : 16); ++ks) if (ks < nksP) umma_ss_w(leader, tmem, m_srh + ks * 16, m_th + ks * 16, idesc_l2, ks != 0);
+#pragma unroll
+    for (int ks = 0; ks < (kNP ? kNP / 16 : 16); ++ks) if (ks < nksP) umma_ss_w(leader, tmem, m_srl + ks * 16, m_th + ks * 16, idesc_l1, true);
     umma_commit_w(leader, l_full);
     int i1 = 0;
-    for (int blk = 0; blk < L.NBLK; ++blk) {
+    for (int blk = 0; blk < NBLK; ++blk) {
       const int buf = blk & 1;
-      mbar_wait(g_free + buf, ((blk >> 1) & 1) ^ 1);
+      mbar_wait_sleep(g_free + buf, ((blk >> 1) & 1) ^ 1);
       tc_fence_after();
       const uint32_t d = tmem + cG + buf * NT2;
-      for (int ch = 0; ch < L.NCH; ++ch, ++i1) {
-        const int s = i1 % NS1;
-        mbar_wait(full1 + s, (i1 / NS1) & 1);
-        tc_fence_after();
-        const uint32_t sa = smem_u32(ring1 + (size_t)s * L.slot1);
-        const uint64_t da = make_smem_desc(sa, L.slot1 / 2, 1024, kLayoutSw128);
-        const int r0 = ch * L.CR0, nk = (ch == 0 ? L.CR0 : NP - L.CR0) / 16;
-        const uint64_t db = m_th + (uint32_t)r0;                      // r0 rows x 16 B, in 16-byte units
-        for (int ks = 0; ks < nk; ++ks) umma_ss_w(leader, d, da + ks * 128, db + ks * 16, idesc_g, (ch | ks) != 0);
-        umma_commit_w(leader, empty1 + s);
+#pragma unroll
+      for (int ch = 0; ch < 2; ++ch) {
+        if (ch < NCH) {
+          const int s = i1 % NS1;
+          mbar_wait_sleep(full1 + s, (i1 / NS1) & 1);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(ring1 + (size_t)s * slot1);
+          const uint64_t da = make_smem_desc(sa, slot1 / 2, 1024, kLayoutSw128);
+          const int r0 = ch * CR0, nk = (ch == 0 ? CR0 : NP - CR0) / 16;
+          const uint64_t db = m_th + (uint32_t)r0;                      // r0 rows x 16 B, in 16-byte units
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks) if (ks < nk) umma_ss_w(leader, d, da + ks * 128, db + ks * 16, idesc_g, (ch | ks) != 0);
+          umma_commit_w(leader, empty1 + s);
+          ++i1;
+        }
       }
       umma_commit_w(leader, g_full + buf);
     }
@@ -241,31 +282,26 @@ sparc_fwd3_kernel(const __grid_constant__ CUtensorMap tmV0, const __grid_constan
     auto stamp = [&]() { if (pf) pf[pi++] = clock64(); };
     stamp();
 
-    // ---- P0 side job: row sums of squares (losses.py:221-222) and the pooled means (losses.py:207-212) straight from the
-    // TMA tiles.  Warp -> 16-byte chunk c (8 columns of the 64-wide block) and row parity: rows lane + 32 k, k = hf, hf + 2,
-    // ... (conflict-free under the 128-byte swizzle).  The pooled IMAGE mean comes from here only when there is no spare
-    // token column (T == NT), see E1.
+    // ---- P0 side job: pooled text mean (losses.py:210-212) straight from the TMA tiles.  Warp -> 16-byte chunk c (8 columns
+    // of the 64-wide block) and row parity: rows lane + 32 k, k = hf, hf + 2, ... (conflict-free under the 128-byte swizzle).
+    // The pooled IMAGE mean comes from here only when there is no spare token column (T == NT), see E1.
     {
       const int c = ew & 7, hf = ew >> 3;
-      float* part = reinterpret_cast<float*>(TH);       // [8 chunks][NP + NT] (the Theta region is unused until E1)
-      float* poolp = part + 8 * (NP + NT);              // [2 modalities][2 parities][D]
-      float ssv[4] = {0.f, 0.f, 0.f, 0.f}, ssl[2] = {0.f, 0.f};
+      float* poolp = reinterpret_cast<float*>(TH);      // [2 modalities][2 parities][D] (the Theta region is unused until E1)
       for (int u = 0; u < KB0; ++u) {
         const int s = u % NS0;
-        mbar_wait(full0 + s, (u / NS0) & 1);
-        const uint8_t* st = ring0 + (size_t)s * L.slot0;
+        mbar_wait_sleep(full0 + s, (u / NS0) & 1);
+        const uint8_t* st = ring0 + (size_t)s * slot0;
         float al[8], av[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) { al[i] = 0.f; av[i] = 0.f; }
+        if (!pool_tc) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const int r = lane + 32 * (2 * k + hf);
-          if (r < NP) {
-            float f8[8];
-            unpack_raw8<kHalf>(*reinterpret_cast<const uint4*>(st + r * 128 + ((c ^ (r & 7)) << 4)), f8);
-            ssv[k] += (f8[0] * f8[0] + f8[1] * f8[1]) + (f8[2] * f8[2] + f8[3] * f8[3]) +
-                      ((f8[4] * f8[4] + f8[5] * f8[5]) + (f8[6] * f8[6] + f8[7] * f8[7]));
-            if (!pool_tc) {
+          for (int k = 0; k < 4; ++k) {
+            const int r = lane + 32 * (2 * k + hf);
+            if (r < NP) {
+              float f8[8];
+              unpack_raw8<kHalf>(*reinterpret_cast<const uint4*>(st + r * 128 + ((c ^ (r & 7)) << 4)), f8);
 #pragma unroll
               for (int i = 0; i < 8; ++i) av[i] += f8[i];                // rows beyond P are zero-filled by TMA
             }
@@ -276,9 +312,7 @@ sparc_fwd3_kernel(const __grid_constant__ CUtensorMap tmV0, const __grid_constan
           const int r = lane + 32 * (2 * k + hf);
           if (r < NT) {
             float f8[8];
-            unpack_raw8<kHalf>(*reinterpret_cast<const uint4*>(st + L.v_bytes + r * 128 + ((c ^ (r & 7)) << 4)), f8);
-            ssl[k] += (f8[0] * f8[0] + f8[1] * f8[1]) + (f8[2] * f8[2] + f8[3] * f8[3]) +
-                      ((f8[4] * f8[4] + f8[5] * f8[5]) + (f8[6] * f8[6] + f8[7] * f8[7]));
+            unpack_raw8<kHalf>(*reinterpret_cast<const uint4*>(st + v_bytes + r * 128 + ((c ^ (r & 7)) << 4)), f8);
             const float m = msk[r];
 #pragma unroll
             for (int i = 0; i < 8; ++i) al[i] = fmaf(m, f8[i], al[i]);
@@ -293,62 +327,76 @@ sparc_fwd3_kernel(const __grid_constant__ CUtensorMap tmV0, const __grid_constan
           if ((lane & 17) == 0) poolp[hf * D + u * 64 + 8 * c + (lane >> 1)] = sv;
         }
       }
-#pragma unroll
-      for (int k = 0; k < 4; ++k) { const int r = lane + 32 * (2 * k + hf); if (r < NP) part[c * (NP + NT) + r] = ssv[k]; }
-#pragma unroll
-      for (int k = 0; k < 2; ++k) { const int r = lane + 32 * (2 * k + hf); if (r < NT) part[c * (NP + NT) + NP + r] = ssl[k]; }
-      f3_epi_bar();
-      for (int i = tid; i < NP + NT; i += 512) {
-        float ss = 0.f;
-#pragma unroll
-        for (int w = 0; w < 8; ++w) ss += part[w * (NP + NT) + i];
-        if (i < NP) {
-          const float n = (i < P) ? 1.f / fmaxf(sqrtf(ss), kF3NormEps) : 0.f;
-          ivn[i] = n;
-          if (i < P) p.inv_vn[(size_t)b * P + i] = n;
-        } else {
-          const int t = i - NP;
-          const float n = (t < T) ? 1.f / fmaxf(sqrtf(ss), kF3NormEps) : 0.f;
-          iln[t] = n;
-          if (t < T) p.inv_ln[(size_t)b * T + t] = n;
-        }
+    }
+    stamp();
+    mbar_wait_sleep(s_full, 0);
+    tc_fence_after();
+    stamp();
+    // ---- row norms from the Gram diagonals (TMEM lane i, column i of its 32 x 32 diagonal block)
+    const int mb = grp & 1, chh = grp >> 1;
+    const int prow = 128 * mb + 32 * q + lane;          // patch of this thread
+    const bool e1_act = mb < MB;
+    if (chh == 0 && e1_act) {
+      float r[32];
+      tmem_ld32(tq + cGV + mb * 128 + 32 * q, r);
+      tmem_ld_wait();
+      const float ss = f3_pick32(r, lane);
+      if (prow < NP) {
+        const float n = (prow < P) ? 1.f / fmaxf(sqrtf(ss), kF3NormEps) : 0.f;
+        ivn[prow] = n;
+        if (prow < P) p.inv_vn[(size_t)b * P + prow] = n;
       }
-      {
-        float cnt = 0.f;
-        for (int t = 0; t < T; ++t) cnt += msk[t];
-        const float inv_cnt = 1.f / fmaxf(cnt, kF3ClampEps), invPm = 1.f / (float)P;
-        for (int i = tid; i < D; i += 512) {
-          p.pooled_l[(size_t)b * D + i] = (poolp[2 * D + i] + poolp[3 * D + i]) * inv_cnt;
-          if (!pool_tc) p.pooled_v[(size_t)b * D + i] = (poolp[i] + poolp[D + i]) * invPm;
-        }
+    } else if (chh == 1 && mb == 0 && 32 * q < NT) {
+      float r[32];
+      if (32 * q + 32 <= NT) tmem_ld32(tq + cGL + 32 * q, r);
+      else {
+        tmem_ld16(tq + cGL + 32 * q, r);
+#pragma unroll
+        for (int i = 16; i < 32; ++i) r[i] = 0.f;
       }
-      f3_epi_bar();
+      tmem_ld_wait();
+      const float ss = f3_pick32(r, lane);
+      const int t = 32 * q + lane;
+      if (t < NT) {
+        const float n = (t < T) ? 1.f / fmaxf(sqrtf(ss), kF3NormEps) : 0.f;
+        cst[t].x = n;
+        if (t < T) p.inv_ln[(size_t)b * T + t] = n;
+      }
+    }
+    {
+      float cnt = 0.f;
+      for (int t = 0; t < T; ++t) cnt += msk[t];
+      const float inv_cnt = 1.f / fmaxf(cnt, kF3ClampEps), invPm = 1.f / (float)P;
+      const float* poolp = reinterpret_cast<const float*>(TH);
+      f3_epi_bar();                                       // pooled partials, ivn, 1/||l|| complete
+      for (int i = tid; i < D; i += 512) {
+        p.pooled_l[(size_t)b * D + i] = (poolp[2 * D + i] + poolp[3 * D + i]) * inv_cnt;
+        if (!pool_tc) p.pooled_v[(size_t)b * D + i] = (poolp[i] + poolp[D + i]) * invPm;
+      }
     }
     stamp();
 
     // ---- E1: thread = patch.  (mb, column half) from the warp group; warps of a non-existent M block idle.
-    const int mb = grp & 1, chh = grp >> 1;
-    const int prow = 128 * mb + 32 * q + lane;          // patch of this thread
-    const bool e1_act = mb < MB;
     const bool live = e1_act && prow < P;
     const float ivp = (e1_act && prow < NP) ? ivn[prow] : 0.f;
     const int cw = NT / 2, c_lo = chh * cw;             // NT / 2 is a multiple of 8
     const int combo = mb * 4 + q;
     const float invP = 1.f / (float)P;
-    mbar_wait(s_full, 0);
-    tc_fence_after();
-    stamp();
     if (e1_act) {
-      for (int c0 = c_lo; c0 < c_lo + cw; c0 += 8) {
-        float x[8];
-        tmem_ld8(tq + mb * NT + c0, x);
-        tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float s = x[j] * ivp * iln[c0 + j];
-          const float lo = warp_redux_min(live ? s : CUDART_INF_F);
-          const float hi = warp_redux_max(live ? s : -CUDART_INF_F);
-          if (lane == j) *reinterpret_cast<float2*>(part_mm + (combo * NT + c0 + j) * 2) = make_float2(lo, hi);
+      for (int g8 = 0; g8 < 5; ++g8) {
+        const int c0 = c_lo + 8 * g8;
+        if (8 * g8 < cw) {
+          float x[8];
+          tmem_ld8(tq + mb * NT + c0, x);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float s = __fmul_rn(__fmul_rn(x[j], ivp), cst[c0 + j].x);
+            const float lo = warp_redux_min(live ? s : CUDART_INF_F);
+            const float hi = warp_redux_max(live ? s : -CUDART_INF_F);
+            if (lane == j) *reinterpret_cast<float2*>(part_mm + (combo * NT + c0 + j) * 2) = make_float2(lo, hi);
+          }
         }
       }
     }
@@ -362,38 +410,45 @@ sparc_fwd3_kernel(const __grid_constant__ CUtensorMap tmV0, const __grid_constan
           const float2 t2 = *reinterpret_cast<const float2*>(part_mm + (w * NT + c_lo + j) * 2);
           mn = fminf(mn, t2.x); mx = fmaxf(mx, t2.y);
         }
+        const bool valid = msk[c_lo + j] != 0.f;
         mnf[c_lo + j] = mn;
-        irf[c_lo + j] = 1.f / (mx - mn + kF3MinMaxEps);
+        cst[c_lo + j].y = valid ? mn : CUDART_INF_F;     // masked token: nn = -inf, nothing kept, no arg-min
+        cst[c_lo + j].z = 1.f / (mx - mn + kF3MinMaxEps);
       }
       __syncwarp();
-      for (int c0 = c_lo; c0 < c_lo + cw; c0 += 8) {
-        float x[8], th[8], sr[8];
-        tmem_ld8(tq + mb * NT + c0, x);
-        tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int t = c0 + j;
-          const float s = x[j] * ivp * iln[t];
-          const float mn = mnf[t];
-          const float nn = (s - mn) * irf[t];
-          const bool valid = msk[t] != 0.f;
-          if (live && valid && s == mn) atomicMin(imn + t, prow);      // first arg-min patch, like torch.min
-          th[j] = (live && valid && !(nn < p.thr)) ? nn : 0.f;
-          if (pool_tc && t == T) th[j] = live ? invP : 0.f;           // spare column: G'[:, T] = mean_p v[p]
-          sr[j] = live ? x[j] : 0.f;
+      for (int g8 = 0; g8 < 5; ++g8) {
+        const int c0 = c_lo + 8 * g8;
+        if (8 * g8 < cw) {
+          float x[8], th[8], sr[8];
+          tmem_ld8(tq + mb * NT + c0, x);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 c4 = cst[c0 + j];
+            const float s = __fmul_rn(__fmul_rn(x[j], ivp), c4.x);     // same roundings as sweep 1 and as the backward
+            const float nn = __fmul_rn(__fsub_rn(s, c4.y), c4.z);
+            if (live && s == c4.y) atomicMin(imn + c0 + j, prow);        // first arg-min patch, like torch.min
+            th[j] = (live && !(nn < p.thr)) ? nn : 0.f;
+            sr[j] = live ? x[j] : 0.f;
+          }
+          if (pool_tc && c0 <= T && T < c0 + 8) {                        // spare column: G'[:, T] = mean_p v[p]
+#pragma unroll
+            for (int j = 0; j < 8; ++j) if (c0 + j == T) th[j] = live ? invP : 0.f;
+          }
+          if (prow < NP) {
+            uint4 hi, lo;
+            const uint32_t off = (uint32_t)((c0 >> 3) * NP + prow) * 16;
+            split_hilo8(th, hi, lo);
+            *reinterpret_cast<uint4*>(TH + off) = hi;
+            *reinterpret_cast<uint4*>(TH + plane + off) = lo;
+            split_hilo8(sr, hi, lo);
+            *reinterpret_cast<uint4*>(SR + off) = hi;
+            *reinterpret_cast<uint4*>(SR + plane + off) = lo;
+          }
+          const float cs = warp_colsum8(th, lane);
+          if ((lane & 17) == 0) part_s[combo * NT + c0 + (lane >> 1)] = cs;
         }
-        if (prow < NP) {
-          uint4 hi, lo;
-          const uint32_t off = (uint32_t)((c0 >> 3) * NP + prow) * 16;
-          split_hilo8(th, hi, lo);
-          *reinterpret_cast<uint4*>(TH + off) = hi;
-          *reinterpret_cast<uint4*>(TH + L.plane + off) = lo;
-          split_hilo8(sr, hi, lo);
-          *reinterpret_cast<uint4*>(SR + off) = hi;
-          *reinterpret_cast<uint4*>(SR + L.plane + off) = lo;
-        }
-        const float cs = warp_colsum8(th, lane);
-        if ((lane & 17) == 0) part_s[combo * NT + c0 + (lane >> 1)] = cs;
       }
     }
     tc_fence_before();
@@ -409,7 +464,7 @@ sparc_fwd3_kernel(const __grid_constant__ CUtensorMap tmV0, const __grid_constan
       const float sigma = fmaxf(sg, kF3ClampEps);
       isg[tid] = valid ? 1.f / sigma : 0.f;
       if (tid < T) {
-        float4 st4 = make_float4(mnf[tid], irf[tid], sigma, __int_as_float(imn[tid]));
+        float4 st4 = make_float4(mnf[tid], cst[tid].z, sigma, __int_as_float(imn[tid]));
         *reinterpret_cast<float4*>(p.stats + ((size_t)b * T + tid) * 4) = st4;
       }
     }
@@ -422,42 +477,47 @@ sparc_fwd3_kernel(const __grid_constant__ CUtensorMap tmV0, const __grid_constan
     float gn2[20];
 #pragma unroll
     for (int k = 0; k < 20; ++k) gn2[k] = 0.f;
-    for (int blk = 0; blk < L.NBLK; ++blk) {
-      const int buf = blk & 1;
-      mbar_wait(g_full + buf, (blk >> 1) & 1);
-      tc_fence_after();
-      const size_t dcol = (size_t)blk * 128 + dl;
-      bf16* gh = p.g_split + ((size_t)b * 2) * T * D + dcol;
-      bf16* gl = gh + (size_t)T * D;
-      const uint32_t tg = tq + cG + buf * NT2 + g_lo;
+    {
+      const size_t pstride = (size_t)T * D;
+      bf16* gh0 = p.g_split + ((size_t)b * 2) * pstride + (size_t)g_lo * D + dl;
+      const int kpool = pool_tc ? T - g_lo : -1;        // local index of the spare column in this group (if any)
+      for (int blk = 0; blk < NBLK; ++blk) {
+        const int buf = blk & 1;
+        mbar_wait_sleep(g_full + buf, (blk >> 1) & 1);
+        tc_fence_after();
+        bf16* gh = gh0 + blk * 128;
+        bf16* gl = gh + pstride;
+        const uint32_t tg = tq + cG + buf * NT2 + g_lo;
 #pragma unroll
-      for (int c = 0; c < 20; c += 4) {                  // 4 columns at a time: hi-part and lo-part of the same tokens
-        if (c < gw_) {
-          float xh[4], xl[4];
-          tmem_ld4(tg + c, xh);
-          tmem_ld4(tg + NT + c, xl);
-          tmem_ld_wait();
-          if (c + 4 >= gw_) {                            // last chunk: the accumulator is in registers
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(g_free + buf);
-          }
+        for (int c = 0; c < 20; c += 4) {                  // 4 columns at a time: hi-part and lo-part of the same tokens
+          if (c < gw_) {
+            float xh[4], xl[4];
+            tmem_ld4(tg + c, xh);
+            tmem_ld4(tg + NT + c, xl);
+            const float4 is4 = *reinterpret_cast<const float4*>(isg + g_lo + c);
+            tmem_ld_wait();
+            if (c + 4 >= gw_) {                            // last chunk: the accumulator is in registers
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(g_free + buf);
+            }
+            const float isv[4] = {is4.x, is4.y, is4.z, is4.w};
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const int t = g_lo + c + k;
-            const float raw = xh[k] + xl[k];
-            if (pool_tc && t == T) p.pooled_v[(size_t)b * D + dcol] = raw;
-            const float g = raw * isg[t];
-            gn2[c + k] = fmaf(g, g, gn2[c + k]);
-            if (t < T) {
-              const bf16 h = __float2bfloat16_rn(g);
-              gh[(size_t)t * D] = h;
-              gl[(size_t)t * D] = __float2bfloat16_rn(g - __bfloat162float(h));
+            for (int k = 0; k < 4; ++k) {
+              const float raw = xh[k] + xl[k];
+              if (c + k == kpool) p.pooled_v[(size_t)b * D + blk * 128 + dl] = raw;
+              const float g = raw * isv[k];
+              gn2[c + k] = fmaf(g, g, gn2[c + k]);
+              if (g_lo + c + k < T) {
+                const bf16 h = __float2bfloat16_rn(g);
+                gh[(size_t)(c + k) * D] = h;
+                gl[(size_t)(c + k) * D] = __float2bfloat16_rn(g - __bfloat162float(h));
+              }
             }
           }
         }
+        if (blk == 0) stamp();
       }
-      if (blk == 0) stamp();
     }
 #pragma unroll
     for (int k = 0; k < 20; ++k) {
@@ -470,66 +530,78 @@ sparc_fwd3_kernel(const __grid_constant__ CUtensorMap tmV0, const __grid_constan
     if (tid < NT) {
       const float s = (part_s[tid] + part_s[NT + tid]) + (part_s[2 * NT + tid] + part_s[3 * NT + tid]);
       const float n = 1.f / fmaxf(sqrtf(s), kF3NormEps);
-      ign[tid] = n;
+      csc[tid] = (msk[tid] != 0.f) ? p.scale * isg[tid] * n : 0.f;
       if (tid < T) p.g_inv_norm[(size_t)b * T + tid] = n;
     }
     f3_epi_bar();
     stamp();
 
     // ---- E3: logits[t][j] = s L'[t][j] / (sigma_t ||G_t|| ||l_j||)  (TMEM: lane = j, columns = t), masked LSE both ways
-    mbar_wait(l_full, 0);
+    mbar_wait_sleep(l_full, 0);
     tc_fence_after();
     float* Lb = reinterpret_cast<float*>(SR);           // [NT][NT + 1], the S_raw^T region is free once L' is done
     const int ldl = NT + 1;
     const int jrow = 32 * q + lane;
     if (32 * q < NT) {                                  // warp-uniform: tcgen05.ld needs the whole warp
       const bool jin = jrow < NT;
-      const bool vj = jin && msk[jrow] != 0.f;
-      const float ilj = jin ? iln[jrow] : 0.f;
+      const bool vj = jin && msk[jin ? jrow : 0] != 0.f;
+      const float ilj = jin ? cst[jrow].x : 0.f;
+      float* lrow = Lb + g_lo * ldl + jrow;
+      float* grow = p.tt_logits ? p.tt_logits + ((size_t)b * T + g_lo) * T + jrow : nullptr;
 #pragma unroll
       for (int c = 0; c < 20; c += 4) {
         if (c < gw_) {
           float xh[4], xl[4];
           tmem_ld4(tq + g_lo + c, xh);
           tmem_ld4(tq + NT + g_lo + c, xl);
+          const float4 cs4 = *reinterpret_cast<const float4*>(csc + g_lo + c);
           tmem_ld_wait();
+          const float csv[4] = {cs4.x, cs4.y, cs4.z, cs4.w};
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
-            const int t = g_lo + c + k;
-            const bool on = vj && msk[t] != 0.f;
-            const float y = on ? (xh[k] + xl[k]) * (p.scale * isg[t] * ign[t]) * ilj : -CUDART_INF_F;
-            if (jin) Lb[t * ldl + jrow] = y;
-            if (p.tt_logits && t < T && jrow < T) p.tt_logits[((size_t)b * T + t) * T + jrow] = y;
+            const bool on = vj && csv[k] != 0.f;
+            const float y = on ? (xh[k] + xl[k]) * csv[k] * ilj : -CUDART_INF_F;
+            if (jin) lrow[(c + k) * ldl] = y;
+            if (grow && g_lo + c + k < T && jrow < T) grow[(size_t)(c + k) * T] = y;
           }
         }
       }
     }
     f3_epi_bar();
     stamp();
-    float ce_r = 0.f, ce_c = 0.f;
-    for (int t = ew; t < T; t += kF3EpiWarps) {          // row direction: softmax over j for token t (loss_vl_local)
-      float m = -CUDART_INF_F;
-      for (int j = lane; j < T; j += 32) m = fmaxf(m, Lb[t * ldl + j]);
-      m = warp_max(m);
-      float s = 0.f;
-      for (int j = lane; j < T; j += 32) { const float y = Lb[t * ldl + j]; s += (y == -CUDART_INF_F) ? 0.f : __expf(y - m); }
-      s = warp_sum(s);
-      const bool valid = msk[t] != 0.f;
-      const float lse = valid ? m + logf(s) : 0.f;
-      if (lane == 0) { p.lse_row[(size_t)b * T + t] = lse; if (valid) ce_r += lse - Lb[t * ldl + t]; }
+    // LSE: 4 threads per row / column, a quarter of the entries each.  |logit| <= |scale| (cosines), so for moderate
+    // scales a fixed shift replaces the max pass (exp never overflows and cannot flush the whole sum to zero).
+    {
+      const int r = tid >> 2, seg = tid & 3;
+      const int sw = (NT + 3) / 4, s_lo = seg * sw, s_hi = min(T, s_lo + sw);
+      const bool fixed = fabsf(p.scale) <= 30.f;
+      const bool rin = r < T;
+      const bool valid = rin && msk[rin ? r : 0] != 0.f;
+#pragma unroll
+      for (int dir = 0; dir < 2; ++dir) {                // 0: row direction (softmax over j), 1: column direction (over t)
+        const int st_r = dir ? 1 : ldl, st_c = dir ? ldl : 1;
+        const float* src = Lb + (rin ? r : 0) * st_r;
+        float m = fabsf(p.scale) * 1.0001f;
+        if (!fixed) {
+          m = -CUDART_INF_F;
+          for (int j = s_lo; j < s_hi; ++j) m = fmaxf(m, src[j * st_c]);
+          m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
+          m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
+        }
+        float s = 0.f;
+        for (int j = s_lo; j < s_hi; ++j) { const float y = src[j * st_c]; s += (y == -CUDART_INF_F) ? 0.f : __expf(y - m); }
+        s += __shfl_xor_sync(0xffffffffu, s, 1);
+        s += __shfl_xor_sync(0xffffffffu, s, 2);
+        const float lse = valid ? m + logf(s) : 0.f;
+        float ce = 0.f;
+        if (rin && seg == 0) {
+          (dir ? p.lse_col : p.lse_row)[(size_t)b * T + r] = lse;
+          if (valid) ce = lse - Lb[r * ldl + r];
+        }
+        const float tot = warp_sum(ce);
+        if (lane == 0) red[dir * kF3EpiWarps + ew] = tot;
+      }
     }
-    for (int j = ew; j < T; j += kF3EpiWarps) {          // column direction: softmax over t for token j (loss_lv_local)
-      float m = -CUDART_INF_F;
-      for (int t = lane; t < T; t += 32) m = fmaxf(m, Lb[t * ldl + j]);
-      m = warp_max(m);
-      float s = 0.f;
-      for (int t = lane; t < T; t += 32) { const float y = Lb[t * ldl + j]; s += (y == -CUDART_INF_F) ? 0.f : __expf(y - m); }
-      s = warp_sum(s);
-      const bool valid = msk[j] != 0.f;
-      const float lse = valid ? m + logf(s) : 0.f;
-      if (lane == 0) { p.lse_col[(size_t)b * T + j] = lse; if (valid) ce_c += lse - Lb[j * ldl + j]; }
-    }
-    if (lane == 0) { red[ew] = ce_r; red[kF3EpiWarps + ew] = ce_c; }
     f3_epi_bar();
     if (tid == 0) {
       float a = 0.f, c = 0.f;
@@ -566,8 +638,14 @@ int sparc_fwd3_launch(const void* v, const void* l, const uint8_t* mask, int B, 
   Fwd3Params prm{prof, P, T, D, thr, scale, mask, row_inv_norm, row_inv_norm + (size_t)B * P, pooled_v, pooled_l, lse_row,
                  lse_col, local_partial, tt_logits, g_inv_norm, (bf16*)g_split, stats};
   const size_t smem = L.total + 1024;
-  CFA_CUDA_TRY(cudaFuncSetAttribute(sparc_fwd3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  sparc_fwd3_kernel<false><<<B, kF3Threads, smem, st>>>(tmV0, tmV1, tmL, prm);
+#define CFA_F3_LAUNCH(NT_, NP_, D_)                                                                                         \
+  do {                                                                                                                      \
+    CFA_CUDA_TRY(cudaFuncSetAttribute(sparc_fwd3_kernel<NT_, NP_, D_, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    sparc_fwd3_kernel<NT_, NP_, D_, false><<<B, kF3Threads, smem, st>>>(tmV0, tmV1, tmL, prm);                              \
+  } while (0)
+  if (L.NT == 80 && L.NP == 208 && D == 512) CFA_F3_LAUNCH(80, 208, 512);      // ViT-B/16 (P = 196 / 197, T = 77)
+  else CFA_F3_LAUNCH(0, 0, 0);
+#undef CFA_F3_LAUNCH
   return launch_status();
 }
 

@@ -31,6 +31,28 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
   return ok != 0;
 }
+// same with a suspend-time hint (ns): the waiting thread sleeps in hardware until the phase completes (or the hint runs
+// out) instead of re-issuing the probe — spinning warps otherwise take issue slots from the warps that do the work
+__device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parity, uint32_t ns) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity), "r"(ns) : "memory");
+  return ok != 0;
+}
+// Bounded wait for the third-generation kernels: long hardware sleeps, clock check only once per wake-up
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait_hint(bar, parity, 20000u)) {
+    if (clock64() - t0 > 4000000000LL) {
+      printf("cfa: mbarrier timeout block %d thread %d bar %u parity %u\n", blockIdx.x, threadIdx.x, smem_u32(bar), parity);
+      __trap();
+    }
+  }
+}
 // Bounded wait: a protocol bug traps after ~2 s instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
