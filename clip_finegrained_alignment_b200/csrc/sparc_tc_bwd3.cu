@@ -35,18 +35,18 @@ constexpr float kB3ClampEps = 1e-8f;
 struct Bwd3Layout {
   int NP, NT, MB, KB0, NBLK, CR0, NCH, NSP;
   uint32_t v_bytes, l_bytes, slotP, slot4, plane, dlb;
-  uint32_t off_sr, off_w, off_ring4, off_ldp, off_dl, off_f, off_bar, total;
+  uint32_t off_sr, off_w, off_ring4, off_stage, off_ldp, off_dl, off_f, off_bar, total;
 };
 
 __host__ __device__ inline Bwd3Layout bwd3_layout(int P, int T, int D) {
   Bwd3Layout L;
   L.NP = (P + 15) & ~15; L.NT = (T + 15) & ~15; L.MB = L.NP > 128 ? 2 : 1; L.KB0 = D / 64; L.NBLK = D / 128;
-  L.NCH = L.NP > 128 ? 2 : 1;
-  L.CR0 = L.NCH == 2 ? 16 * ((L.NP + 31) / 32) : L.NP;
+  // P4 streams v in chunks of NT patch rows, so that every P4 tile pair (v chunk, l, G hi, G lo) is [NT x 128 d]
+  L.CR0 = L.NT;
+  L.NCH = (L.NP + L.NT - 1) / L.NT;
   L.v_bytes = (uint32_t)L.NP * 128; L.l_bytes = (uint32_t)L.NT * 128;
   L.slotP = L.v_bytes + 3 * L.l_bytes;
-  const uint32_t vch = 2u * L.CR0 * 128, ltl = 2u * L.l_bytes;
-  L.slot4 = vch > ltl ? vch : ltl;
+  L.slot4 = 2u * L.l_bytes;
   L.plane = (uint32_t)L.NT * L.NP * 2;
   L.dlb = (uint32_t)L.NT * L.NT * 2;
   const uint32_t op = (2 * L.plane + 1023) & ~1023u;
@@ -63,6 +63,9 @@ __host__ __device__ inline Bwd3Layout bwd3_layout(int P, int T, int D) {
     if (p1_end + ldp > dl0) dl0 = p1_end + ldp;
     dl0 = (dl0 + 127) & ~127u;
     uint32_t end = dl0 + 2 * L.dlb;
+    // per-warp transposition tiles of the P4 output epilogue [8][36] fp32, behind the P4 ring (used after ds_ready only)
+    L.off_stage = L.off_ring4 + 3 * L.slot4;
+    if (L.off_stage + (uint32_t)kB3EpiWarps * 8u * 36u * 4u > end) end = L.off_stage + (uint32_t)kB3EpiWarps * 8u * 36u * 4u;
     // scratch of E3' (column partials [2][8][NT], row partials [2][NP]) lives in the dead dLhat region
     const uint32_t e3 = (16u * L.NT + 2u * L.NP) * 4;
     if (dl0 + e3 > end) end = dl0 + e3;
@@ -113,12 +116,12 @@ sparc_bwd3_kernel(const __grid_constant__ CUtensorMap tmV0, const __grid_constan
   uint8_t* base = CFA_SMEM_BASE_1024(smem_raw);
   const Bwd3Layout L = bwd3_layout(p.P, p.T, kD ? kD : p.D);
   const int NP = kNP ? kNP : L.NP, NT = kNT ? kNT : L.NT, D = kD ? kD : p.D;
-  const int MB = NP > 128 ? 2 : 1, KB0 = D / 64, NBLK = D / 128, NCH = MB;
-  const int CR0 = NCH == 2 ? 16 * ((NP + 31) / 32) : NP;
+  const int MB = NP > 128 ? 2 : 1, KB0 = D / 64, NBLK = D / 128;
+  const int CR0 = NT, NCH = (NP + NT - 1) / NT;       // P4: v in chunks of NT patch rows
   const int NSP = L.NSP, P = p.P, T = p.T;
   const int NT2 = 2 * NT, NT3 = 3 * NT;
   const uint32_t v_bytes = (uint32_t)NP * 128, l_bytes = (uint32_t)NT * 128, slotP = v_bytes + 3 * l_bytes;
-  const uint32_t slot4 = (2u * CR0 * 128 > 2u * l_bytes) ? 2u * CR0 * 128 : 2u * l_bytes;
+  const uint32_t slot4 = 2u * l_bytes;
   const uint32_t plane = (uint32_t)NT * NP * 2, dlb = (uint32_t)NT * NT * 2;
   const int b = blockIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -192,6 +195,12 @@ sparc_bwd3_kernel(const __grid_constant__ CUtensorMap tmV0, const __grid_constan
       cD[t].x = isg;
     }
   }
+  if (warp == 2) {                                     // mdl[t] = m_t / (number of valid tokens)   (losses.py:211 backward)
+    float c = 0.f;
+    for (int t = lane; t < T; t += 32) c += p.mask[(size_t)b * T + t] ? 1.f : 0.f;
+    c = 1.f / fmaxf(warp_sum(c), kB3ClampEps);
+    for (int t = lane; t < NT; t += 32) mdl[t] = (t < T && p.mask[(size_t)b * T + t]) ? c : 0.f;
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -221,9 +230,9 @@ sparc_bwd3_kernel(const __grid_constant__ CUtensorMap tmV0, const __grid_constan
         if (i == 2) mbar_wait_sleep(ds_ready, 0);
         uint8_t* st = ring4 + (size_t)s * slot4;
         if (w < NCH) {
-          mbar_expect_tx(full4 + s, 2u * CR0 * 128);
+          mbar_expect_tx(full4 + s, 2 * l_bytes);
           tma_load_3d(st, &tmV1, full4 + s, blk * 128, w * CR0, b);
-          tma_load_3d(st + CR0 * 128, &tmV1, full4 + s, blk * 128 + 64, w * CR0, b);
+          tma_load_3d(st + l_bytes, &tmV1, full4 + s, blk * 128 + 64, w * CR0, b);
         } else {
           const CUtensorMap* tm = (w == NCH) ? &tmL : &tmG;
           const int pl = (w == NCH) ? b : (w == NCH + 1 ? 2 * b : 2 * b + 1);
@@ -248,9 +257,8 @@ sparc_bwd3_kernel(const __grid_constant__ CUtensorMap tmV0, const __grid_constan
     auto stamp = [&]() { if (pf) pf[pi++] = clock64(); };
     stamp();
     // ---- P1
-    for (int u = 0; u < KB0; ++u) {
-      const int s = u % NSP;
-      mbar_wait_sleep(fullP + s, (u / NSP) & 1);
+    for (int u = 0, s = 0, ph = 0; u < KB0; ++u) {
+      mbar_wait_sleep(fullP + s, ph);
       tc_fence_after();
       const uint32_t sv = smem_u32(ringP + (size_t)s * slotP), sb = sv + v_bytes;
       const uint64_t dv0 = sw0 | (sv >> 4), db0 = sw0 | (sb >> 4);
@@ -263,6 +271,7 @@ sparc_bwd3_kernel(const __grid_constant__ CUtensorMap tmV0, const __grid_constan
         }
       }
       umma_commit_w(leader, emptyP + s);
+      if (++s == NSP) { s = 0; ph ^= 1; }
     }
     umma_commit_w(leader, s_full);
     stamp();
@@ -306,26 +315,25 @@ sparc_bwd3_kernel(const __grid_constant__ CUtensorMap tmV0, const __grid_constan
     tc_fence_after();
     stamp();
     const uint64_t m_ds = make_smem_desc(smem_u32(SR), 128, np16, kLayoutNone);          // dShat'^T hi|lo, MN-major (N = t, K = p)
-    int i4 = 0;
+    int s4 = 0, ph4 = 0;
     long long wfull = 0, wfree = 0;
     for (int blk = 0; blk < NBLK; ++blk) {
       // unit A: dl^T
       { const long long w0 = clock64(); mbar_wait_sleep(oa_free, (blk & 1) ^ 1); wfree += clock64() - w0; }
       tc_fence_after();
-#pragma unroll
-      for (int ch = 0; ch < 2; ++ch) {
-        if (ch < NCH) {
-          const int s = i4 % 3;
-          { const long long w0 = clock64(); mbar_wait_sleep(full4 + s, (i4 / 3) & 1); wfull += clock64() - w0; }
+      for (int ch = 0; ch < NCH; ++ch) {
+        {
+          const int s = s4;
+          { const long long w0 = clock64(); mbar_wait_sleep(full4 + s, ph4); wfull += clock64() - w0; }
           tc_fence_after();
           const uint32_t sa = smem_u32(ring4 + (size_t)s * slot4);
-          const uint64_t da = make_smem_desc(sa, (uint32_t)CR0 * 128, 1024, kLayoutSw128);
-          const int r0 = ch * CR0, nk = (ch == 0 ? CR0 : NP - CR0) / 16;
+          const uint64_t da = make_smem_desc(sa, l_bytes, 1024, kLayoutSw128);
+          const int r0 = ch * CR0, nk = min(CR0, NP - r0) / 16;
           const uint64_t db = m_ds + (uint32_t)r0;
 #pragma unroll
-          for (int ks = 0; ks < 8; ++ks) if (ks < nk) umma_ss_w(leader, tmem + cDL, da + ks * 128, db + ks * 16, id_dl, (ch | ks) != 0);
+          for (int ks = 0; ks < 5; ++ks) if (ks < nk) umma_ss_w(leader, tmem + cDL, da + ks * 128, db + ks * 16, id_dl, (ch | ks) != 0);
           umma_commit_w(leader, empty4 + s);
-          ++i4;
+          if (++s4 == 3) { s4 = 0; ph4 ^= 1; }
         }
       }
       umma_commit_w(leader, oa_full);
@@ -333,9 +341,9 @@ sparc_bwd3_kernel(const __grid_constant__ CUtensorMap tmV0, const __grid_constan
       { const long long w0 = clock64(); mbar_wait_sleep(ob_free, (blk & 1) ^ 1); wfree += clock64() - w0; }
       tc_fence_after();
 #pragma unroll
-      for (int w = 0; w < 3; ++w, ++i4) {
-        const int s = i4 % 3;
-        { const long long w0 = clock64(); mbar_wait_sleep(full4 + s, (i4 / 3) & 1); wfull += clock64() - w0; }
+      for (int w = 0; w < 3; ++w) {
+        const int s = s4;
+        { const long long w0 = clock64(); mbar_wait_sleep(full4 + s, ph4); wfull += clock64() - w0; }
         tc_fence_after();
         const uint32_t sa = smem_u32(ring4 + (size_t)s * slot4);
         const uint64_t da = make_smem_desc(sa, l_bytes, 1024, kLayoutSw128);             // [NT x 64] tile pair, MN-major (M = d)
@@ -354,6 +362,7 @@ sparc_bwd3_kernel(const __grid_constant__ CUtensorMap tmV0, const __grid_constan
           for (int ks = 0; ks < 5; ++ks) if (ks < nksT) umma_ss_w(leader, tmem + cDV, da + ks * 128, k_wh + ks * ksA, id_dg, true);
         }
         umma_commit_w(leader, empty4 + s);
+        if (++s4 == 3) { s4 = 0; ph4 ^= 1; }
       }
       umma_commit_w(leader, ob_full);
     }
@@ -569,28 +578,43 @@ sparc_bwd3_kernel(const __grid_constant__ CUtensorMap tmV0, const __grid_constan
     }
     b3_epi_bar();
     for (int i = tid; i < NP; i += 512) vfac[i] = (vqp[i] + vqp[NP + i]) * ivn[i] * ivn[i];
-    {
-      float cnt = 0.f;
-      for (int t = 0; t < T; ++t) cnt += msk[t];
-      const float invc = 1.f / fmaxf(cnt, kB3ClampEps);
-      if (tid < NT) mdl[tid] = msk[tid] * invc;
-    }
     tc_fence_before();
     fence_proxy_async();
     b3_epi_bar();
     if (lane == 0) mbar_arrive(ds_ready);
     stamp();
 
-    // ---- P4 outputs: thread = feature column d of the block; group -> a quarter of the token / patch columns
+    // ---- P4 outputs.  Arithmetic on the accumulators happens with thread = feature column d (TMEM layout), but every
+    // global access is TRANSPOSED through a per-warp shared-memory tile [8 rows][32 d]: lane -> (row r = lane / 4, 16-byte
+    // chunk ch4 = lane % 4), so one LDG / STG moves 8 rows x 64 contiguous bytes.  (2-byte accesses -- one row per
+    // instruction -- are bound by the LSU instruction rate: 64 bytes per warp instruction is the HBM rate per SM.)
     const float invP = 1.f / (float)P;
     const int tw = NT / 4, t_lo = grp * tw;              // multiple of 4
     const int pw = NP / 4, p_lo = grp * pw;              // multiple of 4
     const int dloc = 32 * q + lane;
-    const bf16* lsrc0 = p.l + ((size_t)b * T + t_lo) * D + dloc;
-    bf16* ldst0 = p.dl + ((size_t)b * T + t_lo) * D + dloc;
-    const bf16* vsrc0 = p.v + ((size_t)b * P + p_lo) * D + dloc;
-    bf16* vdst0 = p.dv + ((size_t)b * P + p_lo) * D + dloc;
+    const int tr = lane >> 2, tc8 = (lane & 3) * 8;      // transposed role: row inside the chunk, first of 8 columns
+    float* stg = reinterpret_cast<float*>(base + L.off_stage) + ew * (8 * 36);
     const int tn = max(0, min(tw, T - t_lo)), pn = max(0, min(pw, P - p_lo));     // live tokens / patches of this group
+    const size_t drow = (size_t)32 * q + tc8;            // column offset of this thread's 16-byte piece inside a block
+    const bf16* lsrc0 = p.l + ((size_t)b * T + t_lo + tr) * D + drow;
+    bf16* ldst0 = p.dl + ((size_t)b * T + t_lo + tr) * D + drow;
+    const bf16* vsrc0 = p.v + ((size_t)b * P + p_lo + tr) * D + drow;
+    bf16* vdst0 = p.dv + ((size_t)b * P + p_lo + tr) * D + drow;
+    // one chunk of 8 (or 4) columns: x[k] (+ per-d term already added) -> tile -> out = x - raw * fac -> global
+    auto emit8 = [&](const float* x, const uint4& raw, float fac, bool row_ok, bf16* dst) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) stg[k * 36 + lane] = x[k];
+      __syncwarp();
+      const float4 a0 = *reinterpret_cast<const float4*>(stg + tr * 36 + tc8);
+      const float4 a1 = *reinterpret_cast<const float4*>(stg + tr * 36 + tc8 + 4);
+      __syncwarp();
+      float rv[8], ov[8];
+      unpack_raw8<kHalf>(raw, rv);
+      ov[0] = fmaf(-rv[0], fac, a0.x); ov[1] = fmaf(-rv[1], fac, a0.y); ov[2] = fmaf(-rv[2], fac, a0.z); ov[3] = fmaf(-rv[3], fac, a0.w);
+      ov[4] = fmaf(-rv[4], fac, a1.x); ov[5] = fmaf(-rv[5], fac, a1.y); ov[6] = fmaf(-rv[6], fac, a1.z); ov[7] = fmaf(-rv[7], fac, a1.w);
+      if (row_ok) *reinterpret_cast<uint4*>(dst) = pack_raw8<kHalf>(ov);
+    };
+    const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
     for (int blk = 0; blk < NBLK; ++blk) {
       const size_t dcol = (size_t)blk * 128 + dloc;
       const float dpl = p.dpool_l ? __ldg(p.dpool_l + (size_t)b * D + dcol) : 0.f;
@@ -598,33 +622,33 @@ sparc_bwd3_kernel(const __grid_constant__ CUtensorMap tmV0, const __grid_constan
       {   // unit A: dl[t][d] = dl^T[d][t] (hi-part + lo-part) - l[t][d] lfac_t + m_t dlbar[d] / cnt
         const bf16* lsrc = lsrc0 + blk * 128;
         bf16* ldst = ldst0 + blk * 128;
-        float raw[20];
+        uint4 raw[3];
 #pragma unroll
-        for (int k = 0; k < 20; ++k) raw[k] = (k < tn) ? b3_raw(lsrc + (size_t)k * D) : 0.f;
+        for (int g = 0; g < 3; ++g)
+          raw[g] = (8 * g < tw && 8 * g + tr < tn) ? __ldg(reinterpret_cast<const uint4*>(lsrc + (size_t)(8 * g) * D)) : zero4;
         mbar_wait_sleep(oa_full, blk & 1);
         tc_fence_after();
 #pragma unroll
-        for (int c = 0; c < 20; c += 4) {
+        for (int g = 0; g < 3; ++g) {
+          const int c = 8 * g;
           if (c < tw) {
-            float xh[4], xl[4];
-            tmem_ld4(tq + cDL + t_lo + c, xh);
-            tmem_ld4(tq + cDL + NT + t_lo + c, xl);
-            const float4 lf4 = *reinterpret_cast<const float4*>(lfacs + t_lo + c);
-            const float4 md4 = *reinterpret_cast<const float4*>(mdl + t_lo + c);
+            float xh[8], xl[8];
+            if (c + 8 <= tw) { tmem_ld8(tq + cDL + t_lo + c, xh); tmem_ld8(tq + cDL + NT + t_lo + c, xl); }
+            else { tmem_ld4(tq + cDL + t_lo + c, xh); tmem_ld4(tq + cDL + NT + t_lo + c, xl); }
+            const float4 md0 = *reinterpret_cast<const float4*>(mdl + t_lo + c);
+            const float4 md1 = (c + 8 <= tw) ? *reinterpret_cast<const float4*>(mdl + t_lo + c + 4) : make_float4(0.f, 0.f, 0.f, 0.f);
             tmem_ld_wait();
-            if (c + 4 >= tw) {                           // last chunk: the accumulator is in registers
+            if (c + 8 >= tw) {                           // last chunk: the accumulator is in registers
               tc_fence_before();
               __syncwarp();
               if (lane == 0) mbar_arrive(oa_free);
             }
-            const float lfv[4] = {lf4.x, lf4.y, lf4.z, lf4.w}, mdv[4] = {md4.x, md4.y, md4.z, md4.w};
+            const float mdv[8] = {md0.x, md0.y, md0.z, md0.w, md1.x, md1.y, md1.z, md1.w};
+            const int nc = (c + 8 <= tw) ? 8 : 4;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              if (c + k < tn) {
-                const float o = fmaf(mdv[k], dpl, fmaf(-raw[c + k], lfv[k], xh[k] + xl[k]));
-                ldst[(size_t)(c + k) * D] = __float2bfloat16_rn(o);
-              }
-            }
+            for (int k = 0; k < 8; ++k) xh[k] = (k < nc) ? fmaf(mdv[k], dpl, xh[k] + xl[k]) : 0.f;
+            const bool ok = c + tr < tn;
+            emit8(xh, raw[g], ok ? lfacs[t_lo + c + tr] : 0.f, ok, ldst + (size_t)c * D);
           }
         }
         if (blk == 0) stamp();
@@ -632,9 +656,7 @@ sparc_bwd3_kernel(const __grid_constant__ CUtensorMap tmV0, const __grid_constan
       {   // unit B: dv[p][d] = dv^T[d][p] - v[p][d] vfac_p + dvbar[d] / P
         const bf16* vsrc = vsrc0 + blk * 128;
         bf16* vdst = vdst0 + blk * 128;
-        float rawc[8], rawn[8];
-#pragma unroll
-        for (int k = 0; k < 8; ++k) rawc[k] = (k < pn) ? b3_raw(vsrc + (size_t)k * D) : 0.f;
+        uint4 rawc = (tr < pn) ? __ldg(reinterpret_cast<const uint4*>(vsrc)) : zero4, rawn = zero4;
         mbar_wait_sleep(ob_full, blk & 1);
         tc_fence_after();
 #pragma unroll
@@ -643,26 +665,19 @@ sparc_bwd3_kernel(const __grid_constant__ CUtensorMap tmV0, const __grid_constan
             float x[8];
             if (c0 + 8 <= pw) tmem_ld8(tq + cDV + p_lo + c0, x);
             else tmem_ld4(tq + cDV + p_lo + c0, x);     // pw is a multiple of 4
-            const float4 vf0 = *reinterpret_cast<const float4*>(vfac + p_lo + c0);
-            const float4 vf1 = (c0 + 8 <= pw) ? *reinterpret_cast<const float4*>(vfac + p_lo + c0 + 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-            for (int k = 0; k < 8; ++k) rawn[k] = (c0 + 8 + k < pn) ? b3_raw(vsrc + (size_t)(c0 + 8 + k) * D) : 0.f;
+            if (c0 + 8 < pw) rawn = (c0 + 8 + tr < pn) ? __ldg(reinterpret_cast<const uint4*>(vsrc + (size_t)(c0 + 8) * D)) : zero4;
             tmem_ld_wait();
             if (c0 + 8 >= pw) {                         // last chunk: the accumulator is in registers
               tc_fence_before();
               __syncwarp();
               if (lane == 0) mbar_arrive(ob_free);
             }
-            const float vfv[8] = {vf0.x, vf0.y, vf0.z, vf0.w, vf1.x, vf1.y, vf1.z, vf1.w};
+            const int nc = (c0 + 8 <= pw) ? 8 : 4;
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
-              if (c0 + k < pn) {
-                const float o = fmaf(-rawc[k], vfv[k], x[k] + dpv);
-                vdst[(size_t)(c0 + k) * D] = __float2bfloat16_rn(o);
-              }
-            }
-#pragma unroll
-            for (int k = 0; k < 8; ++k) rawc[k] = rawn[k];
+            for (int k = 0; k < 8; ++k) x[k] = (k < nc) ? x[k] + dpv : 0.f;
+            const bool ok = c0 + tr < pn;
+            emit8(x, rawc, ok ? vfac[p_lo + c0 + tr] : 0.f, ok, vdst + (size_t)c0 * D);
+            rawc = rawn;
           }
         }
         if (blk == 0) stamp();
@@ -692,7 +707,7 @@ int sparc_bwd3_launch(const void* v, const void* l, const uint8_t* mask, int B, 
   CUtensorMap tmV0, tmV1, tmL, tmG;
   int rc;
   if ((rc = make_tmap_bf16_3d(&tmV0, v, D, P, B, 64, L.NP)) != CFA_OK) return rc;
-  if ((rc = make_tmap_bf16_3d(&tmV1, v, D, P, B, 64, L.CR0)) != CFA_OK) return rc;
+  if ((rc = make_tmap_bf16_3d(&tmV1, v, D, P, B, 64, L.CR0)) != CFA_OK) return rc;     // P4 chunks: NT patch rows
   if ((rc = make_tmap_bf16_3d(&tmL, l, D, T, B, 64, L.NT)) != CFA_OK) return rc;
   if ((rc = make_tmap_bf16_3d(&tmG, g_split, D, T, 2 * (uint64_t)B, 64, L.NT)) != CFA_OK) return rc;
   Bwd3Params prm{prof, P, T, D, thr, scale, mask, row_inv_norm, row_inv_norm + (size_t)B * P, lse_row, lse_col, coef,

@@ -34,7 +34,7 @@ constexpr float kF3NormEps = 1e-12f, kF3MinMaxEps = 1e-8f, kF3ClampEps = 1e-8f;
 struct Fwd3Layout {
   int NP, NT, MB, KB0, NBLK, CR0, NCH, NS0, NS1;
   uint32_t v_bytes, l_bytes, slot0, slot1, plane;      // plane = one of hi / lo of an interleaved [NT/8][NP][8] operand
-  uint32_t off_th, off_sr, off_ring0, off_ring1, off_f, off_bar, total;
+  uint32_t off_th, off_sr, off_stage, off_ring0, off_ring1, off_f, off_bar, total;
 };
 
 __host__ __device__ inline Fwd3Layout fwd3_layout(int P, int T, int D) {
@@ -48,7 +48,12 @@ __host__ __device__ inline Fwd3Layout fwd3_layout(int P, int T, int D) {
   // the Theta^T region doubles as the P0 scratch: pooled-mean partials [4][D]
   const uint32_t scratch = 4u * D * 4;
   const uint32_t op = ((2 * L.plane > scratch ? 2 * L.plane : scratch) + 1023) & ~1023u;
-  L.off_th = 0; L.off_sr = op; L.off_ring1 = 2 * op;
+  // the S_raw^T region is reused once L' is done: E3 logits scratch [NT][NT + 1] fp32, then the per-warp transposition
+  // tiles of the G epilogue (2 planes x [8][32] bf16 per warp)
+  const uint32_t lb = ((uint32_t)L.NT * (L.NT + 1) * 4 + 1023) & ~1023u;
+  const uint32_t srb = lb + (uint32_t)kF3EpiWarps * 1024u;
+  const uint32_t op_sr = ((2 * L.plane > srb ? 2 * L.plane : srb) + 1023) & ~1023u;
+  L.off_th = 0; L.off_sr = op; L.off_stage = op + lb; L.off_ring1 = op + op_sr;
   const uint32_t nf = (uint32_t)L.NP + 9 * L.NT + 8 * 2 * L.NT + 8 * L.NT + 64;
   const uint32_t fixed = 4 * nf + 8 * 32 + 1024;
   const uint32_t budget = 227u * 1024u;
@@ -162,6 +167,12 @@ sparc_fwd3_kernel(const __grid_constant__ CUtensorMap tmV0, const __grid_constan
     msk[i] = (i < T && p.mask[(size_t)b * T + i]) ? 1.f : 0.f;
     imn[i] = 0x7fffffff;
   }
+  if (warp == 2) {                                     // number of valid tokens of this sample (losses.py:211)
+    float c = 0.f;
+    for (int t = lane; t < T; t += 32) c += p.mask[(size_t)b * T + t] ? 1.f : 0.f;
+    c = warp_sum(c);
+    if (lane == 0) red[63] = c;
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -210,9 +221,8 @@ sparc_fwd3_kernel(const __grid_constant__ CUtensorMap tmV0, const __grid_constan
     auto stamp = [&]() { if (pf) pf[pi++] = clock64(); };
     stamp();
     // ---- P0: S^T = v . l^T, Gram tiles of v (per M block) and l
-    for (int u = 0; u < KB0; ++u) {
-      const int s = u % NS0;
-      mbar_wait_sleep(full0 + s, (u / NS0) & 1);
+    for (int u = 0, s = 0, ph = 0; u < KB0; ++u) {
+      mbar_wait_sleep(full0 + s, ph);
       tc_fence_after();
       const uint32_t sv = smem_u32(ring0 + (size_t)s * slot0), sl = sv + v_bytes;
       const uint64_t dv0 = sw0 | (sv >> 4), dl0 = sw0 | (sl >> 4);
@@ -229,6 +239,7 @@ sparc_fwd3_kernel(const __grid_constant__ CUtensorMap tmV0, const __grid_constan
 #pragma unroll
       for (int k = 0; k < 4; ++k) umma_ss_w(leader, tmem + cGL, dl0 + 2 * k, dl0 + 2 * k, idesc_s, (u | k) != 0);
       umma_commit_w(leader, empty0 + s);
+      if (++s == NS0) { s = 0; ph ^= 1; }
     }
     umma_commit_w(leader, s_full);
     stamp();
@@ -246,7 +257,7 @@ sparc_fwd3_kernel(const __grid_constant__ CUtensorMap tmV0, const __grid_constan
 #pragma unroll
     for (int ks = 0; ks < (kNP ? kNP / 16 : 16); ++ks) if (ks < nksP) umma_ss_w(leader, tmem, m_srl + ks * 16, m_th + ks * 16, idesc_l1, true);
     umma_commit_w(leader, l_full);
-    int i1 = 0;
+    int s1 = 0, ph1 = 0;
     for (int blk = 0; blk < NBLK; ++blk) {
       const int buf = blk & 1;
       mbar_wait_sleep(g_free + buf, ((blk >> 1) & 1) ^ 1);
@@ -255,8 +266,8 @@ sparc_fwd3_kernel(const __grid_constant__ CUtensorMap tmV0, const __grid_constan
 #pragma unroll
       for (int ch = 0; ch < 2; ++ch) {
         if (ch < NCH) {
-          const int s = i1 % NS1;
-          mbar_wait_sleep(full1 + s, (i1 / NS1) & 1);
+          const int s = s1;
+          mbar_wait_sleep(full1 + s, ph1);
           tc_fence_after();
           const uint32_t sa = smem_u32(ring1 + (size_t)s * slot1);
           const uint64_t da = make_smem_desc(sa, slot1 / 2, 1024, kLayoutSw128);
@@ -265,7 +276,7 @@ sparc_fwd3_kernel(const __grid_constant__ CUtensorMap tmV0, const __grid_constan
 #pragma unroll
           for (int ks = 0; ks < 8; ++ks) if (ks < nk) umma_ss_w(leader, d, da + ks * 128, db + ks * 16, idesc_g, (ch | ks) != 0);
           umma_commit_w(leader, empty1 + s);
-          ++i1;
+          if (++s1 == NS1) { s1 = 0; ph1 ^= 1; }
         }
       }
       umma_commit_w(leader, g_full + buf);
@@ -288,9 +299,8 @@ sparc_fwd3_kernel(const __grid_constant__ CUtensorMap tmV0, const __grid_constan
     {
       const int c = ew & 7, hf = ew >> 3;
       float* poolp = reinterpret_cast<float*>(TH);      // [2 modalities][2 parities][D] (the Theta region is unused until E1)
-      for (int u = 0; u < KB0; ++u) {
-        const int s = u % NS0;
-        mbar_wait_sleep(full0 + s, (u / NS0) & 1);
+      for (int u = 0, s = 0, ph = 0; u < KB0; ++u) {
+        mbar_wait_sleep(full0 + s, ph);
         const uint8_t* st = ring0 + (size_t)s * slot0;
         float al[8], av[8];
 #pragma unroll
@@ -326,6 +336,7 @@ sparc_fwd3_kernel(const __grid_constant__ CUtensorMap tmV0, const __grid_constan
           const float sv = warp_colsum8(av, lane);
           if ((lane & 17) == 0) poolp[hf * D + u * 64 + 8 * c + (lane >> 1)] = sv;
         }
+        if (++s == NS0) { s = 0; ph ^= 1; }
       }
     }
     stamp();
@@ -364,9 +375,7 @@ sparc_fwd3_kernel(const __grid_constant__ CUtensorMap tmV0, const __grid_constan
       }
     }
     {
-      float cnt = 0.f;
-      for (int t = 0; t < T; ++t) cnt += msk[t];
-      const float inv_cnt = 1.f / fmaxf(cnt, kF3ClampEps), invPm = 1.f / (float)P;
+      const float inv_cnt = 1.f / fmaxf(red[63], kF3ClampEps), invPm = 1.f / (float)P;
       const float* poolp = reinterpret_cast<const float*>(TH);
       f3_epi_bar();                                       // pooled partials, ivn, 1/||l|| complete
       for (int i = tid; i < D; i += 512) {
@@ -474,46 +483,66 @@ sparc_fwd3_kernel(const __grid_constant__ CUtensorMap tmV0, const __grid_constan
     // ---- P1 epilogue: G'^T block [128 d][hi-part NT | lo-part NT] -> G = (hi + lo) / sigma_t: ||G_t||^2, bf16 hi | lo planes
     const int gw_ = NT / 4, g_lo = grp * gw_;           // NT / 4 is a multiple of 4
     const int dl = 32 * q + lane;                        // feature column inside the block
-    float gn2[20];
+    float gn2[24];
 #pragma unroll
-    for (int k = 0; k < 20; ++k) gn2[k] = 0.f;
+    for (int k = 0; k < 24; ++k) gn2[k] = 0.f;
     {
       const size_t pstride = (size_t)T * D;
-      bf16* gh0 = p.g_split + ((size_t)b * 2) * pstride + (size_t)g_lo * D + dl;
       const int kpool = pool_tc ? T - g_lo : -1;        // local index of the spare column in this group (if any)
+      // global stores are transposed through a per-warp tile [8 tokens][32 d] per plane (bf16, 64-byte rows): lane -> (row
+      // lane / 4, 16-byte chunk lane % 4), one STG moves 8 rows x 64 contiguous bytes (2-byte stores are LSU-rate bound)
+      uint8_t* sth = base + L.off_stage + ew * 1024;      // behind the E3 logits scratch; the S_raw^T region is free (L' done)
+      uint8_t* stl = sth + 512;
+      const int tr = lane >> 2, tc16 = (lane & 3) * 16;
+      bf16* gq0 = p.g_split + ((size_t)b * 2) * pstride + (size_t)(g_lo + tr) * D + 32 * q + (lane & 3) * 8;
       for (int blk = 0; blk < NBLK; ++blk) {
         const int buf = blk & 1;
         mbar_wait_sleep(g_full + buf, (blk >> 1) & 1);
         tc_fence_after();
-        bf16* gh = gh0 + blk * 128;
-        bf16* gl = gh + pstride;
+        bf16* gq = gq0 + blk * 128;
         const uint32_t tg = tq + cG + buf * NT2 + g_lo;
 #pragma unroll
-        for (int c = 0; c < 20; c += 4) {                  // 4 columns at a time: hi-part and lo-part of the same tokens
+        for (int c = 0; c < 24; c += 8) {                  // 8 columns at a time: hi-part and lo-part of the same tokens
           if (c < gw_) {
-            float xh[4], xl[4];
-            tmem_ld4(tg + c, xh);
-            tmem_ld4(tg + NT + c, xl);
-            const float4 is4 = *reinterpret_cast<const float4*>(isg + g_lo + c);
+            float xh[8], xl[8];
+            if (pf && blk == 1 && c == 0) pf[12] = clock64();
+            if (c + 8 <= gw_) { tmem_ld8(tg + c, xh); tmem_ld8(tg + NT + c, xl); }
+            else { tmem_ld4(tg + c, xh); tmem_ld4(tg + NT + c, xl); }
+            const float4 is0 = *reinterpret_cast<const float4*>(isg + g_lo + c);
+            const float4 is1 = (c + 8 <= gw_) ? *reinterpret_cast<const float4*>(isg + g_lo + c + 4) : make_float4(0.f, 0.f, 0.f, 0.f);
             tmem_ld_wait();
-            if (c + 4 >= gw_) {                            // last chunk: the accumulator is in registers
+            if (pf && blk == 1 && c == 0) pf[13] = clock64();
+            if (c + 8 >= gw_) {                            // last chunk: the accumulator is in registers
               tc_fence_before();
               __syncwarp();
               if (lane == 0) mbar_arrive(g_free + buf);
             }
-            const float isv[4] = {is4.x, is4.y, is4.z, is4.w};
+            const float isv[8] = {is0.x, is0.y, is0.z, is0.w, is1.x, is1.y, is1.z, is1.w};
+            const int nc = (c + 8 <= gw_) ? 8 : 4;
+            if (c <= kpool && kpool < c + nc) {            // warp-uniform: this chunk holds the spare column
+              float pv = 0.f;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const float raw = xh[k] + xl[k];
-              if (c + k == kpool) p.pooled_v[(size_t)b * D + blk * 128 + dl] = raw;
-              const float g = raw * isv[k];
-              gn2[c + k] = fmaf(g, g, gn2[c + k]);
-              if (g_lo + c + k < T) {
-                const bf16 h = __float2bfloat16_rn(g);
-                gh[(size_t)(c + k) * D] = h;
-                gl[(size_t)(c + k) * D] = __float2bfloat16_rn(g - __bfloat162float(h));
-              }
+              for (int k = 0; k < 8; ++k) pv = (k == kpool - c) ? xh[k] + xl[k] : pv;
+              p.pooled_v[(size_t)b * D + blk * 128 + dl] = pv;
             }
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              const float g = (k < nc) ? (xh[k] + xl[k]) * isv[k] : 0.f;
+              gn2[c + k] = fmaf(g, g, gn2[c + k]);
+              const bf16 h = __float2bfloat16_rn(g);
+              reinterpret_cast<bf16*>(sth)[k * 32 + lane] = h;
+              reinterpret_cast<bf16*>(stl)[k * 32 + lane] = __float2bfloat16_rn(g - __bfloat162float(h));
+            }
+            __syncwarp();
+            if (pf && blk == 1 && c == 0) pf[14] = clock64();
+            const uint4 vh = *reinterpret_cast<const uint4*>(sth + tr * 64 + tc16);
+            const uint4 vl = *reinterpret_cast<const uint4*>(stl + tr * 64 + tc16);
+            __syncwarp();
+            if (tr < nc && g_lo + c + tr < T) {
+              *reinterpret_cast<uint4*>(gq + (size_t)c * D) = vh;
+              *reinterpret_cast<uint4*>(gq + (size_t)c * D + pstride) = vl;
+            }
+            if (pf && blk == 1 && c == 0) pf[15] = clock64();
           }
         }
         if (blk == 0) stamp();
@@ -589,7 +618,7 @@ sparc_fwd3_kernel(const __grid_constant__ CUtensorMap tmV0, const __grid_constan
           m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
         }
         float s = 0.f;
-        for (int j = s_lo; j < s_hi; ++j) { const float y = src[j * st_c]; s += (y == -CUDART_INF_F) ? 0.f : __expf(y - m); }
+        for (int j = s_lo; j < s_hi; ++j) s += __expf(src[j * st_c] - m);          // exp(-inf - m) = 0: masked entries drop out
         s += __shfl_xor_sync(0xffffffffu, s, 1);
         s += __shfl_xor_sync(0xffffffffu, s, 2);
         const float lse = valid ? m + logf(s) : 0.f;

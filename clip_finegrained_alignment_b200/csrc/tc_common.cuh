@@ -42,17 +42,21 @@ __device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parit
       : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity), "r"(ns) : "memory");
   return ok != 0;
 }
-// Bounded wait for the third-generation kernels: long hardware sleeps, clock check only once per wake-up
+// Bounded wait for the third-generation kernels: the probe suspends the thread in hardware; the loop around it is three
+// instructions (a spinning warp takes issue slots from the warps that do the work); the clock is read every 256 wake-ups
 __device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
-  while (!mbar_try_wait_hint(bar, parity, 20000u)) {
-    if (clock64() - t0 > 4000000000LL) {
+  uint32_t n = 0;
+  long long t0 = 0;
+  while (!mbar_try_wait_hint(bar, parity, 100000u)) {
+    if ((++n & 255u) == 0u) { if (t0 == 0) t0 = clock64(); }
+    if ((n & 255u) == 0u && clock64() - t0 > 4000000000LL) {
       printf("cfa: mbarrier timeout block %d thread %d bar %u parity %u\n", blockIdx.x, threadIdx.x, smem_u32(bar), parity);
       __trap();
     }
   }
 }
+
 // Bounded wait: a protocol bug traps after ~2 s instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
