@@ -32,6 +32,11 @@ P, T, D = 196, 77, 512
 L2_BYTES = 126 * 2 ** 20
 METRIC = "sparc_infonce_fwd_bwd_pairs_per_s"
 UNIT = "pairs/s"
+# DRAM traffic of the dominant kernel per launch at config 2 (one `ncu --set full` capture, summary under profiles/)
+TRAFFIC_BWD = 183.6e6
+TRAFFIC_SRC = ("profiles/r1i_ncu_full_summary.csv (sparc_bwd2_kernel): dram read 140.1 MB + write 43.5 MB per launch; to be "
+               "replaced by the third-generation capture")
+SHARE_SRC = "profiles/r1i_launches.csv"
 
 
 def peaks():
@@ -226,29 +231,28 @@ def bench_adamspd(dev, steps, warmup, pk):
 
 
 # --------------------------------------------------------------------------------------------
+def _reference_modules():
+    """The UNMODIFIED reference modules: oracle/_ref (made by oracle/make_ref.py, travels to the GPU box), refreshed from
+    /root/reference when that is mounted (build container)."""
+    from oracle import make_ref
+    make_ref.make_ref(verbose=False)
+    return make_ref.import_ref()
+
+
 def make_cpu_runner(B):
-    """The reference's CPU implementation of the path on a bounded sample: B pairs of the workload's shapes,
-    fp32, all host threads.  Uses the unmodified reference when /root/reference is mounted (build container),
-    else the oracle port (GPU box)."""
+    """The reference's CPU implementation of the path on a bounded sample: B pairs of the workload's shapes, fp32, all
+    host threads, forward + autograd backward of the unmodified reference SPARCLoss (oracle/_ref); the oracle port only
+    if oracle/_ref is absent."""
     torch.set_num_threads(os.cpu_count() or 1)
     g = torch.Generator().manual_seed(42)
     v = torch.randn(B, P, D, generator=g)
     l = torch.randn(B, T, D, generator=g)
     m = torch.ones(B, T, dtype=torch.bool)
     thr = 1.0 / P
-    ref_dir = "/root/reference/finetune"
-    kind = "port"
-    if os.path.isdir(ref_dir):
-        sys.path.insert(0, ref_dir)
-        try:
-            import losses as ref_losses
-            kind = "reference"
-        except Exception:
-            kind = "port"
-        finally:
-            sys.path.pop(0)
+    mods = _reference_modules()
+    kind = "reference" if mods is not None else "port"
     if kind == "reference":
-        mod = ref_losses.SPARCLoss(cfg(thr))
+        mod = mods[0].SPARCLoss(cfg(thr))
 
         def run():
             vv = v.clone().requires_grad_(True)
@@ -260,9 +264,44 @@ def make_cpu_runner(B):
         def run():
             with torch.no_grad():
                 lo.sparc_backward(lo.sparc_forward(v, l, m, thr, 1.0, 1.0, 1.0))
-    what = "unmodified reference losses.py (autograd)" if kind == "reference" else "oracle/losses_oracle.py port"
+    what = "unmodified reference losses.py (autograd fwd + bwd)" if kind == "reference" else "oracle/losses_oracle.py port"
     sample = f"{B} pairs per step of the same shapes (P={P}, T={T}, D={D}), fp32, {what}"
     return run, kind, torch.get_num_threads(), sample
+
+
+def gpu_eager(dev, B, steps=10):
+    """Comparator named by BASELINE.md §4: the unmodified reference SPARCLoss in PyTorch eager mode ON THE B200 (bf16
+    autocast as CUDA autocast would run it), fwd + autograd bwd at the bench batch."""
+    mods = _reference_modules()
+    if mods is None:
+        return {"unavailable": "oracle/_ref not made"}
+    try:
+        crit = mods[0].SPARCLoss(cfg(1.0 / P)).to(dev)
+        g = torch.Generator(device=dev).manual_seed(1)
+        v = torch.randn(B, P, D, device=dev, generator=g).requires_grad_(True)
+        l = torch.randn(B, T, D, device=dev, generator=g).requires_grad_(True)
+        m = torch.ones(B, T, dtype=torch.bool, device=dev)
+
+        def run():
+            v.grad = None; l.grad = None
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                out = crit(v, l, m)
+            out["total_loss"].backward()
+
+        for _ in range(3):
+            run()
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            run()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        ms = e0.elapsed_time(e1) / steps
+        return {"value": round(B / (ms * 1e-3), 1), "unit": UNIT, "ms_per_step": round(ms, 4), "batch": B,
+                "what": "unmodified reference SPARCLoss (oracle/_ref), torch eager + autocast(bf16) on the same B200, fp32 leaves"}
+    except Exception as e:
+        return {"error": repr(e)[:200]}
 
 
 def cpu_baseline(B=32, budget_s=12.0):
@@ -308,7 +347,8 @@ def main():
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch", type=int, default=256, help="pairs per GPU (BASELINE config 2: 256)")
+    ap.add_argument("--batch", type=int, default=0,
+                    help="pairs per GPU; default: BASELINE config 2 (256) on one GPU, config 3 (1024 / GPU) with --gpus > 1")
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "f32", "f16"])
     ap.add_argument("--patches", type=int, default=196, help="vision tokens P (BASELINE config 4: 576)")
     ap.add_argument("--dim", type=int, default=512, help="projection dim D (BASELINE config 4: 768)")
@@ -335,73 +375,90 @@ def main():
     torch.cuda.set_device(dev)
     if world > 1:
         # stdout carries ONE JSON line: NCCL's debug output (its version banner is printed at every level) goes to stderr
-        os.environ["NCCL_DEBUG"] = os.environ.get("CFA_NCCL_DEBUG", "WARN")
+        os.environ.setdefault("NCCL_DEBUG", os.environ.get("CFA_NCCL_DEBUG", "WARN"))
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     from clip_finegrained_alignment_b200 import SPARCLoss, _lib
     pk = peaks()
     dt = {"bf16": torch.bfloat16, "f32": torch.float32, "f16": torch.float16}[args.dtype]
-    B = args.batch
+    B = args.batch if args.batch > 0 else (256 if world == 1 else 1024)
     Bg = B * world
     torch.manual_seed(42 + rank)
-    in_bytes = B * (P + T) * D * torch.empty(0, dtype=dt).element_size()
-    nbuf = max(2, -(-2 * L2_BYTES // in_bytes))            # rotate input sets: working set > 2 x L2
-    vs = [torch.randn(B, P, D, device=dev).to(dt).requires_grad_(True) for _ in range(nbuf)]
-    ls = [torch.randn(B, T, D, device=dev).to(dt).requires_grad_(True) for _ in range(nbuf)]
-    mask = torch.ones(B, T, dtype=torch.bool, device=dev)
-    crit = SPARCLoss(cfg(1.0 / P), gather=(True if args.collective == "peer" else "nccl") if world > 1 else False,
-                     cast_to_bf16=args.cast_to_bf16)
-
-    def step(i):
-        v, l = vs[i % nbuf], ls[i % nbuf]
-        v.grad = None; l.grad = None
-        out = crit(v, l, mask)
-        out["total_loss"].backward()
-        return out["total_loss"]
+    mask_all = {}
 
     def sync_all():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    # initialisation, not warm-up: the first calls load the kernels (CUDA loads modules lazily, with a context
-    # synchronisation each), size the allocator's pools and, with N > 1, create and map the peer exchange blocks
-    init_steps = 10 if world > 1 else 2
-    for i in range(init_steps):
-        step(i)
-    sync_all()
-    for i in range(args.warmup):
-        step(i)
-    sync_all()
+    def timed_run(B, steps, warmup, with_stage_events=True):
+        """W untimed + K timed steps of SPARCLoss fwd + bwd at B pairs per GPU, inputs resident in HBM and rotated over
+        enough sets to exceed 2 x L2; returns device-timed ms (max over ranks) and per-ABI-call device times."""
+        in_bytes = B * (P + T) * D * torch.empty(0, dtype=dt).element_size()
+        nbuf = max(2, -(-2 * L2_BYTES // in_bytes))            # rotate input sets: working set > 2 x L2
+        vs = [torch.randn(B, P, D, device=dev).to(dt).requires_grad_(True) for _ in range(nbuf)]
+        ls = [torch.randn(B, T, D, device=dev).to(dt).requires_grad_(True) for _ in range(nbuf)]
+        mask = torch.ones(B, T, dtype=torch.bool, device=dev)
+        mask_all[B] = mask
+        crit = SPARCLoss(cfg(1.0 / P), gather=(True if args.collective == "peer" else "nccl") if world > 1 else False,
+                         cast_to_bf16=args.cast_to_bf16)
+
+        def step(i):
+            v, l = vs[i % nbuf], ls[i % nbuf]
+            v.grad = None; l.grad = None
+            out = crit(v, l, mask)
+            out["total_loss"].backward()
+            return out["total_loss"]
+
+        # initialisation, not warm-up: the first calls load the kernels (CUDA loads modules lazily, with a context
+        # synchronisation each), size the allocator's pools and, with N > 1, create and map the peer exchange blocks
+        init_steps = 10 if world > 1 else 2
+        for i in range(init_steps):
+            step(i)
+        sync_all()
+        for i in range(warmup):
+            step(i)
+        sync_all()
+        l0 = _lib.launch_count
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t_host = time.perf_counter()
+        e0.record()
+        for i in range(steps):
+            step(warmup + i)
+        e1.record()
+        host_issue_ms = (time.perf_counter() - t_host) * 1e3 / steps      # CPU time to ISSUE one step (no sync inside)
+        sync_all()
+        launches = _lib.launch_count - l0
+        ms_total = e0.elapsed_time(e1)
+        kev = {}
+        if with_stage_events:
+            # per-ABI-call device times: a separate short pass with CUDA events around every call (kept out of the timed
+            # region: the extra event records cost host time)
+            _lib.kernel_events = {name: [] for name in _lib.LAUNCHES if name != "cfa_adamspd_step"}
+            crit_stages = SPARCLoss(cfg(1.0 / P), gather=world > 1, fused_calls=False, cast_to_bf16=args.cast_to_bf16)      # same kernels, one call per stage
+            for i in range(min(10, steps)):
+                v, l = vs[i % nbuf], ls[i % nbuf]
+                v.grad = None; l.grad = None
+                crit_stages(v, l, mask)["total_loss"].backward()
+            sync_all()
+            kev = _lib.kernel_events
+            _lib.kernel_events = None
+        t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+        res = dict(B=B, ms_step=ms_total / steps, value=B * world * steps / (ms_total * 1e-3), launches=launches,
+                   host_issue_ms=host_issue_ms, kev=kev, nbuf=nbuf, in_bytes=in_bytes, init_steps=init_steps, crit=crit)
+        del vs, ls
+        return res
+
     sampler = ClockSampler(local_rank) if rank == 0 else None
-    l0 = _lib.launch_count
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t_host = time.perf_counter()
-    e0.record()
-    for i in range(args.steps):
-        step(args.warmup + i)
-    e1.record()
-    host_issue_ms = (time.perf_counter() - t_host) * 1e3 / args.steps      # CPU time to ISSUE one step (no sync inside)
-    sync_all()
-    launches = _lib.launch_count - l0
-    ms_total = e0.elapsed_time(e1)
-    # per-ABI-call device times: a separate short pass with CUDA events around every call (kept out of the timed region:
-    # the extra event records cost host time)
-    _lib.kernel_events = {name: [] for name in _lib.LAUNCHES if name != "cfa_adamspd_step"}
-    crit_stages = SPARCLoss(cfg(1.0 / P), gather=world > 1, fused_calls=False, cast_to_bf16=args.cast_to_bf16)      # same kernels, one call per stage
-    for i in range(min(10, args.steps)):
-        v, l = vs[i % nbuf], ls[i % nbuf]
-        v.grad = None; l.grad = None
-        crit_stages(v, l, mask)["total_loss"].backward()
-    sync_all()
-    kev = _lib.kernel_events
-    _lib.kernel_events = None
-    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total = float(t.item())
-    ms_step = ms_total / args.steps
-    value = Bg * args.steps / (ms_total * 1e-3)
+    main_run = timed_run(B, args.steps, args.warmup)
+    crit = main_run["crit"]
+    mask = mask_all[B]
+    kev, launches, host_issue_ms = main_run["kev"], main_run["launches"], main_run["host_issue_ms"]
+    nbuf, in_bytes, init_steps = main_run["nbuf"], main_run["in_bytes"], main_run["init_steps"]
+    ms_step, value = main_run["ms_step"], main_run["value"]
     bwd_ms = statistics.mean(a.elapsed_time(b) for a, b in kev["cfa_sparc_bwd"])
     fwd_ms = statistics.mean(a.elapsed_time(b) for a, b in kev["cfa_sparc_fwd"])
 
@@ -445,6 +502,7 @@ def main():
     e2e_run(3)
     sync_all()
     e2e_steps = max(5, min(args.steps, 20))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     lh = e2e_run(e2e_steps)
     e1.record()
@@ -456,6 +514,17 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_val = Bg * e2e_steps / (float(t.item()) * 1e-3)
     clocks = sampler.stop() if sampler else None
+    del bufs
+    # N = 1 only: the same step at BASELINE config 3's per-GPU batch (B = 1024), so that the multi-GPU lines (which run
+    # config 3, B = 1024 / GPU) have their own single-GPU reference in this line
+    config3_n1 = None
+    if world == 1 and args.batch == 0 and (P, D) == (196, 512):
+        torch.cuda.empty_cache()
+        r3 = timed_run(1024, max(5, args.steps // 3), 3, with_stage_events=False)
+        config3_n1 = {"value": round(r3["value"], 1), "unit": UNIT, "ms_per_step": round(r3["ms_step"], 4), "batch_per_gpu": 1024,
+                      "algorithmic_tflops": round(r3["value"] * flops_per_pair(1024) / 1e12, 2),
+                      "note": "weak-scaling reference for the --gpus > 1 lines (BASELINE config 3 runs B = 1024 per GPU)"}
+        del r3
 
     if rank != 0:
         if world > 1:
@@ -484,12 +553,8 @@ def main():
                    "kernel_ms": {k: round(statistics.mean(a.elapsed_time(b) for a, b in ev), 4) for k, ev in kev.items() if ev}},
         "roofline": {"bound": "tensor", "kernel": "cfa_sparc_bwd", "achieved": round(ach, 2), "peak": pk["tf_sus"],
                      "unit": "TFLOP/s", "frac": round(ach / pk["tf_sus"], 5),
-                     "traffic": 183.6e6 if (B == 256 and args.dtype == "bf16") else None,
-                     "traffic_source": "profiles/r1i_ncu_full_summary.csv (sparc_bwd2_kernel): dram read 140.1 MB + write 43.5 MB "
-                                       "per launch; algorithmic 206 MB = v,l 71.6 + saved G hi|lo 40.4 + Q 16.4 + T x T logits 6.1 "
-                                       "read, dv,dl 71.6 written (part of dv/dl is still in L2 at kernel end; the second read "
-                                       "of v,l hits L2)",
-                     "share_of_device_time": "profiles/r1i_launches.csv: sparc_bwd2 46.9 %, sparc_fwd2 31.1 %, global InfoNCE 22.0 %",
+                     "traffic": TRAFFIC_BWD if (B == 256 and args.dtype == "bf16" and (P, D) == (196, 512)) else None,
+                     "traffic_source": TRAFFIC_SRC, "share_of_device_time": SHARE_SRC,
                      "peak_source": pk["src"] + ", sustained bf16 GEMM", "algorithmic_flops_per_launch": bwd_flops},
         "e2e": {"value": round(e2e_val, 1), "unit": UNIT,
                 "h2d_bytes_per_step": int(hv.numel() * hv.element_size() + hl.numel() * hl.element_size() + hm.numel()),
@@ -497,8 +562,12 @@ def main():
                 "note": "pinned host buffers; H2D of step i+1 overlaps compute of step i (copy stream); PCIe-bound"},
         "gpu_launches": launches, "host_issue_ms_per_step": round(host_issue_ms, 4), "clocks": clocks,
     }
-    del vs, ls
+    if config3_n1 is not None:
+        line["config3_n1"] = config3_n1
     torch.cuda.empty_cache()
+    if world == 1 and not args.no_cpu_baseline:
+        line["gpu_eager"] = gpu_eager(dev, B)
+        torch.cuda.empty_cache()
     if not args.no_adamspd:
         line["adamspd"] = bench_adamspd(dev, max(3, min(args.steps, 10)), 3, pk)
     if world == 1 and not args.no_cpu_baseline:

@@ -59,11 +59,14 @@ SIGNATURES = {
     "cfa_peer_close": (C.c_int, [_vp]),
     "cfa_peer_free": (C.c_int, [_vp]),
     "cfa_peer_sync": (C.c_int, [_vp, _i, _i, C.c_uint32, _vp, _sz, _sz, _sz, _i, _vp, _vp]),
+    "cfa_peer_status": (C.c_int, [_vp, _vp, _vp]),
     "cfa_sparc_loss_gathered_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i, _i]),
     "cfa_sparc_loss_gathered_fwd": (C.c_int, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _f, _f, _f, _vp, _sz, _i, _i, _i, _vp,
                                               C.c_uint32, _vp]),
     "cfa_sparc_loss_gathered_bwd": (C.c_int, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _f, _f, _f, _vp, _sz, _vp, _vp, _vp, _vp,
                                               _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
+    "cfa_sparc_loss_gathered_bwd_ex": (C.c_int, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _f, _f, _f, _vp, _sz, _vp, _vp, _vp, _vp,
+                                                 _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _f, _vp]),
     "cfa_count_contrastive_fwd": (C.c_int, [_vp, _vp, _vp, _i, _i, _i, _i, _f, _i, _vp, _vp, _vp]),
     "cfa_count_contrastive_bwd": (C.c_int, [_vp, _vp, _vp, _i, _i, _i, _i, _f, _i, _vp, _vp, _vp, _vp, _vp]),
     "cfa_logits_ce_fwd": (C.c_int, [_vp, _vp, _i, _i, _vp, _vp, _vp, _vp]),
@@ -98,7 +101,7 @@ LAUNCHES = {"cfa_adamspd_step": 2, "cfa_adamspd_step_amp": 4, "cfa_global_infonc
             "cfa_masked_pairwise_fwd": 2, "cfa_masked_pairwise_bwd": 1,
             "cfa_sparc_loss_fwd": 2, "cfa_sparc_loss_bwd": 4,
             "cfa_count_contrastive_fwd": 2, "cfa_count_contrastive_bwd": 1, "cfa_logits_ce_fwd": 2, "cfa_logits_ce_bwd": 1,
-            "cfa_sparc_loss_gathered_fwd": 8, "cfa_sparc_loss_gathered_bwd": 4, "cfa_peer_sync": 1,
+            "cfa_sparc_loss_gathered_fwd": 8, "cfa_sparc_loss_gathered_bwd": 4, "cfa_sparc_loss_gathered_bwd_ex": 4, "cfa_peer_sync": 1,
             "cfa_global_infonce_gathered_fwd": 7, "cfa_global_infonce_gathered_bwd": 2,
             "cfa_tc_selftest": 1, "cfa_tc_selftest_timed": 1}
 launch_count = 0

@@ -546,12 +546,14 @@ __global__ void sparc_coef_kernel(const float* grad7, float gw, float lw, int gl
 struct Grad7Ptrs { const float* g[7]; };
 
 // same as sparc_coef_kernel, the 7 upstream gradients arriving as separate 0-dim tensors (NULL = not used)
-__global__ void sparc_coef_ptrs_kernel(Grad7Ptrs gp, float gw, float lw, int global_batch, const float* out8, float* coef8) {
+__global__ void sparc_coef_ptrs_kernel(Grad7Ptrs gp, float gw, float lw, int global_batch, const float* out8, float* coef8,
+                                       float gscale) {
   float u[7];
   for (int k = 0; k < 7; ++k) u[k] = gp.g[k] ? *gp.g[k] : 0.f;
   const float gl = 0.5f * (u[0] + gw * u[2]);
   const float lo = 0.5f * (u[1] + lw * u[2]);
-  const float cvl = (u[3] + gl) / (float)global_batch, clv = (u[4] + gl) / (float)global_batch;
+  // gscale: world size when the caller's gradients are averaged over ranks afterwards (DDP), see cfa_sparc_loss_gathered_bwd_ex
+  const float cvl = gscale * (u[3] + gl) / (float)global_batch, clv = gscale * (u[4] + gl) / (float)global_batch;
   coef8[0] = cvl; coef8[1] = clv;
   coef8[2] = (u[5] + lo) / out8[7];
   coef8[3] = (u[6] + lo) / out8[7];
@@ -567,9 +569,18 @@ extern "C" int cfa_sparc_coef_ptrs(const float* g_global, const float* g_local, 
                                    int global_batch, const float* out8, float* coef8, void* stream) {
   if (!out8 || !coef8 || global_batch <= 0) return CFA_ERR_BAD_ARG;
   Grad7Ptrs gp{{g_global, g_local, g_total, g_vl, g_lv, g_vl_local, g_lv_local}};
-  sparc_coef_ptrs_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(gp, gw, lw, global_batch, out8, coef8);
+  sparc_coef_ptrs_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(gp, gw, lw, global_batch, out8, coef8, 1.f);
   return launch_status();
 }
+
+namespace cfa {
+int sparc_coef_ptrs_scaled(const float* const g[7], float gw, float lw, int global_batch, const float* out8, float* coef8,
+                           float gscale, cudaStream_t st) {
+  Grad7Ptrs gp{{g[0], g[1], g[2], g[3], g[4], g[5], g[6]}};
+  sparc_coef_ptrs_kernel<<<1, 1, 0, st>>>(gp, gw, lw, global_batch, out8, coef8, gscale);
+  return launch_status();
+}
+}  // namespace cfa
 
 // bytes of global scratch the CUDA-core path needs for this shape (0 when the T x P tiles fit in shared memory)
 extern "C" size_t cfa_sparc_scratch_bytes(int B, int P, int T, int backward) {

@@ -6,18 +6,31 @@
 // HBM directly).
 //
 // Exchange block (4-byte words):   [0,16)  flag[r] = last epoch rank r signalled to this rank (monotonic)
-//                                  [32]    ticket of the multi-block sync kernel      [33] sticky time-out status
+//                                  [32]    ticket of the multi-block sync kernel      [33] number of timed-out barriers
 //                                  [64..)  slot 0 | slot 1, slot = pooled [2][B][D] fp32 | pack [2B+2] fp32
 // Two barriers per step (epoch 2*step+1 after the pooled rows are published, 2*step+2 after the packs are) order every
 // re-use of a slot after its last remote reader; the slot alternates with the step parity on top of that.
 #include "common.cuh"
 #include <cstring>
+#include <cstdlib>
 
 namespace cfa {
 
 constexpr size_t kPeerHeaderWords = 64;
 constexpr int kPeerTicketWord = 32, kPeerStatusWord = 33;
-constexpr unsigned long long kPeerTimeoutNs = 20ull * 1000 * 1000 * 1000;      // a rank that never arrives: poison, do not hang
+// A rank that never arrives: poison THIS step's losses (NaN) and count the event instead of hanging.  The wait is as long
+// as a collective's watchdog (default 600 s, CFA_PEER_TIMEOUT_MS overrides): a rank-0-only checkpoint or evaluation, or a
+// data-loader stall, must not look like a lost rank.  The status word is a COUNTER the host polls (cfa_peer_status /
+// PeerExchange.check()): it is not sticky, a later step whose barrier completes is computed normally.
+static unsigned long long peer_timeout_ns() {
+  static unsigned long long ns = 0;
+  if (ns == 0) {
+    const char* e = getenv("CFA_PEER_TIMEOUT_MS");
+    const double ms = e ? atof(e) : 600000.0;
+    ns = (unsigned long long)((ms > 1.0 ? ms : 1.0) * 1e6);
+  }
+  return ns;
+}
 
 static inline size_t up32w(size_t n) { return (n + 31) & ~(size_t)31; }
 size_t peer_slot_words(int B, int D) { return up32w((size_t)2 * B * D) + up32w((size_t)2 * B + 2); }
@@ -51,7 +64,8 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
 __global__ void __launch_bounds__(1024)
 peer_sync_kernel(const PeerBlocks blocks, int world, int rank, unsigned epoch, const float* __restrict__ push_src,
                  size_t push_off, size_t push_n, size_t pull_off, int pull_n, float* __restrict__ pull_dst,
-                 float* __restrict__ tail2_sums /* optional [2]: sums over the ranks of the last two pulled words */) {
+                 float* __restrict__ tail2_sums /* optional [2]: sums over the ranks of the last two pulled words */,
+                 unsigned long long timeout_ns) {
   float* own = blocks.base[rank];
   {
     float* dst = own + push_off;
@@ -82,13 +96,13 @@ peer_sync_kernel(const PeerBlocks blocks, int world, int rank, unsigned epoch, c
     st_release_sys(reinterpret_cast<unsigned*>(blocks.base[r]) + rank, epoch);   // "rank has published epoch", in r's block
     const unsigned long long t0 = globaltimer_ns();
     while ((int)(ld_acquire_sys(own_u + r) - epoch) < 0) {
-      if (globaltimer_ns() - t0 > kPeerTimeoutNs) { s_timeout = 1; break; }
+      if (globaltimer_ns() - t0 > timeout_ns) { s_timeout = 1; break; }
       __nanosleep(64);
     }
   }
   __syncthreads();
-  if (threadIdx.x == 0 && s_timeout) own_u[kPeerStatusWord] = 1;
-  const bool bad = s_timeout || own_u[kPeerStatusWord] != 0;
+  if (threadIdx.x == 0 && s_timeout) own_u[kPeerStatusWord] += 1;         // counter read by the host (cfa_peer_status)
+  const bool bad = s_timeout != 0;
   for (int r = 0; r < world; ++r)
     for (int i = threadIdx.x; i < pull_n; i += blockDim.x) {
       const float x = ld_relaxed_sys(blocks.base[r] + pull_off + i);
@@ -114,7 +128,8 @@ int peer_sync(void* const* h_blocks, int world, int rank, uint32_t epoch, const 
   int nblk = (int)((push_n / 4 + 1023) / 1024);
   if (nblk < 1) nblk = 1;
   if (nblk > 64) nblk = 64;
-  peer_sync_kernel<<<nblk, 1024, 0, st>>>(pb, world, rank, epoch, push_src, push_off, push_n, pull_off, pull_n, pull_dst, tail2_sums);
+  peer_sync_kernel<<<nblk, 1024, 0, st>>>(pb, world, rank, epoch, push_src, push_off, push_n, pull_off, pull_n, pull_dst, tail2_sums,
+                                          peer_timeout_ns());
   return launch_status();
 }
 
@@ -158,6 +173,14 @@ extern "C" int cfa_peer_close(void* dev_ptr) {
 extern "C" int cfa_peer_free(void* dev_ptr) {
   if (!dev_ptr) return CFA_OK;
   CFA_CUDA_TRY(cudaFree(dev_ptr));
+  return CFA_OK;
+}
+
+// number of barriers of this rank that timed out so far: asynchronous copy of the status word into (pinned) host memory
+extern "C" int cfa_peer_status(const void* own_block, unsigned int* h_count, void* stream) {
+  if (!own_block || !h_count) return CFA_ERR_BAD_ARG;
+  CFA_CUDA_TRY(cudaMemcpyAsync(h_count, (const unsigned*)own_block + kPeerStatusWord, sizeof(unsigned), cudaMemcpyDeviceToHost,
+                               (cudaStream_t)stream));
   return CFA_OK;
 }
 

@@ -141,16 +141,17 @@ extern "C" int cfa_sparc_loss_gathered_fwd(const void* v, const void* l, const u
   if (workspace_bytes < w.total * sizeof(float)) return CFA_ERR_WORKSPACE;
   float* f = (float*)workspace;
   cudaStream_t st = (cudaStream_t)stream;
+  // From here on BOTH barriers of the step are issued whatever happens locally: a rank that returned early would leave its
+  // peers waiting in theirs until the time-out.  The first local error is reported after the second barrier.
   int rc = cfa_sparc_fwd(v, l, mask, B, P, T, D, dtype, thr, scale, f + w.rin, f + w.pooled, f + w.pooled + (size_t)B * D,
                          f + w.lse_row, f + w.lse_col, f + w.part, f + w.tt, f + w.gin, w.saved ? (void*)(f + w.gsplit) : nullptr,
                          w.saved ? f + w.qsave : nullptr, w.scratch_bytes ? (void*)(f + w.scratch) : nullptr, w.scratch_bytes,
                          path, stream);
-  if (rc != CFA_OK) return rc;
   const size_t slot = kPeerHeaderWords + (size_t)(step & 1) * peer_slot_words(B, D);
   const size_t pack_off = slot + up32((size_t)2 * B * D);
   // exchange 1: my pooled [2][B][D] rows become readable by every peer
-  rc = peer_sync(h_peer_blocks, world, rank, 2 * step + 1, f + w.pooled, slot, (size_t)2 * B * D, 0, 0, nullptr, st);
-  if (rc != CFA_OK) return rc;
+  const int rc1 = peer_sync(h_peer_blocks, world, rank, 2 * step + 1, f + w.pooled, slot, (size_t)2 * B * D, 0, 0, nullptr, st);
+  if (rc == CFA_OK) rc = rc1;
   PeerTable pt{};
   pt.n = world;
   for (int r = 0; r < world; ++r) pt.base[r] = (const float*)h_peer_blocks[r] + slot;
@@ -158,14 +159,21 @@ extern "C" int cfa_sparc_loss_gathered_fwd(const void* v, const void* l, const u
   const float* b = a + (size_t)B * D;
   // pack = [lse_a (B) | lse_b (B) | sum CE_a, sum CE_b]: glse and gsums must be adjacent -> use the pack row of this rank
   float* pack = f + w.gpack + (size_t)rank * (2 * B + 2);
-  rc = global_infonce_fwd_peers(a, b, nullptr, nullptr, B, world * B, D, rank * B, scale, 1e-12f, pack, f + w.gnorms,
-                                pack + 2 * B, nullptr, nullptr, 0, 0.f, 0.f, nullptr, f + w.gws, w.gws_bytes, gpath, world, &pt,
-                                stream);
-  if (rc != CFA_OK) return rc;
+  if (rc == CFA_OK)
+    rc = global_infonce_fwd_peers(a, b, nullptr, nullptr, B, world * B, D, rank * B, scale, 1e-12f, pack, f + w.gnorms,
+                                  pack + 2 * B, nullptr, nullptr, 0, 0.f, 0.f, nullptr, f + w.gws, w.gws_bytes, gpath, world, &pt,
+                                  stream);
   // exchange 2: packs of every rank -> gpack (the raw [world][2B+2] layout the finalize / backward kernels index)
-  rc = peer_sync(h_peer_blocks, world, rank, 2 * step + 2, pack, pack_off, (size_t)2 * B + 2, pack_off, 2 * B + 2, f + w.gpack, st);
+  const int rc2 = peer_sync(h_peer_blocks, world, rank, 2 * step + 2, pack, pack_off, (size_t)2 * B + 2, pack_off, 2 * B + 2,
+                            f + w.gpack, st);
+  if (rc == CFA_OK) rc = rc2;
   if (rc != CFA_OK) return rc;
   return cfa_sparc_finalize(f + w.gpack, world * B, f + w.part, mask, B, T, gw, lw, f + w.out8, world, stream);
+}
+
+namespace cfa {
+int sparc_coef_ptrs_scaled(const float* const g[7], float gw, float lw, int global_batch, const float* out8, float* coef8,
+                           float gscale, cudaStream_t st);
 }
 
 extern "C" int cfa_sparc_loss_gathered_bwd(const void* v, const void* l, const uint8_t* mask, int B, int P, int T, int D,
@@ -174,13 +182,23 @@ extern "C" int cfa_sparc_loss_gathered_bwd(const void* v, const void* l, const u
                                            const float* g_total, const float* g_vl, const float* g_lv,
                                            const float* g_vl_local, const float* g_lv_local, void* dv, void* dl, int path,
                                            int world, int rank, void* stream) {
+  return cfa_sparc_loss_gathered_bwd_ex(v, l, mask, B, P, T, D, dtype, thr, scale, gw, lw, workspace, workspace_bytes, g_global,
+                                        g_local, g_total, g_vl, g_lv, g_vl_local, g_lv_local, dv, dl, path, world, rank, 1.f, stream);
+}
+
+extern "C" int cfa_sparc_loss_gathered_bwd_ex(const void* v, const void* l, const uint8_t* mask, int B, int P, int T, int D,
+                                              int dtype, float thr, float scale, float gw, float lw, void* workspace,
+                                              size_t workspace_bytes, const float* g_global, const float* g_local,
+                                              const float* g_total, const float* g_vl, const float* g_lv,
+                                              const float* g_vl_local, const float* g_lv_local, void* dv, void* dl, int path,
+                                              int world, int rank, float global_grad_scale, void* stream) {
   if (B <= 0 || P <= 0 || T <= 0 || D <= 0 || !v || !l || !mask || !workspace || !dv || !dl) return CFA_ERR_BAD_ARG;
   if (world < 2 || world > kMaxPeers || rank < 0 || rank >= world) return CFA_ERR_BAD_ARG;
   const LossWs w = loss_ws_layout(B, P, T, D, dtype, path, world);
   if (workspace_bytes < w.total * sizeof(float)) return CFA_ERR_WORKSPACE;
   float* f = (float*)workspace;
-  int rc = cfa_sparc_coef_ptrs(g_global, g_local, g_total, g_vl, g_lv, g_vl_local, g_lv_local, gw, lw, world * B, f + w.out8,
-                               f + w.coef, stream);
+  const float* const g7[7] = {g_global, g_local, g_total, g_vl, g_lv, g_vl_local, g_lv_local};
+  int rc = sparc_coef_ptrs_scaled(g7, gw, lw, world * B, f + w.out8, f + w.coef, global_grad_scale, (cudaStream_t)stream);
   if (rc != CFA_OK) return rc;
   const int gpath = (dtype == CFA_DTYPE_F32 || path == 1) ? 1 : 0;
   const float* a = f + w.pooled;

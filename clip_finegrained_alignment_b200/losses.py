@@ -154,7 +154,8 @@ class _SparcFunction(torch.autograd.Function):
     no host synchronisation, zero-fill or concatenation anywhere."""
 
     @staticmethod
-    def forward(ctx, v, l, mask, thr, gw, lw, scale, gather, group, path, fused=True):
+    @torch.amp.custom_fwd(device_type="cuda")          # records the autocast state for backward; inputs keep the dtype
+    def forward(ctx, v, l, mask, thr, gw, lw, scale, gather, group, path, fused=True, ddp_mean=True):   # autocast handed over (finetuner.py:120)
         dev = _lib.require_cuda(v, l, mask)
         if v.dtype != l.dtype or v.dtype not in _lib.DTYPE_CODE:
             raise _lib.CfaError(f"SPARCLoss: embeddings must share a dtype in fp32/bf16/fp16, got {v.dtype}, {l.dtype}")
@@ -170,6 +171,7 @@ class _SparcFunction(torch.autograd.Function):
         world, rank, group = _dist_ctx(group, gather)
         ctx.set_materialize_grads(False)               # unused outputs arrive as None: no zero-fill launches
         ctx.peer = None
+        ctx.gscale = float(world) if (ddp_mean and world > 1) else 1.0     # see SPARCLoss.__init__ (gather_grad_reduce)
         if world > 1 and fused and gather != "nccl":
             # gathered loss over peer memory: one library call per direction, no collective call (csrc/peer_exchange.cu)
             gpath = 1 if (v.dtype == torch.float32 or path == 1) else 0
@@ -251,6 +253,7 @@ class _SparcFunction(torch.autograd.Function):
         return out8[:7].clone().unbind(0)
 
     @staticmethod
+    @torch.amp.custom_bwd(device_type="cuda")
     def backward(ctx, *grads):
         v, l, mask_u8, blk = ctx.saved_tensors
         thr, gw, lw, scale, code, path, ptr, gq = ctx.hp
@@ -274,17 +277,19 @@ class _SparcFunction(torch.autograd.Function):
             dl = torch.empty_like(l)
             with (contextlib.nullcontext() if same_dev else torch.cuda.device(dev)):
                 if ctx.peer is not None:
-                    _lib.call("cfa_sparc_loss_gathered_bwd", v.data_ptr(), l.data_ptr(), mask_u8.data_ptr(), B, P, T, D, code,
+                    _lib.call("cfa_sparc_loss_gathered_bwd_ex", v.data_ptr(), l.data_ptr(), mask_u8.data_ptr(), B, P, T, D, code,
                               thr, scale, gw, lw, blk.data_ptr(), blk.numel(), *gptr, dv.data_ptr(), dl.data_ptr(), path,
-                              ctx.peer[0], ctx.peer[1], _lib.stream_ptr())
+                              ctx.peer[0], ctx.peer[1], ctx.gscale, _lib.stream_ptr())
                 else:
                     _lib.call("cfa_sparc_loss_bwd", v.data_ptr(), l.data_ptr(), mask_u8.data_ptr(), B, P, T, D, code, thr,
                               scale, gw, lw, blk.data_ptr(), blk.numel(), *gptr, dv.data_ptr(), dl.data_ptr(), path,
                               _lib.stream_ptr())
-            return dv, dl, None, None, None, None, None, None, None, None, None
+            return dv, dl, None, None, None, None, None, None, None, None, None, None
         with (contextlib.nullcontext() if same_dev else torch.cuda.device(dev)):
             coef = torch.empty(8, dtype=torch.float32, device=dev)
             _lib.call("cfa_sparc_coef_ptrs", *gptr, gw, lw, gst.Bg, ptr[1], coef.data_ptr(), _lib.stream_ptr())
+            if ctx.gscale != 1.0:
+                coef[:2] *= ctx.gscale                 # global term only (coef[2:4] are the rank-local fine-grained ones)
             dpv, dpl = _global_backward(gst, coef)
             dv = torch.empty_like(v)
             dl = torch.empty_like(l)
@@ -293,7 +298,7 @@ class _SparcFunction(torch.autograd.Function):
             _lib.call("cfa_sparc_bwd", v.data_ptr(), l.data_ptr(), mask_u8.data_ptr(), B, P, T, D, code, thr, scale,
                       ptr[5], ptr[2], ptr[3], ptr[6], ptr[7], gq[0], gq[1], coef.data_ptr() + 8, dpv.data_ptr(), dpl.data_ptr(),
                       dv.data_ptr(), dl.data_ptr(), sptr, sbytes, path, _lib.stream_ptr())
-        return dv, dl, None, None, None, None, None, None, None, None, None
+        return dv, dl, None, None, None, None, None, None, None, None, None, None
 
 
 class _PairwiseFunction(torch.autograd.Function):
@@ -364,8 +369,17 @@ class SPARCLoss(nn.Module):
     """SPARC loss (https://arxiv.org/abs/2401.09865), reference API: finetune/losses.py:136-264."""
 
     def __init__(self, config, gather=False, process_group=None, kernel_path: str = "auto",
-                 fused_calls: bool = True, cast_to_bf16: bool = False):
+                 fused_calls: bool = True, cast_to_bf16: bool = False, gather_grad_reduce: str = "mean"):
         super().__init__()
+        # gather_grad_reduce (only with gather=True, world > 1): how the caller combines parameter gradients over ranks.
+        #   "mean" (default, what DistributedDataParallel does, dist_finetuner.py:57): the gradient of the all-gathered
+        #          GLOBAL term is multiplied by the world size, so that after DDP's average every parameter receives
+        #          d(global mean loss)/d(theta) — all-gather-with-grad semantics, where the reduce-scatter sums the ranks'
+        #          contributions before the DDP mean.  The rank-local fine-grained term needs no factor.
+        #   "sum"  (or any scheme that adds the ranks' gradients): the plain d(global mean loss)/d(local rows), once per rank.
+        if gather_grad_reduce not in ("mean", "sum"):
+            raise ValueError(f"gather_grad_reduce must be 'mean' or 'sum', got {gather_grad_reduce!r}")
+        self.gather_grad_reduce = gather_grad_reduce
         # cast_to_bf16 (opt-in): fp16 embeddings — what torch.autocast() hands the loss by default (finetuner.py:120) — and
         # fp32 embeddings (use_amp off, finetuner.py:156) are rounded to bf16 on entry so that the tcgen05 kernels run
         # (measured 17x faster at config 2 than the fp32-exact CUDA-core path those dtypes are otherwise routed to);
@@ -409,7 +423,7 @@ class SPARCLoss(nn.Module):
         out = _SparcFunction.apply(v_patch_embed, l_token_embed, language_mask, float(self.similarity_threshold),
                                    float(self.global_loss_weight), float(self.local_loss_weight),
                                    float(self.inverse_temperature), self.gather, self.process_group, self.kernel_path,
-                                   self.fused_calls)
+                                   self.fused_calls, self.gather_grad_reduce == "mean")
         return dict(zip(SPARC_KEYS, out))                  # one autograd node, 7 outputs
 
 
@@ -418,7 +432,7 @@ class SPARCLoss(nn.Module):
 # ----------------------------------------------------------------------------------------------
 class _ClipFunction(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, img, txt, temperature, gather, group):
+    def forward(ctx, img, txt, temperature, gather, group, ddp_mean=True):
         dev = _lib.require_cuda(img, txt)
         if img.dim() != 2 or img.shape != txt.shape:
             raise _lib.CfaError(f"CustomCLIPLoss: expected two [B,D] tensors, got {tuple(img.shape)}, {tuple(txt.shape)}")
@@ -426,6 +440,7 @@ class _ClipFunction(torch.autograd.Function):
         ctx.peer = None
         with torch.cuda.device(dev):
             world, rank, group = _dist_ctx(group, gather)
+            ctx.gscale = float(world) if (ddp_mean and world > 1) else 1.0      # see SPARCLoss.__init__ (gather_grad_reduce)
             B, D = img.shape
             if world > 1 and gather != "nccl" and img.dtype != torch.float32 \
                     and _L.cfa_global_infonce_path(B, world * B, D, 0) == 2:
@@ -457,31 +472,35 @@ class _ClipFunction(torch.autograd.Function):
             ab, ws = ctx.saved_tensors
             _, B, D = ab.shape
             with torch.cuda.device(ab.device):
-                c = (g.to(torch.float32).reshape(1) * (0.5 / (world * B))).expand(2).contiguous()
+                c = (g.to(torch.float32).reshape(1) * (ctx.gscale * 0.5 / (world * B))).expand(2).contiguous()
                 dab = torch.empty_like(ab)
                 _lib.call("cfa_global_infonce_gathered_bwd", ab.data_ptr(), B, D, scale, 0.0, ws.data_ptr(), ws.numel(),
                           c.data_ptr(), dab.data_ptr(), world, rank, _lib.stream_ptr())
-            return dab[0].to(ctx.dt[0]), dab[1].to(ctx.dt[1]), None, None, None
+            return dab[0].to(ctx.dt[0]), dab[1].to(ctx.dt[1]), None, None, None, None
         gst = ctx.gst
         with torch.cuda.device(gst.a.device):
-            c = (g.to(torch.float32).reshape(1) * (0.5 / gst.Bg)).expand(2).contiguous()
+            c = (g.to(torch.float32).reshape(1) * (ctx.gscale * 0.5 / gst.Bg)).expand(2).contiguous()
             da, db = _global_backward(gst, c)
-        return da.to(ctx.dt[0]), db.to(ctx.dt[1]), None, None, None
+        return da.to(ctx.dt[0]), db.to(ctx.dt[1]), None, None, None, None
 
 
 class CustomCLIPLoss(nn.Module):
     """Symmetric CLIP InfoNCE, reference API: finetune/losses.py:7-36 (logits are DIVIDED by temperature)."""
 
-    def __init__(self, temperature: float = 0.07, gather: bool = False, process_group=None):
+    def __init__(self, temperature: float = 0.07, gather: bool = False, process_group=None,
+                 gather_grad_reduce: str = "mean"):
         super().__init__()
         self.temperature = temperature
         self.gather = gather
         self.process_group = process_group
+        if gather_grad_reduce not in ("mean", "sum"):
+            raise ValueError(f"gather_grad_reduce must be 'mean' or 'sum', got {gather_grad_reduce!r}")
+        self.gather_grad_reduce = gather_grad_reduce       # see SPARCLoss.__init__
 
     def forward(self, image_features: torch.Tensor, text_features: torch.Tensor,
                 custom_features: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
         clip_loss = _ClipFunction.apply(image_features, text_features, float(self.temperature), self.gather,
-                                        self.process_group)
+                                        self.process_group, self.gather_grad_reduce == "mean")
         return {"clip_loss": clip_loss, "total_loss": clip_loss}
 
 

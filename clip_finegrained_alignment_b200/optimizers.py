@@ -238,9 +238,34 @@ class AdamSPD(Optimizer):
             plan.h_evt[k].synchronize()      # normally long finished: two steps ago
         tab = plan.h_np[k]
         tab["g"] = np.fromiter((g.data_ptr() for g in grads), dtype=np.uint64, count=plan.n)
-        # parameters may have been re-pointed (p.data = ...): refresh the static pointers if any changed
+        # The reference re-reads group['pre'][j], group['amsgrad'] and the state tensors on every step (optimizers.py:58-98):
+        # parameters may have been re-pointed (p.data = ...), the anchors replaced (re-anchoring SPD), a state tensor
+        # reassigned or amsgrad toggled since the plan was built -> compare every cached pointer, rebuild on any change
         pptr = np.fromiter((p.data_ptr() for p in plan.grad_params), dtype=np.uint64, count=plan.n)
-        if not np.array_equal(pptr, plan.static["p"]):
+        stale = not np.array_equal(pptr, plan.static["p"])
+        if not stale:
+            ams = plan.amsgrad
+            mptr = np.fromiter((st["exp_avg"].data_ptr() for st in plan.states), dtype=np.uint64, count=plan.n)
+            vptr = np.fromiter((st["exp_avg_sq"].data_ptr() for st in plan.states), dtype=np.uint64, count=plan.n)
+            stale = not (np.array_equal(mptr, plan.static["m"]) and np.array_equal(vptr, plan.static["v"]))
+            if not stale:
+                k2 = 0
+                for gi, group in enumerate(self.param_groups):
+                    if bool(group["amsgrad"]) != bool(ams):
+                        stale = True
+                        break
+                    pre_list = group["pre"]
+                    for j, p in enumerate(group["params"]):
+                        if p.grad is None:
+                            continue
+                        pre = pre_list[j] if pre_list is not None else None
+                        if (0 if pre is None else pre.data_ptr()) != int(plan.static["pre"][k2]):
+                            stale = True
+                            break
+                        k2 += 1
+                    if stale:
+                        break
+        if stale:
             self._plan = None
             plan = self._build_plan(grads)
             return self._launch(plan, grads, amp)

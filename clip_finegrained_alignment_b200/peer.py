@@ -28,6 +28,8 @@ class PeerExchange:
         self.rank = dist.get_rank(group)
         self.B, self.D = B, D
         self.step = 0                                   # gathered forwards issued so far (same on every rank)
+        self._status = None                             # pinned int32: barriers of this rank that timed out
+        self._reported = 0
         self.nbytes = _L.cfa_peer_exchange_bytes(B, D)
         self._own = C.c_void_p()
         handle = (C.c_ubyte * 64)()
@@ -60,7 +62,27 @@ class PeerExchange:
     def next_step(self) -> int:
         s = self.step
         self.step = (s + 1) & 0x7FFFFFFF        # epochs 2s+1, 2s+2 run round the uint32 ring
+        if (s & 63) == 63:
+            self.check()                        # cheap: looks at the value an earlier asynchronous copy brought back
         return s
+
+    def check(self, sync: bool = False) -> None:
+        """Raise CfaError if a device barrier of this rank timed out (a peer never arrived: its step produced NaN losses,
+        which GradScaler would silently turn into skipped steps).  Called every 64 gathered steps; `sync=True` waits for
+        the stream first (end of an epoch, before a checkpoint)."""
+        if self._status is None:
+            self._status = torch.zeros(1, dtype=torch.int32).pin_memory()
+        if sync:
+            torch.cuda.current_stream().synchronize()
+        n = int(self._status[0])                # value copied back by the PREVIOUS call (no host synchronisation)
+        _lib.check(_L.cfa_peer_status(self._own.value, self._status.data_ptr(), _lib.stream_ptr()), "cfa_peer_status")
+        if sync:
+            torch.cuda.current_stream().synchronize()
+            n = int(self._status[0])
+        if n > self._reported:
+            self._reported = n
+            raise _lib.CfaError(f"gathered loss: {n} device barrier(s) of rank {self.rank} timed out waiting for a peer "
+                                "(CFA_PEER_TIMEOUT_MS); the losses of those steps are NaN")
 
     def close(self):
         for p in self._opened:

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define CFA_ABI_VERSION 3
+#define CFA_ABI_VERSION 4
 
 #define CFA_DTYPE_F32 0
 #define CFA_DTYPE_BF16 1
@@ -215,6 +215,10 @@ int cfa_peer_free(void* dev_ptr);
 /* one barrier on its own: push `push_words` floats into the own block at word offset push_off_words, signal `epoch`
  * to every peer, wait for theirs, then pull `pull_words` floats from word offset pull_off_words of EVERY block into
  * pull_dst [world][pull_words].  Word offsets >= 64 (the header holds the flags). */
+/* Barriers of this rank that ran into their time-out so far (a peer never arrived within CFA_PEER_TIMEOUT_MS, default
+ * 600 000 ms): the losses of such a step are NaN.  Asynchronous device-to-host copy of the counter on `stream` into
+ * h_count (pinned memory recommended); the caller decides when to look at it (PeerExchange.check()). */
+int cfa_peer_status(const void* own_block, unsigned int* h_count, void* stream);
 int cfa_peer_sync(void* const* h_peer_blocks, int world, int rank, uint32_t epoch, const float* push_src,
                   size_t push_off_words, size_t push_words, size_t pull_off_words, int pull_words, float* pull_dst,
                   void* stream);
@@ -227,6 +231,17 @@ int cfa_sparc_loss_gathered_bwd(const void* v, const void* l, const uint8_t* mas
                                 const float* g_global, const float* g_local, const float* g_total, const float* g_vl,
                                 const float* g_lv, const float* g_vl_local, const float* g_lv_local, void* dv, void* dl,
                                 int path, int world, int rank, void* stream);
+/* Same with a factor on the GLOBAL term of the gradient.  cfa_sparc_loss_gathered_bwd returns d(global mean loss)/d(local
+ * rows) once per rank.  Under DistributedDataParallel the parameter gradients are AVERAGED over ranks afterwards, which
+ * would divide the global term (identical on every rank) by the world size relative to all-gather-with-grad semantics,
+ * where the reduce-scatter SUMS the ranks' contributions before the DDP mean.  global_grad_scale = world restores
+ * d(global mean loss)/d(theta) after that mean (the rank-local fine-grained term needs no factor: its own 1/N_valid is
+ * per rank).  global_grad_scale = 1: the plain gradient w.r.t. the local rows. */
+int cfa_sparc_loss_gathered_bwd_ex(const void* v, const void* l, const uint8_t* mask, int B, int P, int T, int D, int dtype,
+                                   float thr, float scale, float gw, float lw, void* workspace, size_t workspace_bytes,
+                                   const float* g_global, const float* g_local, const float* g_total, const float* g_vl,
+                                   const float* g_lv, const float* g_vl_local, const float* g_lv_local, void* dv, void* dl,
+                                   int path, int world, int rank, float global_grad_scale, void* stream);
 
 /*
  * The gathered global InfoNCE alone over the same exchange blocks (CustomCLIPLoss / CLIPCountLoss with gather = True:

@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
     for s in syms:
         assert hasattr(raw, s), f"{s} declared in include/cfa_b200.h but not exported"
         assert s in _lib.SIGNATURES, f"{s} has no ctypes signature"
-    assert _lib.lib.cfa_abi_version() == 3
+    assert _lib.lib.cfa_abi_version() == 4
     assert _lib.lib.cfa_error_string(-2).startswith(b"cfa:")
     assert _lib.lib.cfa_adamspd_chunk_elems() == 8192
 
@@ -125,3 +125,11 @@ def test_product_never_imports_oracle():
         for f in files:
             if f.endswith(".py"):
                 assert not pat.search(open(os.path.join(dirpath, f)).read()), f
+
+
+def test_launch_table_holds_ints_for_declared_symbols():
+    """_lib.LAUNCHES feeds bench.py's gpu_launches: every value is a launch count, every key a declared entry point."""
+    from clip_finegrained_alignment_b200 import _lib
+    for name, n in _lib.LAUNCHES.items():
+        assert isinstance(n, int) and n >= 0, (name, n)
+        assert name in _lib.SIGNATURES, name

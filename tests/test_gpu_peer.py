@@ -294,7 +294,29 @@ clip_ok = abs(ca[0] - cb[0]) <= 1e-6 * abs(cb[0]) and float((ca[1] - cb[1]).norm
 a, b = res["True"], res["nccl"]
 ok = used_peer and clip_ok and abs(a[0] - b[0]) <= 1e-6 * abs(b[0]) and abs(a[1] - b[1]) <= 1e-6 * abs(b[1]) \
     and float((a[2] - b[2]).norm() / b[2].norm()) <= 1e-4 and float((a[3] - b[3]).norm() / b[3].norm()) <= 1e-4
-print(json.dumps({"rank": rank, "ok": bool(ok), "used_peer": bool(used_peer), "total": a[0], "total_nccl": b[0]}), flush=True)
+# ---- against the ORACLE on the concatenated batch (not only against the NCCL path of the same kernels)
+from oracle import losses_oracle as lo
+vs = [torch.empty_like(v0) for _ in range(world)]; ls = [torch.empty_like(l0) for _ in range(world)]
+dist.all_gather(vs, v0); dist.all_gather(ls, l0)
+thr = float(torch.tensor(1.0 / P, dtype=torch.float32))
+mc = m.cpu()
+fw = [lo.sparc_forward(x.cpu().double(), y.cpu().double(), mc, thr, 0.0, 1.0, 1.0) for x, y in zip(vs, ls)]
+ga, gb = torch.cat([f["_cache"]["vbar_raw"] for f in fw]), torch.cat([f["_cache"]["lbar_raw"] for f in fw])
+f1, f2 = lo.infonce_forward(ga, gb, 1.0), lo.infonce_forward(gb, ga, 1.0)
+Bg = world * B
+glob = float(0.5 * (f1["loss_sum"] + f2["loss_sum"]) / Bg)
+da, db = lo.symmetric_infonce_backward(f1["ah"], f1["an"], f1["bh"], f1["bn"], f1["lse"], f2["lse"], 1.0, 0.5, 0.5, float(Bg))
+gv, gl = lo.sparc_backward(fw[rank])
+sl = slice(rank * B, (rank + 1) * B)
+# default gather_grad_reduce="mean": the global term carries the factor `world` (DDP averages the ranks afterwards)
+dv_ref = gv + world * (da[sl] / P)[:, None, :]
+dl_ref = gl + world * (db[sl] / fw[rank]["_cache"]["cnt"])[:, None, :] * mc[..., None].double()
+rel = lambda x, r: float((x.double() - r).norm() / r.norm())
+oracle_ok = abs(a[1] - glob) <= 1e-4 * abs(glob) and abs(a[0] - (glob + float(fw[rank]["local_loss"]))) <= 1e-4 * abs(a[0]) \
+    and rel(a[2], dv_ref) <= 1e-3 + 2 ** -8 and rel(a[3], dl_ref) <= 1e-3 + 2 ** -8
+ok = ok and oracle_ok
+print(json.dumps({"rank": rank, "ok": bool(ok), "oracle_ok": bool(oracle_ok), "used_peer": bool(used_peer), "total": a[0],
+                  "total_nccl": b[0], "dv_rel": rel(a[2], dv_ref), "dl_rel": rel(a[3], dl_ref)}), flush=True)
 dist.destroy_process_group()
 sys.exit(0 if ok else 1)
 '''
