@@ -459,7 +459,7 @@ sparc_bwd3_kernel(const __grid_constant__ CUtensorMap tmV0, const __grid_constan
     tc_fence_after();
     stamp();
     if (e_act) {
-#pragma unroll
+#pragma unroll 1                                   // one hot loop body instead of 5 cold copies (instruction fetch)
       for (int g8 = 0; g8 < 5; ++g8) {
         const int c0 = c_lo + 8 * g8;
         if (8 * g8 < cw) {
@@ -507,7 +507,7 @@ sparc_bwd3_kernel(const __grid_constant__ CUtensorMap tmV0, const __grid_constan
     stamp();
     float vq = 0.f;
     if (e_act) {
-#pragma unroll
+#pragma unroll 1                                   // one hot loop body instead of 5 cold copies (instruction fetch)
       for (int g8 = 0; g8 < 5; ++g8) {
         const int c0 = c_lo + 8 * g8;
         if (8 * g8 < cw) {
@@ -615,6 +615,7 @@ sparc_bwd3_kernel(const __grid_constant__ CUtensorMap tmV0, const __grid_constan
       if (row_ok) *reinterpret_cast<uint4*>(dst) = pack_raw8<kHalf>(ov);
     };
     const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll 1
     for (int blk = 0; blk < NBLK; ++blk) {
       const size_t dcol = (size_t)blk * 128 + dloc;
       const float dpl = p.dpool_l ? __ldg(p.dpool_l + (size_t)b * D + dcol) : 0.f;
@@ -656,29 +657,30 @@ sparc_bwd3_kernel(const __grid_constant__ CUtensorMap tmV0, const __grid_constan
       {   // unit B: dv[p][d] = dv^T[d][p] - v[p][d] vfac_p + dvbar[d] / P
         const bf16* vsrc = vsrc0 + blk * 128;
         bf16* vdst = vdst0 + blk * 128;
-        uint4 rawc = (tr < pn) ? __ldg(reinterpret_cast<const uint4*>(vsrc)) : zero4, rawn = zero4;
+        // raw row pieces are requested two chunks ahead (L2 latency ~ 1 k cycles under load, a chunk takes less); the chunk
+        // loop stays ROLLED: one hot body of ~100 instructions instead of 7 copies (instruction fetch)
+        uint4 raw0 = (tr < pn) ? __ldg(reinterpret_cast<const uint4*>(vsrc)) : zero4;
+        uint4 raw1 = (8 < pw && 8 + tr < pn) ? __ldg(reinterpret_cast<const uint4*>(vsrc + (size_t)8 * D)) : zero4;
         mbar_wait_sleep(ob_full, blk & 1);
         tc_fence_after();
-#pragma unroll
-        for (int c0 = 0; c0 < 64; c0 += 8) {
-          if (c0 < pw) {
-            float x[8];
-            if (c0 + 8 <= pw) tmem_ld8(tq + cDV + p_lo + c0, x);
-            else tmem_ld4(tq + cDV + p_lo + c0, x);     // pw is a multiple of 4
-            if (c0 + 8 < pw) rawn = (c0 + 8 + tr < pn) ? __ldg(reinterpret_cast<const uint4*>(vsrc + (size_t)(c0 + 8) * D)) : zero4;
-            tmem_ld_wait();
-            if (c0 + 8 >= pw) {                         // last chunk: the accumulator is in registers
-              tc_fence_before();
-              __syncwarp();
-              if (lane == 0) mbar_arrive(ob_free);
-            }
-            const int nc = (c0 + 8 <= pw) ? 8 : 4;
-#pragma unroll
-            for (int k = 0; k < 8; ++k) x[k] = (k < nc) ? x[k] + dpv : 0.f;
-            const bool ok = c0 + tr < pn;
-            emit8(x, rawc, ok ? vfac[p_lo + c0 + tr] : 0.f, ok, vdst + (size_t)c0 * D);
-            rawc = rawn;
+#pragma unroll 1
+        for (int c0 = 0; c0 < pw; c0 += 8) {
+          float x[8];
+          const bool full8 = c0 + 8 <= pw;
+          if (full8) tmem_ld8(tq + cDV + p_lo + c0, x);
+          else tmem_ld4(tq + cDV + p_lo + c0, x);       // pw is a multiple of 4
+          const uint4 raw2 = (c0 + 16 < pw && c0 + 16 + tr < pn) ? __ldg(reinterpret_cast<const uint4*>(vsrc + (size_t)(c0 + 16) * D)) : zero4;
+          tmem_ld_wait();
+          if (c0 + 8 >= pw) {                           // last chunk: the accumulator is in registers
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(ob_free);
           }
+#pragma unroll
+          for (int k = 0; k < 8; ++k) x[k] = (full8 || k < 4) ? x[k] + dpv : 0.f;
+          const bool ok = c0 + tr < pn;
+          emit8(x, raw0, ok ? vfac[p_lo + c0 + tr] : 0.f, ok, vdst + (size_t)c0 * D);
+          raw0 = raw1; raw1 = raw2;
         }
         if (blk == 0) stamp();
       }

@@ -392,7 +392,7 @@ sparc_fwd3_kernel(const __grid_constant__ CUtensorMap tmV0, const __grid_constan
     const int combo = mb * 4 + q;
     const float invP = 1.f / (float)P;
     if (e1_act) {
-#pragma unroll
+#pragma unroll 1                                   // one hot loop body instead of 5 cold copies (instruction fetch)
       for (int g8 = 0; g8 < 5; ++g8) {
         const int c0 = c_lo + 8 * g8;
         if (8 * g8 < cw) {
@@ -425,7 +425,7 @@ sparc_fwd3_kernel(const __grid_constant__ CUtensorMap tmV0, const __grid_constan
         cst[c_lo + j].z = 1.f / (mx - mn + kF3MinMaxEps);
       }
       __syncwarp();
-#pragma unroll
+#pragma unroll 1                                   // one hot loop body instead of 5 cold copies (instruction fetch)
       for (int g8 = 0; g8 < 5; ++g8) {
         const int c0 = c_lo + 8 * g8;
         if (8 * g8 < cw) {
@@ -495,6 +495,7 @@ sparc_fwd3_kernel(const __grid_constant__ CUtensorMap tmV0, const __grid_constan
       uint8_t* stl = sth + 512;
       const int tr = lane >> 2, tc16 = (lane & 3) * 16;
       bf16* gq0 = p.g_split + ((size_t)b * 2) * pstride + (size_t)(g_lo + tr) * D + 32 * q + (lane & 3) * 8;
+#pragma unroll 1
       for (int blk = 0; blk < NBLK; ++blk) {
         const int buf = blk & 1;
         mbar_wait_sleep(g_full + buf, (blk >> 1) & 1);
@@ -505,13 +506,11 @@ sparc_fwd3_kernel(const __grid_constant__ CUtensorMap tmV0, const __grid_constan
         for (int c = 0; c < 24; c += 8) {                  // 8 columns at a time: hi-part and lo-part of the same tokens
           if (c < gw_) {
             float xh[8], xl[8];
-            if (pf && blk == 1 && c == 0) pf[12] = clock64();
             if (c + 8 <= gw_) { tmem_ld8(tg + c, xh); tmem_ld8(tg + NT + c, xl); }
             else { tmem_ld4(tg + c, xh); tmem_ld4(tg + NT + c, xl); }
             const float4 is0 = *reinterpret_cast<const float4*>(isg + g_lo + c);
             const float4 is1 = (c + 8 <= gw_) ? *reinterpret_cast<const float4*>(isg + g_lo + c + 4) : make_float4(0.f, 0.f, 0.f, 0.f);
             tmem_ld_wait();
-            if (pf && blk == 1 && c == 0) pf[13] = clock64();
             if (c + 8 >= gw_) {                            // last chunk: the accumulator is in registers
               tc_fence_before();
               __syncwarp();
@@ -534,7 +533,6 @@ sparc_fwd3_kernel(const __grid_constant__ CUtensorMap tmV0, const __grid_constan
               reinterpret_cast<bf16*>(stl)[k * 32 + lane] = __float2bfloat16_rn(g - __bfloat162float(h));
             }
             __syncwarp();
-            if (pf && blk == 1 && c == 0) pf[14] = clock64();
             const uint4 vh = *reinterpret_cast<const uint4*>(sth + tr * 64 + tc16);
             const uint4 vl = *reinterpret_cast<const uint4*>(stl + tr * 64 + tc16);
             __syncwarp();
@@ -542,19 +540,19 @@ sparc_fwd3_kernel(const __grid_constant__ CUtensorMap tmV0, const __grid_constan
               *reinterpret_cast<uint4*>(gq + (size_t)c * D) = vh;
               *reinterpret_cast<uint4*>(gq + (size_t)c * D + pstride) = vl;
             }
-            if (pf && blk == 1 && c == 0) pf[15] = clock64();
           }
         }
         if (blk == 0) stamp();
       }
     }
 #pragma unroll
-    for (int k = 0; k < 20; ++k) {
-      if (k < gw_) {
-        const float s = warp_sum(gn2[k]);
-        if (lane == 0) part_s[q * NT + g_lo + k] = s;
+    for (int c = 0; c < 24; c += 8) {                    // column sums over the warp's 32 feature lanes, 8 columns per pass
+      if (c < gw_) {
+        const float s = warp_colsum8(gn2 + c, lane);
+        if ((lane & 17) == 0 && c + (lane >> 1) < gw_) part_s[q * NT + g_lo + c + (lane >> 1)] = s;
       }
     }
+    if (pf) pf[11] = clock64();
     f3_epi_bar();
     if (tid < NT) {
       const float s = (part_s[tid] + part_s[NT + tid]) + (part_s[2 * NT + tid] + part_s[3 * NT + tid]);
@@ -568,6 +566,7 @@ sparc_fwd3_kernel(const __grid_constant__ CUtensorMap tmV0, const __grid_constan
     // ---- E3: logits[t][j] = s L'[t][j] / (sigma_t ||G_t|| ||l_j||)  (TMEM: lane = j, columns = t), masked LSE both ways
     mbar_wait_sleep(l_full, 0);
     tc_fence_after();
+    if (pf) pf[12] = clock64();
     float* Lb = reinterpret_cast<float*>(SR);           // [NT][NT + 1], the S_raw^T region is free once L' is done
     const int ldl = NT + 1;
     const int jrow = 32 * q + lane;
@@ -577,7 +576,7 @@ sparc_fwd3_kernel(const __grid_constant__ CUtensorMap tmV0, const __grid_constan
       const float ilj = jin ? cst[jrow].x : 0.f;
       float* lrow = Lb + g_lo * ldl + jrow;
       float* grow = p.tt_logits ? p.tt_logits + ((size_t)b * T + g_lo) * T + jrow : nullptr;
-#pragma unroll
+#pragma unroll 1
       for (int c = 0; c < 20; c += 4) {
         if (c < gw_) {
           float xh[4], xl[4];
@@ -596,6 +595,7 @@ sparc_fwd3_kernel(const __grid_constant__ CUtensorMap tmV0, const __grid_constan
         }
       }
     }
+    if (pf) pf[13] = clock64();
     f3_epi_bar();
     stamp();
     // LSE: 4 threads per row / column, a quarter of the entries each.  |logit| <= |scale| (cosines), so for moderate
@@ -629,6 +629,7 @@ sparc_fwd3_kernel(const __grid_constant__ CUtensorMap tmV0, const __grid_constan
         }
         const float tot = warp_sum(ce);
         if (lane == 0) red[dir * kF3EpiWarps + ew] = tot;
+        if (pf) pf[14 + dir] = clock64();
       }
     }
     f3_epi_bar();

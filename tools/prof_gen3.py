@@ -39,4 +39,4 @@ for which, setter in (('fwd', _lib.lib.cfa_debug_set_profile_buffer_fwd), ('bwd'
         if which == 'bwd': print('  P4 MMA waits: full %.0f  out_free %.0f' % (float(t[sel, 8].median()), float(t[sel, 9].median())))
         print(' epilogue thread 0:')
         for i, n in enumerate(names[which][1]): print(f'  {n:20s} {float((epi[:, i:i+1] - t0).median()):10.0f}')
-        print('  chunk probe (pf[12..15] deltas):', [float((t[sel, 16+12+k+1] - t[sel, 16+12+k]).median()) for k in range(3)])
+        if which == 'fwd': print('  E3 probes since start (gn2 sums written, l_full seen, logits loop done, LSE dir 0, LSE dir 1):', [float((t[sel, 16+k:16+k+1] - t0).median()) for k in (11, 12, 13, 14, 15)])
