@@ -459,15 +459,20 @@ sparc_bwd3_kernel(const __grid_constant__ CUtensorMap tmV0, const __grid_constan
     tc_fence_after();
     stamp();
     if (e_act) {
+      // software-pipelined TMEM reads (here and in E3'): the loads of chunk g8 + 1 are issued once chunk g8's inputs are
+      // consumed, so their latency overlaps the hi|lo splits and the shared-memory / TMEM stores of chunk g8
+      float x[8], qh[8], ql[8];
+      tmem_ld8(tS + c_lo, x);
+      tmem_ld8(tW + c_lo, qh);
+      tmem_ld8(tZ + c_lo, ql);
 #pragma unroll 1                                   // one hot loop body instead of 5 cold copies (instruction fetch)
       for (int g8 = 0; g8 < 5; ++g8) {
         const int c0 = c_lo + 8 * g8;
         if (8 * g8 < cw) {
-          float x[8], qh[8], ql[8], w[8];
-          tmem_ld8(tS + c0, x);
-          tmem_ld8(tW + c0, qh);
-          tmem_ld8(tZ + c0, ql);
-          tmem_ld_wait();
+          float w[8], sr[8], qq[8];
+          tmem_ld_wait8(x);
+          tmem_ld_wait8(qh);
+          tmem_ld_wait8(ql);
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const float4 a4 = cA[c0 + j];
@@ -475,8 +480,13 @@ sparc_bwd3_kernel(const __grid_constant__ CUtensorMap tmV0, const __grid_constan
             const float raw = live ? x[j] : 0.f;
             const float nn = __fmul_rn(__fsub_rn(__fmul_rn(__fmul_rn(raw, ivp), a4.x), a4.y), a4.z);   // the forward's roundings
             w[j] = (live && !(nn < p.thr)) ? nn * d2.x : 0.f;
-            x[j] = raw;
-            qh[j] = d2.y * (qh[j] + ql[j]);              // -gfac Q (gfac = 0 for masked tokens)
+            sr[j] = raw;
+            qq[j] = d2.y * (qh[j] + ql[j]);              // -gfac Q (gfac = 0 for masked tokens)
+          }
+          if (8 * g8 + 8 < cw) {
+            tmem_ld8(tS + c0 + 8, x);
+            tmem_ld8(tW + c0 + 8, qh);
+            tmem_ld8(tZ + c0 + 8, ql);
           }
           if (prow < NP) {
             uint4 hi, lo;
@@ -484,11 +494,11 @@ sparc_bwd3_kernel(const __grid_constant__ CUtensorMap tmV0, const __grid_constan
             split_hilo8(w, hi, lo);
             *reinterpret_cast<uint4*>(WT + off) = hi;
             *reinterpret_cast<uint4*>(WT + plane + off) = lo;
-            split_hilo8(x, hi, lo);
+            split_hilo8(sr, hi, lo);
             *reinterpret_cast<uint4*>(SR + off) = hi;
             *reinterpret_cast<uint4*>(SR + plane + off) = lo;
           }
-          tmem_st8(tW + c0, qh);
+          tmem_st8(tW + c0, qq);
         }
       }
       tmem_st_wait();
@@ -507,15 +517,18 @@ sparc_bwd3_kernel(const __grid_constant__ CUtensorMap tmV0, const __grid_constan
     stamp();
     float vq = 0.f;
     if (e_act) {
+      float x[8], dw[8], z[8];
+      tmem_ld8(tS + c_lo, x);
+      tmem_ld8(tW + c_lo, dw);
+      tmem_ld8(tZ + c_lo, z);
 #pragma unroll 1                                   // one hot loop body instead of 5 cold copies (instruction fetch)
       for (int g8 = 0; g8 < 5; ++g8) {
         const int c0 = c_lo + 8 * g8;
         if (8 * g8 < cw) {
-          float x[8], dw[8], z[8], pr[8], wg[8];
-          tmem_ld8(tS + c0, x);
-          tmem_ld8(tW + c0, dw);
-          tmem_ld8(tZ + c0, z);
-          tmem_ld_wait();
+          float dsh[8], dk[8], pr[8], wg[8];
+          tmem_ld_wait8(x);
+          tmem_ld_wait8(dw);
+          tmem_ld_wait8(z);
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const float4 a4 = cA[c0 + j];
@@ -525,25 +538,30 @@ sparc_bwd3_kernel(const __grid_constant__ CUtensorMap tmV0, const __grid_constan
             const float nn = __fmul_rn(__fsub_rn(s, a4.y), a4.z);
             const bool kept = live && !(nn < p.thr);
             const float d = kept ? dw[j] : 0.f;
-            dw[j] = d;
+            dk[j] = d;
             const float ds = d * a4.w;                    // / (sigma range)
             const float prod = ds * s;
             pr[j] = prod;
             vq += prod;
-            x[j] = fmaf(ds * a4.x, ivp, live ? z[j] : 0.f);             // dShat' = dShat + Z
+            dsh[j] = fmaf(ds * a4.x, ivp, live ? z[j] : 0.f);           // dShat' = dShat + Z
             wg[j] = kept ? (nn * d2.x) * d2.y : 0.f;                    // -gfac W
+          }
+          if (8 * g8 + 8 < cw) {
+            tmem_ld8(tS + c0 + 8, x);
+            tmem_ld8(tW + c0 + 8, dw);
+            tmem_ld8(tZ + c0 + 8, z);
           }
           if (prow < NP) {
             uint4 hi, lo;
             const uint32_t off = (uint32_t)((c0 >> 3) * NP + prow) * 16;
-            split_hilo8(x, hi, lo);
+            split_hilo8(dsh, hi, lo);
             *reinterpret_cast<uint4*>(SR + off) = hi;
             *reinterpret_cast<uint4*>(SR + plane + off) = lo;
             split_hilo8(wg, hi, lo);
             *reinterpret_cast<uint4*>(WT + off) = hi;
             *reinterpret_cast<uint4*>(WT + plane + off) = lo;
           }
-          const float c1 = warp_colsum8(dw, lane);
+          const float c1 = warp_colsum8(dk, lane);
           const float c2 = warp_colsum8(pr, lane);
           if ((lane & 17) == 0) { part_c[combo * NT + c0 + (lane >> 1)] = c1; part_d[combo * NT + c0 + (lane >> 1)] = c2; }
         }
@@ -601,9 +619,13 @@ sparc_bwd3_kernel(const __grid_constant__ CUtensorMap tmV0, const __grid_constan
     const bf16* vsrc0 = p.v + ((size_t)b * P + p_lo + tr) * D + drow;
     bf16* vdst0 = p.dv + ((size_t)b * P + p_lo + tr) * D + drow;
     // one chunk of 8 (or 4) columns: x[k] (+ per-d term already added) -> tile -> out = x - raw * fac -> global
-    auto emit8 = [&](const float* x, const uint4& raw, float fac, bool row_ok, bf16* dst) {
+    // (two halves, so that the NEXT chunk's TMEM load can be issued between them: its ~350-cycle latency then overlaps the
+    // transposed read-back, the arithmetic and the store of this chunk)
+    auto emit_sts = [&](const float* x) {
 #pragma unroll
       for (int k = 0; k < 8; ++k) stg[k * 36 + lane] = x[k];
+    };
+    auto emit_out = [&](const uint4& raw, float fac, bool row_ok, bf16* dst) {
       __syncwarp();
       const float4 a0 = *reinterpret_cast<const float4*>(stg + tr * 36 + tc8);
       const float4 a1 = *reinterpret_cast<const float4*>(stg + tr * 36 + tc8 + 4);
@@ -629,27 +651,34 @@ sparc_bwd3_kernel(const __grid_constant__ CUtensorMap tmV0, const __grid_constan
           raw[g] = (8 * g < tw && 8 * g + tr < tn) ? __ldg(reinterpret_cast<const uint4*>(lsrc + (size_t)(8 * g) * D)) : zero4;
         mbar_wait_sleep(oa_full, blk & 1);
         tc_fence_after();
+        float xh[8], xl[8];
+        if (8 <= tw) { tmem_ld8(tq + cDL + t_lo, xh); tmem_ld8(tq + cDL + NT + t_lo, xl); }
+        else { tmem_ld4(tq + cDL + t_lo, xh); tmem_ld4(tq + cDL + NT + t_lo, xl); }
 #pragma unroll
         for (int g = 0; g < 3; ++g) {
           const int c = 8 * g;
           if (c < tw) {
-            float xh[8], xl[8];
-            if (c + 8 <= tw) { tmem_ld8(tq + cDL + t_lo + c, xh); tmem_ld8(tq + cDL + NT + t_lo + c, xl); }
-            else { tmem_ld4(tq + cDL + t_lo + c, xh); tmem_ld4(tq + cDL + NT + t_lo + c, xl); }
             const float4 md0 = *reinterpret_cast<const float4*>(mdl + t_lo + c);
             const float4 md1 = (c + 8 <= tw) ? *reinterpret_cast<const float4*>(mdl + t_lo + c + 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-            tmem_ld_wait();
+            tmem_ld_wait8(xh);
+            tmem_ld_wait8(xl);
+            const float mdv[8] = {md0.x, md0.y, md0.z, md0.w, md1.x, md1.y, md1.z, md1.w};
+            const int nc = (c + 8 <= tw) ? 8 : 4;
+            float y[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) y[k] = (k < nc) ? fmaf(mdv[k], dpl, xh[k] + xl[k]) : 0.f;
+            emit_sts(y);
             if (c + 8 >= tw) {                           // last chunk: the accumulator is in registers
               tc_fence_before();
               __syncwarp();
               if (lane == 0) mbar_arrive(oa_free);
+            } else if (c + 16 <= tw) {
+              tmem_ld8(tq + cDL + t_lo + c + 8, xh); tmem_ld8(tq + cDL + NT + t_lo + c + 8, xl);
+            } else {
+              tmem_ld4(tq + cDL + t_lo + c + 8, xh); tmem_ld4(tq + cDL + NT + t_lo + c + 8, xl);
             }
-            const float mdv[8] = {md0.x, md0.y, md0.z, md0.w, md1.x, md1.y, md1.z, md1.w};
-            const int nc = (c + 8 <= tw) ? 8 : 4;
-#pragma unroll
-            for (int k = 0; k < 8; ++k) xh[k] = (k < nc) ? fmaf(mdv[k], dpl, xh[k] + xl[k]) : 0.f;
             const bool ok = c + tr < tn;
-            emit8(xh, raw[g], ok ? lfacs[t_lo + c + tr] : 0.f, ok, ldst + (size_t)c * D);
+            emit_out(raw[g], ok ? lfacs[t_lo + c + tr] : 0.f, ok, ldst + (size_t)c * D);
           }
         }
         if (blk == 0) stamp();
@@ -663,23 +692,29 @@ sparc_bwd3_kernel(const __grid_constant__ CUtensorMap tmV0, const __grid_constan
         uint4 raw1 = (8 < pw && 8 + tr < pn) ? __ldg(reinterpret_cast<const uint4*>(vsrc + (size_t)8 * D)) : zero4;
         mbar_wait_sleep(ob_full, blk & 1);
         tc_fence_after();
+        float x[8];
+        if (8 <= pw) tmem_ld8(tq + cDV + p_lo, x);
+        else tmem_ld4(tq + cDV + p_lo, x);              // pw is a multiple of 4
 #pragma unroll 1
         for (int c0 = 0; c0 < pw; c0 += 8) {
-          float x[8];
           const bool full8 = c0 + 8 <= pw;
-          if (full8) tmem_ld8(tq + cDV + p_lo + c0, x);
-          else tmem_ld4(tq + cDV + p_lo + c0, x);       // pw is a multiple of 4
           const uint4 raw2 = (c0 + 16 < pw && c0 + 16 + tr < pn) ? __ldg(reinterpret_cast<const uint4*>(vsrc + (size_t)(c0 + 16) * D)) : zero4;
-          tmem_ld_wait();
+          tmem_ld_wait8(x);
+          float y[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) y[k] = (full8 || k < 4) ? x[k] + dpv : 0.f;
+          emit_sts(y);
           if (c0 + 8 >= pw) {                           // last chunk: the accumulator is in registers
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(ob_free);
+          } else if (c0 + 16 <= pw) {
+            tmem_ld8(tq + cDV + p_lo + c0 + 8, x);
+          } else {
+            tmem_ld4(tq + cDV + p_lo + c0 + 8, x);
           }
-#pragma unroll
-          for (int k = 0; k < 8; ++k) x[k] = (full8 || k < 4) ? x[k] + dpv : 0.f;
           const bool ok = c0 + tr < pn;
-          emit8(x, raw0, ok ? vfac[p_lo + c0 + tr] : 0.f, ok, vdst + (size_t)c0 * D);
+          emit_out(raw0, ok ? vfac[p_lo + c0 + tr] : 0.f, ok, vdst + (size_t)c0 * D);
           raw0 = raw1; raw1 = raw2;
         }
         if (blk == 0) stamp();

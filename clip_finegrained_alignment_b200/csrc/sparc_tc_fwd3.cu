@@ -392,13 +392,17 @@ sparc_fwd3_kernel(const __grid_constant__ CUtensorMap tmV0, const __grid_constan
     const int combo = mb * 4 + q;
     const float invP = 1.f / (float)P;
     if (e1_act) {
+      float xn[8];
+      tmem_ld8(tq + mb * NT + c_lo, xn);
 #pragma unroll 1                                   // one hot loop body instead of 5 cold copies (instruction fetch)
       for (int g8 = 0; g8 < 5; ++g8) {
         const int c0 = c_lo + 8 * g8;
         if (8 * g8 < cw) {
           float x[8];
-          tmem_ld8(tq + mb * NT + c0, x);
-          tmem_ld_wait();
+          tmem_ld_wait8(xn);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) x[j] = xn[j];
+          if (8 * g8 + 8 < cw) tmem_ld8(tq + mb * NT + c0 + 8, xn);      // next chunk in flight during this one
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const float s = __fmul_rn(__fmul_rn(x[j], ivp), cst[c0 + j].x);
@@ -425,13 +429,17 @@ sparc_fwd3_kernel(const __grid_constant__ CUtensorMap tmV0, const __grid_constan
         cst[c_lo + j].z = 1.f / (mx - mn + kF3MinMaxEps);
       }
       __syncwarp();
+      float xn[8];
+      tmem_ld8(tq + mb * NT + c_lo, xn);
 #pragma unroll 1                                   // one hot loop body instead of 5 cold copies (instruction fetch)
       for (int g8 = 0; g8 < 5; ++g8) {
         const int c0 = c_lo + 8 * g8;
         if (8 * g8 < cw) {
           float x[8], th[8], sr[8];
-          tmem_ld8(tq + mb * NT + c0, x);
-          tmem_ld_wait();
+          tmem_ld_wait8(xn);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) x[j] = xn[j];
+          if (8 * g8 + 8 < cw) tmem_ld8(tq + mb * NT + c0 + 8, xn);      // next chunk in flight during this one
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const float4 c4 = cst[c0 + j];
@@ -502,20 +510,18 @@ sparc_fwd3_kernel(const __grid_constant__ CUtensorMap tmV0, const __grid_constan
         tc_fence_after();
         bf16* gq = gq0 + blk * 128;
         const uint32_t tg = tq + cG + buf * NT2 + g_lo;
+        // software-pipelined TMEM reads: the load of chunk c + 8 is issued as soon as chunk c sits in the staging tile, so
+        // its ~350-cycle latency overlaps the transposed read-back and the stores of chunk c
+        float xh[8], xl[8];
+        if (8 <= gw_) { tmem_ld8(tg, xh); tmem_ld8(tg + NT, xl); }
+        else { tmem_ld4(tg, xh); tmem_ld4(tg + NT, xl); }
 #pragma unroll
         for (int c = 0; c < 24; c += 8) {                  // 8 columns at a time: hi-part and lo-part of the same tokens
           if (c < gw_) {
-            float xh[8], xl[8];
-            if (c + 8 <= gw_) { tmem_ld8(tg + c, xh); tmem_ld8(tg + NT + c, xl); }
-            else { tmem_ld4(tg + c, xh); tmem_ld4(tg + NT + c, xl); }
             const float4 is0 = *reinterpret_cast<const float4*>(isg + g_lo + c);
             const float4 is1 = (c + 8 <= gw_) ? *reinterpret_cast<const float4*>(isg + g_lo + c + 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-            tmem_ld_wait();
-            if (c + 8 >= gw_) {                            // last chunk: the accumulator is in registers
-              tc_fence_before();
-              __syncwarp();
-              if (lane == 0) mbar_arrive(g_free + buf);
-            }
+            tmem_ld_wait8(xh);
+            tmem_ld_wait8(xl);
             const float isv[8] = {is0.x, is0.y, is0.z, is0.w, is1.x, is1.y, is1.z, is1.w};
             const int nc = (c + 8 <= gw_) ? 8 : 4;
             if (c <= kpool && kpool < c + nc) {            // warp-uniform: this chunk holds the spare column
@@ -531,6 +537,15 @@ sparc_fwd3_kernel(const __grid_constant__ CUtensorMap tmV0, const __grid_constan
               const bf16 h = __float2bfloat16_rn(g);
               reinterpret_cast<bf16*>(sth)[k * 32 + lane] = h;
               reinterpret_cast<bf16*>(stl)[k * 32 + lane] = __float2bfloat16_rn(g - __bfloat162float(h));
+            }
+            if (c + 8 >= gw_) {                            // last chunk: the accumulator is in registers
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(g_free + buf);
+            } else if (c + 16 <= gw_) {
+              tmem_ld8(tg + c + 8, xh); tmem_ld8(tg + NT + c + 8, xl);
+            } else {
+              tmem_ld4(tg + c + 8, xh); tmem_ld4(tg + NT + c + 8, xl);
             }
             __syncwarp();
             const uint4 vh = *reinterpret_cast<const uint4*>(sth + tr * 64 + tc16);
@@ -576,22 +591,28 @@ sparc_fwd3_kernel(const __grid_constant__ CUtensorMap tmV0, const __grid_constan
       const float ilj = jin ? cst[jrow].x : 0.f;
       float* lrow = Lb + g_lo * ldl + jrow;
       float* grow = p.tt_logits ? p.tt_logits + ((size_t)b * T + g_lo) * T + jrow : nullptr;
+      float xh[4], xl[4];
+      tmem_ld4(tq + g_lo, xh);
+      tmem_ld4(tq + NT + g_lo, xl);
 #pragma unroll 1
-      for (int c = 0; c < 20; c += 4) {
-        if (c < gw_) {
-          float xh[4], xl[4];
-          tmem_ld4(tq + g_lo + c, xh);
-          tmem_ld4(tq + NT + g_lo + c, xl);
-          const float4 cs4 = *reinterpret_cast<const float4*>(csc + g_lo + c);
-          tmem_ld_wait();
-          const float csv[4] = {cs4.x, cs4.y, cs4.z, cs4.w};
+      for (int c = 0; c < gw_; c += 4) {
+        const float4 cs4 = *reinterpret_cast<const float4*>(csc + g_lo + c);
+        tmem_ld_wait4(xh);
+        tmem_ld_wait4(xl);
+        float y[4];
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const bool on = vj && csv[k] != 0.f;
-            const float y = on ? (xh[k] + xl[k]) * csv[k] * ilj : -CUDART_INF_F;
-            if (jin) lrow[(c + k) * ldl] = y;
-            if (grow && g_lo + c + k < T && jrow < T) grow[(size_t)(c + k) * T] = y;
-          }
+        for (int k = 0; k < 4; ++k) y[k] = xh[k] + xl[k];
+        if (c + 4 < gw_) {                                 // next chunk in flight while this one is scaled and stored
+          tmem_ld4(tq + g_lo + c + 4, xh);
+          tmem_ld4(tq + NT + g_lo + c + 4, xl);
+        }
+        const float csv[4] = {cs4.x, cs4.y, cs4.z, cs4.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const bool on = vj && csv[k] != 0.f;
+          const float z = on ? y[k] * csv[k] * ilj : -CUDART_INF_F;
+          if (jin) lrow[(c + k) * ldl] = z;
+          if (grow && g_lo + c + k < T && jrow < T) grow[(size_t)(c + k) * T] = z;
         }
       }
     }

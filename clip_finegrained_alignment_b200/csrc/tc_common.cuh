@@ -132,6 +132,16 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const float* r) {
                ::"r"(taddr), "r"(u[0]), "r"(u[1]), "r"(u[2]), "r"(u[3]), "r"(u[4]), "r"(u[5]), "r"(u[6]), "r"(u[7]) : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// the same wait, tied to the registers of a load issued EARLIER than the previous statement (software-pipelined TMEM
+// reads: the load of chunk c + 1 is in flight while chunk c is processed): the in/out operands keep the compiler from
+// moving any read of r[] above the wait
+__device__ __forceinline__ void tmem_ld_wait8(float* r) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+f"(r[0]), "+f"(r[1]), "+f"(r[2]), "+f"(r[3]), "+f"(r[4]), "+f"(r[5]), "+f"(r[6]), "+f"(r[7]) :: "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait4(float* r) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;" : "+f"(r[0]), "+f"(r[1]), "+f"(r[2]), "+f"(r[3]) :: "memory");
+}
 // registers -> TMEM: thread i of the warp writes 16 consecutive fp32 columns of TMEM lane (lane_base + i)
 __device__ __forceinline__ void tmem_st16(uint32_t taddr, const float* r) {
   const uint32_t* u = reinterpret_cast<const uint32_t*>(r);
