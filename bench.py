@@ -585,7 +585,7 @@ def main():
         "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": round(ms_step, 4), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
-        "config": {"workload": f"BASELINE config {2 if (P, D) == (196, 512) else ('4' if (P, D) == (576, 768) else 'shapes')}: "
+        "config": {"workload": f"BASELINE config {(3 if (world > 1 and B == 1024) else 2) if (P, D) == (196, 512) else ('4' if (P, D) == (576, 768) else 'shapes')}: "
                                f"{'ViT-L/14@336' if P == 576 else 'ViT-B/16'} SPARC + global InfoNCE fwd+bwd, B={B}/GPU, P={P}, T={T}, "
                                f"D={D}, thr=1/P, s=1, all-True mask" + (", all-gathered global InfoNCE" if world > 1 else ""),
                    "global_batch": Bg, "collective": collective, "launch": main_run["mode"], "init_steps_before_warmup": init_steps, "l2": f"inputs rotated over {nbuf} sets ({nbuf * in_bytes >> 20} MiB > 2x L2)",

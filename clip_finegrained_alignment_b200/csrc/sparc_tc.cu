@@ -1242,7 +1242,7 @@ using namespace cfa;
 // path: 0 = auto (tensor cores when the shape/dtype allows, else CUDA cores), 1 = CUDA cores, 2 = tensor cores
 extern "C" int cfa_sparc_path(int P, int T, int D, int dtype, int path) {
   if (path == 1) return 1;
-  const bool ok = sparc_tc_supported(P, T, D, dtype) || sparc_gen3_enabled(P, T, D, dtype);     // bf16 only (fp16: see sparc_fwd2_supported)
+  const bool ok = sparc_tc_supported(P, T, D, dtype) || sparc_gen3_enabled(P, T, D, dtype);     // bf16; fp16 on the third generation only
   if (path == 2) return ok ? 2 : CFA_ERR_UNSUPPORTED;
   return ok ? 2 : 1;
 }
@@ -1301,7 +1301,7 @@ extern "C" int cfa_sparc_bwd(const void* v, const void* l, const uint8_t* mask, 
   if (which < 0) return which;
   if (which == 2) {
     if (!row_inv_norm || !tt_logits || !g_inv_norm) return CFA_ERR_WORKSPACE;
-    if (dtype == CFA_DTYPE_F16 && (!g_split || !q_save)) return CFA_ERR_WORKSPACE;      // fp16: second generation only
+    if (dtype == CFA_DTYPE_F16 && (!g_split || !q_save)) return CFA_ERR_WORKSPACE;      // fp16: third generation only (needs its buffers)
     if (g_split && q_save && sparc_gen3_enabled(P, T, D, dtype))
       return sparc_bwd3_launch(v, l, mask, B, P, T, D, thr, scale, row_inv_norm, lse_row, lse_col, coef, tt_logits,
                                g_inv_norm, g_split, q_save, dpooled_v, dpooled_l, dv, dl, g_prof_buffer, dtype,

@@ -246,11 +246,11 @@ sparc_bwd3_kernel(const __grid_constant__ CUtensorMap tmV0, const __grid_constan
     // =============================== MMA issuer (warp-uniform control flow, one elected lane issues) ===============================
     const bool leader = elect_one();
     const uint32_t id_p1 = make_idesc16(128, NT3, false, false, kHalf, kHalf);      // raw v x [l ; G hi ; G lo], all K-major
-    const uint32_t id_dw = make_idesc16(128, NT, false, false, false, false);      // S_raw^T (K-major) x dLhat (K-major: N = t)
-    const uint32_t id_z = make_idesc16(128, NT, false, true, false, false);        // W^T (K-major) x dLhat (MN-major: N = j)
-    const uint32_t id_dl = make_idesc16(128, NT2, true, true, kHalf, false);       // raw v^T (MN-major) x dShat'^T hi|lo (MN-major)
-    const uint32_t id_dv = make_idesc16(128, NP, true, false, kHalf, false);       // raw l^T (MN-major) x dShat' (K-major: N = p)
-    const uint32_t id_dg = make_idesc16(128, NP, true, false, false, false);       // G^T (MN-major, bf16) x -gfac W (K-major)
+    const uint32_t id_dw = make_idesc16(128, NT, false, false, kHalf, kHalf);      // S_raw^T (K-major) x dLhat (K-major: N = t)
+    const uint32_t id_z = make_idesc16(128, NT, false, true, kHalf, kHalf);        // W^T (K-major) x dLhat (MN-major: N = j)
+    const uint32_t id_dl = make_idesc16(128, NT2, true, true, kHalf, kHalf);       // raw v^T (MN-major) x dShat'^T hi|lo (MN-major)
+    const uint32_t id_dv = make_idesc16(128, NP, true, false, kHalf, kHalf);       // raw l^T (MN-major) x dShat' (K-major: N = p)
+    const uint32_t id_dg = make_idesc16(128, NP, true, false, kHalf, kHalf);       // G^T (MN-major, bf16) x -gfac W (K-major)
     const uint64_t sw0 = make_smem_desc(0, 16, 1024, kLayoutSw128);
     long long* pf = (p.prof && leader) ? p.prof + (size_t)b * 32 : nullptr;
     int pi = 0;
@@ -378,6 +378,27 @@ sparc_bwd3_kernel(const __grid_constant__ CUtensorMap tmV0, const __grid_constan
     int pi = 0;
     auto stamp = [&]() { if (pf) pf[pi++] = clock64(); };
     stamp();
+    // fp16 operands (kind::f16 takes no mixed fp16 x bf16 pair, so the on-chip operands are fp16 hi|lo): two per-sample powers
+    // of two keep them in fp16's normal range.  sa <= 1 / (max ||v|| max ||l||) scales S_raw (the forward's value, recomputed
+    // from the stored norms); sc ~ 1 / max |dLhat| scales the gradient chain, which is linear in it -- a 2^16 loss scale
+    // (GradScaler) or a 1e-6 coefficient both land at O(1).  The outputs are multiplied by 1 / sc (exact).
+    float sa = 1.f, isa = 1.f, sc = 1.f, isc = 1.f;
+    if (kHalf) {
+      float mv = CUDART_INF_F, ml = CUDART_INF_F, xg = 0.f, xl = 0.f;
+      for (int i = lane; i < NP; i += 32) { const float n = ivn[i]; mv = (n > 0.f) ? fminf(mv, n) : mv; }
+      for (int i = lane; i < NT; i += 32) {
+        const float n = cA[i].x;
+        ml = (n > 0.f) ? fminf(ml, n) : ml;
+        xl = fmaxf(xl, n);
+        xg = fmaxf(xg, (msk[i] != 0.f) ? ignv[i] : 0.f);
+      }
+      mv = warp_redux_min(mv); ml = warp_redux_min(ml); xg = warp_redux_max(xg); xl = warp_redux_max(xl);
+      sa = pow2_floor_clamped(mv * ml);
+      isa = 1.f / sa;
+      const float bound = fabsf(p.scale) * (fabsf(c_r) + fabsf(c_c)) * xg * xl;
+      sc = pow2_floor_clamped(1.f / fmaxf(bound, 1e-37f));
+      isc = 1.f / sc;
+    }
 
     // ---- phase 0 (overlaps P1): saved T x T logits -> dLhat (hi|lo operand [j/8][t][j%8]), gfac_t, ldot_j.
     // A warp covers rpp rows at a time: lane -> (row slot rs, 8-column chunk jc); fixed-order sums (deterministic bits).
@@ -413,11 +434,11 @@ sparc_bwd3_kernel(const __grid_constant__ CUtensorMap tmV0, const __grid_constan
           const float pr = g * yy;
           gd += pr;
           cs[k] += pr;
-          x[k] = p.scale * g * ig * cA[j].x;
+          x[k] = p.scale * g * ig * cA[j].x * sc;
         }
         if (tact) {
           uint4 hi, lo;
-          split_hilo8(x, hi, lo);
+          split_hilo8_t<kHalf>(x, hi, lo);
           const uint32_t off = (uint32_t)(jc * NT + t) * 16;
           *reinterpret_cast<uint4*>(DLh + off) = hi;
           *reinterpret_cast<uint4*>(DLl + off) = lo;
@@ -438,7 +459,7 @@ sparc_bwd3_kernel(const __grid_constant__ CUtensorMap tmV0, const __grid_constan
       if (tid < NT) {
         float s = 0.f;
         for (int w = 0; w < kB3EpiWarps; ++w) s += ldpart[w * NT + tid];
-        ldot[tid] = s;
+        ldot[tid] = s * sc;
       }
       fence_proxy_async();
       b3_epi_bar();
@@ -480,8 +501,8 @@ sparc_bwd3_kernel(const __grid_constant__ CUtensorMap tmV0, const __grid_constan
             const float raw = live ? x[j] : 0.f;
             const float nn = __fmul_rn(__fsub_rn(__fmul_rn(__fmul_rn(raw, ivp), a4.x), a4.y), a4.z);   // the forward's roundings
             w[j] = (live && !(nn < p.thr)) ? nn * d2.x : 0.f;
-            sr[j] = raw;
-            qq[j] = d2.y * (qh[j] + ql[j]);              // -gfac Q (gfac = 0 for masked tokens)
+            sr[j] = kHalf ? raw * sa : raw;
+            qq[j] = (kHalf ? d2.y * (sa * sc) : d2.y) * (qh[j] + ql[j]);     // -gfac Q (gfac = 0 for masked tokens), fp16: x sa sc like the dW sum
           }
           if (8 * g8 + 8 < cw) {
             tmem_ld8(tS + c0 + 8, x);
@@ -491,10 +512,10 @@ sparc_bwd3_kernel(const __grid_constant__ CUtensorMap tmV0, const __grid_constan
           if (prow < NP) {
             uint4 hi, lo;
             const uint32_t off = (uint32_t)((c0 >> 3) * NP + prow) * 16;
-            split_hilo8(w, hi, lo);
+            split_hilo8_t<kHalf>(w, hi, lo);
             *reinterpret_cast<uint4*>(WT + off) = hi;
             *reinterpret_cast<uint4*>(WT + plane + off) = lo;
-            split_hilo8(sr, hi, lo);
+            split_hilo8_t<kHalf>(sr, hi, lo);
             *reinterpret_cast<uint4*>(SR + off) = hi;
             *reinterpret_cast<uint4*>(SR + plane + off) = lo;
           }
@@ -537,29 +558,29 @@ sparc_bwd3_kernel(const __grid_constant__ CUtensorMap tmV0, const __grid_constan
             const float s = __fmul_rn(u, a4.x);
             const float nn = __fmul_rn(__fsub_rn(s, a4.y), a4.z);
             const bool kept = live && !(nn < p.thr);
-            const float d = kept ? dw[j] : 0.f;
+            const float d = kept ? (kHalf ? dw[j] * isa : dw[j]) : 0.f;          // fp16: sc dW from here on
             dk[j] = d;
             const float ds = d * a4.w;                    // / (sigma range)
             const float prod = ds * s;
             pr[j] = prod;
             vq += prod;
             dsh[j] = fmaf(ds * a4.x, ivp, live ? z[j] : 0.f);           // dShat' = dShat + Z
-            wg[j] = kept ? (nn * d2.x) * d2.y : 0.f;                    // -gfac W
-          }
-          if (8 * g8 + 8 < cw) {
-            tmem_ld8(tS + c0 + 8, x);
-            tmem_ld8(tW + c0 + 8, dw);
-            tmem_ld8(tZ + c0 + 8, z);
+            wg[j] = kept ? (nn * d2.x) * (kHalf ? d2.y * sc : d2.y) : 0.f;       // -gfac W
           }
           if (prow < NP) {
             uint4 hi, lo;
             const uint32_t off = (uint32_t)((c0 >> 3) * NP + prow) * 16;
-            split_hilo8(dsh, hi, lo);
+            split_hilo8_t<kHalf>(dsh, hi, lo);
             *reinterpret_cast<uint4*>(SR + off) = hi;
             *reinterpret_cast<uint4*>(SR + plane + off) = lo;
-            split_hilo8(wg, hi, lo);
+            split_hilo8_t<kHalf>(wg, hi, lo);
             *reinterpret_cast<uint4*>(WT + off) = hi;
             *reinterpret_cast<uint4*>(WT + plane + off) = lo;
+          }
+          if (8 * g8 + 8 < cw) {                          // issued after the splits (register pressure); overlaps the column sums
+            tmem_ld8(tS + c0 + 8, x);
+            tmem_ld8(tW + c0 + 8, dw);
+            tmem_ld8(tZ + c0 + 8, z);
           }
           const float c1 = warp_colsum8(dk, lane);
           const float c2 = warp_colsum8(pr, lane);
@@ -583,12 +604,21 @@ sparc_bwd3_kernel(const __grid_constant__ CUtensorMap tmV0, const __grid_constan
       for (int t = c_lo; t < c_lo + cw; ++t) {
         if (imn[t] == prow && msk[t] != 0.f && live) {  // this thread owns the arg-min element of token t
           const uint32_t off = (uint32_t)((t >> 3) * NP + prow) * 16 + (t & 7) * 2;
-          bf16* ph = reinterpret_cast<bf16*>(SR + off);
-          bf16* pl = reinterpret_cast<bf16*>(SR + plane + off);
-          const float f = (__bfloat162float(*ph) + __bfloat162float(*pl)) + dmns[t] * cA[t].x * ivp;
-          const bf16 nh = __float2bfloat16_rn(f);
-          *ph = nh;
-          *pl = __float2bfloat16_rn(f - __bfloat162float(nh));
+          if (kHalf) {
+            __half* ph = reinterpret_cast<__half*>(SR + off);
+            __half* pl = reinterpret_cast<__half*>(SR + plane + off);
+            const float f = (__half2float(*ph) + __half2float(*pl)) + dmns[t] * cA[t].x * ivp;
+            const __half nh = __float2half_rn(f);
+            *ph = nh;
+            *pl = __float2half_rn(f - __half2float(nh));
+          } else {
+            bf16* ph = reinterpret_cast<bf16*>(SR + off);
+            bf16* pl = reinterpret_cast<bf16*>(SR + plane + off);
+            const float f = (__bfloat162float(*ph) + __bfloat162float(*pl)) + dmns[t] * cA[t].x * ivp;
+            const bf16 nh = __float2bfloat16_rn(f);
+            *ph = nh;
+            *pl = __float2bfloat16_rn(f - __bfloat162float(nh));
+          }
           vq += fixv[t];
         }
       }
@@ -666,7 +696,7 @@ sparc_bwd3_kernel(const __grid_constant__ CUtensorMap tmV0, const __grid_constan
             const int nc = (c + 8 <= tw) ? 8 : 4;
             float y[8];
 #pragma unroll
-            for (int k = 0; k < 8; ++k) y[k] = (k < nc) ? fmaf(mdv[k], dpl, xh[k] + xl[k]) : 0.f;
+            for (int k = 0; k < 8; ++k) y[k] = (k < nc) ? fmaf(mdv[k], dpl, kHalf ? (xh[k] + xl[k]) * isc : xh[k] + xl[k]) : 0.f;
             emit_sts(y);
             if (c + 8 >= tw) {                           // last chunk: the accumulator is in registers
               tc_fence_before();
@@ -678,7 +708,7 @@ sparc_bwd3_kernel(const __grid_constant__ CUtensorMap tmV0, const __grid_constan
               tmem_ld4(tq + cDL + t_lo + c + 8, xh); tmem_ld4(tq + cDL + NT + t_lo + c + 8, xl);
             }
             const bool ok = c + tr < tn;
-            emit_out(raw[g], ok ? lfacs[t_lo + c + tr] : 0.f, ok, ldst + (size_t)c * D);
+            emit_out(raw[g], ok ? (kHalf ? lfacs[t_lo + c + tr] * isc : lfacs[t_lo + c + tr]) : 0.f, ok, ldst + (size_t)c * D);
           }
         }
         if (blk == 0) stamp();
@@ -702,7 +732,7 @@ sparc_bwd3_kernel(const __grid_constant__ CUtensorMap tmV0, const __grid_constan
           tmem_ld_wait8(x);
           float y[8];
 #pragma unroll
-          for (int k = 0; k < 8; ++k) y[k] = (full8 || k < 4) ? x[k] + dpv : 0.f;
+          for (int k = 0; k < 8; ++k) y[k] = (full8 || k < 4) ? (kHalf ? fmaf(x[k], isc, dpv) : x[k] + dpv) : 0.f;
           emit_sts(y);
           if (c0 + 8 >= pw) {                           // last chunk: the accumulator is in registers
             tc_fence_before();
@@ -714,7 +744,7 @@ sparc_bwd3_kernel(const __grid_constant__ CUtensorMap tmV0, const __grid_constan
             tmem_ld4(tq + cDV + p_lo + c0 + 8, x);
           }
           const bool ok = c0 + tr < pn;
-          emit_out(raw0, ok ? vfac[p_lo + c0 + tr] : 0.f, ok, vdst + (size_t)c0 * D);
+          emit_out(raw0, ok ? (kHalf ? vfac[p_lo + c0 + tr] * isc : vfac[p_lo + c0 + tr]) : 0.f, ok, vdst + (size_t)c0 * D);
           raw0 = raw1; raw1 = raw2;
         }
         if (blk == 0) stamp();
@@ -728,7 +758,7 @@ sparc_bwd3_kernel(const __grid_constant__ CUtensorMap tmV0, const __grid_constan
 }
 
 bool sparc_bwd3_supported(int P, int T, int D, int dtype) {
-  if (dtype != CFA_DTYPE_BF16) return false;
+  if (dtype != CFA_DTYPE_BF16 && dtype != CFA_DTYPE_F16) return false;
   if (P < 1 || P > 256 || T < 1 || T > 80 || D % 128 || D < 128) return false;
   const Bwd3Layout L = bwd3_layout(P, T, D);
   return L.total + 1024 <= 227 * 1024;
@@ -738,8 +768,9 @@ int sparc_bwd3_launch(const void* v, const void* l, const uint8_t* mask, int B, 
                       const float* row_inv_norm, const float* lse_row, const float* lse_col, const float* coef,
                       const float* tt_logits, const float* g_inv_norm, const void* g_split, const float* stats,
                       const float* dpv, const float* dpl, void* dv, void* dl, long long* prof, int dtype, cudaStream_t st) {
-  if (dtype != CFA_DTYPE_BF16) return CFA_ERR_UNSUPPORTED;
+  if (dtype != CFA_DTYPE_BF16 && dtype != CFA_DTYPE_F16) return CFA_ERR_UNSUPPORTED;
   if (!g_split || !stats || !tt_logits || !g_inv_norm) return CFA_ERR_WORKSPACE;
+  const bool half = dtype == CFA_DTYPE_F16;
   const Bwd3Layout L = bwd3_layout(P, T, D);
   CUtensorMap tmV0, tmV1, tmL, tmG;
   int rc;
@@ -750,13 +781,16 @@ int sparc_bwd3_launch(const void* v, const void* l, const uint8_t* mask, int B, 
   Bwd3Params prm{prof, P, T, D, thr, scale, mask, row_inv_norm, row_inv_norm + (size_t)B * P, lse_row, lse_col, coef,
                  tt_logits, g_inv_norm, stats, dpv, dpl, (const bf16*)v, (const bf16*)l, (bf16*)dv, (bf16*)dl};
   const size_t smem = L.total + 1024;
-#define CFA_B3_LAUNCH(NT_, NP_, D_)                                                                                         \
+#define CFA_B3_LAUNCH(NT_, NP_, D_, H_)                                                                                     \
   do {                                                                                                                      \
-    CFA_CUDA_TRY(cudaFuncSetAttribute(sparc_bwd3_kernel<NT_, NP_, D_, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    sparc_bwd3_kernel<NT_, NP_, D_, false><<<B, kB3Threads, smem, st>>>(tmV0, tmV1, tmL, tmG, prm);                          \
+    CFA_CUDA_TRY(cudaFuncSetAttribute(sparc_bwd3_kernel<NT_, NP_, D_, H_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    sparc_bwd3_kernel<NT_, NP_, D_, H_><<<B, kB3Threads, smem, st>>>(tmV0, tmV1, tmL, tmG, prm);                             \
   } while (0)
-  if (L.NT == 80 && L.NP == 208 && D == 512) CFA_B3_LAUNCH(80, 208, 512);      // ViT-B/16 (P = 196 / 197, T = 77)
-  else CFA_B3_LAUNCH(0, 0, 0);
+  const bool flagship = L.NT == 80 && L.NP == 208 && D == 512;                 // ViT-B/16 (P = 196 / 197, T = 77)
+  if (flagship && !half) CFA_B3_LAUNCH(80, 208, 512, false);
+  else if (flagship) CFA_B3_LAUNCH(80, 208, 512, true);
+  else if (!half) CFA_B3_LAUNCH(0, 0, 0, false);
+  else CFA_B3_LAUNCH(0, 0, 0, true);
 #undef CFA_B3_LAUNCH
   return launch_status();
 }

@@ -676,9 +676,9 @@ static int fwd2_pick_stages(int P, int T, int D) {
 
 bool sparc_fwd2_supported(int P, int T, int D, int dtype) {
   // bf16 only: tcgen05 kind::f16 rejects MIXED operand formats (an fp16 raw tile against the bf16 hi/lo operands produced
-  // on chip raises "illegal instruction" on sm_100a — measured), and fp16 hi/lo operands have too little range for the
-  // gradient tiles.  fp16 embeddings therefore run on the fp32-exact CUDA-core path.  (The kHalf template parameter is
-  // kept for the day the on-chip operands move to fp16 with range scaling; it is never instantiated.)
+  // on chip raises "illegal instruction" on sm_100a -- measured).  fp16 embeddings run on the third-generation kernels
+  // (sparc_tc_fwd3.cu / sparc_tc_bwd3.cu), whose on-chip operands are range-scaled fp16 hi|lo; this generation's kHalf
+  // template parameter is never instantiated.
   if (dtype != CFA_DTYPE_BF16) return false;
   if (!sparc_tc_supported(P, T, D, CFA_DTYPE_BF16)) return false;           // shape limits of the tensor-core layouts
   return fwd2_pick_stages(P, T, D) != 0;

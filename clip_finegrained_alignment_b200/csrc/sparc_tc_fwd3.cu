@@ -212,9 +212,9 @@ sparc_fwd3_kernel(const __grid_constant__ CUtensorMap tmV0, const __grid_constan
     const bool leader = elect_one();
     const uint32_t idesc_s = make_idesc16(128, NT, false, false, kHalf, kHalf);     // raw v (K-major) x raw l (K-major)
     const uint32_t idesc_gv = make_idesc16(128, 128, false, false, kHalf, kHalf);   // Gram tile of one M block of v
-    const uint32_t idesc_l2 = make_idesc16(128, NT2, true, true, false, false);     // S_raw^T (MN-major) x Theta^T hi|lo (MN-major)
-    const uint32_t idesc_l1 = make_idesc16(128, NT, true, true, false, false);
-    const uint32_t idesc_g = make_idesc16(128, NT2, true, true, kHalf, false);      // raw v^T (MN-major tile pair) x Theta^T hi|lo
+    const uint32_t idesc_l2 = make_idesc16(128, NT2, true, true, kHalf, kHalf);     // S_raw^T (MN-major) x Theta^T hi|lo (MN-major)
+    const uint32_t idesc_l1 = make_idesc16(128, NT, true, true, kHalf, kHalf);
+    const uint32_t idesc_g = make_idesc16(128, NT2, true, true, kHalf, kHalf);      // raw v^T (MN-major tile pair) x Theta^T hi|lo
     const uint64_t sw0 = make_smem_desc(0, 16, 1024, kLayoutSw128);
     long long* pf = (p.prof && leader) ? p.prof + (size_t)b * 32 : nullptr;
     int pi = 0;
@@ -383,6 +383,18 @@ sparc_fwd3_kernel(const __grid_constant__ CUtensorMap tmV0, const __grid_constan
         if (!pool_tc) p.pooled_v[(size_t)b * D + i] = (poolp[i] + poolp[D + i]) * invPm;
       }
     }
+    // fp16 operands: S_raw is stored as sa * S_raw with sa = 2^k <= 1 / (max ||v_p|| max ||l_t||), so |sa S_raw| <= 1 sits in
+    // fp16's normal range whatever the embedding magnitudes; the logits undo it (exact: a power of two).  Every warp derives
+    // the same sa from the same shared arrays; sparc_bwd3 recomputes it from the stored norms.
+    float sa = 1.f, isa = 1.f;
+    if (kHalf) {
+      float mv = CUDART_INF_F, ml = CUDART_INF_F;
+      for (int i = lane; i < NP; i += 32) { const float n = ivn[i]; mv = (n > 0.f) ? fminf(mv, n) : mv; }
+      for (int i = lane; i < NT; i += 32) { const float n = cst[i].x; ml = (n > 0.f) ? fminf(ml, n) : ml; }
+      mv = warp_redux_min(mv); ml = warp_redux_min(ml);
+      sa = pow2_floor_clamped(mv * ml);
+      isa = 1.f / sa;
+    }
     stamp();
 
     // ---- E1: thread = patch.  (mb, column half) from the warp group; warps of a non-existent M block idle.
@@ -447,7 +459,7 @@ sparc_fwd3_kernel(const __grid_constant__ CUtensorMap tmV0, const __grid_constan
             const float nn = __fmul_rn(__fsub_rn(s, c4.y), c4.z);
             if (live && s == c4.y) atomicMin(imn + c0 + j, prow);        // first arg-min patch, like torch.min
             th[j] = (live && !(nn < p.thr)) ? nn : 0.f;
-            sr[j] = live ? x[j] : 0.f;
+            sr[j] = live ? (kHalf ? x[j] * sa : x[j]) : 0.f;
           }
           if (pool_tc && c0 <= T && T < c0 + 8) {                        // spare column: G'[:, T] = mean_p v[p]
 #pragma unroll
@@ -456,10 +468,10 @@ sparc_fwd3_kernel(const __grid_constant__ CUtensorMap tmV0, const __grid_constan
           if (prow < NP) {
             uint4 hi, lo;
             const uint32_t off = (uint32_t)((c0 >> 3) * NP + prow) * 16;
-            split_hilo8(th, hi, lo);
+            split_hilo8_t<kHalf>(th, hi, lo);
             *reinterpret_cast<uint4*>(TH + off) = hi;
             *reinterpret_cast<uint4*>(TH + plane + off) = lo;
-            split_hilo8(sr, hi, lo);
+            split_hilo8_t<kHalf>(sr, hi, lo);
             *reinterpret_cast<uint4*>(SR + off) = hi;
             *reinterpret_cast<uint4*>(SR + plane + off) = lo;
           }
@@ -534,9 +546,15 @@ sparc_fwd3_kernel(const __grid_constant__ CUtensorMap tmV0, const __grid_constan
             for (int k = 0; k < 8; ++k) {
               const float g = (k < nc) ? (xh[k] + xl[k]) * isv[k] : 0.f;
               gn2[c + k] = fmaf(g, g, gn2[c + k]);
-              const bf16 h = __float2bfloat16_rn(g);
-              reinterpret_cast<bf16*>(sth)[k * 32 + lane] = h;
-              reinterpret_cast<bf16*>(stl)[k * 32 + lane] = __float2bfloat16_rn(g - __bfloat162float(h));
+              if (kHalf) {                                   // the saved G planes follow the embeddings' format (P1 of the backward)
+                const __half h = __float2half_rn(g);
+                reinterpret_cast<__half*>(sth)[k * 32 + lane] = h;
+                reinterpret_cast<__half*>(stl)[k * 32 + lane] = __float2half_rn(g - __half2float(h));
+              } else {
+                const bf16 h = __float2bfloat16_rn(g);
+                reinterpret_cast<bf16*>(sth)[k * 32 + lane] = h;
+                reinterpret_cast<bf16*>(stl)[k * 32 + lane] = __float2bfloat16_rn(g - __bfloat162float(h));
+              }
             }
             if (c + 8 >= gw_) {                            // last chunk: the accumulator is in registers
               tc_fence_before();
@@ -572,7 +590,7 @@ sparc_fwd3_kernel(const __grid_constant__ CUtensorMap tmV0, const __grid_constan
     if (tid < NT) {
       const float s = (part_s[tid] + part_s[NT + tid]) + (part_s[2 * NT + tid] + part_s[3 * NT + tid]);
       const float n = 1.f / fmaxf(sqrtf(s), kF3NormEps);
-      csc[tid] = (msk[tid] != 0.f) ? p.scale * isg[tid] * n : 0.f;
+      csc[tid] = (msk[tid] != 0.f) ? p.scale * isg[tid] * n * isa : 0.f;
       if (tid < T) p.g_inv_norm[(size_t)b * T + tid] = n;
     }
     f3_epi_bar();
@@ -668,7 +686,7 @@ sparc_fwd3_kernel(const __grid_constant__ CUtensorMap tmV0, const __grid_constan
 }
 
 bool sparc_fwd3_supported(int P, int T, int D, int dtype) {
-  if (dtype != CFA_DTYPE_BF16) return false;
+  if (dtype != CFA_DTYPE_BF16 && dtype != CFA_DTYPE_F16) return false;
   if (P < 1 || P > 256 || T < 1 || T > 80 || D % 128 || D < 128) return false;
   const Fwd3Layout L = fwd3_layout(P, T, D);
   return L.NS1 >= 2 && L.NS0 >= 2 && L.total + 1024 <= 227 * 1024;
@@ -678,8 +696,9 @@ int sparc_fwd3_launch(const void* v, const void* l, const uint8_t* mask, int B, 
                       float scale, float* row_inv_norm, float* pooled_v, float* pooled_l, float* lse_row, float* lse_col,
                       float* local_partial, float* tt_logits, float* g_inv_norm, void* g_split, float* stats,
                       long long* prof, int dtype, cudaStream_t st) {
-  if (dtype != CFA_DTYPE_BF16) return CFA_ERR_UNSUPPORTED;
+  if (dtype != CFA_DTYPE_BF16 && dtype != CFA_DTYPE_F16) return CFA_ERR_UNSUPPORTED;
   if (!g_split || !stats) return CFA_ERR_WORKSPACE;
+  const bool half = dtype == CFA_DTYPE_F16;             // TMA moves 16-bit elements: one tensor-map format serves both
   const Fwd3Layout L = fwd3_layout(P, T, D);
   CUtensorMap tmV0, tmV1, tmL;
   int rc;
@@ -689,13 +708,16 @@ int sparc_fwd3_launch(const void* v, const void* l, const uint8_t* mask, int B, 
   Fwd3Params prm{prof, P, T, D, thr, scale, mask, row_inv_norm, row_inv_norm + (size_t)B * P, pooled_v, pooled_l, lse_row,
                  lse_col, local_partial, tt_logits, g_inv_norm, (bf16*)g_split, stats};
   const size_t smem = L.total + 1024;
-#define CFA_F3_LAUNCH(NT_, NP_, D_)                                                                                         \
+#define CFA_F3_LAUNCH(NT_, NP_, D_, H_)                                                                                     \
   do {                                                                                                                      \
-    CFA_CUDA_TRY(cudaFuncSetAttribute(sparc_fwd3_kernel<NT_, NP_, D_, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    sparc_fwd3_kernel<NT_, NP_, D_, false><<<B, kF3Threads, smem, st>>>(tmV0, tmV1, tmL, prm);                              \
+    CFA_CUDA_TRY(cudaFuncSetAttribute(sparc_fwd3_kernel<NT_, NP_, D_, H_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    sparc_fwd3_kernel<NT_, NP_, D_, H_><<<B, kF3Threads, smem, st>>>(tmV0, tmV1, tmL, prm);                                 \
   } while (0)
-  if (L.NT == 80 && L.NP == 208 && D == 512) CFA_F3_LAUNCH(80, 208, 512);      // ViT-B/16 (P = 196 / 197, T = 77)
-  else CFA_F3_LAUNCH(0, 0, 0);
+  const bool flagship = L.NT == 80 && L.NP == 208 && D == 512;                 // ViT-B/16 (P = 196 / 197, T = 77)
+  if (flagship && !half) CFA_F3_LAUNCH(80, 208, 512, false);
+  else if (flagship) CFA_F3_LAUNCH(80, 208, 512, true);
+  else if (!half) CFA_F3_LAUNCH(0, 0, 0, false);
+  else CFA_F3_LAUNCH(0, 0, 0, true);
 #undef CFA_F3_LAUNCH
   return launch_status();
 }

@@ -172,6 +172,32 @@ __device__ __forceinline__ void split_hilo8(const float* x, uint4& hi, uint4& lo
   lo = make_uint4(l[0], l[1], l[2], l[3]);
 }
 
+// the same split into fp16 hi | lo parts (fp16 embeddings: tcgen05 kind::f16 takes no mixed fp16 x bf16 operand pair, so
+// the on-chip operands follow the raw tiles' format; the callers scale them into fp16's normal range by a power of two)
+__device__ __forceinline__ void split_hilo8_f16(const float* x, uint4& hi, uint4& lo) {
+  uint32_t h[4], l[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const __half2 hh = __floats2half2_rn(x[2 * i], x[2 * i + 1]);
+    const float2 hf = __half22float2(hh);
+    const __half2 ll = __floats2half2_rn(x[2 * i] - hf.x, x[2 * i + 1] - hf.y);
+    h[i] = *reinterpret_cast<const uint32_t*>(&hh);
+    l[i] = *reinterpret_cast<const uint32_t*>(&ll);
+  }
+  hi = make_uint4(h[0], h[1], h[2], h[3]);
+  lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
+template <bool kHalf>
+__device__ __forceinline__ void split_hilo8_t(const float* x, uint4& hi, uint4& lo) {
+  if (kHalf) split_hilo8_f16(x, hi, lo);
+  else split_hilo8(x, hi, lo);
+}
+// largest power of two <= x (x > 0, normal), clamped to [2^-60, 2^60]: exact scale factors for the fp16 operand path
+__device__ __forceinline__ float pow2_floor_clamped(float x) {
+  x = fminf(fmaxf(x, 8.673617379884035e-19f), 1.152921504606847e18f);       // NaN -> lower clamp
+  return __int_as_float(__float_as_int(x) & 0x7f800000);
+}
+
 // warp-wide min / max of one fp32 value per lane (CREDUX.MIN/MAX.F32, sm_100a): every lane gets the result
 __device__ __forceinline__ float warp_redux_min(float v) {
   float r;

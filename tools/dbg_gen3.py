@@ -1,7 +1,7 @@
 """Stage-by-stage check of the third-generation tensor-core SPARC kernels (cfa_sparc_fwd / cfa_sparc_bwd through the
 C ABI) against fp64 torch math: row norms, pooled means, saved G (hi + lo), statistics, logits, LSE; then the full
 SPARCLoss against the oracle.  A hung kernel is reported with the clock64 phase stamps it left in pinned host memory
-instead of blocking the process.   usage: python tools/dbg_gen3.py [B P T D]"""
+instead of blocking the process.   usage: python tools/dbg_gen3.py [B P T D [f16]]"""
 import os, sys, time
 os.environ.setdefault("CUDA_MODULE_LOADING", "EAGER")
 import torch
@@ -9,14 +9,15 @@ sys.path.insert(0, '.')
 from clip_finegrained_alignment_b200 import _lib
 
 B, P, T, D = (int(x) for x in sys.argv[1:5]) if len(sys.argv) >= 5 else (3, 196, 77, 512)
+DT = torch.float16 if (len(sys.argv) >= 6 and sys.argv[5] == "f16") else torch.bfloat16
 s, thr = 1.0, float(torch.tensor(1.0 / P, dtype=torch.float32))
 g = torch.Generator().manual_seed(1)
-v = torch.randn(B, P, D, generator=g).to(torch.bfloat16)
-l = torch.randn(B, T, D, generator=g).to(torch.bfloat16)
+v = torch.randn(B, P, D, generator=g).to(DT)
+l = torch.randn(B, T, D, generator=g).to(DT)
 m = torch.ones(B, T, dtype=torch.bool)
 dev = torch.device("cuda")
 vv, ll, mm = v.to(dev), l.to(dev), m.to(dev).view(torch.uint8)
-code = _lib.DTYPE_CODE[torch.bfloat16]
+code = _lib.DTYPE_CODE[DT]
 L = _lib.lib
 print("path", L.cfa_sparc_path(P, T, D, code, 0), "bwd path", L.cfa_sparc_bwd_path(P, T, D, code, 0))
 
@@ -76,7 +77,7 @@ cmp("inv_ln", rin[B * P:].view(B, T), 1 / ln)
 pooled = blk[:2 * B * D].view(2, B, D)
 cmp("pooled_v", pooled[0], vd.mean(1))
 cmp("pooled_l", pooled[1], ld.mean(1))
-gs = blk[off[8]:off[8] + B * T * D].view(torch.bfloat16).view(B, 2, T, D).float()
+gs = blk[off[8]:off[8] + B * T * D].view(DT).view(B, 2, T, D).float()
 cmp("G", gs[:, 0] + gs[:, 1], G)
 cmp("g_inv_norm", blk[off[7]:off[7] + B * T].view(B, T), 1 / gn)
 stt = blk[off[9]:off[9] + B * T * 4].view(B, T, 4)
