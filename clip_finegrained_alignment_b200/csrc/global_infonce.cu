@@ -6,6 +6,7 @@
 // separate normalise pass and the B x Bg logits never reach memory.
 //   direction 0: rows = a_loc, columns = b_all  (image -> text);   direction 1: rows = b_loc, columns = a_all.
 #include "common.cuh"
+#include <cstdlib>
 #include "simt_tile.cuh"
 #include "global_combine.cuh"
 #include "sparc_paths.h"
@@ -282,9 +283,19 @@ int global_sym_fwd(const float* a, const float* b, int B, int D, float scale, fl
 int global_sym_bwd(const float* a, const float* b, int B, int D, float scale, float eps, const float* lse2, const float* coef2,
                    float** dpart, int* nsplit, void* ws, cudaStream_t st);
 
-// path 0 (auto): rank-local problems up to B = 512 -> symmetric fp32 tiles (latency-bound regime, one logits tile serves
-// both directions); otherwise tensor cores when the shape allows; path 1 keeps everything on fp32 CUDA cores.
-static bool use_sym(int B, int Bg, int D, int path) { return path != 2 && global_sym_supported(B, Bg, D); }
+// path 0 (auto): tensor cores when the shape allows (D % 64 == 0, D <= 512) -- measured under CUDA-graph replay of the
+// SPARC step the tensor-core chain beats the symmetric fp32 tiles at every rank-local batch (B = 64: 0.133 vs 0.144 ms per
+// step, 256: 0.237 vs 0.248, 512: 0.416 vs 0.491; tools/ab_global.sh) -- else the symmetric fp32 tiles for rank-local
+// problems up to B = 512; path 1 keeps everything on fp32 CUDA cores.  CFA_GLOBAL_PREFER_SYM=1 restores the round-1 order.
+static bool prefer_sym() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("CFA_GLOBAL_PREFER_SYM"); v = (e && e[0] == '1') ? 1 : 0; }
+  return v == 1;
+}
+static bool use_sym(int B, int Bg, int D, int path) {
+  if (path == 2 || !global_sym_supported(B, Bg, D)) return false;
+  return path == 1 || prefer_sym() || !global_tc_supported(B, Bg, D);
+}
 static bool use_tc(int B, int Bg, int D, int path) { return path != 1 && !use_sym(B, Bg, D, path) && global_tc_supported(B, Bg, D); }
 
 }  // namespace cfa

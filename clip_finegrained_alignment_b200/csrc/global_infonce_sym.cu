@@ -12,6 +12,7 @@
 #include "common.cuh"
 #include "global_combine.cuh"
 #include <math_constants.h>
+#include <cstdlib>
 
 namespace cfa {
 
