@@ -155,13 +155,20 @@ int cfa_sparc_fwd(const void* v, const void* l, const uint8_t* mask, int B, int 
  * Saved between forward and backward (written by cfa_sparc_fwd, read by cfa_sparc_bwd; the CUDA-core path
  * ignores them): row_inv_norm [B*(P+T)] = 1/max(|v_p|,eps) then 1/max(|l_t|,eps); tt_logits [B*T*T] = the masked,
  * scaled token x token logits (fp32, 24 KB per sample — NOT the T x P similarity, which never leaves the SM);
- * g_inv_norm [B*T] = 1/max(|G_t|,eps); g_split [B][2][T][D] bf16 = the grouped embeddings G as bf16 hi | lo (16-byte
- * aligned, read back through TMA); q_save [B][T][NP] fp32 with NP = (P+15)&~15 = Q = G . v^T (16-byte aligned).
+ * g_inv_norm [B*T] = 1/max(|G_t|,eps); g_split [B][2][T][D] 16-bit = the grouped embeddings G as hi | lo planes in the
+ * embeddings' format (bf16, or fp16 for CFA_DTYPE_F16; 16-byte aligned, read back through TMA); q_save: a 16-byte
+ * aligned fp32 buffer of B*T*NP floats, NP = (P+15)&~15, whose CONTENT is private to the kernel generation that ran the
+ * forward (third generation, sparc_tc_fwd3.cu: the per-token statistics [B][T][4] = min, 1/range, sigma, arg-min patch
+ * in its first B*T*4 floats; second generation, sparc_tc_fwd2.cu: Q = G . v^T as [B][T][NP]) -- hand the backward the
+ * buffers the forward wrote, in the same process and with the same CFA_SPARC_GEN setting.
  * g_split / q_save are optional (both NULL or both set): with them the tensor-core backward runs as pure
- * TMA -> tcgen05 streams (sparc_tc_bwd2.cu), without them it recomputes G per D-block (sparc_tc.cu).
- * path: 0 = auto, 1 = fp32-exact CUDA-core kernels, 2 = tcgen05 tensor-core kernels (bf16, D % 256 == 0,
- * P <= 256, T <= 128; CFA_ERR_UNSUPPORTED otherwise).  cfa_sparc_path reports what `auto` resolves to.  fp16 embeddings
- * run on the CUDA-core kernels: tcgen05 rejects mixed fp16 x bf16 operand formats and the on-chip operands are bf16 hi/lo.
+ * TMA -> tcgen05 streams (sparc_tc_bwd3.cu / sparc_tc_bwd2.cu), without them the first-generation kernels recompute G per
+ * D block (sparc_tc.cu; bf16, D % 256 == 0 only -- shapes only the third generation takes return CFA_ERR_WORKSPACE).
+ * path: 0 = auto, 1 = fp32-exact CUDA-core kernels, 2 = tcgen05 tensor-core kernels or CFA_ERR_UNSUPPORTED.  Tensor-core
+ * shapes: third generation bf16 / fp16, P <= 256, T <= 80, D % 128 == 0 and a shared-memory layout under 227 KB (e.g.
+ * P = 196 / 197, T = 77 at D = 512 ... 1024); older generations bf16, D % 256 == 0, P <= 256, T <= 128.  cfa_sparc_path /
+ * cfa_sparc_bwd_path report what `auto` resolves to for a shape.  fp16 embeddings use range-scaled fp16 hi | lo on-chip operands (tcgen05 kind::f16 takes no mixed
+ * fp16 x bf16 operand pair); everything else (fp32, P > 256, ...) runs on the CUDA-core kernels.
  */
 int cfa_sparc_bwd(const void* v, const void* l, const uint8_t* mask, int B, int P, int T, int D, int dtype,
                   float thr, float scale, const float* row_inv_norm, const float* lse_row, const float* lse_col,

@@ -120,8 +120,8 @@ def _gathered_oracle(vs, ls, mask, thr, s, semantics="reference"):
     return out
 
 
-# last two cases: padded masks ("truncate" semantics) and fp16 embeddings (fine-grained part on the fp32-exact
-# CUDA-core kernels, global part on the tensor cores)
+# last two cases: padded masks ("truncate" semantics) and fp16 embeddings (range-scaled fp16 operands on the
+# tensor cores)
 @pytest.mark.parametrize("N,B,P,T,D,s,dtype,padded", [(2, 64, 50, 20, 256, 1.0, torch.bfloat16, False),
                                                       (4, 24, 196, 77, 512, 2.0, torch.bfloat16, False),
                                                       (3, 130, 33, 20, 256, 1.0, torch.bfloat16, False),

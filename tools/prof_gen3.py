@@ -17,7 +17,7 @@ for _ in range(3):
     v.grad=None; l.grad=None
     crit(v,l,m)['total_loss'].backward()
 names = {'fwd': (['start','P0 issued','w_ready seen','P1 issued'],
-                 ['start','side job done','s_full seen','sweep 1 done','sweep 2 done','sigma done','G blk 0 done','all G done','E3 logits in smem','end']),
+                 ['start','side job done','s_full seen','norms + pooled done','sweep 1 done','sweep 2 done (w_ready)','sigma / stats done','G blk 0 done','all G + csc done','E3 logits in smem','end']),
          'bwd': (['start','P1 issued','e1_ready seen','ds_ready seen','P4 issued'],
                  ['start','phase 0 done','s_full seen','E1 done','dw_full seen','E3 done','dl blk 0 done','dv blk 0 done','end'])}
 for which, setter in (('fwd', _lib.lib.cfa_debug_set_profile_buffer_fwd), ('bwd', _lib.lib.cfa_debug_set_profile_buffer)):
@@ -38,5 +38,5 @@ for which, setter in (('fwd', _lib.lib.cfa_debug_set_profile_buffer_fwd), ('bwd'
         for i, n in enumerate(names[which][0]): print(f'  {n:20s} {float((mma[:, i:i+1] - t0).median()):10.0f}')
         if which == 'bwd': print('  P4 MMA waits: full %.0f  out_free %.0f' % (float(t[sel, 8].median()), float(t[sel, 9].median())))
         print(' epilogue thread 0:')
-        for i, n in enumerate(names[which][1]): print(f'  {n:20s} {float((epi[:, i:i+1] - t0).median()):10.0f}')
+        for i, n in enumerate(names[which][1]): print(f'  {n:24s} {float((epi[:, i:i+1] - t0).median()):10.0f}')
         if which == 'fwd': print('  E3 probes since start (gn2 sums written, l_full seen, logits loop done, LSE dir 0, LSE dir 1):', [float((t[sel, 16+k:16+k+1] - t0).median()) for k in (11, 12, 13, 14, 15)])
