@@ -537,10 +537,12 @@ sparc_fwd3_kernel(const __grid_constant__ CUtensorMap tmV0, const __grid_constan
             const float isv[8] = {is0.x, is0.y, is0.z, is0.w, is1.x, is1.y, is1.z, is1.w};
             const int nc = (c + 8 <= gw_) ? 8 : 4;
             if (c <= kpool && kpool < c + nc) {            // warp-uniform: this chunk holds the spare column
-              float pv = 0.f;
+              // one predicated store per k (a select chain over xh / xl is turned into a local-memory array by the compiler,
+              // which then spills both arrays in EVERY chunk: 768 STL per CTA, measured)
+              float* dstp = p.pooled_v + (size_t)b * D + blk * 128 + dl;
+              const int kk = kpool - c;
 #pragma unroll
-              for (int k = 0; k < 8; ++k) pv = (k == kpool - c) ? xh[k] + xl[k] : pv;
-              p.pooled_v[(size_t)b * D + blk * 128 + dl] = pv;
+              for (int k = 0; k < 8; ++k) if (k == kk) *dstp = xh[k] + xl[k];
             }
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
