@@ -376,7 +376,8 @@ sparc_bwd3_kernel(const __grid_constant__ CUtensorMap tmV0, const __grid_constan
     const float c_r = p.coef[0], c_c = p.coef[1];
     long long* pf = (p.prof && tid == 0) ? p.prof + (size_t)b * 32 + 16 : nullptr;
     int pi = 0;
-    auto stamp = [&]() { if (pf) pf[pi++] = clock64(); };
+    const bool pwarp = p.prof != nullptr && ew == 0;    // warp-uniform: the other 15 warps skip a stamp with one branch
+    auto stamp = [&]() { if (pwarp) { if (pf) pf[pi] = clock64(); ++pi; } };
     stamp();
     // fp16 operands (kind::f16 takes no mixed fp16 x bf16 pair, so the on-chip operands are fp16 hi|lo): two per-sample powers
     // of two keep them in fp16's normal range.  sa <= 1 / (max ||v|| max ||l||) scales S_raw (the forward's value, recomputed
@@ -725,10 +726,18 @@ sparc_bwd3_kernel(const __grid_constant__ CUtensorMap tmV0, const __grid_constan
         float x[8];
         if (8 <= pw) tmem_ld8(tq + cDV + p_lo, x);
         else tmem_ld4(tq + cDV + p_lo, x);              // pw is a multiple of 4
+        // running pointers / limits instead of per-iteration index arithmetic (the loop overhead was ~20 integer
+        // instructions per chunk: ncu source page)
+        const bf16* rp = vsrc + (size_t)16 * D;           // raw rows two chunks ahead
+        bf16* wp = vdst;
+        const float* fp = vfac + p_lo + tr;
+        const int rem = pn - tr;                          // this lane's row c0 + tr is live iff c0 < rem
+        const int lim2 = min(pw, rem) - 16;               // ... and the row two chunks ahead iff c0 < lim2
+        uint32_t ta = tq + cDV + p_lo + 8;
 #pragma unroll 1
         for (int c0 = 0; c0 < pw; c0 += 8) {
           const bool full8 = c0 + 8 <= pw;
-          const uint4 raw2 = (c0 + 16 < pw && c0 + 16 + tr < pn) ? __ldg(reinterpret_cast<const uint4*>(vsrc + (size_t)(c0 + 16) * D)) : zero4;
+          const uint4 raw2 = (c0 < lim2) ? __ldg(reinterpret_cast<const uint4*>(rp)) : zero4;
           tmem_ld_wait8(x);
           float y[8];
 #pragma unroll
@@ -739,13 +748,14 @@ sparc_bwd3_kernel(const __grid_constant__ CUtensorMap tmV0, const __grid_constan
             __syncwarp();
             if (lane == 0) mbar_arrive(ob_free);
           } else if (c0 + 16 <= pw) {
-            tmem_ld8(tq + cDV + p_lo + c0 + 8, x);
+            tmem_ld8(ta, x);
           } else {
-            tmem_ld4(tq + cDV + p_lo + c0 + 8, x);
+            tmem_ld4(ta, x);
           }
-          const bool ok = c0 + tr < pn;
-          emit_out(raw0, ok ? (kHalf ? vfac[p_lo + c0 + tr] * isc : vfac[p_lo + c0 + tr]) : 0.f, ok, vdst + (size_t)c0 * D);
+          const bool ok = c0 < rem;
+          emit_out(raw0, ok ? (kHalf ? fp[c0] * isc : fp[c0]) : 0.f, ok, wp);
           raw0 = raw1; raw1 = raw2;
+          rp += (size_t)8 * D; wp += (size_t)8 * D; ta += 8;
         }
         if (blk == 0) stamp();
       }
