@@ -19,7 +19,10 @@ constexpr int kGtThreads = 320;          // warp 0 TMA, warp 1 MMA, warps 2-9 ep
 constexpr int kGtM = 128, kGtN = 128;
 constexpr uint32_t kGtTileA = kGtM * 128, kGtTileB = kGtN * 128;                 // one 64-wide bf16 block of a tile
 constexpr uint32_t kGtStage = 2 * kGtTileA + 2 * kGtTileB;                       // A_hi A_lo B_hi B_lo = 64 KB
-constexpr int kGtStages = 2;
+constexpr int kGtStages = 3;          // backward (one CTA per SM: it holds all 512 TMEM columns) and small forward grids
+constexpr int kGtFwdStages = 1;       // large forward grids: ONE 64 KB stage per CTA and three CTAs per SM -- the CTAs interleave: three loads in flight per SM
+                                      // and one tile's log-sum-exp epilogue under the other tiles' MMAs (2 stages, 1 CTA/SM: 123 us per launch at
+                                      // 1024 x 8192; this way: see DESIGN.md 3.4)
 
 // ---------------------------------------------------------------------------------------------------------------
 // normalise + split: out[which][row][d], which = 0: a_hi, 1: a_lo, 2: b_hi, 3: b_lo
@@ -71,6 +74,7 @@ struct GtParams {
   float* part_m; float* part_l; float* diag;
   // backward
   const float* lse_loc; const float* lse_all; const float* coef; float* dpart;
+  int dsplit;                           // backward: the D / 64 output blocks are divided over this many CTAs (grid z = 2 dsplit)
   int dpart_atomic;                     // != 0: dpart is ONE zeroed [2][B][D] accumulator, column tiles add into it (red.global)
   int lse_rank_rows, lse_rank_stride;   // > 0: lse_all is the raw all-gather of per-rank [lse_a | lse_b | 2 sums] packs
   volatile int* dbg;      // optional host-mapped progress markers (cfa_debug_set_marker_buffer), [cta][16 warps]
@@ -86,14 +90,15 @@ struct GtSmem {
 };
 
 // S tile (128 x 128) into TMEM columns [0,128): TMA producer + MMA issuer roles; epilogue warps just wait on s_full.
+template <int kStages>
 __device__ __forceinline__ void gt_issue_logits(int warp, int lane, uint8_t* stages, uint64_t* full, uint64_t* empty,
                                                 uint64_t* s_full, uint32_t tmem, const CUtensorMap* tmR, const CUtensorMap* tmC,
                                                 int row0, int col0, int ra, int ca, int KB) {
   if (warp == 0) {
     if (lane == 0) {
       for (int u = 0; u < KB; ++u) {
-        const int slot = u % kGtStages;
-        mbar_wait(empty + slot, ((u / kGtStages) & 1) ^ 1);
+        const int slot = u % kStages;
+        mbar_wait(empty + slot, ((u / kStages) & 1) ^ 1);
         uint8_t* st = stages + (size_t)slot * kGtStage;
         mbar_expect_tx(full + slot, kGtStage);
         tma_load_3d(st, tmR, full + slot, u * 64, row0, ra);                          // A_hi
@@ -107,8 +112,8 @@ __device__ __forceinline__ void gt_issue_logits(int warp, int lane, uint8_t* sta
     const uint32_t idesc = make_idesc_bf16(kGtM, kGtN, false, false);
     const uint64_t sw0 = make_smem_desc(0, 16, 1024, kLayoutSw128);
     for (int u = 0; u < KB; ++u) {
-      const int slot = u % kGtStages;
-      mbar_wait(full + slot, (u / kGtStages) & 1);
+      const int slot = u % kStages;
+      mbar_wait(full + slot, (u / kStages) & 1);
       tc_fence_after();
       const uint32_t s0 = smem_u32(stages + (size_t)slot * kGtStage);
       const uint64_t ahi = sw0 | (s0 >> 4), alo = sw0 | ((s0 + kGtTileA) >> 4);
@@ -125,18 +130,19 @@ __device__ __forceinline__ void gt_issue_logits(int warp, int lane, uint8_t* sta
   }
 }
 
-__global__ void __launch_bounds__(kGtThreads, 1)
+template <int kStages>
+__global__ void __launch_bounds__(kGtThreads, kStages == 1 ? 3 : 1)
 gt_fwd_kernel(const __grid_constant__ CUtensorMap tmLoc, const __grid_constant__ CUtensorMap tmAll, const GtParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* base = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* stages = base;
-  uint64_t* bars = (uint64_t*)(base + kGtStages * kGtStage);
-  uint64_t* full = bars; uint64_t* empty = bars + kGtStages; uint64_t* s_full = bars + 2 * kGtStages;
+  uint64_t* bars = (uint64_t*)(base + kStages * kGtStage);
+  uint64_t* full = bars; uint64_t* empty = bars + kStages; uint64_t* s_full = bars + 2 * kStages;
   uint32_t* tmem_slot = (uint32_t*)(s_full + 1);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int dir = blockIdx.z, row0 = blockIdx.x * kGtM, ct = blockIdx.y, col0 = ct * kGtN, nct = gridDim.y;
   if (threadIdx.x == 0) {
-    for (int i = 0; i < kGtStages; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, 1); }
+    for (int i = 0; i < kStages; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, 1); }
     mbar_init(s_full, 1);
     fence_barrier_init();
     tma_prefetch_desc(&tmLoc); tma_prefetch_desc(&tmAll);
@@ -146,7 +152,7 @@ gt_fwd_kernel(const __grid_constant__ CUtensorMap tmLoc, const __grid_constant__
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  gt_issue_logits(warp, lane, stages, full, empty, s_full, tmem, &tmLoc, &tmAll, row0, col0, dir ? 2 : 0, dir ? 0 : 2, p.D / 64);
+  gt_issue_logits<kStages>(warp, lane, stages, full, empty, s_full, tmem, &tmLoc, &tmAll, row0, col0, dir ? 2 : 0, dir ? 0 : 2, p.D / 64);
   if (warp >= 2) {
     const int q = warp & 3, h = (warp - 2) >> 2, row = 32 * q + lane, grow = row0 + row;
     const uint32_t trow = tmem + ((uint32_t)(32 * q) << 16);
@@ -206,22 +212,26 @@ __global__ void __launch_bounds__(kGtThreads, 1)
 gt_bwd_kernel(const __grid_constant__ CUtensorMap tmLoc, const __grid_constant__ CUtensorMap tmAll, const GtParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* base = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  uint8_t* stages = base;                              // phase A: 2 x 64 KB
+  uint8_t* stages = base;                              // phase A: 3 x 64 KB
   uint8_t* dShi = base;                                // phase B/C alias: dS hi | dS lo | 2 output stages
   uint8_t* dSlo = base + kGtDs;
   uint8_t* ostg = base + 2 * kGtDs;
   uint64_t* bars = (uint64_t*)(base + kGtStages * kGtStage);
-  uint64_t* full = bars; uint64_t* empty = bars + 2; uint64_t* s_full = bars + 4; uint64_t* ds_ready = bars + 5;
-  uint64_t* ofull = bars + 6; uint64_t* oempty = bars + 8; uint64_t* o_done = bars + 10;
-  uint32_t* tmem_slot = (uint32_t*)(bars + 11);
+  uint64_t* full = bars; uint64_t* empty = bars + 3; uint64_t* s_full = bars + 6; uint64_t* ds_ready = bars + 7;
+  uint64_t* ofull = bars + 8; uint64_t* oempty = bars + 10; uint64_t* o_done = bars + 12;
+  uint32_t* tmem_slot = (uint32_t*)(bars + 13);
+  static_assert(kGtStages == 3, "barrier layout above");
   float* lse_s = (float*)(bars + 16);                  // [kGtN] the other direction's LSE of this tile's columns
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int dir = blockIdx.z, row0 = blockIdx.x * kGtM, ct = blockIdx.y, col0 = ct * kGtN, nct = gridDim.y;
+  const int dir = blockIdx.z & 1, dz = blockIdx.z >> 1, row0 = blockIdx.x * kGtM, ct = blockIdx.y, col0 = ct * kGtN, nct = gridDim.y;
   const int D = p.D, KB = D / 64;
+  // output blocks of this CTA (small problems: the D / 64 blocks are divided over dsplit CTAs, each recomputes the logits)
+  const int u_lo = dz * KB / p.dsplit, u_hi = (dz + 1) * KB / p.dsplit;
   const long long gt_t0 = clock64();
   const int ra = dir ? 2 : 0, ca = dir ? 0 : 2;
   if (threadIdx.x == 0) {
-    for (int i = 0; i < 2; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, 1); mbar_init(ofull + i, 1); mbar_init(oempty + i, 1); }
+    for (int i = 0; i < kGtStages; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(ofull + i, 1); mbar_init(oempty + i, 1); }
     mbar_init(s_full, 1); mbar_init(ds_ready, 8); mbar_init(o_done, 1);
     fence_barrier_init();
     tma_prefetch_desc(&tmLoc); tma_prefetch_desc(&tmAll);
@@ -236,7 +246,7 @@ gt_bwd_kernel(const __grid_constant__ CUtensorMap tmLoc, const __grid_constant__
   GT_MARK(3);
 
   // ---- phase A: logits tile
-  gt_issue_logits(warp, lane, stages, full, empty, s_full, tmem, &tmLoc, &tmAll, row0, col0, ra, ca, KB);
+  gt_issue_logits<kGtStages>(warp, lane, stages, full, empty, s_full, tmem, &tmLoc, &tmAll, row0, col0, ra, ca, KB);
   GT_MARK(4);
 
   if (warp == 0) {
@@ -244,9 +254,9 @@ gt_bwd_kernel(const __grid_constant__ CUtensorMap tmLoc, const __grid_constant__
     if (lane == 0) {
       mbar_wait(ds_ready, 0);                          // dS written => phase-A stages are dead, safe to overwrite
       GT_MARK(5);
-      for (int u = 0; u < KB; ++u) {
-        const int slot = u & 1;
-        mbar_wait(oempty + slot, ((u >> 1) & 1) ^ 1);
+      for (int u = u_lo, i = 0; u < u_hi; ++u, ++i) {
+        const int slot = i & 1;
+        mbar_wait(oempty + slot, ((i >> 1) & 1) ^ 1);
         uint8_t* st = ostg + (size_t)slot * kGtOutStage;
         mbar_expect_tx(ofull + slot, kGtOutStage);
         tma_load_3d(st, &tmAll, ofull + slot, u * 64, col0, ca);
@@ -264,9 +274,9 @@ gt_bwd_kernel(const __grid_constant__ CUtensorMap tmLoc, const __grid_constant__
     const uint64_t a_hi = make_smem_desc(smem_u32(dShi), il_lbo, 128, kLayoutNone);
     const uint64_t a_lo = make_smem_desc(smem_u32(dSlo), il_lbo, 128, kLayoutNone);
     const uint32_t a_ks = (2 * il_lbo) >> 4;
-    for (int u = 0; u < KB; ++u) {
-      const int slot = u & 1;
-      mbar_wait(ofull + slot, (u >> 1) & 1);
+    for (int u = u_lo, i = 0; u < u_hi; ++u, ++i) {
+      const int slot = i & 1;
+      mbar_wait(ofull + slot, (i >> 1) & 1);
       tc_fence_after();
       const uint32_t s0 = smem_u32(ostg + (size_t)slot * kGtOutStage);
       const uint64_t bhi = sw0 | (s0 >> 4), blo = sw0 | ((s0 + kGtTileB) >> 4);
@@ -335,12 +345,11 @@ gt_bwd_kernel(const __grid_constant__ CUtensorMap tmLoc, const __grid_constant__
     mbar_wait(o_done, 0);
     tc_fence_after();
     GT_MARK(14);
-    const int dcols = D;
     // TMEM -> registers -> per-warp smem transpose tile -> global: every store instruction writes one 128-byte row
     // segment (lane = column) instead of 32 scattered ones (lane = row).  tcgen05.ld is warp-collective: all lanes load.
     float* tile = reinterpret_cast<float*>(ostg) + (warp - 2) * (32 * 36);       // phase-C operand stages are dead now
     const int rr = lane >> 3, c4 = (lane & 7) * 4;
-    for (int c0 = 32 * h; c0 < dcols; c0 += 64) {
+    for (int c0 = 64 * u_lo + 32 * h; c0 < 64 * u_hi; c0 += 64) {
       float x[32];
       tmem_ld32(trow + c0, x);
       tmem_ld_wait();
@@ -428,10 +437,20 @@ int global_tc_fwd(const float* a_loc, const float* b_loc, const float* a_all, co
   GtParams p{};
   p.B = B; p.Bg = Bg; p.D = D; p.col_offset = col_offset; p.scale = scale;
   p.part_m = h.scratch; p.part_l = p.part_m + (size_t)4 * h.nct * B; p.diag = p.part_l + (size_t)4 * h.nct * B;
-  const size_t smem = kGtStages * kGtStage + 1024 + 1024;
+  // small grids (under two CTAs per SM): one CTA per SM with a 3-deep ring; large grids: single-stage CTAs, three per SM
+  const dim3 grid((B + kGtM - 1) / kGtM, h.nct, 2);
+  const bool big = (size_t)grid.x * grid.y * grid.z >= 2 * 148;
+  const size_t smem = (big ? kGtFwdStages : kGtStages) * kGtStage + 1024 + 1024;
   static bool attr = false;
-  if (!attr) { CFA_CUDA_TRY(cudaFuncSetAttribute(gt_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
-  gt_fwd_kernel<<<dim3((B + kGtM - 1) / kGtM, h.nct, 2), kGtThreads, smem, st>>>(tmLoc, tmAll, p);
+  if (!attr) {
+    CFA_CUDA_TRY(cudaFuncSetAttribute(gt_fwd_kernel<kGtFwdStages>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)(kGtFwdStages * kGtStage + 2048)));
+    CFA_CUDA_TRY(cudaFuncSetAttribute(gt_fwd_kernel<kGtStages>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)(kGtStages * kGtStage + 2048)));
+    attr = true;
+  }
+  if (big) gt_fwd_kernel<kGtFwdStages><<<grid, kGtThreads, smem, st>>>(tmLoc, tmAll, p);
+  else gt_fwd_kernel<kGtStages><<<grid, kGtThreads, smem, st>>>(tmLoc, tmAll, p);
   *part_m = p.part_m; *part_l = p.part_l; *diag = p.diag; *nsplit = 2 * h.nct;
   return launch_status();
 }
@@ -452,7 +471,13 @@ int global_tc_bwd(int B, int Bg, int D, int col_offset, float scale, const float
   const size_t smem = kGtStages * kGtStage + 1024 + 1024;
   static bool attr = false;
   if (!attr) { CFA_CUDA_TRY(cudaFuncSetAttribute(gt_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
-  gt_bwd_kernel<<<dim3((B + kGtM - 1) / kGtM, h.nct, 2), kGtThreads, smem, st>>>(tmLoc, tmAll, p);
+  // few tiles (rank-local batches): divide the D / 64 output blocks over up to 8 CTAs per tile so that the grid covers
+  // the GPU -- each CTA recomputes the logits tile (cheap) and contracts / writes only its blocks
+  const int tiles = ((B + kGtM - 1) / kGtM) * h.nct * 2, KB = D / 64;
+  int ds = 1;
+  while (ds < 8 && KB % (2 * ds) == 0 && tiles * 2 * ds <= 148) ds *= 2;
+  p.dsplit = ds;
+  gt_bwd_kernel<<<dim3((B + kGtM - 1) / kGtM, h.nct, 2 * ds), kGtThreads, smem, st>>>(tmLoc, tmAll, p);
   *dpart = h.scratch; *nsplit = p.dpart_atomic ? 1 : h.nct;
   return launch_status();
 }
