@@ -28,6 +28,20 @@ struct PeerTable {
     if (_e != cudaSuccess) return (int)_e;         \
   } while (0)
 
+// Opt-in to > 48 KB of dynamic shared memory ONCE PER DEVICE (the attribute is per device: a per-process `static bool`
+// guard would leave the second GPU of a multi-device process without it).  `mask` is the call site's static bit set.
+#define CFA_SMEM_ATTR_ONCE(func, bytes)                                                                      \
+  do {                                                                                                       \
+    static unsigned long long cfa_attr_mask_ = 0ull;                                                         \
+    int cfa_dev_ = 0;                                                                                        \
+    CFA_CUDA_TRY(cudaGetDevice(&cfa_dev_));                                                                  \
+    if (cfa_dev_ >= 64 || !((cfa_attr_mask_ >> cfa_dev_) & 1ull)) {                                          \
+      CFA_CUDA_TRY(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes)));   \
+      if (cfa_dev_ < 64) cfa_attr_mask_ |= 1ull << cfa_dev_;                                                 \
+    }                                                                                                        \
+  } while (0)
+
+
 // launch check without synchronising
 static inline int launch_status() { return (int)cudaGetLastError(); }
 

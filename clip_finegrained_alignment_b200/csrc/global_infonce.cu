@@ -364,11 +364,7 @@ int cfa::global_infonce_fwd_peers(const float* a_loc, const float* b_loc, const 
   cudaStream_t st = (cudaStream_t)stream;
   dim3 grid((B + kGR - 1) / kGR, ns, 2);
   const size_t fsmem = sizeof(float) * ((kGR + kGC) * kGLd + kGR + kGC);
-  static bool fattr = false;
-  if (!fattr) {
-    CFA_CUDA_TRY(cudaFuncSetAttribute(global_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
-    fattr = true;
-  }
+  CFA_SMEM_ATTR_ONCE(global_fwd_kernel, fsmem);
   global_fwd_kernel<<<grid, kNT, fsmem, st>>>(a_loc, b_loc, a_all, b_all, B, Bg, D, col_offset, scale, eps, part_m, part_l,
                                           diag, norms2);
   CFA_CUDA_TRY(cudaGetLastError());
@@ -403,11 +399,7 @@ extern "C" int cfa_global_infonce_bwd(const float* a_loc, const float* b_loc, co
   }
   const int ns = gb_splits(B, Bg, D);
   const size_t smem = sizeof(float) * (2 * kBR * kBLd + kBR * kBLdS + kBC * kBLdB + kBC);
-  static bool attr_set = false;
-  if (!attr_set) {
-    CFA_CUDA_TRY(cudaFuncSetAttribute(global_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
-  }
+  CFA_SMEM_ATTR_ONCE(global_bwd_kernel, smem);
   cudaStream_t st = (cudaStream_t)stream;
   const int rb = (B + kBR - 1) / kBR;
   dim3 grid(2 * rb, ns, (D + kBDz - 1) / kBDz);

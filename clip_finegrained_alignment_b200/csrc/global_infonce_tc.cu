@@ -441,14 +441,8 @@ int global_tc_fwd(const float* a_loc, const float* b_loc, const float* a_all, co
   const dim3 grid((B + kGtM - 1) / kGtM, h.nct, 2);
   const bool big = (size_t)grid.x * grid.y * grid.z >= 2 * 148;
   const size_t smem = (big ? kGtFwdStages : kGtStages) * kGtStage + 1024 + 1024;
-  static bool attr = false;
-  if (!attr) {
-    CFA_CUDA_TRY(cudaFuncSetAttribute(gt_fwd_kernel<kGtFwdStages>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)(kGtFwdStages * kGtStage + 2048)));
-    CFA_CUDA_TRY(cudaFuncSetAttribute(gt_fwd_kernel<kGtStages>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)(kGtStages * kGtStage + 2048)));
-    attr = true;
-  }
+  CFA_SMEM_ATTR_ONCE(gt_fwd_kernel<kGtFwdStages>, kGtFwdStages * kGtStage + 2048);
+  CFA_SMEM_ATTR_ONCE(gt_fwd_kernel<kGtStages>, kGtStages * kGtStage + 2048);
   if (big) gt_fwd_kernel<kGtFwdStages><<<grid, kGtThreads, smem, st>>>(tmLoc, tmAll, p);
   else gt_fwd_kernel<kGtStages><<<grid, kGtThreads, smem, st>>>(tmLoc, tmAll, p);
   *part_m = p.part_m; *part_l = p.part_l; *diag = p.diag; *nsplit = 2 * h.nct;
@@ -469,8 +463,7 @@ int global_tc_bwd(int B, int Bg, int D, int col_offset, float scale, const float
   if (p.dpart_atomic) CFA_CUDA_TRY(cudaMemsetAsync(h.scratch, 0, (size_t)2 * B * D * sizeof(float), st));
   p.lse_rank_rows = gathered_ranks > 1 ? B : 0; p.lse_rank_stride = gathered_ranks > 1 ? 2 * B + 2 : 0;
   const size_t smem = kGtStages * kGtStage + 1024 + 1024;
-  static bool attr = false;
-  if (!attr) { CFA_CUDA_TRY(cudaFuncSetAttribute(gt_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
+  CFA_SMEM_ATTR_ONCE(gt_bwd_kernel, smem);
   // few tiles (rank-local batches): divide the D / 64 output blocks over up to 8 CTAs per tile so that the grid covers
   // the GPU -- each CTA recomputes the logits tile (cheap) and contracts / writes only its blocks
   const int tiles = ((B + kGtM - 1) / kGtM) * h.nct * 2, KB = D / 64;

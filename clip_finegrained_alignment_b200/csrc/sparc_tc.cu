@@ -482,8 +482,7 @@ bool sparc_tc_supported(int P, int T, int D, int dtype) {
 int sparc_prep_launch(const void* v, const void* l, const uint8_t* mask, int B, int P, int T, int D, float* inv_vn,
                       float* inv_ln, float* pooled_v, float* pooled_l, cudaStream_t st) {
   const size_t smem = (size_t)8 * D * sizeof(float);
-  static bool attr = false;
-  if (!attr) { CFA_CUDA_TRY(cudaFuncSetAttribute(sparc_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 1024 * 4)); attr = true; }
+  CFA_SMEM_ATTR_ONCE(sparc_prep_kernel, 8 * 1024 * 4);
   sparc_prep_kernel<<<B, 256, smem, st>>>((const bf16*)v, (const bf16*)l, mask, P, T, D, inv_vn, inv_ln, pooled_v, pooled_l);
   return launch_status();
 }
