@@ -603,75 +603,142 @@ sparc_fwd3_kernel(const __grid_constant__ CUtensorMap tmV0, const __grid_constan
     mbar_wait_sleep(l_full, 0);
     tc_fence_after();
     if (pf) pf[12] = clock64();
-    float* Lb = reinterpret_cast<float*>(SR);           // [NT][NT + 1], the S_raw^T region is free once L' is done
-    const int ldl = NT + 1;
-    const int jrow = 32 * q + lane;
-    if (32 * q < NT) {                                  // warp-uniform: tcgen05.ld needs the whole warp
-      const bool jin = jrow < NT;
-      const bool vj = jin && msk[jin ? jrow : 0] != 0.f;
-      const float ilj = jin ? cst[jrow].x : 0.f;
-      float* lrow = Lb + g_lo * ldl + jrow;
-      float* grow = p.tt_logits ? p.tt_logits + ((size_t)b * T + g_lo) * T + jrow : nullptr;
-      float xh[4], xl[4];
-      tmem_ld4(tq + g_lo, xh);
-      tmem_ld4(tq + NT + g_lo, xl);
+    // |logit| <= |scale| (cosines): for moderate scales a FIXED shift replaces the max pass of the log-sum-exp (exp never
+    // overflows and cannot flush a whole sum to zero), and then exp(logit - shift) is the same number for the row and the
+    // column direction: both sums are formed straight from the accumulator registers -- the column direction (over t) is a
+    // per-thread sum, the row direction (over j) a transposed warp reduction -- and the logits never touch shared memory.
+    const bool fixed = fabsf(p.scale) <= 30.f;
+    if (fixed) {
+      float* prow_s = reinterpret_cast<float*>(SR);     // [3][NT] row-direction partials per lane quarter (the S_raw^T region is free)
+      float* pcol_s = prow_s + 3 * NT;                  // [4][NT] column-direction partials per column group
+      float* diag_s = pcol_s + 4 * NT;                  // [NT] logits[t][t]
+      const float mshift = fabsf(p.scale) * 1.0001f;
+      const int jrow = 32 * q + lane;
+      if (32 * q < NT) {                                // warp-uniform: tcgen05.ld needs the whole warp
+        const bool jin = jrow < NT;
+        const bool vj = jin && msk[jin ? jrow : 0] != 0.f;
+        const float ilj = jin ? cst[jrow].x : 0.f;
+        float* grow = p.tt_logits ? p.tt_logits + ((size_t)b * T + g_lo) * T + jrow : nullptr;
+        float csum = 0.f;
+        float xh[4], xl[4];
+        tmem_ld4(tq + g_lo, xh);
+        tmem_ld4(tq + NT + g_lo, xl);
 #pragma unroll 1
-      for (int c = 0; c < gw_; c += 4) {
-        const float4 cs4 = *reinterpret_cast<const float4*>(csc + g_lo + c);
-        tmem_ld_wait4(xh);
-        tmem_ld_wait4(xl);
-        float y[4];
+        for (int c = 0; c < gw_; c += 4) {
+          const float4 cs4 = *reinterpret_cast<const float4*>(csc + g_lo + c);
+          tmem_ld_wait4(xh);
+          tmem_ld_wait4(xl);
+          float y[4];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) y[k] = xh[k] + xl[k];
-        if (c + 4 < gw_) {                                 // next chunk in flight while this one is scaled and stored
-          tmem_ld4(tq + g_lo + c + 4, xh);
-          tmem_ld4(tq + NT + g_lo + c + 4, xl);
+          for (int k = 0; k < 4; ++k) y[k] = xh[k] + xl[k];
+          if (c + 4 < gw_) {                               // next chunk in flight while this one is processed
+            tmem_ld4(tq + g_lo + c + 4, xh);
+            tmem_ld4(tq + NT + g_lo + c + 4, xl);
+          }
+          const float csv[4] = {cs4.x, cs4.y, cs4.z, cs4.w};
+          float e[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const bool on = vj && csv[k] != 0.f;
+            const float z = on ? y[k] * csv[k] * ilj : -CUDART_INF_F;
+            e[k] = on ? __expf(z - mshift) : 0.f;
+            csum += e[k];
+            if (g_lo + c + k == jrow) diag_s[jrow] = z;
+            if (grow && g_lo + c + k < T && jrow < T) grow[(size_t)(c + k) * T] = z;
+          }
+          const float rs = warp_colsum4(e, lane);          // lanes 0, 4, 8, 12: sum over this warp's 32 j of columns c .. c + 3
+          if ((lane & 19) == 0) prow_s[q * NT + g_lo + c + (lane >> 2)] = rs;
         }
-        const float csv[4] = {cs4.x, cs4.y, cs4.z, cs4.w};
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const bool on = vj && csv[k] != 0.f;
-          const float z = on ? y[k] * csv[k] * ilj : -CUDART_INF_F;
-          if (jin) lrow[(c + k) * ldl] = z;
-          if (grow && g_lo + c + k < T && jrow < T) grow[(size_t)(c + k) * T] = z;
+        if (jin) pcol_s[grp * NT + jrow] = csum;
+      }
+      if (pf) pf[13] = clock64();
+      f3_epi_bar();
+      stamp();
+      float ce_r = 0.f, ce_c = 0.f;
+      if (tid < T) {
+        const bool valid = msk[tid] != 0.f;
+        float sr = prow_s[tid];
+        for (int w = 1; 32 * w < NT; ++w) sr += prow_s[w * NT + tid];
+        const float sc_ = (pcol_s[tid] + pcol_s[NT + tid]) + (pcol_s[2 * NT + tid] + pcol_s[3 * NT + tid]);
+        const float lr = valid ? mshift + logf(sr) : 0.f, lc = valid ? mshift + logf(sc_) : 0.f;
+        p.lse_row[(size_t)b * T + tid] = lr;
+        p.lse_col[(size_t)b * T + tid] = lc;
+        if (valid) { ce_r = lr - diag_s[tid]; ce_c = lc - diag_s[tid]; }
+      }
+      ce_r = warp_sum(ce_r); ce_c = warp_sum(ce_c);
+      if (lane == 0) { red[ew] = ce_r; red[kF3EpiWarps + ew] = ce_c; }
+      if (pf) { pf[14] = clock64(); pf[15] = pf[14]; }
+    } else {
+      float* Lb = reinterpret_cast<float*>(SR);           // [NT][NT + 1], the S_raw^T region is free once L' is done
+      const int ldl = NT + 1;
+      const int jrow = 32 * q + lane;
+      if (32 * q < NT) {                                  // warp-uniform: tcgen05.ld needs the whole warp
+        const bool jin = jrow < NT;
+        const bool vj = jin && msk[jin ? jrow : 0] != 0.f;
+        const float ilj = jin ? cst[jrow].x : 0.f;
+        float* lrow = Lb + g_lo * ldl + jrow;
+        float* grow = p.tt_logits ? p.tt_logits + ((size_t)b * T + g_lo) * T + jrow : nullptr;
+        float xh[4], xl[4];
+        tmem_ld4(tq + g_lo, xh);
+        tmem_ld4(tq + NT + g_lo, xl);
+  #pragma unroll 1
+        for (int c = 0; c < gw_; c += 4) {
+          const float4 cs4 = *reinterpret_cast<const float4*>(csc + g_lo + c);
+          tmem_ld_wait4(xh);
+          tmem_ld_wait4(xl);
+          float y[4];
+  #pragma unroll
+          for (int k = 0; k < 4; ++k) y[k] = xh[k] + xl[k];
+          if (c + 4 < gw_) {                                 // next chunk in flight while this one is scaled and stored
+            tmem_ld4(tq + g_lo + c + 4, xh);
+            tmem_ld4(tq + NT + g_lo + c + 4, xl);
+          }
+          const float csv[4] = {cs4.x, cs4.y, cs4.z, cs4.w};
+  #pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const bool on = vj && csv[k] != 0.f;
+            const float z = on ? y[k] * csv[k] * ilj : -CUDART_INF_F;
+            if (jin) lrow[(c + k) * ldl] = z;
+            if (grow && g_lo + c + k < T && jrow < T) grow[(size_t)(c + k) * T] = z;
+          }
         }
       }
-    }
-    if (pf) pf[13] = clock64();
-    f3_epi_bar();
-    stamp();
-    // LSE: 4 threads per row / column, a quarter of the entries each.  |logit| <= |scale| (cosines), so for moderate
-    // scales a fixed shift replaces the max pass (exp never overflows and cannot flush the whole sum to zero).
-    {
-      const int r = tid >> 2, seg = tid & 3;
-      const int sw = (NT + 3) / 4, s_lo = seg * sw, s_hi = min(T, s_lo + sw);
-      const bool fixed = fabsf(p.scale) <= 30.f;
-      const bool rin = r < T;
-      const bool valid = rin && msk[rin ? r : 0] != 0.f;
-#pragma unroll
-      for (int dir = 0; dir < 2; ++dir) {                // 0: row direction (softmax over j), 1: column direction (over t)
-        const int st_r = dir ? 1 : ldl, st_c = dir ? ldl : 1;
-        const float* src = Lb + (rin ? r : 0) * st_r;
-        float m = fabsf(p.scale) * 1.0001f;
-        if (!fixed) {
-          m = -CUDART_INF_F;
-          for (int j = s_lo; j < s_hi; ++j) m = fmaxf(m, src[j * st_c]);
-          m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
-          m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
+      if (pf) pf[13] = clock64();
+      f3_epi_bar();
+      stamp();
+      // LSE: 4 threads per row / column, a quarter of the entries each.  |logit| <= |scale| (cosines), so for moderate
+      // scales a fixed shift replaces the max pass (exp never overflows and cannot flush the whole sum to zero).
+      {
+        const int r = tid >> 2, seg = tid & 3;
+        const int sw = (NT + 3) / 4, s_lo = seg * sw, s_hi = min(T, s_lo + sw);
+        const bool fixed = fabsf(p.scale) <= 30.f;
+        const bool rin = r < T;
+        const bool valid = rin && msk[rin ? r : 0] != 0.f;
+  #pragma unroll
+        for (int dir = 0; dir < 2; ++dir) {                // 0: row direction (softmax over j), 1: column direction (over t)
+          const int st_r = dir ? 1 : ldl, st_c = dir ? ldl : 1;
+          const float* src = Lb + (rin ? r : 0) * st_r;
+          float m = fabsf(p.scale) * 1.0001f;
+          if (!fixed) {
+            m = -CUDART_INF_F;
+            for (int j = s_lo; j < s_hi; ++j) m = fmaxf(m, src[j * st_c]);
+            m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
+            m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
+          }
+          float s = 0.f;                                   // (four independent partial sums were measured SLOWER: 12.7 k vs 7.1 k cycles)
+          for (int j = s_lo; j < s_hi; ++j) s += __expf(src[j * st_c] - m);          // exp(-inf - m) = 0: masked entries drop out
+          s += __shfl_xor_sync(0xffffffffu, s, 1);
+          s += __shfl_xor_sync(0xffffffffu, s, 2);
+          const float lse = valid ? m + logf(s) : 0.f;
+          float ce = 0.f;
+          if (rin && seg == 0) {
+            (dir ? p.lse_col : p.lse_row)[(size_t)b * T + r] = lse;
+            if (valid) ce = lse - Lb[r * ldl + r];
+          }
+          const float tot = warp_sum(ce);
+          if (lane == 0) red[dir * kF3EpiWarps + ew] = tot;
+          if (pf) pf[14 + dir] = clock64();
         }
-        float s = 0.f;                                   // (four independent partial sums were measured SLOWER: 12.7 k vs 7.1 k cycles)
-        for (int j = s_lo; j < s_hi; ++j) s += __expf(src[j * st_c] - m);          // exp(-inf - m) = 0: masked entries drop out
-        s += __shfl_xor_sync(0xffffffffu, s, 1);
-        s += __shfl_xor_sync(0xffffffffu, s, 2);
-        const float lse = valid ? m + logf(s) : 0.f;
-        float ce = 0.f;
-        if (rin && seg == 0) {
-          (dir ? p.lse_col : p.lse_row)[(size_t)b * T + r] = lse;
-          if (valid) ce = lse - Lb[r * ldl + r];
-        }
-        const float tot = warp_sum(ce);
-        if (lane == 0) red[dir * kF3EpiWarps + ew] = tot;
-        if (pf) pf[14 + dir] = clock64();
       }
     }
     f3_epi_bar();

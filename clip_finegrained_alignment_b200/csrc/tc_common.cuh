@@ -235,6 +235,27 @@ __device__ __forceinline__ float warp_colsum8(float* v, int lane) {
   return v[0];
 }
 
+// Same for 4 per-lane values (9 shuffles): lane l ends up with the sum of column ((l >> 3) & 1) * 2 + ((l >> 2) & 1) in v[0]
+// (lanes 0, 4, 8, 12 hold columns 0, 1, 2, 3).
+__device__ __forceinline__ float warp_colsum4(float* v, int lane) {
+#pragma unroll
+  for (int k = 0; k < 4; ++k) v[k] += __shfl_xor_sync(0xffffffffu, v[k], 16);
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const bool up = lane & 8;
+    const float send = up ? v[k] : v[k + 2], keep = up ? v[k + 2] : v[k];
+    v[k] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+  }
+  {
+    const bool up = lane & 4;
+    const float send = up ? v[0] : v[1], keep = up ? v[1] : v[0];
+    v[0] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+  }
+  v[0] += __shfl_xor_sync(0xffffffffu, v[0], 2);
+  v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
+  return v[0];
+}
+
 // ---------------------------------------------------------------- UMMA descriptors
 constexpr uint32_t kLayoutNone = 0, kLayoutSw128 = 2, kLayoutSw64 = 4;
 
