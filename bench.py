@@ -33,10 +33,10 @@ L2_BYTES = 126 * 2 ** 20
 METRIC = "sparc_infonce_fwd_bwd_pairs_per_s"
 UNIT = "pairs/s"
 # DRAM traffic of the dominant kernel per launch at config 2 (one `ncu --set full` capture, summary under profiles/)
-TRAFFIC_BWD = 183.6e6
-TRAFFIC_SRC = ("profiles/r1i_ncu_full_summary.csv (sparc_bwd2_kernel): dram read 140.1 MB + write 43.5 MB per launch; to be "
-               "replaced by the third-generation capture")
-SHARE_SRC = "profiles/r1i_launches.csv"
+TRAFFIC_BWD = 174.06e6
+TRAFFIC_SRC = ("profiles/r2n_ncu_full_summary.csv (sparc_bwd3_kernel, B = 256, `ncu --set full` of tools/run_once.py 256): dram "
+               "read 126.8 MB + write 47.2 MB per launch (algorithmic: inputs 71.6 + saved G 40.4 + logits 6.1 read, 71.6 written)")
+SHARE_SRC = "profiles/r2n_launches.csv (sparc_bwd3 46 %, sparc_fwd3 30 %, global InfoNCE chain 23 % of the step's device time)"
 
 
 def peaks():
