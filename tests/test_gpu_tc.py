@@ -96,6 +96,54 @@ def test_sparc_tc_vs_oracle(B, P, T, D, s):
     assert rel_err(dl.float(), rl) <= 1e-3 + 2.0 ** -8
 
 
+@pytest.mark.parametrize("B,P,T,D,s,dtype", [
+    (2, 196, 77, 512, 50.0, torch.bfloat16),     # |scale| > 30: max-subtracted log-sum-exp branch of sparc_fwd3 (CLIP logit scales reach 100)
+    (2, 196, 77, 512, 100.0, torch.float16),
+    (3, 1, 1, 128, 1.0, torch.bfloat16),         # one patch, one token
+    (2, 17, 3, 128, 2.0, torch.bfloat16),        # tiny ragged tile
+    (2, 255, 80, 256, 1.0, torch.bfloat16),      # T = NT = 80: no spare column (pooled image mean from the CUDA-core side job)
+    (2, 130, 33, 640, 1.0, torch.float16),       # D = 5 x 128, second patch block almost empty
+])
+def test_sparc_gen3_edge_shapes_vs_oracle(B, P, T, D, s, dtype):
+    from clip_finegrained_alignment_b200 import _lib
+    code = _lib.DTYPE_CODE[dtype]
+    assert _lib.lib.cfa_sparc_path(P, T, D, code, 0) == 2
+    g = torch.Generator().manual_seed(P * 13 + T)
+    v = torch.randn(B, P, D, generator=g).to(dtype)
+    l = torch.randn(B, T, D, generator=g).to(dtype)
+    m = torch.ones(B, T, dtype=torch.bool)
+    thr = float(torch.tensor(1.0 / P, dtype=torch.float32))
+    out, dv, dl = _sparc_tc(v, l, m, _cfg(thr, 0.9, 1.1, s))
+    o = lo.sparc_forward(v.double(), l.double(), m, thr, 0.9, 1.1, s)
+    rv, rl = lo.sparc_backward(o)
+    for k in lo.SPARC_KEYS:
+        assert abs(float(out[k]) - float(o[k])) <= 1e-4 * max(1.0, abs(float(o[k]))), (k, float(out[k]), float(o[k]))
+    assert torch.isfinite(dv).all() and torch.isfinite(dl).all()
+    if float(rv.norm()) > 0:
+        assert rel_err(dv.float(), rv) <= 1e-3 + 2.0 ** -8, rel_err(dv.float(), rv)
+    if float(rl.norm()) > 0:
+        assert rel_err(dl.float(), rl) <= 1e-3 + 2.0 ** -8, rel_err(dl.float(), rl)
+
+
+def test_sparc_gen3_fully_masked_sample():
+    """One sample without a single valid token ("truncate" semantics: it contributes nothing to the local loss; the
+    clamped token count keeps its pooled text mean at zero): finite losses and gradients, equal to the oracle."""
+    B, P, T, D = 3, 196, 77, 512
+    g = torch.Generator().manual_seed(77)
+    v = torch.randn(B, P, D, generator=g).to(torch.bfloat16)
+    l = torch.randn(B, T, D, generator=g).to(torch.bfloat16)
+    m = torch.ones(B, T, dtype=torch.bool); m[1, :] = False; m[2, 5:] = False
+    thr = float(torch.tensor(1.0 / P, dtype=torch.float32))
+    out, dv, dl = _sparc_tc(v, l, m, _cfg(thr))
+    o = lo.sparc_forward(v.double(), l.double(), m, thr, 1.0, 1.0, 1.0, mask_semantics="truncate")
+    rv, rl = lo.sparc_backward(o)
+    for k in lo.SPARC_KEYS:
+        assert abs(float(out[k]) - float(o[k])) <= 1e-4 * max(1.0, abs(float(o[k]))), (k, float(out[k]), float(o[k]))
+    assert torch.isfinite(dv).all() and torch.isfinite(dl).all()
+    assert rel_err(dv.float(), rv) <= 1e-3 + 2.0 ** -8 and rel_err(dl.float(), rl) <= 1e-3 + 2.0 ** -8
+    assert float(dl[1].abs().max()) == 0.0
+
+
 @pytest.mark.parametrize("B,P,T,D,s,mag,up", [
     (3, 197, 77, 512, 14.0, 0.5, 65536.0),      # GradScaler-scaled upstream gradient (finetuner.py:120-134)
     (2, 196, 77, 512, 1.0, 1.0, 1.0),           # no loss scale: coefficients ~ 1e-5
