@@ -46,7 +46,7 @@ __host__ __device__ inline Fwd3Layout fwd3_layout(int P, int T, int D) {
   L.slot1 = 2u * L.CR0 * 128;
   L.plane = (uint32_t)L.NT * L.NP * 2;
   // the Theta^T region doubles as the P0 scratch: pooled-mean partials [4][D]
-  const uint32_t scratch = 4u * D * 4;
+  const uint32_t scratch = 4u * D * 4 + 8u * (L.NP + L.NT) * 4;      // + sum-of-squares partials [8 chunks][NP + NT]
   const uint32_t op = ((2 * L.plane > scratch ? 2 * L.plane : scratch) + 1023) & ~1023u;
   // the S_raw^T region is reused once L' is done: E3 logits scratch [NT][NT + 1] fp32, then the per-warp transposition
   // tiles of the G epilogue (2 planes x [8][32] bf16 per warp)
@@ -98,19 +98,6 @@ struct Fwd3Params {
 };
 
 __device__ __forceinline__ void f3_epi_bar() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
-
-// r[lane] of a 32-register array without local memory (5 select levels)
-__device__ __forceinline__ float f3_pick32(const float* r, int lane) {
-  float a[16], b[8], c[4];
-#pragma unroll
-  for (int i = 0; i < 16; ++i) a[i] = (lane & 16) ? r[16 + i] : r[i];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) b[i] = (lane & 8) ? a[8 + i] : a[i];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) c[i] = (lane & 4) ? b[4 + i] : b[i];
-  const float d0 = (lane & 2) ? c[2] : c[0], d1 = (lane & 2) ? c[3] : c[1];
-  return (lane & 1) ? d1 : d0;
-}
 
 template <int kNT, int kNP, int kD, bool kHalf>
 __global__ void __launch_bounds__(kF3Threads, 1)
@@ -179,7 +166,6 @@ sparc_fwd3_kernel(const __grid_constant__ CUtensorMap tmV0, const __grid_constan
   const uint32_t tmem = *tmem_slot;
   const int NT2 = 2 * NT;
   const uint32_t cG = (uint32_t)NT2;                  // G'^T ping-pong buffers at columns NT2 and 2 NT2
-  const uint32_t cGV = (uint32_t)NT2, cGL = (uint32_t)NT2 + 128u * MB;   // P0 only: Gram tiles v . v^T (per M block), l . l^T
 
   if (warp == 0) {
     // =============================== TMA producer ===============================
@@ -211,7 +197,6 @@ sparc_fwd3_kernel(const __grid_constant__ CUtensorMap tmV0, const __grid_constan
     // =============================== MMA issuer (warp-uniform control flow, one elected lane issues) ===============================
     const bool leader = elect_one();
     const uint32_t idesc_s = make_idesc16(128, NT, false, false, kHalf, kHalf);     // raw v (K-major) x raw l (K-major)
-    const uint32_t idesc_gv = make_idesc16(128, 128, false, false, kHalf, kHalf);   // Gram tile of one M block of v
     const uint32_t idesc_l2 = make_idesc16(128, NT2, true, true, kHalf, kHalf);     // S_raw^T (MN-major) x Theta^T hi|lo (MN-major)
     const uint32_t idesc_l1 = make_idesc16(128, NT, true, true, kHalf, kHalf);
     const uint32_t idesc_g = make_idesc16(128, NT2, true, true, kHalf, kHalf);      // raw v^T (MN-major tile pair) x Theta^T hi|lo
@@ -232,12 +217,8 @@ sparc_fwd3_kernel(const __grid_constant__ CUtensorMap tmV0, const __grid_constan
           const uint64_t dvm = dv0 + mb * (16384 >> 4);
 #pragma unroll
           for (int k = 0; k < 4; ++k) umma_ss_w(leader, tmem + mb * NT, dvm + 2 * k, dl0 + 2 * k, idesc_s, (u | k) != 0);
-#pragma unroll
-          for (int k = 0; k < 4; ++k) umma_ss_w(leader, tmem + cGV + mb * 128, dvm + 2 * k, dvm + 2 * k, idesc_gv, (u | k) != 0);
         }
       }
-#pragma unroll
-      for (int k = 0; k < 4; ++k) umma_ss_w(leader, tmem + cGL, dl0 + 2 * k, dl0 + 2 * k, idesc_s, (u | k) != 0);
       umma_commit_w(leader, empty0 + s);
       if (++s == NS0) { s = 0; ph ^= 1; }
     }
@@ -294,27 +275,37 @@ sparc_fwd3_kernel(const __grid_constant__ CUtensorMap tmV0, const __grid_constan
     auto stamp = [&]() { if (pwarp) { if (pf) pf[pi] = clock64(); ++pi; } };
     stamp();
 
-    // ---- P0 side job: pooled text mean (losses.py:210-212) straight from the TMA tiles.  Warp -> 16-byte chunk c (8 columns
-    // of the 64-wide block) and row parity: rows lane + 32 k, k = hf, hf + 2, ... (conflict-free under the 128-byte swizzle).
+    // ---- P0 side job (the epilogue warps are otherwise idle while S accumulates): straight from the TMA tiles in shared
+    // memory, the pooled text mean (losses.py:210-212) and the squared row norms of v and l (F.normalize, :152-153 / :221-222).
+    // Warp -> 16-byte chunk c (8 columns of the 64-wide block) and row parity: rows lane + 32 k, k = hf, hf + 2, ...
+    // (conflict-free under the 128-byte swizzle); every (row, chunk) pair belongs to exactly one thread, which keeps its
+    // sum of squares in a register over all D blocks.  (The norms used to come from tensor-core Gram tiles v_kb v_kb^T,
+    // l_kb l_kb^T issued next to S: that doubled the MMA time of P0 -- 9 k of its 14 k cycles.)
     // The pooled IMAGE mean comes from here only when there is no spare token column (T == NT), see E1.
     {
       const int c = ew & 7, hf = ew >> 3;
       float* poolp = reinterpret_cast<float*>(TH);      // [2 modalities][2 parities][D] (the Theta region is unused until E1)
+      float* ssp = poolp + 4 * D;                       // [8 chunks][NP + NT] sum-of-squares partials
+      float ssv[4] = {0.f, 0.f, 0.f, 0.f}, ssl[2] = {0.f, 0.f};
       for (int u = 0, s = 0, ph = 0; u < KB0; ++u) {
         mbar_wait_sleep(full0 + s, ph);
         const uint8_t* st = ring0 + (size_t)s * slot0;
         float al[8], av[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) { al[i] = 0.f; av[i] = 0.f; }
-        if (!pool_tc) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const int r = lane + 32 * (2 * k + hf);
-            if (r < NP) {
-              float f8[8];
-              unpack_raw8<kHalf>(*reinterpret_cast<const uint4*>(st + r * 128 + ((c ^ (r & 7)) << 4)), f8);
+        for (int k = 0; k < 4; ++k) {
+          const int r = lane + 32 * (2 * k + hf);
+          if (r < NP) {
+            float f8[8];
+            unpack_raw8<kHalf>(*reinterpret_cast<const uint4*>(st + r * 128 + ((c ^ (r & 7)) << 4)), f8);
+            float q2 = ssv[k];
 #pragma unroll
-              for (int i = 0; i < 8; ++i) av[i] += f8[i];                // rows beyond P are zero-filled by TMA
+            for (int i = 0; i < 8; ++i) q2 = fmaf(f8[i], f8[i], q2);     // rows beyond P are zero-filled by TMA
+            ssv[k] = q2;
+            if (!pool_tc) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) av[i] += f8[i];
             }
           }
         }
@@ -325,8 +316,10 @@ sparc_fwd3_kernel(const __grid_constant__ CUtensorMap tmV0, const __grid_constan
             float f8[8];
             unpack_raw8<kHalf>(*reinterpret_cast<const uint4*>(st + v_bytes + r * 128 + ((c ^ (r & 7)) << 4)), f8);
             const float m = msk[r];
+            float q2 = ssl[k];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) al[i] = fmaf(m, f8[i], al[i]);
+            for (int i = 0; i < 8; ++i) { al[i] = fmaf(m, f8[i], al[i]); q2 = fmaf(f8[i], f8[i], q2); }
+            ssl[k] = q2;
           }
         }
         __syncwarp();
@@ -339,51 +332,47 @@ sparc_fwd3_kernel(const __grid_constant__ CUtensorMap tmV0, const __grid_constan
         }
         if (++s == NS0) { s = 0; ph ^= 1; }
       }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { const int r = lane + 32 * (2 * k + hf); if (r < NP) ssp[c * (NP + NT) + r] = ssv[k]; }
+#pragma unroll
+      for (int k = 0; k < 2; ++k) { const int r = lane + 32 * (2 * k + hf); if (r < NT) ssp[c * (NP + NT) + NP + r] = ssl[k]; }
     }
     stamp();
-    mbar_wait_sleep(s_full, 0);
-    tc_fence_after();
-    stamp();
-    // ---- row norms from the Gram diagonals (TMEM lane i, column i of its 32 x 32 diagonal block)
     const int mb = grp & 1, chh = grp >> 1;
     const int prow = 128 * mb + 32 * q + lane;          // patch of this thread
     const bool e1_act = mb < MB;
-    if (chh == 0 && e1_act) {
-      float r[32];
-      tmem_ld32(tq + cGV + mb * 128 + 32 * q, r);
-      tmem_ld_wait();
-      const float ss = f3_pick32(r, lane);
-      if (prow < NP) {
-        const float n = (prow < P) ? 1.f / fmaxf(sqrtf(ss), kF3NormEps) : 0.f;
-        ivn[prow] = n;
-        if (prow < P) p.inv_vn[(size_t)b * P + prow] = n;
-      }
-    } else if (chh == 1 && mb == 0 && 32 * q < NT) {
-      float r[32];
-      if (32 * q + 32 <= NT) tmem_ld32(tq + cGL + 32 * q, r);
-      else {
-        tmem_ld16(tq + cGL + 32 * q, r);
-#pragma unroll
-        for (int i = 16; i < 32; ++i) r[i] = 0.f;
-      }
-      tmem_ld_wait();
-      const float ss = f3_pick32(r, lane);
-      const int t = 32 * q + lane;
-      if (t < NT) {
-        const float n = (t < T) ? 1.f / fmaxf(sqrtf(ss), kF3NormEps) : 0.f;
-        cst[t].x = n;
-        if (t < T) p.inv_ln[(size_t)b * T + t] = n;
-      }
-    }
+    f3_epi_bar();                                       // sum-of-squares and pooled partials complete
     {
+      // row norms: the 8 chunk partials of a row added in fixed order
+      const float* ssp = reinterpret_cast<const float*>(TH) + 4 * D;
+      for (int i = tid; i < NP + NT; i += 512) {
+        float ss = 0.f;
+#pragma unroll
+        for (int cc = 0; cc < 8; ++cc) ss += ssp[cc * (NP + NT) + i];
+        if (i < NP) {
+          const float n = (i < P) ? 1.f / fmaxf(sqrtf(ss), kF3NormEps) : 0.f;
+          ivn[i] = n;
+          if (i < P) p.inv_vn[(size_t)b * P + i] = n;
+        } else {
+          const int t = i - NP;
+          const float n = (t < T) ? 1.f / fmaxf(sqrtf(ss), kF3NormEps) : 0.f;
+          cst[t].x = n;
+          if (t < T) p.inv_ln[(size_t)b * T + t] = n;
+        }
+      }
       const float inv_cnt = 1.f / fmaxf(red[63], kF3ClampEps), invPm = 1.f / (float)P;
       const float* poolp = reinterpret_cast<const float*>(TH);
-      f3_epi_bar();                                       // pooled partials, ivn, 1/||l|| complete
       for (int i = tid; i < D; i += 512) {
         p.pooled_l[(size_t)b * D + i] = (poolp[2 * D + i] + poolp[3 * D + i]) * inv_cnt;
         if (!pool_tc) p.pooled_v[(size_t)b * D + i] = (poolp[i] + poolp[D + i]) * invPm;
       }
     }
+    f3_epi_bar();                                       // ivn, 1/||l|| visible to every warp; the Theta region may be overwritten
+    stamp();
+    mbar_wait_sleep(s_full, 0);
+    tc_fence_after();
+    stamp();
+
     // fp16 operands: S_raw is stored as sa * S_raw with sa = 2^k <= 1 / (max ||v_p|| max ||l_t||), so |sa S_raw| <= 1 sits in
     // fp16's normal range whatever the embedding magnitudes; the logits undo it (exact: a power of two).  Every warp derives
     // the same sa from the same shared arrays; sparc_bwd3 recomputes it from the stored norms.
@@ -396,7 +385,6 @@ sparc_fwd3_kernel(const __grid_constant__ CUtensorMap tmV0, const __grid_constan
       sa = pow2_floor_clamped(mv * ml);
       isa = 1.f / sa;
     }
-    stamp();
 
     // ---- E1: thread = patch.  (mb, column half) from the warp group; warps of a non-existent M block idle.
     const bool live = e1_act && prow < P;

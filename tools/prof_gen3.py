@@ -17,7 +17,7 @@ for _ in range(3):
     v.grad=None; l.grad=None
     crit(v,l,m)['total_loss'].backward()
 names = {'fwd': (['start','P0 issued','w_ready seen','P1 issued'],
-                 ['start','side job done','s_full seen','norms + pooled done','sweep 1 done','sweep 2 done (w_ready)','sigma / stats done','G blk 0 done','all G + csc done','E3 logits in smem','end']),
+                 ['start','side job done','norms + pooled done','s_full seen','sweep 1 done','sweep 2 done (w_ready)','sigma / stats done','G blk 0 done','all G + csc done','E3 logits in smem','end']),
          'bwd': (['start','P1 issued','e1_ready seen','ds_ready seen','P4 issued'],
                  ['start','phase 0 done','s_full seen','E1 done','dw_full seen','E3 done','dl blk 0 done','dv blk 0 done','end'])}
 for which, setter in (('fwd', _lib.lib.cfa_debug_set_profile_buffer_fwd), ('bwd', _lib.lib.cfa_debug_set_profile_buffer)):
