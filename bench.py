@@ -48,6 +48,44 @@ def peaks():
     return dict(hbm=6650.0, tf_burst=1590.0, tf_sus=1400.0, src="fallback (B200_PROFILING.md)")
 
 
+def gpu_local_cpus(dev):
+    """CPUs on the NUMA node the GPU hangs off (sysfs local_cpulist), or None.  Pinned staging buffers are first-touched by
+    the allocating thread: allocating them from a CPU of the GPU's own node keeps the H2D copies of the end-to-end leg off the
+    inter-socket link on multi-socket hosts.  (The boxes of this pool expose ONE node of 16 CPUs -- tools/numa_probe.py: 50-55
+    GB/s either way -- so it is a no-op there; the e2e figure still varies from box to box, 114 k ... 194 k pairs/s.)"""
+    try:
+        pr = torch.cuda.get_device_properties(dev)
+        bdf = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        txt = open(f"/sys/bus/pci/devices/{bdf}/local_cpulist").read().strip()
+        cpus = set()
+        for part in txt.split(","):
+            if not part:
+                continue
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= set(os.sched_getaffinity(0))
+        return sorted(cpus) or None
+    except Exception:
+        return None
+
+
+class numa_local:
+    """with numa_local(dev): ... runs the block on the GPU's local CPUs (no-op when the topology is not exposed)."""
+
+    def __init__(self, dev):
+        self.cpus = gpu_local_cpus(dev)
+
+    def __enter__(self):
+        self.prev = os.sched_getaffinity(0)
+        if self.cpus:
+            os.sched_setaffinity(0, self.cpus)
+        return self
+
+    def __exit__(self, *exc):
+        os.sched_setaffinity(0, self.prev)
+        return False
+
+
 def cfg(thr, s=1.0):
     return types.SimpleNamespace(similarity_threshold=thr, global_loss_weight=1.0, local_loss_weight=1.0,
                                  inverse_temperature=s)
@@ -506,9 +544,11 @@ def main():
     # ---- end to end through the public API with HOST buffers (pinned): every step copies ITS inputs host->device and
     # reads its loss back device->host inside the timed region.  Like any input pipeline, the copy of step i+1 is
     # issued on a copy stream while step i computes (two device buffers); nothing is cached across steps.
-    hv = torch.randn(B, P, D).to(dt).pin_memory()
-    hl = torch.randn(B, T, D).to(dt).pin_memory()
-    hm = torch.ones(B, T, dtype=torch.bool).pin_memory()
+    with numa_local(dev) as nl:
+        hv = torch.randn(B, P, D).to(dt).pin_memory()
+        hl = torch.randn(B, T, D).to(dt).pin_memory()
+        hm = torch.ones(B, T, dtype=torch.bool).pin_memory()
+    numa_note = f"; staging buffers first-touched on the GPU's NUMA node ({len(nl.cpus)} local CPUs)" if nl.cpus else ""
     bufs = [(torch.empty(B, P, D, dtype=dt, device=dev), torch.empty(B, T, D, dtype=dt, device=dev),
              torch.empty(B, T, dtype=torch.bool, device=dev)) for _ in range(2)]
     copy_stream = torch.cuda.Stream(device=dev)
@@ -600,7 +640,7 @@ def main():
         "e2e": {"value": round(e2e_val, 1), "unit": UNIT,
                 "h2d_bytes_per_step": int(hv.numel() * hv.element_size() + hl.numel() * hl.element_size() + hm.numel()),
                 "d2h_bytes_per_step": 4, "steps": e2e_steps,
-                "note": "pinned host buffers; H2D of step i+1 overlaps compute of step i (copy stream); PCIe-bound"},
+                "note": "pinned host buffers; H2D of step i+1 overlaps compute of step i (copy stream); PCIe-bound" + numa_note},
         "gpu_launches": launches, "host_issue_ms_per_step": round(host_issue_ms, 4), "clocks": clocks,
     }
     if config3_n1 is not None:
