@@ -398,3 +398,48 @@ def test_sparc_cast_to_bf16_opt_in():
     assert va.grad.dtype == torch.float16 and la.grad.dtype == torch.float16
     assert float(oa["total_loss"]) == float(ob["total_loss"])
     assert torch.equal(va.grad.float(), vb.grad.float().half().float()) and torch.equal(la.grad.float(), lb.grad.float().half().float())
+
+
+@pytest.mark.parametrize("B,P,T,D,dtype", [(5, 196, 77, 512, torch.bfloat16), (3, 197, 77, 512, torch.float16),
+                                           (4, 50, 20, 128, torch.bfloat16), (2, 255, 80, 256, torch.bfloat16)])
+def test_sparc_tc_stays_inside_its_buffers(B, P, T, D, dtype):
+    """Guard bands (compute-sanitizer is not available on this pool): the inputs, the workspace and the two gradient outputs
+    of the one-call C ABI sit between canary regions inside larger allocations; no kernel of the forward / backward chain
+    (TMA loads with out-of-range rows, 16-byte transposed stores, the saved G planes, statistics, partial buffers) may
+    write a byte outside what it was given, and the inputs must come back unchanged."""
+    from clip_finegrained_alignment_b200 import _lib
+    L = _lib.lib
+    code = _lib.DTYPE_CODE[dtype]
+    guard = 4096                                          # bytes on each side, 128-byte aligned payloads
+    def banded(nbytes):
+        n = (nbytes + 127) & ~127
+        buf = torch.full((guard + n + guard,), 0xA5, dtype=torch.uint8, device="cuda")
+        return buf, buf[guard:guard + nbytes]
+    g = torch.Generator().manual_seed(B + P)
+    esz = 2
+    vb, vpay = banded(B * P * D * esz); lb, lpay = banded(B * T * D * esz)
+    v = vpay.view(dtype).view(B, P, D); l = lpay.view(dtype).view(B, T, D)
+    v.copy_(torch.randn(B, P, D, generator=g).to(dtype)); l.copy_(torch.randn(B, T, D, generator=g).to(dtype))
+    v0, l0 = v.clone(), l.clone()
+    mask = torch.ones(B, T, dtype=torch.uint8, device="cuda"); mask[0, T // 2:] = 0
+    nws = L.cfa_sparc_loss_workspace_bytes(B, P, T, D, code, 0)
+    wb, wpay = banded(nws)
+    db, dpay = banded(B * P * D * esz); eb, epay = banded(B * T * D * esz)
+    thr = float(torch.tensor(1.0 / P, dtype=torch.float32))
+    _lib.call("cfa_sparc_loss_fwd", v.data_ptr(), l.data_ptr(), mask.data_ptr(), B, P, T, D, code, thr, 1.0, 1.0, 1.0,
+              wpay.data_ptr(), nws, 0, _lib.stream_ptr())
+    one = torch.ones(1, device="cuda")
+    _lib.call("cfa_sparc_loss_bwd", v.data_ptr(), l.data_ptr(), mask.data_ptr(), B, P, T, D, code, thr, 1.0, 1.0, 1.0,
+              wpay.data_ptr(), nws, 0, 0, one.data_ptr(), 0, 0, 0, 0, dpay.data_ptr(), epay.data_ptr(), 0, _lib.stream_ptr())
+    torch.cuda.synchronize()
+    for name, buf, nbytes in (("v", vb, B * P * D * esz), ("l", lb, B * T * D * esz), ("workspace", wb, nws),
+                              ("dv", db, B * P * D * esz), ("dl", eb, B * T * D * esz)):
+        n = (nbytes + 127) & ~127
+        assert bool((buf[:guard] == 0xA5).all()), f"{name}: bytes written BEFORE the buffer"
+        assert bool((buf[guard + n:] == 0xA5).all()), f"{name}: bytes written AFTER the buffer"
+        if n > nbytes:
+            assert bool((buf[guard + nbytes:guard + n] == 0xA5).all()), f"{name}: bytes written in the alignment tail"
+    assert torch.equal(v, v0) and torch.equal(l, l0)
+    dv = dpay.view(dtype).view(B, P, D); dl = epay.view(dtype).view(B, T, D)
+    assert torch.isfinite(dv.float()).all() and torch.isfinite(dl.float()).all()
+    assert float(dv.float().abs().sum()) > 0 and float(dl.float().abs().sum()) > 0
