@@ -28,6 +28,27 @@ struct PeerTable {
     if (_e != cudaSuccess) return (int)_e;         \
   } while (0)
 
+// Programmatic dependent launch (griddepcontrol): a kernel launched with cfa_launch_pdl may START while its predecessor in the
+// stream is still running -- once every CTA of the predecessor has executed pdl_launch_dependents() (or exited) -- and must
+// call pdl_wait() before it touches anything the predecessor writes: the wait returns when the predecessor grid has
+// completed and its memory is visible.  A predecessor that never triggers gives ordinary stream order; a kernel launched
+// without the attribute sees both calls as no-ops.
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t cfa_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+#endif
+
 // Opt-in to > 48 KB of dynamic shared memory ONCE PER DEVICE (the attribute is per device: a per-process `static bool`
 // guard would leave the second GPU of a multi-device process without it).  `mask` is the call site's static bit set.
 #define CFA_SMEM_ATTR_ONCE(func, bytes)                                                                      \

@@ -228,6 +228,10 @@ global_norm_bwd_kernel(const float* __restrict__ a_loc, const float* __restrict_
                        const float* __restrict__ part, int nsplit, int B, int D, float* __restrict__ da,
                        float* __restrict__ db) {
   __shared__ float red[4];
+  // launched with the programmatic-dependent-launch attribute: let the next kernel (sparc_bwd3, which needs this kernel's
+  // output only in its last pass) start now, then wait for the kernel that wrote `part` to finish
+  pdl_launch_dependents();
+  pdl_wait();
   const int r = blockIdx.x, dir = blockIdx.y;
   const float* x = (dir ? b_loc : a_loc) + (size_t)r * D;
   float* dx = (dir ? db : da) + (size_t)r * D;
@@ -385,7 +389,8 @@ extern "C" int cfa_global_infonce_bwd(const float* a_loc, const float* b_loc, co
     int nsp;
     const int rc = global_sym_bwd(a_loc, b_loc, B, D, scale, eps, lse_loc2, coef2, &dpart, &nsp, workspace, (cudaStream_t)stream);
     if (rc != CFA_OK) return rc;
-    global_norm_bwd_kernel<<<dim3(B, 2), 128, 0, (cudaStream_t)stream>>>(a_loc, b_loc, norms2, dpart, nsp, B, D, da, db);
+    CFA_CUDA_TRY(cfa_launch_pdl(global_norm_bwd_kernel, dim3(B, 2), dim3(128), 0, (cudaStream_t)stream, a_loc, b_loc, norms2,
+                                (const float*)dpart, nsp, B, D, da, db));
     return launch_status();
   }
   if (use_tc(B, Bg, D, path)) {       // needs the SAME workspace the forward call used (normalised hi/lo operands live there)
@@ -394,7 +399,8 @@ extern "C" int cfa_global_infonce_bwd(const float* a_loc, const float* b_loc, co
     const int rc = global_tc_bwd(B, Bg, D, col_offset, scale, lse_loc2, lse_all2, coef2, &dpart, &nsp, workspace,
                                  gathered_ranks, (cudaStream_t)stream);
     if (rc != CFA_OK) return rc;
-    global_norm_bwd_kernel<<<dim3(B, 2), 128, 0, (cudaStream_t)stream>>>(a_loc, b_loc, norms2, dpart, nsp, B, D, da, db);
+    CFA_CUDA_TRY(cfa_launch_pdl(global_norm_bwd_kernel, dim3(B, 2), dim3(128), 0, (cudaStream_t)stream, a_loc, b_loc, norms2,
+                                (const float*)dpart, nsp, B, D, da, db));
     return launch_status();
   }
   const int ns = gb_splits(B, Bg, D);

@@ -236,6 +236,7 @@ gt_bwd_kernel(const __grid_constant__ CUtensorMap tmLoc, const __grid_constant__
     fence_barrier_init();
     tma_prefetch_desc(&tmLoc); tma_prefetch_desc(&tmAll);
   }
+  pdl_launch_dependents();                             // the dependent (global_norm_bwd_kernel) waits for this grid's completion itself
   GT_MARK(1);
   if (warp == 1) tmem_alloc(tmem_slot, 512);
   GT_MARK(2);

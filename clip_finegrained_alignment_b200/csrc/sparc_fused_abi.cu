@@ -99,9 +99,12 @@ extern "C" int cfa_sparc_loss_bwd(const void* v, const void* l, const uint8_t* m
   rc = cfa_global_infonce_bwd(a, b, a, b, B, B, D, 0, scale, 1e-12f, f + w.glse, f + w.glse, f + w.gnorms, f + w.coef, da, db,
                               f + w.gws, w.gws_bytes, gpath, 0, stream);
   if (rc != CFA_OK) return rc;
-  return cfa_sparc_bwd(v, l, mask, B, P, T, D, dtype, thr, scale, f + w.rin, f + w.lse_row, f + w.lse_col, f + w.tt, f + w.gin,
+  cfa::g_sparc_bwd_pdl_late = true;      // the backward may start under the global InfoNCE backward (see sparc_paths.h)
+  rc = cfa_sparc_bwd(v, l, mask, B, P, T, D, dtype, thr, scale, f + w.rin, f + w.lse_row, f + w.lse_col, f + w.tt, f + w.gin,
                        w.saved ? (const void*)(f + w.gsplit) : nullptr, w.saved ? f + w.qsave : nullptr, f + w.coef + 2, da, db,
                        dv, dl, w.scratch_bytes ? (void*)(f + w.scratch) : nullptr, w.scratch_bytes, path, stream);
+  cfa::g_sparc_bwd_pdl_late = false;
+  return rc;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -210,9 +213,12 @@ extern "C" int cfa_sparc_loss_gathered_bwd_ex(const void* v, const void* l, cons
   rc = cfa_global_infonce_bwd(a, b, a, b, B, world * B, D, rank * B, scale, 1e-12f, pack, f + w.gpack, f + w.gnorms, f + w.coef,
                               da, db, f + w.gws, w.gws_bytes, gpath, world, stream);
   if (rc != CFA_OK) return rc;
-  return cfa_sparc_bwd(v, l, mask, B, P, T, D, dtype, thr, scale, f + w.rin, f + w.lse_row, f + w.lse_col, f + w.tt, f + w.gin,
+  cfa::g_sparc_bwd_pdl_late = true;      // the backward may start under the global InfoNCE backward (see sparc_paths.h)
+  rc = cfa_sparc_bwd(v, l, mask, B, P, T, D, dtype, thr, scale, f + w.rin, f + w.lse_row, f + w.lse_col, f + w.tt, f + w.gin,
                        w.saved ? (const void*)(f + w.gsplit) : nullptr, w.saved ? f + w.qsave : nullptr, f + w.coef + 2, da, db,
                        dv, dl, w.scratch_bytes ? (void*)(f + w.scratch) : nullptr, w.scratch_bytes, path, stream);
+  cfa::g_sparc_bwd_pdl_late = false;
+  return rc;
 }
 
 // ---------------------------------------------------------------------------------------------------------------

@@ -46,7 +46,13 @@ int sparc_fwd3_launch(const void* v, const void* l, const uint8_t* mask, int B, 
 int sparc_bwd3_launch(const void* v, const void* l, const uint8_t* mask, int B, int P, int T, int D, float thr, float scale,
                       const float* row_inv_norm, const float* lse_row, const float* lse_col, const float* coef,
                       const float* tt_logits, const float* g_inv_norm, const void* g_split, const float* stats,
-                      const float* dpv, const float* dpl, void* dv, void* dl, long long* prof, int dtype, cudaStream_t st);
+                      const float* dpv, const float* dpl, void* dv, void* dl, long long* prof, int dtype, cudaStream_t st,
+                      bool pdl_late = false);
+// Set by the one-call entry points (sparc_fused_abi.cu) around their cfa_sparc_bwd call: the kernel launched just before
+// sparc_bwd3 there is global_norm_bwd_kernel, whose only output (d pooled) the backward needs in its last pass, so the
+// backward may start under it (programmatic dependent launch) and wait late.  Everywhere else the wait is the kernel's
+// first instruction.
+extern thread_local bool g_sparc_bwd_pdl_late;
 
 // cfa_global_infonce_fwd with the gathered rows read through a peer table (global_infonce.cu)
 int global_infonce_fwd_peers(const float* a_loc, const float* b_loc, const float* a_all, const float* b_all, int B, int Bg,

@@ -1228,6 +1228,7 @@ int sparc_bwd_tc_launch(const void* v, const void* l, const uint8_t* mask, int B
 }  // namespace cfa
 
 namespace cfa {
+thread_local bool g_sparc_bwd_pdl_late = false;
 // generation switch (tuning aid): CFA_SPARC_GEN=2 keeps the second-generation kernels for A/B runs
 bool sparc_gen3_enabled(int P, int T, int D, int dtype) {
   static int gen = -1;
@@ -1304,7 +1305,7 @@ extern "C" int cfa_sparc_bwd(const void* v, const void* l, const uint8_t* mask, 
     if (g_split && q_save && sparc_gen3_enabled(P, T, D, dtype))
       return sparc_bwd3_launch(v, l, mask, B, P, T, D, thr, scale, row_inv_norm, lse_row, lse_col, coef, tt_logits,
                                g_inv_norm, g_split, q_save, dpooled_v, dpooled_l, dv, dl, g_prof_buffer, dtype,
-                               (cudaStream_t)stream);
+                               (cudaStream_t)stream, g_sparc_bwd_pdl_late);
     if (!sparc_tc_supported(P, T, D, dtype)) return CFA_ERR_WORKSPACE;
     if (g_split && q_save && sparc_bwd2_supported(P, T, D, dtype))      // streaming backward on the saved G / Q
       return sparc_bwd2_launch(v, l, mask, B, P, T, D, thr, scale, row_inv_norm, lse_row, lse_col, coef, tt_logits,

@@ -97,6 +97,7 @@ struct Bwd3Params {
   const float* stats;       // [B][T][4] min, 1/range, sigma, arg-min patch
   const float* dpool_v;
   const float* dpool_l;
+  int pdl_late;             // != 0: griddepcontrol.wait right before the first read of dpool_*, else at kernel start
   const bf16* v;
   const bf16* l;
   bf16* dv;
@@ -113,6 +114,7 @@ __global__ void __launch_bounds__(kB3Threads, 1)
 sparc_bwd3_kernel(const __grid_constant__ CUtensorMap tmV0, const __grid_constant__ CUtensorMap tmV1,
                   const __grid_constant__ CUtensorMap tmL, const __grid_constant__ CUtensorMap tmG, const Bwd3Params p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
+  if (!p.pdl_late) pdl_wait();                        // ordinary stream order (see g_sparc_bwd_pdl_late)
   uint8_t* base = CFA_SMEM_BASE_1024(smem_raw);
   const Bwd3Layout L = bwd3_layout(p.P, p.T, kD ? kD : p.D);
   const int NP = kNP ? kNP : L.NP, NT = kNT ? kNT : L.NT, D = kD ? kD : p.D;
@@ -633,6 +635,12 @@ sparc_bwd3_kernel(const __grid_constant__ CUtensorMap tmV0, const __grid_constan
     if (lane == 0) mbar_arrive(ds_ready);
     stamp();
 
+    // Everything above needs only the forward's saved buffers and the coefficients; the gradient of the pooled embeddings
+    // (dpool_v / dpool_l, written by the kernel launched just before this one) is first read here.  This kernel is launched
+    // with the programmatic-dependent-launch attribute, so it may have started while that kernel (and the global InfoNCE
+    // backward in front of it) was still running: wait for it now.  (Ordinary stream order otherwise: a no-op.)
+    pdl_wait();
+
     // ---- P4 outputs.  Arithmetic on the accumulators happens with thread = feature column d (TMEM layout), but every
     // global access is TRANSPOSED through a per-warp shared-memory tile [8 rows][32 d]: lane -> (row r = lane / 4, 16-byte
     // chunk ch4 = lane % 4), so one LDG / STG moves 8 rows x 64 contiguous bytes.  (2-byte accesses -- one row per
@@ -777,7 +785,8 @@ bool sparc_bwd3_supported(int P, int T, int D, int dtype) {
 int sparc_bwd3_launch(const void* v, const void* l, const uint8_t* mask, int B, int P, int T, int D, float thr, float scale,
                       const float* row_inv_norm, const float* lse_row, const float* lse_col, const float* coef,
                       const float* tt_logits, const float* g_inv_norm, const void* g_split, const float* stats,
-                      const float* dpv, const float* dpl, void* dv, void* dl, long long* prof, int dtype, cudaStream_t st) {
+                      const float* dpv, const float* dpl, void* dv, void* dl, long long* prof, int dtype, cudaStream_t st,
+                      bool pdl_late) {
   if (dtype != CFA_DTYPE_BF16 && dtype != CFA_DTYPE_F16) return CFA_ERR_UNSUPPORTED;
   if (!g_split || !stats || !tt_logits || !g_inv_norm) return CFA_ERR_WORKSPACE;
   const bool half = dtype == CFA_DTYPE_F16;
@@ -789,12 +798,12 @@ int sparc_bwd3_launch(const void* v, const void* l, const uint8_t* mask, int B, 
   if ((rc = make_tmap_bf16_3d(&tmL, l, D, T, B, 64, L.NT)) != CFA_OK) return rc;
   if ((rc = make_tmap_bf16_3d(&tmG, g_split, D, T, 2 * (uint64_t)B, 64, L.NT)) != CFA_OK) return rc;
   Bwd3Params prm{prof, P, T, D, thr, scale, mask, row_inv_norm, row_inv_norm + (size_t)B * P, lse_row, lse_col, coef,
-                 tt_logits, g_inv_norm, stats, dpv, dpl, (const bf16*)v, (const bf16*)l, (bf16*)dv, (bf16*)dl};
+                 tt_logits, g_inv_norm, stats, dpv, dpl, pdl_late ? 1 : 0, (const bf16*)v, (const bf16*)l, (bf16*)dv, (bf16*)dl};
   const size_t smem = L.total + 1024;
 #define CFA_B3_LAUNCH(NT_, NP_, D_, H_)                                                                                     \
   do {                                                                                                                      \
     CFA_CUDA_TRY(cudaFuncSetAttribute(sparc_bwd3_kernel<NT_, NP_, D_, H_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    sparc_bwd3_kernel<NT_, NP_, D_, H_><<<B, kB3Threads, smem, st>>>(tmV0, tmV1, tmL, tmG, prm);                             \
+    CFA_CUDA_TRY(cfa_launch_pdl(sparc_bwd3_kernel<NT_, NP_, D_, H_>, dim3(B), dim3(kB3Threads), smem, st, tmV0, tmV1, tmL, tmG, prm)); \
   } while (0)
   const bool flagship = L.NT == 80 && L.NP == 208 && D == 512;                 // ViT-B/16 (P = 196 / 197, T = 77)
   if (flagship && !half) CFA_B3_LAUNCH(80, 208, 512, false);
