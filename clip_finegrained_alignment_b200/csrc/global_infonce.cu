@@ -98,6 +98,8 @@ global_combine_kernel(const float* __restrict__ part_m, const float* __restrict_
                       const float* __restrict__ local_partial, const uint8_t* __restrict__ mask, int T, float gw, float lw,
                       float* __restrict__ out8) {
   __shared__ float red[8];
+  pdl_launch_dependents();                             // programmatic dependent launch (common.cuh): start early, wait here
+  pdl_wait();
   global_combine_body(part_m, part_l, diag, B, nsplit, lse, sums2, global_batch, local_partial, mask, T, gw, lw, out8, red);
 }
 
@@ -109,6 +111,8 @@ __global__ void __launch_bounds__(256)
 global_merge_rows_kernel(const float* __restrict__ part_m, const float* __restrict__ part_l, int B, int nsplit,
                          float* __restrict__ lse) {
   __shared__ float sm[8][32], sl[8][32];
+  pdl_launch_dependents();
+  pdl_wait();
   const int tx = threadIdx.x & 31, sg = threadIdx.x >> 5;
   const int idx = blockIdx.x * 32 + tx;
   float M = -CUDART_INF_F, Lq = 0.f;
@@ -354,11 +358,12 @@ int cfa::global_infonce_fwd_peers(const float* a_loc, const float* b_loc, const 
                                  workspace, gathered_ranks, peers, (cudaStream_t)stream);
     if (rc != CFA_OK) return rc;
     if (nsp > 8) {                                    // measured at 32 partials per row: single merge CTA 15 us, grid merge + sum 4 + 2 us
-      global_merge_rows_kernel<<<(2 * B + 31) / 32, 256, 0, (cudaStream_t)stream>>>(pm, pl, B, nsp, lse2);
+      CFA_CUDA_TRY(cfa_launch_pdl(2, global_merge_rows_kernel, dim3((2 * B + 31) / 32), dim3(256), 0, (cudaStream_t)stream,
+                                  (const float*)pm, (const float*)pl, B, nsp, lse2));
       nsp = 0;
     }
-    global_combine_kernel<<<1, kNT, 0, (cudaStream_t)stream>>>(pm, pl, dg, B, nsp, lse2, sums2, Bg, local_partial, mask, T, gw,
-                                                               lw, out8);
+    CFA_CUDA_TRY(cfa_launch_pdl(2, global_combine_kernel, dim3(1), dim3(kNT), 0, (cudaStream_t)stream, (const float*)pm,
+                                (const float*)pl, (const float*)dg, B, nsp, lse2, sums2, Bg, local_partial, mask, T, gw, lw, out8));
     return launch_status();
   }
   const int ns = gf_splits(B, Bg);
@@ -389,7 +394,7 @@ extern "C" int cfa_global_infonce_bwd(const float* a_loc, const float* b_loc, co
     int nsp;
     const int rc = global_sym_bwd(a_loc, b_loc, B, D, scale, eps, lse_loc2, coef2, &dpart, &nsp, workspace, (cudaStream_t)stream);
     if (rc != CFA_OK) return rc;
-    CFA_CUDA_TRY(cfa_launch_pdl(global_norm_bwd_kernel, dim3(B, 2), dim3(128), 0, (cudaStream_t)stream, a_loc, b_loc, norms2,
+    CFA_CUDA_TRY(cfa_launch_pdl(1, global_norm_bwd_kernel, dim3(B, 2), dim3(128), 0, (cudaStream_t)stream, a_loc, b_loc, norms2,
                                 (const float*)dpart, nsp, B, D, da, db));
     return launch_status();
   }
@@ -399,7 +404,7 @@ extern "C" int cfa_global_infonce_bwd(const float* a_loc, const float* b_loc, co
     const int rc = global_tc_bwd(B, Bg, D, col_offset, scale, lse_loc2, lse_all2, coef2, &dpart, &nsp, workspace,
                                  gathered_ranks, (cudaStream_t)stream);
     if (rc != CFA_OK) return rc;
-    CFA_CUDA_TRY(cfa_launch_pdl(global_norm_bwd_kernel, dim3(B, 2), dim3(128), 0, (cudaStream_t)stream, a_loc, b_loc, norms2,
+    CFA_CUDA_TRY(cfa_launch_pdl(1, global_norm_bwd_kernel, dim3(B, 2), dim3(128), 0, (cudaStream_t)stream, a_loc, b_loc, norms2,
                                 (const float*)dpart, nsp, B, D, da, db));
     return launch_status();
   }

@@ -31,6 +31,8 @@ __global__ void __launch_bounds__(256)
 gt_split_kernel(const float* __restrict__ a, const float* __restrict__ b, int rows, int D, float eps,
                 bf16* __restrict__ out, float* __restrict__ norms /* [2][loc_rows] or NULL */, int rank_rows, size_t rank_stride,
                 const PeerTable peers, int loc_row0, int loc_rows) {
+  pdl_launch_dependents();                             // programmatic dependent launch (common.cuh): start early, wait here
+  pdl_wait();
   // norms are kept for the LOCAL rows only (global rows [loc_row0, loc_row0 + loc_rows)): the local operand tiles are a
   // row window of the all-rows array, so one launch serves both
   // rank_rows / rank_stride: global row g = r * rank_rows + i lives at base + r * rank_stride + i * D (the raw output of
@@ -147,11 +149,13 @@ gt_fwd_kernel(const __grid_constant__ CUtensorMap tmLoc, const __grid_constant__
     fence_barrier_init();
     tma_prefetch_desc(&tmLoc); tma_prefetch_desc(&tmAll);
   }
+  pdl_launch_dependents();
   if (warp == 1) tmem_alloc(tmem_slot, 128);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  pdl_wait();                                          // prologue done under the split kernel; its output is read from here on
   gt_issue_logits<kStages>(warp, lane, stages, full, empty, s_full, tmem, &tmLoc, &tmAll, row0, col0, dir ? 2 : 0, dir ? 0 : 2, p.D / 64);
   if (warp >= 2) {
     const int q = warp & 3, h = (warp - 2) >> 2, row = 32 * q + lane, grow = row0 + row;
@@ -426,11 +430,14 @@ int global_tc_fwd(const float* a_loc, const float* b_loc, const float* a_all, co
   PeerTable none{};
   // ONE launch: every global row is normalised and split once; the local rows' norms come out of the same pass
   if (peers && peers->n > 1)
-    gt_split_kernel<<<dim3((Bg + 7) / 8, 2), 256, 0, st>>>(nullptr, nullptr, Bg, D, eps, h.all_split, norms2, B, 0, *peers, col_offset, B);
+    CFA_CUDA_TRY(cfa_launch_pdl(2, gt_split_kernel, dim3((Bg + 7) / 8, 2), dim3(256), 0, st, (const float*)nullptr, (const float*)nullptr, Bg, D, eps,
+                                h.all_split, norms2, B, (size_t)0, *peers, col_offset, B));
   else if (gathered_ranks > 1)
-    gt_split_kernel<<<dim3((Bg + 7) / 8, 2), 256, 0, st>>>(a_all, b_all, Bg, D, eps, h.all_split, norms2, B, (size_t)2 * B * D, none, col_offset, B);
+    CFA_CUDA_TRY(cfa_launch_pdl(2, gt_split_kernel, dim3((Bg + 7) / 8, 2), dim3(256), 0, st, a_all, b_all, Bg, D, eps, h.all_split, norms2, B,
+                                (size_t)2 * B * D, none, col_offset, B));
   else
-    gt_split_kernel<<<dim3((Bg + 7) / 8, 2), 256, 0, st>>>(a_all, b_all, Bg, D, eps, h.all_split, norms2, Bg, 0, none, col_offset, B);
+    CFA_CUDA_TRY(cfa_launch_pdl(2, gt_split_kernel, dim3((Bg + 7) / 8, 2), dim3(256), 0, st, a_all, b_all, Bg, D, eps, h.all_split, norms2, Bg,
+                                (size_t)0, none, col_offset, B));
   CFA_CUDA_TRY(cudaGetLastError());
   CUtensorMap tmLoc, tmAll;
   int rc = gt_maps(h, B, Bg, D, col_offset, &tmLoc, &tmAll);
@@ -444,8 +451,8 @@ int global_tc_fwd(const float* a_loc, const float* b_loc, const float* a_all, co
   const size_t smem = (big ? kGtFwdStages : kGtStages) * kGtStage + 1024 + 1024;
   CFA_SMEM_ATTR_ONCE(gt_fwd_kernel<kGtFwdStages>, kGtFwdStages * kGtStage + 2048);
   CFA_SMEM_ATTR_ONCE(gt_fwd_kernel<kGtStages>, kGtStages * kGtStage + 2048);
-  if (big) gt_fwd_kernel<kGtFwdStages><<<grid, kGtThreads, smem, st>>>(tmLoc, tmAll, p);
-  else gt_fwd_kernel<kGtStages><<<grid, kGtThreads, smem, st>>>(tmLoc, tmAll, p);
+  if (big) CFA_CUDA_TRY(cfa_launch_pdl(2, gt_fwd_kernel<kGtFwdStages>, grid, dim3(kGtThreads), smem, st, tmLoc, tmAll, p));
+  else CFA_CUDA_TRY(cfa_launch_pdl(2, gt_fwd_kernel<kGtStages>, grid, dim3(kGtThreads), smem, st, tmLoc, tmAll, p));
   *part_m = p.part_m; *part_l = p.part_l; *diag = p.diag; *nsplit = 2 * h.nct;
   return launch_status();
 }

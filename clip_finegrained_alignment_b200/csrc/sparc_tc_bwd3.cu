@@ -803,7 +803,7 @@ int sparc_bwd3_launch(const void* v, const void* l, const uint8_t* mask, int B, 
 #define CFA_B3_LAUNCH(NT_, NP_, D_, H_)                                                                                     \
   do {                                                                                                                      \
     CFA_CUDA_TRY(cudaFuncSetAttribute(sparc_bwd3_kernel<NT_, NP_, D_, H_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    CFA_CUDA_TRY(cfa_launch_pdl(sparc_bwd3_kernel<NT_, NP_, D_, H_>, dim3(B), dim3(kB3Threads), smem, st, tmV0, tmV1, tmL, tmG, prm)); \
+    CFA_CUDA_TRY(cfa_launch_pdl(1, sparc_bwd3_kernel<NT_, NP_, D_, H_>, dim3(B), dim3(kB3Threads), smem, st, tmV0, tmV1, tmL, tmG, prm)); \
   } while (0)
   const bool flagship = L.NT == 80 && L.NP == 208 && D == 512;                 // ViT-B/16 (P = 196 / 197, T = 77)
   if (flagship && !half) CFA_B3_LAUNCH(80, 208, 512, false);

@@ -104,6 +104,7 @@ __global__ void __launch_bounds__(kF3Threads, 1)
 sparc_fwd3_kernel(const __grid_constant__ CUtensorMap tmV0, const __grid_constant__ CUtensorMap tmV1,
                   const __grid_constant__ CUtensorMap tmL, const Fwd3Params p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
+  pdl_launch_dependents();                             // the next kernel (normalise / split of the pooled embeddings) may set up under this one
   uint8_t* base = CFA_SMEM_BASE_1024(smem_raw);
   const Fwd3Layout L = fwd3_layout(p.P, p.T, kD ? kD : p.D);
   const int NP = kNP ? kNP : L.NP, NT = kNT ? kNT : L.NT, D = kD ? kD : p.D;
