@@ -99,7 +99,7 @@ for _name, (_res, _args) in SIGNATURES.items():
 LAUNCHES = {"cfa_adamspd_step": 2, "cfa_adamspd_step_amp": 4, "cfa_global_infonce_fwd": 1, "cfa_global_infonce_bwd": 2,
             "cfa_sparc_fwd": 1, "cfa_sparc_bwd": 1, "cfa_sparc_finalize": 1, "cfa_sparc_coef": 1, "cfa_sparc_coef_ptrs": 1,
             "cfa_masked_pairwise_fwd": 2, "cfa_masked_pairwise_bwd": 1,
-            "cfa_sparc_loss_fwd": 4, "cfa_sparc_loss_bwd": 4,     # tensor-core chain: fwd3 + split + logits + combine | coef + logits-bwd + norm-bwd + bwd3
+            "cfa_sparc_loss_fwd": 4, "cfa_sparc_loss_bwd": 3,     # tensor-core chain: fwd3 + split + logits + combine | logits-bwd + norm-bwd + bwd3 (coefficients evaluated in-kernel)
             "cfa_count_contrastive_fwd": 2, "cfa_count_contrastive_bwd": 1, "cfa_logits_ce_fwd": 2, "cfa_logits_ce_bwd": 1,
             "cfa_sparc_loss_gathered_fwd": 8, "cfa_sparc_loss_gathered_bwd": 4, "cfa_sparc_loss_gathered_bwd_ex": 4, "cfa_peer_sync": 1,
             "cfa_global_infonce_gathered_fwd": 7, "cfa_global_infonce_gathered_bwd": 2,

@@ -29,6 +29,33 @@ struct PeerTable {
     if (_e != cudaSuccess) return (int)_e;         \
   } while (0)
 
+// Upstream-gradient fan-in of the SPARC loss (autograd of losses.py:217,252,254-264) evaluated INSIDE the consuming kernels:
+// the 7 upstream gradients arrive as device pointers (NULL = output unused), out8[7] is the number of valid tokens.
+//   c[0], c[1]: coefficients of the two global InfoNCE directions (already divided by the global batch, times gscale)
+//   c[2], c[3]: coefficients of the two token-level directions (already divided by n_valid)
+// Same expressions as sparc_coef_ptrs_kernel (losses_simt.cu), which the per-stage entry points still launch.
+struct CoefSrc {
+  const float* g[7];
+  const float* out8;
+  float gw, lw, gscale;
+  int global_batch;
+  int on;                  // 0: the kernel reads a precomputed coefficient array instead
+};
+#ifdef __CUDACC__
+__device__ __forceinline__ void coef_from_src(const CoefSrc& s, float c[4]) {
+  float u[7];
+#pragma unroll
+  for (int k = 0; k < 7; ++k) u[k] = s.g[k] ? *s.g[k] : 0.f;
+  const float gl = 0.5f * (u[0] + s.gw * u[2]);
+  const float lo = 0.5f * (u[1] + s.lw * u[2]);
+  c[0] = s.gscale * (u[3] + gl) / (float)s.global_batch;
+  c[1] = s.gscale * (u[4] + gl) / (float)s.global_batch;
+  const float nv = s.out8[7];
+  c[2] = (u[5] + lo) / nv;
+  c[3] = (u[6] + lo) / nv;
+}
+#endif
+
 // Programmatic dependent launch (griddepcontrol): a kernel launched with cfa_launch_pdl may START while its predecessor in the
 // stream is still running -- once every CTA of the predecessor has executed pdl_launch_dependents() (or exited) -- and must
 // call pdl_wait() before it touches anything the predecessor writes: the wait returns when the predecessor grid has

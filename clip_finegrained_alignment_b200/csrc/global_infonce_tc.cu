@@ -76,12 +76,14 @@ struct GtParams {
   float* part_m; float* part_l; float* diag;
   // backward
   const float* lse_loc; const float* lse_all; const float* coef; float* dpart;
+  CoefSrc cs;                           // cs.on: coefficients from the upstream-gradient pointers (one-call entry points)
   int dsplit;                           // backward: the D / 64 output blocks are divided over this many CTAs (grid z = 2 dsplit)
   int dpart_atomic;                     // != 0: dpart is ONE zeroed [2][B][D] accumulator, column tiles add into it (red.global)
   int lse_rank_rows, lse_rank_stride;   // > 0: lse_all is the raw all-gather of per-rank [lse_a | lse_b | 2 sums] packs
   volatile int* dbg;      // optional host-mapped progress markers (cfa_debug_set_marker_buffer), [cta][16 warps]
 };
 static int* g_gt_dbg = nullptr;
+thread_local const CoefSrc* g_coef_src = nullptr;      // set by the one-call entry points around their backward (sparc_paths.h)
 #define GT_MARK(v) do { if (p.dbg && lane == 0) { p.dbg[((((blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 16 + warp) * 32) + (v)] = (int)(clock64() - gt_t0); } } while (0)
 
 
@@ -299,7 +301,14 @@ gt_bwd_kernel(const __grid_constant__ CUtensorMap tmLoc, const __grid_constant__
   } else {
     const int q = warp & 3, h = (warp - 2) >> 2, row = 32 * q + lane, grow = row0 + row;
     const uint32_t trow = tmem + ((uint32_t)(32 * q) << 16);
-    const float c_self = p.coef[dir], c_other = p.coef[1 - dir];
+    float c_self, c_other;
+    if (p.cs.on) {
+      float c4[4];
+      coef_from_src(p.cs, c4);
+      c_self = c4[dir]; c_other = c4[1 - dir];
+    } else {
+      c_self = p.coef[dir]; c_other = p.coef[1 - dir];
+    }
     const float lse_self = (grow < p.B) ? p.lse_loc[(size_t)dir * p.B + grow] : 0.f;
     const float* lse_other = p.lse_all + (p.lse_rank_rows ? (size_t)(1 - dir) * p.lse_rank_rows : (size_t)(1 - dir) * p.Bg);
     if (h == 0) {
@@ -467,6 +476,7 @@ int global_tc_bwd(int B, int Bg, int D, int col_offset, float scale, const float
   GtParams p{};
   p.B = B; p.Bg = Bg; p.D = D; p.col_offset = col_offset; p.scale = scale;
   p.lse_loc = lse_loc2; p.lse_all = lse_all2; p.coef = coef2; p.dpart = h.scratch; p.dbg = g_gt_dbg;
+  if (g_coef_src) p.cs = *g_coef_src;
   p.dpart_atomic = h.nct > 2;
   if (p.dpart_atomic) CFA_CUDA_TRY(cudaMemsetAsync(h.scratch, 0, (size_t)2 * B * D * sizeof(float), st));
   p.lse_rank_rows = gathered_ranks > 1 ? B : 0; p.lse_rank_stride = gathered_ranks > 1 ? 2 * B + 2 : 0;

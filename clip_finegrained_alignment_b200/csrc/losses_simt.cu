@@ -548,16 +548,14 @@ struct Grad7Ptrs { const float* g[7]; };
 // same as sparc_coef_kernel, the 7 upstream gradients arriving as separate 0-dim tensors (NULL = not used)
 __global__ void sparc_coef_ptrs_kernel(Grad7Ptrs gp, float gw, float lw, int global_batch, const float* out8, float* coef8,
                                        float gscale) {
-  float u[7];
-  for (int k = 0; k < 7; ++k) u[k] = gp.g[k] ? *gp.g[k] : 0.f;
-  const float gl = 0.5f * (u[0] + gw * u[2]);
-  const float lo = 0.5f * (u[1] + lw * u[2]);
   // gscale: world size when the caller's gradients are averaged over ranks afterwards (DDP), see cfa_sparc_loss_gathered_bwd_ex
-  const float cvl = gscale * (u[3] + gl) / (float)global_batch, clv = gscale * (u[4] + gl) / (float)global_batch;
-  coef8[0] = cvl; coef8[1] = clv;
-  coef8[2] = (u[5] + lo) / out8[7];
-  coef8[3] = (u[6] + lo) / out8[7];
-  coef8[4] = clv; coef8[5] = cvl; coef8[6] = 0.f; coef8[7] = 0.f;
+  CoefSrc s{{gp.g[0], gp.g[1], gp.g[2], gp.g[3], gp.g[4], gp.g[5], gp.g[6]}, out8, gw, lw, gscale, global_batch, 1};
+  float c[4];
+  coef_from_src(s, c);
+  coef8[0] = c[0]; coef8[1] = c[1];
+  coef8[2] = c[2];
+  coef8[3] = c[3];
+  coef8[4] = c[1]; coef8[5] = c[0]; coef8[6] = 0.f; coef8[7] = 0.f;
 }
 
 }  // namespace cfa

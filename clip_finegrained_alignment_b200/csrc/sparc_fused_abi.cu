@@ -88,10 +88,21 @@ extern "C" int cfa_sparc_loss_bwd(const void* v, const void* l, const uint8_t* m
   const LossWs w = loss_ws_layout(B, P, T, D, dtype, path);
   if (workspace_bytes < w.total * sizeof(float)) return CFA_ERR_WORKSPACE;
   float* f = (float*)workspace;
-  int rc = cfa_sparc_coef_ptrs(g_global, g_local, g_total, g_vl, g_lv, g_vl_local, g_lv_local, gw, lw, B, f + w.out8, f + w.coef,
-                               stream);
-  if (rc != CFA_OK) return rc;
   const int gpath = (dtype == CFA_DTYPE_F32 || path == 1) ? 1 : 0;
+  // both consumers on tensor cores (gt_bwd_kernel, sparc_bwd3_kernel): they evaluate the upstream-gradient fan-in themselves
+  // and no coefficient kernel is launched; otherwise cfa_sparc_coef_ptrs fills the coefficient array as before
+  const bool inline_coef = w.saved && cfa_global_infonce_path(B, B, D, gpath) == 2 && cfa_sparc_bwd_path(P, T, D, dtype, path) == 2 &&
+                           cfa::sparc_gen3_enabled(P, T, D, dtype);
+  const cfa::CoefSrc cs{{g_global, g_local, g_total, g_vl, g_lv, g_vl_local, g_lv_local}, f + w.out8, gw, lw, 1.f, B, 1};
+  int rc = CFA_OK;
+  if (!inline_coef) {
+    rc = cfa_sparc_coef_ptrs(g_global, g_local, g_total, g_vl, g_lv, g_vl_local, g_lv_local, gw, lw, B, f + w.out8, f + w.coef, stream);
+    if (rc != CFA_OK) return rc;
+  }
+  struct CoefScope {                                   // cleared on every exit path
+    explicit CoefScope(const cfa::CoefSrc* p) { cfa::g_coef_src = p; }
+    ~CoefScope() { cfa::g_coef_src = nullptr; }
+  } coef_scope(inline_coef ? &cs : nullptr);
   const float* a = f + w.pooled;
   const float* b = a + (size_t)B * D;
   float* da = f + w.dab;

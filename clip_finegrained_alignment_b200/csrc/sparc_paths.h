@@ -53,6 +53,9 @@ int sparc_bwd3_launch(const void* v, const void* l, const uint8_t* mask, int B, 
 // backward may start under it (programmatic dependent launch) and wait late.  Everywhere else the wait is the kernel's
 // first instruction.
 extern thread_local bool g_sparc_bwd_pdl_late;
+// Non-null while a one-call entry point runs its backward: gt_bwd_kernel and sparc_bwd3_kernel then evaluate the upstream-
+// gradient fan-in themselves (CoefSrc, common.cuh) and no coefficient kernel is launched.
+extern thread_local const CoefSrc* g_coef_src;
 
 // cfa_global_infonce_fwd with the gathered rows read through a peer table (global_infonce.cu)
 int global_infonce_fwd_peers(const float* a_loc, const float* b_loc, const float* a_all, const float* b_all, int B, int Bg,

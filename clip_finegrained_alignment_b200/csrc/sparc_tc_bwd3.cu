@@ -97,6 +97,7 @@ struct Bwd3Params {
   const float* stats;       // [B][T][4] min, 1/range, sigma, arg-min patch
   const float* dpool_v;
   const float* dpool_l;
+  CoefSrc cs;               // cs.on: coefficients from the upstream-gradient pointers instead of `coef`
   int pdl_late;             // != 0: griddepcontrol.wait right before the first read of dpool_*, else at kernel start
   const bf16* v;
   const bf16* l;
@@ -375,7 +376,14 @@ sparc_bwd3_kernel(const __grid_constant__ CUtensorMap tmV0, const __grid_constan
     const int ew = warp - 2, q = warp & 3, grp = ew >> 2;
     const uint32_t tq = tmem + ((uint32_t)(32 * q) << 16);
     const int tid = ew * 32 + lane;
-    const float c_r = p.coef[0], c_c = p.coef[1];
+    float c_r, c_c;
+    if (p.cs.on) {
+      float c4[4];
+      coef_from_src(p.cs, c4);
+      c_r = c4[2]; c_c = c4[3];
+    } else {
+      c_r = p.coef[0]; c_c = p.coef[1];
+    }
     long long* pf = (p.prof && tid == 0) ? p.prof + (size_t)b * 32 + 16 : nullptr;
     int pi = 0;
     const bool pwarp = p.prof != nullptr && ew == 0;    // warp-uniform: the other 15 warps skip a stamp with one branch
@@ -798,7 +806,7 @@ int sparc_bwd3_launch(const void* v, const void* l, const uint8_t* mask, int B, 
   if ((rc = make_tmap_bf16_3d(&tmL, l, D, T, B, 64, L.NT)) != CFA_OK) return rc;
   if ((rc = make_tmap_bf16_3d(&tmG, g_split, D, T, 2 * (uint64_t)B, 64, L.NT)) != CFA_OK) return rc;
   Bwd3Params prm{prof, P, T, D, thr, scale, mask, row_inv_norm, row_inv_norm + (size_t)B * P, lse_row, lse_col, coef,
-                 tt_logits, g_inv_norm, stats, dpv, dpl, pdl_late ? 1 : 0, (const bf16*)v, (const bf16*)l, (bf16*)dv, (bf16*)dl};
+                 tt_logits, g_inv_norm, stats, dpv, dpl, g_coef_src ? *g_coef_src : CoefSrc{}, pdl_late ? 1 : 0, (const bf16*)v, (const bf16*)l, (bf16*)dv, (bf16*)dl};
   const size_t smem = L.total + 1024;
 #define CFA_B3_LAUNCH(NT_, NP_, D_, H_)                                                                                     \
   do {                                                                                                                      \
