@@ -191,7 +191,11 @@ int cfa_sparc_max_patches(int T, int backward);
  * cfa_global_infonce_bwd + cfa_sparc_bwd, over one 128-byte-aligned workspace of cfa_sparc_loss_workspace_bytes() whose
  * layout is private to the library.  After the forward the first 8 floats of the workspace hold out[0..7] (see
  * cfa_sparc_finalize); the backward must be given the same, untouched workspace.  g_*: DEVICE scalars, the upstream
- * gradients of the 7 outputs (NULL = unused).  Saves ~4 host calls and ~4 allocations per step.
+ * gradients of the 7 outputs (NULL = unused); they must stay valid until the backward's kernels have run (on the
+ * tensor-core chain the kernels read them directly and no coefficient kernel is launched).  Saves ~4 host calls and ~4
+ * allocations per step.  The backward's kernels are chained with programmatic dependent launch (the fine-grained
+ * backward starts under the global InfoNCE backward and waits for it right before its output pass); to anything
+ * enqueued after the call the stream behaves as usual.  CFA_PDL=0 disables the overlap.
  */
 size_t cfa_sparc_loss_workspace_bytes(int B, int P, int T, int D, int dtype, int path);
 int cfa_sparc_loss_fwd(const void* v, const void* l, const uint8_t* mask, int B, int P, int T, int D, int dtype, float thr,
