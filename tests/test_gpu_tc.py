@@ -105,6 +105,9 @@ def test_sparc_tc_vs_oracle(B, P, T, D, s):
     (2, 130, 33, 640, 1.0, torch.float16),       # D = 5 x 128, second patch block almost empty
 ])
 def test_sparc_gen3_edge_shapes_vs_oracle(B, P, T, D, s, dtype):
+    import os
+    if os.environ.get("CFA_SPARC_GEN") == "2":
+        pytest.skip("third-generation kernels switched off (A/B aid)")
     from clip_finegrained_alignment_b200 import _lib
     code = _lib.DTYPE_CODE[dtype]
     assert _lib.lib.cfa_sparc_path(P, T, D, code, 0) == 2
@@ -155,6 +158,9 @@ def test_sparc_fp16_on_tensor_cores(B, P, T, D, s, mag, up):
     """fp16 embeddings (torch.autocast's default; finetuner.py:51,120-134 with GradScaler) on the tcgen05 path: tcgen05
     kind::f16 takes no mixed fp16 x bf16 operand pair, so the on-chip operands are fp16 hi|lo, kept in range by two
     per-sample powers of two (csrc/sparc_tc_bwd3.cu).  fp64 oracle on the fp16-representable inputs, 1e-3."""
+    import os
+    if os.environ.get("CFA_SPARC_GEN") == "2":
+        pytest.skip("fp16 needs the third-generation kernels (switched off: A/B aid)")
     from clip_finegrained_alignment_b200 import SPARCLoss, _lib
     g = torch.Generator().manual_seed(B * 31 + P)
     v0 = (torch.randn(B, P, D, generator=g) * mag).to(torch.float16)
