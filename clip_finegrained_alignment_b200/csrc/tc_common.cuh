@@ -403,10 +403,16 @@ static inline int make_tmap_bf16_3d(CUtensorMap* m, const void* base, uint64_t d
   cuuint64_t strides[2] = {d0 * 2, (plane_stride ? plane_stride : d0 * d1) * 2};
   cuuint32_t box[3] = {box0, box1, 1};
   cuuint32_t estr[3] = {1, 1, 1};
-  CUresult r = enc(m, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, box0 == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
-                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = CUDA_SUCCESS;
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    r = enc(m, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, box0 == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+            CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    // The encoder is a DRIVER entry point: on a thread without a current context (a backward whose first CUDA call is this
+    // one, on autograd's worker thread) it reports CUDA_ERROR_INVALID_CONTEXT -> bind the primary context and retry.
+    if (r != CUDA_ERROR_INVALID_CONTEXT) break;
+    cudaFree(nullptr);
+  }
   return r == CUDA_SUCCESS ? CFA_OK : CFA_ERR_BAD_ARG;
 }
 
